@@ -1,0 +1,132 @@
+/*
+ * perc_abi.h -- C-ABI of libperc_b200.so, the B200 (sm_100a) replacement for the
+ * percolation-realization hot path of IsaiahSteinke/Percolation.
+ *
+ * The reference has no FFI: it is 20 monolithic Fortran-77 PROGRAMs whose hot path is
+ * inline code blocks.  Each entry point below replaces one of those blocks (cited as
+ * file:line into the reference's Fortran/ tree, Sq = Square, Tri = Triangular) so the
+ * Fortran drivers keep their structure and call this library through ISO_C_BINDING
+ * (fortran/perc_iface.f90; binding stub in INTEGRATION.md).
+ *
+ * Conventions (Fortran-callable, bind(C) without VALUE):
+ *   - every scalar is passed BY REFERENCE; INTEGER <-> int32_t, DOUBLE PRECISION <-> double;
+ *   - sites are 1-based, row-major rn = y*m + x (x = 1..m fastest; row y = 0 is the grounded
+ *     bottom edge, y = n-1 the top edge at Va)                      Sq/site.f:371-469
+ *   - 2-D arrays are column-major: border(nb,2) = nb "lo" ends followed by nb "hi" ends
+ *     Sq/bond.f:40,112-129
+ *   - bond row numbering is the reference's own (do i=1,t-1; do j=1,scn; if nn(j)>i)
+ *   - labels are CANONICAL: label = smallest member id (site rn; a bond whose two ends are
+ *     both unoccupied in a mixed problem is its own cluster, label t + row).  The reference's
+ *     labels are creation counters; its partition and c() sizes are identical.
+ *   - caller owns every host array; the library owns device memory behind the handle;
+ *   - return value: 0 ok; < 0 bad argument (PERC_E_*); > 0 a cudaError_t code.  Never aborts
+ *     (the reference's convention is `pause`, Sq/bondc.f:737,777).
+ *   - one handle per host thread / GPU; calls on a handle are serialised by the caller.
+ * There is no CPU fallback: without a CUDA device perc_create fails with the CUDA error.
+ */
+#ifndef PERC_ABI_H
+#define PERC_ABI_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PERC_SQUARE      1   /* lattype, MATLAB/ConductCalc.m:30 */
+#define PERC_TRIANGULAR  2
+#define PERC_SITE        1   /* perctype, MATLAB/ConductCalc.m:29 */
+#define PERC_BOND        2
+#define PERC_MIXED       3
+
+#define PERC_E_ARG       (-1)  /* bad argument                                  */
+#define PERC_E_ODD_M     (-2)  /* triangular lattice needs even m  */
+#define PERC_E_HANDLE    (-3)  /* unknown handle                                */
+#define PERC_E_STATE     (-4)  /* call order (e.g. conduct before label)        */
+#define PERC_E_SIZE      (-5)  /* lattice too large for 32-bit labels           */
+#define PERC_E_NOSPAN    (-6)  /* requested cluster does not span               */
+
+/* ---- geometry (host-only index arithmetic; no device needed) ------------------------------ */
+/* nb formulas Sq/site.f:89-93, Tri/site.f:91-95 */
+int32_t perc_geom_nb(const int32_t *lattice, const int32_t *m, const int32_t *n, const int32_t *pbc, int32_t *nb);
+/* bond list b(nb,2) in the reference's numbering, Sq/bond.f:112-129 (= bondlist.txt, Sq/site.f:106-124) */
+int32_t perc_geom_bondlist(const int32_t *lattice, const int32_t *m, const int32_t *n, const int32_t *pbc, int32_t *b);
+/* neighbours of site rn in nearestn order, 0 = none; nn has 6 entries. Sq/site.f:371-469, Tri/site.f:373-558 */
+int32_t perc_geom_nearestn(const int32_t *lattice, const int32_t *m, const int32_t *n, const int32_t *pbc,
+                           const int32_t *rn, int32_t *nn);
+
+/* ---- handle: the parameter block m, n, pbc, lattice (Sq/site.f:51-67) --------------------- */
+int32_t perc_create(int64_t *h, const int32_t *lattice, const int32_t *m, const int32_t *n,
+                    const int32_t *pbc, const int32_t *device);
+int32_t perc_destroy(const int64_t *h);
+int32_t perc_sync(const int64_t *h);
+
+/* ---- occupancy inputs ------------------------------------------------------------------------ */
+/* order(t): the shuffled site order of Sq/site.f:131-147; sites order(1..k) get occupied (:164-176).
+ * Uploads the order once (as a rank table) -- later calls may re-threshold with perc_set_fill. */
+int32_t perc_set_site_order(const int64_t *h, const int32_t *order);
+/* border(nb,2): the shuffled bond order of Sq/bond.f:137-150 */
+int32_t perc_set_bond_order(const int64_t *h, const int32_t *border);
+/* fill counts ks = int(ps*t), kb = int(pb*nb) (Sq/site.f:164, Sq/bond.f:167); -1 keeps the current one */
+int32_t perc_set_fill(const int64_t *h, const int32_t *ks, const int32_t *kb);
+/* direct occupancy flags (0/1 bytes): socc(t) by site, bocc(nb) by reference bond row; either may be NULL */
+int32_t perc_set_occupancy(const int64_t *h, const uint8_t *socc, const uint8_t *bocc);
+/* B200 occupancy generator replacing permute.f + rand (Fortran/permute.f:39-44): counter-based
+ * Philox-4x32-10 keys per element, EXACTLY ks (kb) smallest keys occupied (ties by element id).
+ * stream: realization index.  -1 for ks / kb skips that element type. */
+int32_t perc_generate(const int64_t *h, const int64_t *seed, const int64_t *stream,
+                      const int32_t *ks, const int32_t *kb);
+/* read back the occupancy in reference layout: socc(t) bytes, bocc(nb) bytes (either may be NULL) */
+int32_t perc_get_occupancy(const int64_t *h, uint8_t *socc, uint8_t *bocc);
+
+/* ---- labeling + sizes + spanning (Sq/site.f:162-344, bond.f:165-432, sitebond.f:187-458) ---- */
+/* kind = PERC_SITE | PERC_BOND | PERC_MIXED.  Results stay on the device until fetched. */
+int32_t perc_label(const int64_t *h, const int32_t *kind);
+/* summary: ncl = number of clusters, maxcs / maxcn = largest cluster size and its (canonical) label
+ * (Sq/site.f:278-287), nspan = number of spanning clusters */
+int32_t perc_summary(const int64_t *h, int64_t *ncl, int32_t *maxcs, int32_t *maxcn, int32_t *nspan);
+int32_t perc_get_site_labels(const int64_t *h, int32_t *s);           /* s(t)            */
+int32_t perc_get_bond_labels(const int64_t *h, int32_t *b3);          /* b(nb,3) column 3 */
+int32_t perc_get_sizes(const int64_t *h, int32_t *c);                 /* c(t): c(label) = size, else 0 */
+/* spanning clusters, ascending canonical id; ids[0] is the default choice for perc_conduct.
+ * (reference: lowest historical label that spans, Sq/site.f:309-344 -- SURVEY F7) */
+int32_t perc_span(const int64_t *h, const int32_t *max_ids, int32_t *nspan, int32_t *ids, int32_t *sizes);
+/* exact cluster-size histogram: hist(s) = number of clusters of size s for s = 1..nbins-1,
+ * hist(nbins) = clusters of size >= nbins.  (multiset of non-zero c()) */
+int32_t perc_hist(const int64_t *h, const int32_t *nbins, int64_t *hist);
+
+/* reference-shaped one-call wrappers (upload order, label, download) */
+int32_t perc_site(const int64_t *h, const int32_t *order, const int32_t *k,
+                  int32_t *s, int32_t *c, int32_t *maxcs, int32_t *perccln, int32_t *perccls);
+int32_t perc_bond(const int64_t *h, const int32_t *border, const int32_t *k,
+                  int32_t *b3, int32_t *c, int32_t *maxcs, int32_t *perccln, int32_t *perccls);
+int32_t perc_sitebond(const int64_t *h, const int32_t *sorder, const int32_t *ks,
+                      const int32_t *border, const int32_t *kb,
+                      int32_t *s, int32_t *b3, int32_t *c, int32_t *maxcs, int32_t *perccln, int32_t *perccls);
+
+/* first-spanning search of the *_perc drivers (Sq/site_perc.f:133-254, bond_perc.f, sb_perc.f,
+ * bs_perc.f): smallest fill count of `which` (PERC_SITE or PERC_BOND elements) at which a spanning
+ * cluster exists, the other count held fixed; kstar = 0 if it never spans.  f = real(kstar)/real(N). */
+int32_t perc_first_span(const int64_t *h, const int32_t *kind, const int32_t *which,
+                        int32_t *kstar, float *f, int32_t *maxcs, int32_t *perccls);
+
+/* ---- Kirchhoff conductance (Sq/bondc.f:465-595 + linbcg :750-838) ----------------------------- */
+/* cluster_id: canonical id of a spanning cluster (0 = ids[0]).  Reference defaults: Va = g0 = 1
+ * (:85-86), gleak = 1e-12 (:487), tol = 1e-8, itmax = 2500 (:545), read_thresh = 1e-10 (:576). */
+int32_t perc_conduct(const int64_t *h, const int32_t *cluster_id, const double *Va, const double *g0,
+                     const double *gleak, const double *tol, const int32_t *itmax, const double *read_thresh,
+                     double *Gtop, double *Gbot, int32_t *iter, double *err);
+int32_t perc_get_voltage(const int64_t *h, double *Vint);             /* Vint(t-2m), Sq/bondc.f:545 */
+
+/* ---- instrumentation ---------------------------------------------------------------------------- */
+/* kernels launched by this handle since creation (bench.py's gpu_launches) */
+int32_t perc_launch_count(const int64_t *h, int64_t *count);
+/* device time (ms, CUDA events on the handle's stream) of the last call's phases:
+ * 0 mask build, 1 CCL local, 2 CCL merge, 3 CCL flatten+sizes, 4 spanning, 5 PCG total,
+ * 6 PCG SpMV kernel avg, 7 PCG update kernel avg */
+int32_t perc_phase_ms(const int64_t *h, const int32_t *nphase, float *ms);
+/* raw stream handle (cudaStream_t) so a host can order its own work against the library's */
+int32_t perc_stream(const int64_t *h, uint64_t *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

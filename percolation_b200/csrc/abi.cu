@@ -1,0 +1,500 @@
+// abi.cu -- extern "C" entry points of libperc_b200.so (see include/perc_abi.h).
+// Thin argument checking + dispatch; all compute is in the CUDA kernels of the sibling files.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include "../../include/perc_abi.h"
+#include "context.h"
+
+namespace perc {
+
+static std::mutex g_mu;
+static std::unordered_map<int64_t, Ctx*> g_ctx;
+static int64_t g_next = 1;
+
+static Ctx* lookup(const int64_t* h)
+{
+    if (!h) return nullptr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_ctx.find(*h);
+    return it == g_ctx.end() ? nullptr : it->second;
+}
+
+void* ctx_dev_stage(Ctx* c, size_t bytes)
+{
+    if (bytes > c->d_stage_bytes) {
+        if (c->d_stage) { cudaStreamSynchronize(c->stream); cudaFree(c->d_stage); c->d_stage = nullptr; c->d_stage_bytes = 0; }
+        size_t want = bytes + (bytes >> 3) + 256;
+        if (cudaMalloc(&c->d_stage, want) != cudaSuccess) return nullptr;
+        c->d_stage_bytes = want;
+    }
+    return c->d_stage;
+}
+
+void* ctx_host_stage(Ctx* c, size_t bytes)
+{
+    if (bytes > c->h_stage_bytes) {
+        if (c->h_stage) { cudaFreeHost(c->h_stage); c->h_stage = nullptr; c->h_stage_bytes = 0; }
+        if (cudaMallocHost(&c->h_stage, bytes) != cudaSuccess) return nullptr;
+        c->h_stage_bytes = bytes;
+    }
+    return c->h_stage;
+}
+
+int ctx_alloc(Ctx* c)
+{
+    const int64_t t = c->g.t;
+    PERC_CUDA(cudaSetDevice(c->device));
+    PERC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PERC_CUDA(cudaMalloc(&c->srank, sizeof(int32_t) * t));
+    PERC_CUDA(cudaMalloc(&c->brank, sizeof(int32_t) * t * c->g.ndir));
+    PERC_CUDA(cudaMalloc(&c->mask, t));
+    PERC_CUDA(cudaMalloc(&c->label, sizeof(int32_t) * t));
+    PERC_CUDA(cudaMalloc(&c->size, sizeof(int32_t) * t));
+    PERC_CUDA(cudaMalloc(&c->span_mark, sizeof(int32_t) * t));
+    PERC_CUDA(cudaMalloc(&c->span_ids, sizeof(int32_t) * MAX_SPAN));
+    PERC_CUDA(cudaMalloc(&c->d_sum, sizeof(Summary)));
+    PERC_CUDA(cudaMalloc(&c->d_pcg, sizeof(PcgState)));
+    PERC_CUDA(cudaMallocHost(&c->h_pcg, sizeof(PcgState)));
+    PERC_CUDA(cudaMalloc(&c->d_hist, sizeof(unsigned long long) * (4096 + 8)));
+    c->cand_cap = 8192;
+    PERC_CUDA(cudaMalloc(&c->d_cand, sizeof(unsigned long long) * 2 * c->cand_cap));
+    PERC_CUDA(cudaMemsetAsync(c->span_mark, 0, sizeof(int32_t) * t, c->stream));
+    PERC_CUDA(cudaMemsetAsync(c->srank, 0x7f, sizeof(int32_t) * t, c->stream));
+    PERC_CUDA(cudaMemsetAsync(c->brank, 0x7f, sizeof(int32_t) * t * c->g.ndir, c->stream));
+    for (auto& e : c->ev) PERC_CUDA(cudaEventCreate(&e));
+    PERC_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int ensure_pcg(Ctx* c)
+{
+    if (c->vx) return 0;
+    const int64_t t = c->g.t;
+    PERC_CUDA(cudaMalloc(&c->cfull, t));
+    PERC_CUDA(cudaMalloc(&c->vx, sizeof(double) * t));
+    PERC_CUDA(cudaMalloc(&c->vr, sizeof(double) * t));
+    PERC_CUDA(cudaMalloc(&c->vp, sizeof(double) * t));
+    PERC_CUDA(cudaMalloc(&c->vq, sizeof(double) * t));
+    return 0;
+}
+
+void ctx_free(Ctx* c)
+{
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void* ptrs[] = {c->srank, c->brank, c->mask, c->label, c->size, c->span_mark, c->span_ids, c->d_sum, c->d_pcg,
+                    c->d_hist, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vq, c->partial, c->d_stage};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (c->h_pcg) cudaFreeHost(c->h_pcg);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+}
+
+static int check_geom(int lattice, int m, int n, int pbc)
+{
+    if (lattice != LAT_SQUARE && lattice != LAT_TRIANGULAR) return PERC_E_ARG;
+    if (m < 2 || n < 2 || (pbc != 0 && pbc != 1)) return PERC_E_ARG;
+    if (pbc && m < 3) return PERC_E_ARG;
+    if (lattice == LAT_TRIANGULAR && (m & 1)) return PERC_E_ODD_M;
+    if ((int64_t)m * n > 0x7ffffff0LL / 4) return PERC_E_SIZE;     // int32 labels and bond rows
+    return 0;
+}
+
+static int set_fill(Ctx* c, int ks, int kb)
+{
+    if (ks >= 0) {
+        if (ks > c->g.t) return PERC_E_ARG;
+        if (c->site_src == SRC_PHILOX) { int rc = occ_generate(c, c->seed, c->stream_id, ks, -1); if (rc) return rc; }
+        c->ks = ks;
+    }
+    if (kb >= 0) {
+        if (kb > c->g.nb) return PERC_E_ARG;
+        if (c->bond_src == SRC_PHILOX) { int rc = occ_generate(c, c->seed, c->stream_id, -1, kb); if (rc) return rc; }
+        c->kb = kb;
+    }
+    c->labeled = false;
+    return 0;
+}
+
+static int download(Ctx* c, void* dst, const void* src, size_t bytes)
+{
+    PERC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    PERC_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+}  // namespace perc
+
+using namespace perc;
+
+#define GET_CTX(h)                                   \
+    Ctx* c = lookup(h);                              \
+    if (!c) return PERC_E_HANDLE;                    \
+    { cudaError_t e__ = cudaSetDevice(c->device); if (e__ != cudaSuccess) return (int)e__; }
+
+extern "C" {
+
+int32_t perc_geom_nb(const int32_t* lattice, const int32_t* m, const int32_t* n, const int32_t* pbc, int32_t* nb)
+{
+    if (!lattice || !m || !n || !pbc || !nb) return PERC_E_ARG;
+    int rc = check_geom(*lattice, *m, *n, *pbc);
+    if (rc) return rc;
+    *nb = (int32_t)make_geom(*lattice, *m, *n, *pbc).nb;
+    return 0;
+}
+
+int32_t perc_geom_bondlist(const int32_t* lattice, const int32_t* m, const int32_t* n, const int32_t* pbc, int32_t* b)
+{
+    if (!lattice || !m || !n || !pbc || !b) return PERC_E_ARG;
+    int rc = check_geom(*lattice, *m, *n, *pbc);
+    if (rc) return rc;
+    Geom g = make_geom(*lattice, *m, *n, *pbc);
+    for (int64_t r = 0; r < g.nb; ++r) {
+        int64_t a; int dir;
+        ref_row_to_owner(g, r, &a, &dir);
+        int64_t o = bond_other_end(g, (int)(a % g.m), (int)(a / g.m), dir);
+        int64_t lo = a < o ? a : o, hi = a < o ? o : a;
+        b[r] = (int32_t)lo + 1;
+        b[g.nb + r] = (int32_t)hi + 1;
+    }
+    return 0;
+}
+
+int32_t perc_geom_nearestn(const int32_t* lattice, const int32_t* m, const int32_t* n, const int32_t* pbc,
+                           const int32_t* rn, int32_t* nn)
+{
+    if (!lattice || !m || !n || !pbc || !rn || !nn) return PERC_E_ARG;
+    int rc = check_geom(*lattice, *m, *n, *pbc);
+    if (rc) return rc;
+    Geom g = make_geom(*lattice, *m, *n, *pbc);
+    if (*rn < 1 || *rn > g.t) return PERC_E_ARG;
+    int64_t i = *rn - 1;
+    int x = (int)(i % g.m), y = (int)(i / g.m);
+    unsigned ex = neighbour_bits(g, x, y);
+    int xl = x > 0 ? x - 1 : g.m - 1, xr = x + 1 < g.m ? x + 1 : 0;
+    int64_t row = i - x;
+    for (int k = 0; k < 6; ++k) nn[k] = 0;
+    // nearestn order: ascending site number for in-lattice neighbours, periodic wraps appended last
+    int64_t cand[8]; int cnt = 0;
+    struct { unsigned bit; int64_t j; bool wrap; } dirs[8] = {
+        {NB_SW, row - g.m + xl, false}, {NB_S, i - g.m, false}, {NB_SE, row - g.m + xr, x + 1 == g.m},
+        {NB_W, row + xl, x == 0}, {NB_E, row + xr, x + 1 == g.m},
+        {NB_NW, row + g.m + xl, x == 0}, {NB_N, i + g.m, false}, {NB_NE, row + g.m + xr, false}};
+    for (int pass = 0; pass < 2; ++pass)
+        for (int k = 0; k < 8; ++k)
+            if ((ex & dirs[k].bit) && dirs[k].wrap == (pass == 1)) cand[cnt++] = dirs[k].j;
+    // wrapped neighbours are listed in ascending site number too
+    for (int k = 0; k < cnt && k < 6; ++k) nn[k] = (int32_t)cand[k] + 1;
+    return 0;
+}
+
+int32_t perc_create(int64_t* h, const int32_t* lattice, const int32_t* m, const int32_t* n,
+                    const int32_t* pbc, const int32_t* device)
+{
+    if (!h || !lattice || !m || !n || !pbc || !device) return PERC_E_ARG;
+    int rc = check_geom(*lattice, *m, *n, *pbc);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return (int)e;                 // no CPU fallback: fail loudly
+    if (*device < 0 || *device >= ndev) return PERC_E_ARG;
+    Ctx* c = new Ctx();
+    c->g = make_geom(*lattice, *m, *n, *pbc);
+    c->device = *device;
+    rc = ctx_alloc(c);
+    if (rc) { ctx_free(c); delete c; return rc; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    *h = g_next++;
+    g_ctx[*h] = c;
+    return 0;
+}
+
+int32_t perc_destroy(const int64_t* h)
+{
+    if (!h) return PERC_E_ARG;
+    Ctx* c = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_ctx.find(*h);
+        if (it == g_ctx.end()) return PERC_E_HANDLE;
+        c = it->second;
+        g_ctx.erase(it);
+    }
+    ctx_free(c);
+    delete c;
+    return 0;
+}
+
+int32_t perc_sync(const int64_t* h)
+{
+    GET_CTX(h);
+    return (int)cudaStreamSynchronize(c->stream);
+}
+
+int32_t perc_set_site_order(const int64_t* h, const int32_t* order)
+{
+    GET_CTX(h);
+    if (!order) return PERC_E_ARG;
+    return occ_upload_site_order(c, order);
+}
+
+int32_t perc_set_bond_order(const int64_t* h, const int32_t* border)
+{
+    GET_CTX(h);
+    if (!border) return PERC_E_ARG;
+    return occ_upload_bond_order(c, border);
+}
+
+int32_t perc_set_fill(const int64_t* h, const int32_t* ks, const int32_t* kb)
+{
+    GET_CTX(h);
+    if (!ks || !kb) return PERC_E_ARG;
+    return set_fill(c, *ks, *kb);
+}
+
+int32_t perc_set_occupancy(const int64_t* h, const uint8_t* socc, const uint8_t* bocc)
+{
+    GET_CTX(h);
+    return occ_upload_flags(c, socc, bocc);
+}
+
+int32_t perc_generate(const int64_t* h, const int64_t* seed, const int64_t* stream, const int32_t* ks, const int32_t* kb)
+{
+    GET_CTX(h);
+    if (!seed || !stream || !ks || !kb) return PERC_E_ARG;
+    return occ_generate(c, (unsigned long long)*seed, (unsigned long long)*stream, *ks, *kb);
+}
+
+int32_t perc_get_occupancy(const int64_t* h, uint8_t* socc, uint8_t* bocc)
+{
+    GET_CTX(h);
+    return occ_export(c, socc, bocc);
+}
+
+int32_t perc_label(const int64_t* h, const int32_t* kind)
+{
+    GET_CTX(h);
+    if (!kind || *kind < KIND_SITE || *kind > KIND_MIXED) return PERC_E_ARG;
+    if ((*kind == KIND_SITE || *kind == KIND_MIXED) && c->site_src == SRC_NONE) return PERC_E_STATE;
+    if ((*kind == KIND_BOND || *kind == KIND_MIXED) && c->bond_src == SRC_NONE) return PERC_E_STATE;
+    return ccl_run(c, *kind);
+}
+
+int32_t perc_summary(const int64_t* h, int64_t* ncl, int32_t* maxcs, int32_t* maxcn, int32_t* nspan)
+{
+    GET_CTX(h);
+    if (!c->labeled) return PERC_E_STATE;
+    const Summary& s = c->h_sum;
+    int32_t ms = (int32_t)(s.maxpack >> 32);
+    int32_t mn = ms ? (int32_t)(0xffffffffu - (unsigned)(s.maxpack & 0xffffffffu)) : 0;
+    if (ms == 0 && s.nlone > 0) { ms = 1; mn = 0; }     // only lone bonds: size-1 clusters
+    if (ncl) *ncl = (int64_t)(s.ncl + s.nlone);
+    if (maxcs) *maxcs = ms;
+    if (maxcn) *maxcn = mn;
+    if (nspan) *nspan = s.nspan;
+    return 0;
+}
+
+int32_t perc_get_site_labels(const int64_t* h, int32_t* s)
+{
+    GET_CTX(h);
+    if (!c->labeled || !s) return PERC_E_STATE;
+    if (c->kind == KIND_BOND) { std::memset(s, 0, sizeof(int32_t) * c->g.t); return 0; }   // bond problem has no s()
+    return download(c, s, c->label, sizeof(int32_t) * c->g.t);
+}
+
+int32_t perc_get_bond_labels(const int64_t* h, int32_t* b3)
+{
+    GET_CTX(h);
+    if (!c->labeled || !b3) return PERC_E_STATE;
+    return ccl_export_bond_labels(c, b3);
+}
+
+int32_t perc_get_sizes(const int64_t* h, int32_t* cs)
+{
+    GET_CTX(h);
+    if (!c->labeled || !cs) return PERC_E_STATE;
+    return download(c, cs, c->size, sizeof(int32_t) * c->g.t);
+}
+
+int32_t perc_span(const int64_t* h, const int32_t* max_ids, int32_t* nspan, int32_t* ids, int32_t* sizes)
+{
+    GET_CTX(h);
+    if (!c->labeled || !max_ids || !nspan) return PERC_E_STATE;
+    *nspan = c->h_sum.nspan;
+    int k = (int)c->h_span_ids.size();
+    if (k > *max_ids) k = *max_ids;
+    for (int j = 0; j < k; ++j) { if (ids) ids[j] = c->h_span_ids[j]; if (sizes) sizes[j] = c->h_span_sizes[j]; }
+    return 0;
+}
+
+int32_t perc_hist(const int64_t* h, const int32_t* nbins, int64_t* hist)
+{
+    GET_CTX(h);
+    if (!c->labeled || !nbins || !hist) return PERC_E_STATE;
+    return ccl_hist(c, *nbins, hist);
+}
+
+static int finish_label(Ctx* c, int32_t* maxcs, int32_t* perccln, int32_t* perccls)
+{
+    const Summary& s = c->h_sum;
+    int32_t ms = (int32_t)(s.maxpack >> 32);
+    if (ms == 0 && s.nlone > 0) ms = 1;
+    if (maxcs) *maxcs = ms;
+    if (perccln) *perccln = c->h_span_ids.empty() ? 0 : c->h_span_ids[0];
+    if (perccls) *perccls = c->h_span_ids.empty() ? 0 : c->h_span_sizes[0];
+    return 0;
+}
+
+int32_t perc_site(const int64_t* h, const int32_t* order, const int32_t* k,
+                  int32_t* s, int32_t* cs, int32_t* maxcs, int32_t* perccln, int32_t* perccls)
+{
+    GET_CTX(h);
+    if (!order || !k) return PERC_E_ARG;
+    int rc = occ_upload_site_order(c, order);
+    if (rc) return rc;
+    rc = set_fill(c, *k, -1);
+    if (rc) return rc;
+    rc = ccl_run(c, KIND_SITE);
+    if (rc) return rc;
+    if (s) { rc = download(c, s, c->label, sizeof(int32_t) * c->g.t); if (rc) return rc; }
+    if (cs) { rc = download(c, cs, c->size, sizeof(int32_t) * c->g.t); if (rc) return rc; }
+    return finish_label(c, maxcs, perccln, perccls);
+}
+
+int32_t perc_bond(const int64_t* h, const int32_t* border, const int32_t* k,
+                  int32_t* b3, int32_t* cs, int32_t* maxcs, int32_t* perccln, int32_t* perccls)
+{
+    GET_CTX(h);
+    if (!border || !k) return PERC_E_ARG;
+    int rc = occ_upload_bond_order(c, border);
+    if (rc) return rc;
+    rc = set_fill(c, -1, *k);
+    if (rc) return rc;
+    rc = ccl_run(c, KIND_BOND);
+    if (rc) return rc;
+    if (b3) { rc = ccl_export_bond_labels(c, b3); if (rc) return rc; }
+    if (cs) { rc = download(c, cs, c->size, sizeof(int32_t) * c->g.t); if (rc) return rc; }
+    return finish_label(c, maxcs, perccln, perccls);
+}
+
+int32_t perc_sitebond(const int64_t* h, const int32_t* sorder, const int32_t* ks,
+                      const int32_t* border, const int32_t* kb,
+                      int32_t* s, int32_t* b3, int32_t* cs, int32_t* maxcs, int32_t* perccln, int32_t* perccls)
+{
+    GET_CTX(h);
+    if (!sorder || !ks || !border || !kb) return PERC_E_ARG;
+    int rc = occ_upload_site_order(c, sorder);
+    if (rc) return rc;
+    rc = occ_upload_bond_order(c, border);
+    if (rc) return rc;
+    rc = set_fill(c, *ks, *kb);
+    if (rc) return rc;
+    rc = ccl_run(c, KIND_MIXED);
+    if (rc) return rc;
+    if (s) { rc = download(c, s, c->label, sizeof(int32_t) * c->g.t); if (rc) return rc; }
+    if (b3) { rc = ccl_export_bond_labels(c, b3); if (rc) return rc; }
+    if (cs) { rc = download(c, cs, c->size, sizeof(int32_t) * c->g.t); if (rc) return rc; }
+    return finish_label(c, maxcs, perccln, perccls);
+}
+
+int32_t perc_first_span(const int64_t* h, const int32_t* kind, const int32_t* which,
+                        int32_t* kstar, float* f, int32_t* maxcs, int32_t* perccls)
+{
+    GET_CTX(h);
+    if (!kind || !which || !kstar) return PERC_E_ARG;
+    if (*kind < KIND_SITE || *kind > KIND_MIXED) return PERC_E_ARG;
+    if (*which != KIND_SITE && *which != KIND_BOND) return PERC_E_ARG;
+    if (*kind == KIND_SITE && *which != KIND_SITE) return PERC_E_ARG;
+    if (*kind == KIND_BOND && *which != KIND_BOND) return PERC_E_ARG;
+    const bool sites = *which == KIND_SITE;
+    int64_t N = sites ? c->g.t : c->g.nb;
+    auto probe = [&](int k, int* spans) -> int {
+        int rc = sites ? set_fill(c, k, -1) : set_fill(c, -1, k);
+        if (rc) return rc;
+        rc = ccl_run(c, *kind);
+        if (rc) return rc;
+        *spans = c->h_sum.nspan > 0;
+        return 0;
+    };
+    int spans = 0;
+    int rc = probe((int)N, &spans);
+    if (rc) return rc;
+    int lo = 0, hi = (int)N;            // invariant: lo does not span, hi spans
+    if (!spans) hi = 0;
+    else {
+        while (hi - lo > 1) {
+            int mid = lo + (hi - lo) / 2;
+            rc = probe(mid, &spans);
+            if (rc) return rc;
+            if (spans) hi = mid; else lo = mid;
+        }
+        rc = probe(hi, &spans);
+        if (rc) return rc;
+    }
+    *kstar = hi;
+    if (f) *f = (float)hi / (float)N;     // f = real(sf)/real(t), REAL*4 (Sq/site_perc.f:221)
+    return finish_label(c, maxcs, nullptr, perccls);
+}
+
+int32_t perc_conduct(const int64_t* h, const int32_t* cluster_id, const double* Va, const double* g0,
+                     const double* gleak, const double* tol, const int32_t* itmax, const double* read_thresh,
+                     double* Gtop, double* Gbot, int32_t* iter, double* err)
+{
+    GET_CTX(h);
+    if (!cluster_id || !Va || !g0 || !gleak || !tol || !itmax || !read_thresh || !Gtop || !Gbot || !iter || !err)
+        return PERC_E_ARG;
+    if (!c->labeled) return PERC_E_STATE;
+    if (c->g.n < 3 || *Va == 0.0 || *itmax < 0) return PERC_E_ARG;
+    int cid = *cluster_id;
+    if (cid == 0) {
+        if (c->h_span_ids.empty()) return PERC_E_NOSPAN;
+        cid = c->h_span_ids[0];
+    } else {
+        bool ok = false;
+        for (int v : c->h_span_ids) ok |= (v == cid);
+        if (!ok) return PERC_E_NOSPAN;
+    }
+    int rc = ensure_pcg(c);
+    if (rc) return rc;
+    int it = 0;
+    rc = pcg_solve(c, cid, *Va, *g0, *gleak, *tol, *itmax, *read_thresh, Gtop, Gbot, &it, err);
+    *iter = it;
+    return rc;
+}
+
+int32_t perc_get_voltage(const int64_t* h, double* Vint)
+{
+    GET_CTX(h);
+    if (!c->solved || !Vint) return PERC_E_STATE;
+    return download(c, Vint, c->vx + c->g.m, sizeof(double) * (c->g.t - 2 * (int64_t)c->g.m));
+}
+
+int32_t perc_launch_count(const int64_t* h, int64_t* count)
+{
+    GET_CTX(h);
+    if (!count) return PERC_E_ARG;
+    *count = c->launches;
+    return 0;
+}
+
+int32_t perc_phase_ms(const int64_t* h, const int32_t* nphase, float* ms)
+{
+    GET_CTX(h);
+    if (!nphase || !ms) return PERC_E_ARG;
+    for (int k = 0; k < *nphase && k < 8; ++k) ms[k] = c->phase_ms[k];
+    return 0;
+}
+
+int32_t perc_stream(const int64_t* h, uint64_t* stream)
+{
+    GET_CTX(h);
+    if (!stream) return PERC_E_ARG;
+    *stream = (uint64_t)(uintptr_t)c->stream;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+// context.h -- per-handle state of libperc_b200 (host side, C++).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+#include "geometry.cuh"
+
+namespace perc {
+
+constexpr int RANK_NONE = 0x7fffffff;
+
+// tile of the block-local CCL kernel (sites); TW must be 32 (one warp per row segment)
+constexpr int CCL_TW = 32;
+constexpr int CCL_TH = 32;
+
+// device-side summary written by the labeling pipeline
+struct Summary {
+    unsigned long long ncl;        // clusters with a site-id label
+    unsigned long long nlone;      // mixed problem: occupied bonds with no occupied end (size-1 clusters)
+    unsigned long long maxpack;    // (size << 32) | (0xffffffff - label)  -> max size, then min label
+    unsigned long long nocc_sites; // occupied sites in the mask
+    unsigned long long nocc_bonds; // occupied bonds in the mask
+    int nspan;                     // spanning clusters found
+    int span_overflow;
+};
+
+constexpr int MAX_SPAN = 4096;
+
+// PCG scalars living on the device (one solve at a time per handle)
+struct PcgState {
+    double bknum, bkden, akden, ak, bk, rr, bnrm, err, tol;
+    double Itop, Ibot;
+    int iter, itmax, done;
+    unsigned int ticket_a, ticket_b;   // last-block-done counters
+};
+
+struct PhiloxThreshold {
+    unsigned long long key;   // occupied iff elem_key < key || (elem_key == key && id <= id)
+    unsigned long long id;
+    int enabled;              // 0: nothing occupied
+    int all;                  // 1: everything occupied
+};
+
+enum OccSource { SRC_NONE = 0, SRC_RANK = 1, SRC_PHILOX = 2 };
+
+struct Ctx {
+    Geom g;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+
+    // ---- occupancy inputs
+    int32_t* srank = nullptr;     // [t]        rank of the site in the fill order
+    int32_t* brank = nullptr;     // [ndir][t]  rank of the bond owned by (site, dir)
+    int site_src = SRC_NONE, bond_src = SRC_NONE;
+    int ks = 0, kb = 0;
+    unsigned long long seed = 0, stream_id = 0;
+    PhiloxThreshold thr_site{}, thr_bond{};
+
+    // ---- realization state
+    uint8_t* mask = nullptr;      // [t]
+    int32_t* label = nullptr;     // [t]  parent+1 during CCL, canonical label after flatten
+    int32_t* size = nullptr;      // [t]  size by canonical label (index label-1)
+    int32_t* span_mark = nullptr; // [t]  scratch, kept zero between calls
+    int32_t* span_ids = nullptr;  // [MAX_SPAN]
+    Summary* d_sum = nullptr;
+    Summary h_sum{};
+    std::vector<int32_t> h_span_ids, h_span_sizes;
+    int kind = 0;
+    bool labeled = false;
+
+    // ---- conductance
+    uint8_t* cfull = nullptr;     // [t] conducting-neighbour bits (8 directions)
+    double* vx = nullptr;         // [t] solution (rows 0 and n-1 unused)
+    double* vr = nullptr;
+    double* vp = nullptr;
+    double* vq = nullptr;
+    double* partial = nullptr;    // per-block partial sums
+    int partial_cap = 0;
+    PcgState* d_pcg = nullptr;
+    PcgState* h_pcg = nullptr;    // pinned
+    bool solved = false;
+
+    // ---- selection scratch
+    unsigned long long* d_hist = nullptr;   // [4096 + 8]
+    unsigned long long* d_cand = nullptr;   // candidate (key,id) pairs
+    int cand_cap = 0;
+
+    // ---- host staging
+    void* h_stage = nullptr;      // pinned staging buffer
+    size_t h_stage_bytes = 0;
+    void* d_stage = nullptr;
+    size_t d_stage_bytes = 0;
+
+    // ---- instrumentation
+    int64_t launches = 0;
+    float phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[12] = {};
+};
+
+// ---- implemented in the .cu files -----------------------------------------------------------
+int ctx_alloc(Ctx* c);
+void ctx_free(Ctx* c);
+void* ctx_host_stage(Ctx* c, size_t bytes);
+void* ctx_dev_stage(Ctx* c, size_t bytes);
+
+int occ_upload_site_order(Ctx* c, const int32_t* order);
+int occ_upload_bond_order(Ctx* c, const int32_t* border);
+int occ_upload_flags(Ctx* c, const uint8_t* socc, const uint8_t* bocc);
+int occ_generate(Ctx* c, unsigned long long seed, unsigned long long stream, int ks, int kb);
+int occ_export(Ctx* c, uint8_t* socc, uint8_t* bocc);
+int occ_build_mask(Ctx* c, int kind);
+
+int ccl_run(Ctx* c, int kind);
+int ccl_fetch_summary(Ctx* c);
+int ccl_hist(Ctx* c, int nbins, int64_t* hist);
+int ccl_export_bond_labels(Ctx* c, int32_t* b3);
+
+int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double tol, int itmax,
+              double read_thresh, double* Gtop, double* Gbot, int* iter, double* err);
+
+#define PERC_CUDA(call)                                              \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) return (int)e__;                     \
+    } while (0)
+
+}  // namespace perc

@@ -1,0 +1,257 @@
+"""ctypes binding of libperc_b200.so (the C-ABI of include/perc_abi.h).
+
+Every call goes through the C-ABI exactly as the Fortran ISO_C_BINDING drivers do
+(scalars by reference, 1-based ids, column-major 2-D arrays).  There is no CPU
+fallback: if the library is missing or no CUDA device is present, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libperc_b200.so")
+
+SQUARE, TRIANGULAR = 1, 2
+SITE, BOND, MIXED = 1, 2, 3
+
+E_ARG, E_ODD_M, E_HANDLE, E_STATE, E_SIZE, E_NOSPAN = -1, -2, -3, -4, -5, -6
+_ENAMES = {E_ARG: "PERC_E_ARG", E_ODD_M: "PERC_E_ODD_M", E_HANDLE: "PERC_E_HANDLE", E_STATE: "PERC_E_STATE",
+           E_SIZE: "PERC_E_SIZE", E_NOSPAN: "PERC_E_NOSPAN"}
+
+# every symbol include/perc_abi.h declares
+SYMBOLS = [
+    "perc_geom_nb", "perc_geom_bondlist", "perc_geom_nearestn",
+    "perc_create", "perc_destroy", "perc_sync",
+    "perc_set_site_order", "perc_set_bond_order", "perc_set_fill", "perc_set_occupancy",
+    "perc_generate", "perc_get_occupancy",
+    "perc_label", "perc_summary", "perc_get_site_labels", "perc_get_bond_labels", "perc_get_sizes",
+    "perc_span", "perc_hist", "perc_site", "perc_bond", "perc_sitebond", "perc_first_span",
+    "perc_conduct", "perc_get_voltage", "perc_launch_count", "perc_phase_ms", "perc_stream",
+]
+
+
+class PercError(RuntimeError):
+    def __init__(self, fn, code):
+        self.code = code
+        what = _ENAMES.get(code, "cudaError %d" % code if code > 0 else "error %d" % code)
+        super().__init__("%s failed: %s" % (fn, what))
+
+
+_lib = None
+
+
+def load():
+    """load the shared library; fails loudly when it has not been built"""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError("libperc_b200.so is not built (run `python -m percolation_b200.build` "
+                              "or __graft_entry__.build()); there is no CPU fallback")
+        _lib = C.CDLL(SO_PATH)
+        for s in SYMBOLS:
+            getattr(_lib, s).restype = C.c_int32
+    return _lib
+
+
+def _i32(v):
+    return C.byref(C.c_int32(int(v)))
+
+
+def _i64(v):
+    return C.byref(C.c_int64(int(v)))
+
+
+def _f64(v):
+    return C.byref(C.c_double(float(v)))
+
+
+def _ptr(a, ct):
+    return a.ctypes.data_as(C.POINTER(ct)) if a is not None else None
+
+
+def _ck(fn, rc):
+    if rc != 0:
+        raise PercError(fn, rc)
+
+
+def geom_nb(lattice, m, n, pbc):
+    out = C.c_int32(0)
+    _ck("perc_geom_nb", load().perc_geom_nb(_i32(lattice), _i32(m), _i32(n), _i32(pbc), C.byref(out)))
+    return out.value
+
+
+def geom_bondlist(lattice, m, n, pbc):
+    """(b1, b2): the reference's bond list b(nb,1:2) (Sq/bond.f:112-129)"""
+    nb = geom_nb(lattice, m, n, pbc)
+    b = np.zeros(2 * nb, np.int32)
+    _ck("perc_geom_bondlist", load().perc_geom_bondlist(_i32(lattice), _i32(m), _i32(n), _i32(pbc), _ptr(b, C.c_int32)))
+    return b[:nb].copy(), b[nb:].copy()
+
+
+def geom_nearestn(lattice, m, n, pbc, rn):
+    nn = np.zeros(6, np.int32)
+    _ck("perc_geom_nearestn", load().perc_geom_nearestn(_i32(lattice), _i32(m), _i32(n), _i32(pbc), _i32(rn),
+                                                        _ptr(nn, C.c_int32)))
+    return nn[:4 if lattice == SQUARE else 6].copy()
+
+
+class Lattice:
+    """one handle = the reference's parameter block (lattice, m, n, pbc) on one GPU"""
+
+    def __init__(self, lattice, m, n, pbc=0, device=0):
+        self.lattice, self.m, self.n, self.pbc = int(lattice), int(m), int(n), int(pbc)
+        self.t = self.m * self.n
+        self._h = C.c_int64(0)
+        self._lib = load()
+        _ck("perc_create", self._lib.perc_create(C.byref(self._h), _i32(lattice), _i32(m), _i32(n), _i32(pbc),
+                                                 _i32(device)))
+        self.nb = geom_nb(lattice, m, n, pbc)
+
+    def close(self):
+        if self._h.value:
+            self._lib.perc_destroy(C.byref(self._h))
+            self._h = C.c_int64(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _call(self, name, *args):
+        _ck(name, getattr(self._lib, name)(C.byref(self._h), *args))
+
+    # ---- occupancy
+    def set_site_order(self, order):
+        order = np.ascontiguousarray(order, np.int32)
+        assert order.size == self.t
+        self._call("perc_set_site_order", _ptr(order, C.c_int32))
+
+    def set_bond_order(self, bo1, bo2=None):
+        """border(nb,2) column-major: pass (lo, hi) columns or one flat array of 2*nb"""
+        border = np.ascontiguousarray(np.concatenate([bo1, bo2]) if bo2 is not None else bo1, np.int32)
+        assert border.size == 2 * self.nb
+        self._call("perc_set_bond_order", _ptr(border, C.c_int32))
+
+    def set_fill(self, ks=-1, kb=-1):
+        self._call("perc_set_fill", _i32(ks), _i32(kb))
+
+    def set_occupancy(self, socc=None, bocc=None):
+        s = None if socc is None else np.ascontiguousarray(socc, np.uint8)
+        b = None if bocc is None else np.ascontiguousarray(bocc, np.uint8)
+        self._call("perc_set_occupancy", _ptr(s, C.c_uint8), _ptr(b, C.c_uint8))
+
+    def generate(self, seed, stream=0, ks=-1, kb=-1):
+        self._call("perc_generate", _i64(seed), _i64(stream), _i32(ks), _i32(kb))
+
+    def get_occupancy(self, sites=True, bonds=True):
+        s = np.zeros(self.t, np.uint8) if sites else None
+        b = np.zeros(self.nb, np.uint8) if bonds else None
+        self._call("perc_get_occupancy", _ptr(s, C.c_uint8), _ptr(b, C.c_uint8))
+        return s, b
+
+    # ---- labeling
+    def label(self, kind):
+        self._call("perc_label", _i32(kind))
+
+    def summary(self):
+        ncl, maxcs, maxcn, nspan = C.c_int64(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._call("perc_summary", C.byref(ncl), C.byref(maxcs), C.byref(maxcn), C.byref(nspan))
+        return dict(ncl=ncl.value, maxcs=maxcs.value, maxcn=maxcn.value, nspan=nspan.value)
+
+    def site_labels(self):
+        s = np.zeros(self.t, np.int32)
+        self._call("perc_get_site_labels", _ptr(s, C.c_int32))
+        return s
+
+    def bond_labels(self):
+        b3 = np.zeros(self.nb, np.int32)
+        self._call("perc_get_bond_labels", _ptr(b3, C.c_int32))
+        return b3
+
+    def sizes(self):
+        c = np.zeros(self.t, np.int32)
+        self._call("perc_get_sizes", _ptr(c, C.c_int32))
+        return c
+
+    def span(self, max_ids=4096):
+        ids = np.zeros(max_ids, np.int32)
+        sizes = np.zeros(max_ids, np.int32)
+        nspan = C.c_int32(0)
+        self._call("perc_span", _i32(max_ids), C.byref(nspan), _ptr(ids, C.c_int32), _ptr(sizes, C.c_int32))
+        k = min(nspan.value, max_ids)
+        return ids[:k].copy(), sizes[:k].copy()
+
+    def hist(self, nbins):
+        h = np.zeros(nbins, np.int64)
+        self._call("perc_hist", _i32(nbins), _ptr(h, C.c_int64))
+        return h
+
+    def site(self, order, k):
+        """Sq/site.f:162-344 in one call: returns s, c, dict(maxcs, perccln, perccls)"""
+        order = np.ascontiguousarray(order, np.int32)
+        s = np.zeros(self.t, np.int32)
+        c = np.zeros(self.t, np.int32)
+        a, b, d = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._call("perc_site", _ptr(order, C.c_int32), _i32(k), _ptr(s, C.c_int32), _ptr(c, C.c_int32),
+                   C.byref(a), C.byref(b), C.byref(d))
+        return s, c, dict(maxcs=a.value, perccln=b.value, perccls=d.value)
+
+    def bond(self, bo1, bo2, k):
+        border = np.ascontiguousarray(np.concatenate([bo1, bo2]), np.int32)
+        b3 = np.zeros(self.nb, np.int32)
+        c = np.zeros(self.t, np.int32)
+        a, b, d = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._call("perc_bond", _ptr(border, C.c_int32), _i32(k), _ptr(b3, C.c_int32), _ptr(c, C.c_int32),
+                   C.byref(a), C.byref(b), C.byref(d))
+        return b3, c, dict(maxcs=a.value, perccln=b.value, perccls=d.value)
+
+    def sitebond(self, sorder, ks, bo1, bo2, kb):
+        sorder = np.ascontiguousarray(sorder, np.int32)
+        border = np.ascontiguousarray(np.concatenate([bo1, bo2]), np.int32)
+        s = np.zeros(self.t, np.int32)
+        b3 = np.zeros(self.nb, np.int32)
+        c = np.zeros(self.t, np.int32)
+        a, b, d = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._call("perc_sitebond", _ptr(sorder, C.c_int32), _i32(ks), _ptr(border, C.c_int32), _i32(kb),
+                   _ptr(s, C.c_int32), _ptr(b3, C.c_int32), _ptr(c, C.c_int32), C.byref(a), C.byref(b), C.byref(d))
+        return s, b3, c, dict(maxcs=a.value, perccln=b.value, perccls=d.value)
+
+    def first_span(self, kind, which):
+        kstar, f, maxcs, perccls = C.c_int32(0), C.c_float(0), C.c_int32(0), C.c_int32(0)
+        self._call("perc_first_span", _i32(kind), _i32(which), C.byref(kstar), C.byref(f), C.byref(maxcs),
+                   C.byref(perccls))
+        return dict(kstar=kstar.value, f=np.float32(f.value), maxcs=maxcs.value, perccls=perccls.value)
+
+    # ---- conductance
+    def conduct(self, cluster_id=0, Va=1.0, g0=1.0, gleak=1e-12, tol=1e-8, itmax=2500, read_thresh=1e-10):
+        Gtop, Gbot, err, it = C.c_double(0), C.c_double(0), C.c_double(0), C.c_int32(0)
+        self._call("perc_conduct", _i32(cluster_id), _f64(Va), _f64(g0), _f64(gleak), _f64(tol), _i32(itmax),
+                   _f64(read_thresh), C.byref(Gtop), C.byref(Gbot), C.byref(it), C.byref(err))
+        return dict(Gtop=Gtop.value, Gbot=Gbot.value, iter=it.value, err=err.value)
+
+    def voltage(self):
+        v = np.zeros(self.t - 2 * self.m, np.float64)
+        self._call("perc_get_voltage", _ptr(v, C.c_double))
+        return v
+
+    # ---- instrumentation
+    def launch_count(self):
+        n = C.c_int64(0)
+        self._call("perc_launch_count", C.byref(n))
+        return n.value
+
+    def phase_ms(self):
+        ms = np.zeros(8, np.float32)
+        self._call("perc_phase_ms", _i32(8), _ptr(ms, C.c_float))
+        return ms
+
+    def sync(self):
+        self._call("perc_sync")

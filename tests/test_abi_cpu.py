@@ -1,0 +1,64 @@
+"""CPU-side checks of the product library: it loads, exports every symbol that
+include/perc_abi.h declares, and its closed-form geometry (host index arithmetic,
+no device) reproduces the oracle's literal nearestn / bond-list restatement."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def P():
+    import percolation_b200 as P
+    from percolation_b200 import build
+    build.build()
+    P.load()
+    return P
+
+
+def test_exports_every_declared_symbol(P):
+    hdr = open(os.path.join(ROOT, "include", "perc_abi.h")).read()
+    declared = sorted(set(re.findall(r"^int32_t\s+(perc_\w+)\s*\(", hdr, re.M)))
+    assert declared == sorted(P.SYMBOLS)
+    lib = P.load()
+    for s in declared:
+        assert hasattr(lib, s), s
+
+
+GEOMS = [(lat, m, n, pbc) for lat in (1, 2) for (m, n) in ((4, 3), (6, 5), (8, 2), (10, 10), (34, 7), (66, 35))
+         for pbc in (0, 1)]
+
+
+@pytest.mark.parametrize("lat,m,n,pbc", GEOMS)
+def test_bond_numbering_matches_reference_enumeration(P, O, lat, m, n, pbc):
+    assert P.geom_nb(lat, m, n, pbc) == O.nb(lat, m, n, pbc)
+    b1, b2 = P.geom_bondlist(lat, m, n, pbc)
+    r1, r2 = O.bondlist(lat, m, n, pbc)
+    assert (b1 == r1).all() and (b2 == r2).all()
+
+
+@pytest.mark.parametrize("lat,m,n,pbc", [g for g in GEOMS if g[1] <= 10])
+def test_nearestn_matches_reference(P, O, lat, m, n, pbc):
+    for rn in range(1, m * n + 1):
+        assert list(P.geom_nearestn(lat, m, n, pbc, rn)) == list(O.nearestn(lat, m, n, pbc, rn)), rn
+
+
+def test_argument_errors(P):
+    with pytest.raises(P.PercError) as e:
+        P.geom_nb(2, 7, 6, 0)                 # odd m on the triangular lattice
+    assert e.value.code == -2
+    with pytest.raises(P.PercError):
+        P.geom_nb(3, 8, 8, 0)
+    with pytest.raises(P.PercError):
+        P.geom_nb(1, 1, 8, 0)
+
+
+def test_no_device_fails_loudly(P):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(P.PercError):
+        P.Lattice(1, 8, 8)

@@ -1,0 +1,359 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the
+same seeded inputs.  Integer / index results must be bit-exact; conductance must agree
+to 1e-9 relative with both sides converged to <= 1e-12."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def P():
+    import percolation_b200 as P
+    P.load()
+    return P
+
+
+def occ_from(order, k, total):
+    occ = np.zeros(total, np.uint8)
+    occ[np.asarray(order[:k]) - 1] = 1
+    return occ
+
+
+def bond_occ_from(b1, b2, bo1, bo2, k, t):
+    key = b1.astype(np.int64) * (t + 1) + b2
+    srt = np.argsort(key)
+    q = bo1[:k].astype(np.int64) * (t + 1) + bo2[:k]
+    rows = srt[np.searchsorted(key[srt], q)]
+    occ = np.zeros(len(b1), np.uint8)
+    occ[rows] = 1
+    return occ
+
+
+SHAPES = [(50, 50), (70, 45), (32, 32), (34, 66), (128, 96), (6, 3)]
+CASES = [(lat, m, n, pbc) for lat in (1, 2) for (m, n) in SHAPES for pbc in (0, 1)]
+
+
+@pytest.mark.parametrize("lat,m,n,pbc", CASES)
+def test_site_labels_sizes_span(P, O, lat, m, n, pbc):
+    t = m * n
+    b1, b2 = O.bondlist(lat, m, n, pbc)
+    with P.Lattice(lat, m, n, pbc) as L:
+        order = O.shuffle_sites(1080115 + m, t)
+        for frac in (0.0, 0.3, 0.5, 0.6, 0.75, 1.0):
+            k = O.fill_count(frac, t)
+            s, c, res = L.site(order, k)
+            want, _, wsz, ncl, wmax = O.label_uf(O.SITE, lat, m, n, pbc, b1, b2, site_occ=occ_from(order, k, t))
+            assert (s == want).all()
+            assert (c == wsz[1:]).all()
+            sm = L.summary()
+            assert sm["ncl"] == ncl and sm["maxcs"] == wmax
+            ids = O.spanning(O.SITE, m, n, b1, b2, want, None)
+            gids, gsz = L.span()
+            assert list(gids) == list(ids) and list(gsz) == [wsz[i] for i in ids]
+            assert res["perccln"] == (ids[0] if len(ids) else 0)
+            nbins = 64
+            h = L.hist(nbins)
+            oh = O.size_hist(O.SITE, t, wsz, None, t)
+            assert (h[:nbins - 1] == oh[1:nbins]).all() and h[nbins - 1] == oh[nbins:].sum()
+
+
+@pytest.mark.parametrize("lat,m,n,pbc", CASES)
+def test_bond_labels_sizes_span(P, O, lat, m, n, pbc):
+    t = m * n
+    b1, b2 = O.bondlist(lat, m, n, pbc)
+    nb = len(b1)
+    with P.Lattice(lat, m, n, pbc) as L:
+        bo1, bo2 = O.shuffle_bonds(184489 + n, b1, b2)
+        for frac in (0.0, 0.2, 0.35, 0.5, 0.7, 1.0):
+            k = O.fill_count(frac, nb)
+            b3, c, res = L.bond(bo1, bo2, k)
+            occ = bond_occ_from(b1, b2, bo1, bo2, k, t)
+            _, want, wsz, ncl, wmax = O.label_uf(O.BOND, lat, m, n, pbc, b1, b2, bond_occ=occ)
+            assert (b3 == want).all()
+            assert (c == wsz[1:]).all()
+            sm = L.summary()
+            assert sm["ncl"] == ncl and sm["maxcs"] == wmax
+            ids = O.spanning(O.BOND, m, n, b1, b2, None, want)
+            gids, gsz = L.span()
+            assert list(gids) == list(ids) and list(gsz) == [wsz[i] for i in ids]
+            _, bocc = L.get_occupancy(sites=False)
+            assert (bocc == occ).all()
+
+
+@pytest.mark.parametrize("lat,m,n,pbc", CASES)
+def test_mixed_labels_sizes_span(P, O, lat, m, n, pbc):
+    t = m * n
+    b1, b2 = O.bondlist(lat, m, n, pbc)
+    nb = len(b1)
+    with P.Lattice(lat, m, n, pbc) as L:
+        sorder = O.shuffle_sites(8811064 % 100000 + m, t)
+        bo1, bo2 = O.shuffle_bonds(3784068 + n, b1, b2)
+        for fs, fb in ((0.0, 0.4), (0.5, 0.5), (0.8, 0.6), (0.8, 0.0), (1.0, 1.0), (0.7, 0.9)):
+            ks, kb = O.fill_count(fs, t), O.fill_count(fb, nb)
+            s, b3, c, res = L.sitebond(sorder, ks, bo1, bo2, kb)
+            socc = occ_from(sorder, ks, t)
+            bocc = bond_occ_from(b1, b2, bo1, bo2, kb, t)
+            ws, wb, wsz, ncl, wmax = O.label_uf(O.MIXED, lat, m, n, pbc, b1, b2, site_occ=socc, bond_occ=bocc)
+            assert (s == ws).all()
+            assert (b3 == wb).all()
+            assert (c == wsz[1:]).all()
+            sm = L.summary()
+            assert sm["ncl"] == ncl and sm["maxcs"] == wmax
+            ids = O.spanning(O.MIXED, m, n, b1, b2, ws, wb)
+            gids, gsz = L.span()
+            assert list(gids) == list(ids)
+            h = L.hist(32)
+            oh = O.size_hist(O.MIXED, t, wsz, wb, t + nb)
+            assert (h[:31] == oh[1:32]).all() and h[31] == oh[32:].sum()
+
+
+def test_png_fixtures_through_gpu(P, O):
+    """the reference's own renderings: largest cluster (green) == GPU max cluster"""
+    z = np.load(os.path.join(HERE, "golden", "png_fixtures.npz"))
+    M = N = 50
+    handles = {lat: P.Lattice(lat, M, N, 0) for lat in (1, 2)}
+    lists = {lat: O.bondlist(lat, M, N, 0) for lat in (1, 2)}
+    checked = 0
+    for row in z["index"]:
+        key, kind, lat, p, name = str(row).split("|")
+        kind, lat = int(kind), int(lat)
+        dots = np.unpackbits(z[key + "_dots"])[: M * N]
+        cls = z[key + "_cls"]
+        L = handles[lat]
+        b1, b2 = lists[lat]
+        if kind == O.SITE:
+            L.set_occupancy(socc=dots)
+            L.label(P.SITE)
+            s = L.site_labels()
+            lab_of_bond = s[b1 - 1]
+            occb = (dots[b1 - 1] == 1) & (dots[b2 - 1] == 1)
+        else:
+            L.set_occupancy(bocc=(cls > 0).astype(np.uint8))
+            L.label(P.BOND)
+            lab_of_bond = L.bond_labels()
+            occb = cls > 0
+        assert ((lab_of_bond > 0) & occb == occb).all(), name
+        c = L.sizes()
+        sm = L.summary()
+        green = cls == 2
+        if green.any():
+            labs = np.unique(lab_of_bond[green])
+            assert all(c[l - 1] == sm["maxcs"] for l in labs), name
+            assert (green == (occb & np.isin(lab_of_bond, labs))).all(), name
+        checked += 1
+    assert checked == 65
+    for L in handles.values():
+        L.close()
+
+
+@pytest.mark.parametrize("lat,kind", [(1, 2), (2, 2), (1, 1), (2, 1), (1, 3), (2, 3)])
+@pytest.mark.parametrize("pbc", [0, 1])
+def test_conductance_vs_oracle(P, O, lat, kind, pbc):
+    m, n = 40, 36
+    t = m * n
+    b1, b2 = O.bondlist(lat, m, n, pbc)
+    nb = len(b1)
+    done = 0
+    with P.Lattice(lat, m, n, pbc) as L:
+        for seed in range(5):
+            sorder = O.shuffle_sites(626504 + seed, t)
+            bo1, bo2 = O.shuffle_bonds(184489 + seed, b1, b2)
+            if kind == O.BOND:
+                kb = O.fill_count(0.54 if lat == 1 else 0.38, nb)
+                b3, c, res = L.bond(bo1, bo2, kb)
+                s = None
+            elif kind == O.SITE:
+                ks = O.fill_count(0.63 if lat == 1 else 0.54, t)
+                s, c, res = L.site(sorder, ks)
+                b3 = None
+            else:
+                ks, kb = O.fill_count(0.85, t), O.fill_count(0.68 if lat == 1 else 0.5, nb)
+                s, b3, c, res = L.sitebond(sorder, ks, bo1, bo2, kb)
+            if not res["perccln"]:
+                continue
+            cid = res["perccln"]
+            w = O.weights(kind, b1, b2, s, b3, cid)
+            # (a) reference defaults: same recurrences -> same iteration count, same G to rounding
+            ref = O.conduct_literal(m, n, b1, b2, w)
+            got = L.conduct(cid)
+            assert got["iter"] == ref["iter"]
+            assert abs(got["Gtop"] - ref["Gtop"]) <= 1e-9 * abs(ref["Gtop"])
+            assert abs(got["Gbot"] - ref["Gbot"]) <= 1e-9 * abs(ref["Gbot"])
+            # (b) both converged: 1e-9 relative (tolerance of the north star), in fact ~1e-12
+            ref = O.conduct_cg(m, n, b1, b2, w, tol=1e-13, itmax=200000)
+            got = L.conduct(cid, tol=1e-13, itmax=200000)
+            assert got["err"] <= 1e-13
+            assert abs(got["Gtop"] - ref["Gtop"]) <= 1e-9 * abs(ref["Gtop"])
+            assert abs(got["Gbot"] - ref["Gbot"]) <= 1e-9 * abs(ref["Gbot"])
+            # (c) independent residual check of the GPU voltages on the CPU
+            chk = O.conduct_check(m, n, b1, b2, w, L.voltage())
+            assert chk["err"] <= 2e-13
+            assert abs(chk["Gtop"] - got["Gtop"]) <= 1e-12 * abs(got["Gtop"])
+            done += 1
+            if done == 2:
+                break
+    assert done >= 1
+
+
+def test_full_lattice_closed_form(P, O):
+    """every bond occupied: square G = m/(n-1) exactly"""
+    for (m, n, pbc) in ((10, 10, 0), (16, 8, 1), (50, 50, 0)):
+        with P.Lattice(1, m, n, pbc) as L:
+            L.set_occupancy(bocc=np.ones(L.nb, np.uint8))
+            L.label(P.BOND)
+            r = L.conduct(0, tol=1e-13, itmax=100000)
+            assert abs(r["Gtop"] - m / (n - 1)) < 1e-10 and abs(r["Gbot"] - m / (n - 1)) < 1e-10
+    for (m, n, pbc, want) in ((10, 10, 0, 1.662318388765), (16, 8, 1, 3.576045037457)):
+        with P.Lattice(2, m, n, pbc) as L:
+            L.set_occupancy(socc=np.ones(L.t, np.uint8))
+            L.label(P.SITE)
+            r = L.conduct(0, tol=1e-13, itmax=100000)
+            assert abs(r["Gtop"] - want) < 2e-11 and abs(r["Gbot"] - want) < 2e-11
+
+
+def test_first_span_matches_literal_fill(P, O):
+    for lat in (1, 2):
+        m = n = 24
+        t = m * n
+        b1, b2 = O.bondlist(lat, m, n, 0)
+        seeds = O.seed_table(58302, 6, 1000000)              # Sq/site_perc.f:69-75
+        with P.Lattice(lat, m, n, 0) as L:
+            for sd in seeds:
+                order = O.shuffle_sites(int(sd), t)
+                _, c, res = O.site_literal(lat, m, n, 0, order, t, stop_at_span=True)
+                L.set_site_order(order)
+                got = L.first_span(P.SITE, P.SITE)
+                assert got["kstar"] == res["filled"]
+                assert got["f"] == O.fraction(res["filled"], t)
+                assert got["maxcs"] == res["maxcs"] and got["perccls"] == res["perccls"]
+                bo1, bo2 = O.shuffle_bonds(int(sd), b1, b2)
+                _, c, res = O.bond_literal(lat, m, n, 0, b1, b2, bo1, bo2, len(b1), stop_at_span=True)
+                L.set_bond_order(bo1, bo2)
+                got = L.first_span(P.BOND, P.BOND)
+                assert got["kstar"] == res["filled"] and got["maxcs"] == res["maxcs"]
+                # mixed, sites fixed at ps = 0.8, bonds added (Sq/sb_perc.f)
+                ks = O.fill_count(0.8, t)
+                s, b3, c, res = O.sitebond_literal(lat, m, n, 0, b1, b2, order, ks, bo1, bo2, len(b1), stop_at_span=True)
+                L.set_fill(ks=ks)
+                got = L.first_span(P.MIXED, P.BOND)
+                assert got["kstar"] == (res["filled"] if res["perccln"] else 0)
+
+
+# ---- K1 generator -------------------------------------------------------------------------
+def philox_keys(seed, stream, typ, ids):
+    """numpy restatement of csrc/philox.cuh (Philox-4x32-10)"""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    ids = np.asarray(ids, np.uint64)
+    c0 = ids & np.uint64(0xffffffff)
+    c1 = ids >> np.uint64(32)
+    c2 = np.full_like(ids, np.uint64(stream & 0xffffffff))
+    c3 = np.full_like(ids, np.uint64((stream >> 32) & 0xffffffff))
+    k0 = np.uint64(seed & 0xffffffff)
+    k1 = np.uint64(((seed >> 32) & 0xffffffff) ^ (0x5bd1e995 if typ else 0))
+    mask = np.uint64(0xffffffff)
+    for _ in range(10):
+        p0 = M0 * c0
+        p1 = M1 * c2
+        n0 = ((p1 >> np.uint64(32)) ^ c1 ^ k0) & mask
+        n1 = p1 & mask
+        n2 = ((p0 >> np.uint64(32)) ^ c3 ^ k1) & mask
+        n3 = p0 & mask
+        c0, c1, c2, c3 = n0, n1, n2, n3
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return (c0 << np.uint64(32)) | c1
+
+
+def test_philox_known_answer():
+    # Random123 KAT: counter 0, key 0 -> 6627e8d5 e169c58d bc57ac4c 9b00dbd8
+    k = philox_keys(0, 0, 0, [0])[0]
+    assert int(k) == (0x6627e8d5 << 32) | 0xe169c58d
+
+
+@pytest.mark.parametrize("lat,m,n,pbc", [(1, 50, 50, 0), (2, 64, 40, 1), (1, 257, 129, 1)])
+def test_generator_exact_count_and_keys(P, lat, m, n, pbc):
+    seed, stream = 20240611, 3
+    with P.Lattice(lat, m, n, pbc) as L:
+        t, nb = L.t, L.nb
+        b1, b2 = P.geom_bondlist(lat, m, n, pbc)
+        for fs, fb in ((0.6, 0.35), (0.0, 1.0), (1.0, 0.0), (0.5927, 0.5)):
+            ks, kb = int(fs * t), int(fb * nb)
+            L.generate(seed, stream, ks, kb)
+            socc, bocc = L.get_occupancy()
+            assert int(socc.sum()) == ks and int(bocc.sum()) == kb
+            keys = philox_keys(seed, stream, 0, np.arange(t))
+            order = np.lexsort((np.arange(t), keys))
+            want = np.zeros(t, np.uint8)
+            want[order[:ks]] = 1
+            assert (socc == want).all()
+        # nesting: a larger fill count keeps every previously occupied element (sweep property)
+        L.generate(seed, stream, int(0.5 * t), int(0.4 * nb))
+        s1, bb1 = L.get_occupancy()
+        L.set_fill(int(0.6 * t), int(0.5 * nb))
+        s2, bb2 = L.get_occupancy()
+        assert (s2 >= s1).all() and (bb2 >= bb1).all()
+        assert int(s2.sum()) == int(0.6 * t) and int(bb2.sum()) == int(0.5 * nb)
+        # different realizations differ
+        L.generate(seed, stream + 1, int(0.5 * t), -1)
+        s3, _ = L.get_occupancy(bonds=False)
+        assert (s3 != s1).any()
+
+
+# ---- larger lattices -----------------------------------------------------------------------
+@pytest.mark.parametrize("lat,kind,L_", [(1, 1, 1024), (2, 2, 1024), (1, 3, 1024), (2, 1, 2048)])
+def test_large_lattice_vs_oracle(P, O, lat, kind, L_):
+    m = n = L_
+    t = m * n
+    b1, b2 = O.bondlist(lat, m, n, 0)
+    nb = len(b1)
+    with P.Lattice(lat, m, n, 0) as L:
+        ks = int((0.5927 if lat == 1 else 0.5) * t) if kind == 1 else int(0.8 * t)
+        kb = int((0.5 if lat == 1 else 0.3473) * nb) if kind == 2 else int(0.66 * nb)
+        L.generate(777, 0, ks if kind != 2 else -1, kb if kind != 1 else -1)
+        L.label(kind)
+        socc, bocc = L.get_occupancy(sites=kind != 2, bonds=kind != 1)
+        ws, wb, wsz, ncl, wmax = O.label_uf(kind, lat, m, n, 0, b1, b2, site_occ=socc, bond_occ=bocc)
+        if kind != 2:
+            assert (L.site_labels() == ws).all()
+        if kind != 1:
+            assert (L.bond_labels() == wb).all()
+        assert (L.sizes() == wsz[1:]).all()
+        sm = L.summary()
+        assert sm["ncl"] == ncl and sm["maxcs"] == wmax
+        ids = O.spanning(kind, m, n, b1, b2, ws, wb)
+        assert list(L.span()[0]) == list(ids)
+
+
+def test_full_size_properties_L4096(P):
+    """BASELINE config sizes: size-independent properties (sum of sizes == occupied count,
+    labels are fixed points, idempotence, spanning monotone in the fill)"""
+    m = n = 4096
+    with P.Lattice(1, m, n, 0) as L:
+        t, nb = L.t, L.nb
+        ks, kb = int(0.8 * t), int(0.66 * nb)
+        L.generate(12345, 0, ks, kb)
+        L.label(P.MIXED)
+        s = L.site_labels()
+        c = L.sizes()
+        sm = L.summary()
+        occ = s > 0
+        assert int(occ.sum()) == ks
+        roots = np.nonzero(c > 0)[0]
+        assert (s[roots] == roots + 1).all()                    # canonical label = own id at the root
+        assert (s[occ] <= np.nonzero(occ)[0] + 1).all()          # label is the minimum member id
+        assert (c[s[occ] - 1] > 0).all()
+        h = L.hist(8)
+        nlone = sm["ncl"] - len(roots)
+        assert int(c.astype(np.int64).sum()) + nlone == ks + kb  # every element in exactly one cluster
+        assert h.sum() == sm["ncl"]
+        L.label(P.MIXED)                                         # idempotent
+        assert (L.site_labels() == s).all() and (L.sizes() == c).all()
+        sp_hi = L.summary()["nspan"]
+        L.set_fill(kb=int(0.45 * nb))
+        L.label(P.MIXED)
+        assert L.summary()["nspan"] == 0 and sp_hi >= 1
