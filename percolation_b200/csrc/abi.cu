@@ -76,6 +76,7 @@ static int ensure_pcg(Ctx* c)
     PERC_CUDA(cudaMalloc(&c->vx, sizeof(double) * t));
     PERC_CUDA(cudaMalloc(&c->vr, sizeof(double) * t));
     PERC_CUDA(cudaMalloc(&c->vp, sizeof(double) * t));
+    PERC_CUDA(cudaMalloc(&c->vp2, sizeof(double) * t));
     PERC_CUDA(cudaMalloc(&c->vq, sizeof(double) * t));
     return 0;
 }
@@ -85,7 +86,7 @@ void ctx_free(Ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     void* ptrs[] = {c->srank, c->brank, c->mask, c->label, c->size, c->span_mark, c->span_ids, c->d_sum, c->d_pcg,
-                    c->d_hist, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vq, c->partial, c->d_stage};
+                    c->d_hist, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vp2, c->vq, c->partial, c->d_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_pcg) cudaFreeHost(c->h_pcg);
     if (c->h_stage) cudaFreeHost(c->h_stage);

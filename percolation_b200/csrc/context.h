@@ -73,6 +73,7 @@ struct Ctx {
     double* vx = nullptr;         // [t] solution (rows 0 and n-1 unused)
     double* vr = nullptr;
     double* vp = nullptr;
+    double* vp2 = nullptr;        // p is double-buffered (the fused SpMV reads neighbours' old p)
     double* vq = nullptr;
     double* partial = nullptr;    // per-block partial sums
     int partial_cap = 0;

@@ -160,8 +160,8 @@ pcg_init_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
 template <int LAT>
 __global__ void __launch_bounds__(SP_THREADS)
 pcg_spmv_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, const double* __restrict__ vr,
-                double* __restrict__ vp, double* __restrict__ vq, double* __restrict__ partial,
-                PcgState* __restrict__ st)
+                const double* __restrict__ vp_old, double* __restrict__ vp, double* __restrict__ vq,
+                double* __restrict__ partial, PcgState* __restrict__ st)
 {
     if (st->done) return;
     __shared__ double pn[SP_HY * SP_HX];
@@ -178,7 +178,7 @@ pcg_spmv_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, const 
             int64_t j = (int64_t)gy * g.m + gx;
             unsigned ex = neighbour_bits(g, gx, gy), cf = cfull[j];
             double d = diag_of(cf, ex, prm.g0, prm.gleak);
-            v = vr[j] / d + bk * vp[j];
+            v = vr[j] / d + bk * vp_old[j];      // p is double-buffered: neighbours' tiles write vp
         }
         pn[k] = v;
     }
@@ -311,6 +311,7 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     build_cfull_kernel<<<nblk(g.t), 256, 0, s>>>(g, c->kind, cluster_id, c->mask, c->label, c->cfull);
     pcg_init_kernel<<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, c->vp, c->vq, c->partial, c->d_pcg, tol, itmax);
     c->launches += 2;
+    double* pold = c->vp; double* pnew = c->vp2;
     float sp_ms = 0.f, up_ms = 0.f; int nsamp = 0;
     int chunk = 16;
     for (;;) {
@@ -320,11 +321,12 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
             bool sample = (k == 0);
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[8], s));
             if (g.lattice == LAT_SQUARE)
-                pcg_spmv_kernel<LAT_SQUARE><<<sgrid, SP_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, c->vp, c->vq, c->partial, c->d_pcg);
+                pcg_spmv_kernel<LAT_SQUARE><<<sgrid, SP_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vq, c->partial, c->d_pcg);
             else
-                pcg_spmv_kernel<LAT_TRIANGULAR><<<sgrid, SP_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, c->vp, c->vq, c->partial, c->d_pcg);
+                pcg_spmv_kernel<LAT_TRIANGULAR><<<sgrid, SP_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vq, c->partial, c->d_pcg);
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[9], s));
-            pcg_update_kernel<<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, c->vp, c->vq, c->partial, c->d_pcg);
+            pcg_update_kernel<<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, pnew, c->vq, c->partial, c->d_pcg);
+            { double* tmp = pold; pold = pnew; pnew = tmp; }
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[10], s));
             c->launches += 2;
         }
