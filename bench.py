@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the percolation-realization hot path on B200.
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): square-lattice
+mixed site/bond percolation, L = 4096, ps = 0.80, pb = 0.70 (about 4 % above the bond threshold
+at that ps), one "step" = one realization: occupancy (K1 Philox generator, exact counts) ->
+cluster labeling + sizes + spanning (K2-K5) -> Kirchhoff conductance of the spanning cluster
+(K6-K8 Jacobi-PCG, fp64, tol 1e-10).  Metric: conductance realizations / s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, through the C-ABI)
+  python bench.py --impl reference ...                            CPU arm: the oracle port of the
+        reference's algorithm on the host cores (the Fortran itself cannot be built here: no
+        Fortran compiler in the image), each step a bounded sample.
+
+For N > 1 (torchrun, one rank per GPU) realizations are sharded across ranks with no data-path
+collective; one NCCL all-reduce merges the statistics at the end (weak scaling).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "conductance realizations/sec at L=4096 near p_c; CCL Gsites/s; % HBM peak"
+UNIT = "realizations/s"
+SEED = 20240611
+ITERS_FILE = os.path.join(ROOT, "profiles", "bench_iters.json")
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm / cpu_baseline: the oracle port timed on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def host_occupancy(rng, t, nb, ks, kb):
+    socc = np.zeros(t, np.uint8)
+    socc[np.argpartition(rng.random(t), ks)[:ks]] = 1
+    bocc = np.zeros(nb, np.uint8)
+    bocc[np.argpartition(rng.random(nb), kb)[:kb]] = 1
+    return socc, bocc
+
+
+def cpu_sample(Lsz, ps, pb, socc, bocc, nthreads, cg_iters, full_iters):
+    """every thread runs one realization's bounded sample concurrently (one realization per core):
+    union-find labeling + spanning + `cg_iters` Jacobi-PCG iterations; the solve is extrapolated to
+    `full_iters` iterations (the count the same recurrences need, measured on the GPU arm)."""
+    from oracle import pyoracle as O
+    m = n = Lsz
+    b1, b2 = O.bondlist(O.SQUARE, m, n, 0)
+    out = [None] * nthreads
+
+    def work(k):
+        t0 = time.perf_counter()
+        ws, wb, wsz, ncl, wmax = O.label_uf(O.MIXED, O.SQUARE, m, n, 0, b1, b2, site_occ=socc, bond_occ=bocc)
+        ids = O.spanning(O.MIXED, m, n, b1, b2, ws, wb)
+        t_label = time.perf_counter() - t0
+        cid = int(ids[0]) if len(ids) else int(np.argmax(wsz))
+        w = O.weights(O.MIXED, b1, b2, ws, wb, cid)
+        t_cg = O.cg_time_iters(m, n, b1, b2, w, cg_iters)
+        out[k] = (t_label, t_cg / cg_iters)
+
+    ths = [threading.Thread(target=work, args=(k,)) for k in range(nthreads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    wall = time.perf_counter() - t0
+    t_label = float(np.mean([o[0] for o in out]))
+    t_iter = float(np.mean([o[1] for o in out]))
+    per_real = t_label + full_iters * t_iter
+    return {"value": nthreads / per_real, "t_label_s": t_label, "t_iter_s": t_iter, "sample_wall_s": wall}
+
+
+def full_iters_hint():
+    try:
+        with open(ITERS_FILE) as f:
+            d = json.load(f)
+        return int(d["mean_iters"]), "profiles/bench_iters.json (GPU arm, same recurrences)"
+    except Exception:
+        return 67000, "documented constant (DESIGN.md)"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Lsz = args.L
+    t, nb = Lsz * Lsz, 2 * Lsz * Lsz - 2 * Lsz
+    ks, kb = int(args.ps * t), int(args.pb * nb)
+    nthreads = max(1, min(os.cpu_count() or 1, args.cpu_threads))
+    iters, src = full_iters_hint()
+    rng = np.random.default_rng(SEED)
+    vals, t0 = [], None
+    for step in range(args.warmup + args.steps):
+        socc, bocc = host_occupancy(rng, t, nb, ks, kb)
+        if step == args.warmup:
+            t0 = time.perf_counter()
+        r = cpu_sample(Lsz, args.ps, args.pb, socc, bocc, nthreads, args.cpu_cg_iters, iters)
+        if step >= args.warmup:
+            vals.append(r)
+    wall = time.perf_counter() - t0
+    value = float(np.mean([v["value"] for v in vals]))
+    sample = ("per step and per thread: union-find labeling + spanning of one L=%d realization (%.2f s) + %d "
+              "Jacobi-PCG iterations (%.3f s/iter), solve extrapolated to %d iterations [%s]; C port of the "
+              "reference algorithm, gcc -O2 (no Fortran compiler in the image)"
+              % (Lsz, vals[-1]["t_label_s"], args.cpu_cg_iters, vals[-1]["t_iter_s"], iters, src))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * nthreads / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "bench_wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": "C3 square mixed site/bond L=%d, ps=%.2f, pb=%.2f, labeling+spanning+Kirchhoff PCG"
+                        % (args.L, args.ps, args.pb),
+            "lattice": "square", "L": args.L, "ps": args.ps, "pb": args.pb, "tol": args.tol,
+            "occupancy": "Philox-4x32-10 exact-count generator, one stream per realization",
+            "l2": "per-iteration working set %.2f GB > 126 MB L2 (no flush needed)" % (5 * 8 * args.L * args.L / 1e9),
+            "parallelism": "realizations sharded over %d GPU(s), one final NCCL all-reduce of statistics" % args.gpus}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import percolation_b200 as P
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    Lsz = args.L
+    L = P.Lattice(P.SQUARE, Lsz, Lsz, 0, device=local)
+    t, nb = L.t, L.nb
+    ks, kb = int(args.ps * t), int(args.pb * nb)
+    lib = P.load()
+    sptr = C.c_uint64(0)
+    lib.perc_stream(C.byref(L._h), C.byref(sptr))
+    ext = torch.cuda.ExternalStream(sptr.value, device=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stats = {"G": [], "iters": [], "spmv_ms": [], "upd_ms": [], "ccl_ms": [], "pcg_ms": [], "nspan": []}
+
+    def step(i, record):
+        L.generate(SEED, rank * 1000003 + i, ks, kb)
+        L.label(P.MIXED)
+        ph = L.phase_ms().copy()
+        r = L.conduct(0, tol=args.tol, itmax=args.itmax)
+        ph2 = L.phase_ms()
+        if record:
+            stats["G"].append(0.5 * (r["Gtop"] + r["Gbot"]))
+            stats["iters"].append(r["iter"])
+            stats["ccl_ms"].append(float(ph[1] + ph[2] + ph[3]))
+            stats["spmv_ms"].append(float(ph2[6]))
+            stats["upd_ms"].append(float(ph2[7]))
+            stats["pcg_ms"].append(float(ph2[5]))
+        return r
+
+    for i in range(args.warmup):
+        step(i, False)
+    clocks = ClockSampler(local)
+    launches0 = L.launch_count()
+    barrier()
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for i in range(args.steps):
+        step(args.warmup + i, True)
+    e1.record(ext)
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    launches = L.launch_count() - launches0
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+
+    # ---- e2e: the same realization pipeline through the reference-shaped C-ABI calls with HOST
+    # buffers: orders uploaded from pinned host memory, labels / sizes / G read back every step
+    rng = np.random.default_rng(SEED + rank)
+    b1, b2 = P.geom_bondlist(P.SQUARE, Lsz, Lsz, 0)
+    pin = lambda n_, dt: torch.empty(n_, dtype=dt, pin_memory=True)
+    h_sorder, h_border = pin(t, torch.int32), pin(2 * nb, torch.int32)
+    h_s, h_b3, h_c = pin(t, torch.int32), pin(nb, torch.int32), pin(t, torch.int32)
+    ip = lambda ten: C.cast(ten.data_ptr(), C.POINTER(C.c_int32))
+    i32 = lambda v: C.byref(C.c_int32(int(v)))
+    f64 = lambda v: C.byref(C.c_double(float(v)))
+    e2e_steps = args.e2e_steps if args.e2e_steps >= 0 else args.steps
+    e2e_val, e2e_G = None, []
+    if e2e_steps > 0:
+        perms = []
+        for i in range(e2e_steps):
+            perms.append((rng.permutation(t).astype(np.int32) + 1, rng.permutation(nb)))
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            so, bp = perms[i]
+            h_sorder.numpy()[:] = so                       # the driver's shuffled orders (host side)
+            h_border.numpy()[:nb] = b1[bp]
+            h_border.numpy()[nb:] = b2[bp]
+            mc, pc, pl = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+            rc = lib.perc_sitebond(C.byref(L._h), ip(h_sorder), i32(ks), ip(h_border), i32(kb),
+                                   ip(h_s), ip(h_b3), ip(h_c), C.byref(mc), C.byref(pc), C.byref(pl))
+            assert rc == 0, rc
+            Gt, Gb, er, it = C.c_double(0), C.c_double(0), C.c_double(0), C.c_int32(0)
+            rc = lib.perc_conduct(C.byref(L._h), i32(0), f64(1.0), f64(1.0), f64(1e-12), f64(args.tol),
+                                  i32(args.itmax), f64(1e-10), C.byref(Gt), C.byref(Gb), C.byref(it), C.byref(er))
+            assert rc == 0, rc
+            e2e_G.append(0.5 * (Gt.value + Gb.value))
+        torch.cuda.synchronize()
+        el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        e2e_val = world * e2e_steps / float(el.item())
+
+    # ---- statistics: one NCCL all-reduce (sum G, sum G^2, count, iterations)
+    st = torch.tensor([sum(stats["G"]), sum(g * g for g in stats["G"]), len(stats["G"]), sum(stats["iters"])],
+                      dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(st, op=dist.ReduceOp.SUM)
+    st = st.tolist()
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        interior = t - 2 * Lsz
+        spmv_ms = float(np.mean(stats["spmv_ms"]))
+        upd_ms = float(np.mean(stats["upd_ms"]))
+        ccl_ms = float(np.mean(stats["ccl_ms"]))
+        spmv_bytes = 33.0 * interior          # r 8 + p_old 8 + conduct byte 1 read; p 8 + q 8 written
+        upd_bytes = 49.0 * interior           # x, p, r, q read (32) + byte; x, r written (16)
+        ach = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+        value = world * args.steps / (ms_total * 1e-3)
+        mean_iters = st[3] / max(st[2], 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "clocks": clk,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 4 * t + 8 * nb,
+                    "d2h_bytes_per_step": 8 * t + 4 * nb + 64, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "pcg_spmv_kernel (fused p-update + 5-point SpMV + dot)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
+                         "avg_launch_ms": spmv_ms},
+            "extra": {
+                "pcg_update_kernel": {"achieved_gbs": upd_bytes / (upd_ms * 1e-3) / 1e9,
+                                      "frac": upd_bytes / (upd_ms * 1e-3) / 1e9 / peak, "avg_launch_ms": upd_ms},
+                "ccl": {"gsites_per_s": t / (ccl_ms * 1e-3) / 1e9, "ms": ccl_ms,
+                        "achieved_gbs": 5.0 * t / (ccl_ms * 1e-3) / 1e9, "frac": 5.0 * t / (ccl_ms * 1e-3) / 1e9 / peak},
+                "mean_pcg_iterations": mean_iters, "mean_G": st[0] / max(st[2], 1),
+                "pcg_ms_per_iteration": float(np.mean(stats["pcg_ms"])) / max(np.mean(stats["iters"]), 1),
+                "realizations": int(st[2]),
+            },
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            socc, bocc = L.get_occupancy()
+            nthreads = max(1, min(os.cpu_count() or 1, args.cpu_threads))
+            r = cpu_sample(Lsz, args.ps, args.pb, socc, bocc, nthreads, args.cpu_cg_iters, int(round(mean_iters)))
+            line["cpu_baseline"] = {
+                "value": r["value"], "unit": UNIT, "cores": nthreads, "kind": "port",
+                "sample": ("per thread: union-find labeling + spanning of the last timed realization (%.2f s) + %d "
+                           "Jacobi-PCG iterations (%.3f s/iter) extrapolated to the %d iterations the GPU solve "
+                           "took; C port of the reference algorithm, gcc -O2 (no Fortran compiler in the image)"
+                           % (r["t_label_s"], args.cpu_cg_iters, r["t_iter_s"], int(round(mean_iters))))}
+            try:
+                os.makedirs(os.path.dirname(ITERS_FILE), exist_ok=True)
+                with open(ITERS_FILE, "w") as f:
+                    json.dump({"mean_iters": int(round(mean_iters)), "L": Lsz, "ps": args.ps, "pb": args.pb,
+                               "tol": args.tol}, f)
+            except Exception:
+                pass
+        print(json.dumps(line), flush=True)
+    L.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--L", type=int, default=4096)
+    ap.add_argument("--ps", type=float, default=0.80)
+    ap.add_argument("--pb", type=float, default=0.70)
+    ap.add_argument("--tol", type=float, default=1e-10)
+    ap.add_argument("--itmax", type=int, default=2000000)
+    ap.add_argument("--e2e-steps", type=int, default=-1)
+    ap.add_argument("--cpu-threads", type=int, default=8)
+    ap.add_argument("--cpu-cg-iters", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
