@@ -21,11 +21,18 @@ namespace perc {
 // ------------------------------------------------------------------------------------------
 // union-find primitives (parents always point to a smaller index; the root is the minimum)
 // ------------------------------------------------------------------------------------------
+// find with path halving.  The plain store races benignly with atomicMin linking: it only ever
+// writes an ancestor of `a`, and a failed atomicMin keeps uniting the displaced parent.
 __device__ __forceinline__ int sm_find(volatile int* lab, int a)
 {
-    int p;
-    while ((p = lab[a]) != a) a = p;
-    return a;
+    for (;;) {
+        int p = lab[a];
+        if (p == a) return a;
+        int gp = lab[p];
+        if (gp == p) return p;
+        lab[a] = gp;
+        a = gp;
+    }
 }
 
 __device__ __forceinline__ void sm_unite(int* lab, int a, int b)

@@ -99,8 +99,11 @@ __device__ __forceinline__ double block_sum(double v, double* sh)
 __device__ __forceinline__ bool last_block(unsigned* ticket)
 {
     __shared__ unsigned s_last;
-    __threadfence();
-    if (threadIdx.x == 0) s_last = atomicInc(ticket, gridDim.x * gridDim.y - 1) == gridDim.x * gridDim.y - 1;
+    if (threadIdx.x == 0) {
+        __threadfence();          // publish this block's partial (written by thread 0) before taking a ticket
+        s_last = atomicInc(ticket, gridDim.x * gridDim.y - 1) == gridDim.x * gridDim.y - 1;
+        __threadfence();
+    }
     __syncthreads();
     return s_last != 0;
 }
@@ -252,6 +255,202 @@ pcg_update_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, doub
 }
 
 // ------------------------------------------------------------------------------------------
+// K6/K7, vectorised variants (even m): 2 sites per thread with 128-bit accesses, (d, 1/d) from a
+// 64-entry shared table indexed by (#conducting, #leak) bonds instead of an fp64 division, and a
+// constant neighbourhood for tiles that do not touch the lattice boundary.
+// ------------------------------------------------------------------------------------------
+constexpr int S2_TX = 128, S2_TY = 32, S2_THREADS = 256, S2_LD = S2_TX + 4;
+
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+
+__device__ __forceinline__ void fill_dtab(double2* tab, const PcgParams& prm)
+{
+    if (threadIdx.x < 64) {
+        int nc = threadIdx.x >> 3, nl = threadIdx.x & 7;
+        double d = (double)nc * prm.g0 + (double)nl * prm.gleak;
+        tab[threadIdx.x] = make_double2(d, d > 0.0 ? 1.0 / d : 0.0);
+    }
+}
+
+template <int LAT>
+__device__ __forceinline__ unsigned interior_ex(int gx)
+{
+    if (LAT == LAT_SQUARE) return NB_E | NB_N | NB_W | NB_S;
+    return (gx & 1) ? (NB_E | NB_N | NB_W | NB_S | NB_SW | NB_SE) : (NB_E | NB_N | NB_W | NB_S | NB_NW | NB_NE);
+}
+
+template <int LAT>
+__global__ void __launch_bounds__(S2_THREADS)
+pcg_spmv2_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, const double* __restrict__ vr,
+                 const double* __restrict__ vp_old, double* __restrict__ vp, double* __restrict__ vq,
+                 double* __restrict__ partial, PcgState* __restrict__ st)
+{
+    if (st->done) return;
+    __shared__ __align__(16) double pn[(S2_TY + 2) * S2_LD];
+    __shared__ double2 tab[64];
+    __shared__ double sh[32];
+    const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
+    fill_dtab(tab, prm);
+    const double bk = st->bk;
+    // tiles are swept from the END of the lattice to its start: the update kernel sweeps forward, so
+    // each kernel starts on the data the previous one touched last (still resident in the 126 MB L2)
+    const int bx = gridDim.x - 1 - blockIdx.x, by = gridDim.y - 1 - blockIdx.y;
+    const int x0 = bx * S2_TX, y0 = by * S2_TY;
+    // every cell of tile + halo has its full neighbourhood inside the lattice
+    const bool interior = x0 >= 2 && x0 + S2_TX <= g.m - 2 && y0 >= 2 && y0 + S2_TY <= g.n - 2;
+    __syncthreads();
+
+    auto scalar_pn = [&](int hx, int gy) -> double {
+        int64_t j = (int64_t)gy * g.m + hx;
+        unsigned cf = cfull[j];
+        unsigned ex = interior ? interior_ex<LAT>(hx) : neighbour_bits(g, hx, gy);
+        int nc = __popc(cf);
+        return vr[j] * tab[(nc << 3) | (__popc(ex) - nc)].y + bk * vp_old[j];
+    };
+
+    // phase 1: p_new = r / d + bk * p_old on tile + halo (p is double-buffered)
+    const int gx = x0 + 2 * tx;
+    for (int ly = ty - 1; ly <= S2_TY; ly += S2_THREADS / 64) {
+        const int gy = y0 + ly;
+        const bool rowok = gy >= 1 && gy < g.n - 1;
+        double2 v = make_double2(0.0, 0.0);
+        if (rowok) {
+            if (gx < g.m) {
+                int64_t i = (int64_t)gy * g.m + gx;
+                double2 r2 = ld2(vr + i), p2 = ld2(vp_old + i);
+                uchar2 c2 = *reinterpret_cast<const uchar2*>(cfull + i);
+                unsigned e0 = interior ? interior_ex<LAT>(gx) : neighbour_bits(g, gx, gy);
+                unsigned e1 = interior ? interior_ex<LAT>(gx + 1) : neighbour_bits(g, gx + 1, gy);
+                int n0 = __popc((unsigned)c2.x), n1 = __popc((unsigned)c2.y);
+                v.x = r2.x * tab[(n0 << 3) | (__popc(e0) - n0)].y + bk * p2.x;
+                v.y = r2.y * tab[(n1 << 3) | (__popc(e1) - n1)].y + bk * p2.y;
+            } else if (gx == g.m && g.pbc) {
+                v.x = scalar_pn(0, gy);                     // partial tile: wrapped right neighbour of x = m-1
+            }
+        }
+        st2(&pn[(ly + 1) * S2_LD + 2 + 2 * tx], v);
+    }
+    // halo columns x0-1 and x0+S2_TX: one cell per thread
+    if (tid < 2 * (S2_TY + 2)) {
+        const int side = tid >= S2_TY + 2, ly = tid - side * (S2_TY + 2) - 1;
+        const int gy = y0 + ly;
+        int hx = side ? x0 + S2_TX : x0 - 1;
+        if (g.pbc) { if (hx == -1) hx = g.m - 1; else if (hx == g.m) hx = 0; }
+        double hv = 0.0;
+        if (gy >= 1 && gy < g.n - 1 && hx >= 0 && hx < g.m) hv = scalar_pn(hx, gy);
+        pn[(ly + 1) * S2_LD + (side ? S2_TX + 2 : 1)] = hv;
+    }
+    __syncthreads();
+
+    // phase 2: q = A p_new, dot(p_new, q)
+    const double dg = prm.g0 - prm.gleak;
+    double dot = 0.0;
+    for (int ly = ty; ly < S2_TY; ly += S2_THREADS / 64) {
+        const int gy = y0 + ly;
+        if (gy < 1 || gy >= g.n - 1 || gx >= g.m) continue;
+        int64_t i = (int64_t)gy * g.m + gx;
+        uchar2 c2 = *reinterpret_cast<const uchar2*>(cfull + i);
+        const unsigned cf0 = c2.x, cf1 = c2.y;
+        const double* c = &pn[(ly + 1) * S2_LD + 2 + 2 * tx];
+        const double2 cc = ld2(c), up = ld2(c + S2_LD), dn = ld2(c - S2_LD);
+        const double lf = c[-1], rt = c[2];
+        unsigned e0, e1;
+        double all0, all1;
+        if (interior) {
+            e0 = interior_ex<LAT>(gx); e1 = interior_ex<LAT>(gx + 1);
+            all0 = (cc.y + lf) + (up.x + dn.x);
+            all1 = (rt + cc.x) + (up.y + dn.y);
+            if (LAT == LAT_TRIANGULAR) { all0 += c[S2_LD - 1] + up.y; all1 += dn.x + c[-S2_LD + 2]; }
+        } else {
+            e0 = neighbour_bits(g, gx, gy); e1 = neighbour_bits(g, gx + 1, gy);
+            all0 = 0.0; all1 = 0.0;
+            if (e0 & NB_E) all0 += cc.y;  if (e0 & NB_W) all0 += lf;  if (e0 & NB_N) all0 += up.x;  if (e0 & NB_S) all0 += dn.x;
+            if (e1 & NB_E) all1 += rt;    if (e1 & NB_W) all1 += cc.x; if (e1 & NB_N) all1 += up.y; if (e1 & NB_S) all1 += dn.y;
+            if (LAT == LAT_TRIANGULAR) {
+                if (e0 & NB_NW) all0 += c[S2_LD - 1]; if (e0 & NB_NE) all0 += up.y;
+                if (e1 & NB_SW) all1 += dn.x;         if (e1 & NB_SE) all1 += c[-S2_LD + 2];
+            }
+        }
+        double con0 = 0.0, con1 = 0.0;            // conducting neighbours (cfull bits only on existing bonds)
+        if (cf0 & NB_E) con0 += cc.y;  if (cf0 & NB_W) con0 += lf;   if (cf0 & NB_N) con0 += up.x;  if (cf0 & NB_S) con0 += dn.x;
+        if (cf1 & NB_E) con1 += rt;    if (cf1 & NB_W) con1 += cc.x; if (cf1 & NB_N) con1 += up.y;  if (cf1 & NB_S) con1 += dn.y;
+        if (LAT == LAT_TRIANGULAR) {
+            if (cf0 & NB_NW) con0 += c[S2_LD - 1]; if (cf0 & NB_NE) con0 += up.y;
+            if (cf1 & NB_SW) con1 += dn.x;         if (cf1 & NB_SE) con1 += c[-S2_LD + 2];
+        }
+        int n0 = __popc(cf0), n1 = __popc(cf1);
+        double d0 = tab[(n0 << 3) | (__popc(e0) - n0)].x, d1 = tab[(n1 << 3) | (__popc(e1) - n1)].x;
+        double2 q;
+        q.x = d0 * cc.x - (prm.gleak * all0 + dg * con0);
+        q.y = d1 * cc.y - (prm.gleak * all1 + dg * con1);
+        st2(vp + i, cc);
+        st2(vq + i, q);
+        dot += cc.x * q.x + cc.y * q.y;
+    }
+    double bs = block_sum(dot, sh);
+    int bid = by * gridDim.x + bx;
+    if (threadIdx.x == 0) partial[bid] = bs;
+    if (last_block(&st->ticket_a)) {
+        double tot = fold_partials(partial, gridDim.x * gridDim.y, 1, 0, sh);
+        if (threadIdx.x == 0) { st->akden = tot; st->ak = st->bknum / tot; }
+    }
+}
+
+// K7 vectorised: pairs of sites, rows 1..n-2 as one linear range (m even -> 16-byte aligned)
+template <int LAT>
+__global__ void __launch_bounds__(UP_THREADS)
+pcg_update2_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double* __restrict__ vx,
+                   double* __restrict__ vr, const double* __restrict__ vp, const double* __restrict__ vq,
+                   double* __restrict__ partial, PcgState* __restrict__ st, int keep_x)
+{
+    if (st->done) return;
+    __shared__ double2 tab[64];
+    __shared__ double sh[32];
+    fill_dtab(tab, prm);
+    __syncthreads();
+    const double ak = st->ak;
+    double s_rz = 0.0, s_rr = 0.0;
+    const int64_t lo = g.m, hi = g.t - g.m;
+    const int64_t npair = (hi - lo) >> 1;
+    const int hm = g.m >> 1;
+    // grid-stride: the whole grid sweeps the vectors front to back (fixed assignment -> deterministic sums)
+    for (int64_t k = (int64_t)blockIdx.x * UP_THREADS + threadIdx.x; k < npair; k += (int64_t)gridDim.x * UP_THREADS) {
+        const int64_t i = lo + 2 * k;
+        double2 p = ld2(vp + i), q = ld2(vq + i), r = ld2(vr + i);
+        uchar2 c2 = *reinterpret_cast<const uchar2*>(cfull + i);
+        r.x -= ak * q.x; r.y -= ak * q.y;
+        st2(vr + i, r);
+        if (keep_x) {
+            double2 x = ld2(vx + i);
+            x.x += ak * p.x; x.y += ak * p.y;
+            st2(vx + i, x);
+        }
+        // neighbourhood size: only the lattice boundary columns / rows 1 and n-2 differ from the bulk
+        int xx = (int)((k % hm) << 1), y = (int)(i / g.m);
+        unsigned e0, e1;
+        if (xx >= 2 && xx + 2 < g.m && y >= 1 && y + 1 < g.n) { e0 = interior_ex<LAT>(xx); e1 = interior_ex<LAT>(xx + 1); }
+        else { e0 = neighbour_bits(g, xx, y); e1 = neighbour_bits(g, xx + 1, y); }
+        int n0 = __popc((unsigned)c2.x), n1 = __popc((unsigned)c2.y);
+        s_rz += r.x * r.x * tab[(n0 << 3) | (__popc(e0) - n0)].y + r.y * r.y * tab[(n1 << 3) | (__popc(e1) - n1)].y;
+        s_rr += r.x * r.x + r.y * r.y;
+    }
+    double a = block_sum(s_rz, sh), c = block_sum(s_rr, sh);
+    if (threadIdx.x == 0) { partial[blockIdx.x * 2 + 0] = a; partial[blockIdx.x * 2 + 1] = c; }
+    if (last_block(&st->ticket_b)) {
+        double fa = fold_partials(partial, gridDim.x, 2, 0, sh);
+        double fc = fold_partials(partial, gridDim.x, 2, 1, sh);
+        if (threadIdx.x == 0) {
+            int it = st->iter + 1;
+            double err = sqrt(fc) / st->bnrm;
+            st->iter = it; st->err = err; st->rr = fc;
+            st->bkden = st->bknum; st->bknum = fa; st->bk = fa / st->bkden;
+            if (!(err > st->tol) || it > st->itmax) st->done = 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K8: read-out (Sq/bondc.f:554-592): Iout = G~ V on rows 0 and n-1, G~ keeps the full
 // diagonal but only off-diagonals with |g| >= read_thresh (second sprsin, :576)
 // ------------------------------------------------------------------------------------------
@@ -295,6 +494,8 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     cudaStream_t s = c->stream;
     PcgParams prm{g0, gleak, Va, read_thresh};
     dim3 sgrid((g.m + SP_TX - 1) / SP_TX, (g.n + SP_TY - 1) / SP_TY);
+    dim3 sgrid2((g.m + S2_TX - 1) / S2_TX, (g.n + S2_TY - 1) / S2_TY);
+    const bool vec = (g.m % 2) == 0;     // 128-bit paths need even m (rows stay 16-byte aligned)
     int ugrid = 148 * 8;
     int64_t interior = g.t - 2 * (int64_t)g.m;
     if (ugrid > (interior + UP_THREADS - 1) / UP_THREADS) ugrid = (int)((interior + UP_THREADS - 1) / UP_THREADS);
@@ -313,31 +514,45 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     c->launches += 2;
     double* pold = c->vp; double* pnew = c->vp2;
     float sp_ms = 0.f, up_ms = 0.f; int nsamp = 0;
-    int chunk = 16;
+    int chunk = 16, iters_before = 0;
     for (;;) {
         for (int k = 0; k < chunk; ++k) {
-            // the first iteration of a chunk is always live (we stop launching once done is seen):
-            // bracket its two kernels with events -> average per-kernel device time
-            bool sample = (k == 0);
+            // bracket the two kernels of one mid-chunk iteration with events (the pipeline is full
+            // there, so the bracket is the kernels' own device time) -> average per-kernel time
+            bool sample = (k == chunk / 2);
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[8], s));
-            if (g.lattice == LAT_SQUARE)
+            if (vec) {
+                if (g.lattice == LAT_SQUARE)
+                    pcg_spmv2_kernel<LAT_SQUARE><<<sgrid2, S2_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vq, c->partial, c->d_pcg);
+                else
+                    pcg_spmv2_kernel<LAT_TRIANGULAR><<<sgrid2, S2_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vq, c->partial, c->d_pcg);
+            } else if (g.lattice == LAT_SQUARE)
                 pcg_spmv_kernel<LAT_SQUARE><<<sgrid, SP_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vq, c->partial, c->d_pcg);
             else
                 pcg_spmv_kernel<LAT_TRIANGULAR><<<sgrid, SP_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vq, c->partial, c->d_pcg);
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[9], s));
-            pcg_update_kernel<<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, pnew, c->vq, c->partial, c->d_pcg);
+            if (vec) {
+                if (g.lattice == LAT_SQUARE)
+                    pcg_update2_kernel<LAT_SQUARE><<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, pnew, c->vq, c->partial, c->d_pcg, 1);
+                else
+                    pcg_update2_kernel<LAT_TRIANGULAR><<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, pnew, c->vq, c->partial, c->d_pcg, 1);
+            } else
+                pcg_update_kernel<<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, pnew, c->vq, c->partial, c->d_pcg);
             { double* tmp = pold; pold = pnew; pnew = tmp; }
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[10], s));
             c->launches += 2;
         }
         PERC_CUDA(cudaMemcpyAsync(c->h_pcg, c->d_pcg, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
         PERC_CUDA(cudaStreamSynchronize(s));
-        {
+        // a sample is valid if the solve was still live when it ran (always true for a chunk that
+        // ended not-done; for the final chunk only if it finished after the sampled iteration)
+        if (!c->h_pcg->done || c->h_pcg->iter > iters_before + chunk / 2) {
             float a = 0.f, b = 0.f;
             cudaEventElapsedTime(&a, c->ev[8], c->ev[9]);
             cudaEventElapsedTime(&b, c->ev[9], c->ev[10]);
             sp_ms += a; up_ms += b; nsamp++;
         }
+        iters_before = c->h_pcg->iter;
         if (c->h_pcg->done) break;
         if (chunk < 256) chunk *= 2;
     }
