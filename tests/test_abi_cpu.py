@@ -62,3 +62,20 @@ def test_no_device_fails_loudly(P):
         pytest.skip("a GPU is present")
     with pytest.raises(P.PercError):
         P.Lattice(1, 8, 8)
+
+
+def _build_c_driver(tmpdir):
+    import subprocess
+    exe = os.path.join(tmpdir, "abi_c_driver")
+    so_dir = os.path.join(ROOT, "percolation_b200")
+    subprocess.check_call(["gcc", "-O2", "-o", exe, os.path.join(ROOT, "tests", "abi_c_driver.c"),
+                           "-L" + so_dir, "-lperc_b200", "-Wl,-rpath," + so_dir])
+    return exe
+
+
+def test_c_driver_links_and_geometry(P, tmp_path):
+    """a C driver written with Fortran calling conventions links against the C-ABI"""
+    import subprocess
+    exe = _build_c_driver(str(tmp_path))
+    out = subprocess.run([exe, "geometry-only"], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("OK geometry"), out.stdout + out.stderr

@@ -359,3 +359,12 @@ def test_full_size_properties_L4096(P):
         L.set_fill(kb=int(0.45 * nb))
         L.label(P.MIXED)
         assert L.summary()["nspan"] == 0 and sp_hi >= 1
+
+
+def test_c_driver_full_path(P, tmp_path):
+    """Fortran-convention C driver: enumerate, shuffle, perc_bond, perc_conduct"""
+    import subprocess
+    from test_abi_cpu import _build_c_driver
+    exe = _build_c_driver(str(tmp_path))
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("OK nb="), out.stdout + out.stderr
