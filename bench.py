@@ -195,6 +195,7 @@ def workload_config(args):
 def run_ours(args):
     import torch
     import percolation_b200 as P
+    from percolation_b200.shard import Stats, stream_id
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -223,7 +224,7 @@ def run_ours(args):
     stats = {"G": [], "iters": [], "spmv_ms": [], "upd_ms": [], "ccl_ms": [], "pcg_ms": [], "nspan": []}
 
     def step(i, record):
-        L.generate(SEED, rank * 1000003 + i, ks, kb)
+        L.generate(SEED, stream_id(rank, i), ks, kb)
         L.label(P.MIXED)
         ph = L.phase_ms().copy()
         r = L.conduct(0, tol=args.tol, itmax=args.itmax)
@@ -295,12 +296,13 @@ def run_ours(args):
             dist.all_reduce(el, op=dist.ReduceOp.MAX)
         e2e_val = world * e2e_steps / float(el.item())
 
-    # ---- statistics: one NCCL all-reduce (sum G, sum G^2, count, iterations)
-    st = torch.tensor([sum(stats["G"]), sum(g * g for g in stats["G"]), len(stats["G"]), sum(stats["iters"])],
-                      dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(st, op=dist.ReduceOp.SUM)
-    st = st.tolist()
+    # ---- statistics: one NCCL all-reduce of the statistics block (multi-GPU mode 1)
+    merged = Stats()
+    for G_, it_ in zip(stats["G"], stats["iters"]):
+        merged.add(G=G_, iters=it_, spans=True)
+    merged.allreduce(dist, device="cuda")
+    sd = merged.asdict()
+    st = [sd["sum_G"], sd["sum_G2"], sd["count"], sd["iters"]]
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
