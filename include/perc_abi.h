@@ -114,6 +114,14 @@ int32_t perc_first_span(const int64_t *h, const int32_t *kind, const int32_t *wh
 int32_t perc_conduct(const int64_t *h, const int32_t *cluster_id, const double *Va, const double *g0,
                      const double *gleak, const double *tol, const int32_t *itmax, const double *read_thresh,
                      double *Gtop, double *Gbot, int32_t *iter, double *err);
+/* same solve for the p-sweep drivers (Sq/bond_cond.f:392-485), which only write pb, Gbot, Gtop, avg
+ * (:481-482): the iterate x is kept on rows 1 and n-2 only -- the rows the read-out G~.V (:576-592)
+ * consumes -- so Gtop / Gbot / iter / err are bit-identical to perc_conduct while the interior
+ * voltages are not formed (16 B per site and iteration less HBM traffic).  perc_get_voltage is not
+ * available after this call (PERC_E_STATE). */
+int32_t perc_conduct_g(const int64_t *h, const int32_t *cluster_id, const double *Va, const double *g0,
+                       const double *gleak, const double *tol, const int32_t *itmax, const double *read_thresh,
+                       double *Gtop, double *Gbot, int32_t *iter, double *err);
 int32_t perc_get_voltage(const int64_t *h, double *Vint);             /* Vint(t-2m), Sq/bondc.f:545 */
 
 /* ---- instrumentation ---------------------------------------------------------------------------- */

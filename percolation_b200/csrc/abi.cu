@@ -52,15 +52,15 @@ int ctx_alloc(Ctx* c)
     PERC_CUDA(cudaMalloc(&c->mask, t));
     PERC_CUDA(cudaMalloc(&c->label, sizeof(int32_t) * t));
     PERC_CUDA(cudaMalloc(&c->size, sizeof(int32_t) * t));
-    PERC_CUDA(cudaMalloc(&c->span_mark, sizeof(int32_t) * t));
-    PERC_CUDA(cudaMalloc(&c->span_ids, sizeof(int32_t) * MAX_SPAN));
+    PERC_CUDA(cudaMalloc(&c->rootlist, sizeof(int32_t) * t));
     PERC_CUDA(cudaMalloc(&c->d_sum, sizeof(Summary)));
+    PERC_CUDA(cudaMallocHost(&c->h_sum_pin, sizeof(Summary)));
+    PERC_CUDA(cudaMemsetAsync(c->d_sum, 0, sizeof(Summary), c->stream));
     PERC_CUDA(cudaMalloc(&c->d_pcg, sizeof(PcgState)));
     PERC_CUDA(cudaMallocHost(&c->h_pcg, sizeof(PcgState)));
     PERC_CUDA(cudaMalloc(&c->d_hist, sizeof(unsigned long long) * (4096 + 8)));
     c->cand_cap = 8192;
     PERC_CUDA(cudaMalloc(&c->d_cand, sizeof(unsigned long long) * 2 * c->cand_cap));
-    PERC_CUDA(cudaMemsetAsync(c->span_mark, 0, sizeof(int32_t) * t, c->stream));
     PERC_CUDA(cudaMemsetAsync(c->srank, 0x7f, sizeof(int32_t) * t, c->stream));
     PERC_CUDA(cudaMemsetAsync(c->brank, 0x7f, sizeof(int32_t) * t * c->g.ndir, c->stream));
     for (auto& e : c->ev) PERC_CUDA(cudaEventCreate(&e));
@@ -77,7 +77,7 @@ static int ensure_pcg(Ctx* c)
     PERC_CUDA(cudaMalloc(&c->vr, sizeof(double) * t));
     PERC_CUDA(cudaMalloc(&c->vp, sizeof(double) * t));
     PERC_CUDA(cudaMalloc(&c->vp2, sizeof(double) * t));
-    PERC_CUDA(cudaMalloc(&c->vq, sizeof(double) * t));
+    if (c->g.m & 1) PERC_CUDA(cudaMalloc(&c->vq, sizeof(double) * t));     // only the odd-m fallback stores q = A p
     return 0;
 }
 
@@ -85,10 +85,11 @@ void ctx_free(Ctx* c)
 {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    void* ptrs[] = {c->srank, c->brank, c->mask, c->label, c->size, c->span_mark, c->span_ids, c->d_sum, c->d_pcg,
+    void* ptrs[] = {c->srank, c->brank, c->mask, c->label, c->size, c->rootlist, c->d_sum, c->d_pcg,
                     c->d_hist, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vp2, c->vq, c->partial, c->d_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_pcg) cudaFreeHost(c->h_pcg);
+    if (c->h_sum_pin) cudaFreeHost(c->h_sum_pin);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -318,7 +319,7 @@ int32_t perc_get_sizes(const int64_t* h, int32_t* cs)
 {
     GET_CTX(h);
     if (!c->labeled || !cs) return PERC_E_STATE;
-    return download(c, cs, c->size, sizeof(int32_t) * c->g.t);
+    return ccl_export_sizes(c, cs);
 }
 
 int32_t perc_span(const int64_t* h, const int32_t* max_ids, int32_t* nspan, int32_t* ids, int32_t* sizes)
@@ -362,7 +363,7 @@ int32_t perc_site(const int64_t* h, const int32_t* order, const int32_t* k,
     rc = ccl_run(c, KIND_SITE);
     if (rc) return rc;
     if (s) { rc = download(c, s, c->label, sizeof(int32_t) * c->g.t); if (rc) return rc; }
-    if (cs) { rc = download(c, cs, c->size, sizeof(int32_t) * c->g.t); if (rc) return rc; }
+    if (cs) { rc = ccl_export_sizes(c, cs); if (rc) return rc; }
     return finish_label(c, maxcs, perccln, perccls);
 }
 
@@ -378,7 +379,7 @@ int32_t perc_bond(const int64_t* h, const int32_t* border, const int32_t* k,
     rc = ccl_run(c, KIND_BOND);
     if (rc) return rc;
     if (b3) { rc = ccl_export_bond_labels(c, b3); if (rc) return rc; }
-    if (cs) { rc = download(c, cs, c->size, sizeof(int32_t) * c->g.t); if (rc) return rc; }
+    if (cs) { rc = ccl_export_sizes(c, cs); if (rc) return rc; }
     return finish_label(c, maxcs, perccln, perccls);
 }
 
@@ -398,7 +399,7 @@ int32_t perc_sitebond(const int64_t* h, const int32_t* sorder, const int32_t* ks
     if (rc) return rc;
     if (s) { rc = download(c, s, c->label, sizeof(int32_t) * c->g.t); if (rc) return rc; }
     if (b3) { rc = ccl_export_bond_labels(c, b3); if (rc) return rc; }
-    if (cs) { rc = download(c, cs, c->size, sizeof(int32_t) * c->g.t); if (rc) return rc; }
+    if (cs) { rc = ccl_export_sizes(c, cs); if (rc) return rc; }
     return finish_label(c, maxcs, perccln, perccls);
 }
 
@@ -441,11 +442,10 @@ int32_t perc_first_span(const int64_t* h, const int32_t* kind, const int32_t* wh
     return finish_label(c, maxcs, nullptr, perccls);
 }
 
-int32_t perc_conduct(const int64_t* h, const int32_t* cluster_id, const double* Va, const double* g0,
-                     const double* gleak, const double* tol, const int32_t* itmax, const double* read_thresh,
-                     double* Gtop, double* Gbot, int32_t* iter, double* err)
+static int conduct_common(Ctx* c, const int32_t* cluster_id, const double* Va, const double* g0,
+                          const double* gleak, const double* tol, const int32_t* itmax, const double* read_thresh,
+                          int keep_x, double* Gtop, double* Gbot, int32_t* iter, double* err)
 {
-    GET_CTX(h);
     if (!cluster_id || !Va || !g0 || !gleak || !tol || !itmax || !read_thresh || !Gtop || !Gbot || !iter || !err)
         return PERC_E_ARG;
     if (!c->labeled) return PERC_E_STATE;
@@ -462,15 +462,31 @@ int32_t perc_conduct(const int64_t* h, const int32_t* cluster_id, const double* 
     int rc = ensure_pcg(c);
     if (rc) return rc;
     int it = 0;
-    rc = pcg_solve(c, cid, *Va, *g0, *gleak, *tol, *itmax, *read_thresh, Gtop, Gbot, &it, err);
+    rc = pcg_solve(c, cid, *Va, *g0, *gleak, *tol, *itmax, *read_thresh, keep_x, Gtop, Gbot, &it, err);
     *iter = it;
     return rc;
+}
+
+int32_t perc_conduct(const int64_t* h, const int32_t* cluster_id, const double* Va, const double* g0,
+                     const double* gleak, const double* tol, const int32_t* itmax, const double* read_thresh,
+                     double* Gtop, double* Gbot, int32_t* iter, double* err)
+{
+    GET_CTX(h);
+    return conduct_common(c, cluster_id, Va, g0, gleak, tol, itmax, read_thresh, 1, Gtop, Gbot, iter, err);
+}
+
+int32_t perc_conduct_g(const int64_t* h, const int32_t* cluster_id, const double* Va, const double* g0,
+                       const double* gleak, const double* tol, const int32_t* itmax, const double* read_thresh,
+                       double* Gtop, double* Gbot, int32_t* iter, double* err)
+{
+    GET_CTX(h);
+    return conduct_common(c, cluster_id, Va, g0, gleak, tol, itmax, read_thresh, 0, Gtop, Gbot, iter, err);
 }
 
 int32_t perc_get_voltage(const int64_t* h, double* Vint)
 {
     GET_CTX(h);
-    if (!c->solved || !Vint) return PERC_E_STATE;
+    if (!c->solved || !c->have_x || !Vint) return PERC_E_STATE;
     return download(c, Vint, c->vx + c->g.m, sizeof(double) * (c->g.t - 2 * (int64_t)c->g.m));
 }
 

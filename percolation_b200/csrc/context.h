@@ -4,27 +4,11 @@
 #include <stdint.h>
 #include <vector>
 #include "geometry.cuh"
+#include "ccl_tile.cuh"
 
 namespace perc {
 
 constexpr int RANK_NONE = 0x7fffffff;
-
-// tile of the block-local CCL kernel (sites); TW must be 32 (one warp per row segment)
-constexpr int CCL_TW = 32;
-constexpr int CCL_TH = 32;
-
-// device-side summary written by the labeling pipeline
-struct Summary {
-    unsigned long long ncl;        // clusters with a site-id label
-    unsigned long long nlone;      // mixed problem: occupied bonds with no occupied end (size-1 clusters)
-    unsigned long long maxpack;    // (size << 32) | (0xffffffff - label)  -> max size, then min label
-    unsigned long long nocc_sites; // occupied sites in the mask
-    unsigned long long nocc_bonds; // occupied bonds in the mask
-    int nspan;                     // spanning clusters found
-    int span_overflow;
-};
-
-constexpr int MAX_SPAN = 4096;
 
 // PCG scalars living on the device (one solve at a time per handle)
 struct PcgState {
@@ -59,10 +43,10 @@ struct Ctx {
     // ---- realization state
     uint8_t* mask = nullptr;      // [t]
     int32_t* label = nullptr;     // [t]  parent+1 during CCL, canonical label after flatten
-    int32_t* size = nullptr;      // [t]  size by canonical label (index label-1)
-    int32_t* span_mark = nullptr; // [t]  scratch, kept zero between calls
-    int32_t* span_ids = nullptr;  // [MAX_SPAN]
+    int32_t* size = nullptr;      // [t]  cluster size at the ROOT's index (label-1); other entries undefined
+    int32_t* rootlist = nullptr;  // [t]  site indices of the tile-local roots of the last labeling
     Summary* d_sum = nullptr;
+    Summary* h_sum_pin = nullptr; // pinned mirror
     Summary h_sum{};
     std::vector<int32_t> h_span_ids, h_span_sizes;
     int kind = 0;
@@ -80,6 +64,7 @@ struct Ctx {
     PcgState* d_pcg = nullptr;
     PcgState* h_pcg = nullptr;    // pinned
     bool solved = false;
+    bool have_x = false;          // the last solve kept the interior voltages (perc_conduct, not perc_conduct_g)
 
     // ---- selection scratch
     unsigned long long* d_hist = nullptr;   // [4096 + 8]
@@ -115,9 +100,10 @@ int ccl_run(Ctx* c, int kind);
 int ccl_fetch_summary(Ctx* c);
 int ccl_hist(Ctx* c, int nbins, int64_t* hist);
 int ccl_export_bond_labels(Ctx* c, int32_t* b3);
+int ccl_export_sizes(Ctx* c, int32_t* cs);
 
 int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double tol, int itmax,
-              double read_thresh, double* Gtop, double* Gbot, int* iter, double* err);
+              double read_thresh, int keep_x, double* Gtop, double* Gbot, int* iter, double* err);
 
 #define PERC_CUDA(call)                                              \
     do {                                                             \

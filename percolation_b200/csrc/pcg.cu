@@ -10,8 +10,10 @@
 // rows 1..n-2, rows 0 / n-1 are Dirichlet (0 / Va).  One byte per site (cfull) says which of
 // its up-to-6 bonds conduct; weights and the diagonal are rebuilt from it on the fly.
 //
-//   K6  pcg_spmv_kernel    p <- r/d + bk*p (tile + halo, shared memory), q = A p, sum p.q
-//   K7  pcg_update_kernel  x += ak p, r -= ak q, sums r.r/d (next bknum) and r.r (err)
+//   K6  pcg_tile_kernel<0> p <- r/d + bk*p (tile + halo, shared memory), sum p.(A p)
+//   K7  pcg_tile_kernel<1> r -= ak (A p) with A p recomputed (q is never stored), x += ak p,
+//                          sums r.r/d (next bknum) and r.r (err)
+//       (pcg_spmv_kernel / pcg_update_kernel: scalar fallback with a stored q for odd m)
 //   K8  pcg_readout_kernel literal Gtop / Gbot incl. the 1e-10 drop rule of the 2nd sprsin
 // Reductions are two-stage and fixed-order (per-block partial, last block folds them), so a
 // solve is bit-reproducible for a given lattice size.
@@ -255,7 +257,7 @@ pcg_update_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, doub
 }
 
 // ------------------------------------------------------------------------------------------
-// K6/K7, vectorised variants (even m): 2 sites per thread with 128-bit accesses, (d, 1/d) from a
+// helpers of the vectorised kernels (even m): 2 sites per thread with 128-bit accesses, (d, 1/d) from a
 // 64-entry shared table indexed by (#conducting, #leak) bonds instead of an fp64 division, and a
 // constant neighbourhood for tiles that do not touch the lattice boundary.
 // ------------------------------------------------------------------------------------------
@@ -280,11 +282,21 @@ __device__ __forceinline__ unsigned interior_ex(int gx)
     return (gx & 1) ? (NB_E | NB_N | NB_W | NB_S | NB_SW | NB_SE) : (NB_E | NB_N | NB_W | NB_S | NB_NW | NB_NE);
 }
 
-template <int LAT>
+// ------------------------------------------------------------------------------------------
+// K6'/K7' (even m): the q = A p vector is never stored.  Both kernels stage p on tile + halo in shared
+// memory and apply the stencil; MODE 0 builds the new direction and p.Ap, MODE 1 RECOMPUTES A p to
+// update the residual once ak is known.  HBM traffic per site and iteration:
+//   MODE 0: r 8 + p_old 8 + cfull 1 read, p 8 written                      = 25 B
+//   MODE 1: p 8 + r 8 + cfull 1 read, r 8 written (+ x 8 read, 8 written)  = 25 B (41 B with keep_x)
+// against 82 B for the stored-q pair above.  The fp64 stencil is done twice; the SMs have the
+// headroom (HBM-bound either way).  keep_x = 0 keeps x only on rows 1 and n-2, the rows the read-out
+// (K8) consumes: Gtop / Gbot come out bit-identical, the interior voltages are simply not formed.
+// ------------------------------------------------------------------------------------------
+template <int LAT, int MODE>
 __global__ void __launch_bounds__(S2_THREADS)
-pcg_spmv2_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, const double* __restrict__ vr,
-                 const double* __restrict__ vp_old, double* __restrict__ vp, double* __restrict__ vq,
-                 double* __restrict__ partial, PcgState* __restrict__ st)
+pcg_tile_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double* __restrict__ vr,
+                const double* __restrict__ vp_in, double* __restrict__ vp_out, double* __restrict__ vx,
+                double* __restrict__ partial, PcgState* __restrict__ st, int keep_x)
 {
     if (st->done) return;
     __shared__ __align__(16) double pn[(S2_TY + 2) * S2_LD];
@@ -292,10 +304,11 @@ pcg_spmv2_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, const
     __shared__ double sh[32];
     const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
     fill_dtab(tab, prm);
-    const double bk = st->bk;
-    // tiles are swept from the END of the lattice to its start: the update kernel sweeps forward, so
-    // each kernel starts on the data the previous one touched last (still resident in the 126 MB L2)
-    const int bx = gridDim.x - 1 - blockIdx.x, by = gridDim.y - 1 - blockIdx.y;
+    const double bk = st->bk, ak = st->ak;
+    // MODE 0 sweeps the tiles from the END of the lattice to its start, MODE 1 front to back: each
+    // kernel starts on the data the previous one touched last (still resident in the 126 MB L2)
+    const int bx = MODE == 0 ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+    const int by = MODE == 0 ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
     const int x0 = bx * S2_TX, y0 = by * S2_TY;
     // every cell of tile + halo has its full neighbourhood inside the lattice
     const bool interior = x0 >= 2 && x0 + S2_TX <= g.m - 2 && y0 >= 2 && y0 + S2_TY <= g.n - 2;
@@ -303,13 +316,15 @@ pcg_spmv2_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, const
 
     auto scalar_pn = [&](int hx, int gy) -> double {
         int64_t j = (int64_t)gy * g.m + hx;
+        if (MODE == 1) return vp_in[j];
         unsigned cf = cfull[j];
         unsigned ex = interior ? interior_ex<LAT>(hx) : neighbour_bits(g, hx, gy);
         int nc = __popc(cf);
-        return vr[j] * tab[(nc << 3) | (__popc(ex) - nc)].y + bk * vp_old[j];
+        return vr[j] * tab[(nc << 3) | (__popc(ex) - nc)].y + bk * vp_in[j];
     };
 
-    // phase 1: p_new = r / d + bk * p_old on tile + halo (p is double-buffered)
+    // phase 1: the direction p on tile + halo.  MODE 0: p = r / d + bk * p_old (p is double-buffered:
+    // neighbouring tiles still read p_old); MODE 1: p as stored by MODE 0
     const int gx = x0 + 2 * tx;
     for (int ly = ty - 1; ly <= S2_TY; ly += S2_THREADS / 64) {
         const int gy = y0 + ly;
@@ -318,13 +333,16 @@ pcg_spmv2_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, const
         if (rowok) {
             if (gx < g.m) {
                 int64_t i = (int64_t)gy * g.m + gx;
-                double2 r2 = ld2(vr + i), p2 = ld2(vp_old + i);
-                uchar2 c2 = *reinterpret_cast<const uchar2*>(cfull + i);
-                unsigned e0 = interior ? interior_ex<LAT>(gx) : neighbour_bits(g, gx, gy);
-                unsigned e1 = interior ? interior_ex<LAT>(gx + 1) : neighbour_bits(g, gx + 1, gy);
-                int n0 = __popc((unsigned)c2.x), n1 = __popc((unsigned)c2.y);
-                v.x = r2.x * tab[(n0 << 3) | (__popc(e0) - n0)].y + bk * p2.x;
-                v.y = r2.y * tab[(n1 << 3) | (__popc(e1) - n1)].y + bk * p2.y;
+                if (MODE == 1) v = ld2(vp_in + i);
+                else {
+                    double2 r2 = ld2(vr + i), p2 = ld2(vp_in + i);
+                    uchar2 c2 = *reinterpret_cast<const uchar2*>(cfull + i);
+                    unsigned e0 = interior ? interior_ex<LAT>(gx) : neighbour_bits(g, gx, gy);
+                    unsigned e1 = interior ? interior_ex<LAT>(gx + 1) : neighbour_bits(g, gx + 1, gy);
+                    int n0 = __popc((unsigned)c2.x), n1 = __popc((unsigned)c2.y);
+                    v.x = r2.x * tab[(n0 << 3) | (__popc(e0) - n0)].y + bk * p2.x;
+                    v.y = r2.y * tab[(n1 << 3) | (__popc(e1) - n1)].y + bk * p2.y;
+                }
             } else if (gx == g.m && g.pbc) {
                 v.x = scalar_pn(0, gy);                     // partial tile: wrapped right neighbour of x = m-1
             }
@@ -343,9 +361,9 @@ pcg_spmv2_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, const
     }
     __syncthreads();
 
-    // phase 2: q = A p_new, dot(p_new, q)
+    // phase 2: q = A p; MODE 0: dot(p, q); MODE 1: r -= ak q, x += ak p, sums r.r/d and r.r
     const double dg = prm.g0 - prm.gleak;
-    double dot = 0.0;
+    double acc0 = 0.0, acc1 = 0.0;
     for (int ly = ty; ly < S2_TY; ly += S2_THREADS / 64) {
         const int gy = y0 + ly;
         if (gy < 1 || gy >= g.n - 1 || gx >= g.m) continue;
@@ -379,73 +397,48 @@ pcg_spmv2_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, const
             if (cf0 & NB_NW) con0 += c[S2_LD - 1]; if (cf0 & NB_NE) con0 += up.y;
             if (cf1 & NB_SW) con1 += dn.x;         if (cf1 & NB_SE) con1 += c[-S2_LD + 2];
         }
-        int n0 = __popc(cf0), n1 = __popc(cf1);
-        double d0 = tab[(n0 << 3) | (__popc(e0) - n0)].x, d1 = tab[(n1 << 3) | (__popc(e1) - n1)].x;
+        const int n0 = __popc(cf0), n1 = __popc(cf1);
+        const double2 t0 = tab[(n0 << 3) | (__popc(e0) - n0)], t1 = tab[(n1 << 3) | (__popc(e1) - n1)];
         double2 q;
-        q.x = d0 * cc.x - (prm.gleak * all0 + dg * con0);
-        q.y = d1 * cc.y - (prm.gleak * all1 + dg * con1);
-        st2(vp + i, cc);
-        st2(vq + i, q);
-        dot += cc.x * q.x + cc.y * q.y;
-    }
-    double bs = block_sum(dot, sh);
-    int bid = by * gridDim.x + bx;
-    if (threadIdx.x == 0) partial[bid] = bs;
-    if (last_block(&st->ticket_a)) {
-        double tot = fold_partials(partial, gridDim.x * gridDim.y, 1, 0, sh);
-        if (threadIdx.x == 0) { st->akden = tot; st->ak = st->bknum / tot; }
-    }
-}
-
-// K7 vectorised: pairs of sites, rows 1..n-2 as one linear range (m even -> 16-byte aligned)
-template <int LAT>
-__global__ void __launch_bounds__(UP_THREADS)
-pcg_update2_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double* __restrict__ vx,
-                   double* __restrict__ vr, const double* __restrict__ vp, const double* __restrict__ vq,
-                   double* __restrict__ partial, PcgState* __restrict__ st, int keep_x)
-{
-    if (st->done) return;
-    __shared__ double2 tab[64];
-    __shared__ double sh[32];
-    fill_dtab(tab, prm);
-    __syncthreads();
-    const double ak = st->ak;
-    double s_rz = 0.0, s_rr = 0.0;
-    const int64_t lo = g.m, hi = g.t - g.m;
-    const int64_t npair = (hi - lo) >> 1;
-    const int hm = g.m >> 1;
-    // grid-stride: the whole grid sweeps the vectors front to back (fixed assignment -> deterministic sums)
-    for (int64_t k = (int64_t)blockIdx.x * UP_THREADS + threadIdx.x; k < npair; k += (int64_t)gridDim.x * UP_THREADS) {
-        const int64_t i = lo + 2 * k;
-        double2 p = ld2(vp + i), q = ld2(vq + i), r = ld2(vr + i);
-        uchar2 c2 = *reinterpret_cast<const uchar2*>(cfull + i);
-        r.x -= ak * q.x; r.y -= ak * q.y;
-        st2(vr + i, r);
-        if (keep_x) {
-            double2 x = ld2(vx + i);
-            x.x += ak * p.x; x.y += ak * p.y;
-            st2(vx + i, x);
+        q.x = t0.x * cc.x - (prm.gleak * all0 + dg * con0);
+        q.y = t1.x * cc.y - (prm.gleak * all1 + dg * con1);
+        if (MODE == 0) {
+            st2(vp_out + i, cc);
+            acc0 += cc.x * q.x + cc.y * q.y;
+        } else {
+            double2 r = ld2(vr + i);
+            r.x -= ak * q.x; r.y -= ak * q.y;
+            st2(vr + i, r);
+            if (keep_x || gy == 1 || gy == g.n - 2) {
+                double2 x = ld2(vx + i);
+                x.x += ak * cc.x; x.y += ak * cc.y;
+                st2(vx + i, x);
+            }
+            acc0 += r.x * r.x * t0.y + r.y * r.y * t1.y;
+            acc1 += r.x * r.x + r.y * r.y;
         }
-        // neighbourhood size: only the lattice boundary columns / rows 1 and n-2 differ from the bulk
-        int xx = (int)((k % hm) << 1), y = (int)(i / g.m);
-        unsigned e0, e1;
-        if (xx >= 2 && xx + 2 < g.m && y >= 1 && y + 1 < g.n) { e0 = interior_ex<LAT>(xx); e1 = interior_ex<LAT>(xx + 1); }
-        else { e0 = neighbour_bits(g, xx, y); e1 = neighbour_bits(g, xx + 1, y); }
-        int n0 = __popc((unsigned)c2.x), n1 = __popc((unsigned)c2.y);
-        s_rz += r.x * r.x * tab[(n0 << 3) | (__popc(e0) - n0)].y + r.y * r.y * tab[(n1 << 3) | (__popc(e1) - n1)].y;
-        s_rr += r.x * r.x + r.y * r.y;
     }
-    double a = block_sum(s_rz, sh), c = block_sum(s_rr, sh);
-    if (threadIdx.x == 0) { partial[blockIdx.x * 2 + 0] = a; partial[blockIdx.x * 2 + 1] = c; }
-    if (last_block(&st->ticket_b)) {
-        double fa = fold_partials(partial, gridDim.x, 2, 0, sh);
-        double fc = fold_partials(partial, gridDim.x, 2, 1, sh);
-        if (threadIdx.x == 0) {
-            int it = st->iter + 1;
-            double err = sqrt(fc) / st->bnrm;
-            st->iter = it; st->err = err; st->rr = fc;
-            st->bkden = st->bknum; st->bknum = fa; st->bk = fa / st->bkden;
-            if (!(err > st->tol) || it > st->itmax) st->done = 1;
+    const int bid = by * gridDim.x + bx, nblocks = gridDim.x * gridDim.y;
+    if (MODE == 0) {
+        double bs = block_sum(acc0, sh);
+        if (threadIdx.x == 0) partial[bid] = bs;
+        if (last_block(&st->ticket_a)) {
+            double tot = fold_partials(partial, nblocks, 1, 0, sh);
+            if (threadIdx.x == 0) { st->akden = tot; st->ak = st->bknum / tot; }
+        }
+    } else {
+        double a = block_sum(acc0, sh), b = block_sum(acc1, sh);
+        if (threadIdx.x == 0) { partial[bid * 2 + 0] = a; partial[bid * 2 + 1] = b; }
+        if (last_block(&st->ticket_b)) {
+            double fa = fold_partials(partial, nblocks, 2, 0, sh);
+            double fc = fold_partials(partial, nblocks, 2, 1, sh);
+            if (threadIdx.x == 0) {
+                int it = st->iter + 1;
+                double err = sqrt(fc) / st->bnrm;
+                st->iter = it; st->err = err; st->rr = fc;
+                st->bkden = st->bknum; st->bknum = fa; st->bk = fa / st->bkden;
+                if (!(err > st->tol) || it > st->itmax) st->done = 1;     // loop guard iter <= itmax (:780)
+            }
         }
     }
 }
@@ -488,7 +481,7 @@ pcg_readout_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, con
 static unsigned nblk(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
 int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double tol, int itmax,
-              double read_thresh, double* Gtop, double* Gbot, int* iter, double* err)
+              double read_thresh, int keep_x, double* Gtop, double* Gbot, int* iter, double* err)
 {
     const Geom& g = c->g;
     cudaStream_t s = c->stream;
@@ -502,6 +495,8 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     if (ugrid < 1) ugrid = 1;
     int need = (int)(sgrid.x * sgrid.y);
     if (need < ugrid * 3) need = ugrid * 3;
+    if (need < (int)(2 * sgrid2.x * sgrid2.y)) need = (int)(2 * sgrid2.x * sgrid2.y);
+    if (!vec) keep_x = 1;                // the scalar fallback (odd m) always forms x
     if (need > c->partial_cap) {
         if (c->partial) cudaFree(c->partial);
         PERC_CUDA(cudaMalloc(&c->partial, sizeof(double) * need));
@@ -523,9 +518,9 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[8], s));
             if (vec) {
                 if (g.lattice == LAT_SQUARE)
-                    pcg_spmv2_kernel<LAT_SQUARE><<<sgrid2, S2_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vq, c->partial, c->d_pcg);
+                    pcg_tile_kernel<LAT_SQUARE, 0><<<sgrid2, S2_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vx, c->partial, c->d_pcg, keep_x);
                 else
-                    pcg_spmv2_kernel<LAT_TRIANGULAR><<<sgrid2, S2_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vq, c->partial, c->d_pcg);
+                    pcg_tile_kernel<LAT_TRIANGULAR, 0><<<sgrid2, S2_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vx, c->partial, c->d_pcg, keep_x);
             } else if (g.lattice == LAT_SQUARE)
                 pcg_spmv_kernel<LAT_SQUARE><<<sgrid, SP_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vq, c->partial, c->d_pcg);
             else
@@ -533,9 +528,9 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[9], s));
             if (vec) {
                 if (g.lattice == LAT_SQUARE)
-                    pcg_update2_kernel<LAT_SQUARE><<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, pnew, c->vq, c->partial, c->d_pcg, 1);
+                    pcg_tile_kernel<LAT_SQUARE, 1><<<sgrid2, S2_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pnew, nullptr, c->vx, c->partial, c->d_pcg, keep_x);
                 else
-                    pcg_update2_kernel<LAT_TRIANGULAR><<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, pnew, c->vq, c->partial, c->d_pcg, 1);
+                    pcg_tile_kernel<LAT_TRIANGULAR, 1><<<sgrid2, S2_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pnew, nullptr, c->vx, c->partial, c->d_pcg, keep_x);
             } else
                 pcg_update_kernel<<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, pnew, c->vq, c->partial, c->d_pcg);
             { double* tmp = pold; pold = pnew; pnew = tmp; }
@@ -570,6 +565,7 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     *iter = c->h_pcg->iter;
     *err = c->h_pcg->err;
     c->solved = true;
+    c->have_x = keep_x != 0;
     return 0;
 }
 
