@@ -185,7 +185,9 @@ def workload_config(args):
                         % (args.L, args.ps, args.pb),
             "lattice": "square", "L": args.L, "ps": args.ps, "pb": args.pb, "tol": args.tol,
             "occupancy": "Philox-4x32-10 exact-count generator, one stream per realization",
-            "l2": "per-iteration working set %.2f GB > 126 MB L2 (no flush needed)" % (5 * 8 * args.L * args.L / 1e9),
+            "l2": "per-iteration working set %.2f GB > 126 MB L2 (no flush needed)" % (3 * 8 * args.L * args.L / 1e9),
+            "conduct": "perc_conduct (voltages kept)" if getattr(args, "voltages", False) else
+                       "perc_conduct_g (Gtop/Gbot of the p-sweep drivers; interior voltages not formed)",
             "parallelism": "realizations sharded over %d GPU(s), one final NCCL all-reduce of statistics" % args.gpus}
 
 
@@ -227,7 +229,7 @@ def run_ours(args):
         L.generate(SEED, stream_id(rank, i), ks, kb)
         L.label(P.MIXED)
         ph = L.phase_ms().copy()
-        r = L.conduct(0, tol=args.tol, itmax=args.itmax)
+        r = L.conduct(0, tol=args.tol, itmax=args.itmax, voltages=args.voltages)
         ph2 = L.phase_ms()
         if record:
             stats["G"].append(0.5 * (r["Gtop"] + r["Gbot"]))
@@ -286,7 +288,8 @@ def run_ours(args):
                                    ip(h_s), ip(h_b3), ip(h_c), C.byref(mc), C.byref(pc), C.byref(pl))
             assert rc == 0, rc
             Gt, Gb, er, it = C.c_double(0), C.c_double(0), C.c_double(0), C.c_int32(0)
-            rc = lib.perc_conduct(C.byref(L._h), i32(0), f64(1.0), f64(1.0), f64(1e-12), f64(args.tol),
+            conduct = lib.perc_conduct if args.voltages else lib.perc_conduct_g
+            rc = conduct(C.byref(L._h), i32(0), f64(1.0), f64(1.0), f64(1e-12), f64(args.tol),
                                   i32(args.itmax), f64(1e-10), C.byref(Gt), C.byref(Gb), C.byref(it), C.byref(er))
             assert rc == 0, rc
             e2e_G.append(0.5 * (Gt.value + Gb.value))
@@ -310,8 +313,8 @@ def run_ours(args):
         spmv_ms = float(np.mean(stats["spmv_ms"]))
         upd_ms = float(np.mean(stats["upd_ms"]))
         ccl_ms = float(np.mean(stats["ccl_ms"]))
-        spmv_bytes = 33.0 * interior          # r 8 + p_old 8 + conduct byte 1 read; p 8 + q 8 written
-        upd_bytes = 49.0 * interior           # x, p, r, q read (32) + byte; x, r written (16)
+        spmv_bytes = 25.0 * interior          # r 8 + p_old 8 + conduct byte 1 read; p 8 written (q = A p is never stored)
+        upd_bytes = (41.0 if args.voltages else 25.0) * interior   # p 8 + r 8 + byte read, r 8 written (+ x 8 + 8)
         ach = spmv_bytes / (spmv_ms * 1e-3) / 1e9
         value = world * args.steps / (ms_total * 1e-3)
         mean_iters = st[3] / max(st[2], 1)
@@ -324,12 +327,12 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 4 * t + 8 * nb,
                     "d2h_bytes_per_step": 8 * t + 4 * nb + 64, "steps": e2e_steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "pcg_spmv_kernel (fused p-update + 5-point SpMV + dot)",
+            "roofline": {"bound": "hbm", "kernel": "pcg_tile_kernel<0> (fused p-update + 5-point SpMV + dot, q not stored)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
                          "avg_launch_ms": spmv_ms},
             "extra": {
-                "pcg_update_kernel": {"achieved_gbs": upd_bytes / (upd_ms * 1e-3) / 1e9,
+                "pcg_tile_kernel<1> (residual update, A p recomputed)": {"achieved_gbs": upd_bytes / (upd_ms * 1e-3) / 1e9,
                                       "frac": upd_bytes / (upd_ms * 1e-3) / 1e9 / peak, "avg_launch_ms": upd_ms},
                 "ccl": {"gsites_per_s": t / (ccl_ms * 1e-3) / 1e9, "ms": ccl_ms,
                         "achieved_gbs": 5.0 * t / (ccl_ms * 1e-3) / 1e9, "frac": 5.0 * t / (ccl_ms * 1e-3) / 1e9 / peak},
@@ -376,6 +379,8 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=8)
     ap.add_argument("--cpu-cg-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--voltages", action="store_true",
+                    help="form the interior voltages too (perc_conduct instead of perc_conduct_g; same G)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

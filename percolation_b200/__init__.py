@@ -2,5 +2,6 @@
 IsaiahSteinke/Percolation: occupancy generator, cluster labeling, spanning / cluster sizes,
 Kirchhoff conductance.  The product is libperc_b200.so (hand-written CUDA behind the C-ABI of
 include/perc_abi.h); this package only loads it.  No CPU fallback."""
-from .lib import (BOND, MIXED, SITE, SQUARE, TRIANGULAR, Lattice, PercError, SO_PATH, SYMBOLS,  # noqa: F401
+from .lib import (BOND, E_ARG, E_NOSPAN, E_ODD_M, E_SIZE, E_STATE, MIXED, SITE, SQUARE, TRIANGULAR,  # noqa: F401
+                  Lattice, PercError, SO_PATH, SYMBOLS,
                   geom_bondlist, geom_nb, geom_nearestn, load)

@@ -46,6 +46,7 @@ int ctx_alloc(Ctx* c)
 {
     const int64_t t = c->g.t;
     PERC_CUDA(cudaSetDevice(c->device));
+    PERC_CUDA(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
     PERC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     PERC_CUDA(cudaMalloc(&c->srank, sizeof(int32_t) * t));
     PERC_CUDA(cudaMalloc(&c->brank, sizeof(int32_t) * t * c->g.ndir));
@@ -77,7 +78,7 @@ static int ensure_pcg(Ctx* c)
     PERC_CUDA(cudaMalloc(&c->vr, sizeof(double) * t));
     PERC_CUDA(cudaMalloc(&c->vp, sizeof(double) * t));
     PERC_CUDA(cudaMalloc(&c->vp2, sizeof(double) * t));
-    if (c->g.m & 1) PERC_CUDA(cudaMalloc(&c->vq, sizeof(double) * t));     // only the odd-m fallback stores q = A p
+    if (c->g.m % 16) PERC_CUDA(cudaMalloc(&c->vq, sizeof(double) * t));    // only the scalar fallback stores q = A p
     return 0;
 }
 

@@ -30,6 +30,7 @@ enum OccSource { SRC_NONE = 0, SRC_RANK = 1, SRC_PHILOX = 2 };
 struct Ctx {
     Geom g;
     int device = 0;
+    int num_sms = 148;
     cudaStream_t stream = nullptr;
 
     // ---- occupancy inputs

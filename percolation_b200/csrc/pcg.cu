@@ -10,10 +10,10 @@
 // rows 1..n-2, rows 0 / n-1 are Dirichlet (0 / Va).  One byte per site (cfull) says which of
 // its up-to-6 bonds conduct; weights and the diagonal are rebuilt from it on the fly.
 //
-//   K6  pcg_tile_kernel<0> p <- r/d + bk*p (tile + halo, shared memory), sum p.(A p)
-//   K7  pcg_tile_kernel<1> r -= ak (A p) with A p recomputed (q is never stored), x += ak p,
+//   K6  pcg_pipe_kernel<0> p <- r/d + bk*p (tile + halo, shared memory), sum p.(A p)
+//   K7  pcg_pipe_kernel<1> r -= ak (A p) with A p recomputed (q is never stored), x += ak p,
 //                          sums r.r/d (next bknum) and r.r (err)
-//       (pcg_spmv_kernel / pcg_update_kernel: scalar fallback with a stored q for odd m)
+//       (pcg_spmv_kernel / pcg_update_kernel: scalar fallback with a stored q when m is not a multiple of 16)
 //   K8  pcg_readout_kernel literal Gtop / Gbot incl. the 1e-10 drop rule of the 2nd sprsin
 // Reductions are two-stage and fixed-order (per-block partial, last block folds them), so a
 // solve is bit-reproducible for a given lattice size.
@@ -141,7 +141,8 @@ pcg_init_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
             double z = b / d;
             s_b += z * z; s_rz += b * z; s_rr += b * b;
         }
-        vx[i] = 0.0; vr[i] = b; vp[i] = 0.0; vq[i] = 0.0;
+        vx[i] = 0.0; vr[i] = b; vp[i] = 0.0;
+        if (vq) vq[i] = 0.0;          // only the odd-m fallback stores q
     }
     double a = block_sum(s_b, sh), c = block_sum(s_rz, sh), e = block_sum(s_rr, sh);
     if (threadIdx.x == 0) { partial[blockIdx.x * 3 + 0] = a; partial[blockIdx.x * 3 + 1] = c; partial[blockIdx.x * 3 + 2] = e; }
@@ -261,7 +262,6 @@ pcg_update_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, doub
 // 64-entry shared table indexed by (#conducting, #leak) bonds instead of an fp64 division, and a
 // constant neighbourhood for tiles that do not touch the lattice boundary.
 // ------------------------------------------------------------------------------------------
-constexpr int S2_TX = 128, S2_TY = 32, S2_THREADS = 256, S2_LD = S2_TX + 4;
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
@@ -283,155 +283,247 @@ __device__ __forceinline__ unsigned interior_ex(int gx)
 }
 
 // ------------------------------------------------------------------------------------------
-// K6'/K7' (even m): the q = A p vector is never stored.  Both kernels stage p on tile + halo in shared
-// memory and apply the stencil; MODE 0 builds the new direction and p.Ap, MODE 1 RECOMPUTES A p to
-// update the residual once ak is known.  HBM traffic per site and iteration:
+// K6'/K7' (m % 16 == 0): persistent, double-buffered tile pipeline; the q = A p vector is never stored.
+// One CTA per SM walks over the 128 x 32 tiles of the lattice.  While the CTA computes tile k from
+// one shared-memory stage, the asynchronous copies (cp.async / LDGSTS, 16 bytes each, zero-filled
+// outside the lattice) of tile k+1 (+ one-site halo) are already in flight into the other stage, so
+// ~75 KB per SM are always outstanding and no load latency is exposed to the arithmetic.
+//   MODE 0: p_new = r / d + bk * p_old in place on tile + halo, q = A p_new, p.q      (K6)
+//   MODE 1: q = A p RECOMPUTED, r -= ak q, x += ak p, sums r.r/d and r.r              (K7)
+// HBM traffic per site and iteration:
 //   MODE 0: r 8 + p_old 8 + cfull 1 read, p 8 written                      = 25 B
 //   MODE 1: p 8 + r 8 + cfull 1 read, r 8 written (+ x 8 read, 8 written)  = 25 B (41 B with keep_x)
-// against 82 B for the stored-q pair above.  The fp64 stencil is done twice; the SMs have the
-// headroom (HBM-bound either way).  keep_x = 0 keeps x only on rows 1 and n-2, the rows the read-out
-// (K8) consumes: Gtop / Gbot come out bit-identical, the interior voltages are simply not formed.
+// against 82 B for a stored-q pair.  The fp64 stencil is done twice; the SMs have the headroom.
+// keep_x = 0 keeps x only on rows 1 and n-2, the rows the read-out (K8) consumes: Gtop / Gbot come
+// out bit-identical, the interior voltages are simply not formed.
+// Partial sums are stored per TILE and folded in tile order, so the result does not depend on the
+// number of CTAs.
 // ------------------------------------------------------------------------------------------
+constexpr int PT_TX = 128, PT_TY = 32, PT_THREADS = 512, PT_ROWS = PT_TY + 2;
+constexpr int PT_LD = PT_TX + 4;            // doubles per staged row: [1] left halo, [2..129] tile, [130] right halo
+constexpr int PT_CLD = PT_TX + 32;          // bytes per staged cfull row: [12..15] left halo word, [16..143] tile, [144..147] right halo word
+constexpr int PT_STAGE_BYTES = 2 * PT_ROWS * PT_LD * 8 + PT_ROWS * PT_CLD;
+constexpr size_t PT_SMEM = 2 * (size_t)PT_STAGE_BYTES + sizeof(double2) * 64 + sizeof(double) * 32;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, bool valid)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(valid ? 8 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, bool valid)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+
+struct PtStage { double* sp; double* sr; uint8_t* scf; };
+
+__device__ __forceinline__ PtStage pt_stage(unsigned char* raw, int k)
+{
+    PtStage s;
+    unsigned char* base = raw + (size_t)k * PT_STAGE_BYTES;
+    s.sp = reinterpret_cast<double*>(base);
+    s.sr = s.sp + PT_ROWS * PT_LD;
+    s.scf = reinterpret_cast<uint8_t*>(s.sr + PT_ROWS * PT_LD);
+    return s;
+}
+
+// issue the asynchronous copies of one tile (+ halo) into a stage
+template <int MODE>
+__device__ __forceinline__ void pt_issue(const Geom& g, const PtStage& s, int x0, int y0, const uint8_t* __restrict__ cfull,
+                                         const double* __restrict__ vr, const double* __restrict__ vp_in)
+{
+    const int tid = threadIdx.x;
+    for (int k = tid; k < PT_ROWS * (PT_TX / 2); k += PT_THREADS) {           // tile columns, 2 doubles per copy
+        const int pr = k / (PT_TX / 2), cx = (k % (PT_TX / 2)) * 2;
+        const int gy = y0 + pr - 1, gx = x0 + cx;
+        if (gx >= g.m) continue;                                             // never read (and the halo column lives there)
+        const bool ok = gy >= 0 && gy < g.n;
+        const int64_t j = ok ? (int64_t)gy * g.m + gx : 0;
+        cp_async16(&s.sp[pr * PT_LD + 2 + cx], vp_in + j, ok && gy >= 1 && gy < g.n - 1);   // Dirichlet rows: p = 0
+        if (MODE == 0 || (pr >= 1 && pr <= PT_TY)) cp_async16(&s.sr[pr * PT_LD + 2 + cx], vr + j, ok);
+    }
+    for (int k = tid; k < PT_ROWS * (PT_TX / 16); k += PT_THREADS) {          // conduct bytes, 16 per copy
+        const int pr = k / (PT_TX / 16), cx = (k % (PT_TX / 16)) * 16;
+        const int gy = y0 + pr - 1, gx = x0 + cx;
+        if (gx >= g.m) continue;
+        const bool ok = gy >= 0 && gy < g.n;
+        cp_async16(&s.scf[pr * PT_CLD + 16 + cx], cfull + (ok ? (int64_t)gy * g.m + gx : 0), ok);
+    }
+    if (tid < 2 * PT_ROWS) {                                                 // halo columns (periodic wrap aware)
+        const int side = tid >= PT_ROWS, pr = tid - side * PT_ROWS;
+        const int gy = y0 + pr - 1;
+        const int xe = g.m - x0 < PT_TX ? g.m - x0 : PT_TX;                   // real columns of this tile
+        int hx = side ? x0 + xe : x0 - 1;
+        if (g.pbc) { if (hx == -1) hx = g.m - 1; else if (hx == g.m) hx = 0; }
+        const bool ok = gy >= 0 && gy < g.n && hx >= 0 && hx < g.m;
+        const int64_t j = ok ? (int64_t)gy * g.m + hx : 0;
+        const int col = side ? 2 + xe : 1;
+        cp_async8(&s.sp[pr * PT_LD + col], vp_in + j, ok && gy >= 1 && gy < g.n - 1);
+        if (MODE == 0) {
+            cp_async8(&s.sr[pr * PT_LD + col], vr + j, ok);
+            // the conduct byte of the halo cell: the aligned 4-byte word that holds it
+            cp_async4(&s.scf[pr * PT_CLD + (side ? 16 + PT_TX : 12)], cfull + (j & ~(int64_t)3), ok);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 template <int LAT, int MODE>
-__global__ void __launch_bounds__(S2_THREADS)
-pcg_tile_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double* __restrict__ vr,
+__global__ void __launch_bounds__(PT_THREADS, 1)
+pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double* __restrict__ vr,
                 const double* __restrict__ vp_in, double* __restrict__ vp_out, double* __restrict__ vx,
-                double* __restrict__ partial, PcgState* __restrict__ st, int keep_x)
+                double* __restrict__ partial, PcgState* __restrict__ st, int keep_x, int ntx, int ntiles)
 {
     if (st->done) return;
-    __shared__ __align__(16) double pn[(S2_TY + 2) * S2_LD];
-    __shared__ double2 tab[64];
-    __shared__ double sh[32];
+    extern __shared__ __align__(16) unsigned char pt_raw[];
+    double2* tab = reinterpret_cast<double2*>(pt_raw + 2 * (size_t)PT_STAGE_BYTES);
+    double* sh = reinterpret_cast<double*>(tab + 64);
     const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
-    fill_dtab(tab, prm);
+    if (tid < 64) {
+        int nc = tid >> 3, nl = tid & 7;
+        double d = (double)nc * prm.g0 + (double)nl * prm.gleak;
+        tab[tid] = make_double2(d, d > 0.0 ? 1.0 / d : 0.0);
+    }
     const double bk = st->bk, ak = st->ak;
+    const double dg = prm.g0 - prm.gleak;
     // MODE 0 sweeps the tiles from the END of the lattice to its start, MODE 1 front to back: each
     // kernel starts on the data the previous one touched last (still resident in the 126 MB L2)
-    const int bx = MODE == 0 ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
-    const int by = MODE == 0 ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
-    const int x0 = bx * S2_TX, y0 = by * S2_TY;
-    // every cell of tile + halo has its full neighbourhood inside the lattice
-    const bool interior = x0 >= 2 && x0 + S2_TX <= g.m - 2 && y0 >= 2 && y0 + S2_TY <= g.n - 2;
-    __syncthreads();
+    auto tile_of = [&](int t) { return MODE == 0 ? ntiles - 1 - t : t; };
 
-    auto scalar_pn = [&](int hx, int gy) -> double {
-        int64_t j = (int64_t)gy * g.m + hx;
-        if (MODE == 1) return vp_in[j];
-        unsigned cf = cfull[j];
-        unsigned ex = interior ? interior_ex<LAT>(hx) : neighbour_bits(g, hx, gy);
-        int nc = __popc(cf);
-        return vr[j] * tab[(nc << 3) | (__popc(ex) - nc)].y + bk * vp_in[j];
-    };
+    int t = blockIdx.x;
+    if (t < ntiles) { int tl = tile_of(t); pt_issue<MODE>(g, pt_stage(pt_raw, 0), (tl % ntx) * PT_TX, (tl / ntx) * PT_TY, cfull, vr, vp_in); }
+    for (int k = 0; t < ntiles; t += gridDim.x, ++k) {
+        const int tl = tile_of(t), x0 = (tl % ntx) * PT_TX, y0 = (tl / ntx) * PT_TY;
+        const PtStage s = pt_stage(pt_raw, k & 1);
+        const int tn = t + gridDim.x;
+        if (tn < ntiles) {
+            int tnl = tile_of(tn);
+            pt_issue<MODE>(g, pt_stage(pt_raw, (k + 1) & 1), (tnl % ntx) * PT_TX, (tnl / ntx) * PT_TY, cfull, vr, vp_in);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        // every cell of tile + halo has its full neighbourhood inside the lattice
+        const bool interior = x0 >= 2 && x0 + PT_TX <= g.m - 2 && y0 >= 2 && y0 + PT_TY <= g.n - 2;
+        const int xe = g.m - x0 < PT_TX ? g.m - x0 : PT_TX;
 
-    // phase 1: the direction p on tile + halo.  MODE 0: p = r / d + bk * p_old (p is double-buffered:
-    // neighbouring tiles still read p_old); MODE 1: p as stored by MODE 0
-    const int gx = x0 + 2 * tx;
-    for (int ly = ty - 1; ly <= S2_TY; ly += S2_THREADS / 64) {
-        const int gy = y0 + ly;
-        const bool rowok = gy >= 1 && gy < g.n - 1;
-        double2 v = make_double2(0.0, 0.0);
-        if (rowok) {
-            if (gx < g.m) {
-                int64_t i = (int64_t)gy * g.m + gx;
-                if (MODE == 1) v = ld2(vp_in + i);
-                else {
-                    double2 r2 = ld2(vr + i), p2 = ld2(vp_in + i);
-                    uchar2 c2 = *reinterpret_cast<const uchar2*>(cfull + i);
-                    unsigned e0 = interior ? interior_ex<LAT>(gx) : neighbour_bits(g, gx, gy);
-                    unsigned e1 = interior ? interior_ex<LAT>(gx + 1) : neighbour_bits(g, gx + 1, gy);
-                    int n0 = __popc((unsigned)c2.x), n1 = __popc((unsigned)c2.y);
+        // ---- MODE 0: p_new = r / d + bk * p_old, in place on tile + halo (p is double-buffered in
+        // HBM: neighbouring tiles still read p_old) ---------------------------------------------------
+        if (MODE == 0) {
+            for (int c = tid; c < PT_ROWS * (PT_TX / 2); c += PT_THREADS) {
+                const int pr = c / (PT_TX / 2), cx = (c % (PT_TX / 2)) * 2;
+                const int gy = y0 + pr - 1, gx = x0 + cx;
+                if (gx >= g.m) continue;
+                double2 v = make_double2(0.0, 0.0);
+                if (gy >= 1 && gy < g.n - 1) {
+                    const double2 r2 = ld2(&s.sr[pr * PT_LD + 2 + cx]), p2 = ld2(&s.sp[pr * PT_LD + 2 + cx]);
+                    const unsigned c0 = s.scf[pr * PT_CLD + 16 + cx], c1 = s.scf[pr * PT_CLD + 17 + cx];
+                    const unsigned e0 = interior ? interior_ex<LAT>(gx) : neighbour_bits(g, gx, gy);
+                    const unsigned e1 = interior ? interior_ex<LAT>(gx + 1) : neighbour_bits(g, gx + 1, gy);
+                    const int n0 = __popc(c0), n1 = __popc(c1);
                     v.x = r2.x * tab[(n0 << 3) | (__popc(e0) - n0)].y + bk * p2.x;
                     v.y = r2.y * tab[(n1 << 3) | (__popc(e1) - n1)].y + bk * p2.y;
                 }
-            } else if (gx == g.m && g.pbc) {
-                v.x = scalar_pn(0, gy);                     // partial tile: wrapped right neighbour of x = m-1
+                st2(&s.sp[pr * PT_LD + 2 + cx], v);
             }
+            if (tid < 2 * PT_ROWS) {
+                const int side = tid >= PT_ROWS, pr = tid - side * PT_ROWS;
+                const int gy = y0 + pr - 1;
+                int hx = side ? x0 + xe : x0 - 1;
+                if (g.pbc) { if (hx == -1) hx = g.m - 1; else if (hx == g.m) hx = 0; }
+                const int col = side ? 2 + xe : 1;
+                double v = 0.0;
+                if (gy >= 1 && gy < g.n - 1 && hx >= 0 && hx < g.m) {
+                    const unsigned cf = s.scf[pr * PT_CLD + (side ? 16 + PT_TX : 12) + (hx & 3)];
+                    const unsigned ex = neighbour_bits(g, hx, gy);
+                    const int nc = __popc(cf);
+                    v = s.sr[pr * PT_LD + col] * tab[(nc << 3) | (__popc(ex) - nc)].y + bk * s.sp[pr * PT_LD + col];
+                }
+                s.sp[pr * PT_LD + col] = v;
+            }
+            __syncthreads();
         }
-        st2(&pn[(ly + 1) * S2_LD + 2 + 2 * tx], v);
-    }
-    // halo columns x0-1 and x0+S2_TX: one cell per thread
-    if (tid < 2 * (S2_TY + 2)) {
-        const int side = tid >= S2_TY + 2, ly = tid - side * (S2_TY + 2) - 1;
-        const int gy = y0 + ly;
-        int hx = side ? x0 + S2_TX : x0 - 1;
-        if (g.pbc) { if (hx == -1) hx = g.m - 1; else if (hx == g.m) hx = 0; }
-        double hv = 0.0;
-        if (gy >= 1 && gy < g.n - 1 && hx >= 0 && hx < g.m) hv = scalar_pn(hx, gy);
-        pn[(ly + 1) * S2_LD + (side ? S2_TX + 2 : 1)] = hv;
-    }
-    __syncthreads();
 
-    // phase 2: q = A p; MODE 0: dot(p, q); MODE 1: r -= ak q, x += ak p, sums r.r/d and r.r
-    const double dg = prm.g0 - prm.gleak;
-    double acc0 = 0.0, acc1 = 0.0;
-    for (int ly = ty; ly < S2_TY; ly += S2_THREADS / 64) {
-        const int gy = y0 + ly;
-        if (gy < 1 || gy >= g.n - 1 || gx >= g.m) continue;
-        int64_t i = (int64_t)gy * g.m + gx;
-        uchar2 c2 = *reinterpret_cast<const uchar2*>(cfull + i);
-        const unsigned cf0 = c2.x, cf1 = c2.y;
-        const double* c = &pn[(ly + 1) * S2_LD + 2 + 2 * tx];
-        const double2 cc = ld2(c), up = ld2(c + S2_LD), dn = ld2(c - S2_LD);
-        const double lf = c[-1], rt = c[2];
-        unsigned e0, e1;
-        double all0, all1;
-        if (interior) {
-            e0 = interior_ex<LAT>(gx); e1 = interior_ex<LAT>(gx + 1);
-            all0 = (cc.y + lf) + (up.x + dn.x);
-            all1 = (rt + cc.x) + (up.y + dn.y);
-            if (LAT == LAT_TRIANGULAR) { all0 += c[S2_LD - 1] + up.y; all1 += dn.x + c[-S2_LD + 2]; }
-        } else {
-            e0 = neighbour_bits(g, gx, gy); e1 = neighbour_bits(g, gx + 1, gy);
-            all0 = 0.0; all1 = 0.0;
-            if (e0 & NB_E) all0 += cc.y;  if (e0 & NB_W) all0 += lf;  if (e0 & NB_N) all0 += up.x;  if (e0 & NB_S) all0 += dn.x;
-            if (e1 & NB_E) all1 += rt;    if (e1 & NB_W) all1 += cc.x; if (e1 & NB_N) all1 += up.y; if (e1 & NB_S) all1 += dn.y;
+        // ---- stencil: q = A p from shared memory; MODE 0: dot(p, q); MODE 1: r -= ak q, x += ak p ----
+        const int gx = x0 + 2 * tx;
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int ly = ty; ly < PT_TY; ly += PT_THREADS / 64) {
+            const int gy = y0 + ly;
+            if (gy < 1 || gy >= g.n - 1 || gx >= g.m) continue;
+            const int64_t i = (int64_t)gy * g.m + gx;
+            const unsigned cf0 = s.scf[(ly + 1) * PT_CLD + 16 + 2 * tx], cf1 = s.scf[(ly + 1) * PT_CLD + 17 + 2 * tx];
+            const double* c = &s.sp[(ly + 1) * PT_LD + 2 + 2 * tx];
+            const double2 cc = ld2(c), up = ld2(c + PT_LD), dn = ld2(c - PT_LD);
+            const double lf = c[-1], rt = c[2];
+            unsigned e0, e1;
+            double all0, all1;
+            if (interior) {
+                e0 = interior_ex<LAT>(gx); e1 = interior_ex<LAT>(gx + 1);
+                all0 = (cc.y + lf) + (up.x + dn.x);
+                all1 = (rt + cc.x) + (up.y + dn.y);
+                if (LAT == LAT_TRIANGULAR) { all0 += c[PT_LD - 1] + up.y; all1 += dn.x + c[-PT_LD + 2]; }
+            } else {
+                e0 = neighbour_bits(g, gx, gy); e1 = neighbour_bits(g, gx + 1, gy);
+                all0 = 0.0; all1 = 0.0;
+                if (e0 & NB_E) all0 += cc.y;  if (e0 & NB_W) all0 += lf;  if (e0 & NB_N) all0 += up.x;  if (e0 & NB_S) all0 += dn.x;
+                if (e1 & NB_E) all1 += rt;    if (e1 & NB_W) all1 += cc.x; if (e1 & NB_N) all1 += up.y; if (e1 & NB_S) all1 += dn.y;
+                if (LAT == LAT_TRIANGULAR) {
+                    if (e0 & NB_NW) all0 += c[PT_LD - 1]; if (e0 & NB_NE) all0 += up.y;
+                    if (e1 & NB_SW) all1 += dn.x;         if (e1 & NB_SE) all1 += c[-PT_LD + 2];
+                }
+            }
+            double con0 = 0.0, con1 = 0.0;        // conducting neighbours (cfull bits only on existing bonds)
+            if (cf0 & NB_E) con0 += cc.y;  if (cf0 & NB_W) con0 += lf;   if (cf0 & NB_N) con0 += up.x;  if (cf0 & NB_S) con0 += dn.x;
+            if (cf1 & NB_E) con1 += rt;    if (cf1 & NB_W) con1 += cc.x; if (cf1 & NB_N) con1 += up.y;  if (cf1 & NB_S) con1 += dn.y;
             if (LAT == LAT_TRIANGULAR) {
-                if (e0 & NB_NW) all0 += c[S2_LD - 1]; if (e0 & NB_NE) all0 += up.y;
-                if (e1 & NB_SW) all1 += dn.x;         if (e1 & NB_SE) all1 += c[-S2_LD + 2];
+                if (cf0 & NB_NW) con0 += c[PT_LD - 1]; if (cf0 & NB_NE) con0 += up.y;
+                if (cf1 & NB_SW) con1 += dn.x;         if (cf1 & NB_SE) con1 += c[-PT_LD + 2];
+            }
+            const int n0 = __popc(cf0), n1 = __popc(cf1);
+            const double2 t0 = tab[(n0 << 3) | (__popc(e0) - n0)], t1 = tab[(n1 << 3) | (__popc(e1) - n1)];
+            double2 q;
+            q.x = t0.x * cc.x - (prm.gleak * all0 + dg * con0);
+            q.y = t1.x * cc.y - (prm.gleak * all1 + dg * con1);
+            if (MODE == 0) {
+                st2(vp_out + i, cc);
+                acc0 += cc.x * q.x + cc.y * q.y;
+            } else {
+                double2 r = ld2(&s.sr[(ly + 1) * PT_LD + 2 + 2 * tx]);
+                r.x -= ak * q.x; r.y -= ak * q.y;
+                st2(vr + i, r);
+                if (keep_x || gy == 1 || gy == g.n - 2) {
+                    double2 x = ld2(vx + i);
+                    x.x += ak * cc.x; x.y += ak * cc.y;
+                    st2(vx + i, x);
+                }
+                acc0 += r.x * r.x * t0.y + r.y * r.y * t1.y;
+                acc1 += r.x * r.x + r.y * r.y;
             }
         }
-        double con0 = 0.0, con1 = 0.0;            // conducting neighbours (cfull bits only on existing bonds)
-        if (cf0 & NB_E) con0 += cc.y;  if (cf0 & NB_W) con0 += lf;   if (cf0 & NB_N) con0 += up.x;  if (cf0 & NB_S) con0 += dn.x;
-        if (cf1 & NB_E) con1 += rt;    if (cf1 & NB_W) con1 += cc.x; if (cf1 & NB_N) con1 += up.y;  if (cf1 & NB_S) con1 += dn.y;
-        if (LAT == LAT_TRIANGULAR) {
-            if (cf0 & NB_NW) con0 += c[S2_LD - 1]; if (cf0 & NB_NE) con0 += up.y;
-            if (cf1 & NB_SW) con1 += dn.x;         if (cf1 & NB_SE) con1 += c[-S2_LD + 2];
-        }
-        const int n0 = __popc(cf0), n1 = __popc(cf1);
-        const double2 t0 = tab[(n0 << 3) | (__popc(e0) - n0)], t1 = tab[(n1 << 3) | (__popc(e1) - n1)];
-        double2 q;
-        q.x = t0.x * cc.x - (prm.gleak * all0 + dg * con0);
-        q.y = t1.x * cc.y - (prm.gleak * all1 + dg * con1);
+        // per-tile partial sums (block_sum synchronises: every thread is done with this stage afterwards)
         if (MODE == 0) {
-            st2(vp_out + i, cc);
-            acc0 += cc.x * q.x + cc.y * q.y;
+            double bs = block_sum(acc0, sh);
+            if (tid == 0) partial[tl] = bs;
         } else {
-            double2 r = ld2(vr + i);
-            r.x -= ak * q.x; r.y -= ak * q.y;
-            st2(vr + i, r);
-            if (keep_x || gy == 1 || gy == g.n - 2) {
-                double2 x = ld2(vx + i);
-                x.x += ak * cc.x; x.y += ak * cc.y;
-                st2(vx + i, x);
-            }
-            acc0 += r.x * r.x * t0.y + r.y * r.y * t1.y;
-            acc1 += r.x * r.x + r.y * r.y;
+            double a = block_sum(acc0, sh), b = block_sum(acc1, sh);
+            if (tid == 0) { partial[tl * 2 + 0] = a; partial[tl * 2 + 1] = b; }
         }
     }
-    const int bid = by * gridDim.x + bx, nblocks = gridDim.x * gridDim.y;
     if (MODE == 0) {
-        double bs = block_sum(acc0, sh);
-        if (threadIdx.x == 0) partial[bid] = bs;
         if (last_block(&st->ticket_a)) {
-            double tot = fold_partials(partial, nblocks, 1, 0, sh);
+            double tot = fold_partials(partial, ntiles, 1, 0, sh);
             if (threadIdx.x == 0) { st->akden = tot; st->ak = st->bknum / tot; }
         }
     } else {
-        double a = block_sum(acc0, sh), b = block_sum(acc1, sh);
-        if (threadIdx.x == 0) { partial[bid * 2 + 0] = a; partial[bid * 2 + 1] = b; }
         if (last_block(&st->ticket_b)) {
-            double fa = fold_partials(partial, nblocks, 2, 0, sh);
-            double fc = fold_partials(partial, nblocks, 2, 1, sh);
+            double fa = fold_partials(partial, ntiles, 2, 0, sh);
+            double fc = fold_partials(partial, ntiles, 2, 1, sh);
             if (threadIdx.x == 0) {
                 int it = st->iter + 1;
                 double err = sqrt(fc) / st->bnrm;
@@ -487,20 +579,30 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     cudaStream_t s = c->stream;
     PcgParams prm{g0, gleak, Va, read_thresh};
     dim3 sgrid((g.m + SP_TX - 1) / SP_TX, (g.n + SP_TY - 1) / SP_TY);
-    dim3 sgrid2((g.m + S2_TX - 1) / S2_TX, (g.n + S2_TY - 1) / S2_TY);
-    const bool vec = (g.m % 2) == 0;     // 128-bit paths need even m (rows stay 16-byte aligned)
+    const int ntx = (g.m + PT_TX - 1) / PT_TX, ntiles = ntx * ((g.n + PT_TY - 1) / PT_TY);
+    const int pgrid = ntiles < c->num_sms ? ntiles : c->num_sms;     // one persistent CTA per SM
+    const bool vec = (g.m % 16) == 0;    // staged kernels: rows of the fp64 vectors and of the byte mask are 16-byte aligned
     int ugrid = 148 * 8;
     int64_t interior = g.t - 2 * (int64_t)g.m;
     if (ugrid > (interior + UP_THREADS - 1) / UP_THREADS) ugrid = (int)((interior + UP_THREADS - 1) / UP_THREADS);
     if (ugrid < 1) ugrid = 1;
     int need = (int)(sgrid.x * sgrid.y);
     if (need < ugrid * 3) need = ugrid * 3;
-    if (need < (int)(2 * sgrid2.x * sgrid2.y)) need = (int)(2 * sgrid2.x * sgrid2.y);
-    if (!vec) keep_x = 1;                // the scalar fallback (odd m) always forms x
+    if (need < 2 * ntiles) need = 2 * ntiles;
+    const int want_x = keep_x;
+    if (!vec) keep_x = 1;                // the scalar fallback always forms x
     if (need > c->partial_cap) {
         if (c->partial) cudaFree(c->partial);
         PERC_CUDA(cudaMalloc(&c->partial, sizeof(double) * need));
         c->partial_cap = need;
+    }
+    static bool attr_set = false;
+    if (vec && !attr_set) {
+        PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_SQUARE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+        PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_SQUARE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+        PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_TRIANGULAR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+        PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_TRIANGULAR, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+        attr_set = true;
     }
     PERC_CUDA(cudaMemsetAsync(c->d_pcg, 0, sizeof(PcgState), s));
     PERC_CUDA(cudaEventRecord(c->ev[6], s));
@@ -518,9 +620,9 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[8], s));
             if (vec) {
                 if (g.lattice == LAT_SQUARE)
-                    pcg_tile_kernel<LAT_SQUARE, 0><<<sgrid2, S2_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vx, c->partial, c->d_pcg, keep_x);
+                    pcg_pipe_kernel<LAT_SQUARE, 0><<<pgrid, PT_THREADS, PT_SMEM, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles);
                 else
-                    pcg_tile_kernel<LAT_TRIANGULAR, 0><<<sgrid2, S2_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vx, c->partial, c->d_pcg, keep_x);
+                    pcg_pipe_kernel<LAT_TRIANGULAR, 0><<<pgrid, PT_THREADS, PT_SMEM, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles);
             } else if (g.lattice == LAT_SQUARE)
                 pcg_spmv_kernel<LAT_SQUARE><<<sgrid, SP_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vq, c->partial, c->d_pcg);
             else
@@ -528,9 +630,9 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[9], s));
             if (vec) {
                 if (g.lattice == LAT_SQUARE)
-                    pcg_tile_kernel<LAT_SQUARE, 1><<<sgrid2, S2_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pnew, nullptr, c->vx, c->partial, c->d_pcg, keep_x);
+                    pcg_pipe_kernel<LAT_SQUARE, 1><<<pgrid, PT_THREADS, PT_SMEM, s>>>(g, prm, c->cfull, c->vr, pnew, nullptr, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles);
                 else
-                    pcg_tile_kernel<LAT_TRIANGULAR, 1><<<sgrid2, S2_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pnew, nullptr, c->vx, c->partial, c->d_pcg, keep_x);
+                    pcg_pipe_kernel<LAT_TRIANGULAR, 1><<<pgrid, PT_THREADS, PT_SMEM, s>>>(g, prm, c->cfull, c->vr, pnew, nullptr, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles);
             } else
                 pcg_update_kernel<<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, pnew, c->vq, c->partial, c->d_pcg);
             { double* tmp = pold; pold = pnew; pnew = tmp; }
@@ -565,7 +667,7 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     *iter = c->h_pcg->iter;
     *err = c->h_pcg->err;
     c->solved = true;
-    c->have_x = keep_x != 0;
+    c->have_x = want_x != 0;
     return 0;
 }
 

@@ -151,10 +151,12 @@ def test_png_fixtures_through_gpu(P, O):
         L.close()
 
 
+# m = 40: scalar kernels (stored q); m % 16 == 0: staged kernels (cp.async tiles, q recomputed), incl.
+# partial tiles (m = 48, 144) and several tiles per row / column (144 x 70)
+@pytest.mark.parametrize("m,n", [(40, 36), (48, 36), (144, 70)])
 @pytest.mark.parametrize("lat,kind", [(1, 2), (2, 2), (1, 1), (2, 1), (1, 3), (2, 3)])
 @pytest.mark.parametrize("pbc", [0, 1])
-def test_conductance_vs_oracle(P, O, lat, kind, pbc):
-    m, n = 40, 36
+def test_conductance_vs_oracle(P, O, lat, kind, pbc, m, n):
     t = m * n
     b1, b2 = O.bondlist(lat, m, n, pbc)
     nb = len(b1)
@@ -196,6 +198,12 @@ def test_conductance_vs_oracle(P, O, lat, kind, pbc):
             chk = O.conduct_check(m, n, b1, b2, w, L.voltage())
             assert chk["err"] <= 2e-13
             assert abs(chk["Gtop"] - got["Gtop"]) <= 1e-12 * abs(got["Gtop"])
+            # (d) the sweep-driver entry point (no interior voltages): bit-identical G, iter, err
+            gonly = L.conduct(cid, tol=1e-13, itmax=200000, voltages=False)
+            assert gonly == got
+            with pytest.raises(P.PercError) as e:
+                L.voltage()
+            assert e.value.code == P.E_STATE
             done += 1
             if done == 2:
                 break
