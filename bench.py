@@ -327,12 +327,12 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 4 * t + 8 * nb,
                     "d2h_bytes_per_step": 8 * t + 4 * nb + 64, "steps": e2e_steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "pcg_tile_kernel<0> (fused p-update + 5-point SpMV + dot, q not stored)",
+            "roofline": {"bound": "hbm", "kernel": "pcg_pipe_kernel<0> (persistent cp.async pipeline: p-update + 5-point SpMV + dot, q not stored)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
                          "avg_launch_ms": spmv_ms},
             "extra": {
-                "pcg_tile_kernel<1> (residual update, A p recomputed)": {"achieved_gbs": upd_bytes / (upd_ms * 1e-3) / 1e9,
+                "pcg_pipe_kernel<1> (residual update, A p recomputed)": {"achieved_gbs": upd_bytes / (upd_ms * 1e-3) / 1e9,
                                       "frac": upd_bytes / (upd_ms * 1e-3) / 1e9 / peak, "avg_launch_ms": upd_ms},
                 "ccl": {"gsites_per_s": t / (ccl_ms * 1e-3) / 1e9, "ms": ccl_ms,
                         "achieved_gbs": 5.0 * t / (ccl_ms * 1e-3) / 1e9, "frac": 5.0 * t / (ccl_ms * 1e-3) / 1e9 / peak},

@@ -300,10 +300,20 @@ __device__ __forceinline__ unsigned interior_ex(int gx)
 // number of CTAs.
 // ------------------------------------------------------------------------------------------
 constexpr int PT_TX = 128, PT_TY = 32, PT_THREADS = 512, PT_ROWS = PT_TY + 2;
+constexpr int PT_RPT = PT_TY / (PT_THREADS / 64);      // consecutive tile rows per thread in the stencil
 constexpr int PT_LD = PT_TX + 4;            // doubles per staged row: [1] left halo, [2..129] tile, [130] right halo
 constexpr int PT_CLD = PT_TX + 32;          // bytes per staged cfull row: [12..15] left halo word, [16..143] tile, [144..147] right halo word
 constexpr int PT_STAGE_BYTES = 2 * PT_ROWS * PT_LD * 8 + PT_ROWS * PT_CLD;
-constexpr size_t PT_SMEM = 2 * (size_t)PT_STAGE_BYTES + sizeof(double2) * 64 + sizeof(double) * 32;
+// 1/d table, one private copy per lane (entry [idx][lane]): a lookup is conflict-free whatever the indices
+constexpr size_t PT_SMEM = 2 * (size_t)PT_STAGE_BYTES + sizeof(double) * 64 * 32 + sizeof(double) * 32;
+
+// diagonal of a site with nc conducting and nl leaking bonds; int -> double by the 2^52 trick (no I2F)
+__device__ __forceinline__ double pt_diag(int nc, int nl, const PcgParams& prm)
+{
+    const double two52 = 4503599627370496.0;
+    const double dc = __hiloint2double(0x43300000, nc) - two52, dl = __hiloint2double(0x43300000, nl) - two52;
+    return __fma_rn(dl, prm.gleak, __dmul_rn(dc, prm.g0));
+}
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid)
 {
@@ -339,21 +349,34 @@ __device__ __forceinline__ void pt_issue(const Geom& g, const PtStage& s, int x0
                                          const double* __restrict__ vr, const double* __restrict__ vp_in)
 {
     const int tid = threadIdx.x;
-    for (int k = tid; k < PT_ROWS * (PT_TX / 2); k += PT_THREADS) {           // tile columns, 2 doubles per copy
-        const int pr = k / (PT_TX / 2), cx = (k % (PT_TX / 2)) * 2;
-        const int gy = y0 + pr - 1, gx = x0 + cx;
-        if (gx >= g.m) continue;                                             // never read (and the halo column lives there)
-        const bool ok = gy >= 0 && gy < g.n;
-        const int64_t j = ok ? (int64_t)gy * g.m + gx : 0;
-        cp_async16(&s.sp[pr * PT_LD + 2 + cx], vp_in + j, ok && gy >= 1 && gy < g.n - 1);   // Dirichlet rows: p = 0
-        if (MODE == 0 || (pr >= 1 && pr <= PT_TY)) cp_async16(&s.sr[pr * PT_LD + 2 + cx], vr + j, ok);
+    {
+        // tile columns, 2 doubles per copy: the thread keeps its column pair and walks up the rows in
+        // steps of PT_THREADS / 64 (one pointer increment per copy instead of index arithmetic)
+        const int cx = (tid & 63) * 2, prb = tid >> 6, gx = x0 + cx;
+        if (gx < g.m) {                                                      // columns >= m are never read
+            const int64_t off = (int64_t)(y0 + prb - 1) * g.m + gx, step = (int64_t)(PT_THREADS / 64) * g.m;
+            const double* pp = vp_in + off;
+            const double* rp = vr + off;
+            int so = prb * PT_LD + 2 + cx;
+#pragma unroll
+            for (int it = 0; it < (PT_ROWS + PT_THREADS / 64 - 1) / (PT_THREADS / 64); ++it) {
+                const int pr = prb + it * (PT_THREADS / 64), gy = y0 + pr - 1;
+                if (pr < PT_ROWS) {
+                    const bool ok = (unsigned)gy < (unsigned)g.n;
+                    cp_async16(&s.sp[so], ok ? pp : vp_in, ok && gy >= 1 && gy < g.n - 1);       // Dirichlet rows: p = 0
+                    if (MODE == 0 || (pr >= 1 && pr <= PT_TY)) cp_async16(&s.sr[so], ok ? rp : vr, ok);
+                }
+                pp += step; rp += step; so += (PT_THREADS / 64) * PT_LD;
+            }
+        }
     }
-    for (int k = tid; k < PT_ROWS * (PT_TX / 16); k += PT_THREADS) {          // conduct bytes, 16 per copy
-        const int pr = k / (PT_TX / 16), cx = (k % (PT_TX / 16)) * 16;
+    if (tid < PT_ROWS * (PT_TX / 16)) {                                       // conduct bytes, 16 per copy
+        const int pr = tid / (PT_TX / 16), cx = (tid % (PT_TX / 16)) * 16;
         const int gy = y0 + pr - 1, gx = x0 + cx;
-        if (gx >= g.m) continue;
-        const bool ok = gy >= 0 && gy < g.n;
-        cp_async16(&s.scf[pr * PT_CLD + 16 + cx], cfull + (ok ? (int64_t)gy * g.m + gx : 0), ok);
+        if (gx < g.m) {
+            const bool ok = (unsigned)gy < (unsigned)g.n;
+            cp_async16(&s.scf[pr * PT_CLD + 16 + cx], cfull + (ok ? (int64_t)gy * g.m + gx : 0), ok);
+        }
     }
     if (tid < 2 * PT_ROWS) {                                                 // halo columns (periodic wrap aware)
         const int side = tid >= PT_ROWS, pr = tid - side * PT_ROWS;
@@ -382,13 +405,12 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
 {
     if (st->done) return;
     extern __shared__ __align__(16) unsigned char pt_raw[];
-    double2* tab = reinterpret_cast<double2*>(pt_raw + 2 * (size_t)PT_STAGE_BYTES);
-    double* sh = reinterpret_cast<double*>(tab + 64);
-    const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6;
-    if (tid < 64) {
-        int nc = tid >> 3, nl = tid & 7;
-        double d = (double)nc * prm.g0 + (double)nl * prm.gleak;
-        tab[tid] = make_double2(d, d > 0.0 ? 1.0 / d : 0.0);
+    double* dinv = reinterpret_cast<double*>(pt_raw + 2 * (size_t)PT_STAGE_BYTES);      // [64][32]
+    double* sh = dinv + 64 * 32;
+    const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6, lane = tid & 31;
+    for (int k = tid; k < 64 * 32; k += PT_THREADS) {
+        const double d = pt_diag((k >> 5) >> 3, (k >> 5) & 7, prm);
+        dinv[k] = d > 0.0 ? 1.0 / d : 0.0;
     }
     const double bk = st->bk, ak = st->ak;
     const double dg = prm.g0 - prm.gleak;
@@ -415,21 +437,25 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
         // ---- MODE 0: p_new = r / d + bk * p_old, in place on tile + halo (p is double-buffered in
         // HBM: neighbouring tiles still read p_old) ---------------------------------------------------
         if (MODE == 0) {
-            for (int c = tid; c < PT_ROWS * (PT_TX / 2); c += PT_THREADS) {
-                const int pr = c / (PT_TX / 2), cx = (c % (PT_TX / 2)) * 2;
-                const int gy = y0 + pr - 1, gx = x0 + cx;
-                if (gx >= g.m) continue;
-                double2 v = make_double2(0.0, 0.0);
-                if (gy >= 1 && gy < g.n - 1) {
-                    const double2 r2 = ld2(&s.sr[pr * PT_LD + 2 + cx]), p2 = ld2(&s.sp[pr * PT_LD + 2 + cx]);
-                    const unsigned c0 = s.scf[pr * PT_CLD + 16 + cx], c1 = s.scf[pr * PT_CLD + 17 + cx];
-                    const unsigned e0 = interior ? interior_ex<LAT>(gx) : neighbour_bits(g, gx, gy);
-                    const unsigned e1 = interior ? interior_ex<LAT>(gx + 1) : neighbour_bits(g, gx + 1, gy);
-                    const int n0 = __popc(c0), n1 = __popc(c1);
-                    v.x = r2.x * tab[(n0 << 3) | (__popc(e0) - n0)].y + bk * p2.x;
-                    v.y = r2.y * tab[(n1 << 3) | (__popc(e1) - n1)].y + bk * p2.y;
+            const int cx = (tid & 63) * 2, prb = tid >> 6, gxc = x0 + cx;
+            if (gxc < g.m) {
+                const unsigned e0i = interior_ex<LAT>(gxc), e1i = interior_ex<LAT>(gxc + 1);
+#pragma unroll
+                for (int it = 0; it < (PT_ROWS + PT_THREADS / 64 - 1) / (PT_THREADS / 64); ++it) {
+                    const int pr = prb + it * (PT_THREADS / 64), gy = y0 + pr - 1;
+                    if (pr >= PT_ROWS) continue;
+                    double2 v = make_double2(0.0, 0.0);
+                    if (gy >= 1 && gy < g.n - 1) {
+                        const double2 r2 = ld2(&s.sr[pr * PT_LD + 2 + cx]), p2 = ld2(&s.sp[pr * PT_LD + 2 + cx]);
+                        const unsigned c01 = *reinterpret_cast<const unsigned short*>(&s.scf[pr * PT_CLD + 16 + cx]);
+                        const unsigned e0 = interior ? e0i : neighbour_bits(g, gxc, gy);
+                        const unsigned e1 = interior ? e1i : neighbour_bits(g, gxc + 1, gy);
+                        const int n0 = __popc(c01 & 0xffu), n1 = __popc(c01 >> 8);
+                        v.x = r2.x * dinv[(((n0 << 3) | (__popc(e0) - n0)) << 5) + lane] + bk * p2.x;
+                        v.y = r2.y * dinv[(((n1 << 3) | (__popc(e1) - n1)) << 5) + lane] + bk * p2.y;
+                    }
+                    st2(&s.sp[pr * PT_LD + 2 + cx], v);
                 }
-                st2(&s.sp[pr * PT_LD + 2 + cx], v);
             }
             if (tid < 2 * PT_ROWS) {
                 const int side = tid >= PT_ROWS, pr = tid - side * PT_ROWS;
@@ -442,69 +468,80 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
                     const unsigned cf = s.scf[pr * PT_CLD + (side ? 16 + PT_TX : 12) + (hx & 3)];
                     const unsigned ex = neighbour_bits(g, hx, gy);
                     const int nc = __popc(cf);
-                    v = s.sr[pr * PT_LD + col] * tab[(nc << 3) | (__popc(ex) - nc)].y + bk * s.sp[pr * PT_LD + col];
+                    v = s.sr[pr * PT_LD + col] * dinv[(((nc << 3) | (__popc(ex) - nc)) << 5) + lane] + bk * s.sp[pr * PT_LD + col];
                 }
                 s.sp[pr * PT_LD + col] = v;
             }
             __syncthreads();
         }
 
-        // ---- stencil: q = A p from shared memory; MODE 0: dot(p, q); MODE 1: r -= ak q, x += ak p ----
+        // ---- stencil: q = A p from shared memory; MODE 0: dot(p, q); MODE 1: r -= ak q, x += ak p.
+        // A thread owns 2 columns x PT_RPT consecutive rows and slides a 3-row window up the tile ------
         const int gx = x0 + 2 * tx;
         double acc0 = 0.0, acc1 = 0.0;
+        {
+            const int r0 = ty * PT_RPT;
+            const double* c = &s.sp[(r0 + 1) * PT_LD + 2 + 2 * tx];
+            double2 dn = ld2(c - PT_LD), cc = ld2(c);
+            double dlf = c[-PT_LD - 1], drt = c[-PT_LD + 2];      // row below: x-1 and x+2 (triangular diagonals)
 #pragma unroll
-        for (int ly = ty; ly < PT_TY; ly += PT_THREADS / 64) {
-            const int gy = y0 + ly;
-            if (gy < 1 || gy >= g.n - 1 || gx >= g.m) continue;
-            const int64_t i = (int64_t)gy * g.m + gx;
-            const unsigned cf0 = s.scf[(ly + 1) * PT_CLD + 16 + 2 * tx], cf1 = s.scf[(ly + 1) * PT_CLD + 17 + 2 * tx];
-            const double* c = &s.sp[(ly + 1) * PT_LD + 2 + 2 * tx];
-            const double2 cc = ld2(c), up = ld2(c + PT_LD), dn = ld2(c - PT_LD);
-            const double lf = c[-1], rt = c[2];
-            unsigned e0, e1;
-            double all0, all1;
-            if (interior) {
-                e0 = interior_ex<LAT>(gx); e1 = interior_ex<LAT>(gx + 1);
-                all0 = (cc.y + lf) + (up.x + dn.x);
-                all1 = (rt + cc.x) + (up.y + dn.y);
-                if (LAT == LAT_TRIANGULAR) { all0 += c[PT_LD - 1] + up.y; all1 += dn.x + c[-PT_LD + 2]; }
-            } else {
-                e0 = neighbour_bits(g, gx, gy); e1 = neighbour_bits(g, gx + 1, gy);
-                all0 = 0.0; all1 = 0.0;
-                if (e0 & NB_E) all0 += cc.y;  if (e0 & NB_W) all0 += lf;  if (e0 & NB_N) all0 += up.x;  if (e0 & NB_S) all0 += dn.x;
-                if (e1 & NB_E) all1 += rt;    if (e1 & NB_W) all1 += cc.x; if (e1 & NB_N) all1 += up.y; if (e1 & NB_S) all1 += dn.y;
+            for (int j = 0; j < PT_RPT; ++j, c += PT_LD) {
+                const int ly = r0 + j, gy = y0 + ly;
+                const double2 up = ld2(c + PT_LD);
+                const double lf = c[-1], rt = c[2];
+                const bool valid = gy >= 1 && gy < g.n - 1 && gx < g.m;
+                const unsigned c01 = *reinterpret_cast<const unsigned short*>(&s.scf[(ly + 1) * PT_CLD + 16 + 2 * tx]);
+                const unsigned cf0 = c01 & 0xffu, cf1 = c01 >> 8;
+                unsigned e0, e1;
+                double all0, all1;
+                if (interior) {
+                    e0 = interior_ex<LAT>(gx); e1 = interior_ex<LAT>(gx + 1);
+                    all0 = (cc.y + lf) + (up.x + dn.x);
+                    all1 = (rt + cc.x) + (up.y + dn.y);
+                    if (LAT == LAT_TRIANGULAR) { all0 += c[PT_LD - 1] + up.y; all1 += dn.x + drt; }
+                } else {
+                    e0 = neighbour_bits(g, gx, gy); e1 = neighbour_bits(g, gx + 1, gy);
+                    all0 = 0.0; all1 = 0.0;
+                    if (e0 & NB_E) all0 += cc.y;  if (e0 & NB_W) all0 += lf;  if (e0 & NB_N) all0 += up.x;  if (e0 & NB_S) all0 += dn.x;
+                    if (e1 & NB_E) all1 += rt;    if (e1 & NB_W) all1 += cc.x; if (e1 & NB_N) all1 += up.y; if (e1 & NB_S) all1 += dn.y;
+                    if (LAT == LAT_TRIANGULAR) {
+                        if (e0 & NB_NW) all0 += c[PT_LD - 1]; if (e0 & NB_NE) all0 += up.y;
+                        if (e1 & NB_SW) all1 += dn.x;         if (e1 & NB_SE) all1 += drt;
+                    }
+                }
+                double con0 = 0.0, con1 = 0.0;    // conducting neighbours (cfull bits only on existing bonds)
+                if (cf0 & NB_E) con0 += cc.y;  if (cf0 & NB_W) con0 += lf;   if (cf0 & NB_N) con0 += up.x;  if (cf0 & NB_S) con0 += dn.x;
+                if (cf1 & NB_E) con1 += rt;    if (cf1 & NB_W) con1 += cc.x; if (cf1 & NB_N) con1 += up.y;  if (cf1 & NB_S) con1 += dn.y;
                 if (LAT == LAT_TRIANGULAR) {
-                    if (e0 & NB_NW) all0 += c[PT_LD - 1]; if (e0 & NB_NE) all0 += up.y;
-                    if (e1 & NB_SW) all1 += dn.x;         if (e1 & NB_SE) all1 += c[-PT_LD + 2];
+                    if (cf0 & NB_NW) con0 += c[PT_LD - 1]; if (cf0 & NB_NE) con0 += up.y;
+                    if (cf1 & NB_SW) con1 += dn.x;         if (cf1 & NB_SE) con1 += drt;
                 }
-            }
-            double con0 = 0.0, con1 = 0.0;        // conducting neighbours (cfull bits only on existing bonds)
-            if (cf0 & NB_E) con0 += cc.y;  if (cf0 & NB_W) con0 += lf;   if (cf0 & NB_N) con0 += up.x;  if (cf0 & NB_S) con0 += dn.x;
-            if (cf1 & NB_E) con1 += rt;    if (cf1 & NB_W) con1 += cc.x; if (cf1 & NB_N) con1 += up.y;  if (cf1 & NB_S) con1 += dn.y;
-            if (LAT == LAT_TRIANGULAR) {
-                if (cf0 & NB_NW) con0 += c[PT_LD - 1]; if (cf0 & NB_NE) con0 += up.y;
-                if (cf1 & NB_SW) con1 += dn.x;         if (cf1 & NB_SE) con1 += c[-PT_LD + 2];
-            }
-            const int n0 = __popc(cf0), n1 = __popc(cf1);
-            const double2 t0 = tab[(n0 << 3) | (__popc(e0) - n0)], t1 = tab[(n1 << 3) | (__popc(e1) - n1)];
-            double2 q;
-            q.x = t0.x * cc.x - (prm.gleak * all0 + dg * con0);
-            q.y = t1.x * cc.y - (prm.gleak * all1 + dg * con1);
-            if (MODE == 0) {
-                st2(vp_out + i, cc);
-                acc0 += cc.x * q.x + cc.y * q.y;
-            } else {
-                double2 r = ld2(&s.sr[(ly + 1) * PT_LD + 2 + 2 * tx]);
-                r.x -= ak * q.x; r.y -= ak * q.y;
-                st2(vr + i, r);
-                if (keep_x || gy == 1 || gy == g.n - 2) {
-                    double2 x = ld2(vx + i);
-                    x.x += ak * cc.x; x.y += ak * cc.y;
-                    st2(vx + i, x);
+                const int n0 = __popc(cf0), n1 = __popc(cf1), l0 = __popc(e0) - n0, l1 = __popc(e1) - n1;
+                double2 q;
+                q.x = pt_diag(n0, l0, prm) * cc.x - (prm.gleak * all0 + dg * con0);
+                q.y = pt_diag(n1, l1, prm) * cc.y - (prm.gleak * all1 + dg * con1);
+                if (valid) {
+                    const int64_t i = (int64_t)gy * g.m + gx;
+                    if (MODE == 0) {
+                        st2(vp_out + i, cc);
+                        acc0 += cc.x * q.x + cc.y * q.y;
+                    } else {
+                        double2 r = ld2(&s.sr[(ly + 1) * PT_LD + 2 + 2 * tx]);
+                        r.x -= ak * q.x; r.y -= ak * q.y;
+                        st2(vr + i, r);
+                        if (keep_x || gy == 1 || gy == g.n - 2) {
+                            double2 x = ld2(vx + i);
+                            x.x += ak * cc.x; x.y += ak * cc.y;
+                            st2(vx + i, x);
+                        }
+                        acc0 += r.x * r.x * dinv[(((n0 << 3) | l0) << 5) + lane] + r.y * r.y * dinv[(((n1 << 3) | l1) << 5) + lane];
+                        acc1 += r.x * r.x + r.y * r.y;
+                    }
                 }
-                acc0 += r.x * r.x * t0.y + r.y * r.y * t1.y;
-                acc1 += r.x * r.x + r.y * r.y;
+                dlf = lf; drt = rt;
+                dn = cc; cc = up;
             }
+            (void)dlf;
         }
         // per-tile partial sums (block_sum synchronises: every thread is done with this stage afterwards)
         if (MODE == 0) {
