@@ -43,6 +43,8 @@ extern "C" {
 #define PERC_E_STATE     (-4)  /* call order (e.g. conduct before label)        */
 #define PERC_E_SIZE      (-5)  /* lattice too large for 32-bit labels           */
 #define PERC_E_NOSPAN    (-6)  /* requested cluster does not span               */
+#define PERC_E_NCCL      (-7)  /* libnccl.so.2 could not be loaded (slab mode)    */
+#define PERC_E_IFACE     (-8)  /* ranks disagree on an interface row (slab mode) */
 
 /* ---- geometry (host-only index arithmetic; no device needed) ------------------------------ */
 /* nb formulas Sq/site.f:89-93, Tri/site.f:91-95 */
@@ -123,6 +125,35 @@ int32_t perc_conduct_g(const int64_t *h, const int32_t *cluster_id, const double
                        const double *gleak, const double *tol, const int32_t *itmax, const double *read_thresh,
                        double *Gtop, double *Gbot, int32_t *iter, double *err);
 int32_t perc_get_voltage(const int64_t *h, double *Vint);             /* Vint(t-2m), Sq/bondc.f:545 */
+
+/* ---- one lattice decomposed into row slabs over several GPUs (north star: L = 65536 over 8 x B200) ----
+ * The reference has no counterpart (serial program, t <= 10^6, Sq/site.f:37); the entry points mirror
+ * the single-GPU ones.  One process per GPU; rank r of nranks holds rows [n*r/nranks, n*(r+1)/nranks) of
+ * the m x n lattice plus one halo row on each inner side.  The occupancy comes from the generator
+ * (element keys are functions of the lattice-wide element id, so the realization is the one the
+ * single-GPU handle draws); perc_label labels the slab, all-gathers the interface rows over NCCL and
+ * stitches the clusters with a union-find every rank runs redundantly; perc_conduct_g exchanges one halo
+ * row of the residual per iteration (ncclSend/ncclRecv) and all-reduces the two dot products.
+ * Lattice-wide labels / sizes / counts are 64-bit (t = 2^32 at L = 65536). */
+int32_t perc_create_slab(int64_t *h, const int32_t *lattice, const int32_t *m, const int32_t *n,
+                         const int32_t *pbc, const int32_t *device, const int32_t *nranks, const int32_t *rank);
+/* NCCL bootstrap: rank 0 calls perc_comm_unique_id, the host distributes the 128 bytes (MPI_Bcast in a
+ * Fortran driver), every rank calls perc_comm_init.  NCCL is loaded at run time (libnccl.so.2). */
+int32_t perc_comm_unique_id(uint8_t *id128);
+int32_t perc_comm_init(const int64_t *h, const uint8_t *id128);
+int32_t perc_slab_rows(const int64_t *h, int32_t *ya, int32_t *yb);     /* owned rows [ya, yb), 0-based */
+int32_t perc_generate_i8(const int64_t *h, const int64_t *seed, const int64_t *stream,
+                         const int64_t *ks, const int64_t *kb);         /* perc_generate with 64-bit fill counts */
+int32_t perc_summary_i8(const int64_t *h, int64_t *ncl, int64_t *maxcs, int64_t *maxcn, int64_t *nspan);
+int32_t perc_span_i8(const int64_t *h, const int32_t *max_ids, int32_t *nspan, int64_t *ids, int64_t *sizes);
+/* s((yb-ya)*m): lattice-wide canonical labels of the rows this rank owns */
+int32_t perc_get_site_labels_i8(const int64_t *h, int64_t *s);
+/* the stitch's host union-find on its own (no device; CPU tests): gathered = nranks blocks of 5*m+8 words
+ * (layout: percolation_b200/csrc/slab.h); out_summary(5) = ncl, nlone, maxcs, maxcn, nspan; out_pairs(4,k) =
+ * (root id, representative id, class label, class size) of every interface cluster the calling rank holds */
+int32_t perc_stitch_host(const int32_t *nranks, const int32_t *rank, const int32_t *m, const int64_t *gathered,
+                         int64_t *out_summary, const int32_t *max_span, int64_t *span_ids, int64_t *span_sizes,
+                         const int32_t *max_pairs, int32_t *npairs, int64_t *out_pairs);
 
 /* ---- instrumentation ---------------------------------------------------------------------------- */
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */

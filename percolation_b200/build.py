@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libperc_b200.so")
-SOURCES = ["abi.cu", "occupancy.cu", "ccl.cu", "pcg.cu"]
+SOURCES = ["abi.cu", "occupancy.cu", "ccl.cu", "pcg.cu", "slab.cu"]
 HEADERS = ["context.h", "geometry.cuh", "philox.cuh", os.path.join("..", "..", "include", "perc_abi.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]
@@ -23,7 +23,7 @@ def needs_build():
     if not os.path.exists(SO):
         return True
     mt = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS + ["ccl_tile.cuh"]] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS + ["ccl_tile.cuh", "slab.h"]] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > mt for d in deps)
 
 
@@ -32,7 +32,7 @@ def build(force=False, verbose=False):
         return SO
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + \
-        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", SO]
+        [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-o", SO]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -32,6 +32,22 @@ void* ctx_dev_stage(Ctx* c, size_t bytes)
     return c->d_stage;
 }
 
+// rank tables exist only once a caller supplies an order / flags (the generator needs none)
+int ctx_ensure_ranks(Ctx* c, bool sites, bool bonds)
+{
+    const int64_t t = c->g.t;
+    if (c->nranks > 1) return PERC_E_STATE;              // slab handles take their occupancy from the generator
+    if (sites && !c->srank) {
+        PERC_CUDA(cudaMalloc(&c->srank, sizeof(int32_t) * t));
+        PERC_CUDA(cudaMemsetAsync(c->srank, 0x7f, sizeof(int32_t) * t, c->stream));
+    }
+    if (bonds && !c->brank) {
+        PERC_CUDA(cudaMalloc(&c->brank, sizeof(int32_t) * t * c->g.ndir));
+        PERC_CUDA(cudaMemsetAsync(c->brank, 0x7f, sizeof(int32_t) * t * c->g.ndir, c->stream));
+    }
+    return 0;
+}
+
 void* ctx_host_stage(Ctx* c, size_t bytes)
 {
     if (bytes > c->h_stage_bytes) {
@@ -48,8 +64,6 @@ int ctx_alloc(Ctx* c)
     PERC_CUDA(cudaSetDevice(c->device));
     PERC_CUDA(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
     PERC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    PERC_CUDA(cudaMalloc(&c->srank, sizeof(int32_t) * t));
-    PERC_CUDA(cudaMalloc(&c->brank, sizeof(int32_t) * t * c->g.ndir));
     PERC_CUDA(cudaMalloc(&c->mask, t));
     PERC_CUDA(cudaMalloc(&c->label, sizeof(int32_t) * t));
     PERC_CUDA(cudaMalloc(&c->size, sizeof(int32_t) * t));
@@ -62,8 +76,6 @@ int ctx_alloc(Ctx* c)
     PERC_CUDA(cudaMalloc(&c->d_hist, sizeof(unsigned long long) * (4096 + 8)));
     c->cand_cap = 8192;
     PERC_CUDA(cudaMalloc(&c->d_cand, sizeof(unsigned long long) * 2 * c->cand_cap));
-    PERC_CUDA(cudaMemsetAsync(c->srank, 0x7f, sizeof(int32_t) * t, c->stream));
-    PERC_CUDA(cudaMemsetAsync(c->brank, 0x7f, sizeof(int32_t) * t * c->g.ndir, c->stream));
     for (auto& e : c->ev) PERC_CUDA(cudaEventCreate(&e));
     PERC_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
@@ -86,6 +98,9 @@ void ctx_free(Ctx* c)
 {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    slab_comm_destroy(c);
+    if (c->d_iface) cudaFree(c->d_iface);
+    if (c->h_iface) cudaFreeHost(c->h_iface);
     void* ptrs[] = {c->srank, c->brank, c->mask, c->label, c->size, c->rootlist, c->d_sum, c->d_pcg,
                     c->d_hist, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vp2, c->vq, c->partial, c->d_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -106,10 +121,10 @@ static int check_geom(int lattice, int m, int n, int pbc)
     return 0;
 }
 
-static int set_fill(Ctx* c, int ks, int kb)
+static int set_fill(Ctx* c, int64_t ks, int64_t kb)
 {
     if (ks >= 0) {
-        if (ks > c->g.t) return PERC_E_ARG;
+        if (ks > c->g.tg) return PERC_E_ARG;
         if (c->site_src == SRC_PHILOX) { int rc = occ_generate(c, c->seed, c->stream_id, ks, -1); if (rc) return rc; }
         c->ks = ks;
     }
@@ -290,6 +305,7 @@ int32_t perc_summary(const int64_t* h, int64_t* ncl, int32_t* maxcs, int32_t* ma
 {
     GET_CTX(h);
     if (!c->labeled) return PERC_E_STATE;
+    if (c->nranks > 1) return PERC_E_STATE;              // lattice-wide values need 64 bits: perc_summary_i8
     const Summary& s = c->h_sum;
     int32_t ms = (int32_t)(s.maxpack >> 32);
     int32_t mn = ms ? (int32_t)(0xffffffffu - (unsigned)(s.maxpack & 0xffffffffu)) : 0;
@@ -452,7 +468,13 @@ static int conduct_common(Ctx* c, const int32_t* cluster_id, const double* Va, c
     if (!c->labeled) return PERC_E_STATE;
     if (c->g.n < 3 || *Va == 0.0 || *itmax < 0) return PERC_E_ARG;
     int cid = *cluster_id;
-    if (cid == 0) {
+    if (c->nranks > 1) {
+        // slab of a decomposed lattice: the default spanning cluster (smallest lattice-wide label); every
+        // rank solves with the label that cluster carries locally (0: no part of it lives here)
+        if (cid != 0) return PERC_E_ARG;
+        if (c->h_span_gid.empty()) return PERC_E_NOSPAN;
+        cid = slab_local_label_of(c, c->h_span_gid[0]);
+    } else if (cid == 0) {
         if (c->h_span_ids.empty()) return PERC_E_NOSPAN;
         cid = c->h_span_ids[0];
     } else {
@@ -489,6 +511,126 @@ int32_t perc_get_voltage(const int64_t* h, double* Vint)
     GET_CTX(h);
     if (!c->solved || !c->have_x || !Vint) return PERC_E_STATE;
     return download(c, Vint, c->vx + c->g.m, sizeof(double) * (c->g.t - 2 * (int64_t)c->g.m));
+}
+
+// ---- one lattice decomposed into row slabs over several GPUs -------------------------------------
+int32_t perc_create_slab(int64_t* h, const int32_t* lattice, const int32_t* m, const int32_t* n,
+                         const int32_t* pbc, const int32_t* device, const int32_t* nranks, const int32_t* rank)
+{
+    if (!h || !lattice || !m || !n || !pbc || !device || !nranks || !rank) return PERC_E_ARG;
+    if (*lattice != LAT_SQUARE && *lattice != LAT_TRIANGULAR) return PERC_E_ARG;
+    if (*m < 2 || *n < 2 || (*pbc != 0 && *pbc != 1) || (*pbc && *m < 3)) return PERC_E_ARG;
+    if (*lattice == LAT_TRIANGULAR && (*m & 1)) return PERC_E_ODD_M;
+    if (*nranks < 1 || *rank < 0 || *rank >= *nranks) return PERC_E_ARG;
+    if (*n / *nranks < 2) return PERC_E_ARG;                         // every slab needs two rows of its own
+    Geom g = make_slab_geom(*lattice, *m, *n, *pbc, *nranks, *rank);
+    if (g.t > 0x7ffffff0LL) return PERC_E_SIZE;                      // rank-local labels are 32-bit
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return (int)e;
+    if (*device < 0 || *device >= ndev) return PERC_E_ARG;
+    Ctx* c = new Ctx();
+    c->g = g;
+    c->device = *device;
+    c->nranks = *nranks; c->rank = *rank;
+    int rc = ctx_alloc(c);
+    if (rc) { ctx_free(c); delete c; return rc; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    *h = g_next++;
+    g_ctx[*h] = c;
+    return 0;
+}
+
+int32_t perc_comm_unique_id(uint8_t* id128)
+{
+    if (!id128) return PERC_E_ARG;
+    return slab_unique_id(id128);
+}
+
+int32_t perc_comm_init(const int64_t* h, const uint8_t* id128)
+{
+    GET_CTX(h);
+    if (!id128) return PERC_E_ARG;
+    if (c->nranks == 1) return 0;
+    return slab_comm_init(c, id128);
+}
+
+int32_t perc_slab_rows(const int64_t* h, int32_t* ya, int32_t* yb)
+{
+    GET_CTX(h);
+    if (ya) *ya = c->g.y0 + c->g.own_lo;
+    if (yb) *yb = c->g.y0 + c->g.own_hi;
+    return 0;
+}
+
+int32_t perc_generate_i8(const int64_t* h, const int64_t* seed, const int64_t* stream, const int64_t* ks, const int64_t* kb)
+{
+    GET_CTX(h);
+    if (!seed || !stream || !ks || !kb) return PERC_E_ARG;
+    return occ_generate(c, (unsigned long long)*seed, (unsigned long long)*stream, *ks, *kb);
+}
+
+int32_t perc_summary_i8(const int64_t* h, int64_t* ncl, int64_t* maxcs, int64_t* maxcn, int64_t* nspan)
+{
+    GET_CTX(h);
+    if (!c->labeled) return PERC_E_STATE;
+    if (c->nranks > 1) {
+        const StitchResult& R = c->stitch;
+        if (ncl) *ncl = R.ncl + R.nlone;
+        if (maxcs) *maxcs = R.maxcs ? R.maxcs : (R.nlone > 0 ? 1 : 0);
+        if (maxcn) *maxcn = R.maxgid;
+        if (nspan) *nspan = (int64_t)R.span_gid.size();
+        return 0;
+    }
+    int32_t ms = 0, mn = 0, ns = 0;
+    int rc = perc_summary(h, ncl, &ms, &mn, &ns);
+    if (maxcs) *maxcs = ms;
+    if (maxcn) *maxcn = mn;
+    if (nspan) *nspan = ns;
+    return rc;
+}
+
+int32_t perc_span_i8(const int64_t* h, const int32_t* max_ids, int32_t* nspan, int64_t* ids, int64_t* sizes)
+{
+    GET_CTX(h);
+    if (!c->labeled || !max_ids || !nspan) return PERC_E_STATE;
+    *nspan = (int32_t)c->h_span_gid.size();
+    int k = (int)c->h_span_gid.size();
+    if (k > *max_ids) k = *max_ids;
+    for (int j = 0; j < k; ++j) { if (ids) ids[j] = c->h_span_gid[j]; if (sizes) sizes[j] = c->h_span_total[j]; }
+    return 0;
+}
+
+int32_t perc_get_site_labels_i8(const int64_t* h, int64_t* s)
+{
+    GET_CTX(h);
+    if (!c->labeled || !s) return PERC_E_STATE;
+    return slab_export_labels(c, s);
+}
+
+// the redundant host union-find of the stitch, on its own (no device): gathered = nranks blocks of
+// 5*m + 8 int64 words (layout in csrc/slab.h).  out_summary[5] = ncl, nlone, maxcs, maxcn, nspan;
+// pairs (root id, representative id, class label, class size) of the calling rank go to out_pairs[4*k..].
+int32_t perc_stitch_host(const int32_t* nranks, const int32_t* rank, const int32_t* m, const int64_t* gathered,
+                         int64_t* out_summary, const int32_t* max_span, int64_t* span_ids, int64_t* span_sizes,
+                         const int32_t* max_pairs, int32_t* npairs, int64_t* out_pairs)
+{
+    if (!nranks || !rank || !m || !gathered || !out_summary || !max_span || !max_pairs || !npairs) return PERC_E_ARG;
+    StitchResult R;
+    stitch_host(*nranks, *rank, *m, gathered, &R);
+    if (R.error) return PERC_E_ARG;
+    out_summary[0] = R.ncl; out_summary[1] = R.nlone; out_summary[2] = R.maxcs; out_summary[3] = R.maxgid;
+    out_summary[4] = (int64_t)R.span_gid.size();
+    for (int k = 0; k < (int)R.span_gid.size() && k < *max_span; ++k) {
+        if (span_ids) span_ids[k] = R.span_gid[k];
+        if (span_sizes) span_sizes[k] = R.span_size[k];
+    }
+    *npairs = (int32_t)R.root_gid.size();
+    for (int k = 0; k < *npairs && k < *max_pairs && out_pairs; ++k) {
+        out_pairs[4 * k + 0] = R.root_gid[k]; out_pairs[4 * k + 1] = R.rep_gid[k];
+        out_pairs[4 * k + 2] = R.class_gid[k]; out_pairs[4 * k + 3] = R.class_total[k];
+    }
+    return 0;
 }
 
 int32_t perc_launch_count(const int64_t* h, int64_t* count)

@@ -47,7 +47,7 @@ ccl_local_kernel(Geom g, const uint8_t* __restrict__ mask, int32_t* __restrict__
     tile_phase2_level<LAT, 4>(s, tid); __syncthreads();
     tile_phase2_level<LAT, 5>(s, tid); __syncthreads();
     tile_phase2_level<LAT, 6>(s, tid); __syncthreads();
-    tile_phase3<LAT, KIND>(s, g, x0, tid, r);
+    tile_phase3<LAT, KIND>(s, g, x0, y0, tid, r);
     __syncthreads();
     tile_phase4_fill(s, g, x0, y0, tid, r, size);
     __syncthreads();
@@ -74,7 +74,7 @@ ccl_merge_kernel(Geom g, const uint8_t* __restrict__ mask, int32_t* __restrict__
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 ccl_rootfix_kernel(int32_t* __restrict__ label, int32_t* __restrict__ size, const int32_t* __restrict__ rootlist,
-                   Summary* __restrict__ sum)
+                   Summary* __restrict__ sum, int count)
 {
     const unsigned nroots = sum->nroots;
     unsigned cnt = 0;
@@ -87,6 +87,7 @@ ccl_rootfix_kernel(int32_t* __restrict__ label, int32_t* __restrict__ size, cons
         cnt += isroot;
         if (pk > best) best = pk;
     }
+    if (!count) return;                 // slab handles count afterwards (a root may own no site here)
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     for (int o = 16; o; o >>= 1) {
         unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
@@ -274,20 +275,40 @@ int ccl_run(Ctx* c, int kind)
     }
     PERC_CUDA(cudaEventRecord(c->ev[3], st));
 
-    ccl_rootfix_kernel<<<148 * 8, 256, 0, st>>>(c->label, c->size, c->rootlist, c->d_sum);
+    const bool slab = c->nranks > 1;
+    ccl_rootfix_kernel<<<148 * 8, 256, 0, st>>>(c->label, c->size, c->rootlist, c->d_sum, slab ? 0 : 1);
     int64_t nquad = g.t / 4;
     if (nquad) ccl_flatten4_kernel<<<nblk(nquad), 256, 0, st>>>(nquad, c->label);
     if (g.t % 4) ccl_flatten1_kernel<<<1, 256, 0, st>>>(nquad * 4, g.t, c->label);
     c->launches += 2 + (g.t % 4 ? 1 : 0);
     PERC_CUDA(cudaEventRecord(c->ev[4], st));
 
-    ccl_span_kernel<<<1, 1024, sizeof(unsigned) * ((g.m + 31) / 32), st>>>(g.m, (int64_t)(g.n - 1) * g.m, c->label, c->size, c->d_sum);
-    c->launches++;
+    if (slab) {
+        // slab of a decomposed lattice: exact rank-local counts, then the clusters are stitched across the
+        // interfaces (all-gather of the interface rows + redundant union-find); spanning comes out of that
+        rc = slab_count_roots(c);
+        if (rc) return rc;
+        rc = slab_stitch(c);
+        if (rc) return rc;
+    } else {
+        ccl_span_kernel<<<1, 1024, sizeof(unsigned) * ((g.m + 31) / 32), st>>>(g.m, (int64_t)(g.n - 1) * g.m, c->label, c->size, c->d_sum);
+        c->launches++;
+    }
     PERC_CUDA(cudaEventRecord(c->ev[5], st));
     PERC_CUDA(cudaGetLastError());
     c->kind = kind;
     c->labeled = true;
-    return ccl_fetch_summary(c);
+    rc = ccl_fetch_summary(c);
+    if (rc) return rc;
+    if (slab) {
+        c->h_span_gid = c->stitch.span_gid; c->h_span_total = c->stitch.span_size;
+        c->h_sum.nspan = (int)c->h_span_gid.size();
+        c->h_span_ids.clear(); c->h_span_sizes.clear();
+    } else {
+        c->h_span_gid.assign(c->h_span_ids.begin(), c->h_span_ids.end());
+        c->h_span_total.assign(c->h_span_sizes.begin(), c->h_span_sizes.end());
+    }
+    return 0;
 }
 
 int ccl_fetch_summary(Ctx* c)

@@ -307,14 +307,16 @@ PERC_HD void tile_phase2_level(TileSmem& s, int tid)
 // owner site is unoccupied (dangling onto this site).  A bond with no occupied end is a lone
 // size-1 cluster (Sq/sitebond.f:231-242), counted into s.lone.
 template <int LAT, int KIND>
-PERC_HD void tile_phase3(TileSmem& s, const Geom& g, int x0, int tid, TileRegs& r)
+PERC_HD void tile_phase3(TileSmem& s, const Geom& g, int x0, int y0, int tid, TileRegs& r)
 {
     const int w = tid % CT_NW, ly = tid / CT_NW, pr = ly + 1;
     const int base = ly * CT_TW + (w << 5);
     const uint32_t S = s.pS[pr][w], T = s.pT[ly][w];
     const uint32_t E = s.pE[pr][w], N = s.pN[pr][w], NW = s.pNW[pr][w], NE = s.pNE[pr][w];
     uint32_t inW = 0, inS = 0, inSW = 0, inSE = 0;
-    if (KIND == KIND_MIXED) {
+    // slab handles: only the rows this rank owns are counted (halo rows are the neighbour's)
+    const bool owned = y0 + ly >= g.own_lo && y0 + ly < g.own_hi;
+    if (KIND == KIND_MIXED && owned) {
         const int xe = g.m - x0 < CT_TW ? g.m - x0 : CT_TW;
         const int wl = (xe - 1) >> 5, bl = (xe - 1) & 31;          // word / bit of the last real column
         auto dang = [](uint8_t v, unsigned bit) -> uint32_t { return ((v & bit) && !(v & MASK_SITE)) ? 1u : 0u; };
@@ -382,7 +384,8 @@ PERC_HD void tile_phase3(TileSmem& s, const Geom& g, int x0, int tid, TileRegs& 
         s.lab[base + a] = root;
         if (root == base + a) rootbits |= 1u << a;
         int wgt;
-        if (KIND == KIND_SITE) wgt = popc32(seg);
+        if (!owned) wgt = 0;
+        else if (KIND == KIND_SITE) wgt = popc32(seg);
         else {
             wgt = popc32(seg & E) + popc32(seg & N);
             if (LAT == LAT_TRIANGULAR) wgt += popc32(seg & NW) + popc32(seg & NE);
@@ -433,6 +436,7 @@ PERC_HD void tile_phase4_fill(TileSmem& s, const Geom& g, int x0, int y0, int ti
         if (c < 0) { ++nloc; continue; }
         const int32_t gl = tile_global_label(g, x0, y0, node);
         size[gl - 1] = c;
+        if (c == 0) continue;                    // lives in halo rows only: the neighbour rank counts it
         ++nclosed;
         unsigned long long pk = ((unsigned long long)(unsigned)c << 32) | (unsigned long long)(0xffffffffu - (unsigned)gl);
         if (pk > best) best = pk;

@@ -5,6 +5,7 @@
 #include <vector>
 #include "geometry.cuh"
 #include "ccl_tile.cuh"
+#include "slab.h"
 
 namespace perc {
 
@@ -14,6 +15,7 @@ constexpr int RANK_NONE = 0x7fffffff;
 struct PcgState {
     double bknum, bkden, akden, ak, bk, rr, bnrm, err, tol;
     double Itop, Ibot;
+    double red[4];                     // slab mode: rank-local sums waiting for the all-reduce
     int iter, itmax, done;
     unsigned int ticket_a, ticket_b;   // last-block-done counters
 };
@@ -31,13 +33,23 @@ struct Ctx {
     Geom g;
     int device = 0;
     int num_sms = 148;
+
+    // ---- slab decomposition (SURVEY 8e mode 2); nranks = 1: the whole lattice lives here
+    int nranks = 1, rank = 0;
+    void* comm = nullptr;                // ncclComm_t
+    int64_t* d_iface = nullptr;          // [nranks + 1] interface blocks (all-gather target + own block)
+    int64_t* h_iface = nullptr;          // pinned
+    StitchResult stitch;
+    std::vector<int32_t> tab_rep;        // interface classes held by this rank: representative root (ascending)
+    std::vector<int64_t> tab_gid, tab_total;   //   -> lattice-wide label and size
+    std::vector<int64_t> h_span_gid, h_span_total;
     cudaStream_t stream = nullptr;
 
     // ---- occupancy inputs
     int32_t* srank = nullptr;     // [t]        rank of the site in the fill order
     int32_t* brank = nullptr;     // [ndir][t]  rank of the bond owned by (site, dir)
     int site_src = SRC_NONE, bond_src = SRC_NONE;
-    int ks = 0, kb = 0;
+    int64_t ks = 0, kb = 0;
     unsigned long long seed = 0, stream_id = 0;
     PhiloxThreshold thr_site{}, thr_bond{};
 
@@ -88,12 +100,13 @@ struct Ctx {
 int ctx_alloc(Ctx* c);
 void ctx_free(Ctx* c);
 void* ctx_host_stage(Ctx* c, size_t bytes);
+int ctx_ensure_ranks(Ctx* c, bool sites, bool bonds);
 void* ctx_dev_stage(Ctx* c, size_t bytes);
 
 int occ_upload_site_order(Ctx* c, const int32_t* order);
 int occ_upload_bond_order(Ctx* c, const int32_t* border);
 int occ_upload_flags(Ctx* c, const uint8_t* socc, const uint8_t* bocc);
-int occ_generate(Ctx* c, unsigned long long seed, unsigned long long stream, int ks, int kb);
+int occ_generate(Ctx* c, unsigned long long seed, unsigned long long stream, int64_t ks, int64_t kb);
 int occ_export(Ctx* c, uint8_t* socc, uint8_t* bocc);
 int occ_build_mask(Ctx* c, int kind);
 
@@ -102,6 +115,17 @@ int ccl_fetch_summary(Ctx* c);
 int ccl_hist(Ctx* c, int nbins, int64_t* hist);
 int ccl_export_bond_labels(Ctx* c, int32_t* b3);
 int ccl_export_sizes(Ctx* c, int32_t* cs);
+
+int slab_unique_id(void* id128);
+int slab_comm_init(Ctx* c, const void* id128);
+void slab_comm_destroy(Ctx* c);
+int slab_allreduce_f64(Ctx* c, double* buf, int count);
+int slab_allreduce_i64(Ctx* c, int64_t* buf, int count);
+int slab_halo_exchange(Ctx* c, void* array, int bytes_per_site);
+int slab_count_roots(Ctx* c);
+int slab_stitch(Ctx* c);
+int32_t slab_local_label_of(const Ctx* c, int64_t gid);
+int slab_export_labels(Ctx* c, int64_t* out);
 
 int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double tol, int itmax,
               double read_thresh, int keep_x, double* Gtop, double* Gbot, int* iter, double* err);

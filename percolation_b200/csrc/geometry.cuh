@@ -35,11 +35,17 @@ enum : unsigned {
 };
 
 struct Geom {
-    int lattice, m, n, pbc;
-    int64_t t;        // m * n
-    int64_t nb;       // number of lattice bonds (Sq/site.f:89-93, Tri/site.f:91-95)
+    int lattice, m, n, pbc;   // n = lattice rows HELD by this handle (the whole lattice, or a slab + halo rows)
+    int64_t t;        // m * n  (sites held)
+    int64_t nb;       // number of bonds of the WHOLE lattice (Sq/site.f:89-93, Tri/site.f:91-95)
     int ndir;         // owned directions per site: 2 (square) or 4 (triangular)
     int row_bonds;    // reference bond rows contributed by one lattice row y < n-1
+    // slab decomposition of one lattice over several GPUs (SURVEY 8e mode 2).  A handle holds the
+    // rows [y0, y0 + n) of a lattice of ng rows; rows [own_lo, own_hi) (local numbering) belong to it,
+    // the one row below / above is a halo copy of the neighbour's boundary row.  Whole lattice on one
+    // GPU: y0 = 0, ng = n, own_lo = 0, own_hi = n.
+    int y0, ng, own_lo, own_hi;
+    int64_t tg;       // m * ng (sites of the whole lattice)
 };
 
 PERC_HD Geom make_geom(int lattice, int m, int n, int pbc)
@@ -55,17 +61,32 @@ PERC_HD Geom make_geom(int lattice, int m, int n, int pbc)
         g.row_bonds = pbc ? 3 * m : 3 * m - 2;
         g.nb = pbc ? (int64_t)m * (3 * n - 2) : 3 * (int64_t)m * n - 2 * m - 2 * n + 1;
     }
+    g.y0 = 0; g.ng = n; g.own_lo = 0; g.own_hi = n; g.tg = g.t;
     return g;
 }
 
-// does site (x,y) own a bond in direction dir?
+// slab of rank `rank` of `nranks`: rows [ya, yb) of the ng-row lattice plus one halo row on each inner side
+PERC_HD Geom make_slab_geom(int lattice, int m, int ng, int pbc, int nranks, int rank)
+{
+    Geom g = make_geom(lattice, m, ng, pbc);                 // nb, row_bonds, tg of the whole lattice
+    const int ya = (int)((int64_t)ng * rank / nranks), yb = (int)((int64_t)ng * (rank + 1) / nranks);
+    const int hb = rank > 0 ? 1 : 0, ha = rank + 1 < nranks ? 1 : 0;
+    g.y0 = ya - hb;
+    g.n = yb - ya + hb + ha;
+    g.t = (int64_t)m * g.n;
+    g.own_lo = hb; g.own_hi = hb + (yb - ya);
+    return g;
+}
+
+// does site (x,y) own a bond in direction dir?  (x, y: LOCAL coordinates of the handle; the vertical
+// extent is that of the whole lattice)
 PERC_HD bool bond_exists(const Geom& g, int x, int y, int dir)
 {
     switch (dir) {
     case DIR_E:  return x + 1 < g.m || g.pbc;
-    case DIR_N:  return y + 1 < g.n;
-    case DIR_NW: return g.lattice == LAT_TRIANGULAR && !(x & 1) && y + 1 < g.n && (x > 0 || g.pbc);
-    case DIR_NE: return g.lattice == LAT_TRIANGULAR && !(x & 1) && y + 1 < g.n;
+    case DIR_N:  return g.y0 + y + 1 < g.ng;
+    case DIR_NW: return g.lattice == LAT_TRIANGULAR && !(x & 1) && g.y0 + y + 1 < g.ng && (x > 0 || g.pbc);
+    case DIR_NE: return g.lattice == LAT_TRIANGULAR && !(x & 1) && g.y0 + y + 1 < g.ng;
     }
     return false;
 }
@@ -75,7 +96,7 @@ PERC_HD unsigned owned_bond_bits(const Geom& g, int x, int y)
 {
     unsigned b = 0;
     if (x + 1 < g.m || g.pbc) b |= MASK_E;
-    if (y + 1 < g.n) {
+    if (g.y0 + y + 1 < g.ng) {
         b |= MASK_N;
         if (g.lattice == LAT_TRIANGULAR && !(x & 1)) {
             b |= MASK_NE;
@@ -181,6 +202,18 @@ PERC_HD void ref_row_to_owner(const Geom& g, int64_t r, int64_t* site, int* dir)
     *site = (int64_t)y * g.m + x;
 }
 
+// ---- rows of a handle (LOCAL row y; the whole lattice on one GPU: every interior row is both) ------
+// rows whose unknowns this handle solves: owned, and not a Dirichlet row (0 and ng-1) of the lattice
+PERC_HD bool solve_row(const Geom& g, int y)
+{
+    return y >= g.own_lo && y < g.own_hi && g.y0 + y >= 1 && g.y0 + y <= g.ng - 2;
+}
+// rows that carry a value of the search direction p: the solve rows plus the halo copies of the neighbours'
+PERC_HD bool p_row(const Geom& g, int y)
+{
+    return y >= 0 && y < g.n && g.y0 + y >= 1 && g.y0 + y <= g.ng - 2;
+}
+
 // ---- full 8-direction neighbourhood (conductance stencil) --------------------------------
 // bits: 0 E, 1 N, 2 NW, 3 NE, 4 W, 5 S, 6 SW, 7 SE.  Up-type (x even) triangular sites use
 // E,N,NW,NE,W,S; down-type use E,N,W,S,SW,SE; square sites E,N,W,S.
@@ -189,7 +222,7 @@ enum : unsigned { NB_E = 1u, NB_N = 2u, NB_NW = 4u, NB_NE = 8u, NB_W = 16u, NB_S
 PERC_HD unsigned neighbour_bits(const Geom& g, int x, int y)
 {
     unsigned b = 0;
-    bool xl = x > 0 || g.pbc, xr = x + 1 < g.m || g.pbc, yu = y + 1 < g.n, yd = y > 0;
+    bool xl = x > 0 || g.pbc, xr = x + 1 < g.m || g.pbc, yu = g.y0 + y + 1 < g.ng, yd = g.y0 + y > 0;
     if (xr) b |= NB_E;
     if (xl) b |= NB_W;
     if (yu) b |= NB_N;

@@ -29,7 +29,8 @@ struct RankSrc {
 
 struct PhiloxSrc {
     unsigned long long seed, stream;
-    int64_t t;
+    int64_t t;              // sites of the WHOLE lattice: element ids are global, so a slab of a decomposed
+                            // lattice draws exactly the occupancy the single-GPU run draws
     PhiloxThreshold ts, tb;
     __device__ __forceinline__ bool site(int64_t i) const
     {
@@ -68,8 +69,8 @@ static AnySrc make_src(const Ctx* c)
     AnySrc s;
     s.r.srank = c->site_src == SRC_RANK ? c->srank : nullptr;
     s.r.brank = c->bond_src == SRC_RANK ? c->brank : nullptr;
-    s.r.t = c->g.t; s.r.ks = c->ks; s.r.kb = c->kb;
-    s.p.seed = c->seed; s.p.stream = c->stream_id; s.p.t = c->g.t;
+    s.r.t = c->g.t; s.r.ks = (int)c->ks; s.r.kb = (int)c->kb;
+    s.p.seed = c->seed; s.p.stream = c->stream_id; s.p.t = c->g.tg;
     s.p.ts = c->thr_site; s.p.tb = c->thr_bond;
     s.site_src = c->site_src; s.bond_src = c->bond_src;
     return s;
@@ -85,27 +86,30 @@ __global__ void __launch_bounds__(256) build_mask_kernel(Geom g, int kind, AnySr
     unsigned ns = 0, nbd = 0;
     if (i < g.t) {
         int x = (int)(i % g.m), y = (int)(i / g.m);
+        const int64_t ig = i + (int64_t)g.y0 * g.m;      // index in the whole lattice (= i unless this is a slab)
+        const int gy = y + g.y0;
+        const bool owned = y >= g.own_lo && y < g.own_hi;
         unsigned own = owned_bond_bits(g, x, y);
         unsigned bits = 0;
         bool site = false;
         if (kind == KIND_SITE) {
-            site = src.site(i);
+            site = src.site(ig);
             bits = own;                                   // every lattice bond is present
-            ns = site;
+            ns = site && owned;
         } else {
 #pragma unroll
             for (int d = 0; d < 4; ++d)
-                if ((own >> (d + 1)) & 1u) if (src.bond(d, i)) bits |= 2u << d;
-            nbd = __popc(bits);
-            if (kind == KIND_MIXED) { site = src.site(i); ns = site; }
+                if ((own >> (d + 1)) & 1u) if (src.bond(d, ig)) bits |= 2u << d;
+            nbd = owned ? __popc(bits) : 0;
+            if (kind == KIND_MIXED) { site = src.site(ig); ns = site && owned; }
             else {
                 // bond problem: a site is a cluster node iff one of its bonds is occupied
                 site = bits != 0;
-                if (!site && (x > 0 || g.pbc)) site = src.bond(DIR_E, i - x + (x > 0 ? x - 1 : g.m - 1));
-                if (!site && y > 0) site = src.bond(DIR_N, i - g.m);
-                if (!site && g.lattice == LAT_TRIANGULAR && (x & 1) && y > 0) {
-                    site = src.bond(DIR_NE, i - g.m - 1);
-                    if (!site && (x + 1 < g.m || g.pbc)) site = src.bond(DIR_NW, i - g.m - x + (x + 1 < g.m ? x + 1 : 0));
+                if (!site && (x > 0 || g.pbc)) site = src.bond(DIR_E, ig - x + (x > 0 ? x - 1 : g.m - 1));
+                if (!site && gy > 0) site = src.bond(DIR_N, ig - g.m);
+                if (!site && g.lattice == LAT_TRIANGULAR && (x & 1) && gy > 0) {
+                    site = src.bond(DIR_NE, ig - g.m - 1);
+                    if (!site && (x + 1 < g.m || g.pbc)) site = src.bond(DIR_NW, ig - g.m - x + (x + 1 < g.m ? x + 1 : 0));
                 }
             }
         }
@@ -192,6 +196,7 @@ static unsigned nblk(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) /
 int occ_upload_site_order(Ctx* c, const int32_t* order)
 {
     int64_t t = c->g.t;
+    { int rc = ctx_ensure_ranks(c, true, false); if (rc) return rc; }
     int32_t* d = (int32_t*)ctx_dev_stage(c, sizeof(int32_t) * t);
     if (!d) return (int)cudaErrorMemoryAllocation;
     PERC_CUDA(cudaMemcpyAsync(d, order, sizeof(int32_t) * t, cudaMemcpyHostToDevice, c->stream));
@@ -206,6 +211,7 @@ int occ_upload_site_order(Ctx* c, const int32_t* order)
 int occ_upload_bond_order(Ctx* c, const int32_t* border)
 {
     int64_t nb = c->g.nb, t = c->g.t;
+    { int rc = ctx_ensure_ranks(c, false, true); if (rc) return rc; }
     int32_t* d = (int32_t*)ctx_dev_stage(c, sizeof(int32_t) * 2 * nb + 64);
     if (!d) return (int)cudaErrorMemoryAllocation;
     int* bad = (int*)(d + 2 * nb);
@@ -226,6 +232,7 @@ int occ_upload_bond_order(Ctx* c, const int32_t* border)
 int occ_upload_flags(Ctx* c, const uint8_t* socc, const uint8_t* bocc)
 {
     int64_t t = c->g.t, nb = c->g.nb;
+    { int rc = ctx_ensure_ranks(c, socc != nullptr, bocc != nullptr); if (rc) return rc; }
     if (socc) {
         uint8_t* d = (uint8_t*)ctx_dev_stage(c, t);
         if (!d) return (int)cudaErrorMemoryAllocation;
@@ -269,8 +276,10 @@ __global__ void export_bonds_kernel(Geom g, AnySrc src, uint8_t* __restrict__ bo
 
 int occ_export(Ctx* c, uint8_t* socc, uint8_t* bocc)
 {
+    if (c->nranks > 1) return -4;          // whole-lattice layout: not available on a slab handle
     AnySrc src = make_src(c);
     int64_t t = c->g.t, nb = c->g.nb;
+    { int rc = ctx_ensure_ranks(c, socc != nullptr, bocc != nullptr); if (rc) return rc; }
     if (socc) {
         uint8_t* d = (uint8_t*)ctx_dev_stage(c, t);
         if (!d) return (int)cudaErrorMemoryAllocation;
@@ -348,6 +357,9 @@ __global__ void __launch_bounds__(256) select_gather_kernel(Geom g, int type, un
 // find the k-th smallest (1-based) (key, id) among the N elements of `type`
 static int select_threshold(Ctx* c, int type, int64_t N, int64_t k, PhiloxThreshold* out)
 {
+    // keys are a pure function of the global element id: a slab handle selects over the WHOLE lattice
+    // (redundantly on every rank, no communication) and so finds the threshold the single-GPU run finds
+    const Geom gw = make_geom(c->g.lattice, c->g.m, c->g.ng, c->g.pbc);
     out->enabled = 1; out->all = 0; out->key = 0; out->id = 0;
     if (k <= 0) { out->enabled = 0; return 0; }
     if (k >= N) { out->all = 1; return 0; }
@@ -379,7 +391,7 @@ static int select_threshold(Ctx* c, int type, int64_t N, int64_t k, PhiloxThresh
         bool first = true;
         for (;;) {
             PERC_CUDA(cudaMemsetAsync(c->d_hist, 0, sizeof(unsigned long long) * (SEL_BINS + 8), c->stream));
-            select_hist_kernel<<<grid, 256, 0, c->stream>>>(c->g, type, c->seed, c->stream_id, cur_lo, sh, 0, c->d_hist);
+            select_hist_kernel<<<grid, 256, 0, c->stream>>>(gw, type, c->seed, c->stream_id, cur_lo, sh, 0, c->d_hist);
             c->launches++;
             PERC_CUDA(cudaMemcpyAsync(hist.data(), c->d_hist, sizeof(unsigned long long) * (SEL_BINS + 1),
                                       cudaMemcpyDeviceToHost, c->stream));
@@ -398,7 +410,7 @@ static int select_threshold(Ctx* c, int type, int64_t N, int64_t k, PhiloxThresh
                 unsigned long long width = sh >= 64 ? 0ull : (1ull << sh);
                 unsigned long long* cnt = c->d_hist + SEL_BINS + 4;
                 PERC_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
-                select_gather_kernel<<<grid, 256, 0, c->stream>>>(c->g, type, c->seed, c->stream_id, cur_lo, width,
+                select_gather_kernel<<<grid, 256, 0, c->stream>>>(gw, type, c->seed, c->stream_id, cur_lo, width,
                                                                   c->d_cand, c->cand_cap, cnt);
                 c->launches++;
                 std::vector<unsigned long long> cand(2 * (size_t)inbin);
@@ -420,13 +432,13 @@ static int select_threshold(Ctx* c, int type, int64_t N, int64_t k, PhiloxThresh
     return -5;
 }
 
-int occ_generate(Ctx* c, unsigned long long seed, unsigned long long stream, int ks, int kb)
+int occ_generate(Ctx* c, unsigned long long seed, unsigned long long stream, int64_t ks, int64_t kb)
 {
     c->seed = seed; c->stream_id = stream;
     int rc = 0;
     if (ks >= 0) {
-        if (ks > c->g.t) return -1;
-        rc = select_threshold(c, 0, c->g.t, ks, &c->thr_site);
+        if (ks > c->g.tg) return -1;
+        rc = select_threshold(c, 0, c->g.tg, ks, &c->thr_site);
         if (rc) return rc;
         c->site_src = SRC_PHILOX; c->ks = ks;
     }

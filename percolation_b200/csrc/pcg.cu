@@ -47,9 +47,10 @@ build_cfull_kernel(Geom g, int kind, int32_t cid, const uint8_t* __restrict__ ma
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.t) return;
     int x = (int)(i % g.m), y = (int)(i / g.m);
+    if (y < g.own_lo || y >= g.own_hi) return;          // halo rows: copied from the neighbour rank
     unsigned ex = neighbour_bits(g, x, y);
     unsigned out = 0;
-    bool mine = label[i] == cid;
+    bool mine = cid != 0 && label[i] == cid;
     unsigned mk = mask[i];
     int xl = x > 0 ? x - 1 : g.m - 1, xr = x + 1 < g.m ? x + 1 : 0;
     int64_t row = i - x;
@@ -123,7 +124,7 @@ __device__ __forceinline__ double fold_partials(const double* partial, int cnt, 
 __global__ void __launch_bounds__(UP_THREADS)
 pcg_init_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double* __restrict__ vx,
                 double* __restrict__ vr, double* __restrict__ vp, double* __restrict__ vq,
-                double* __restrict__ partial, PcgState* __restrict__ st, double tol, int itmax)
+                double* __restrict__ partial, PcgState* __restrict__ st, double tol, int itmax, int dist)
 {
     __shared__ double sh[32];
     double s_b = 0.0, s_rz = 0.0, s_rr = 0.0;
@@ -131,7 +132,7 @@ pcg_init_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < g.t; i += stride) {
         int x = (int)(i % g.m), y = (int)(i / g.m);
         double b = 0.0;
-        if (y == g.n - 2 && y >= 1) {
+        if (g.y0 + y == g.ng - 2 && solve_row(g, y)) {
             unsigned ex = neighbour_bits(g, x, y), cf = cfull[i];
             // bonds into the top row: N, NW, NE
             if (ex & NB_N)  b += ((cf & NB_N)  ? prm.g0 : prm.gleak) * prm.Va;
@@ -156,6 +157,7 @@ pcg_init_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
             st->akden = 0.0; st->ak = 0.0; st->err = 0.0;
             st->iter = 0; st->itmax = itmax; st->tol = tol; st->done = 0;
             st->Itop = 0.0; st->Ibot = 0.0;
+            if (dist) { st->red[0] = fa; st->red[1] = fc; st->red[2] = fe; }   // summed over the ranks, then pcg_post
         }
     }
 }
@@ -363,7 +365,7 @@ __device__ __forceinline__ void pt_issue(const Geom& g, const PtStage& s, int x0
                 const int pr = prb + it * (PT_THREADS / 64), gy = y0 + pr - 1;
                 if (pr < PT_ROWS) {
                     const bool ok = (unsigned)gy < (unsigned)g.n;
-                    cp_async16(&s.sp[so], ok ? pp : vp_in, ok && gy >= 1 && gy < g.n - 1);       // Dirichlet rows: p = 0
+                    cp_async16(&s.sp[so], ok ? pp : vp_in, ok && p_row(g, gy));               // Dirichlet rows: p = 0
                     if (MODE == 0 || (pr >= 1 && pr <= PT_TY)) cp_async16(&s.sr[so], ok ? rp : vr, ok);
                 }
                 pp += step; rp += step; so += (PT_THREADS / 64) * PT_LD;
@@ -387,7 +389,7 @@ __device__ __forceinline__ void pt_issue(const Geom& g, const PtStage& s, int x0
         const bool ok = gy >= 0 && gy < g.n && hx >= 0 && hx < g.m;
         const int64_t j = ok ? (int64_t)gy * g.m + hx : 0;
         const int col = side ? 2 + xe : 1;
-        cp_async8(&s.sp[pr * PT_LD + col], vp_in + j, ok && gy >= 1 && gy < g.n - 1);
+        cp_async8(&s.sp[pr * PT_LD + col], vp_in + j, ok && p_row(g, gy));
         if (MODE == 0) {
             cp_async8(&s.sr[pr * PT_LD + col], vr + j, ok);
             // the conduct byte of the halo cell: the aligned 4-byte word that holds it
@@ -401,7 +403,7 @@ template <int LAT, int MODE>
 __global__ void __launch_bounds__(PT_THREADS, 1)
 pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double* __restrict__ vr,
                 const double* __restrict__ vp_in, double* __restrict__ vp_out, double* __restrict__ vx,
-                double* __restrict__ partial, PcgState* __restrict__ st, int keep_x, int ntx, int ntiles)
+                double* __restrict__ partial, PcgState* __restrict__ st, int keep_x, int ntx, int ntiles, int dist)
 {
     if (st->done) return;
     extern __shared__ __align__(16) unsigned char pt_raw[];
@@ -412,7 +414,7 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
         const double d = pt_diag((k >> 5) >> 3, (k >> 5) & 7, prm);
         dinv[k] = d > 0.0 ? 1.0 / d : 0.0;
     }
-    const double bk = st->bk, ak = st->ak;
+    const double bk = st->bk, ak = st->ak;          // slab mode: set by pcg_post_kernel after the all-reduce
     const double dg = prm.g0 - prm.gleak;
     // MODE 0 sweeps the tiles from the END of the lattice to its start, MODE 1 front to back: each
     // kernel starts on the data the previous one touched last (still resident in the 126 MB L2)
@@ -431,7 +433,7 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
         } else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         // every cell of tile + halo has its full neighbourhood inside the lattice
-        const bool interior = x0 >= 2 && x0 + PT_TX <= g.m - 2 && y0 >= 2 && y0 + PT_TY <= g.n - 2;
+        const bool interior = x0 >= 2 && x0 + PT_TX <= g.m - 2 && g.y0 + y0 >= 2 && g.y0 + y0 + PT_TY <= g.ng - 2;
         const int xe = g.m - x0 < PT_TX ? g.m - x0 : PT_TX;
 
         // ---- MODE 0: p_new = r / d + bk * p_old, in place on tile + halo (p is double-buffered in
@@ -445,7 +447,7 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
                     const int pr = prb + it * (PT_THREADS / 64), gy = y0 + pr - 1;
                     if (pr >= PT_ROWS) continue;
                     double2 v = make_double2(0.0, 0.0);
-                    if (gy >= 1 && gy < g.n - 1) {
+                    if (p_row(g, gy)) {
                         const double2 r2 = ld2(&s.sr[pr * PT_LD + 2 + cx]), p2 = ld2(&s.sp[pr * PT_LD + 2 + cx]);
                         const unsigned c01 = *reinterpret_cast<const unsigned short*>(&s.scf[pr * PT_CLD + 16 + cx]);
                         const unsigned e0 = interior ? e0i : neighbour_bits(g, gxc, gy);
@@ -455,6 +457,8 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
                         v.y = r2.y * dinv[(((n1 << 3) | (__popc(e1) - n1)) << 5) + lane] + bk * p2.y;
                     }
                     st2(&s.sp[pr * PT_LD + 2 + cx], v);
+                    // slab mode: the halo copies of p are advanced here (pointwise recurrence) and stored for MODE 1
+                    if (pr >= 1 && pr <= PT_TY && p_row(g, gy) && !solve_row(g, gy)) st2(vp_out + (int64_t)gy * g.m + gxc, v);
                 }
             }
             if (tid < 2 * PT_ROWS) {
@@ -464,7 +468,7 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
                 if (g.pbc) { if (hx == -1) hx = g.m - 1; else if (hx == g.m) hx = 0; }
                 const int col = side ? 2 + xe : 1;
                 double v = 0.0;
-                if (gy >= 1 && gy < g.n - 1 && hx >= 0 && hx < g.m) {
+                if (p_row(g, gy) && hx >= 0 && hx < g.m) {
                     const unsigned cf = s.scf[pr * PT_CLD + (side ? 16 + PT_TX : 12) + (hx & 3)];
                     const unsigned ex = neighbour_bits(g, hx, gy);
                     const int nc = __popc(cf);
@@ -489,7 +493,7 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
                 const int ly = r0 + j, gy = y0 + ly;
                 const double2 up = ld2(c + PT_LD);
                 const double lf = c[-1], rt = c[2];
-                const bool valid = gy >= 1 && gy < g.n - 1 && gx < g.m;
+                const bool valid = solve_row(g, gy) && gx < g.m;
                 const unsigned c01 = *reinterpret_cast<const unsigned short*>(&s.scf[(ly + 1) * PT_CLD + 16 + 2 * tx]);
                 const unsigned cf0 = c01 & 0xffu, cf1 = c01 >> 8;
                 unsigned e0, e1;
@@ -529,7 +533,7 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
                         double2 r = ld2(&s.sr[(ly + 1) * PT_LD + 2 + 2 * tx]);
                         r.x -= ak * q.x; r.y -= ak * q.y;
                         st2(vr + i, r);
-                        if (keep_x || gy == 1 || gy == g.n - 2) {
+                        if (keep_x || g.y0 + gy == 1 || g.y0 + gy == g.ng - 2) {
                             double2 x = ld2(vx + i);
                             x.x += ak * cc.x; x.y += ak * cc.y;
                             st2(vx + i, x);
@@ -561,7 +565,8 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
         if (last_block(&st->ticket_b)) {
             double fa = fold_partials(partial, ntiles, 2, 0, sh);
             double fc = fold_partials(partial, ntiles, 2, 1, sh);
-            if (threadIdx.x == 0) {
+            if (threadIdx.x == 0 && dist) { st->red[0] = fa; st->red[1] = fc; }      // summed over the ranks, then pcg_post
+            if (threadIdx.x == 0 && !dist) {
                 int it = st->iter + 1;
                 double err = sqrt(fc) / st->bnrm;
                 st->iter = it; st->err = err; st->rr = fc;
@@ -570,6 +575,22 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
             }
         }
     }
+}
+
+// slab mode: the scalar recurrences, run by one thread after the all-reduce of the rank-local sums
+//   phase 0: after pcg_init (red = |D^-1 b|^2, b.z, b.b)   phase 1: after MODE 0 (akden)
+//   phase 2: after MODE 1 (red = r.z, r.r)                  phase 3: after the read-out (Itop, Ibot are summed in place)
+__global__ void pcg_post_kernel(PcgState* st, int phase)
+{
+    if (phase == 0) { st->bnrm = sqrt(st->red[0]); st->bknum = st->red[1]; st->rr = st->red[2]; return; }
+    if (st->done) return;
+    if (phase == 1) { st->ak = st->bknum / st->akden; return; }
+    const double fa = st->red[0], fc = st->red[1];
+    const int it = st->iter + 1;
+    const double err = sqrt(fc) / st->bnrm;
+    st->iter = it; st->err = err; st->rr = fc;
+    st->bkden = st->bknum; st->bknum = fa; st->bk = fa / st->bkden;
+    if (!(err > st->tol) || it > st->itmax) st->done = 1;             // loop guard iter <= itmax (:780)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -584,6 +605,8 @@ pcg_readout_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, con
     double stop = 0.0, sbot = 0.0;
     for (int x = threadIdx.x; x < g.m; x += blockDim.x) {
         for (int e = 0; e < 2; ++e) {
+            // lattice rows 0 and ng-1: held by the first / last rank of a decomposed lattice
+            if (e == 0 ? g.y0 != 0 : g.y0 + g.n != g.ng) continue;
             int y = e == 0 ? 0 : g.n - 1;
             int64_t i = (int64_t)y * g.m + x;
             unsigned ex = neighbour_bits(g, x, y), cf = cfull[i];
@@ -591,7 +614,7 @@ pcg_readout_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, con
             double acc = diag_of(cf, ex, prm.g0, prm.gleak) * vi;
             int xl = x > 0 ? x - 1 : g.m - 1, xr = x + 1 < g.m ? x + 1 : 0;
             int64_t row = i - x;
-#define VAL(j) ((j) < g.m ? 0.0 : ((j) >= g.t - g.m ? prm.Va : vx[j]))
+#define VAL(j) (g.y0 + (j) / g.m == 0 ? 0.0 : (g.y0 + (j) / g.m == g.ng - 1 ? prm.Va : vx[j]))
 #define NB(bit, j) if (ex & bit) { double w = (cf & bit) ? prm.g0 : prm.gleak; if (fabs(w) >= prm.read_thresh) acc -= w * VAL(j); }
             NB(NB_E, row + xr) NB(NB_W, row + xl) NB(NB_N, i + g.m) NB(NB_S, i - g.m)
             NB(NB_NW, row + g.m + xl) NB(NB_NE, row + g.m + xr) NB(NB_SW, row - g.m + xl) NB(NB_SE, row - g.m + xr)
@@ -619,6 +642,8 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     const int ntx = (g.m + PT_TX - 1) / PT_TX, ntiles = ntx * ((g.n + PT_TY - 1) / PT_TY);
     const int pgrid = ntiles < c->num_sms ? ntiles : c->num_sms;     // one persistent CTA per SM
     const bool vec = (g.m % 16) == 0;    // staged kernels: rows of the fp64 vectors and of the byte mask are 16-byte aligned
+    const int dist = c->nranks > 1;      // slab of a decomposed lattice: sums all-reduced, halo rows exchanged
+    if (dist && !vec) return -1;         // the scalar fallback is single-GPU only
     int ugrid = 148 * 8;
     int64_t interior = g.t - 2 * (int64_t)g.m;
     if (ugrid > (interior + UP_THREADS - 1) / UP_THREADS) ugrid = (int)((interior + UP_THREADS - 1) / UP_THREADS);
@@ -641,11 +666,20 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
         PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_TRIANGULAR, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
         attr_set = true;
     }
+    int rc;
     PERC_CUDA(cudaMemsetAsync(c->d_pcg, 0, sizeof(PcgState), s));
     PERC_CUDA(cudaEventRecord(c->ev[6], s));
     build_cfull_kernel<<<nblk(g.t), 256, 0, s>>>(g, c->kind, cluster_id, c->mask, c->label, c->cfull);
-    pcg_init_kernel<<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, c->vp, c->vq, c->partial, c->d_pcg, tol, itmax);
+    if (dist) { rc = slab_halo_exchange(c, c->cfull, 1); if (rc) return rc; }           // conduct bytes of the halo rows
+    pcg_init_kernel<<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, c->vp, c->vq, c->partial, c->d_pcg, tol, itmax, dist);
     c->launches += 2;
+    if (dist) {
+        rc = slab_allreduce_f64(c, c->d_pcg->red, 3); if (rc) return rc;
+        pcg_post_kernel<<<1, 1, 0, s>>>(c->d_pcg, 0);
+        rc = slab_halo_exchange(c, c->vr, 8); if (rc) return rc;                        // r = b on the halo rows
+        PERC_CUDA(cudaMemsetAsync(c->vp2, 0, sizeof(double) * g.t, s));
+        c->launches++;
+    }
     double* pold = c->vp; double* pnew = c->vp2;
     float sp_ms = 0.f, up_ms = 0.f; int nsamp = 0;
     int chunk = 16, iters_before = 0;
@@ -657,21 +691,32 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[8], s));
             if (vec) {
                 if (g.lattice == LAT_SQUARE)
-                    pcg_pipe_kernel<LAT_SQUARE, 0><<<pgrid, PT_THREADS, PT_SMEM, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles);
+                    pcg_pipe_kernel<LAT_SQUARE, 0><<<pgrid, PT_THREADS, PT_SMEM, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles, dist);
                 else
-                    pcg_pipe_kernel<LAT_TRIANGULAR, 0><<<pgrid, PT_THREADS, PT_SMEM, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles);
+                    pcg_pipe_kernel<LAT_TRIANGULAR, 0><<<pgrid, PT_THREADS, PT_SMEM, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles, dist);
             } else if (g.lattice == LAT_SQUARE)
                 pcg_spmv_kernel<LAT_SQUARE><<<sgrid, SP_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vq, c->partial, c->d_pcg);
             else
                 pcg_spmv_kernel<LAT_TRIANGULAR><<<sgrid, SP_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vq, c->partial, c->d_pcg);
+            if (dist) {
+                rc = slab_allreduce_f64(c, &c->d_pcg->akden, 1); if (rc) return rc;      // p.Ap over all slabs
+                pcg_post_kernel<<<1, 1, 0, s>>>(c->d_pcg, 1);
+                c->launches++;
+            }
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[9], s));
             if (vec) {
                 if (g.lattice == LAT_SQUARE)
-                    pcg_pipe_kernel<LAT_SQUARE, 1><<<pgrid, PT_THREADS, PT_SMEM, s>>>(g, prm, c->cfull, c->vr, pnew, nullptr, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles);
+                    pcg_pipe_kernel<LAT_SQUARE, 1><<<pgrid, PT_THREADS, PT_SMEM, s>>>(g, prm, c->cfull, c->vr, pnew, nullptr, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles, dist);
                 else
-                    pcg_pipe_kernel<LAT_TRIANGULAR, 1><<<pgrid, PT_THREADS, PT_SMEM, s>>>(g, prm, c->cfull, c->vr, pnew, nullptr, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles);
+                    pcg_pipe_kernel<LAT_TRIANGULAR, 1><<<pgrid, PT_THREADS, PT_SMEM, s>>>(g, prm, c->cfull, c->vr, pnew, nullptr, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles, dist);
             } else
                 pcg_update_kernel<<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, pnew, c->vq, c->partial, c->d_pcg);
+            if (dist) {
+                rc = slab_allreduce_f64(c, c->d_pcg->red, 2); if (rc) return rc;         // r.z and r.r over all slabs
+                pcg_post_kernel<<<1, 1, 0, s>>>(c->d_pcg, 2);
+                rc = slab_halo_exchange(c, c->vr, 8); if (rc) return rc;                 // boundary rows of the new residual
+                c->launches++;
+            }
             { double* tmp = pold; pold = pnew; pnew = tmp; }
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[10], s));
             c->launches += 2;
@@ -692,6 +737,7 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     }
     pcg_readout_kernel<<<1, 256, 0, s>>>(g, prm, c->cfull, c->vx, c->d_pcg);
     c->launches++;
+    if (dist) { rc = slab_allreduce_f64(c, &c->d_pcg->Itop, 2); if (rc) return rc; }     // Itop from the last rank, Ibot from the first
     PERC_CUDA(cudaEventRecord(c->ev[7], s));
     PERC_CUDA(cudaMemcpyAsync(c->h_pcg, c->d_pcg, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
     PERC_CUDA(cudaStreamSynchronize(s));

@@ -15,9 +15,9 @@ SO_PATH = os.path.join(_HERE, "libperc_b200.so")
 SQUARE, TRIANGULAR = 1, 2
 SITE, BOND, MIXED = 1, 2, 3
 
-E_ARG, E_ODD_M, E_HANDLE, E_STATE, E_SIZE, E_NOSPAN = -1, -2, -3, -4, -5, -6
+E_ARG, E_ODD_M, E_HANDLE, E_STATE, E_SIZE, E_NOSPAN, E_NCCL, E_IFACE = -1, -2, -3, -4, -5, -6, -7, -8
 _ENAMES = {E_ARG: "PERC_E_ARG", E_ODD_M: "PERC_E_ODD_M", E_HANDLE: "PERC_E_HANDLE", E_STATE: "PERC_E_STATE",
-           E_SIZE: "PERC_E_SIZE", E_NOSPAN: "PERC_E_NOSPAN"}
+           E_SIZE: "PERC_E_SIZE", E_NOSPAN: "PERC_E_NOSPAN", E_NCCL: "PERC_E_NCCL", E_IFACE: "PERC_E_IFACE"}
 
 # every symbol include/perc_abi.h declares
 SYMBOLS = [
@@ -28,6 +28,8 @@ SYMBOLS = [
     "perc_label", "perc_summary", "perc_get_site_labels", "perc_get_bond_labels", "perc_get_sizes",
     "perc_span", "perc_hist", "perc_site", "perc_bond", "perc_sitebond", "perc_first_span",
     "perc_conduct", "perc_conduct_g", "perc_get_voltage", "perc_launch_count", "perc_phase_ms", "perc_stream",
+    "perc_create_slab", "perc_comm_unique_id", "perc_comm_init", "perc_slab_rows", "perc_generate_i8",
+    "perc_summary_i8", "perc_span_i8", "perc_get_site_labels_i8", "perc_stitch_host",
 ]
 
 
@@ -257,3 +259,77 @@ class Lattice:
 
     def sync(self):
         self._call("perc_sync")
+
+
+# ---- one lattice decomposed into row slabs over several GPUs ---------------------------------------
+IFACE_WORDS = lambda m: 5 * m + 8          # block a rank contributes to the interface all-gather (csrc/slab.h)
+
+
+def comm_unique_id():
+    """NCCL bootstrap id (128 bytes); rank 0 creates it, the host program distributes it"""
+    buf = np.zeros(128, np.uint8)
+    _ck("perc_comm_unique_id", load().perc_comm_unique_id(_ptr(buf, C.c_uint8)))
+    return buf
+
+
+def stitch_host(nranks, rank, m, gathered, max_span=4096):
+    """the stitch's redundant host union-find on its own (no device needed)"""
+    gathered = np.ascontiguousarray(gathered, np.int64)
+    assert gathered.size == nranks * IFACE_WORDS(m)
+    summary = np.zeros(5, np.int64)
+    ids, sizes = np.zeros(max_span, np.int64), np.zeros(max_span, np.int64)
+    max_pairs = 2 * m
+    pairs = np.zeros(4 * max_pairs, np.int64)
+    npairs = C.c_int32(0)
+    _ck("perc_stitch_host", load().perc_stitch_host(_i32(nranks), _i32(rank), _i32(m), _ptr(gathered, C.c_int64),
+                                                    _ptr(summary, C.c_int64), _i32(max_span), _ptr(ids, C.c_int64),
+                                                    _ptr(sizes, C.c_int64), _i32(max_pairs), C.byref(npairs),
+                                                    _ptr(pairs, C.c_int64)))
+    ns = int(summary[4])
+    return dict(ncl=int(summary[0]), nlone=int(summary[1]), maxcs=int(summary[2]), maxcn=int(summary[3]), nspan=ns,
+                span_ids=ids[:ns].copy(), span_sizes=sizes[:ns].copy(), pairs=pairs[:4 * npairs.value].reshape(-1, 4).copy())
+
+
+class SlabLattice(Lattice):
+    """rank `rank` of `nranks`: rows [n*rank/nranks, n*(rank+1)/nranks) of one m x n lattice (+ halo rows)"""
+
+    def __init__(self, lattice, m, n, pbc, device, nranks, rank, unique_id=None):
+        self.lattice, self.m, self.n, self.pbc = int(lattice), int(m), int(n), int(pbc)
+        self.t = self.m * self.n
+        self.nranks, self.rank = int(nranks), int(rank)
+        self._h = C.c_int64(0)
+        self._lib = load()
+        _ck("perc_create_slab", self._lib.perc_create_slab(C.byref(self._h), _i32(lattice), _i32(m), _i32(n), _i32(pbc),
+                                                           _i32(device), _i32(nranks), _i32(rank)))
+        ya, yb = C.c_int32(0), C.c_int32(0)
+        self._call("perc_slab_rows", C.byref(ya), C.byref(yb))
+        self.ya, self.yb = ya.value, yb.value
+        if lattice == SQUARE:
+            self.nb = m * (2 * n - 1) if pbc else 2 * m * n - m - n
+        else:
+            self.nb = m * (3 * n - 2) if pbc else 3 * m * n - 2 * m - 2 * n + 1
+        if nranks > 1:
+            assert unique_id is not None, "every rank needs the NCCL id created by rank 0 (comm_unique_id)"
+            uid = np.ascontiguousarray(unique_id, np.uint8)
+            self._call("perc_comm_init", _ptr(uid, C.c_uint8))
+
+    def generate(self, seed, stream=0, ks=-1, kb=-1):
+        self._call("perc_generate_i8", _i64(seed), _i64(stream), _i64(ks), _i64(kb))
+
+    def summary(self):
+        ncl, maxcs, maxcn, nspan = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._call("perc_summary_i8", C.byref(ncl), C.byref(maxcs), C.byref(maxcn), C.byref(nspan))
+        return dict(ncl=ncl.value, maxcs=maxcs.value, maxcn=maxcn.value, nspan=nspan.value)
+
+    def span(self, max_ids=4096):
+        ids, sizes = np.zeros(max_ids, np.int64), np.zeros(max_ids, np.int64)
+        nspan = C.c_int32(0)
+        self._call("perc_span_i8", _i32(max_ids), C.byref(nspan), _ptr(ids, C.c_int64), _ptr(sizes, C.c_int64))
+        k = min(nspan.value, max_ids)
+        return ids[:k].copy(), sizes[:k].copy()
+
+    def site_labels(self):
+        """lattice-wide canonical labels (int64) of the rows this rank owns"""
+        s = np.zeros((self.yb - self.ya) * self.m, np.int64)
+        self._call("perc_get_site_labels_i8", _ptr(s, C.c_int64))
+        return s
