@@ -155,6 +155,22 @@ int32_t perc_stitch_host(const int32_t *nranks, const int32_t *rank, const int32
                          int64_t *out_summary, const int32_t *max_span, int64_t *span_ids, int64_t *span_sizes,
                          const int32_t *max_pairs, int32_t *npairs, int64_t *out_pairs);
 
+/* ---- batches of independent realizations: the trial loops `do ii = 1, numtrials` of the *_perc and
+ * bond_cond drivers (Sq/site_perc.f:87, Sq/bond_perc.f, Sq/sb_perc.f:104, Sq/bond_cond.f:123) ------------
+ * Realization i = 0..nreal-1 draws stream = stream0 + i from the generator with exact fill counts ks / kb,
+ * is labeled, and is folded into device-resident statistics; nothing is synchronised inside the loop.
+ * hist(nbins): cluster-size histogram summed over the batch (layout of perc_hist); stats(16), int64:
+ *  (1) realizations (2) sum ncl (3) sum maxcs (4) realizations that span (5) sum nspan (6) sum perccls
+ *  (7) failed selections -- must be 0 -- (8) sum maxcs^2 (9) sum occupied sites (10) sum occupied bonds */
+int32_t perc_batch(const int64_t *h, const int32_t *kind, const int32_t *nreal, const int64_t *seed,
+                   const int64_t *stream0, const int32_t *ks, const int32_t *kb, const int32_t *nbins,
+                   int64_t *hist, int64_t *stats);
+/* independent realizations sharded over GPUs (one process per GPU, no data-path collective): communicator
+ * for the single reduction of the statistics at the end, and that reduction (integer sums are order
+ * independent: the result is the same for any number of GPUs) */
+int32_t perc_comm_init_rank(const int64_t *h, const int32_t *nranks, const int32_t *rank, const uint8_t *id128);
+int32_t perc_allreduce_stats(const int64_t *h, const int32_t *ni, int64_t *ivals, const int32_t *nd, double *dvals);
+
 /* ---- instrumentation ---------------------------------------------------------------------------- */
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 int32_t perc_launch_count(const int64_t *h, int64_t *count);

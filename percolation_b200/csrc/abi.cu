@@ -73,7 +73,8 @@ int ctx_alloc(Ctx* c)
     PERC_CUDA(cudaMemsetAsync(c->d_sum, 0, sizeof(Summary), c->stream));
     PERC_CUDA(cudaMalloc(&c->d_pcg, sizeof(PcgState)));
     PERC_CUDA(cudaMallocHost(&c->h_pcg, sizeof(PcgState)));
-    PERC_CUDA(cudaMalloc(&c->d_hist, sizeof(unsigned long long) * (4096 + 8)));
+    PERC_CUDA(cudaMalloc(&c->d_hist, sizeof(unsigned long long) * (4096 + 16)));
+    PERC_CUDA(cudaMalloc(&c->d_thr, sizeof(PhiloxThreshold) * 2));
     c->cand_cap = 8192;
     PERC_CUDA(cudaMalloc(&c->d_cand, sizeof(unsigned long long) * 2 * c->cand_cap));
     for (auto& e : c->ev) PERC_CUDA(cudaEventCreate(&e));
@@ -102,7 +103,7 @@ void ctx_free(Ctx* c)
     if (c->d_iface) cudaFree(c->d_iface);
     if (c->h_iface) cudaFreeHost(c->h_iface);
     void* ptrs[] = {c->srank, c->brank, c->mask, c->label, c->size, c->rootlist, c->d_sum, c->d_pcg,
-                    c->d_hist, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vp2, c->vq, c->partial, c->d_stage};
+                    c->d_hist, c->d_thr, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vp2, c->vq, c->partial, c->d_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_pcg) cudaFreeHost(c->h_pcg);
     if (c->h_sum_pin) cudaFreeHost(c->h_sum_pin);
@@ -630,6 +631,60 @@ int32_t perc_stitch_host(const int32_t* nranks, const int32_t* rank, const int32
         out_pairs[4 * k + 0] = R.root_gid[k]; out_pairs[4 * k + 1] = R.rep_gid[k];
         out_pairs[4 * k + 2] = R.class_gid[k]; out_pairs[4 * k + 3] = R.class_total[k];
     }
+    return 0;
+}
+
+// ---- batches of independent realizations (trial loops of the *_perc / bond_cond drivers) ----------
+int32_t perc_batch(const int64_t* h, const int32_t* kind, const int32_t* nreal, const int64_t* seed, const int64_t* stream0,
+                   const int32_t* ks, const int32_t* kb, const int32_t* nbins, int64_t* hist, int64_t* stats)
+{
+    GET_CTX(h);
+    if (!kind || !nreal || !seed || !stream0 || !ks || !kb || !nbins || !stats) return PERC_E_ARG;
+    if (*kind < KIND_SITE || *kind > KIND_MIXED || *nreal < 0 || *nbins < 0) return PERC_E_ARG;
+    if ((*kind != KIND_BOND && (*ks < 0 || *ks > c->g.t)) || (*kind != KIND_SITE && (*kb < 0 || *kb > c->g.nb))) return PERC_E_ARG;
+    return batch_run(c, *kind, *nreal, (unsigned long long)*seed, (unsigned long long)*stream0, *ks, *kb, *nbins, hist, stats);
+}
+
+// communicator for handles that shard independent realizations (mode 1): same bootstrap as the slab mode
+int32_t perc_comm_init_rank(const int64_t* h, const int32_t* nranks, const int32_t* rank, const uint8_t* id128)
+{
+    GET_CTX(h);
+    if (!nranks || !rank || !id128 || *nranks < 1 || *rank < 0 || *rank >= *nranks) return PERC_E_ARG;
+    if (c->nranks > 1) return PERC_E_STATE;                 // a slab handle already owns its communicator
+    if (*nranks == 1) return 0;
+    const int keep_n = c->nranks, keep_r = c->rank;
+    c->nranks = *nranks; c->rank = *rank;
+    int rc = slab_comm_init(c, id128);
+    c->stat_nranks = *nranks;
+    c->nranks = keep_n; c->rank = keep_r;
+    return rc;
+}
+
+// the one NCCL reduction of the statistics at the end of a sharded run (sum of int64 / float64 arrays,
+// host buffers in and out); a handle without a communicator leaves the arrays as they are
+int32_t perc_allreduce_stats(const int64_t* h, const int32_t* ni, int64_t* ivals, const int32_t* nd, double* dvals)
+{
+    GET_CTX(h);
+    if (!ni || !nd || *ni < 0 || *nd < 0) return PERC_E_ARG;
+    if (!c->comm || c->stat_nranks <= 1) return 0;
+    const size_t bytes = sizeof(int64_t) * (size_t)*ni + sizeof(double) * (size_t)*nd;
+    if (!bytes) return 0;
+    char* d = (char*)ctx_dev_stage(c, bytes + 64);
+    if (!d) return (int)cudaErrorMemoryAllocation;
+    int64_t* di = (int64_t*)d;
+    double* dd = (double*)(d + sizeof(int64_t) * (size_t)*ni);
+    if (*ni) PERC_CUDA(cudaMemcpyAsync(di, ivals, sizeof(int64_t) * *ni, cudaMemcpyHostToDevice, c->stream));
+    if (*nd) PERC_CUDA(cudaMemcpyAsync(dd, dvals, sizeof(double) * *nd, cudaMemcpyHostToDevice, c->stream));
+    const int keep = c->nranks;
+    c->nranks = c->stat_nranks;                              // the reduction helpers skip single-rank handles
+    int rc = 0;
+    if (*ni) rc = slab_allreduce_i64(c, di, *ni);
+    if (!rc && *nd) rc = slab_allreduce_f64(c, dd, *nd);
+    c->nranks = keep;
+    if (rc) return rc;
+    if (*ni) PERC_CUDA(cudaMemcpyAsync(ivals, di, sizeof(int64_t) * *ni, cudaMemcpyDeviceToHost, c->stream));
+    if (*nd) PERC_CUDA(cudaMemcpyAsync(dvals, dd, sizeof(double) * *nd, cudaMemcpyDeviceToHost, c->stream));
+    PERC_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -1,0 +1,109 @@
+// batch.cu -- many independent realizations on one handle without leaving the device.
+//
+// The reference's trial loops (`do ii = 1, numtrials`, Sq/site_perc.f:87, Sq/bond_cond.f:123,
+// Sq/sb_perc.f:104) run one realization after the other and write one text row each.  Here every
+// realization i = 0 .. nreal-1 draws its occupancy from the generator (stream = stream0 + i, exact
+// fill counts ks / kb), is labeled, and is folded into statistics that stay on the device: the
+// cluster-size histogram n_s and a block of integer sums.  No host synchronisation happens inside
+// the loop (the exact-count selection runs device-resident, occupancy.cu); one download at the end.
+// Integer sums are order independent, so shards of a batch on different GPUs all-reduce to the same
+// result for any number of GPUs (SURVEY 8e mode 1).
+#include "context.h"
+
+namespace perc {
+
+// stats: [0] realizations  [1] sum ncl  [2] sum maxcs  [3] realizations with a spanning cluster
+//        [4] sum nspan  [5] sum size of the default spanning cluster  [6] failed selections
+//        [7] sum maxcs^2  [8] sum occupied sites  [9] sum occupied bonds
+__global__ void batch_accum_kernel(const Summary* __restrict__ sum, unsigned long long* __restrict__ hist, int nbins,
+                                   long long* __restrict__ stats)
+{
+    const unsigned long long mp = sum->maxpack;
+    long long ms = (long long)(mp >> 32);
+    if (ms == 0 && sum->nlone > 0) ms = 1;
+    stats[0] += 1;
+    stats[1] += (long long)(sum->ncl + sum->nlone);
+    stats[2] += ms;
+    stats[7] += ms * ms;
+    stats[8] += (long long)sum->nocc_sites;
+    stats[9] += (long long)sum->nocc_bonds;
+    int ns = sum->nspan < MAX_SPAN ? sum->nspan : MAX_SPAN;
+    if (ns > 0) {
+        stats[3] += 1;
+        stats[4] += ns;
+        int best = 0;                                   // default choice: smallest canonical id
+        for (int k = 1; k < ns; ++k) if (sum->span_ids[k] < sum->span_ids[best]) best = k;
+        stats[5] += sum->span_sizes[best];
+    }
+    if (nbins > 0 && sum->nlone) hist[0] += sum->nlone;  // lone bonds are size-1 clusters
+}
+
+__global__ void __launch_bounds__(256)
+batch_hist_kernel(int64_t t, const int32_t* __restrict__ label, const int32_t* __restrict__ size, int nbins,
+                  unsigned long long* __restrict__ hist)
+{
+    extern __shared__ unsigned sh_hist[];
+    int nsh = nbins < 4096 ? nbins : 4096;
+    for (int k = threadIdx.x; k < nsh; k += blockDim.x) sh_hist[k] = 0;
+    __syncthreads();
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t; i += stride) {
+        if (label[i] != (int32_t)(i + 1)) continue;          // sizes live at the roots
+        int32_t s = size[i];
+        if (s > 0) {
+            int b = s < nbins ? s - 1 : nbins - 1;
+            if (b < nsh) atomicAdd(&sh_hist[b], 1u);
+            else atomicAdd(&hist[b], 1ull);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nsh; k += blockDim.x)
+        if (sh_hist[k]) atomicAdd(&hist[k], (unsigned long long)sh_hist[k]);
+}
+
+constexpr int BATCH_NSTATS = 16;
+
+int batch_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsigned long long stream0, int64_t ks, int64_t kb,
+              int nbins, int64_t* hist, int64_t* stats)
+{
+    if (c->nranks > 1) return -4;
+    cudaStream_t st = c->stream;
+    const size_t hb = sizeof(unsigned long long) * (size_t)(nbins > 0 ? nbins : 1);
+    unsigned long long* d_hist = nullptr;
+    long long* d_stats = nullptr;
+    PERC_CUDA(cudaMalloc(&d_hist, hb));
+    PERC_CUDA(cudaMalloc(&d_stats, sizeof(long long) * BATCH_NSTATS));
+    PERC_CUDA(cudaMemsetAsync(d_hist, 0, hb, st));
+    PERC_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(long long) * BATCH_NSTATS, st));
+    int rc = 0;
+    c->batch_thr = true;
+    const int nsh = nbins < 4096 ? nbins : 4096;
+    for (int i = 0; i < nreal && rc == 0; ++i) {
+        rc = occ_generate_dev(c, seed, stream0 + (unsigned long long)i, kind != KIND_BOND ? ks : -1, kind != KIND_SITE ? kb : -1,
+                              (unsigned long long*)(d_stats + 6));
+        if (rc) break;
+        rc = ccl_launch(c, kind);
+        if (rc) break;
+        if (nbins > 0) {
+            batch_hist_kernel<<<148 * 4, 256, sizeof(unsigned) * nsh, st>>>(c->g.t, c->label, c->size, nbins, d_hist);
+            c->launches++;
+        }
+        batch_accum_kernel<<<1, 1, 0, st>>>(c->d_sum, d_hist, nbins, d_stats);
+        c->launches++;
+    }
+    c->batch_thr = false;
+    c->labeled = false;              // the per-realization state on the host was never fetched
+    if (rc == 0) {
+        if (nbins > 0 && hist) PERC_CUDA(cudaMemcpyAsync(hist, d_hist, hb, cudaMemcpyDeviceToHost, st));
+        long long h[BATCH_NSTATS];
+        PERC_CUDA(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+        PERC_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < BATCH_NSTATS; ++k) stats[k] = h[k];
+        rc = (int)cudaGetLastError();
+    } else cudaStreamSynchronize(st);
+    cudaFree(d_hist);
+    cudaFree(d_stats);
+    return rc;
+}
+
+}  // namespace perc

@@ -237,7 +237,7 @@ static cudaError_t launch_local(Ctx* c, dim3 grid, int vec)
     return cudaGetLastError();
 }
 
-int ccl_run(Ctx* c, int kind)
+int ccl_launch(Ctx* c, int kind)
 {
     const Geom& g = c->g;
     cudaStream_t st = c->stream;
@@ -297,6 +297,14 @@ int ccl_run(Ctx* c, int kind)
     PERC_CUDA(cudaEventRecord(c->ev[5], st));
     PERC_CUDA(cudaGetLastError());
     c->kind = kind;
+    return 0;
+}
+
+int ccl_run(Ctx* c, int kind)
+{
+    int rc = ccl_launch(c, kind);
+    if (rc) return rc;
+    const bool slab = c->nranks > 1;
     c->labeled = true;
     rc = ccl_fetch_summary(c);
     if (rc) return rc;

@@ -37,6 +37,7 @@ struct Ctx {
     // ---- slab decomposition (SURVEY 8e mode 2); nranks = 1: the whole lattice lives here
     int nranks = 1, rank = 0;
     void* comm = nullptr;                // ncclComm_t
+    int stat_nranks = 1;                 // ranks of a communicator used only to reduce statistics (mode 1)
     int64_t* d_iface = nullptr;          // [nranks + 1] interface blocks (all-gather target + own block)
     int64_t* h_iface = nullptr;          // pinned
     StitchResult stitch;
@@ -52,6 +53,8 @@ struct Ctx {
     int64_t ks = 0, kb = 0;
     unsigned long long seed = 0, stream_id = 0;
     PhiloxThreshold thr_site{}, thr_bond{};
+    PhiloxThreshold* d_thr = nullptr;    // [2] batch mode: thresholds selected on the device
+    bool batch_thr = false;              // the mask builder reads d_thr instead of thr_site / thr_bond
 
     // ---- realization state
     uint8_t* mask = nullptr;      // [t]
@@ -80,7 +83,7 @@ struct Ctx {
     bool have_x = false;          // the last solve kept the interior voltages (perc_conduct, not perc_conduct_g)
 
     // ---- selection scratch
-    unsigned long long* d_hist = nullptr;   // [4096 + 8]
+    unsigned long long* d_hist = nullptr;   // [4096 + 16]: window histogram, below-count, SelState
     unsigned long long* d_cand = nullptr;   // candidate (key,id) pairs
     int cand_cap = 0;
 
@@ -107,10 +110,15 @@ int occ_upload_site_order(Ctx* c, const int32_t* order);
 int occ_upload_bond_order(Ctx* c, const int32_t* border);
 int occ_upload_flags(Ctx* c, const uint8_t* socc, const uint8_t* bocc);
 int occ_generate(Ctx* c, unsigned long long seed, unsigned long long stream, int64_t ks, int64_t kb);
+int occ_generate_dev(Ctx* c, unsigned long long seed, unsigned long long stream, int64_t ks, int64_t kb,
+                     unsigned long long* d_nfail);
 int occ_export(Ctx* c, uint8_t* socc, uint8_t* bocc);
 int occ_build_mask(Ctx* c, int kind);
 
 int ccl_run(Ctx* c, int kind);
+int ccl_launch(Ctx* c, int kind);        // the labeling pipeline without the final host synchronisation
+int batch_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsigned long long stream0, int64_t ks, int64_t kb,
+              int nbins, int64_t* hist, int64_t* stats);
 int ccl_fetch_summary(Ctx* c);
 int ccl_hist(Ctx* c, int nbins, int64_t* hist);
 int ccl_export_bond_labels(Ctx* c, int32_t* b3);

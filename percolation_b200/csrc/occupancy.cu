@@ -80,8 +80,10 @@ static AnySrc make_src(const Ctx* c)
 // mask builder (one thread per site)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) build_mask_kernel(Geom g, int kind, AnySrc src, uint8_t* __restrict__ mask,
-                                                         Summary* __restrict__ sum)
+                                                         Summary* __restrict__ sum, const PhiloxThreshold* __restrict__ dthr)
 {
+    // batch mode: the exact-count thresholds were selected on the device and never visited the host
+    if (dthr) { src.p.ts = dthr[0]; src.p.tb = dthr[1]; }
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned ns = 0, nbd = 0;
     if (i < g.t) {
@@ -134,7 +136,7 @@ int occ_build_mask(Ctx* c, int kind)
     AnySrc src = make_src(c);
     int64_t t = c->g.t;
     unsigned blocks = (unsigned)((t + 255) / 256);
-    build_mask_kernel<<<blocks, 256, 0, c->stream>>>(c->g, kind, src, c->mask, c->d_sum);
+    build_mask_kernel<<<blocks, 256, 0, c->stream>>>(c->g, kind, src, c->mask, c->d_sum, c->batch_thr ? c->d_thr : nullptr);
     c->launches++;
     return (int)cudaGetLastError();
 }
@@ -430,6 +432,144 @@ static int select_threshold(Ctx* c, int type, int64_t N, int64_t k, PhiloxThresh
         shift = 52; lo = 0;                    // estimate window missed: restart on the whole key range
     }
     return -5;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1, device-resident variant for batches of realizations: the same window histogram, but the bin
+// scan, the gather of the chosen bin and the pick of the k-th (key, id) all stay on the device, so
+// a batch runs without a single host synchronisation.  The window is +-8 sigma around the expected
+// key; if it misses, or the bin holds more than SEL_CAND keys, the threshold is flagged invalid and
+// the batch reports the realization (the caller re-runs it through occ_generate).
+// ------------------------------------------------------------------------------------------
+struct SelState { unsigned long long lo, width, below, inbin, count; int ok; int pad; };
+
+__global__ void __launch_bounds__(1024) select_scan_kernel(const unsigned long long* __restrict__ hist, long long k,
+                                                           unsigned long long lo, int shift, int cap, SelState* __restrict__ st)
+{
+    __shared__ unsigned long long part[1024];
+    const int tid = threadIdx.x;
+    unsigned long long v[4], s = 0;
+    for (int j = 0; j < 4; ++j) { v[j] = hist[tid * 4 + j]; s += v[j]; }
+    part[tid] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                     // inclusive scan of the per-thread sums
+        unsigned long long add = tid >= o ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += add;
+        __syncthreads();
+    }
+    const unsigned long long below = hist[SEL_BINS], total = part[1023];
+    const unsigned long long want = (unsigned long long)(k - 1);
+    if (tid == 0) { st->ok = (below <= want && want < below + total) ? 1 : 0; st->count = 0; }
+    __syncthreads();
+    unsigned long long cum = below + part[tid] - s;          // keys before this thread's first bin
+    for (int j = 0; j < 4; ++j) {
+        if (cum <= want && want < cum + v[j]) {
+            st->lo = lo + ((unsigned long long)(tid * 4 + j) << shift);
+            st->width = 1ull << shift;
+            st->below = cum;
+            st->inbin = v[j];
+            if (v[j] > (unsigned long long)cap) st->ok = 0;
+        }
+        cum += v[j];
+    }
+}
+
+__global__ void __launch_bounds__(256) select_gather_dev_kernel(Geom g, int type, unsigned long long seed, unsigned long long stream,
+                                                                SelState* __restrict__ st, unsigned long long* __restrict__ cand, int cap)
+{
+    if (!st->ok) return;
+    const unsigned long long lo = st->lo, width = st->width;
+    int64_t nelem = type == 0 ? g.t : (int64_t)g.ndir * g.t;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += stride) {
+        if (type == 1) {
+            int dir = (int)(e / g.t);
+            int64_t i = e - (int64_t)dir * g.t;
+            if (!bond_exists(g, (int)(i % g.m), (int)(i / g.m), dir)) continue;
+        }
+        unsigned long long k = elem_key(seed, stream, type, (unsigned long long)e);
+        if (k < lo || k - lo >= width) continue;
+        unsigned long long pos = atomicAdd(&st->count, 1ull);
+        if (pos < (unsigned long long)cap) { cand[2 * pos] = k; cand[2 * pos + 1] = (unsigned long long)e; }
+    }
+}
+
+// the (k - below)-th smallest (key, id) of the gathered bin, by rank counting
+__global__ void __launch_bounds__(1024) select_pick_kernel(long long k, const SelState* __restrict__ st,
+                                                           const unsigned long long* __restrict__ cand, int cap,
+                                                           PhiloxThreshold* __restrict__ thr, unsigned long long* __restrict__ nfail)
+{
+    if (threadIdx.x == 0) { thr->enabled = 1; thr->all = 0; }
+    if (!st->ok || st->count > (unsigned long long)cap || st->count != st->inbin) {
+        if (threadIdx.x == 0) { thr->key = 0; thr->id = 0; thr->enabled = 0; atomicAdd(nfail, 1ull); }
+        return;
+    }
+    const int n = (int)st->count;
+    const long long want = k - 1 - (long long)st->below;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long ki = cand[2 * i], ii = cand[2 * i + 1];
+        long long rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const unsigned long long kj = cand[2 * j], ij = cand[2 * j + 1];
+            rank += (kj < ki) || (kj == ki && ij < ii);
+        }
+        if (rank == want) { thr->key = ki; thr->id = ii; }
+    }
+}
+
+// device-resident threshold of realization (seed, stream): no host synchronisation
+static int select_threshold_dev(Ctx* c, int type, int64_t N, int64_t k, unsigned long long seed, unsigned long long stream,
+                                PhiloxThreshold* d_out, unsigned long long* d_nfail)
+{
+    PhiloxThreshold h{};
+    h.enabled = 1;
+    if (k <= 0 || k >= N) {
+        h.enabled = k > 0; h.all = k >= N;
+        PERC_CUDA(cudaMemcpyAsync(d_out, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));   // pageable: staged by the runtime
+        return 0;
+    }
+    const Geom gw = make_geom(c->g.lattice, c->g.m, c->g.ng, c->g.pbc);
+    long double frac = (long double)k / (long double)N;
+    long double sigma = sqrtl((long double)N * frac * (1.0L - frac));
+    long double hw = (8.0L * sigma + 16.0L) / (long double)N * 18446744073709551616.0L;
+    int shift = 0;
+    while (shift < 52 && ldexpl(1.0L, shift) * (SEL_BINS / 2) < hw) shift++;
+    long double centre = frac * 18446744073709551616.0L, span_half = ldexpl(1.0L, shift) * (SEL_BINS / 2);
+    long double l = centre - span_half, maxlo = 18446744073709551616.0L - ldexpl(1.0L, shift) * SEL_BINS;
+    if (l < 0) l = 0;
+    if (l > maxlo) l = maxlo;
+    unsigned long long lo = (unsigned long long)l;
+    if (shift >= 52) { shift = 52; lo = 0; }
+    SelState* st = (SelState*)(c->d_hist + SEL_BINS + 1);
+    unsigned grid = 148 * 8;
+    PERC_CUDA(cudaMemsetAsync(c->d_hist, 0, sizeof(unsigned long long) * (SEL_BINS + 8), c->stream));
+    select_hist_kernel<<<grid, 256, 0, c->stream>>>(gw, type, seed, stream, lo, shift, 0, c->d_hist);
+    select_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_hist, (long long)k, lo, shift, c->cand_cap, st);
+    select_gather_dev_kernel<<<grid, 256, 0, c->stream>>>(gw, type, seed, stream, st, c->d_cand, c->cand_cap);
+    select_pick_kernel<<<1, 1024, 0, c->stream>>>((long long)k, st, c->d_cand, c->cand_cap, d_out, d_nfail);
+    c->launches += 4;
+    return (int)cudaGetLastError();
+}
+
+// thresholds of one realization of a batch -> c->d_thr[0] (sites), c->d_thr[1] (bonds)
+int occ_generate_dev(Ctx* c, unsigned long long seed, unsigned long long stream, int64_t ks, int64_t kb,
+                     unsigned long long* d_nfail)
+{
+    c->seed = seed; c->stream_id = stream;
+    int rc = 0;
+    if (ks >= 0) {
+        rc = select_threshold_dev(c, 0, c->g.tg, ks, seed, stream, c->d_thr + 0, d_nfail);
+        if (rc) return rc;
+        c->site_src = SRC_PHILOX; c->ks = ks;
+    }
+    if (kb >= 0) {
+        rc = select_threshold_dev(c, 1, c->g.nb, kb, seed, stream, c->d_thr + 1, d_nfail);
+        if (rc) return rc;
+        c->bond_src = SRC_PHILOX; c->kb = kb;
+    }
+    c->labeled = false;
+    return 0;
 }
 
 int occ_generate(Ctx* c, unsigned long long seed, unsigned long long stream, int64_t ks, int64_t kb)

@@ -335,6 +335,15 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src, bool valid
 
 struct PtStage { double* sp; double* sr; uint8_t* scf; };
 
+template <int DIST> __device__ __forceinline__ bool pt_solve_row(const Geom& g, int y)
+{
+    return DIST ? solve_row(g, y) : (y >= 1 && y < g.n - 1);
+}
+template <int DIST> __device__ __forceinline__ bool pt_p_row(const Geom& g, int y)
+{
+    return DIST ? p_row(g, y) : (y >= 1 && y < g.n - 1);
+}
+
 __device__ __forceinline__ PtStage pt_stage(unsigned char* raw, int k)
 {
     PtStage s;
@@ -346,7 +355,7 @@ __device__ __forceinline__ PtStage pt_stage(unsigned char* raw, int k)
 }
 
 // issue the asynchronous copies of one tile (+ halo) into a stage
-template <int MODE>
+template <int MODE, int DIST>
 __device__ __forceinline__ void pt_issue(const Geom& g, const PtStage& s, int x0, int y0, const uint8_t* __restrict__ cfull,
                                          const double* __restrict__ vr, const double* __restrict__ vp_in)
 {
@@ -365,7 +374,7 @@ __device__ __forceinline__ void pt_issue(const Geom& g, const PtStage& s, int x0
                 const int pr = prb + it * (PT_THREADS / 64), gy = y0 + pr - 1;
                 if (pr < PT_ROWS) {
                     const bool ok = (unsigned)gy < (unsigned)g.n;
-                    cp_async16(&s.sp[so], ok ? pp : vp_in, ok && p_row(g, gy));               // Dirichlet rows: p = 0
+                    cp_async16(&s.sp[so], ok ? pp : vp_in, ok && pt_p_row<DIST>(g, gy));               // Dirichlet rows: p = 0
                     if (MODE == 0 || (pr >= 1 && pr <= PT_TY)) cp_async16(&s.sr[so], ok ? rp : vr, ok);
                 }
                 pp += step; rp += step; so += (PT_THREADS / 64) * PT_LD;
@@ -389,7 +398,7 @@ __device__ __forceinline__ void pt_issue(const Geom& g, const PtStage& s, int x0
         const bool ok = gy >= 0 && gy < g.n && hx >= 0 && hx < g.m;
         const int64_t j = ok ? (int64_t)gy * g.m + hx : 0;
         const int col = side ? 2 + xe : 1;
-        cp_async8(&s.sp[pr * PT_LD + col], vp_in + j, ok && p_row(g, gy));
+        cp_async8(&s.sp[pr * PT_LD + col], vp_in + j, ok && pt_p_row<DIST>(g, gy));
         if (MODE == 0) {
             cp_async8(&s.sr[pr * PT_LD + col], vr + j, ok);
             // the conduct byte of the halo cell: the aligned 4-byte word that holds it
@@ -399,11 +408,12 @@ __device__ __forceinline__ void pt_issue(const Geom& g, const PtStage& s, int x0
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-template <int LAT, int MODE>
+// DIST = 0: whole lattice on this GPU (row tests fold to 1 <= y <= n-2); DIST = 1: slab of a decomposed lattice
+template <int LAT, int MODE, int DIST>
 __global__ void __launch_bounds__(PT_THREADS, 1)
 pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double* __restrict__ vr,
                 const double* __restrict__ vp_in, double* __restrict__ vp_out, double* __restrict__ vx,
-                double* __restrict__ partial, PcgState* __restrict__ st, int keep_x, int ntx, int ntiles, int dist)
+                double* __restrict__ partial, PcgState* __restrict__ st, int keep_x, int ntx, int ntiles)
 {
     if (st->done) return;
     extern __shared__ __align__(16) unsigned char pt_raw[];
@@ -421,19 +431,19 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
     auto tile_of = [&](int t) { return MODE == 0 ? ntiles - 1 - t : t; };
 
     int t = blockIdx.x;
-    if (t < ntiles) { int tl = tile_of(t); pt_issue<MODE>(g, pt_stage(pt_raw, 0), (tl % ntx) * PT_TX, (tl / ntx) * PT_TY, cfull, vr, vp_in); }
+    if (t < ntiles) { int tl = tile_of(t); pt_issue<MODE, DIST>(g, pt_stage(pt_raw, 0), (tl % ntx) * PT_TX, (tl / ntx) * PT_TY, cfull, vr, vp_in); }
     for (int k = 0; t < ntiles; t += gridDim.x, ++k) {
         const int tl = tile_of(t), x0 = (tl % ntx) * PT_TX, y0 = (tl / ntx) * PT_TY;
         const PtStage s = pt_stage(pt_raw, k & 1);
         const int tn = t + gridDim.x;
         if (tn < ntiles) {
             int tnl = tile_of(tn);
-            pt_issue<MODE>(g, pt_stage(pt_raw, (k + 1) & 1), (tnl % ntx) * PT_TX, (tnl / ntx) * PT_TY, cfull, vr, vp_in);
+            pt_issue<MODE, DIST>(g, pt_stage(pt_raw, (k + 1) & 1), (tnl % ntx) * PT_TX, (tnl / ntx) * PT_TY, cfull, vr, vp_in);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         // every cell of tile + halo has its full neighbourhood inside the lattice
-        const bool interior = x0 >= 2 && x0 + PT_TX <= g.m - 2 && g.y0 + y0 >= 2 && g.y0 + y0 + PT_TY <= g.ng - 2;
+        const bool interior = x0 >= 2 && x0 + PT_TX <= g.m - 2 && (DIST ? g.y0 : 0) + y0 >= 2 && (DIST ? g.y0 : 0) + y0 + PT_TY <= (DIST ? g.ng : g.n) - 2;
         const int xe = g.m - x0 < PT_TX ? g.m - x0 : PT_TX;
 
         // ---- MODE 0: p_new = r / d + bk * p_old, in place on tile + halo (p is double-buffered in
@@ -447,7 +457,7 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
                     const int pr = prb + it * (PT_THREADS / 64), gy = y0 + pr - 1;
                     if (pr >= PT_ROWS) continue;
                     double2 v = make_double2(0.0, 0.0);
-                    if (p_row(g, gy)) {
+                    if (pt_p_row<DIST>(g, gy)) {
                         const double2 r2 = ld2(&s.sr[pr * PT_LD + 2 + cx]), p2 = ld2(&s.sp[pr * PT_LD + 2 + cx]);
                         const unsigned c01 = *reinterpret_cast<const unsigned short*>(&s.scf[pr * PT_CLD + 16 + cx]);
                         const unsigned e0 = interior ? e0i : neighbour_bits(g, gxc, gy);
@@ -458,7 +468,7 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
                     }
                     st2(&s.sp[pr * PT_LD + 2 + cx], v);
                     // slab mode: the halo copies of p are advanced here (pointwise recurrence) and stored for MODE 1
-                    if (pr >= 1 && pr <= PT_TY && p_row(g, gy) && !solve_row(g, gy)) st2(vp_out + (int64_t)gy * g.m + gxc, v);
+                    if (DIST && pr >= 1 && pr <= PT_TY && pt_p_row<DIST>(g, gy) && !pt_solve_row<DIST>(g, gy)) st2(vp_out + (int64_t)gy * g.m + gxc, v);
                 }
             }
             if (tid < 2 * PT_ROWS) {
@@ -468,7 +478,7 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
                 if (g.pbc) { if (hx == -1) hx = g.m - 1; else if (hx == g.m) hx = 0; }
                 const int col = side ? 2 + xe : 1;
                 double v = 0.0;
-                if (p_row(g, gy) && hx >= 0 && hx < g.m) {
+                if (pt_p_row<DIST>(g, gy) && hx >= 0 && hx < g.m) {
                     const unsigned cf = s.scf[pr * PT_CLD + (side ? 16 + PT_TX : 12) + (hx & 3)];
                     const unsigned ex = neighbour_bits(g, hx, gy);
                     const int nc = __popc(cf);
@@ -493,7 +503,7 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
                 const int ly = r0 + j, gy = y0 + ly;
                 const double2 up = ld2(c + PT_LD);
                 const double lf = c[-1], rt = c[2];
-                const bool valid = solve_row(g, gy) && gx < g.m;
+                const bool valid = pt_solve_row<DIST>(g, gy) && gx < g.m;
                 const unsigned c01 = *reinterpret_cast<const unsigned short*>(&s.scf[(ly + 1) * PT_CLD + 16 + 2 * tx]);
                 const unsigned cf0 = c01 & 0xffu, cf1 = c01 >> 8;
                 unsigned e0, e1;
@@ -533,7 +543,7 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
                         double2 r = ld2(&s.sr[(ly + 1) * PT_LD + 2 + 2 * tx]);
                         r.x -= ak * q.x; r.y -= ak * q.y;
                         st2(vr + i, r);
-                        if (keep_x || g.y0 + gy == 1 || g.y0 + gy == g.ng - 2) {
+                        if (keep_x || (DIST ? g.y0 : 0) + gy == 1 || (DIST ? g.y0 : 0) + gy == (DIST ? g.ng : g.n) - 2) {
                             double2 x = ld2(vx + i);
                             x.x += ak * cc.x; x.y += ak * cc.y;
                             st2(vx + i, x);
@@ -565,8 +575,8 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
         if (last_block(&st->ticket_b)) {
             double fa = fold_partials(partial, ntiles, 2, 0, sh);
             double fc = fold_partials(partial, ntiles, 2, 1, sh);
-            if (threadIdx.x == 0 && dist) { st->red[0] = fa; st->red[1] = fc; }      // summed over the ranks, then pcg_post
-            if (threadIdx.x == 0 && !dist) {
+            if (threadIdx.x == 0 && DIST) { st->red[0] = fa; st->red[1] = fc; }      // summed over the ranks, then pcg_post
+            if (threadIdx.x == 0 && !DIST) {
                 int it = st->iter + 1;
                 double err = sqrt(fc) / st->bnrm;
                 st->iter = it; st->err = err; st->rr = fc;
@@ -660,10 +670,14 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     }
     static bool attr_set = false;
     if (vec && !attr_set) {
-        PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_SQUARE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
-        PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_SQUARE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
-        PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_TRIANGULAR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
-        PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_TRIANGULAR, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+        PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_SQUARE, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+        PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_SQUARE, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+        PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_SQUARE, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+        PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_SQUARE, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+        PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_TRIANGULAR, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+        PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_TRIANGULAR, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+        PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_TRIANGULAR, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+        PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_TRIANGULAR, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
         attr_set = true;
     }
     int rc;
@@ -680,6 +694,17 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
         PERC_CUDA(cudaMemsetAsync(c->vp2, 0, sizeof(double) * g.t, s));
         c->launches++;
     }
+#define PIPE_ARGS(pin, pout) (g, prm, c->cfull, c->vr, pin, pout, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles)
+#define PIPE_LAUNCH(MODE, pin, pout)                                                                             \
+    do {                                                                                                         \
+        if (g.lattice == LAT_SQUARE) {                                                                           \
+            if (dist) pcg_pipe_kernel<LAT_SQUARE, MODE, 1><<<pgrid, PT_THREADS, PT_SMEM, s>>> PIPE_ARGS(pin, pout); \
+            else pcg_pipe_kernel<LAT_SQUARE, MODE, 0><<<pgrid, PT_THREADS, PT_SMEM, s>>> PIPE_ARGS(pin, pout);      \
+        } else {                                                                                                 \
+            if (dist) pcg_pipe_kernel<LAT_TRIANGULAR, MODE, 1><<<pgrid, PT_THREADS, PT_SMEM, s>>> PIPE_ARGS(pin, pout); \
+            else pcg_pipe_kernel<LAT_TRIANGULAR, MODE, 0><<<pgrid, PT_THREADS, PT_SMEM, s>>> PIPE_ARGS(pin, pout);  \
+        }                                                                                                        \
+    } while (0)
     double* pold = c->vp; double* pnew = c->vp2;
     float sp_ms = 0.f, up_ms = 0.f; int nsamp = 0;
     int chunk = 16, iters_before = 0;
@@ -690,10 +715,7 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
             bool sample = (k == chunk / 2);
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[8], s));
             if (vec) {
-                if (g.lattice == LAT_SQUARE)
-                    pcg_pipe_kernel<LAT_SQUARE, 0><<<pgrid, PT_THREADS, PT_SMEM, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles, dist);
-                else
-                    pcg_pipe_kernel<LAT_TRIANGULAR, 0><<<pgrid, PT_THREADS, PT_SMEM, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles, dist);
+                PIPE_LAUNCH(0, pold, pnew);
             } else if (g.lattice == LAT_SQUARE)
                 pcg_spmv_kernel<LAT_SQUARE><<<sgrid, SP_THREADS, 0, s>>>(g, prm, c->cfull, c->vr, pold, pnew, c->vq, c->partial, c->d_pcg);
             else
@@ -705,10 +727,7 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
             }
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[9], s));
             if (vec) {
-                if (g.lattice == LAT_SQUARE)
-                    pcg_pipe_kernel<LAT_SQUARE, 1><<<pgrid, PT_THREADS, PT_SMEM, s>>>(g, prm, c->cfull, c->vr, pnew, nullptr, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles, dist);
-                else
-                    pcg_pipe_kernel<LAT_TRIANGULAR, 1><<<pgrid, PT_THREADS, PT_SMEM, s>>>(g, prm, c->cfull, c->vr, pnew, nullptr, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles, dist);
+                PIPE_LAUNCH(1, pnew, nullptr);
             } else
                 pcg_update_kernel<<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, pnew, c->vq, c->partial, c->d_pcg);
             if (dist) {
@@ -752,6 +771,8 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     c->solved = true;
     c->have_x = want_x != 0;
     return 0;
+#undef PIPE_LAUNCH
+#undef PIPE_ARGS
 }
 
 }  // namespace perc

@@ -30,6 +30,7 @@ SYMBOLS = [
     "perc_conduct", "perc_conduct_g", "perc_get_voltage", "perc_launch_count", "perc_phase_ms", "perc_stream",
     "perc_create_slab", "perc_comm_unique_id", "perc_comm_init", "perc_slab_rows", "perc_generate_i8",
     "perc_summary_i8", "perc_span_i8", "perc_get_site_labels_i8", "perc_stitch_host",
+    "perc_batch", "perc_comm_init_rank", "perc_allreduce_stats",
 ]
 
 
@@ -231,6 +232,29 @@ class Lattice:
         self._call("perc_first_span", _i32(kind), _i32(which), C.byref(kstar), C.byref(f), C.byref(maxcs),
                    C.byref(perccls))
         return dict(kstar=kstar.value, f=np.float32(f.value), maxcs=maxcs.value, perccls=perccls.value)
+
+    # ---- batches of independent realizations
+    BATCH_STATS = ("realizations", "sum_ncl", "sum_maxcs", "spanning", "sum_nspan", "sum_perccls", "failed",
+                   "sum_maxcs2", "sum_sites", "sum_bonds")
+
+    def batch(self, kind, nreal, seed, stream0=0, ks=0, kb=0, nbins=0):
+        """nreal realizations (streams stream0 .. stream0+nreal-1) labeled on the device; returns (hist, stats)"""
+        hist = np.zeros(max(nbins, 1), np.int64)
+        stats = np.zeros(16, np.int64)
+        self._call("perc_batch", _i32(kind), _i32(nreal), _i64(seed), _i64(stream0), _i32(ks), _i32(kb), _i32(nbins),
+                   _ptr(hist, C.c_int64), _ptr(stats, C.c_int64))
+        return hist[:nbins].copy(), dict(zip(self.BATCH_STATS, (int(v) for v in stats)))
+
+    def comm_init_rank(self, nranks, rank, unique_id):
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        self._call("perc_comm_init_rank", _i32(nranks), _i32(rank), _ptr(uid, C.c_uint8))
+
+    def allreduce_stats(self, ivals=None, dvals=None):
+        """one NCCL reduction (sum) of the statistics of a sharded run; in place, returns the arrays"""
+        iv = np.ascontiguousarray(ivals if ivals is not None else [], np.int64)
+        dv = np.ascontiguousarray(dvals if dvals is not None else [], np.float64)
+        self._call("perc_allreduce_stats", _i32(iv.size), _ptr(iv, C.c_int64), _i32(dv.size), _ptr(dv, C.c_double))
+        return iv, dv
 
     # ---- conductance
     def conduct(self, cluster_id=0, Va=1.0, g0=1.0, gleak=1e-12, tol=1e-8, itmax=2500, read_thresh=1e-10,

@@ -376,3 +376,38 @@ def test_c_driver_full_path(P, tmp_path):
     exe = _build_c_driver(str(tmp_path))
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("OK nb="), out.stdout + out.stderr
+
+
+# ---- batches of realizations (device-resident selection + statistics) ------------------------
+@pytest.mark.parametrize("lat,kind,m,n,pbc,ps,pb", [(1, 1, 100, 100, 0, 0.60, 0.0), (2, 2, 128, 96, 1, 0.0, 0.35),
+                                                   (1, 3, 144, 80, 0, 0.8, 0.62), (2, 1, 64, 64, 0, 0.5, 0.0)])
+def test_batch_equals_realization_loop(P, lat, kind, m, n, pbc, ps, pb):
+    """perc_batch (no host synchronisation inside) == the same realizations one call at a time"""
+    nreal, nbins, seed, stream0 = 7, 48, 58302, 11
+    with P.Lattice(lat, m, n, pbc) as L:
+        ks, kb = int(ps * L.t), int(pb * L.nb)
+        hist = np.zeros(nbins, np.int64)
+        want = dict(realizations=0, sum_ncl=0, sum_maxcs=0, spanning=0, sum_nspan=0, sum_perccls=0, failed=0, sum_maxcs2=0,
+                    sum_sites=0, sum_bonds=0)
+        for i in range(nreal):
+            L.generate(seed, stream0 + i, ks if kind != 2 else -1, kb if kind != 1 else -1)
+            L.label(kind)
+            hist += L.hist(nbins)
+            sm = L.summary()
+            ids, sizes = L.span()
+            want["realizations"] += 1
+            want["sum_ncl"] += sm["ncl"]
+            want["sum_maxcs"] += sm["maxcs"]
+            want["sum_maxcs2"] += sm["maxcs"] ** 2
+            want["spanning"] += len(ids) > 0
+            want["sum_nspan"] += len(ids)
+            want["sum_perccls"] += int(sizes[0]) if len(ids) else 0
+            want["sum_sites"] += ks if kind != 2 else 0
+            want["sum_bonds"] += kb if kind != 1 else 0
+        got_hist, got = L.batch(kind, nreal, seed, stream0, ks, kb, nbins)
+        assert got == want
+        assert (got_hist == hist).all()
+        # a handle is usable as before after a batch
+        L.generate(seed, stream0, ks if kind != 2 else -1, kb if kind != 1 else -1)
+        L.label(kind)
+        assert L.summary()["ncl"] > 0
