@@ -36,7 +36,8 @@ void stitch_host(int nranks, int rank, int m, const int64_t* gathered, StitchRes
             if ((side == 0 && r == 0) || (side == 1 && r == nranks - 1)) continue;
             const int64_t* ids = blk + (side ? L.rowB() : L.rowA());
             const int64_t* sz = blk + (side ? L.sizeB() : L.sizeA());
-            for (int x = 0; x < m; ++x) if (ids[x]) nodes.push_back({node_key(r, ids[x]), sz[x]});
+            for (int x = 0; x < m; ++x)                      // neighbouring sites mostly repeat the label: keep the changes
+                if (ids[x] && (x == 0 || ids[x] != ids[x - 1])) nodes.push_back({node_key(r, ids[x]), sz[x]});
         }
     }
     std::sort(nodes.begin(), nodes.end(), [](const Node& a, const Node& b) { return a.key < b.key; });
@@ -54,6 +55,7 @@ void stitch_host(int nranks, int rank, int m, const int64_t* gathered, StitchRes
         for (int x = 0; x < m; ++x) {
             if ((lo[x] != 0) != (hi[x] != 0)) { out->error = 1; return; }
             if (!lo[x]) continue;
+            if (x > 0 && lo[x] == lo[x - 1] && hi[x] == hi[x - 1]) continue;      // same pair as the column before
             int a = uf_find(parent, index_of(node_key(r, lo[x]))), b = uf_find(parent, index_of(node_key(r + 1, hi[x])));
             if (a != b) parent[a > b ? a : b] = a > b ? b : a;
         }
@@ -93,7 +95,7 @@ void stitch_host(int nranks, int rank, int m, const int64_t* gathered, StitchRes
         const int64_t* top = gathered + (nranks - 1) * W + L.rowTop();
         std::vector<int> cls;
         for (int x = 0; x < m; ++x) {
-            if (!top[x]) continue;
+            if (!top[x] || (x > 0 && top[x] == top[x - 1])) continue;
             int k = index_of(node_key(nranks - 1, top[x]));
             if (k < 0) continue;
             int c = uf_find(parent, k);

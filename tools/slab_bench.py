@@ -47,6 +47,7 @@ def main():
            "label_device_ms": float(ph[1] + ph[2] + ph[3] + ph[4]), "mask_ms": float(ph[0]),
            "gsites_per_s_wall": t / min(times) / 1e9, "ncl": sm["ncl"], "maxcs": sm["maxcs"], "nspan": sm["nspan"]}
     if sm["nspan"] and args.iters > 0:
+        S.conduct(0, tol=1e-30, itmax=15, voltages=False)      # warm-up: NCCL sets its channels up on first use
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         res = S.conduct(0, tol=1e-30, itmax=args.iters - 1, voltages=False)
