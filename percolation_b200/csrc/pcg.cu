@@ -18,6 +18,7 @@
 // Reductions are two-stage and fixed-order (per-block partial, last block folds them), so a
 // solve is bit-reproducible for a given lattice size.
 #include <cmath>
+#include <cuda.h>
 #include "context.h"
 
 namespace perc {
@@ -305,9 +306,11 @@ constexpr int PT_TX = 128, PT_TY = 32, PT_THREADS = 512, PT_ROWS = PT_TY + 2;
 constexpr int PT_RPT = PT_TY / (PT_THREADS / 64);      // consecutive tile rows per thread in the stencil
 constexpr int PT_LD = PT_TX + 4;            // doubles per staged row: [1] left halo, [2..129] tile, [130] right halo
 constexpr int PT_CLD = PT_TX + 32;          // bytes per staged cfull row: [12..15] left halo word, [16..143] tile, [144..147] right halo word
-constexpr int PT_STAGE_BYTES = 2 * PT_ROWS * PT_LD * 8 + PT_ROWS * PT_CLD;
+constexpr int PT_VEC_BYTES = (PT_ROWS * PT_LD * 8 + 127) / 128 * 128;      // one staged fp64 tile (TMA destinations: 128-byte aligned)
+constexpr int PT_CF_BYTES = (PT_ROWS * PT_CLD + 127) / 128 * 128;
+constexpr int PT_STAGE_BYTES = 2 * PT_VEC_BYTES + PT_CF_BYTES;
 // 1/d table, one private copy per lane (entry [idx][lane]): a lookup is conflict-free whatever the indices
-constexpr size_t PT_SMEM = 2 * (size_t)PT_STAGE_BYTES + sizeof(double) * 64 * 32 + sizeof(double) * 32;
+constexpr size_t PT_SMEM = 2 * (size_t)PT_STAGE_BYTES + sizeof(double) * 64 * 32 + sizeof(double) * 32 + 16;
 
 // diagonal of a site with nc conducting and nl leaking bonds; int -> double by the 2^52 trick (no I2F)
 __device__ __forceinline__ double pt_diag(int nc, int nl, const PcgParams& prm)
@@ -349,74 +352,89 @@ __device__ __forceinline__ PtStage pt_stage(unsigned char* raw, int k)
     PtStage s;
     unsigned char* base = raw + (size_t)k * PT_STAGE_BYTES;
     s.sp = reinterpret_cast<double*>(base);
-    s.sr = s.sp + PT_ROWS * PT_LD;
-    s.scf = reinterpret_cast<uint8_t*>(s.sr + PT_ROWS * PT_LD);
+    s.sr = reinterpret_cast<double*>(base + PT_VEC_BYTES);
+    s.scf = reinterpret_cast<uint8_t*>(base + 2 * PT_VEC_BYTES);
     return s;
 }
 
-// issue the asynchronous copies of one tile (+ halo) into a stage
+// ---- TMA bulk copies (cp.async.bulk, completion counted on an mbarrier) ---------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one TMA tensor copy: box (w x PT_ROWS) of a row-major 2-D array at element coordinates (cx, cy); elements
+// outside the array arrive as zeros
+__device__ __forceinline__ void tma_box_g2s(void* dst, const CUtensorMap* map, int cx, int cy, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(cx), "r"(cy), "r"(smem_u32(bar)) : "memory");
+}
+
+// Issue the asynchronous copies of one tile (+ halo) into a stage: ONE thread, three TMA tensor copies
+// (cp.async.bulk.tensor.2d, SASS UTMALDG): the 132 x 34 fp64 boxes of p and r at (x0-2, y0-1) and the
+// 160 x 34 byte box of the conduct mask at (x0-16, y0-1).  The boxes carry the halo rows / columns with
+// them, and whatever lies outside the lattice arrives as zeros.  The stage's mbarrier counts the bytes.
+template <int MODE>
+__device__ __forceinline__ void pt_issue(const PtStage& s, unsigned long long* bar, int x0, int y0,
+                                         const CUtensorMap* tm_p, const CUtensorMap* tm_r, const CUtensorMap* tm_cf)
+{
+    if (threadIdx.x != 0) return;
+    mbar_arrive_expect(bar, 2u * PT_ROWS * PT_LD * 8u + PT_ROWS * PT_CLD);
+    tma_box_g2s(s.sp, tm_p, x0 - 2, y0 - 1, bar);
+    tma_box_g2s(s.sr, tm_r, x0 - 2, y0 - 1, bar);
+    tma_box_g2s(s.scf, tm_cf, x0 - 16, y0 - 1, bar);
+}
+
+// periodic wrap: the halo column of an edge tile lives at the other end of the lattice row (plain loads:
+// two tiles per lattice row, only with pbc)
 template <int MODE, int DIST>
-__device__ __forceinline__ void pt_issue(const Geom& g, const PtStage& s, int x0, int y0, const uint8_t* __restrict__ cfull,
-                                         const double* __restrict__ vr, const double* __restrict__ vp_in)
+__device__ __forceinline__ void pt_wrap_halo(const Geom& g, const PtStage& s, int x0, int y0, const uint8_t* __restrict__ cfull,
+                                             const double* __restrict__ vr, const double* __restrict__ vp_in)
 {
     const int tid = threadIdx.x;
-    {
-        // tile columns, 2 doubles per copy: the thread keeps its column pair and walks up the rows in
-        // steps of PT_THREADS / 64 (one pointer increment per copy instead of index arithmetic)
-        const int cx = (tid & 63) * 2, prb = tid >> 6, gx = x0 + cx;
-        if (gx < g.m) {                                                      // columns >= m are never read
-            const int64_t off = (int64_t)(y0 + prb - 1) * g.m + gx, step = (int64_t)(PT_THREADS / 64) * g.m;
-            const double* pp = vp_in + off;
-            const double* rp = vr + off;
-            int so = prb * PT_LD + 2 + cx;
-#pragma unroll
-            for (int it = 0; it < (PT_ROWS + PT_THREADS / 64 - 1) / (PT_THREADS / 64); ++it) {
-                const int pr = prb + it * (PT_THREADS / 64), gy = y0 + pr - 1;
-                if (pr < PT_ROWS) {
-                    const bool ok = (unsigned)gy < (unsigned)g.n;
-                    cp_async16(&s.sp[so], ok ? pp : vp_in, ok && pt_p_row<DIST>(g, gy));               // Dirichlet rows: p = 0
-                    if (MODE == 0 || (pr >= 1 && pr <= PT_TY)) cp_async16(&s.sr[so], ok ? rp : vr, ok);
-                }
-                pp += step; rp += step; so += (PT_THREADS / 64) * PT_LD;
-            }
-        }
+    if (!g.pbc || tid >= 2 * PT_ROWS) return;
+    const int side = tid >= PT_ROWS, pr = tid - side * PT_ROWS;
+    const int gy = y0 + pr - 1;
+    const int xe = g.m - x0 < PT_TX ? g.m - x0 : PT_TX;
+    if (side ? x0 + PT_TX < g.m : x0 != 0) return;                            // inner halo columns came with the row
+    if (gy < 0 || gy >= g.n) return;
+    const int hx = side ? 0 : g.m - 1;
+    const int64_t j = (int64_t)gy * g.m + hx;
+    const int col = side ? 2 + xe : 1;
+    s.sp[pr * PT_LD + col] = vp_in[j];
+    if (MODE == 0) {
+        s.sr[pr * PT_LD + col] = vr[j];
+        s.scf[pr * PT_CLD + (side ? 16 + xe : 15)] = cfull[j];
     }
-    if (tid < PT_ROWS * (PT_TX / 16)) {                                       // conduct bytes, 16 per copy
-        const int pr = tid / (PT_TX / 16), cx = (tid % (PT_TX / 16)) * 16;
-        const int gy = y0 + pr - 1, gx = x0 + cx;
-        if (gx < g.m) {
-            const bool ok = (unsigned)gy < (unsigned)g.n;
-            cp_async16(&s.scf[pr * PT_CLD + 16 + cx], cfull + (ok ? (int64_t)gy * g.m + gx : 0), ok);
-        }
-    }
-    if (tid < 2 * PT_ROWS) {                                                 // halo columns (periodic wrap aware)
-        const int side = tid >= PT_ROWS, pr = tid - side * PT_ROWS;
-        const int gy = y0 + pr - 1;
-        const int xe = g.m - x0 < PT_TX ? g.m - x0 : PT_TX;                   // real columns of this tile
-        int hx = side ? x0 + xe : x0 - 1;
-        if (g.pbc) { if (hx == -1) hx = g.m - 1; else if (hx == g.m) hx = 0; }
-        const bool ok = gy >= 0 && gy < g.n && hx >= 0 && hx < g.m;
-        const int64_t j = ok ? (int64_t)gy * g.m + hx : 0;
-        const int col = side ? 2 + xe : 1;
-        cp_async8(&s.sp[pr * PT_LD + col], vp_in + j, ok && pt_p_row<DIST>(g, gy));
-        if (MODE == 0) {
-            cp_async8(&s.sr[pr * PT_LD + col], vr + j, ok);
-            // the conduct byte of the halo cell: the aligned 4-byte word that holds it
-            cp_async4(&s.scf[pr * PT_CLD + (side ? 16 + PT_TX : 12)], cfull + (j & ~(int64_t)3), ok);
-        }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // DIST = 0: whole lattice on this GPU (row tests fold to 1 <= y <= n-2); DIST = 1: slab of a decomposed lattice
 template <int LAT, int MODE, int DIST>
 __global__ void __launch_bounds__(PT_THREADS, 1)
-pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double* __restrict__ vr,
-                const double* __restrict__ vp_in, double* __restrict__ vp_out, double* __restrict__ vx,
+pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_r,
+                const __grid_constant__ CUtensorMap tm_cf, Geom g, PcgParams prm, const uint8_t* __restrict__ cfull,
+                double* __restrict__ vr, const double* __restrict__ vp_in, double* __restrict__ vp_out, double* __restrict__ vx,
                 double* __restrict__ partial, PcgState* __restrict__ st, int keep_x, int ntx, int ntiles)
 {
     if (st->done) return;
-    extern __shared__ __align__(16) unsigned char pt_raw[];
+    extern __shared__ __align__(128) unsigned char pt_raw[];
     double* dinv = reinterpret_cast<double*>(pt_raw + 2 * (size_t)PT_STAGE_BYTES);      // [64][32]
     double* sh = dinv + 64 * 32;
     const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6, lane = tid & 31;
@@ -424,6 +442,13 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
         const double d = pt_diag((k >> 5) >> 3, (k >> 5) & 7, prm);
         dinv[k] = d > 0.0 ? 1.0 / d : 0.0;
     }
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sh + 32);          // one mbarrier per stage
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     const double bk = st->bk, ak = st->ak;          // slab mode: set by pcg_post_kernel after the all-reduce
     const double dg = prm.g0 - prm.gleak;
     // MODE 0 sweeps the tiles from the END of the lattice to its start, MODE 1 front to back: each
@@ -431,17 +456,18 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
     auto tile_of = [&](int t) { return MODE == 0 ? ntiles - 1 - t : t; };
 
     int t = blockIdx.x;
-    if (t < ntiles) { int tl = tile_of(t); pt_issue<MODE, DIST>(g, pt_stage(pt_raw, 0), (tl % ntx) * PT_TX, (tl / ntx) * PT_TY, cfull, vr, vp_in); }
+    if (t < ntiles) { int tl = tile_of(t); pt_issue<MODE>(pt_stage(pt_raw, 0), &bars[0], (tl % ntx) * PT_TX, (tl / ntx) * PT_TY, &tm_p, &tm_r, &tm_cf); }
     for (int k = 0; t < ntiles; t += gridDim.x, ++k) {
         const int tl = tile_of(t), x0 = (tl % ntx) * PT_TX, y0 = (tl / ntx) * PT_TY;
         const PtStage s = pt_stage(pt_raw, k & 1);
         const int tn = t + gridDim.x;
-        if (tn < ntiles) {
+        if (tn < ntiles) {                              // the other stage was released by the barriers of the last tile
             int tnl = tile_of(tn);
-            pt_issue<MODE, DIST>(g, pt_stage(pt_raw, (k + 1) & 1), (tnl % ntx) * PT_TX, (tnl / ntx) * PT_TY, cfull, vr, vp_in);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
+            pt_issue<MODE>(pt_stage(pt_raw, (k + 1) & 1), &bars[(k + 1) & 1], (tnl % ntx) * PT_TX, (tnl / ntx) * PT_TY, &tm_p, &tm_r, &tm_cf);
+        }
+        mbar_wait(&bars[k & 1], (unsigned)((k >> 1) & 1));
+        pt_wrap_halo<MODE, DIST>(g, s, x0, y0, cfull, vr, vp_in);
+        if (g.pbc) __syncthreads();
         // every cell of tile + halo has its full neighbourhood inside the lattice
         const bool interior = x0 >= 2 && x0 + PT_TX <= g.m - 2 && (DIST ? g.y0 : 0) + y0 >= 2 && (DIST ? g.y0 : 0) + y0 + PT_TY <= (DIST ? g.ng : g.n) - 2;
         const int xe = g.m - x0 < PT_TX ? g.m - x0 : PT_TX;
@@ -479,7 +505,7 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
                 const int col = side ? 2 + xe : 1;
                 double v = 0.0;
                 if (pt_p_row<DIST>(g, gy) && hx >= 0 && hx < g.m) {
-                    const unsigned cf = s.scf[pr * PT_CLD + (side ? 16 + PT_TX : 12) + (hx & 3)];
+                    const unsigned cf = s.scf[pr * PT_CLD + (side ? 16 + xe : 15)];
                     const unsigned ex = neighbour_bits(g, hx, gy);
                     const int nc = __popc(cf);
                     v = s.sr[pr * PT_LD + col] * dinv[(((nc << 3) | (__popc(ex) - nc)) << 5) + lane] + bk * s.sp[pr * PT_LD + col];
@@ -557,6 +583,8 @@ pcg_pipe_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
             }
             (void)dlf;
         }
+        // generic-proxy accesses to this stage are ordered before the bulk copies that will refill it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         // per-tile partial sums (block_sum synchronises: every thread is done with this stage afterwards)
         if (MODE == 0) {
             double bs = block_sum(acc0, sh);
@@ -642,6 +670,32 @@ pcg_readout_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, con
 // ------------------------------------------------------------------------------------------
 static unsigned nblk(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
+// 2-D TMA descriptor of a row-major (cols x rows) array; box = box_cols x PT_ROWS elements.  The driver entry
+// point is resolved at run time, so the library still links against nothing but the CUDA runtime.
+static int make_tensor_map(CUtensorMap* map, void* base, int elem_bytes, int cols, int rows, int box_cols)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return (int)e;
+        if (!fn || q != cudaDriverEntryPointSuccess) return (int)cudaErrorNotSupported;
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * elem_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)PT_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(map, elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 900 + (int)r;
+}
+
 int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double tol, int itmax,
               double read_thresh, int keep_x, double* Gtop, double* Gbot, int* iter, double* err)
 {
@@ -668,6 +722,7 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
         PERC_CUDA(cudaMalloc(&c->partial, sizeof(double) * need));
         c->partial_cap = need;
     }
+    int rc = 0;
     static bool attr_set = false;
     if (vec && !attr_set) {
         PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_SQUARE, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
@@ -680,21 +735,28 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
         PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_TRIANGULAR, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
         attr_set = true;
     }
-    int rc;
     PERC_CUDA(cudaMemsetAsync(c->d_pcg, 0, sizeof(PcgState), s));
     PERC_CUDA(cudaEventRecord(c->ev[6], s));
     build_cfull_kernel<<<nblk(g.t), 256, 0, s>>>(g, c->kind, cluster_id, c->mask, c->label, c->cfull);
     if (dist) { rc = slab_halo_exchange(c, c->cfull, 1); if (rc) return rc; }           // conduct bytes of the halo rows
     pcg_init_kernel<<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, c->vp, c->vq, c->partial, c->d_pcg, tol, itmax, dist);
     c->launches += 2;
+    PERC_CUDA(cudaMemsetAsync(c->vp2, 0, sizeof(double) * g.t, s));     // rows the kernels never write (Dirichlet) must read 0
     if (dist) {
         rc = slab_allreduce_f64(c, c->d_pcg->red, 3); if (rc) return rc;
         pcg_post_kernel<<<1, 1, 0, s>>>(c->d_pcg, 0);
         rc = slab_halo_exchange(c, c->vr, 8); if (rc) return rc;                        // r = b on the halo rows
-        PERC_CUDA(cudaMemsetAsync(c->vp2, 0, sizeof(double) * g.t, s));
         c->launches++;
     }
-#define PIPE_ARGS(pin, pout) (g, prm, c->cfull, c->vr, pin, pout, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles)
+    // TMA descriptors of the arrays the pipeline stages (row-major m x n, boxes of 34 rows)
+    CUtensorMap tm_r{}, tm_pa{}, tm_pb{}, tm_cf{};
+    if (vec) {
+        rc = make_tensor_map(&tm_r, c->vr, 8, g.m, g.n, PT_LD); if (rc) return rc;
+        rc = make_tensor_map(&tm_pa, c->vp, 8, g.m, g.n, PT_LD); if (rc) return rc;
+        rc = make_tensor_map(&tm_pb, c->vp2, 8, g.m, g.n, PT_LD); if (rc) return rc;
+        rc = make_tensor_map(&tm_cf, c->cfull, 1, g.m, g.n, PT_CLD); if (rc) return rc;
+    }
+#define PIPE_ARGS(pin, pout) ((pin) == c->vp ? tm_pa : tm_pb, tm_r, tm_cf, g, prm, c->cfull, c->vr, pin, pout, c->vx, c->partial, c->d_pcg, keep_x, ntx, ntiles)
 #define PIPE_LAUNCH(MODE, pin, pout)                                                                             \
     do {                                                                                                         \
         if (g.lattice == LAT_SQUARE) {                                                                           \
