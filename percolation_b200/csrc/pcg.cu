@@ -309,8 +309,8 @@ constexpr int PT_CLD = PT_TX + 32;          // bytes per staged cfull row: [12..
 constexpr int PT_VEC_BYTES = (PT_ROWS * PT_LD * 8 + 127) / 128 * 128;      // one staged fp64 tile (TMA destinations: 128-byte aligned)
 constexpr int PT_CF_BYTES = (PT_ROWS * PT_CLD + 127) / 128 * 128;
 constexpr int PT_STAGE_BYTES = 2 * PT_VEC_BYTES + PT_CF_BYTES;
-// 1/d table, one private copy per lane (entry [idx][lane]): a lookup is conflict-free whatever the indices
-constexpr size_t PT_SMEM = 2 * (size_t)PT_STAGE_BYTES + sizeof(double) * 64 * 32 + sizeof(double) * 32 + 16;
+// (d, 1/d) table, one private copy per lane (entry [idx][lane]): a lookup is conflict-free whatever the indices
+constexpr size_t PT_SMEM = 2 * (size_t)PT_STAGE_BYTES + sizeof(double2) * 64 * 32 + sizeof(double) * 32 + 16;
 
 // diagonal of a site with nc conducting and nl leaking bonds; int -> double by the 2^52 trick (no I2F)
 __device__ __forceinline__ double pt_diag(int nc, int nl, const PcgParams& prm)
@@ -337,6 +337,12 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src, bool valid
 }
 
 struct PtStage { double* sp; double* sr; uint8_t* scf; };
+
+// acc += v if bit != 0, as ONE predicated DADD (the compiler's select-then-add costs two FSEL more)
+__device__ __forceinline__ void padd(double& acc, double v, unsigned bit)
+{
+    asm("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p add.f64 %0, %0, %1;\n}" : "+d"(acc) : "d"(v), "r"(bit));
+}
 
 template <int DIST> __device__ __forceinline__ bool pt_solve_row(const Geom& g, int y)
 {
@@ -435,12 +441,12 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
 {
     if (st->done) return;
     extern __shared__ __align__(128) unsigned char pt_raw[];
-    double* dinv = reinterpret_cast<double*>(pt_raw + 2 * (size_t)PT_STAGE_BYTES);      // [64][32]
-    double* sh = dinv + 64 * 32;
+    double2* dtab = reinterpret_cast<double2*>(pt_raw + 2 * (size_t)PT_STAGE_BYTES);    // [64][32] (d, 1/d)
+    double* sh = reinterpret_cast<double*>(dtab + 64 * 32);
     const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6, lane = tid & 31;
     for (int k = tid; k < 64 * 32; k += PT_THREADS) {
         const double d = pt_diag((k >> 5) >> 3, (k >> 5) & 7, prm);
-        dinv[k] = d > 0.0 ? 1.0 / d : 0.0;
+        dtab[k] = make_double2(d, d > 0.0 ? 1.0 / d : 0.0);
     }
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sh + 32);          // one mbarrier per stage
     if (tid == 0) {
@@ -489,8 +495,8 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
                         const unsigned e0 = interior ? e0i : neighbour_bits(g, gxc, gy);
                         const unsigned e1 = interior ? e1i : neighbour_bits(g, gxc + 1, gy);
                         const int n0 = __popc(c01 & 0xffu), n1 = __popc(c01 >> 8);
-                        v.x = r2.x * dinv[(((n0 << 3) | (__popc(e0) - n0)) << 5) + lane] + bk * p2.x;
-                        v.y = r2.y * dinv[(((n1 << 3) | (__popc(e1) - n1)) << 5) + lane] + bk * p2.y;
+                        v.x = r2.x * dtab[(((n0 << 3) | (__popc(e0) - n0)) << 5) + lane].y + bk * p2.x;
+                        v.y = r2.y * dtab[(((n1 << 3) | (__popc(e1) - n1)) << 5) + lane].y + bk * p2.y;
                     }
                     st2(&s.sp[pr * PT_LD + 2 + cx], v);
                     // slab mode: the halo copies of p are advanced here (pointwise recurrence) and stored for MODE 1
@@ -508,7 +514,7 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
                     const unsigned cf = s.scf[pr * PT_CLD + (side ? 16 + xe : 15)];
                     const unsigned ex = neighbour_bits(g, hx, gy);
                     const int nc = __popc(cf);
-                    v = s.sr[pr * PT_LD + col] * dinv[(((nc << 3) | (__popc(ex) - nc)) << 5) + lane] + bk * s.sp[pr * PT_LD + col];
+                    v = s.sr[pr * PT_LD + col] * dtab[(((nc << 3) | (__popc(ex) - nc)) << 5) + lane].y + bk * s.sp[pr * PT_LD + col];
                 }
                 s.sp[pr * PT_LD + col] = v;
             }
@@ -550,16 +556,17 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
                     }
                 }
                 double con0 = 0.0, con1 = 0.0;    // conducting neighbours (cfull bits only on existing bonds)
-                if (cf0 & NB_E) con0 += cc.y;  if (cf0 & NB_W) con0 += lf;   if (cf0 & NB_N) con0 += up.x;  if (cf0 & NB_S) con0 += dn.x;
-                if (cf1 & NB_E) con1 += rt;    if (cf1 & NB_W) con1 += cc.x; if (cf1 & NB_N) con1 += up.y;  if (cf1 & NB_S) con1 += dn.y;
+                padd(con0, cc.y, cf0 & NB_E); padd(con0, lf, cf0 & NB_W);   padd(con0, up.x, cf0 & NB_N); padd(con0, dn.x, cf0 & NB_S);
+                padd(con1, rt, cf1 & NB_E);   padd(con1, cc.x, cf1 & NB_W); padd(con1, up.y, cf1 & NB_N); padd(con1, dn.y, cf1 & NB_S);
                 if (LAT == LAT_TRIANGULAR) {
-                    if (cf0 & NB_NW) con0 += c[PT_LD - 1]; if (cf0 & NB_NE) con0 += up.y;
-                    if (cf1 & NB_SW) con1 += dn.x;         if (cf1 & NB_SE) con1 += drt;
+                    padd(con0, c[PT_LD - 1], cf0 & NB_NW); padd(con0, up.y, cf0 & NB_NE);
+                    padd(con1, dn.x, cf1 & NB_SW);         padd(con1, drt, cf1 & NB_SE);
                 }
                 const int n0 = __popc(cf0), n1 = __popc(cf1), l0 = __popc(e0) - n0, l1 = __popc(e1) - n1;
+                const double2 t0 = dtab[(((n0 << 3) | l0) << 5) + lane], t1 = dtab[(((n1 << 3) | l1) << 5) + lane];
                 double2 q;
-                q.x = pt_diag(n0, l0, prm) * cc.x - (prm.gleak * all0 + dg * con0);
-                q.y = pt_diag(n1, l1, prm) * cc.y - (prm.gleak * all1 + dg * con1);
+                q.x = t0.x * cc.x - (prm.gleak * all0 + dg * con0);
+                q.y = t1.x * cc.y - (prm.gleak * all1 + dg * con1);
                 if (valid) {
                     const int64_t i = (int64_t)gy * g.m + gx;
                     if (MODE == 0) {
@@ -574,7 +581,7 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
                             x.x += ak * cc.x; x.y += ak * cc.y;
                             st2(vx + i, x);
                         }
-                        acc0 += r.x * r.x * dinv[(((n0 << 3) | l0) << 5) + lane] + r.y * r.y * dinv[(((n1 << 3) | l1) << 5) + lane];
+                        acc0 += r.x * r.x * t0.y + r.y * r.y * t1.y;
                         acc1 += r.x * r.x + r.y * r.y;
                     }
                 }
