@@ -35,6 +35,16 @@ SEED = 20240611
 ITERS_FILE = os.path.join(ROOT, "profiles", "bench_iters.json")
 
 
+def ncu_traffic_bytes(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json, written by tools/ncu_traffic.py)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return float(json.load(f)[kernel_key]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -303,7 +313,13 @@ def run_ours(args):
     merged = Stats()
     for G_, it_ in zip(stats["G"], stats["iters"]):
         merged.add(G=G_, iters=it_, spans=True)
-    merged.allreduce(dist, device="cuda")
+    if dist is not None:
+        # the library's communicator (NCCL, bootstrapped with an id broadcast by the host program) and its
+        # single reduction of the statistics block -- perc_comm_init_rank / perc_allreduce_stats
+        uid = torch.from_numpy(P.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
+        dist.broadcast(uid, 0)
+        L.comm_init_rank(world, rank, uid.cpu().numpy())
+        merged.allreduce_native(L)
     sd = merged.asdict()
     st = [sd["sum_G"], sd["sum_G2"], sd["count"], sd["iters"]]
 
@@ -328,7 +344,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": 8 * t + 4 * nb + 64, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "pcg_pipe_kernel<0> (persistent cp.async pipeline: p-update + 5-point SpMV + dot, q not stored)",
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": ncu_traffic_bytes("pcg_pipe_kernel<0>") if Lsz == 4096 else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
                          "avg_launch_ms": spmv_ms},
             "extra": {

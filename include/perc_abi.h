@@ -165,6 +165,14 @@ int32_t perc_stitch_host(const int32_t *nranks, const int32_t *rank, const int32
 int32_t perc_batch(const int64_t *h, const int32_t *kind, const int32_t *nreal, const int64_t *seed,
                    const int64_t *stream0, const int32_t *ks, const int32_t *kb, const int32_t *nbins,
                    int64_t *hist, int64_t *stats);
+/* the same batch with the Kirchhoff conductance of every realization's default spanning cluster (trial loop of
+ * Sq/bond_cond.f:123-498 at one fill; parameters as perc_conduct).  G(2,nreal) = Gtop, Gbot; iters(nreal) (-1: the
+ * realization does not span, G = 0).  Lattices of t <= 13312 sites are solved one CTA per realization in a single
+ * launch (the whole linbcg loop inside the kernel); larger ones realization by realization. */
+int32_t perc_batch_conduct(const int64_t *h, const int32_t *kind, const int32_t *nreal, const int64_t *seed,
+                           const int64_t *stream0, const int32_t *ks, const int32_t *kb, const double *Va,
+                           const double *g0, const double *gleak, const double *tol, const int32_t *itmax,
+                           const double *read_thresh, double *G, int32_t *iters, int64_t *stats);
 /* independent realizations sharded over GPUs (one process per GPU, no data-path collective): communicator
  * for the single reduction of the statistics at the end, and that reduction (integer sums are order
  * independent: the result is the same for any number of GPUs) */

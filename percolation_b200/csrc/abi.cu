@@ -645,6 +645,21 @@ int32_t perc_batch(const int64_t* h, const int32_t* kind, const int32_t* nreal, 
     return batch_run(c, *kind, *nreal, (unsigned long long)*seed, (unsigned long long)*stream0, *ks, *kb, *nbins, hist, stats);
 }
 
+int32_t perc_batch_conduct(const int64_t* h, const int32_t* kind, const int32_t* nreal, const int64_t* seed, const int64_t* stream0,
+                           const int32_t* ks, const int32_t* kb, const double* Va, const double* g0, const double* gleak,
+                           const double* tol, const int32_t* itmax, const double* read_thresh,
+                           double* G, int32_t* iters, int64_t* stats)
+{
+    GET_CTX(h);
+    if (!kind || !nreal || !seed || !stream0 || !ks || !kb || !Va || !g0 || !gleak || !tol || !itmax || !read_thresh || !G || !iters || !stats)
+        return PERC_E_ARG;
+    if (*kind < KIND_SITE || *kind > KIND_MIXED || *nreal < 0 || c->g.n < 3 || *Va == 0.0 || *itmax < 0) return PERC_E_ARG;
+    if ((*kind != KIND_BOND && (*ks < 0 || *ks > c->g.t)) || (*kind != KIND_SITE && (*kb < 0 || *kb > c->g.nb))) return PERC_E_ARG;
+    if (!pcg_small_fits(c->g)) { int rc = ensure_pcg(c); if (rc) return rc; }
+    return batch_conduct_run(c, *kind, *nreal, (unsigned long long)*seed, (unsigned long long)*stream0, *ks, *kb,
+                             *Va, *g0, *gleak, *tol, *itmax, *read_thresh, G, iters, stats);
+}
+
 // communicator for handles that shard independent realizations (mode 1): same bootstrap as the slab mode
 int32_t perc_comm_init_rank(const int64_t* h, const int32_t* nranks, const int32_t* rank, const uint8_t* id128)
 {

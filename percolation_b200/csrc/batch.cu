@@ -106,4 +106,67 @@ int batch_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsigned lon
     return rc;
 }
 
+// batch of realizations WITH the Kirchhoff conductance of each one's default spanning cluster (the trial
+// loop of Sq/bond_cond.f:123-498 at one fill).  Small lattices (t <= 13312): label every realization into
+// its slot of a conduct-byte batch, then ONE launch solves them all, one CTA each (pcg_small_kernel).
+// Larger lattices: realization by realization through the pipelined solver.
+// G(2, nreal) = Gtop, Gbot (0, 0 and iters = -1 for a realization without a spanning cluster).
+int batch_conduct_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsigned long long stream0, int64_t ks, int64_t kb,
+                      double Va, double g0, double gleak, double tol, int itmax, double read_thresh,
+                      double* G, int32_t* iters, int64_t* stats)
+{
+    if (c->nranks > 1) return -4;
+    cudaStream_t st = c->stream;
+    const Geom& g = c->g;
+    int rc = 0;
+    for (int k = 0; k < BATCH_NSTATS; ++k) stats[k] = 0;
+    if (!pcg_small_fits(g)) {
+        for (int i = 0; i < nreal; ++i) {
+            rc = occ_generate(c, seed, stream0 + (unsigned long long)i, kind != KIND_BOND ? ks : -1, kind != KIND_SITE ? kb : -1);
+            if (rc) return rc;
+            rc = ccl_run(c, kind);
+            if (rc) return rc;
+            stats[0] += 1;
+            G[2 * i] = G[2 * i + 1] = 0.0; iters[i] = -1;
+            if (c->h_span_ids.empty()) continue;
+            stats[3] += 1;
+            if (!c->vx) return -4;                        // the caller (abi) allocates the solver vectors first
+            double err = 0.0; int it = 0;
+            rc = pcg_solve(c, c->h_span_ids[0], Va, g0, gleak, tol, itmax, read_thresh, 0, &G[2 * i], &G[2 * i + 1], &it, &err);
+            if (rc) return rc;
+            iters[i] = it;
+        }
+        return 0;
+    }
+    uint8_t* d_cf = nullptr; double* d_G = nullptr; double* d_err = nullptr; int* d_it = nullptr; long long* d_stats = nullptr;
+    PERC_CUDA(cudaMalloc(&d_cf, (size_t)nreal * g.t));
+    PERC_CUDA(cudaMalloc(&d_G, sizeof(double) * 2 * nreal));
+    PERC_CUDA(cudaMalloc(&d_err, sizeof(double) * nreal));
+    PERC_CUDA(cudaMalloc(&d_it, sizeof(int) * nreal));
+    PERC_CUDA(cudaMalloc(&d_stats, sizeof(long long) * BATCH_NSTATS));
+    PERC_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(long long) * BATCH_NSTATS, st));
+    c->batch_thr = true;
+    for (int i = 0; i < nreal && rc == 0; ++i) {
+        rc = occ_generate_dev(c, seed, stream0 + (unsigned long long)i, kind != KIND_BOND ? ks : -1, kind != KIND_SITE ? kb : -1,
+                              (unsigned long long*)(d_stats + 6));
+        if (!rc) rc = ccl_launch(c, kind);
+        if (!rc) rc = pcg_small_stage(c, d_cf, i);
+        if (!rc) { batch_accum_kernel<<<1, 1, 0, st>>>(c->d_sum, nullptr, 0, d_stats); c->launches++; }
+    }
+    c->batch_thr = false;
+    c->labeled = false;
+    if (!rc) rc = pcg_small_solve(c, d_cf, nreal, Va, g0, gleak, tol, itmax, read_thresh, d_G, d_it, d_err);
+    if (!rc) {
+        long long h[BATCH_NSTATS];
+        PERC_CUDA(cudaMemcpyAsync(G, d_G, sizeof(double) * 2 * nreal, cudaMemcpyDeviceToHost, st));
+        PERC_CUDA(cudaMemcpyAsync(iters, d_it, sizeof(int) * nreal, cudaMemcpyDeviceToHost, st));
+        PERC_CUDA(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+        PERC_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < BATCH_NSTATS; ++k) stats[k] = h[k];
+        rc = (int)cudaGetLastError();
+    } else cudaStreamSynchronize(st);
+    cudaFree(d_cf); cudaFree(d_G); cudaFree(d_err); cudaFree(d_it); cudaFree(d_stats);
+    return rc;
+}
+
 }  // namespace perc

@@ -135,6 +135,13 @@ int slab_stitch(Ctx* c);
 int32_t slab_local_label_of(const Ctx* c, int64_t gid);
 int slab_export_labels(Ctx* c, int64_t* out);
 
+bool pcg_small_fits(const Geom& g);
+int pcg_small_stage(Ctx* c, uint8_t* cfbatch, int slot);
+int pcg_small_solve(Ctx* c, const uint8_t* cfbatch, int nreal, double Va, double g0, double gleak, double tol, int itmax,
+                    double read_thresh, double* d_G, int* d_iters, double* d_errs);
+int batch_conduct_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsigned long long stream0, int64_t ks, int64_t kb,
+                      double Va, double g0, double gleak, double tol, int itmax, double read_thresh,
+                      double* G, int32_t* iters, int64_t* stats);
 int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double tol, int itmax,
               double read_thresh, int keep_x, double* Gtop, double* Gbot, int* iter, double* err);
 

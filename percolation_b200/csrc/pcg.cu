@@ -23,6 +23,8 @@
 
 namespace perc {
 
+static unsigned nblk64(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
 constexpr int SP_TX = 64, SP_TY = 16, SP_THREADS = 256;      // SpMV tile
 constexpr int SP_HX = SP_TX + 2, SP_HY = SP_TY + 2;
 constexpr int UP_THREADS = 256;
@@ -43,10 +45,16 @@ __device__ __forceinline__ double diag_of(unsigned cf, unsigned ex, double g0, d
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 build_cfull_kernel(Geom g, int kind, int32_t cid, const uint8_t* __restrict__ mask, const int32_t* __restrict__ label,
-                   uint8_t* __restrict__ cfull)
+                   uint8_t* __restrict__ cfull, const Summary* __restrict__ dsum)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.t) return;
+    if (dsum) {
+        // batch mode: the default spanning cluster (smallest canonical id) is chosen on the device; 0 = none spans
+        cid = 0;
+        const int ns = dsum->nspan < MAX_SPAN ? dsum->nspan : MAX_SPAN;
+        for (int k = 0; k < ns; ++k) if (cid == 0 || dsum->span_ids[k] < cid) cid = dsum->span_ids[k];
+    }
     int x = (int)(i % g.m), y = (int)(i / g.m);
     if (y < g.own_lo || y >= g.own_hi) return;          // halo rows: copied from the neighbour rank
     unsigned ex = neighbour_bits(g, x, y);
@@ -673,6 +681,193 @@ pcg_readout_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, con
 }
 
 // ------------------------------------------------------------------------------------------
+// K7s: small lattices, one CTA per realization (BASELINE configs[0]: L = 100, 1000 realizations).  The whole
+// Jacobi-PCG solve of one realization runs inside one CTA: p and r live in shared memory, q = A p in
+// registers, the two reductions of an iteration are block reductions, nothing returns to the host or to
+// another kernel until the solve is done; a batch is one launch with grid = realizations.  Same
+// recurrences, matrix, stopping rule and read-out as above (Sq/bondc.f:465-595).
+// ------------------------------------------------------------------------------------------
+constexpr int SM_THREADS = 1024, SM_KMAX = 13;           // up to 13 sites per thread: t <= 13312 (L <= 115)
+
+__device__ __forceinline__ double sm_block_sum(double v, double* sh)
+{
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < SM_THREADS / 32; ++k) s += sh[k];    // every thread folds the same 32 partials in the same order
+    return s;
+}
+
+template <int LAT>
+__global__ void __launch_bounds__(SM_THREADS, 1)
+pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, double tol, int itmax,
+                 double* __restrict__ Gout, int* __restrict__ iters, double* __restrict__ errs)
+{
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int t = (int)g.t, m = g.m;
+    double* sp = reinterpret_cast<double*>(sm_raw);
+    double* sr = sp + t;
+    double* sx = sr + t;                                     // x on rows 1 and n-2 only (the read-out rows)
+    double* sh = sx + 2 * m;                                 // 32 partials
+    double2* tab = reinterpret_cast<double2*>(sh + 32);      // 64 x (d, 1/d)
+    uint8_t* scf = reinterpret_cast<uint8_t*>(tab + 64);
+    const int tid = threadIdx.x;
+    const uint8_t* cfg = cfbatch + (size_t)blockIdx.x * t;
+    if (tid < 64) {
+        const double d = (double)(tid >> 3) * prm.g0 + (double)(tid & 7) * prm.gleak;
+        tab[tid] = make_double2(d, d > 0.0 ? 1.0 / d : 0.0);
+    }
+    bool any = false;
+    for (int i = tid; i < t; i += SM_THREADS) { uint8_t c = cfg[i]; scf[i] = c; any |= c != 0; }
+    const int K = (t + SM_THREADS - 1) / SM_THREADS;
+    // no spanning cluster in this realization (the conduct mask is empty): report G = 0
+    if (!__syncthreads_or(any)) {
+        if (tid == 0) { Gout[2 * blockIdx.x] = 0.0; Gout[2 * blockIdx.x + 1] = 0.0; iters[blockIdx.x] = -1; errs[blockIdx.x] = 0.0; }
+        return;
+    }
+    // r = b (bonds from row n-2 into the top row at Va), p = 0; bnrm = |D^-1 b|, bknum = b.z
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int i = tid; i < t; i += SM_THREADS) {
+        const int x = i % m, y = i / m;
+        double b = 0.0;
+        if (y == g.n - 2 && y >= 1) {
+            const unsigned ex = neighbour_bits(g, x, y), cf = scf[i];
+            if (ex & NB_N)  b += ((cf & NB_N)  ? prm.g0 : prm.gleak) * prm.Va;
+            if (ex & NB_NW) b += ((cf & NB_NW) ? prm.g0 : prm.gleak) * prm.Va;
+            if (ex & NB_NE) b += ((cf & NB_NE) ? prm.g0 : prm.gleak) * prm.Va;
+            const int nc = __popc(cf);
+            const double z = b * tab[(nc << 3) | (__popc(ex) - nc)].y;
+            s0 += z * z; s1 += b * z; s2 += b * b;
+        }
+        sr[i] = b; sp[i] = 0.0;
+    }
+    const double bnrm = sqrt(sm_block_sum(s0, sh));
+    double bknum = sm_block_sum(s1, sh), bkden = 1.0, bk = 0.0, err = 0.0;
+    (void)sm_block_sum(s2, sh);
+    for (int i = tid; i < 2 * m; i += SM_THREADS) sx[i] = 0.0;
+    int iter = 0;
+    const double dg = prm.g0 - prm.gleak;
+    for (;;) {
+        // p = r / d + bk p  (interior rows)
+        for (int i = tid; i < t; i += SM_THREADS) {
+            const int y = i / m;
+            if (y < 1 || y >= g.n - 1) continue;
+            const int x = i - y * m;
+            const unsigned ex = neighbour_bits(g, x, y), cf = scf[i];
+            const int nc = __popc(cf);
+            sp[i] = sr[i] * tab[(nc << 3) | (__popc(ex) - nc)].y + bk * sp[i];
+        }
+        __syncthreads();
+        // q = A p, p.q
+        double q[SM_KMAX], dot = 0.0;
+#pragma unroll
+        for (int k = 0; k < SM_KMAX; ++k) {
+            q[k] = 0.0;
+            const int i = tid + k * SM_THREADS;
+            if (k >= K || i >= t) continue;
+            const int y = i / m;
+            if (y < 1 || y >= g.n - 1) continue;
+            const int x = i - y * m, row = i - x;
+            const unsigned ex = neighbour_bits(g, x, y), cf = scf[i];
+            const int xl = x > 0 ? x - 1 : m - 1, xr = x + 1 < m ? x + 1 : 0;
+            double all = 0.0, con = 0.0;
+#define NBR(bit, j) if (ex & bit) { const double v = sp[j]; all += v; if (cf & bit) con += v; }
+            NBR(NB_E, row + xr) NBR(NB_W, row + xl) NBR(NB_N, i + m) NBR(NB_S, i - m)
+            if (LAT == LAT_TRIANGULAR) { NBR(NB_NW, row + m + xl) NBR(NB_NE, row + m + xr) NBR(NB_SW, row - m + xl) NBR(NB_SE, row - m + xr) }
+#undef NBR
+            const int nc = __popc(cf);
+            const double pc = sp[i];
+            q[k] = tab[(nc << 3) | (__popc(ex) - nc)].x * pc - (prm.gleak * all + dg * con);
+            dot += pc * q[k];
+        }
+        const double akden = sm_block_sum(dot, sh);
+        const double ak = bknum / akden;
+        // x += ak p (read-out rows), r -= ak q, r.z and r.r
+        double rz = 0.0, rr = 0.0;
+#pragma unroll
+        for (int k = 0; k < SM_KMAX; ++k) {
+            const int i = tid + k * SM_THREADS;
+            if (k >= K || i >= t) continue;
+            const int y = i / m;
+            if (y < 1 || y >= g.n - 1) continue;
+            const int x = i - y * m;
+            const unsigned ex = neighbour_bits(g, x, y), cf = scf[i];
+            const int nc = __popc(cf);
+            const double r = sr[i] - ak * q[k];
+            sr[i] = r;
+            if (y == 1) sx[x] += ak * sp[i];
+            if (y == g.n - 2) sx[m + x] += ak * sp[i];         // (n = 3: row 1 is both; the read-out uses sx[x])
+            rz += r * r * tab[(nc << 3) | (__popc(ex) - nc)].y;
+            rr += r * r;
+        }
+        const double fa = sm_block_sum(rz, sh), fc = sm_block_sum(rr, sh);
+        ++iter;
+        err = sqrt(fc) / bnrm;
+        bkden = bknum; bknum = fa; bk = fa / bkden;
+        if (!(err > tol) || iter > itmax) break;             // loop guard iter <= itmax (:780)
+    }
+    // read-out (Sq/bondc.f:554-592)
+    __syncthreads();
+    double stop = 0.0, sbot = 0.0;
+    for (int x = tid; x < m; x += SM_THREADS) {
+        for (int e = 0; e < 2; ++e) {
+            const int y = e == 0 ? 0 : g.n - 1;
+            const int i = y * m + x, row = i - x;
+            const unsigned ex = neighbour_bits(g, x, y), cf = scf[i];
+            const double vi = e == 0 ? 0.0 : prm.Va;
+            double acc = diag_of(cf, ex, prm.g0, prm.gleak) * vi;
+            const int xl = x > 0 ? x - 1 : m - 1, xr = x + 1 < m ? x + 1 : 0;
+#define VAL(j) ((j) / m == 0 ? 0.0 : ((j) / m == g.n - 1 ? prm.Va : ((j) / m == 1 ? sx[(j) - m] : sx[m + (j) - (g.n - 2) * m])))
+#define NB(bit, j) if (ex & bit) { double w = (cf & bit) ? prm.g0 : prm.gleak; if (fabs(w) >= prm.read_thresh) acc -= w * VAL(j); }
+            NB(NB_E, row + xr) NB(NB_W, row + xl) NB(NB_N, i + m) NB(NB_S, i - m)
+            NB(NB_NW, row + m + xl) NB(NB_NE, row + m + xr) NB(NB_SW, row - m + xl) NB(NB_SE, row - m + xr)
+#undef NB
+#undef VAL
+            if (e == 0) sbot += acc; else stop += acc;
+        }
+    }
+    const double Itop = sm_block_sum(stop, sh), Ibot = sm_block_sum(sbot, sh);
+    if (tid == 0) {
+        Gout[2 * blockIdx.x] = Itop / prm.Va; Gout[2 * blockIdx.x + 1] = fabs(Ibot) / prm.Va;
+        iters[blockIdx.x] = iter; errs[blockIdx.x] = err;
+    }
+}
+
+static size_t small_smem_bytes(const Geom& g) { return sizeof(double) * (2 * (size_t)g.t + 2 * (size_t)g.m + 32) + sizeof(double2) * 64 + (size_t)g.t + 16; }
+
+bool pcg_small_fits(const Geom& g) { return g.t <= (int64_t)SM_KMAX * SM_THREADS && small_smem_bytes(g) <= 227 * 1024 && g.n >= 3; }
+
+// conduct byte map of the realization just labeled (default spanning cluster chosen on the device) -> slot of a batch
+int pcg_small_stage(Ctx* c, uint8_t* cfbatch, int slot)
+{
+    const Geom& g = c->g;
+    build_cfull_kernel<<<nblk64(g.t), 256, 0, c->stream>>>(g, c->kind, 0, c->mask, c->label, cfbatch + (size_t)slot * g.t, c->d_sum);
+    c->launches++;
+    return (int)cudaGetLastError();
+}
+
+int pcg_small_solve(Ctx* c, const uint8_t* cfbatch, int nreal, double Va, double g0, double gleak, double tol, int itmax,
+                    double read_thresh, double* d_G, int* d_iters, double* d_errs)
+{
+    const Geom& g = c->g;
+    PcgParams prm{g0, gleak, Va, read_thresh};
+    const size_t smem = small_smem_bytes(g);
+    if (g.lattice == LAT_SQUARE) {
+        PERC_CUDA(cudaFuncSetAttribute(pcg_small_kernel<LAT_SQUARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pcg_small_kernel<LAT_SQUARE><<<nreal, SM_THREADS, smem, c->stream>>>(g, prm, cfbatch, tol, itmax, d_G, d_iters, d_errs);
+    } else {
+        PERC_CUDA(cudaFuncSetAttribute(pcg_small_kernel<LAT_TRIANGULAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pcg_small_kernel<LAT_TRIANGULAR><<<nreal, SM_THREADS, smem, c->stream>>>(g, prm, cfbatch, tol, itmax, d_G, d_iters, d_errs);
+    }
+    c->launches++;
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------
 static unsigned nblk(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
@@ -744,7 +939,7 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     }
     PERC_CUDA(cudaMemsetAsync(c->d_pcg, 0, sizeof(PcgState), s));
     PERC_CUDA(cudaEventRecord(c->ev[6], s));
-    build_cfull_kernel<<<nblk(g.t), 256, 0, s>>>(g, c->kind, cluster_id, c->mask, c->label, c->cfull);
+    build_cfull_kernel<<<nblk(g.t), 256, 0, s>>>(g, c->kind, cluster_id, c->mask, c->label, c->cfull, nullptr);
     if (dist) { rc = slab_halo_exchange(c, c->cfull, 1); if (rc) return rc; }           // conduct bytes of the halo rows
     pcg_init_kernel<<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, c->vp, c->vq, c->partial, c->d_pcg, tol, itmax, dist);
     c->launches += 2;

@@ -30,7 +30,7 @@ SYMBOLS = [
     "perc_conduct", "perc_conduct_g", "perc_get_voltage", "perc_launch_count", "perc_phase_ms", "perc_stream",
     "perc_create_slab", "perc_comm_unique_id", "perc_comm_init", "perc_slab_rows", "perc_generate_i8",
     "perc_summary_i8", "perc_span_i8", "perc_get_site_labels_i8", "perc_stitch_host",
-    "perc_batch", "perc_comm_init_rank", "perc_allreduce_stats",
+    "perc_batch", "perc_batch_conduct", "perc_comm_init_rank", "perc_allreduce_stats",
 ]
 
 
@@ -244,6 +244,18 @@ class Lattice:
         self._call("perc_batch", _i32(kind), _i32(nreal), _i64(seed), _i64(stream0), _i32(ks), _i32(kb), _i32(nbins),
                    _ptr(hist, C.c_int64), _ptr(stats, C.c_int64))
         return hist[:nbins].copy(), dict(zip(self.BATCH_STATS, (int(v) for v in stats)))
+
+    def batch_conduct(self, kind, nreal, seed, stream0=0, ks=0, kb=0, Va=1.0, g0=1.0, gleak=1e-12, tol=1e-8, itmax=2500,
+                      read_thresh=1e-10):
+        """nreal realizations: labeling + Kirchhoff conductance of each default spanning cluster; returns
+        (G[nreal, 2] = Gtop, Gbot; iters[nreal] (-1: no spanning cluster); stats)"""
+        G = np.zeros(2 * nreal, np.float64)
+        iters = np.zeros(nreal, np.int32)
+        stats = np.zeros(16, np.int64)
+        self._call("perc_batch_conduct", _i32(kind), _i32(nreal), _i64(seed), _i64(stream0), _i32(ks), _i32(kb), _f64(Va),
+                   _f64(g0), _f64(gleak), _f64(tol), _i32(itmax), _f64(read_thresh), _ptr(G, C.c_double),
+                   _ptr(iters, C.c_int32), _ptr(stats, C.c_int64))
+        return G.reshape(nreal, 2), iters, dict(zip(self.BATCH_STATS, (int(v) for v in stats)))
 
     def comm_init_rank(self, nranks, rank, unique_id):
         uid = np.ascontiguousarray(unique_id, np.uint8)

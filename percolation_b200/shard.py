@@ -53,6 +53,15 @@ class Stats:
             self.hist = th.cpu().numpy()
         return self
 
+    def allreduce_native(self, lattice):
+        """the same single reduction through the library's own NCCL communicator
+        (perc_comm_init_rank + perc_allreduce_stats): what a Fortran driver calls"""
+        iv, dv = lattice.allreduce_stats(self.hist, self.v)
+        self.v = dv
+        if self.hist.size:
+            self.hist = iv
+        return self
+
     def asdict(self):
         d = dict(zip(self.FIELDS, self.v.tolist()))
         n = max(d["count"], 1)

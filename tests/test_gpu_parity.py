@@ -411,3 +411,33 @@ def test_batch_equals_realization_loop(P, lat, kind, m, n, pbc, ps, pb):
         L.generate(seed, stream0, ks if kind != 2 else -1, kb if kind != 1 else -1)
         L.label(kind)
         assert L.summary()["ncl"] > 0
+
+
+@pytest.mark.parametrize("lat,kind,m,n,pbc,ps,pb", [(1, 1, 100, 100, 0, 0.62, 0.0), (2, 2, 64, 48, 1, 0.0, 0.40),
+                                                   (1, 3, 96, 60, 0, 0.85, 0.68), (1, 2, 144, 128, 0, 0.0, 0.53)])
+def test_batch_conduct_equals_realization_loop(P, lat, kind, m, n, pbc, ps, pb):
+    """perc_batch_conduct (small lattices: one CTA per realization, the whole solve in one launch; the last
+    case is too large for that and goes realization by realization) == perc_generate + perc_label +
+    perc_conduct_g one realization at a time, both converged to 1e-13"""
+    nreal, seed, stream0 = 6, 626504, 3
+    with P.Lattice(lat, m, n, pbc) as L:
+        ks, kb = int(ps * L.t), int(pb * L.nb)
+        want, spans = [], 0
+        for i in range(nreal):
+            L.generate(seed, stream0 + i, ks if kind != 2 else -1, kb if kind != 1 else -1)
+            L.label(kind)
+            if len(L.span()[0]):
+                r = L.conduct(0, tol=1e-13, itmax=200000, voltages=False)
+                want.append((r["Gtop"], r["Gbot"], r["iter"]))
+                spans += 1
+            else:
+                want.append((0.0, 0.0, -1))
+        G, iters, st = L.batch_conduct(kind, nreal, seed, stream0, ks, kb, tol=1e-13, itmax=200000)
+        assert st["realizations"] == nreal and st["spanning"] == spans and st["failed"] == 0
+        assert spans >= 1
+        for i, (gt, gb, it) in enumerate(want):
+            if it < 0:
+                assert iters[i] == -1 and G[i, 0] == 0.0 and G[i, 1] == 0.0
+            else:
+                assert abs(G[i, 0] - gt) <= 1e-9 * abs(gt) and abs(G[i, 1] - gb) <= 1e-9 * abs(gb), (i, G[i], gt, gb)
+                assert abs(int(iters[i]) - it) <= max(3, it // 50)
