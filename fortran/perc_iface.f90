@@ -185,6 +185,105 @@ module perc_iface
       integer(c_int32_t), intent(out) :: iter
     end function
 
+    ! the same solve for the p-sweep drivers (Sq/bond_cond.f:392-485 write only pb, Gbot, Gtop, avg):
+    ! identical Gtop / Gbot / iter / err, interior voltages not formed
+    integer(c_int32_t) function perc_conduct_g(h, cluster_id, Va, g0, gleak, tol, itmax, read_thresh, &
+                                               Gtop, Gbot, iter, err) bind(C, name="perc_conduct_g")
+      import :: c_int32_t, c_int64_t, c_double
+      integer(c_int64_t), intent(in) :: h
+      integer(c_int32_t), intent(in) :: cluster_id, itmax
+      real(c_double), intent(in) :: Va, g0, gleak, tol, read_thresh
+      real(c_double), intent(out) :: Gtop, Gbot, err
+      integer(c_int32_t), intent(out) :: iter
+    end function
+
+    ! ---- trial loops on the device (do ii = 1, numtrials: Sq/site_perc.f:87, Sq/bond_cond.f:123) ----
+    integer(c_int32_t) function perc_batch(h, kind, nreal, seed, stream0, ks, kb, nbins, hist, stats) &
+        bind(C, name="perc_batch")
+      import :: c_int32_t, c_int64_t
+      integer(c_int64_t), intent(in) :: h, seed, stream0
+      integer(c_int32_t), intent(in) :: kind, nreal, ks, kb, nbins
+      integer(c_int64_t), intent(out) :: hist(*), stats(16)
+    end function
+
+    integer(c_int32_t) function perc_batch_conduct(h, kind, nreal, seed, stream0, ks, kb, Va, g0, gleak, tol, itmax, &
+                                                   read_thresh, G, iters, stats) bind(C, name="perc_batch_conduct")
+      import :: c_int32_t, c_int64_t, c_double
+      integer(c_int64_t), intent(in) :: h, seed, stream0
+      integer(c_int32_t), intent(in) :: kind, nreal, ks, kb, itmax
+      real(c_double), intent(in) :: Va, g0, gleak, tol, read_thresh
+      real(c_double), intent(out) :: G(2, *)             ! Gtop, Gbot per realization
+      integer(c_int32_t), intent(out) :: iters(*)
+      integer(c_int64_t), intent(out) :: stats(16)
+    end function
+
+    ! ---- several GPUs: one process (MPI rank) per GPU ------------------------------------------------
+    ! NCCL bootstrap: rank 0 calls perc_comm_unique_id, MPI_Bcast the 128 bytes, every rank initialises
+    integer(c_int32_t) function perc_comm_unique_id(id128) bind(C, name="perc_comm_unique_id")
+      import :: c_int32_t, c_int8_t
+      integer(c_int8_t), intent(out) :: id128(128)
+    end function
+
+    ! mode 1: independent realizations per rank, one reduction of the statistics at the end
+    integer(c_int32_t) function perc_comm_init_rank(h, nranks, rank, id128) bind(C, name="perc_comm_init_rank")
+      import :: c_int32_t, c_int64_t, c_int8_t
+      integer(c_int64_t), intent(in) :: h
+      integer(c_int32_t), intent(in) :: nranks, rank
+      integer(c_int8_t), intent(in) :: id128(128)
+    end function
+
+    integer(c_int32_t) function perc_allreduce_stats(h, ni, ivals, nd, dvals) bind(C, name="perc_allreduce_stats")
+      import :: c_int32_t, c_int64_t, c_double
+      integer(c_int64_t), intent(in) :: h
+      integer(c_int32_t), intent(in) :: ni, nd
+      integer(c_int64_t), intent(inout) :: ivals(*)
+      real(c_double), intent(inout) :: dvals(*)
+    end function
+
+    ! mode 2: ONE lattice decomposed into row slabs (rank r holds rows n*r/nranks .. n*(r+1)/nranks - 1)
+    integer(c_int32_t) function perc_create_slab(h, lattice, m, n, pbc, device, nranks, rank) bind(C, name="perc_create_slab")
+      import :: c_int32_t, c_int64_t
+      integer(c_int64_t), intent(out) :: h
+      integer(c_int32_t), intent(in) :: lattice, m, n, pbc, device, nranks, rank
+    end function
+
+    integer(c_int32_t) function perc_comm_init(h, id128) bind(C, name="perc_comm_init")
+      import :: c_int32_t, c_int64_t, c_int8_t
+      integer(c_int64_t), intent(in) :: h
+      integer(c_int8_t), intent(in) :: id128(128)
+    end function
+
+    integer(c_int32_t) function perc_slab_rows(h, ya, yb) bind(C, name="perc_slab_rows")
+      import :: c_int32_t, c_int64_t
+      integer(c_int64_t), intent(in) :: h
+      integer(c_int32_t), intent(out) :: ya, yb
+    end function
+
+    integer(c_int32_t) function perc_generate_i8(h, seed, stream, ks, kb) bind(C, name="perc_generate_i8")
+      import :: c_int32_t, c_int64_t
+      integer(c_int64_t), intent(in) :: h, seed, stream, ks, kb
+    end function
+
+    integer(c_int32_t) function perc_summary_i8(h, ncl, maxcs, maxcn, nspan) bind(C, name="perc_summary_i8")
+      import :: c_int32_t, c_int64_t
+      integer(c_int64_t), intent(in) :: h
+      integer(c_int64_t), intent(out) :: ncl, maxcs, maxcn, nspan
+    end function
+
+    integer(c_int32_t) function perc_span_i8(h, max_ids, nspan, ids, sizes) bind(C, name="perc_span_i8")
+      import :: c_int32_t, c_int64_t
+      integer(c_int64_t), intent(in) :: h
+      integer(c_int32_t), intent(in) :: max_ids
+      integer(c_int32_t), intent(out) :: nspan
+      integer(c_int64_t), intent(out) :: ids(*), sizes(*)
+    end function
+
+    integer(c_int32_t) function perc_get_site_labels_i8(h, s) bind(C, name="perc_get_site_labels_i8")
+      import :: c_int32_t, c_int64_t
+      integer(c_int64_t), intent(in) :: h
+      integer(c_int64_t), intent(out) :: s(*)            ! s((yb-ya)*m): lattice-wide labels of the owned rows
+    end function
+
     integer(c_int32_t) function perc_get_voltage(h, Vint) bind(C, name="perc_get_voltage")
       import :: c_int32_t, c_int64_t, c_double
       integer(c_int64_t), intent(in) :: h

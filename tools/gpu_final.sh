@@ -1,0 +1,13 @@
+#!/bin/bash
+# round-end evidence on one B200: GPU tests, smoke, full bench (both arms), launch list, full ncu captures
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -8 > gpurun_out/pytest_gpu.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+timeout 300 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+timeout 300 python tools/ccl_bench.py > gpurun_out/ccl_bench.log 2>&1
+timeout 300 python tools/batch_bench.py > gpurun_out/batch_bench.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 0 --itmax 300 --no-cpu-baseline --e2e-steps 0 > gpurun_out/ncu_launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'pcg_pipe' -s 100 -c 2 -o gpurun_out/prof_pcg_final -f python bench.py --steps 1 --warmup 0 --itmax 300 --no-cpu-baseline --e2e-steps 0 > gpurun_out/ncu_pcg_final.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'ccl_|build_mask' -s 8 -c 6 -o gpurun_out/prof_ccl_final -f python tools/ccl_bench.py quick > gpurun_out/ncu_ccl_final.log 2>&1
+cat gpurun_out/pytest_gpu.log gpurun_out/smoke.log; cut -c1-600 gpurun_out/bench.json; cut -c1-400 gpurun_out/bench_ref.json; cat gpurun_out/ccl_bench.log
