@@ -382,6 +382,9 @@ PERC_HD void tile_phase3(TileSmem& s, const Geom& g, int x0, int y0, int tid, Ti
         // read-only find: a path-halving store of another thread could overwrite the root written here
         const int root = tile_find_ro(s.lab, base + a);
         s.lab[base + a] = root;
+        // spread the root over the other sites of the run: their entries of s.lab are no union-find nodes
+        // (no find ever reads them), they stage the per-site root for the coalesced label output
+        for (uint32_t sg = seg & ~(1u << a); sg; sg &= sg - 1) s.lab[base + lobit(sg)] = root;
         if (root == base + a) rootbits |= 1u << a;
         int wgt;
         if (!owned) wgt = 0;
@@ -408,25 +411,12 @@ PERC_HD int32_t tile_global_label(const Geom& g, int x0, int y0, int node)
     return (y0 + node / CT_TW) * g.m + x0 + (node % CT_TW) + 1;       // t < 2^31 (check_geom)
 }
 
-// Every thread spreads the roots of its nodes over the sites of their runs (inside its own 32 entries
-// of s.lab, highest node first so no root is overwritten before it is read), and sorts its tile-local
-// roots into CLOSED clusters (no site on the border ring: final, counted here) and border roots (root list).
+// Every thread sorts its tile-local roots into CLOSED clusters (no site on the border ring: final, counted
+// here) and border roots (root list).  Runs after the barrier that completes the per-root sizes.
 PERC_HD void tile_phase4_fill(TileSmem& s, const Geom& g, int x0, int y0, int tid, TileRegs& r, int32_t* __restrict__ size)
 {
     const int w = tid % CT_NW, ly = tid / CT_NW;
     const int base = ly * CT_TW + (w << 5);
-    const uint32_t S = s.pS[ly + 1][w];
-    uint32_t upper = 0xFFFFFFFFu;
-    uint32_t t = s.pT[ly][w];
-    for (int it = warp_max_count(popc32(t)); it > 0; --it) {
-        warp_converge();
-        if (!t) continue;
-        const int a = hibit(t);
-        t &= ~(1u << a);
-        const int root = s.lab[base + a];
-        for (uint32_t seg = S & upper & ~((1u << a) - 1u) & ~(1u << a); seg; seg &= seg - 1) s.lab[base + lobit(seg)] = root;
-        upper = (1u << a) - 1u;
-    }
     int nloc = 0;
     unsigned nclosed = 0;
     unsigned long long best = 0;

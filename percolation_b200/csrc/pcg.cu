@@ -269,22 +269,12 @@ pcg_update_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, doub
 }
 
 // ------------------------------------------------------------------------------------------
-// helpers of the vectorised kernels (even m): 2 sites per thread with 128-bit accesses, (d, 1/d) from a
-// 64-entry shared table indexed by (#conducting, #leak) bonds instead of an fp64 division, and a
-// constant neighbourhood for tiles that do not touch the lattice boundary.
+// helpers of the pipelined kernels: 2 sites per thread with 128-bit accesses, and a constant neighbourhood
+// for tiles that do not touch the lattice boundary.
 // ------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
-
-__device__ __forceinline__ void fill_dtab(double2* tab, const PcgParams& prm)
-{
-    if (threadIdx.x < 64) {
-        int nc = threadIdx.x >> 3, nl = threadIdx.x & 7;
-        double d = (double)nc * prm.g0 + (double)nl * prm.gleak;
-        tab[threadIdx.x] = make_double2(d, d > 0.0 ? 1.0 / d : 0.0);
-    }
-}
 
 template <int LAT>
 __device__ __forceinline__ unsigned interior_ex(int gx)
@@ -296,8 +286,8 @@ __device__ __forceinline__ unsigned interior_ex(int gx)
 // ------------------------------------------------------------------------------------------
 // K6'/K7' (m % 16 == 0): persistent, double-buffered tile pipeline; the q = A p vector is never stored.
 // One CTA per SM walks over the 128 x 32 tiles of the lattice.  While the CTA computes tile k from
-// one shared-memory stage, the asynchronous copies (cp.async / LDGSTS, 16 bytes each, zero-filled
-// outside the lattice) of tile k+1 (+ one-site halo) are already in flight into the other stage, so
+// one shared-memory stage, the TMA tensor copies (cp.async.bulk.tensor.2d, completion on an mbarrier,
+// zero-filled outside the lattice) of tile k+1 (+ halo) are already in flight into the other stage, so
 // ~75 KB per SM are always outstanding and no load latency is exposed to the arithmetic.
 //   MODE 0: p_new = r / d + bk * p_old in place on tile + halo, q = A p_new, p.q      (K6)
 //   MODE 1: q = A p RECOMPUTED, r -= ak q, x += ak p, sums r.r/d and r.r              (K7)
@@ -326,22 +316,6 @@ __device__ __forceinline__ double pt_diag(int nc, int nl, const PcgParams& prm)
     const double two52 = 4503599627370496.0;
     const double dc = __hiloint2double(0x43300000, nc) - two52, dl = __hiloint2double(0x43300000, nl) - two52;
     return __fma_rn(dl, prm.gleak, __dmul_rn(dc, prm.g0));
-}
-
-__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid)
-{
-    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(valid ? 16 : 0) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* dst, const void* src, bool valid)
-{
-    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(valid ? 8 : 0) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* dst, const void* src, bool valid)
-{
-    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(valid ? 4 : 0) : "memory");
 }
 
 struct PtStage { double* sp; double* sr; uint8_t* scf; };
