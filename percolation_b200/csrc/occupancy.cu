@@ -36,7 +36,7 @@ struct PhiloxSrc {
     {
         if (!ts.enabled) return false;
         if (ts.all) return true;
-        unsigned long long k = elem_key(seed, stream, 0, (unsigned long long)i);
+        unsigned long long k = site_key(seed, stream, (unsigned long long)i);
         return k < ts.key || (k == ts.key && (unsigned long long)i <= ts.id);
     }
     __device__ __forceinline__ bool bond(int dir, int64_t i) const
@@ -44,10 +44,24 @@ struct PhiloxSrc {
         if (!tb.enabled) return false;
         if (tb.all) return true;
         unsigned long long id = (unsigned long long)dir * t + i;
-        unsigned long long k = elem_key(seed, stream, 1, id);
+        unsigned long long k = bond_key(seed, stream, dir, (unsigned long long)i);
         return k < tb.key || (k == tb.key && id <= tb.id);
     }
 };
+
+// the E/N (pair 0) or NW/NE (pair 1) bonds owned by site i from ONE Philox call: bits 1 (first) | 2 (second)
+__device__ __forceinline__ unsigned philox_bond_pair(const PhiloxSrc& p, int pair, int64_t i)
+{
+    if (!p.tb.enabled) return 0;
+    if (p.tb.all) return 3u;
+    unsigned long long A, B;
+    elem_key_pair(p.seed, p.stream, 1 + pair, (unsigned long long)i, A, B);
+    const unsigned long long idA = (unsigned long long)(2 * pair) * p.t + i, idB = (unsigned long long)(2 * pair + 1) * p.t + i;
+    unsigned r = 0;
+    if (A < p.tb.key || (A == p.tb.key && idA <= p.tb.id)) r |= 1u;
+    if (B < p.tb.key || (B == p.tb.key && idB <= p.tb.id)) r |= 2u;
+    return r;
+}
 
 // mixed source: sites and bonds may come from different inputs
 struct AnySrc {
@@ -99,9 +113,15 @@ __global__ void __launch_bounds__(256) build_mask_kernel(Geom g, int kind, AnySr
             bits = own;                                   // every lattice bond is present
             ns = site && owned;
         } else {
+            if (src.bond_src == SRC_PHILOX) {
+                // E and N from one Philox call, NW and NE (triangular up-type sites) from a second one
+                if (own & (MASK_E | MASK_N)) bits |= (philox_bond_pair(src.p, 0, ig) << 1) & own;
+                if (own & (MASK_NW | MASK_NE)) bits |= (philox_bond_pair(src.p, 1, ig) << 3) & own;
+            } else {
 #pragma unroll
-            for (int d = 0; d < 4; ++d)
-                if ((own >> (d + 1)) & 1u) if (src.bond(d, ig)) bits |= 2u << d;
+                for (int d = 0; d < 4; ++d)
+                    if ((own >> (d + 1)) & 1u) if (src.bond(d, ig)) bits |= 2u << d;
+            }
             nbd = owned ? __popc(bits) : 0;
             if (kind == KIND_MIXED) { site = src.site(ig); ns = site && owned; }
             else {
@@ -307,6 +327,38 @@ int occ_export(Ctx* c, uint8_t* socc, uint8_t* bocc)
 constexpr int SEL_BINS = 4096;
 constexpr int SEL_CAND = 8192;
 
+// The selection kernels walk over Philox CALLS (two keys each, philox.cuh) and visit every element of
+// the whole lattice once: visit(key, id).  type 0: sites; type 1: bonds (E/N call per site, NW/NE call
+// per up-type site of the triangular lattice).
+template <typename F>
+__device__ __forceinline__ void for_each_key(const Geom& g, int type, unsigned long long seed, unsigned long long stream, F visit)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long A, B;
+    if (type == 0) {
+        for (int64_t c = first; 2 * c < g.t; c += stride) {
+            elem_key_pair(seed, stream, 0, (unsigned long long)c, A, B);
+            visit(A, (unsigned long long)(2 * c));
+            if (2 * c + 1 < g.t) visit(B, (unsigned long long)(2 * c + 1));
+        }
+        return;
+    }
+    for (int64_t i = first; i < g.t; i += stride) {
+        const int x = (int)(i % g.m), y = (int)(i / g.m);
+        const unsigned own = owned_bond_bits(g, x, y);
+        if (own & (MASK_E | MASK_N)) {
+            elem_key_pair(seed, stream, 1, (unsigned long long)i, A, B);
+            if (own & MASK_E) visit(A, (unsigned long long)i);
+            if (own & MASK_N) visit(B, (unsigned long long)g.t + i);
+        }
+        if (own & (MASK_NW | MASK_NE)) {
+            elem_key_pair(seed, stream, 2, (unsigned long long)i, A, B);
+            if (own & MASK_NW) visit(A, 2ull * g.t + i);
+            if (own & MASK_NE) visit(B, 3ull * g.t + i);
+        }
+    }
+}
+
 // histogram of keys in [lo, lo + SEL_BINS << shift); hist[SEL_BINS] = keys below lo
 __global__ void __launch_bounds__(256) select_hist_kernel(Geom g, int type, unsigned long long seed,
                                                           unsigned long long stream, unsigned long long lo,
@@ -315,20 +367,11 @@ __global__ void __launch_bounds__(256) select_hist_kernel(Geom g, int type, unsi
     __shared__ unsigned sh[SEL_BINS + 1];
     for (int k = threadIdx.x; k <= SEL_BINS; k += blockDim.x) sh[k] = 0;
     __syncthreads();
-    int64_t nelem = type == 0 ? g.t : (int64_t)g.ndir * g.t;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += stride) {
-        if (type == 1) {
-            int dir = (int)(e / g.t);
-            int64_t i = e - (int64_t)dir * g.t;
-            if (!bond_exists(g, (int)(i % g.m), (int)(i / g.m), dir)) continue;
-        }
-        unsigned long long k = elem_key(seed, stream, type, (unsigned long long)e);
-        if (k < lo) { atomicAdd(&sh[SEL_BINS], 1u); continue; }
-        unsigned long long d = k - lo;
-        unsigned long long b = whole ? (d >> shift) : (d >> shift);
+    for_each_key(g, type, seed, stream, [&](unsigned long long k, unsigned long long) {
+        if (k < lo) { atomicAdd(&sh[SEL_BINS], 1u); return; }
+        unsigned long long b = (k - lo) >> shift;
         if (b < (unsigned long long)SEL_BINS) atomicAdd(&sh[(int)b], 1u);
-    }
+    });
     __syncthreads();
     for (int k = threadIdx.x; k <= SEL_BINS; k += blockDim.x)
         if (sh[k]) atomicAdd(&hist[k], (unsigned long long)sh[k]);
@@ -340,20 +383,12 @@ __global__ void __launch_bounds__(256) select_gather_kernel(Geom g, int type, un
                                                             unsigned long long width, unsigned long long* __restrict__ cand,
                                                             int cap, unsigned long long* __restrict__ count)
 {
-    int64_t nelem = type == 0 ? g.t : (int64_t)g.ndir * g.t;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += stride) {
-        if (type == 1) {
-            int dir = (int)(e / g.t);
-            int64_t i = e - (int64_t)dir * g.t;
-            if (!bond_exists(g, (int)(i % g.m), (int)(i / g.m), dir)) continue;
-        }
-        unsigned long long k = elem_key(seed, stream, type, (unsigned long long)e);
-        if (k < lo) continue;
-        if (width != 0 && k - lo >= width) continue;
+    for_each_key(g, type, seed, stream, [&](unsigned long long k, unsigned long long id) {
+        if (k < lo) return;
+        if (width != 0 && k - lo >= width) return;
         unsigned long long pos = atomicAdd(count, 1ull);
-        if (pos < (unsigned long long)cap) { cand[2 * pos] = k; cand[2 * pos + 1] = (unsigned long long)e; }
-    }
+        if (pos < (unsigned long long)cap) { cand[2 * pos] = k; cand[2 * pos + 1] = id; }
+    });
 }
 
 // find the k-th smallest (1-based) (key, id) among the N elements of `type`
@@ -480,19 +515,11 @@ __global__ void __launch_bounds__(256) select_gather_dev_kernel(Geom g, int type
 {
     if (!st->ok) return;
     const unsigned long long lo = st->lo, width = st->width;
-    int64_t nelem = type == 0 ? g.t : (int64_t)g.ndir * g.t;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nelem; e += stride) {
-        if (type == 1) {
-            int dir = (int)(e / g.t);
-            int64_t i = e - (int64_t)dir * g.t;
-            if (!bond_exists(g, (int)(i % g.m), (int)(i / g.m), dir)) continue;
-        }
-        unsigned long long k = elem_key(seed, stream, type, (unsigned long long)e);
-        if (k < lo || k - lo >= width) continue;
+    for_each_key(g, type, seed, stream, [&](unsigned long long k, unsigned long long id) {
+        if (k < lo || k - lo >= width) return;
         unsigned long long pos = atomicAdd(&st->count, 1ull);
-        if (pos < (unsigned long long)cap) { cand[2 * pos] = k; cand[2 * pos + 1] = (unsigned long long)e; }
-    }
+        if (pos < (unsigned long long)cap) { cand[2 * pos] = k; cand[2 * pos + 1] = id; }
+    });
 }
 
 // the (k - below)-th smallest (key, id) of the gathered bin, by rank counting

@@ -300,7 +300,7 @@ __device__ __forceinline__ unsigned interior_ex(int gx)
 // Partial sums are stored per TILE and folded in tile order, so the result does not depend on the
 // number of CTAs.
 // ------------------------------------------------------------------------------------------
-constexpr int PT_TX = 128, PT_TY = 32, PT_THREADS = 512, PT_ROWS = PT_TY + 2;
+constexpr int PT_TX = 128, PT_TY = 36, PT_THREADS = 768, PT_ROWS = PT_TY + 2;
 constexpr int PT_RPT = PT_TY / (PT_THREADS / 64);      // consecutive tile rows per thread in the stencil
 constexpr int PT_LD = PT_TX + 4;            // doubles per staged row: [1] left halo, [2..129] tile, [130] right halo
 constexpr int PT_CLD = PT_TX + 32;          // bytes per staged cfull row: [12..15] left halo word, [16..143] tile, [144..147] right halo word
@@ -663,18 +663,24 @@ pcg_readout_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, con
 // ------------------------------------------------------------------------------------------
 constexpr int SM_THREADS = 1024, SM_KMAX = 13;           // up to 13 sites per thread: t <= 13312 (L <= 115)
 
-__device__ __forceinline__ double sm_block_sum(double v, double* sh)
+// block sum of two values at once; every thread gets the result (fixed order: warp shuffles, then warp 0
+// folds the 32 per-warp partials with shuffles and broadcasts through shared memory)
+__device__ __forceinline__ double2 sm_block_sum2(double a, double b, double* sh)
 {
-    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    for (int o = 16; o; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();                                          // the previous result has been read by everyone
+    if (lane == 0) { sh[w] = a; sh[32 + w] = b; }
     __syncthreads();
-    if (lane == 0) sh[w] = v;
+    if (w == 0) {
+        a = sh[lane]; b = sh[32 + lane];
+        for (int o = 16; o; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
+        if (lane == 0) { sh[64] = a; sh[65] = b; }
+    }
     __syncthreads();
-    double s = 0.0;
-#pragma unroll
-    for (int k = 0; k < SM_THREADS / 32; ++k) s += sh[k];    // every thread folds the same 32 partials in the same order
-    return s;
+    return make_double2(sh[64], sh[65]);
 }
+__device__ __forceinline__ double sm_block_sum(double v, double* sh) { return sm_block_sum2(v, 0.0, sh).x; }
 
 template <int LAT>
 __global__ void __launch_bounds__(SM_THREADS, 1)
@@ -686,8 +692,8 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
     double* sp = reinterpret_cast<double*>(sm_raw);
     double* sr = sp + t;
     double* sx = sr + t;                                     // x on rows 1 and n-2 only (the read-out rows)
-    double* sh = sx + 2 * m;                                 // 32 partials
-    double2* tab = reinterpret_cast<double2*>(sh + 32);      // 64 x (d, 1/d)
+    double* sh = sx + 2 * m;                                 // 2 x 32 partials + 2 results
+    double2* tab = reinterpret_cast<double2*>(sh + 66);      // 64 x (d, 1/d)
     uint8_t* scf = reinterpret_cast<uint8_t*>(tab + 64);
     const int tid = threadIdx.x;
     const uint8_t* cfg = cfbatch + (size_t)blockIdx.x * t;
@@ -719,9 +725,10 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
         }
         sr[i] = b; sp[i] = 0.0;
     }
-    const double bnrm = sqrt(sm_block_sum(s0, sh));
-    double bknum = sm_block_sum(s1, sh), bkden = 1.0, bk = 0.0, err = 0.0;
-    (void)sm_block_sum(s2, sh);
+    const double2 init = sm_block_sum2(s0, s1, sh);
+    const double bnrm = sqrt(init.x);
+    double bknum = init.y, bkden = 1.0, bk = 0.0, err = 0.0;
+    (void)s2;
     for (int i = tid; i < 2 * m; i += SM_THREADS) sx[i] = 0.0;
     int iter = 0;
     const double dg = prm.g0 - prm.gleak;
@@ -778,7 +785,8 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
             rz += r * r * tab[(nc << 3) | (__popc(ex) - nc)].y;
             rr += r * r;
         }
-        const double fa = sm_block_sum(rz, sh), fc = sm_block_sum(rr, sh);
+        const double2 fs = sm_block_sum2(rz, rr, sh);
+        const double fa = fs.x, fc = fs.y;
         ++iter;
         err = sqrt(fc) / bnrm;
         bkden = bknum; bknum = fa; bk = fa / bkden;
@@ -804,14 +812,15 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
             if (e == 0) sbot += acc; else stop += acc;
         }
     }
-    const double Itop = sm_block_sum(stop, sh), Ibot = sm_block_sum(sbot, sh);
+    const double2 cur = sm_block_sum2(stop, sbot, sh);
+    const double Itop = cur.x, Ibot = cur.y;
     if (tid == 0) {
         Gout[2 * blockIdx.x] = Itop / prm.Va; Gout[2 * blockIdx.x + 1] = fabs(Ibot) / prm.Va;
         iters[blockIdx.x] = iter; errs[blockIdx.x] = err;
     }
 }
 
-static size_t small_smem_bytes(const Geom& g) { return sizeof(double) * (2 * (size_t)g.t + 2 * (size_t)g.m + 32) + sizeof(double2) * 64 + (size_t)g.t + 16; }
+static size_t small_smem_bytes(const Geom& g) { return sizeof(double) * (2 * (size_t)g.t + 2 * (size_t)g.m + 66) + sizeof(double2) * 64 + (size_t)g.t + 16; }
 
 bool pcg_small_fits(const Geom& g) { return g.t <= (int64_t)SM_KMAX * SM_THREADS && small_smem_bytes(g) <= 227 * 1024 && g.n >= 3; }
 

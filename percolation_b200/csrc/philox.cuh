@@ -25,15 +25,35 @@ PERC_HD void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
     }
 }
 
-// type 0 = site (id = site index), type 1 = bond (id = dir * t + owner site index)
-PERC_HD unsigned long long elem_key(unsigned long long seed, unsigned long long stream, int type,
-                                    unsigned long long id)
+// One Philox call yields 128 bits = TWO 64-bit element keys, A = (c0, c1) and B = (c2, c3):
+//   sites : call (type 0, counter = i >> 1)        -> site i takes half i & 1
+//   bonds : call (type 1, counter = owner site i)  -> E bond = A, N bond = B
+//           call (type 2, counter = owner site i)  -> NW bond = A, NE bond = B   (triangular, x even)
+// (half as many Philox evaluations per lattice site as one call per element).  Ties between equal keys
+// are broken by the element id: site i, bond dir * t + i.
+PERC_HD void elem_key_pair(unsigned long long seed, unsigned long long stream, int type, unsigned long long counter,
+                           unsigned long long& A, unsigned long long& B)
 {
-    uint32_t c[4] = {(uint32_t)id, (uint32_t)(id >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
+    uint32_t c[4] = {(uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
     uint32_t k0 = (uint32_t)seed;
-    uint32_t k1 = (uint32_t)(seed >> 32) ^ (type ? 0x5bd1e995u : 0u);
+    uint32_t k1 = (uint32_t)(seed >> 32) ^ (type == 0 ? 0u : type == 1 ? 0x5bd1e995u : 0x2545f491u);
     philox4x32_10(c, k0, k1);
-    return ((unsigned long long)c[0] << 32) | (unsigned long long)c[1];
+    A = ((unsigned long long)c[0] << 32) | (unsigned long long)c[1];
+    B = ((unsigned long long)c[2] << 32) | (unsigned long long)c[3];
+}
+
+PERC_HD unsigned long long site_key(unsigned long long seed, unsigned long long stream, unsigned long long i)
+{
+    unsigned long long A, B;
+    elem_key_pair(seed, stream, 0, i >> 1, A, B);
+    return (i & 1) ? B : A;
+}
+
+PERC_HD unsigned long long bond_key(unsigned long long seed, unsigned long long stream, int dir, unsigned long long i)
+{
+    unsigned long long A, B;
+    elem_key_pair(seed, stream, dir < 2 ? 1 : 2, i, A, B);
+    return (dir & 1) ? B : A;
 }
 
 }  // namespace perc

@@ -255,16 +255,16 @@ def test_first_span_matches_literal_fill(P, O):
 
 
 # ---- K1 generator -------------------------------------------------------------------------
-def philox_keys(seed, stream, typ, ids):
-    """numpy restatement of csrc/philox.cuh (Philox-4x32-10)"""
+def philox_pairs(seed, stream, typ, counters):
+    """numpy restatement of csrc/philox.cuh (Philox-4x32-10): the two 64-bit keys (A, B) of each call"""
     M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
-    ids = np.asarray(ids, np.uint64)
+    ids = np.asarray(counters, np.uint64)
     c0 = ids & np.uint64(0xffffffff)
     c1 = ids >> np.uint64(32)
     c2 = np.full_like(ids, np.uint64(stream & 0xffffffff))
     c3 = np.full_like(ids, np.uint64((stream >> 32) & 0xffffffff))
     k0 = np.uint64(seed & 0xffffffff)
-    k1 = np.uint64(((seed >> 32) & 0xffffffff) ^ (0x5bd1e995 if typ else 0))
+    k1 = np.uint64(((seed >> 32) & 0xffffffff) ^ (0, 0x5bd1e995, 0x2545f491)[typ])
     mask = np.uint64(0xffffffff)
     for _ in range(10):
         p0 = M0 * c0
@@ -276,13 +276,45 @@ def philox_keys(seed, stream, typ, ids):
         c0, c1, c2, c3 = n0, n1, n2, n3
         k0 = (k0 + np.uint64(0x9E3779B9)) & mask
         k1 = (k1 + np.uint64(0xBB67AE85)) & mask
-    return (c0 << np.uint64(32)) | c1
+    return (c0 << np.uint64(32)) | c1, (c2 << np.uint64(32)) | c3
+
+
+def site_keys(seed, stream, t):
+    """site i takes half i & 1 of call (type 0, counter i >> 1)"""
+    A, B = philox_pairs(seed, stream, 0, np.arange((t + 1) // 2))
+    return np.stack([A, B], 1).reshape(-1)[:t]
+
+
+def bond_keys_and_ids(seed, stream, lat, m, n, pbc, b1, b2):
+    """(key, tie-break id) of every bond in reference row order: E/N from call (type 1, owner), NW/NE from
+    call (type 2, owner); id = dir * t + owner"""
+    t = m * n
+    lo, hi = b1.astype(np.int64) - 1, b2.astype(np.int64) - 1
+    x1, y1, y2 = lo % m, lo // m, hi // m
+    d = hi - lo
+    dirn = np.full(len(lo), -1)
+    owner = lo.copy()
+    same = y1 == y2
+    dirn[same & (d == 1)] = 0
+    wrap = same & (d == m - 1) & (m > 2)                       # periodic E bond, owned by the row's last site
+    dirn[wrap] = 0
+    owner[wrap] = hi[wrap]
+    up = y2 == y1 + 1
+    dirn[up & (d == m)] = 1
+    if lat == 2:
+        dirn[up & (d == m + 1)] = 3
+        dirn[up & ((d == m - 1) | ((x1 == 0) & (d == 2 * m - 1)))] = 2
+    assert (dirn >= 0).all()
+    A1, B1 = philox_pairs(seed, stream, 1, owner)
+    A2, B2 = philox_pairs(seed, stream, 2, owner)
+    key = np.where(dirn == 0, A1, np.where(dirn == 1, B1, np.where(dirn == 2, A2, B2)))
+    return key, dirn * t + owner
 
 
 def test_philox_known_answer():
     # Random123 KAT: counter 0, key 0 -> 6627e8d5 e169c58d bc57ac4c 9b00dbd8
-    k = philox_keys(0, 0, 0, [0])[0]
-    assert int(k) == (0x6627e8d5 << 32) | 0xe169c58d
+    A, B = philox_pairs(0, 0, 0, [0])
+    assert int(A[0]) == (0x6627e8d5 << 32) | 0xe169c58d and int(B[0]) == (0xbc57ac4c << 32) | 0x9b00dbd8
 
 
 @pytest.mark.parametrize("lat,m,n,pbc", [(1, 50, 50, 0), (2, 64, 40, 1), (1, 257, 129, 1)])
@@ -296,11 +328,16 @@ def test_generator_exact_count_and_keys(P, lat, m, n, pbc):
             L.generate(seed, stream, ks, kb)
             socc, bocc = L.get_occupancy()
             assert int(socc.sum()) == ks and int(bocc.sum()) == kb
-            keys = philox_keys(seed, stream, 0, np.arange(t))
+            keys = site_keys(seed, stream, t)
             order = np.lexsort((np.arange(t), keys))
             want = np.zeros(t, np.uint8)
             want[order[:ks]] = 1
             assert (socc == want).all()
+            bkey, bid = bond_keys_and_ids(seed, stream, lat, m, n, pbc, b1, b2)
+            order = np.lexsort((bid, bkey))
+            want = np.zeros(nb, np.uint8)
+            want[order[:kb]] = 1
+            assert (bocc == want).all()
         # nesting: a larger fill count keeps every previously occupied element (sweep property)
         L.generate(seed, stream, int(0.5 * t), int(0.4 * nb))
         s1, bb1 = L.get_occupancy()

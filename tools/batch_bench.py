@@ -19,9 +19,11 @@ def run_conduct(name, lat, kind, Lsz, ps, pb, nreal, tol=1e-8, itmax=2500):
     with P.Lattice(lat, Lsz, Lsz, 0) as L:
         ks, kb = int(ps * L.t), int(pb * L.nb)
         L.batch_conduct(kind, 8, 1, 0, ks, kb, tol=tol, itmax=itmax)
-        t0 = time.perf_counter()
-        G, iters, st = L.batch_conduct(kind, nreal, 20240611, 0, ks, kb, tol=tol, itmax=itmax)
-        dt = time.perf_counter() - t0
+        dt = 1e9
+        for rep in range(3):                                     # best of 3 (the first call also pays allocations)
+            t0 = time.perf_counter()
+            G, iters, st = L.batch_conduct(kind, nreal, 20240611, 0, ks, kb, tol=tol, itmax=itmax)
+            dt = min(dt, time.perf_counter() - t0)
         sp = iters >= 0
         print(json.dumps({"config": name, "L": Lsz, "realizations": nreal, "seconds": dt, "realizations_per_s": nreal / dt,
                           "spanning_fraction": float(sp.mean()), "mean_G": float(G[sp, 0].mean()) if sp.any() else 0.0,
