@@ -116,6 +116,13 @@ int32_t perc_first_span(const int64_t *h, const int32_t *kind, const int32_t *wh
 int32_t perc_conduct(const int64_t *h, const int32_t *cluster_id, const double *Va, const double *g0,
                      const double *gleak, const double *tol, const int32_t *itmax, const double *read_thresh,
                      double *Gtop, double *Gbot, int32_t *iter, double *err);
+/* perc_conduct with the voltages of the handle's previous perc_conduct / perc_conduct_warm as the initial
+ * guess -- linbcg's own `x` is in/out (Sq/bondc.f:759-763, r = b - A x); the reference driver zeroes it before
+ * every sweep point (Sq/bond_cond.f:400-405), successive points of a p-sweep differ by 0.5 % of the bonds.
+ * Same converged answer (to tol); falls back to x = 0 when there is no previous solution. */
+int32_t perc_conduct_warm(const int64_t *h, const int32_t *cluster_id, const double *Va, const double *g0,
+                          const double *gleak, const double *tol, const int32_t *itmax, const double *read_thresh,
+                          double *Gtop, double *Gbot, int32_t *iter, double *err);
 /* same solve for the p-sweep drivers (Sq/bond_cond.f:392-485), which only write pb, Gbot, Gtop, avg
  * (:481-482): the iterate x is kept on rows 1 and n-2 only -- the rows the read-out G~.V (:576-592)
  * consumes -- so Gtop / Gbot / iter / err are bit-identical to perc_conduct while the interior

@@ -462,7 +462,7 @@ int32_t perc_first_span(const int64_t* h, const int32_t* kind, const int32_t* wh
 
 static int conduct_common(Ctx* c, const int32_t* cluster_id, const double* Va, const double* g0,
                           const double* gleak, const double* tol, const int32_t* itmax, const double* read_thresh,
-                          int keep_x, double* Gtop, double* Gbot, int32_t* iter, double* err)
+                          int keep_x, double* Gtop, double* Gbot, int32_t* iter, double* err, int warm = 0)
 {
     if (!cluster_id || !Va || !g0 || !gleak || !tol || !itmax || !read_thresh || !Gtop || !Gbot || !iter || !err)
         return PERC_E_ARG;
@@ -486,7 +486,7 @@ static int conduct_common(Ctx* c, const int32_t* cluster_id, const double* Va, c
     int rc = ensure_pcg(c);
     if (rc) return rc;
     int it = 0;
-    rc = pcg_solve(c, cid, *Va, *g0, *gleak, *tol, *itmax, *read_thresh, keep_x, Gtop, Gbot, &it, err);
+    rc = pcg_solve(c, cid, *Va, *g0, *gleak, *tol, *itmax, *read_thresh, keep_x, Gtop, Gbot, &it, err, warm);
     *iter = it;
     return rc;
 }
@@ -497,6 +497,17 @@ int32_t perc_conduct(const int64_t* h, const int32_t* cluster_id, const double* 
 {
     GET_CTX(h);
     return conduct_common(c, cluster_id, Va, g0, gleak, tol, itmax, read_thresh, 1, Gtop, Gbot, iter, err);
+}
+
+int32_t perc_conduct_warm(const int64_t* h, const int32_t* cluster_id, const double* Va, const double* g0,
+                          const double* gleak, const double* tol, const int32_t* itmax, const double* read_thresh,
+                          double* Gtop, double* Gbot, int32_t* iter, double* err)
+{
+    GET_CTX(h);
+    // the labeling between two sweep points invalidates `solved`; the voltages themselves are still there
+    const bool have = c->have_x && c->vx != nullptr;
+    if (have) c->solved = true;
+    return conduct_common(c, cluster_id, Va, g0, gleak, tol, itmax, read_thresh, 1, Gtop, Gbot, iter, err, have ? 1 : 0);
 }
 
 int32_t perc_conduct_g(const int64_t* h, const int32_t* cluster_id, const double* Va, const double* g0,

@@ -143,7 +143,7 @@ int batch_conduct_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsi
                       double Va, double g0, double gleak, double tol, int itmax, double read_thresh,
                       double* G, int32_t* iters, int64_t* stats);
 int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double tol, int itmax,
-              double read_thresh, int keep_x, double* Gtop, double* Gbot, int* iter, double* err);
+              double read_thresh, int keep_x, double* Gtop, double* Gbot, int* iter, double* err, int warm = 0);
 
 #define PERC_CUDA(call)                                              \
     do {                                                             \

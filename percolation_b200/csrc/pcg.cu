@@ -133,7 +133,7 @@ __device__ __forceinline__ double fold_partials(const double* partial, int cnt, 
 __global__ void __launch_bounds__(UP_THREADS)
 pcg_init_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double* __restrict__ vx,
                 double* __restrict__ vr, double* __restrict__ vp, double* __restrict__ vq,
-                double* __restrict__ partial, PcgState* __restrict__ st, double tol, int itmax, int dist)
+                double* __restrict__ partial, PcgState* __restrict__ st, double tol, int itmax, int dist, int warm)
 {
     __shared__ double sh[32];
     double s_b = 0.0, s_rz = 0.0, s_rr = 0.0;
@@ -149,9 +149,28 @@ pcg_init_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
             if (ex & NB_NE) b += ((cf & NB_NE) ? prm.g0 : prm.gleak) * prm.Va;
             double d = diag_of(cf, ex, prm.g0, prm.gleak);
             double z = b / d;
-            s_b += z * z; s_rz += b * z; s_rr += b * b;
+            s_b += z * z;
+            if (!warm) { s_rz += b * z; s_rr += b * b; }
         }
-        vx[i] = 0.0; vr[i] = b; vp[i] = 0.0;
+        double r = b;
+        if (warm) {
+            // linbcg with a non-zero initial guess (Sq/bondc.f:759-763: r = b - A x): x holds the previous
+            // solution (rows 0 / n-1 of x are 0, so Dirichlet neighbours drop out; their share is in b)
+            if (solve_row(g, y)) {
+                const unsigned ex = neighbour_bits(g, x, y), cf = cfull[i];
+                const int xl = x > 0 ? x - 1 : g.m - 1, xr = x + 1 < g.m ? x + 1 : 0;
+                const int64_t row = i - x;
+                const double d = diag_of(cf, ex, prm.g0, prm.gleak);
+                double acc = d * vx[i];
+#define NB(bit, j) if (ex & bit) acc -= ((cf & bit) ? prm.g0 : prm.gleak) * vx[j];
+                NB(NB_E, row + xr) NB(NB_W, row + xl) NB(NB_N, i + g.m) NB(NB_S, i - g.m)
+                NB(NB_NW, row + g.m + xl) NB(NB_NE, row + g.m + xr) NB(NB_SW, row - g.m + xl) NB(NB_SE, row - g.m + xr)
+#undef NB
+                r = b - acc;
+                s_rz += r * (r / d); s_rr += r * r;
+            }
+        } else vx[i] = 0.0;
+        vr[i] = r; vp[i] = 0.0;
         if (vq) vq[i] = 0.0;          // only the odd-m fallback stores q
     }
     double a = block_sum(s_b, sh), c = block_sum(s_rz, sh), e = block_sum(s_rr, sh);
@@ -882,9 +901,12 @@ static int make_tensor_map(CUtensorMap* map, void* base, int elem_bytes, int col
 }
 
 int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double tol, int itmax,
-              double read_thresh, int keep_x, double* Gtop, double* Gbot, int* iter, double* err)
+              double read_thresh, int keep_x, double* Gtop, double* Gbot, int* iter, double* err, int warm)
 {
     const Geom& g = c->g;
+    // warm start: the voltages of the handle's previous solve are the initial guess (they must exist)
+    if (warm && !(c->solved && c->have_x && c->nranks == 1)) warm = 0;
+    if (warm) keep_x = 1;
     cudaStream_t s = c->stream;
     PcgParams prm{g0, gleak, Va, read_thresh};
     dim3 sgrid((g.m + SP_TX - 1) / SP_TX, (g.n + SP_TY - 1) / SP_TY);
@@ -924,7 +946,7 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     PERC_CUDA(cudaEventRecord(c->ev[6], s));
     build_cfull_kernel<<<nblk(g.t), 256, 0, s>>>(g, c->kind, cluster_id, c->mask, c->label, c->cfull, nullptr);
     if (dist) { rc = slab_halo_exchange(c, c->cfull, 1); if (rc) return rc; }           // conduct bytes of the halo rows
-    pcg_init_kernel<<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, c->vp, c->vq, c->partial, c->d_pcg, tol, itmax, dist);
+    pcg_init_kernel<<<ugrid, UP_THREADS, 0, s>>>(g, prm, c->cfull, c->vx, c->vr, c->vp, c->vq, c->partial, c->d_pcg, tol, itmax, dist, warm);
     c->launches += 2;
     PERC_CUDA(cudaMemsetAsync(c->vp2, 0, sizeof(double) * g.t, s));     // rows the kernels never write (Dirichlet) must read 0
     if (dist) {

@@ -27,7 +27,7 @@ SYMBOLS = [
     "perc_generate", "perc_get_occupancy",
     "perc_label", "perc_summary", "perc_get_site_labels", "perc_get_bond_labels", "perc_get_sizes",
     "perc_span", "perc_hist", "perc_site", "perc_bond", "perc_sitebond", "perc_first_span",
-    "perc_conduct", "perc_conduct_g", "perc_get_voltage", "perc_launch_count", "perc_phase_ms", "perc_stream",
+    "perc_conduct", "perc_conduct_warm", "perc_conduct_g", "perc_get_voltage", "perc_launch_count", "perc_phase_ms", "perc_stream",
     "perc_create_slab", "perc_comm_unique_id", "perc_comm_init", "perc_slab_rows", "perc_generate_i8",
     "perc_summary_i8", "perc_span_i8", "perc_get_site_labels_i8", "perc_stitch_host",
     "perc_batch", "perc_batch_conduct", "perc_comm_init_rank", "perc_allreduce_stats",
@@ -270,10 +270,11 @@ class Lattice:
 
     # ---- conductance
     def conduct(self, cluster_id=0, Va=1.0, g0=1.0, gleak=1e-12, tol=1e-8, itmax=2500, read_thresh=1e-10,
-                voltages=True):
-        """Sq/bondc.f:465-595.  voltages=False -> perc_conduct_g (same G, interior voltages not formed)"""
+                voltages=True, warm=False):
+        """Sq/bondc.f:465-595.  voltages=False -> perc_conduct_g (same G, interior voltages not formed);
+        warm=True -> perc_conduct_warm (initial guess = the handle's previous voltages)"""
         Gtop, Gbot, err, it = C.c_double(0), C.c_double(0), C.c_double(0), C.c_int32(0)
-        self._call("perc_conduct" if voltages else "perc_conduct_g", _i32(cluster_id), _f64(Va), _f64(g0), _f64(gleak), _f64(tol), _i32(itmax),
+        self._call("perc_conduct_warm" if warm else "perc_conduct" if voltages else "perc_conduct_g", _i32(cluster_id), _f64(Va), _f64(g0), _f64(gleak), _f64(tol), _i32(itmax),
                    _f64(read_thresh), C.byref(Gtop), C.byref(Gbot), C.byref(it), C.byref(err))
         return dict(Gtop=Gtop.value, Gbot=Gbot.value, iter=it.value, err=err.value)
 

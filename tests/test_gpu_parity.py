@@ -478,3 +478,28 @@ def test_batch_conduct_equals_realization_loop(P, lat, kind, m, n, pbc, ps, pb):
             else:
                 assert abs(G[i, 0] - gt) <= 1e-9 * abs(gt) and abs(G[i, 1] - gb) <= 1e-9 * abs(gb), (i, G[i], gt, gb)
                 assert abs(int(iters[i]) - it) <= max(3, it // 50)
+
+
+@pytest.mark.parametrize("lat,kind,m,n", [(1, 2, 64, 48), (1, 3, 144, 80), (2, 2, 50, 40)])
+def test_warm_start_sweep(P, lat, kind, m, n):
+    """p-sweep on one bond order (Sq/bond_cond.f:208-485): perc_conduct_warm starts from the previous point's
+    voltages and must reach the same converged conductance as a cold start"""
+    with P.Lattice(lat, m, n, 0) as L:
+        ks = int(0.85 * L.t) if kind == 3 else -1
+        p0 = 0.54 if lat == 1 and kind == 2 else 0.70 if kind == 3 else 0.38
+        fills = [int((p0 + 0.005 * j) * L.nb) for j in range(5)]
+        L.generate(31337, 0, ks, fills[0])
+        cold, warm = [], []
+        for kb in fills:
+            L.set_fill(kb=kb)
+            L.label(kind)
+            assert len(L.span()[0]) >= 1
+            cold.append(L.conduct(0, tol=1e-13, itmax=400000))
+        for j, kb in enumerate(fills):
+            L.set_fill(kb=kb)
+            L.label(kind)
+            warm.append(L.conduct(0, tol=1e-13, itmax=400000, warm=j > 0))
+        for c, w in zip(cold, warm):
+            assert abs(c["Gtop"] - w["Gtop"]) <= 1e-9 * abs(c["Gtop"]) and abs(c["Gbot"] - w["Gbot"]) <= 1e-9 * abs(c["Gbot"])
+            assert w["err"] <= 1e-13
+        assert sum(w["iter"] for w in warm[1:]) < sum(c["iter"] for c in cold[1:])
