@@ -522,7 +522,7 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
             __syncthreads();
         }
 
-        // ---- stencil: q = A p from shared memory; MODE 0: dot(p, q); MODE 1: r -= ak q, x += ak p.
+        // ---- MODE 0: p.Ap as bond energies; MODE 1: q = A p from shared memory, r -= ak q, x += ak p.
         // A thread owns 2 columns x PT_RPT consecutive rows and slides a 3-row window up the tile ------
         const int gx = x0 + 2 * tx;
         double acc0 = 0.0, acc1 = 0.0;
@@ -539,6 +539,42 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
                 const bool valid = pt_solve_row<DIST>(g, gy) && gx < g.m;
                 const unsigned c01 = *reinterpret_cast<const unsigned short*>(&s.scf[(ly + 1) * PT_CLD + 16 + 2 * tx]);
                 const unsigned cf0 = c01 & 0xffu, cf1 = c01 >> 8;
+                if (MODE == 0) {
+                    // p.Ap as the energy of the bonds OWNED by this pair of sites, sum over E, N (NW, NE) of
+                    // w (p_i - p_j)^2: half the neighbours of the stencil form, no diagonal lookup, and >= 0
+                    // by construction.  Dirichlet rows hold p = 0 in shared memory, so a bond into them
+                    // comes out as w p_i^2; bonds of Dirichlet-row owners (row 0 -> row 1) are included.
+                    const int G = (DIST ? g.y0 : 0) + gy, NG = DIST ? g.ng : g.n;
+                    const bool owner = (DIST ? (gy >= g.own_lo && gy < g.own_hi) : (gy >= 0 && gy < g.n)) && gx < g.m;
+                    if (owner) {
+                        const double dE0 = cc.x - cc.y, dE1 = cc.y - rt, dN0 = cc.x - up.x, dN1 = cc.y - up.y;
+                        double all = 0.0, con = 0.0;
+                        if (interior) {
+                            all = (dE0 * dE0 + dE1 * dE1) + (dN0 * dN0 + dN1 * dN1);
+                            padd(con, dE0 * dE0, cf0 & NB_E); padd(con, dE1 * dE1, cf1 & NB_E);
+                            padd(con, dN0 * dN0, cf0 & NB_N); padd(con, dN1 * dN1, cf1 & NB_N);
+                            if (LAT == LAT_TRIANGULAR) {
+                                const double dNW = cc.x - c[PT_LD - 1], dNE = cc.x - up.y;
+                                all += dNW * dNW + dNE * dNE;
+                                padd(con, dNW * dNW, cf0 & NB_NW); padd(con, dNE * dNE, cf0 & NB_NE);
+                            }
+                        } else {
+                            const unsigned e0 = neighbour_bits(g, gx, gy), e1 = neighbour_bits(g, gx + 1, gy);
+                            const bool rowE = G >= 1 && G <= NG - 2;      // an E bond joins two sites of one row
+                            if (rowE && (e0 & NB_E)) { all += dE0 * dE0; padd(con, dE0 * dE0, cf0 & NB_E); }
+                            if (rowE && (e1 & NB_E)) { all += dE1 * dE1; padd(con, dE1 * dE1, cf1 & NB_E); }
+                            if (e0 & NB_N) { all += dN0 * dN0; padd(con, dN0 * dN0, cf0 & NB_N); }
+                            if (e1 & NB_N) { all += dN1 * dN1; padd(con, dN1 * dN1, cf1 & NB_N); }
+                            if (LAT == LAT_TRIANGULAR) {
+                                const double dNW = cc.x - c[PT_LD - 1], dNE = cc.x - up.y;
+                                if (e0 & NB_NW) { all += dNW * dNW; padd(con, dNW * dNW, cf0 & NB_NW); }
+                                if (e0 & NB_NE) { all += dNE * dNE; padd(con, dNE * dNE, cf0 & NB_NE); }
+                            }
+                        }
+                        acc0 += prm.gleak * all + dg * con;
+                    }
+                    if (valid) st2(vp_out + (int64_t)gy * g.m + gx, cc);
+                } else {
                 unsigned e0, e1;
                 double all0, all1;
                 if (interior) {
@@ -570,21 +606,17 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
                 q.y = t1.x * cc.y - (prm.gleak * all1 + dg * con1);
                 if (valid) {
                     const int64_t i = (int64_t)gy * g.m + gx;
-                    if (MODE == 0) {
-                        st2(vp_out + i, cc);
-                        acc0 += cc.x * q.x + cc.y * q.y;
-                    } else {
-                        double2 r = ld2(&s.sr[(ly + 1) * PT_LD + 2 + 2 * tx]);
-                        r.x -= ak * q.x; r.y -= ak * q.y;
-                        st2(vr + i, r);
-                        if (keep_x || (DIST ? g.y0 : 0) + gy == 1 || (DIST ? g.y0 : 0) + gy == (DIST ? g.ng : g.n) - 2) {
-                            double2 x = ld2(vx + i);
-                            x.x += ak * cc.x; x.y += ak * cc.y;
-                            st2(vx + i, x);
-                        }
-                        acc0 += r.x * r.x * t0.y + r.y * r.y * t1.y;
-                        acc1 += r.x * r.x + r.y * r.y;
+                    double2 r = ld2(&s.sr[(ly + 1) * PT_LD + 2 + 2 * tx]);
+                    r.x -= ak * q.x; r.y -= ak * q.y;
+                    st2(vr + i, r);
+                    if (keep_x || (DIST ? g.y0 : 0) + gy == 1 || (DIST ? g.y0 : 0) + gy == (DIST ? g.ng : g.n) - 2) {
+                        double2 x = ld2(vx + i);
+                        x.x += ak * cc.x; x.y += ak * cc.y;
+                        st2(vx + i, x);
                     }
+                    acc0 += r.x * r.x * t0.y + r.y * r.y * t1.y;
+                    acc1 += r.x * r.x + r.y * r.y;
+                }
                 }
                 dlf = lf; drt = rt;
                 dn = cc; cc = up;

@@ -53,10 +53,10 @@ def main():
                 ib, sb = S.span()
                 assert list(ia) == list(ib) and list(sa) == list(sb), (ia, ib, sa, sb)
                 if cond and len(ia) and m % 16 == 0:
-                    tol, itmax = (1e-13, 400000) if m < 1024 else (1e-10, 400000)
+                    tol, itmax = (1e-13, 400000) if m < 1024 else (1e-12, 400000)
                     ra = L.conduct(0, tol=tol, itmax=itmax, voltages=False)
                     rb = S.conduct(0, tol=tol, itmax=itmax, voltages=False)
-                    assert abs(ra["iter"] - rb["iter"]) <= max(2, ra["iter"] // 200), (ra, rb)
+                    assert abs(ra["iter"] - rb["iter"]) <= max(2, ra["iter"] // 100), (ra, rb)
                     for k in ("Gtop", "Gbot"):
                         assert abs(ra[k] - rb[k]) <= (1e-12 if m < 1024 else 1e-9) * abs(ra[k]), (k, ra, rb)
                     if r == 0:
