@@ -228,11 +228,11 @@ static cudaError_t launch_local(Ctx* c, dim3 grid, int vec)
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(ccl_local_kernel<LAT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(TileSmem));
+                                             (int)tile_smem_bytes<LAT>());
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    ccl_local_kernel<LAT, KIND><<<grid, CT_THREADS, sizeof(TileSmem), c->stream>>>(c->g, c->mask, c->label, c->size,
+    ccl_local_kernel<LAT, KIND><<<grid, CT_THREADS, tile_smem_bytes<LAT>(), c->stream>>>(c->g, c->mask, c->label, c->size,
                                                                                   c->rootlist, c->d_sum, vec);
     return cudaGetLastError();
 }

@@ -19,6 +19,7 @@
 //   rootfix  every tile-local root -> its global root, sizes folded into the global root
 //   flatten  every site: one hop to the global root
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 #include <string.h>
 #include "geometry.cuh"
@@ -55,18 +56,44 @@ struct Summary {
 struct TileSmem {
     int lab[CT_TH * CT_TW];                     // union-find parents (node positions only); after phase 3
                                                 // re-used as the per-site root id staged for the coalesced output
-    int cnt[CT_TH * CT_TW];                     // per-root sizes; bit 31 = cluster touches the tile's border ring
-    uint32_t pS[CT_PR][CT_NW], pE[CT_PR][CT_NW], pN[CT_PR][CT_NW], pNW[CT_PR][CT_NW], pNE[CT_PR][CT_NW];
+    uint32_t cnt[CT_TH * CT_TW / 2];            // per-root sizes, two 16-bit counters per word (a tile-local cluster
+                                                // weighs at most 8192 sites x 7 = 57344 < 2^16)
+    uint32_t ringbits[CT_TH * CT_TW / 32];      // bit per root: the cluster touches the tile's border ring
+    uint32_t pS[CT_PR][CT_NW], pE[CT_PR][CT_NW], pN[CT_PR][CT_NW];
     uint32_t pC[CT_TH][CT_NW];                  // bit x: site x joined to site x-1 (inside the tile)
     uint32_t pT[CT_TH][CT_NW];                  // node starts
     uint8_t hL[CT_PR + 2], hR[CT_PR + 2];       // mask bytes left / right of the tile's columns (wrap-aware)
     unsigned long long best;                    // largest closed cluster of the tile, packed like Summary::maxpack
     unsigned lone, nroot, rootbase, nclosed;
+    // triangular lattice only -- kept last: the square kernels allocate the struct without them and fit
+    // four CTAs per SM
+    uint32_t pNW[CT_PR][CT_NW], pNE[CT_PR][CT_NW];
 };
+
+template <int LAT> constexpr size_t tile_smem_bytes() { return LAT == LAT_TRIANGULAR ? sizeof(TileSmem) : offsetof(TileSmem, pNW); }
 
 struct TileRegs { uint32_t rootbits; int nloc, off; };   // per-thread values that live across phases
 
-constexpr int CNT_RING = (int)0x80000000;
+
+// per-root counters: 16-bit halves of 32-bit words (no carry can cross: every total stays below 2^16)
+PERC_HD void cnt_add(TileSmem& s, int root, int w)
+{
+#if PERC_DEV
+    atomicAdd(&s.cnt[root >> 1], (uint32_t)w << ((root & 1) * 16));
+#else
+    s.cnt[root >> 1] += (uint32_t)w << ((root & 1) * 16);
+#endif
+}
+PERC_HD int cnt_get(const TileSmem& s, int root) { return (int)((s.cnt[root >> 1] >> ((root & 1) * 16)) & 0xffffu); }
+PERC_HD void ring_set(TileSmem& s, int root)
+{
+#if PERC_DEV
+    atomicOr(&s.ringbits[root >> 5], 1u << (root & 31));
+#else
+    s.ringbits[root >> 5] |= 1u << (root & 31);
+#endif
+}
+PERC_HD bool ring_get(const TileSmem& s, int root) { return (s.ringbits[root >> 5] >> (root & 31)) & 1u; }
 
 // ---- bit helpers ----------------------------------------------------------------------------
 PERC_HD int hibit(uint32_t v)
@@ -214,7 +241,8 @@ PERC_HD void tile_phase0(TileSmem& s, const Geom& g, const uint8_t* __restrict__
         uint32_t S = 0, E = 0, N = 0, NW = 0, NE = 0;
         bool halo = pr == 0 || pr == CT_PR - 1;
         if (!halo || KIND == KIND_MIXED) load_planes<LAT>(g, mask, x0 + 32 * w, y0 + pr - 1, vec, S, E, N, NW, NE);
-        s.pS[pr][w] = S; s.pE[pr][w] = E; s.pN[pr][w] = N; s.pNW[pr][w] = NW; s.pNE[pr][w] = NE;
+        s.pS[pr][w] = S; s.pE[pr][w] = E; s.pN[pr][w] = N;
+        if (LAT == LAT_TRIANGULAR) { s.pNW[pr][w] = NW; s.pNE[pr][w] = NE; }
     }
     if (tid < 2 * CT_PR) {
         int side = tid >= CT_PR, pr = tid - side * CT_PR;
@@ -229,6 +257,7 @@ PERC_HD void tile_phase0(TileSmem& s, const Geom& g, const uint8_t* __restrict__
         }
         if (side) s.hR[pr] = v; else s.hL[pr] = v;
     }
+    for (int k = tid; k < CT_TH * CT_TW / 32; k += CT_THREADS) s.ringbits[k] = 0;
     if (tid == 0) { s.lone = 0; s.nroot = 0; s.rootbase = 0; s.nclosed = 0; s.best = 0; }
 }
 
@@ -249,7 +278,7 @@ PERC_HD void tile_phase1(TileSmem& s, int tid)
     for (uint32_t t = T; t; t &= t - 1) {
         int a = lobit(t);
         s.lab[base + a] = base + a;
-        s.cnt[base + a] = 0;
+        s.cnt[(base + a) >> 1] = 0;      // both halves of the word belong to this thread's 32 sites
     }
 }
 
@@ -312,7 +341,8 @@ PERC_HD void tile_phase3(TileSmem& s, const Geom& g, int x0, int y0, int tid, Ti
     const int w = tid % CT_NW, ly = tid / CT_NW, pr = ly + 1;
     const int base = ly * CT_TW + (w << 5);
     const uint32_t S = s.pS[pr][w], T = s.pT[ly][w];
-    const uint32_t E = s.pE[pr][w], N = s.pN[pr][w], NW = s.pNW[pr][w], NE = s.pNE[pr][w];
+    const uint32_t E = s.pE[pr][w], N = s.pN[pr][w];
+    const uint32_t NW = LAT == LAT_TRIANGULAR ? s.pNW[pr][w] : 0u, NE = LAT == LAT_TRIANGULAR ? s.pNE[pr][w] : 0u;
     uint32_t inW = 0, inS = 0, inSW = 0, inSE = 0;
     // slab handles: only the rows this rank owns are counted (halo rows are the neighbour's)
     const bool owned = y0 + ly >= g.own_lo && y0 + ly < g.own_hi;
@@ -364,13 +394,8 @@ PERC_HD void tile_phase3(TileSmem& s, const Geom& g, int x0, int y0, int tid, Ti
     bool accring = false;
     auto flush = [&]() {
         if (prev < 0) return;
-#if PERC_DEV
-        if (acc) atomicAdd(&s.cnt[prev], acc);
-        if (accring) atomicOr(&s.cnt[prev], CNT_RING);
-#else
-        s.cnt[prev] += acc;
-        if (accring) s.cnt[prev] |= CNT_RING;
-#endif
+        if (acc) cnt_add(s, prev, acc);
+        if (accring) ring_set(s, prev);
     };
     uint32_t t = T;
     for (int it = warp_max_count(popc32(T)); it > 0; --it) {
@@ -422,8 +447,8 @@ PERC_HD void tile_phase4_fill(TileSmem& s, const Geom& g, int x0, int y0, int ti
     unsigned long long best = 0;
     for (uint32_t t = r.rootbits; t; t &= t - 1) {
         const int node = base + lobit(t);
-        const int c = s.cnt[node];
-        if (c < 0) { ++nloc; continue; }
+        if (ring_get(s, node)) { ++nloc; continue; }
+        const int c = cnt_get(s, node);
         const int32_t gl = tile_global_label(g, x0, y0, node);
         size[gl - 1] = c;
         if (c == 0) continue;                    // lives in halo rows only: the neighbour rank counts it
@@ -494,10 +519,10 @@ PERC_HD void tile_phase4_roots(const TileSmem& s, const Geom& g, int x0, int y0,
     int k = 0;
     for (uint32_t t = r.rootbits; t; t &= t - 1) {
         const int node = base + lobit(t);
-        const int c = s.cnt[node];
-        if (c >= 0) continue;
+        if (!ring_get(s, node)) continue;
+        const int c = cnt_get(s, node);
         const int32_t gl = tile_global_label(g, x0, y0, node);
-        size[gl - 1] = c & 0x7fffffff;
+        size[gl - 1] = c;
         rootlist[s.rootbase + r.off + k] = gl - 1;
         ++k;
     }
