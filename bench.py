@@ -343,7 +343,7 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 4 * t + 8 * nb,
                     "d2h_bytes_per_step": 8 * t + 4 * nb + 64, "steps": e2e_steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "pcg_pipe_kernel<0> (persistent TMA tile pipeline: p-update + 5-point SpMV + dot, q not stored)",
+            "roofline": {"bound": "hbm", "kernel": "pcg_pipe_kernel<0> (persistent TMA tile pipeline: p = r/d + bk p, p.Ap as bond energies; q = A p is never stored)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic_bytes("pcg_pipe_kernel<0>") if Lsz == 4096 else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,

@@ -185,6 +185,17 @@ module perc_iface
       integer(c_int32_t), intent(out) :: iter
     end function
 
+    ! perc_conduct starting from the voltages of the previous sweep point (linbcg's x is in/out, Sq/bondc.f:759-763)
+    integer(c_int32_t) function perc_conduct_warm(h, cluster_id, Va, g0, gleak, tol, itmax, read_thresh, &
+                                                  Gtop, Gbot, iter, err) bind(C, name="perc_conduct_warm")
+      import :: c_int32_t, c_int64_t, c_double
+      integer(c_int64_t), intent(in) :: h
+      integer(c_int32_t), intent(in) :: cluster_id, itmax
+      real(c_double), intent(in) :: Va, g0, gleak, tol, read_thresh
+      real(c_double), intent(out) :: Gtop, Gbot, err
+      integer(c_int32_t), intent(out) :: iter
+    end function
+
     ! the same solve for the p-sweep drivers (Sq/bond_cond.f:392-485 write only pb, Gbot, Gtop, avg):
     ! identical Gtop / Gbot / iter / err, interior voltages not formed
     integer(c_int32_t) function perc_conduct_g(h, cluster_id, Va, g0, gleak, tol, itmax, read_thresh, &
