@@ -393,7 +393,7 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-10)
     ap.add_argument("--itmax", type=int, default=2000000)
     ap.add_argument("--e2e-steps", type=int, default=-1)
-    ap.add_argument("--cpu-threads", type=int, default=8)
+    ap.add_argument("--cpu-threads", type=int, default=16, help="host threads of the CPU arm (capped at the core count)")
     ap.add_argument("--cpu-cg-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--voltages", action="store_true",

@@ -145,6 +145,13 @@ module perc_iface
       integer(c_int64_t), intent(out) :: hist(*)
     end function
 
+    integer(c_int32_t) function perc_hist_log2(h, nbins, hist) bind(C, name="perc_hist_log2")
+      import :: c_int32_t, c_int64_t
+      integer(c_int64_t), intent(in) :: h
+      integer(c_int32_t), intent(in) :: nbins
+      integer(c_int64_t), intent(out) :: hist(*)
+    end function
+
     integer(c_int32_t) function perc_site(h, order, k, s, c, maxcs, perccln, perccls) bind(C, name="perc_site")
       import :: c_int32_t, c_int64_t
       integer(c_int64_t), intent(in) :: h

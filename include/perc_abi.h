@@ -94,6 +94,8 @@ int32_t perc_span(const int64_t *h, const int32_t *max_ids, int32_t *nspan, int3
 /* exact cluster-size histogram: hist(s) = number of clusters of size s for s = 1..nbins-1,
  * hist(nbins) = clusters of size >= nbins.  (multiset of non-zero c()) */
 int32_t perc_hist(const int64_t *h, const int32_t *nbins, int64_t *hist);
+/* log-binned: hist(b+1) = clusters with 2^b <= size < 2^(b+1), the last bin takes the rest (n_s plots) */
+int32_t perc_hist_log2(const int64_t *h, const int32_t *nbins, int64_t *hist);
 
 /* reference-shaped one-call wrappers (upload order, label, download) */
 int32_t perc_site(const int64_t *h, const int32_t *order, const int32_t *k,

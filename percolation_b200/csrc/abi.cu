@@ -358,6 +358,14 @@ int32_t perc_hist(const int64_t* h, const int32_t* nbins, int64_t* hist)
     return ccl_hist(c, *nbins, hist);
 }
 
+int32_t perc_hist_log2(const int64_t* h, const int32_t* nbins, int64_t* hist)
+{
+    GET_CTX(h);
+    if (!c->labeled || !nbins || !hist) return PERC_E_STATE;
+    if (c->nranks > 1) return PERC_E_STATE;
+    return ccl_hist(c, *nbins, hist, 1);
+}
+
 static int finish_label(Ctx* c, int32_t* maxcs, int32_t* perccln, int32_t* perccls)
 {
     const Summary& s = c->h_sum;

@@ -47,6 +47,7 @@ ccl_local_kernel(Geom g, const uint8_t* __restrict__ mask, int32_t* __restrict__
     tile_phase2_level<LAT, 4>(s, tid); __syncthreads();
     tile_phase2_level<LAT, 5>(s, tid); __syncthreads();
     tile_phase2_level<LAT, 6>(s, tid); __syncthreads();
+    tile_clear_ring(s, tid); __syncthreads();
     tile_phase3<LAT, KIND>(s, g, x0, y0, tid, r);
     __syncthreads();
     tile_phase4_fill(s, g, x0, y0, tid, r, size);
@@ -161,9 +162,10 @@ ccl_span_kernel(int m, int64_t top0, const int32_t* __restrict__ label, const in
 // ------------------------------------------------------------------------------------------
 // K4: exact histogram: hist[s-1] for s < nbins, hist[nbins-1] = sizes >= nbins
 // ------------------------------------------------------------------------------------------
+// logbin = 0: hist[s-1] for s < nbins, hist[nbins-1] = sizes >= nbins;  logbin = 1: hist[floor(log2 s)]
 __global__ void __launch_bounds__(256)
 ccl_hist_kernel(int64_t t, const int32_t* __restrict__ label, const int32_t* __restrict__ size, int nbins,
-                unsigned long long* __restrict__ hist)
+                unsigned long long* __restrict__ hist, int logbin)
 {
     extern __shared__ unsigned sh_hist[];
     int nsh = nbins < 4096 ? nbins : 4096;
@@ -174,7 +176,8 @@ ccl_hist_kernel(int64_t t, const int32_t* __restrict__ label, const int32_t* __r
         if (label[i] != (int32_t)(i + 1)) continue;          // sizes live at the roots
         int32_t s = size[i];
         if (s > 0) {
-            int b = s < nbins ? s - 1 : nbins - 1;
+            int b = logbin ? 31 - __clz(s) : s - 1;
+            if (b >= nbins) b = nbins - 1;
             if (b < nsh) atomicAdd(&sh_hist[b], 1u);
             else atomicAdd(&hist[b], 1ull);
         }
@@ -336,14 +339,14 @@ int ccl_fetch_summary(Ctx* c)
     return 0;
 }
 
-int ccl_hist(Ctx* c, int nbins, int64_t* hist)
+int ccl_hist(Ctx* c, int nbins, int64_t* hist, int logbin)
 {
     if (nbins < 1) return -1;
     unsigned long long* d = (unsigned long long*)ctx_dev_stage(c, sizeof(unsigned long long) * nbins);
     if (!d) return (int)cudaErrorMemoryAllocation;
     PERC_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * nbins, c->stream));
     int nsh = nbins < 4096 ? nbins : 4096;
-    ccl_hist_kernel<<<148 * 4, 256, sizeof(unsigned) * nsh, c->stream>>>(c->g.t, c->label, c->size, nbins, d);
+    ccl_hist_kernel<<<148 * 4, 256, sizeof(unsigned) * nsh, c->stream>>>(c->g.t, c->label, c->size, nbins, d, logbin);
     c->launches++;
     PERC_CUDA(cudaMemcpyAsync(hist, d, sizeof(unsigned long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
     PERC_CUDA(cudaStreamSynchronize(c->stream));

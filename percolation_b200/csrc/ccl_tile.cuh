@@ -58,9 +58,11 @@ struct TileSmem {
                                                 // re-used as the per-site root id staged for the coalesced output
     uint32_t cnt[CT_TH * CT_TW / 2];            // per-root sizes, two 16-bit counters per word (a tile-local cluster
                                                 // weighs at most 8192 sites x 7 = 57344 < 2^16)
-    uint32_t ringbits[CT_TH * CT_TW / 32];      // bit per root: the cluster touches the tile's border ring
     uint32_t pS[CT_PR][CT_NW], pE[CT_PR][CT_NW], pN[CT_PR][CT_NW];
-    uint32_t pC[CT_TH][CT_NW];                  // bit x: site x joined to site x-1 (inside the tile)
+    union {
+        uint32_t pC[CT_TH][CT_NW];              // phases 1-2: bit x: site x joined to site x-1 (inside the tile)
+        uint32_t ringbits[CT_TH * CT_TW / 32];  // phases 3-4: bit per root: the cluster touches the tile's border ring
+    };
     uint32_t pT[CT_TH][CT_NW];                  // node starts
     uint8_t hL[CT_PR + 2], hR[CT_PR + 2];       // mask bytes left / right of the tile's columns (wrap-aware)
     unsigned long long best;                    // largest closed cluster of the tile, packed like Summary::maxpack
@@ -257,7 +259,6 @@ PERC_HD void tile_phase0(TileSmem& s, const Geom& g, const uint8_t* __restrict__
         }
         if (side) s.hR[pr] = v; else s.hL[pr] = v;
     }
-    for (int k = tid; k < CT_TH * CT_TW / 32; k += CT_THREADS) s.ringbits[k] = 0;
     if (tid == 0) { s.lone = 0; s.nroot = 0; s.rootbase = 0; s.nclosed = 0; s.best = 0; }
 }
 
@@ -328,6 +329,13 @@ PERC_HD void tile_phase2_level(TileSmem& s, int tid)
             tile_unite(s.lab, base + hibit(T & le_mask(x)), node_of(s, ly + 1, (w << 5) + x + 1));
         }
     }
+}
+
+// between the last union level and phase 3 (separate barrier on both sides): the run-connectivity plane is
+// dead, its storage becomes the ring bitmap
+PERC_HD void tile_clear_ring(TileSmem& s, int tid)
+{
+    for (int k = tid; k < CT_TH * CT_TW / 32; k += CT_THREADS) s.ringbits[k] = 0;
 }
 
 // ---- phase 3: node -> root, sizes -------------------------------------------------------------

@@ -120,7 +120,7 @@ int ccl_launch(Ctx* c, int kind);        // the labeling pipeline without the fi
 int batch_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsigned long long stream0, int64_t ks, int64_t kb,
               int nbins, int64_t* hist, int64_t* stats);
 int ccl_fetch_summary(Ctx* c);
-int ccl_hist(Ctx* c, int nbins, int64_t* hist);
+int ccl_hist(Ctx* c, int nbins, int64_t* hist, int logbin = 0);
 int ccl_export_bond_labels(Ctx* c, int32_t* b3);
 int ccl_export_sizes(Ctx* c, int32_t* cs);
 

@@ -26,7 +26,7 @@ SYMBOLS = [
     "perc_set_site_order", "perc_set_bond_order", "perc_set_fill", "perc_set_occupancy",
     "perc_generate", "perc_get_occupancy",
     "perc_label", "perc_summary", "perc_get_site_labels", "perc_get_bond_labels", "perc_get_sizes",
-    "perc_span", "perc_hist", "perc_site", "perc_bond", "perc_sitebond", "perc_first_span",
+    "perc_span", "perc_hist", "perc_hist_log2", "perc_site", "perc_bond", "perc_sitebond", "perc_first_span",
     "perc_conduct", "perc_conduct_warm", "perc_conduct_g", "perc_get_voltage", "perc_launch_count", "perc_phase_ms", "perc_stream",
     "perc_create_slab", "perc_comm_unique_id", "perc_comm_init", "perc_slab_rows", "perc_generate_i8",
     "perc_summary_i8", "perc_span_i8", "perc_get_site_labels_i8", "perc_stitch_host",
@@ -195,6 +195,11 @@ class Lattice:
     def hist(self, nbins):
         h = np.zeros(nbins, np.int64)
         self._call("perc_hist", _i32(nbins), _ptr(h, C.c_int64))
+        return h
+
+    def hist_log2(self, nbins=32):
+        h = np.zeros(nbins, np.int64)
+        self._call("perc_hist_log2", _i32(nbins), _ptr(h, C.c_int64))
         return h
 
     def site(self, order, k):

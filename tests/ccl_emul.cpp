@@ -50,6 +50,7 @@ static void run_local(const Geom& g, const uint8_t* mask, int32_t* label, int32_
 #define LEVEL(K) for (int tid = CT_THREADS - 1; tid >= 0; --tid) tile_phase2_level<LAT, K>(*s, tid)
             LEVEL(1); LEVEL(2); LEVEL(3); LEVEL(4); LEVEL(5); LEVEL(6);
 #undef LEVEL
+            for (int tid = 0; tid < CT_THREADS; ++tid) tile_clear_ring(*s, tid);
             for (int tid = 0; tid < CT_THREADS; ++tid) tile_phase3<LAT, KIND>(*s, g, x0, y0, tid, regs[tid]);
             for (int tid = 0; tid < CT_THREADS; ++tid) tile_phase4_fill(*s, g, x0, y0, tid, regs[tid], size);
             tile_phase4_reserve(*s, sum);

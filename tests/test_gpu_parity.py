@@ -60,6 +60,10 @@ def test_site_labels_sizes_span(P, O, lat, m, n, pbc):
             h = L.hist(nbins)
             oh = O.size_hist(O.SITE, t, wsz, None, max(t, nbins))
             assert (h[:nbins - 1] == oh[1:nbins]).all() and h[nbins - 1] == oh[nbins:].sum()
+            hl = L.hist_log2(8)                      # log-binned: [2^b, 2^(b+1)), the last bin takes the rest
+            sz = wsz[wsz > 0].astype(np.int64)
+            want_l = np.bincount(np.minimum(np.floor(np.log2(sz)).astype(int), 7), minlength=8) if len(sz) else np.zeros(8, int)
+            assert (hl == want_l).all()
 
 
 @pytest.mark.parametrize("lat,m,n,pbc", CASES)
