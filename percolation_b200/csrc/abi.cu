@@ -99,6 +99,8 @@ void ctx_free(Ctx* c)
 {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (Ctx* k : c->batch_kids) { ctx_free(k); delete k; }
+    c->batch_kids.clear();
     slab_comm_destroy(c);
     if (c->d_iface) cudaFree(c->d_iface);
     if (c->h_iface) cudaFreeHost(c->h_iface);

@@ -8,6 +8,7 @@
 // the loop (the exact-count selection runs device-resident, occupancy.cu); one download at the end.
 // Integer sums are order independent, so shards of a batch on different GPUs all-reduce to the same
 // result for any number of GPUs (SURVEY 8e mode 1).
+#include <vector>
 #include "context.h"
 
 namespace perc {
@@ -62,47 +63,82 @@ batch_hist_kernel(int64_t t, const int32_t* __restrict__ label, const int32_t* _
 }
 
 constexpr int BATCH_NSTATS = 16;
+constexpr int BATCH_WAYS = 4;
+
+// Small lattices do not fill the GPU (L = 1024 is 128 tiles for 148 SMs, L = 100 is one): a batch round-robins
+// its realizations over up to BATCH_WAYS contexts, each with its own arrays and stream, so that the kernels
+// of different realizations overlap.  ways[0] is the handle itself; the children are created once and kept.
+static int batch_contexts(Ctx* c, int nreal, std::vector<Ctx*>& ways)
+{
+    ways.assign(1, c);
+    int want = c->g.t <= ((int64_t)1 << 22) ? BATCH_WAYS : 1;
+    if (want > nreal) want = nreal;
+    while ((int)c->batch_kids.size() < want - 1) {
+        Ctx* k = new Ctx();
+        k->g = c->g; k->device = c->device;
+        int rc = ctx_alloc(k);
+        if (rc) { ctx_free(k); delete k; return rc; }
+        c->batch_kids.push_back(k);
+    }
+    for (int j = 0; j < want - 1; ++j) ways.push_back(c->batch_kids[j]);
+    return 0;
+}
 
 int batch_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsigned long long stream0, int64_t ks, int64_t kb,
               int nbins, int64_t* hist, int64_t* stats)
 {
     if (c->nranks > 1) return -4;
-    cudaStream_t st = c->stream;
-    const size_t hb = sizeof(unsigned long long) * (size_t)(nbins > 0 ? nbins : 1);
-    unsigned long long* d_hist = nullptr;
-    long long* d_stats = nullptr;
-    PERC_CUDA(cudaMalloc(&d_hist, hb));
-    PERC_CUDA(cudaMalloc(&d_stats, sizeof(long long) * BATCH_NSTATS));
-    PERC_CUDA(cudaMemsetAsync(d_hist, 0, hb, st));
-    PERC_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(long long) * BATCH_NSTATS, st));
-    int rc = 0;
-    c->batch_thr = true;
+    std::vector<Ctx*> ways;
+    int rc = batch_contexts(c, nreal, ways);
+    if (rc) return rc;
+    const int K = (int)ways.size();
+    const int nb1 = nbins > 0 ? nbins : 1;
+    const size_t hb = sizeof(unsigned long long) * (size_t)nb1;
+    // per way: [nb1] histogram words, then BATCH_NSTATS statistics words
+    unsigned long long* d_acc = nullptr;
+    const size_t way_words = (size_t)nb1 + BATCH_NSTATS;
+    PERC_CUDA(cudaMalloc(&d_acc, sizeof(unsigned long long) * way_words * K));
+    PERC_CUDA(cudaMemset(d_acc, 0, sizeof(unsigned long long) * way_words * K));
+    PERC_CUDA(cudaDeviceSynchronize());              // the ways' streams do not synchronise with the legacy stream
     const int nsh = nbins < 4096 ? nbins : 4096;
+    for (Ctx* w : ways) w->batch_thr = true;
     for (int i = 0; i < nreal && rc == 0; ++i) {
-        rc = occ_generate_dev(c, seed, stream0 + (unsigned long long)i, kind != KIND_BOND ? ks : -1, kind != KIND_SITE ? kb : -1,
+        Ctx* w = ways[i % K];
+        unsigned long long* d_hist = d_acc + way_words * (i % K);
+        long long* d_stats = (long long*)(d_hist + nb1);
+        rc = occ_generate_dev(w, seed, stream0 + (unsigned long long)i, kind != KIND_BOND ? ks : -1, kind != KIND_SITE ? kb : -1,
                               (unsigned long long*)(d_stats + 6));
         if (rc) break;
-        rc = ccl_launch(c, kind);
+        rc = ccl_launch(w, kind);
         if (rc) break;
         if (nbins > 0) {
-            batch_hist_kernel<<<148 * 4, 256, sizeof(unsigned) * nsh, st>>>(c->g.t, c->label, c->size, nbins, d_hist);
-            c->launches++;
+            batch_hist_kernel<<<148 * 4, 256, sizeof(unsigned) * nsh, w->stream>>>(w->g.t, w->label, w->size, nbins, d_hist);
+            w->launches++;
         }
-        batch_accum_kernel<<<1, 1, 0, st>>>(c->d_sum, d_hist, nbins, d_stats);
-        c->launches++;
+        batch_accum_kernel<<<1, 1, 0, w->stream>>>(w->d_sum, d_hist, nbins, d_stats);
+        w->launches++;
     }
-    c->batch_thr = false;
-    c->labeled = false;              // the per-realization state on the host was never fetched
+    for (Ctx* w : ways) {
+        w->batch_thr = false;
+        w->labeled = false;          // the per-realization state on the host was never fetched
+        cudaError_t e = cudaStreamSynchronize(w->stream);
+        if (!rc && e != cudaSuccess) rc = (int)e;
+        if (w != c) { c->launches += w->launches; w->launches = 0; }
+    }
     if (rc == 0) {
-        if (nbins > 0 && hist) PERC_CUDA(cudaMemcpyAsync(hist, d_hist, hb, cudaMemcpyDeviceToHost, st));
-        long long h[BATCH_NSTATS];
-        PERC_CUDA(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
-        PERC_CUDA(cudaStreamSynchronize(st));
-        for (int k = 0; k < BATCH_NSTATS; ++k) stats[k] = h[k];
+        std::vector<unsigned long long> h(way_words * K);
+        PERC_CUDA(cudaMemcpy(h.data(), d_acc, sizeof(unsigned long long) * way_words * K, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < BATCH_NSTATS; ++k) stats[k] = 0;
+        if (nbins > 0 && hist) for (int b = 0; b < nbins; ++b) hist[b] = 0;
+        for (int j = 0; j < K; ++j) {
+            const unsigned long long* hw = h.data() + way_words * j;
+            if (nbins > 0 && hist) for (int b = 0; b < nbins; ++b) hist[b] += (int64_t)hw[b];
+            for (int k = 0; k < BATCH_NSTATS; ++k) stats[k] += (int64_t)hw[nb1 + k];
+        }
         rc = (int)cudaGetLastError();
-    } else cudaStreamSynchronize(st);
-    cudaFree(d_hist);
-    cudaFree(d_stats);
+    }
+    (void)hb;
+    cudaFree(d_acc);
     return rc;
 }
 
@@ -145,16 +181,37 @@ int batch_conduct_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsi
     PERC_CUDA(cudaMalloc(&d_it, sizeof(int) * nreal));
     PERC_CUDA(cudaMalloc(&d_stats, sizeof(long long) * BATCH_NSTATS));
     PERC_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(long long) * BATCH_NSTATS, st));
-    c->batch_thr = true;
+    // labeling of the realizations: round-robin over the ways (statistics: one block of words per way)
+    std::vector<Ctx*> ways;
+    rc = batch_contexts(c, nreal, ways);
+    const int K = (int)ways.size();
+    long long* d_wstats = nullptr;
+    if (!rc) { PERC_CUDA(cudaMalloc(&d_wstats, sizeof(long long) * BATCH_NSTATS * K)); PERC_CUDA(cudaMemset(d_wstats, 0, sizeof(long long) * BATCH_NSTATS * K)); PERC_CUDA(cudaDeviceSynchronize()); }
+    for (Ctx* w : ways) w->batch_thr = true;
     for (int i = 0; i < nreal && rc == 0; ++i) {
-        rc = occ_generate_dev(c, seed, stream0 + (unsigned long long)i, kind != KIND_BOND ? ks : -1, kind != KIND_SITE ? kb : -1,
-                              (unsigned long long*)(d_stats + 6));
-        if (!rc) rc = ccl_launch(c, kind);
-        if (!rc) rc = pcg_small_stage(c, d_cf, i);
-        if (!rc) { batch_accum_kernel<<<1, 1, 0, st>>>(c->d_sum, nullptr, 0, d_stats); c->launches++; }
+        Ctx* w = ways[i % K];
+        long long* ws = d_wstats + BATCH_NSTATS * (i % K);
+        rc = occ_generate_dev(w, seed, stream0 + (unsigned long long)i, kind != KIND_BOND ? ks : -1, kind != KIND_SITE ? kb : -1,
+                              (unsigned long long*)(ws + 6));
+        if (!rc) rc = ccl_launch(w, kind);
+        if (!rc) rc = pcg_small_stage(w, d_cf, i);
+        if (!rc) { batch_accum_kernel<<<1, 1, 0, w->stream>>>(w->d_sum, nullptr, 0, ws); w->launches++; }
     }
-    c->batch_thr = false;
-    c->labeled = false;
+    for (Ctx* w : ways) {
+        w->batch_thr = false;
+        w->labeled = false;
+        cudaError_t e = cudaStreamSynchronize(w->stream);      // every conduct map is staged before the solve starts
+        if (!rc && e != cudaSuccess) rc = (int)e;
+        if (w != c) { c->launches += w->launches; w->launches = 0; }
+    }
+    if (!rc) {
+        std::vector<long long> hs((size_t)BATCH_NSTATS * K);
+        PERC_CUDA(cudaMemcpy(hs.data(), d_wstats, sizeof(long long) * BATCH_NSTATS * K, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < BATCH_NSTATS; ++k) { long long sum = 0; for (int j = 0; j < K; ++j) sum += hs[(size_t)j * BATCH_NSTATS + k]; hs[k] = sum; }
+        PERC_CUDA(cudaMemcpy(d_stats, hs.data(), sizeof(long long) * BATCH_NSTATS, cudaMemcpyHostToDevice));
+        PERC_CUDA(cudaDeviceSynchronize());
+    }
+    if (d_wstats) cudaFree(d_wstats);
     if (!rc) rc = pcg_small_solve(c, d_cf, nreal, Va, g0, gleak, tol, itmax, read_thresh, d_G, d_it, d_err);
     if (!rc) {
         long long h[BATCH_NSTATS];

@@ -93,6 +93,9 @@ struct Ctx {
     void* d_stage = nullptr;
     size_t d_stage_bytes = 0;
 
+    // ---- batches: child contexts (own arrays + stream) so that small lattices overlap on the GPU
+    std::vector<Ctx*> batch_kids;
+
     // ---- instrumentation
     int64_t launches = 0;
     float phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
