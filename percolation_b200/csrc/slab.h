@@ -26,11 +26,6 @@ struct IfaceLayout {
     PERC_HD int64_t words() const { return 5 * (int64_t)m + 8; }
 };
 
-struct StitchClass {
-    int64_t gid;      // lattice-wide canonical label: smallest member site id (1-based)
-    int64_t total;    // cluster size over all ranks
-};
-
 struct StitchResult {
     // for the calling rank: every interface cluster it holds
     std::vector<int64_t> root_gid;     // lattice-wide id of the rank-local root (ascending)
