@@ -99,3 +99,41 @@ extern "C" int ccl_emul(int lattice, int m, int n, int pbc, int kind, const uint
     delete sum;
     return 0;
 }
+
+
+// Slab of a decomposed lattice (rank `rank` of `nranks`): the rank-local labeling with sizes restricted to
+// the owned rows, exactly what the GPU does before the stitch.  socc / bocc describe the WHOLE lattice.
+// label / csize: g.t = m * (rows held) entries; out[0..1] = ncl (closed clusters only), nlone; out[5..8] =
+// y0, rows held, own_lo, own_hi.
+extern "C" int ccl_emul_slab(int lattice, int m, int ng, int pbc, int kind, int nranks, int rank,
+                             const uint8_t* socc, const uint8_t* bocc, int32_t* label, int32_t* csize, int64_t* out)
+{
+    Geom gw = make_geom(lattice, m, ng, pbc);
+    std::vector<uint8_t> wmask;
+    build_mask(gw, kind, socc, bocc, wmask);
+    Geom g = make_slab_geom(lattice, m, ng, pbc, nranks, rank);
+    const uint8_t* mask = wmask.data() + (int64_t)g.y0 * m;            // bond bits follow the WHOLE lattice's geometry
+    std::vector<int32_t> size((size_t)g.t, 0x5a5a5a5a), rootlist((size_t)g.t, -1);
+    for (int64_t i = 0; i < g.t; ++i) label[i] = 0x7f7f7f7f;
+    Summary* sum = new Summary;
+    memset(sum, 0, sizeof(Summary));
+    const bool vec = (m % 16) == 0;
+    const bool sq = lattice == LAT_SQUARE;
+#define RUN(L, K) run_local<L, K>(g, mask, label, size.data(), rootlist.data(), sum, vec)
+    if (sq) { if (kind == KIND_SITE) RUN(LAT_SQUARE, KIND_SITE); else if (kind == KIND_BOND) RUN(LAT_SQUARE, KIND_BOND); else RUN(LAT_SQUARE, KIND_MIXED); }
+    else    { if (kind == KIND_SITE) RUN(LAT_TRIANGULAR, KIND_SITE); else if (kind == KIND_BOND) RUN(LAT_TRIANGULAR, KIND_BOND); else RUN(LAT_TRIANGULAR, KIND_MIXED); }
+#undef RUN
+    int nrowb = (g.n - 1) / CT_TH, nwords = (g.m + 31) / 32, ncolb = (g.m - 1) / CT_TW + (g.pbc ? 1 : 0);
+    int64_t nitems = (int64_t)nrowb * nwords * 32 + (int64_t)ncolb * g.n;
+    for (int64_t id = 0; id < nitems; ++id) {
+        if (sq) merge_item<LAT_SQUARE>(g, mask, label, nrowb, nwords, ncolb, id, vec);
+        else merge_item<LAT_TRIANGULAR>(g, mask, label, nrowb, nwords, ncolb, id, vec);
+    }
+    for (int64_t k = 0; k < sum->nroots; ++k) { int isroot; rootfix_item(label, size.data(), rootlist.data(), k, true, &isroot); }
+    for (int64_t i = g.t - 1; i >= 0; --i) label[i] = flatten_one(label, label[i]);
+    for (int64_t i = 0; i < g.t; ++i) csize[i] = label[i] == (int32_t)(i + 1) ? size[i] : 0;
+    out[0] = (int64_t)sum->ncl; out[1] = (int64_t)sum->nlone;
+    out[5] = g.y0; out[6] = g.n; out[7] = g.own_lo; out[8] = g.own_hi;
+    delete sum;
+    return 0;
+}
