@@ -170,7 +170,8 @@ int32_t perc_stitch_host(const int32_t *nranks, const int32_t *rank, const int32
  * is labeled, and is folded into device-resident statistics; nothing is synchronised inside the loop.
  * hist(nbins): cluster-size histogram summed over the batch (layout of perc_hist); stats(16), int64:
  *  (1) realizations (2) sum ncl (3) sum maxcs (4) realizations that span (5) sum nspan (6) sum perccls
- *  (7) failed selections -- must be 0 -- (8) sum maxcs^2 (9) sum occupied sites (10) sum occupied bonds */
+ *  (7) failed selections -- must be 0 -- (8) sum maxcs^2 (9) sum occupied sites (10) sum occupied bonds.
+ * The handle's occupancy input is consumed: call perc_generate / perc_set_*_order again before perc_label. */
 int32_t perc_batch(const int64_t *h, const int32_t *kind, const int32_t *nreal, const int64_t *seed,
                    const int64_t *stream0, const int32_t *ks, const int32_t *kb, const int32_t *nbins,
                    int64_t *hist, int64_t *stats);

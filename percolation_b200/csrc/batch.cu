@@ -121,6 +121,7 @@ int batch_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsigned lon
     for (Ctx* w : ways) {
         w->batch_thr = false;
         w->labeled = false;          // the per-realization state on the host was never fetched
+        w->site_src = SRC_NONE; w->bond_src = SRC_NONE;     // the batch's thresholds lived on the device only
         cudaError_t e = cudaStreamSynchronize(w->stream);
         if (!rc && e != cudaSuccess) rc = (int)e;
         if (w != c) { c->launches += w->launches; w->launches = 0; }
@@ -200,6 +201,7 @@ int batch_conduct_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsi
     for (Ctx* w : ways) {
         w->batch_thr = false;
         w->labeled = false;
+        w->site_src = SRC_NONE; w->bond_src = SRC_NONE;
         cudaError_t e = cudaStreamSynchronize(w->stream);      // every conduct map is staged before the solve starts
         if (!rc && e != cudaSuccess) rc = (int)e;
         if (w != c) { c->launches += w->launches; w->launches = 0; }

@@ -448,7 +448,11 @@ def test_batch_equals_realization_loop(P, lat, kind, m, n, pbc, ps, pb):
         got_hist, got = L.batch(kind, nreal, seed, stream0, ks, kb, nbins)
         assert got == want
         assert (got_hist == hist).all()
-        # a handle is usable as before after a batch
+        # a batch consumes the handle's occupancy input ...
+        with pytest.raises(P.PercError) as e:
+            L.label(kind)
+        assert e.value.code == P.E_STATE
+        # ... and the handle is usable as before once it gets a new one
         L.generate(seed, stream0, ks if kind != 2 else -1, kb if kind != 1 else -1)
         L.label(kind)
         assert L.summary()["ncl"] > 0
