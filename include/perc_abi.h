@@ -141,7 +141,7 @@ int32_t perc_get_voltage(const int64_t *h, double *Vint);             /* Vint(t-
  * the m x n lattice plus one halo row on each inner side.  The occupancy comes from the generator
  * (element keys are functions of the lattice-wide element id, so the realization is the one the
  * single-GPU handle draws); perc_label labels the slab, all-gathers the interface rows over NCCL and
- * stitches the clusters with a union-find every rank runs redundantly; perc_conduct_g exchanges one halo
+ * stitches the clusters with a union-find every rank runs redundantly on its GPU; perc_conduct_g exchanges one halo
  * row of the residual per iteration (ncclSend/ncclRecv) and all-reduces the two dot products.
  * Lattice-wide labels / sizes / counts are 64-bit (t = 2^32 at L = 65536). */
 int32_t perc_create_slab(int64_t *h, const int32_t *lattice, const int32_t *m, const int32_t *n,
@@ -157,7 +157,8 @@ int32_t perc_summary_i8(const int64_t *h, int64_t *ncl, int64_t *maxcs, int64_t 
 int32_t perc_span_i8(const int64_t *h, const int32_t *max_ids, int32_t *nspan, int64_t *ids, int64_t *sizes);
 /* s((yb-ya)*m): lattice-wide canonical labels of the rows this rank owns */
 int32_t perc_get_site_labels_i8(const int64_t *h, int64_t *s);
-/* the stitch's host union-find on its own (no device; CPU tests): gathered = nranks blocks of 5*m+8 words
+/* the stitch on its own, its device code executed item by item on the host (no device needed; CPU tests):
+ * gathered = nranks blocks of 5*m+8 words
  * (layout: percolation_b200/csrc/slab.h); out_summary(5) = ncl, nlone, maxcs, maxcn, nspan; out_pairs(4,k) =
  * (root id, representative id, class label, class size) of every interface cluster the calling rank holds */
 int32_t perc_stitch_host(const int32_t *nranks, const int32_t *rank, const int32_t *m, const int64_t *gathered,

@@ -103,6 +103,7 @@ void ctx_free(Ctx* c)
     c->batch_kids.clear();
     slab_comm_destroy(c);
     if (c->d_iface) cudaFree(c->d_iface);
+    if (c->d_stitch) cudaFree(c->d_stitch);
     if (c->h_iface) cudaFreeHost(c->h_iface);
     void* ptrs[] = {c->srank, c->brank, c->mask, c->label, c->size, c->rootlist, c->d_sum, c->d_pcg,
                     c->d_hist, c->d_thr, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vp2, c->vq, c->partial, c->d_stage};

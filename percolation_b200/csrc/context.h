@@ -40,6 +40,8 @@ struct Ctx {
     int stat_nranks = 1;                 // ranks of a communicator used only to reduce statistics (mode 1)
     int64_t* d_iface = nullptr;          // [nranks + 1] interface blocks (all-gather target + own block)
     int64_t* h_iface = nullptr;          // pinned
+    void* d_stitch = nullptr;            // hash table + outputs of the device-side stitch
+    size_t d_stitch_bytes = 0;
     StitchResult stitch;
     std::vector<int32_t> tab_rep;        // interface classes held by this rank: representative root (ascending)
     std::vector<int64_t> tab_gid, tab_total;   //   -> lattice-wide label and size

@@ -2,130 +2,77 @@
 #include <dlfcn.h>
 #include <algorithm>
 #include <cstring>
-#include <unordered_map>
 #include "context.h"
 #include "slab.h"
+#include "slab_stitch.cuh"
 
 namespace perc {
 
 // ------------------------------------------------------------------------------------------
-// host: union-find over the interface labels (run redundantly by every rank)
+// the stitch (slab_stitch.cuh) run item by item on the host: CPU tests of the logic the kernels below execute
 // ------------------------------------------------------------------------------------------
-namespace {
-struct Node { int64_t key; int64_t size; };       // key = (rank << 40) | lattice-wide id of the rank-local root
-
-inline int64_t node_key(int rank, int64_t gid) { return ((int64_t)rank << 40) | gid; }
-
-int uf_find(std::vector<int>& p, int a)
+static int stitch_table_size(int nranks, int m, int* logH)
 {
-    while (p[a] != a) { p[a] = p[p[a]]; a = p[a]; }
-    return a;
+    int64_t entries = 2 * (int64_t)(nranks > 1 ? nranks - 1 : 1) * m;
+    int lg = 10;
+    while (((int64_t)1 << lg) < 2 * entries) ++lg;
+    *logH = lg;
+    return 1 << lg;
 }
-}  // namespace
+
+static void stitch_collect(const StitchTab& T, const long long* out, unsigned long long maxgid, const int64_t* span,
+                           const int64_t* pairs, int m, int nranks, const int64_t* gathered, StitchResult* R)
+{
+    IfaceLayout L{m};
+    *R = StitchResult();
+    R->error = (int)out[6];
+    if (R->error) return;
+    for (int r = 0; r < nranks; ++r) {
+        const int64_t* sc = gathered + r * L.words() + L.scalars();
+        R->ncl += sc[0];
+        R->nlone += sc[1];
+    }
+    R->ncl += out[0];
+    R->maxcs = out[1];
+    R->maxgid = out[1] > 0 && maxgid != STITCH_NONE ? (int64_t)maxgid : 0;
+    int ns = (int)(out[3] < MAX_SPAN_CLASSES ? out[3] : MAX_SPAN_CLASSES);
+    std::vector<std::pair<int64_t, int64_t>> sp;
+    for (int k = 0; k < ns; ++k) sp.push_back({span[2 * k], span[2 * k + 1]});
+    std::sort(sp.begin(), sp.end());
+    for (auto& e : sp) { R->span_gid.push_back(e.first); R->span_size.push_back(e.second); }
+    int np = (int)(out[4] < T.cap ? out[4] : T.cap);
+    std::vector<int> order(np);
+    for (int k = 0; k < np; ++k) order[k] = k;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return pairs[4 * a] < pairs[4 * b]; });
+    for (int k : order) {
+        R->root_gid.push_back(pairs[4 * k]); R->rep_gid.push_back(pairs[4 * k + 1]);
+        R->class_gid.push_back(pairs[4 * k + 2]); R->class_total.push_back(pairs[4 * k + 3]);
+    }
+}
 
 void stitch_host(int nranks, int rank, int m, const int64_t* gathered, StitchResult* out)
 {
-    IfaceLayout L{m};
-    const int64_t W = L.words();
-    *out = StitchResult();
-    // 1. nodes: the distinct (rank, cluster) pairs seen on interface rows, with their rank-local sizes
-    std::vector<Node> nodes;
-    for (int r = 0; r < nranks; ++r) {
-        const int64_t* blk = gathered + r * W;
-        for (int side = 0; side < 2; ++side) {
-            if ((side == 0 && r == 0) || (side == 1 && r == nranks - 1)) continue;
-            const int64_t* ids = blk + (side ? L.rowB() : L.rowA());
-            const int64_t* sz = blk + (side ? L.sizeB() : L.sizeA());
-            for (int x = 0; x < m; ++x)                      // neighbouring sites mostly repeat the label: keep the changes
-                if (ids[x] && (x == 0 || ids[x] != ids[x - 1])) nodes.push_back({node_key(r, ids[x]), sz[x]});
-        }
-    }
-    std::sort(nodes.begin(), nodes.end(), [](const Node& a, const Node& b) { return a.key < b.key; });
-    nodes.erase(std::unique(nodes.begin(), nodes.end(), [](const Node& a, const Node& b) { return a.key == b.key; }), nodes.end());
-    auto index_of = [&](int64_t key) -> int {
-        auto it = std::lower_bound(nodes.begin(), nodes.end(), key, [](const Node& a, int64_t k) { return a.key < k; });
-        return (it != nodes.end() && it->key == key) ? (int)(it - nodes.begin()) : -1;
-    };
-    // 2. unions: row yb is the top halo row of rank r and the first owned row of rank r + 1
-    std::vector<int> parent(nodes.size());
-    for (size_t k = 0; k < nodes.size(); ++k) parent[k] = (int)k;
-    for (int r = 0; r + 1 < nranks; ++r) {
-        const int64_t* lo = gathered + r * W + L.rowB();
-        const int64_t* hi = gathered + (r + 1) * W + L.rowA();
-        for (int x = 0; x < m; ++x) {
-            if ((lo[x] != 0) != (hi[x] != 0)) { out->error = 1; return; }
-            if (!lo[x]) continue;
-            if (x > 0 && lo[x] == lo[x - 1] && hi[x] == hi[x - 1]) continue;      // same pair as the column before
-            int a = uf_find(parent, index_of(node_key(r, lo[x]))), b = uf_find(parent, index_of(node_key(r + 1, hi[x])));
-            if (a != b) parent[a > b ? a : b] = a > b ? b : a;
-        }
-    }
-    // 3. classes: canonical label = smallest member id; size = sum of the rank-local sizes
-    const int64_t MASK40 = ((int64_t)1 << 40) - 1;
-    std::vector<int64_t> cgid(nodes.size(), 0), ctot(nodes.size(), 0);
-    std::vector<int> cpos(nodes.size(), 0);                      // members with a non-zero rank-local size
-    for (size_t k = 0; k < nodes.size(); ++k) {
-        int c = uf_find(parent, (int)k);
-        int64_t gid = nodes[k].key & MASK40;
-        if (cgid[c] == 0 || gid < cgid[c]) cgid[c] = gid;
-        ctot[c] += nodes[k].size;
-        cpos[c] += nodes[k].size > 0;
-    }
-    // 4. lattice-wide summary
-    int64_t best_size = 0, best_gid = 0;
-    auto consider = [&](int64_t size, int64_t gid) {
-        if (size > best_size || (size == best_size && size > 0 && gid < best_gid)) { best_size = size; best_gid = gid; }
-    };
-    for (int r = 0; r < nranks; ++r) {
-        const int64_t* sc = gathered + r * W + L.scalars();
-        out->ncl += sc[0];
-        out->nlone += sc[1];
-        // the rank's largest cluster; if it is an interface cluster its class (below) supersedes it
-        int k = index_of(node_key(r, sc[3]));
-        if (k < 0) consider(sc[2], sc[3]);
-    }
-    for (size_t c = 0; c < nodes.size(); ++c) {
-        if (parent[c] != (int)c) continue;
-        out->ncl -= cpos[c] - (ctot[c] > 0 ? 1 : 0);              // the members were counted once per rank
-        consider(ctot[c], cgid[c]);
-    }
-    out->maxcs = best_size; out->maxgid = best_gid;
-    // 5. spanning: the class reaches row 0 (canonical label <= m) and a site of the top row
-    {
-        const int64_t* top = gathered + (nranks - 1) * W + L.rowTop();
-        std::vector<int> cls;
-        for (int x = 0; x < m; ++x) {
-            if (!top[x] || (x > 0 && top[x] == top[x - 1])) continue;
-            int k = index_of(node_key(nranks - 1, top[x]));
-            if (k < 0) continue;
-            int c = uf_find(parent, k);
-            if (cgid[c] <= m) cls.push_back(c);
-        }
-        std::sort(cls.begin(), cls.end());
-        cls.erase(std::unique(cls.begin(), cls.end()), cls.end());
-        std::vector<std::pair<int64_t, int64_t>> sp;
-        for (int c : cls) sp.push_back({cgid[c], ctot[c]});
-        std::sort(sp.begin(), sp.end());
-        for (auto& e : sp) { out->span_gid.push_back(e.first); out->span_size.push_back(e.second); }
-    }
-    // 6. this rank's interface clusters: representative = its smallest root of the class
-    std::unordered_map<int, int64_t> rep;                        // class -> smallest root id of this rank
-    const int64_t klo = node_key(rank, 0), khi = node_key(rank + 1, 0);
-    for (size_t k = 0; k < nodes.size(); ++k) {
-        if (nodes[k].key < klo || nodes[k].key >= khi) continue;
-        int c = uf_find(parent, (int)k);
-        int64_t gid = nodes[k].key & MASK40;
-        auto it = rep.find(c);
-        if (it == rep.end() || gid < it->second) rep[c] = gid;
-    }
-    for (size_t k = 0; k < nodes.size(); ++k) {
-        if (nodes[k].key < klo || nodes[k].key >= khi) continue;
-        int c = uf_find(parent, (int)k);
-        out->root_gid.push_back(nodes[k].key & MASK40);
-        out->rep_gid.push_back(rep[c]);
-        out->class_gid.push_back(cgid[c]);
-        out->class_total.push_back(ctot[c]);
-    }
+    StitchTab T{};
+    T.H = stitch_table_size(nranks, m, &T.logH);
+    T.cap = 2 * m;
+    std::vector<int64_t> keys(T.H), hsize(T.H), span(2 * MAX_SPAN_CLASSES), pairs(4 * (size_t)T.cap);
+    std::vector<int32_t> parent(T.H), cpos(T.H), flag(T.H);
+    std::vector<unsigned long long> cgid(T.H), rep(T.H);
+    std::vector<long long> ctot(T.H), scal(8);
+    T.keys = keys.data(); T.hsize = hsize.data(); T.parent = parent.data(); T.cgid = cgid.data(); T.ctot = ctot.data();
+    T.cpos = cpos.data(); T.rep = rep.data(); T.flag = flag.data(); T.out = scal.data(); T.span = span.data(); T.pairs = pairs.data();
+    unsigned long long maxgid = STITCH_NONE;
+    for (int s = 0; s < T.H; ++s) stitch_clear(T, s);
+    for (int64_t e = 0; e < 2 * (int64_t)nranks * m; ++e) stitch_nodes(T, nranks, m, gathered, e);
+    for (int64_t e = (int64_t)nranks * m - 1; e >= 0; --e) stitch_unions(T, nranks, m, gathered, e);       // any order must work
+    for (int s = 0; s < T.H; ++s) stitch_classes(T, rank, s);
+    for (int s = 0; s < T.H; ++s) stitch_summary_a(T, s);
+    for (int r = 0; r < nranks; ++r) stitch_summary_rank(T, m, gathered, r);
+    for (int s = 0; s < T.H; ++s) stitch_summary_b(T, s, &maxgid);
+    for (int r = 0; r < nranks; ++r) stitch_summary_rank_b(T, m, gathered, r, &maxgid);
+    for (int x = 0; x < m; ++x) stitch_span(T, nranks, m, gathered, x);
+    for (int s = 0; s < T.H; ++s) stitch_mine(T, rank, s, nullptr, 0);
+    stitch_collect(T, scal.data(), maxgid, span.data(), pairs.data(), m, nranks, gathered, out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -279,13 +226,6 @@ slab_rootcount_kernel(const int32_t* __restrict__ label, const int32_t* __restri
     if (best) atomicMax(&sum->maxpack, best);
 }
 
-// point every interface root of a class at the class representative of this rank
-__global__ void slab_relabel_kernel(int npairs, const int32_t* __restrict__ root, const int32_t* __restrict__ rep, int32_t* __restrict__ label)
-{
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < npairs && root[k] != rep[k]) label[root[k]] = rep[k] + 1;
-}
-
 __global__ void __launch_bounds__(256)
 slab_flatten_kernel(int64_t t, int32_t* label)
 {
@@ -326,7 +266,74 @@ int slab_count_roots(Ctx* c)
     return (int)cudaGetLastError();
 }
 
-// all-gather of the interface rows, redundant host union-find, relabel
+// the stitch phases as kernels: one thread per item
+__global__ void k_stitch_clear(StitchTab T) { int s = blockIdx.x * blockDim.x + threadIdx.x; if (s < T.H) stitch_clear(T, s); }
+__global__ void k_stitch_nodes(StitchTab T, int nranks, int m, const int64_t* __restrict__ gathered)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < 2 * (int64_t)nranks * m) stitch_nodes(T, nranks, m, gathered, e);
+}
+__global__ void k_stitch_unions(StitchTab T, int nranks, int m, const int64_t* __restrict__ gathered)
+{
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < (int64_t)nranks * m) stitch_unions(T, nranks, m, gathered, e);
+}
+__global__ void k_stitch_classes(StitchTab T, int rank) { int s = blockIdx.x * blockDim.x + threadIdx.x; if (s < T.H) stitch_classes(T, rank, s); }
+__global__ void k_stitch_summary_a(StitchTab T, int nranks, int m, const int64_t* __restrict__ gathered)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < T.H) stitch_summary_a(T, s);
+    if (s < nranks) stitch_summary_rank(T, m, gathered, s);
+}
+__global__ void k_stitch_summary_b(StitchTab T, int nranks, int m, const int64_t* __restrict__ gathered, unsigned long long* maxgid)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < T.H) stitch_summary_b(T, s, maxgid);
+    if (s < nranks) stitch_summary_rank_b(T, m, gathered, s, maxgid);
+}
+__global__ void k_stitch_span(StitchTab T, int nranks, int m, const int64_t* __restrict__ gathered)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < m) stitch_span(T, nranks, m, gathered, x);
+}
+__global__ void k_stitch_mine(StitchTab T, int rank, int32_t* label, int64_t off)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < T.H) stitch_mine(T, rank, s, label, off);
+}
+
+// device scratch of the stitch: one allocation, carved into the table's arrays
+static int stitch_device_table(Ctx* c, StitchTab* T, unsigned long long** maxgid)
+{
+    const Geom& g = c->g;
+    T->H = stitch_table_size(c->nranks, g.m, &T->logH);
+    T->cap = 2 * g.m;
+    const size_t H = (size_t)T->H;
+    const size_t bytes = H * (8 + 8 + 4 + 8 + 8 + 4 + 8 + 4) + 8 * 8 + 8 + sizeof(int64_t) * 2 * MAX_SPAN_CLASSES + sizeof(int64_t) * 4 * (size_t)T->cap + 256;
+    if (bytes > c->d_stitch_bytes) {
+        if (c->d_stitch) cudaFree(c->d_stitch);
+        c->d_stitch = nullptr; c->d_stitch_bytes = 0;
+        PERC_CUDA(cudaMalloc(&c->d_stitch, bytes));
+        c->d_stitch_bytes = bytes;
+    }
+    char* p = (char*)c->d_stitch;
+    T->keys = (int64_t*)p; p += 8 * H;
+    T->hsize = (int64_t*)p; p += 8 * H;
+    T->cgid = (unsigned long long*)p; p += 8 * H;
+    T->ctot = (long long*)p; p += 8 * H;
+    T->rep = (unsigned long long*)p; p += 8 * H;
+    T->out = (long long*)p; p += 8 * 8;
+    *maxgid = (unsigned long long*)p; p += 8;
+    T->span = (int64_t*)p; p += sizeof(int64_t) * 2 * MAX_SPAN_CLASSES;
+    T->pairs = (int64_t*)p; p += sizeof(int64_t) * 4 * (size_t)T->cap;
+    T->parent = (int32_t*)p; p += 4 * H;
+    T->cpos = (int32_t*)p; p += 4 * H;
+    T->flag = (int32_t*)p; p += 4 * H;
+    return 0;
+}
+
+// all-gather of the interface rows, then the union-find of slab_stitch.cuh on the device (every rank runs the
+// same stitch redundantly: no second exchange) and the relabel of this rank's interface roots
 int slab_stitch(Ctx* c)
 {
     const Geom& g = c->g;
@@ -335,7 +342,7 @@ int slab_stitch(Ctx* c)
     cudaStream_t st = c->stream;
     if (!c->d_iface) {
         PERC_CUDA(cudaMalloc(&c->d_iface, sizeof(int64_t) * W * (c->nranks + 1)));
-        PERC_CUDA(cudaMallocHost(&c->h_iface, sizeof(int64_t) * W * c->nranks));
+        PERC_CUDA(cudaMallocHost(&c->h_iface, sizeof(int64_t) * (W * c->nranks + 4 * (size_t)(2 * g.m) + 2 * MAX_SPAN_CLASSES + 16)));
     }
     int64_t* mine = c->d_iface + W * c->nranks;
     slab_iface_kernel<<<nblk(g.m), 256, 0, st>>>(g, c->rank, c->nranks, c->label, c->size, mine);
@@ -345,31 +352,45 @@ int slab_stitch(Ctx* c)
         if (!c->comm) return -4;
         PERC_NCCL(g_nccl.AllGather(mine, c->d_iface, (size_t)W, NCCL_INT64, (NcclComm)c->comm, st));
     } else PERC_CUDA(cudaMemcpyAsync(c->d_iface, mine, sizeof(int64_t) * W, cudaMemcpyDeviceToDevice, st));
+
+    StitchTab T{};
+    unsigned long long* d_maxgid = nullptr;
+    int rc = stitch_device_table(c, &T, &d_maxgid);
+    if (rc) return rc;
+    const int64_t off = (int64_t)g.y0 * g.m;
+    k_stitch_clear<<<nblk(T.H), 256, 0, st>>>(T);
+    PERC_CUDA(cudaMemsetAsync(d_maxgid, 0xff, sizeof(unsigned long long), st));
+    k_stitch_nodes<<<nblk(2 * (int64_t)c->nranks * g.m), 256, 0, st>>>(T, c->nranks, g.m, c->d_iface);
+    k_stitch_unions<<<nblk((int64_t)c->nranks * g.m), 256, 0, st>>>(T, c->nranks, g.m, c->d_iface);
+    k_stitch_classes<<<nblk(T.H), 256, 0, st>>>(T, c->rank);
+    k_stitch_summary_a<<<nblk(T.H), 256, 0, st>>>(T, c->nranks, g.m, c->d_iface);
+    k_stitch_summary_b<<<nblk(T.H), 256, 0, st>>>(T, c->nranks, g.m, c->d_iface, d_maxgid);
+    k_stitch_span<<<nblk(g.m), 256, 0, st>>>(T, c->nranks, g.m, c->d_iface);
+    k_stitch_mine<<<nblk(T.H), 256, 0, st>>>(T, c->rank, c->label, off);
+    slab_flatten_kernel<<<nblk(g.t), 256, 0, st>>>(g.t, c->label);
+    c->launches += 9;
+    // results: scalars + largest label + spanning classes + this rank's (root, representative, label, size) list
+    int64_t* h_sc = c->h_iface + W * c->nranks;            // [8] out, [1] maxgid, spans, pairs
+    PERC_CUDA(cudaMemcpyAsync(h_sc, T.out, sizeof(long long) * 8 + 8 + sizeof(int64_t) * 2 * MAX_SPAN_CLASSES, cudaMemcpyDeviceToHost, st));
     PERC_CUDA(cudaMemcpyAsync(c->h_iface, c->d_iface, sizeof(int64_t) * W * c->nranks, cudaMemcpyDeviceToHost, st));
     PERC_CUDA(cudaStreamSynchronize(st));
-    StitchResult& R = c->stitch;
-    stitch_host(c->nranks, c->rank, g.m, c->h_iface, &R);
-    if (R.error) return -8;
-    // relabel: interface roots of one class -> the class representative of this rank
-    const int np = (int)R.root_gid.size();
-    const int64_t off = (int64_t)g.y0 * g.m;
-    c->tab_rep.clear(); c->tab_gid.clear(); c->tab_total.clear();
+    const long long* out = (const long long*)h_sc;
+    const int np = (int)(out[4] < T.cap ? out[4] : T.cap);
+    int64_t* h_pairs = h_sc + 9 + 2 * MAX_SPAN_CLASSES;
     if (np) {
-        std::vector<int32_t> h(2 * (size_t)np);
-        for (int k = 0; k < np; ++k) { h[k] = (int32_t)(R.root_gid[k] - off - 1); h[np + k] = (int32_t)(R.rep_gid[k] - off - 1); }
-        int32_t* d = (int32_t*)ctx_dev_stage(c, sizeof(int32_t) * 2 * np + sizeof(int64_t) * np + 64);
-        if (!d) return (int)cudaErrorMemoryAllocation;
-        PERC_CUDA(cudaMemcpyAsync(d, h.data(), sizeof(int32_t) * 2 * np, cudaMemcpyHostToDevice, st));
-        slab_relabel_kernel<<<nblk(np), 256, 0, st>>>(np, d, d + np, c->label);
-        slab_flatten_kernel<<<nblk(g.t), 256, 0, st>>>(g.t, c->label);
-        c->launches += 2;
+        PERC_CUDA(cudaMemcpyAsync(h_pairs, T.pairs, sizeof(int64_t) * 4 * (size_t)np, cudaMemcpyDeviceToHost, st));
         PERC_CUDA(cudaStreamSynchronize(st));
-        // table rep -> (class label, class size), ascending rep
-        std::vector<std::pair<int32_t, int>> reps;
-        for (int k = 0; k < np; ++k) if (R.root_gid[k] == R.rep_gid[k]) reps.push_back({(int32_t)(R.rep_gid[k] - off - 1), k});
-        std::sort(reps.begin(), reps.end());
-        for (auto& e : reps) { c->tab_rep.push_back(e.first); c->tab_gid.push_back(R.class_gid[e.second]); c->tab_total.push_back(R.class_total[e.second]); }
     }
+    StitchResult& R = c->stitch;
+    stitch_collect(T, out, (unsigned long long)h_sc[8], h_sc + 9, h_pairs, g.m, c->nranks, c->h_iface, &R);
+    if (R.error) return -8;
+    // table representative -> (class label, class size), ascending representative
+    c->tab_rep.clear(); c->tab_gid.clear(); c->tab_total.clear();
+    std::vector<std::pair<int32_t, int>> reps;
+    for (int k = 0; k < (int)R.root_gid.size(); ++k)
+        if (R.root_gid[k] == R.rep_gid[k]) reps.push_back({(int32_t)(R.rep_gid[k] - off - 1), k});
+    std::sort(reps.begin(), reps.end());
+    for (auto& e : reps) { c->tab_rep.push_back(e.first); c->tab_gid.push_back(R.class_gid[e.second]); c->tab_total.push_back(R.class_total[e.second]); }
     return 0;
 }
 

@@ -3,10 +3,11 @@
 // Every rank labels its slab (+ one halo row on each inner side) on its own; the clusters are then
 // stitched across the G-1 interfaces: one NCCL all-gather of each rank's interface rows (the label of
 // every site as a lattice-wide id, and the rank-local size of that cluster), after which EVERY rank
-// runs the same small union-find over the interface labels on the host (redundantly: no second
-// exchange, no iteration until quiescence) and relabels its own sites.  The Kirchhoff solve exchanges
-// one halo row of the residual per iteration with the slab below / above (ncclSend / ncclRecv over
-// NVLink) and all-reduces the two dot products.
+// runs the same small union-find over the interface labels on its GPU (slab_stitch.cuh: hash table of
+// the (rank, cluster) nodes, atomicMin unions; redundantly on every rank: no second exchange, no
+// iteration until quiescence) and relabels its own sites.  The Kirchhoff solve exchanges one halo row
+// of the residual per iteration with the slab below / above (ncclSend / ncclRecv over NVLink) and
+// all-reduces the two dot products.
 #pragma once
 #include <stdint.h>
 #include <vector>
@@ -38,7 +39,8 @@ struct StitchResult {
     int error = 0;                                   // != 0: the ranks disagree on the occupancy of an interface row
 };
 
-// pure host code (also exported through the C-ABI as perc_stitch_host for the CPU tests)
+// the stitch's item functions (slab_stitch.cuh) run one by one on the host: exported through the C-ABI as
+// perc_stitch_host so that the CPU tests exercise the very code the kernels execute
 void stitch_host(int nranks, int rank, int m, const int64_t* gathered, StitchResult* out);
 
 }  // namespace perc
