@@ -47,3 +47,61 @@ def test_literal_bicg_equals_pcg_and_conserves_current(O, lat):
         assert chk["err"] < 1e-12 and chk["Gtop"] == c1["Gtop"]
         return
     pytest.fail("no spanning realization among the seeds")
+
+
+# ---- second implementation: the reference's own MATLAB route (direct solve) ---------------------
+def direct_solve(m, n, b1, b2, w, Va=1.0, read_thresh=1e-10):
+    """MATLAB/ConductCalc.m:150-196 restated with scipy: full conductance matrix G (off-diagonals -w, diagonal
+    = minus the row sum), interior block solved directly (`Gtemp\\Itemp`), I = G V, Gtop / Gbot from the
+    currents of the top / bottom row.  The Fortran read-out keeps the full diagonal but drops off-diagonals
+    below 1e-10 (second sprsin, Sq/bondc.f:576); `read_thresh` applies that rule so both routes are comparable."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    t = m * n
+    i, j = b1.astype(np.int64) - 1, b2.astype(np.int64) - 1
+    off = sp.coo_matrix((np.concatenate([-w, -w]), (np.concatenate([i, j]), np.concatenate([j, i]))), shape=(t, t)).tocsr()
+    diag = -np.asarray(off.sum(axis=1)).ravel()
+    G = off + sp.diags(diag)
+    inner = np.arange(m, t - m)
+    top = np.arange(t - m, t)
+    Gii = G[inner][:, inner].tocsc()
+    rhs = -np.asarray(G[inner][:, top].sum(axis=1)).ravel() * Va
+    Vint = spla.spsolve(Gii, rhs)
+    V = np.zeros(t)
+    V[inner] = Vint
+    V[top] = Va
+    keep = off.copy()
+    keep.data[np.abs(keep.data) < read_thresh] = 0.0
+    I = (keep + sp.diags(diag)) @ V
+    return I[top].sum() / Va, abs(I[:m].sum()) / Va, Vint
+
+
+@pytest.mark.parametrize("lat,kind,pbc", [(1, 2, 0), (2, 2, 1), (1, 1, 0), (2, 1, 0), (1, 3, 1), (2, 3, 0)])
+def test_oracle_conductance_equals_direct_solve(O, lat, kind, pbc):
+    """pins the oracle's Kirchhoff solve (literal linbcg recurrences, leak bonds, read-out threshold) against an
+    independent direct solve of the same matrix -- the route the reference's MATLAB post-processing takes"""
+    m, n = 24, 20
+    t = m * n
+    b1, b2 = O.bondlist(lat, m, n, pbc)
+    nb = len(b1)
+    rng = np.random.default_rng(17 * lat + kind + pbc)
+    done = 0
+    for trial in range(12):
+        ps, pb = (0.66 if lat == 1 else 0.56), (0.56 if lat == 1 else 0.40)
+        if kind == 3:
+            ps, pb = 0.9, (0.62 if lat == 1 else 0.45)
+        socc = (rng.random(t) < ps).astype(np.uint8) if kind != 2 else None
+        bocc = (rng.random(nb) < pb).astype(np.uint8) if kind != 1 else None
+        ws, wb, wsz, ncl, wmax = O.label_uf(kind, lat, m, n, pbc, b1, b2, site_occ=socc, bond_occ=bocc)
+        ids = O.spanning(kind, m, n, b1, b2, ws, wb)
+        if not len(ids):
+            continue
+        w = O.weights(kind, b1, b2, ws, wb, int(ids[0]))
+        got = O.conduct_cg(m, n, b1, b2, w, tol=1e-14, itmax=200000)
+        Gtop, Gbot, Vint = direct_solve(m, n, b1, b2, w)
+        assert abs(got["Gtop"] - Gtop) <= 1e-9 * abs(Gtop) and abs(got["Gbot"] - Gbot) <= 1e-9 * abs(Gbot)
+        assert np.abs(got["Vint"] - Vint).max() <= 1e-8
+        done += 1
+        if done == 2:
+            break
+    assert done >= 1
