@@ -5,7 +5,7 @@ Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 
 mixed site/bond percolation, L = 4096, ps = 0.80, pb = 0.70 (about 4 % above the bond threshold
 at that ps), one "step" = one realization: occupancy (K1 Philox generator, exact counts) ->
 cluster labeling + sizes + spanning (K2-K5) -> Kirchhoff conductance of the spanning cluster
-(K6-K8 Jacobi-PCG, fp64, tol 1e-10).  Metric: conductance realizations / s.
+(K6-K8 Jacobi-PCG, fp64, tol 1e-10; one-pass iteration kernel by default, --solver classic for the two-kernel form).  Metric: conductance realizations / s.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, through the C-ABI)
   python bench.py --impl reference ...                            CPU arm: the oracle port of the
@@ -233,7 +233,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    stats = {"G": [], "iters": [], "spmv_ms": [], "upd_ms": [], "ccl_ms": [], "pcg_ms": [], "nspan": []}
+    stats = {"G": [], "iters": [], "spmv_ms": [], "upd_ms": [], "ccl_ms": [], "pcg_ms": [], "nspan": [], "fused": []}
+    if args.solver != "auto":
+        L.set_solver(1 if args.solver == "classic" else 0)
 
     def step(i, record):
         L.generate(SEED, stream_id(rank, i), ks, kb)
@@ -248,6 +250,7 @@ def run_ours(args):
             stats["spmv_ms"].append(float(ph2[6]))
             stats["upd_ms"].append(float(ph2[7]))
             stats["pcg_ms"].append(float(ph2[5]))
+            stats["fused"].append(L.solver_used())
         return r
 
     for i in range(args.warmup):
@@ -329,7 +332,17 @@ def run_ours(args):
         spmv_ms = float(np.mean(stats["spmv_ms"]))
         upd_ms = float(np.mean(stats["upd_ms"]))
         ccl_ms = float(np.mean(stats["ccl_ms"]))
-        spmv_bytes = 25.0 * interior          # r 8 + p_old 8 + conduct byte 1 read; p 8 written (q = A p is never stored)
+        fused = bool(stats["fused"]) and all(stats["fused"])
+        if fused:
+            # one-pass iteration kernel: r 8 + s 8 + conduct byte 1 read; r 8 + s 8 written
+            spmv_bytes = 33.0 * interior
+            roof_key = "pcg_fused_kernel"
+            roof_name = ("pcg_fused_kernel (one Jacobi-PCG iteration in one persistent TMA-fed pass: s = A D^-1 r + beta s, "
+                         "r -= alpha s, sums r.r/d, r.r and the bond energy of D^-1 r; p and x only on the read-out rows)")
+        else:
+            spmv_bytes = 25.0 * interior          # r 8 + p_old 8 + conduct byte 1 read; p 8 written (q = A p is never stored)
+            roof_key = "pcg_pipe_kernel<0>"
+            roof_name = "pcg_pipe_kernel<0> (persistent TMA tile pipeline: p = r/d + bk p, p.Ap as bond energies; q = A p is never stored)"
         upd_bytes = (41.0 if args.voltages else 25.0) * interior   # p 8 + r 8 + byte read, r 8 written (+ x 8 + 8)
         ach = spmv_bytes / (spmv_ms * 1e-3) / 1e9
         value = world * args.steps / (ms_total * 1e-3)
@@ -343,14 +356,13 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 4 * t + 8 * nb,
                     "d2h_bytes_per_step": 8 * t + 4 * nb + 64, "steps": e2e_steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "pcg_pipe_kernel<0> (persistent TMA tile pipeline: p = r/d + bk p, p.Ap as bond energies; q = A p is never stored)",
+            "roofline": {"bound": "hbm", "kernel": roof_name,
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": ncu_traffic_bytes("pcg_pipe_kernel<0>") if Lsz == 4096 else None,
+                         "traffic": ncu_traffic_bytes(roof_key) if Lsz == 4096 else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
                          "avg_launch_ms": spmv_ms},
             "extra": {
-                "pcg_pipe_kernel<1> (residual update, A p recomputed)": {"achieved_gbs": upd_bytes / (upd_ms * 1e-3) / 1e9,
-                                      "frac": upd_bytes / (upd_ms * 1e-3) / 1e9 / peak, "avg_launch_ms": upd_ms},
+                "pcg_solver": "one-pass (33 B per site and iteration)" if fused else "two-kernel (50 B per site and iteration)",
                 "ccl": {"gsites_per_s": t / (ccl_ms * 1e-3) / 1e9, "ms": ccl_ms,
                         "achieved_gbs": 5.0 * t / (ccl_ms * 1e-3) / 1e9, "frac": 5.0 * t / (ccl_ms * 1e-3) / 1e9 / peak},
                 "mean_pcg_iterations": mean_iters, "mean_G": st[0] / max(st[2], 1),
@@ -358,6 +370,10 @@ def run_ours(args):
                 "realizations": int(st[2]),
             },
         }
+        if not fused and upd_ms > 0:
+            line["extra"]["pcg_pipe_kernel<1> (residual update, A p recomputed)"] = {
+                "achieved_gbs": upd_bytes / (upd_ms * 1e-3) / 1e9, "frac": upd_bytes / (upd_ms * 1e-3) / 1e9 / peak,
+                "avg_launch_ms": upd_ms}
         if world == 1 and not args.no_cpu_baseline:
             socc, bocc = L.get_occupancy()
             nthreads = max(1, min(os.cpu_count() or 1, args.cpu_threads))
@@ -396,6 +412,8 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=16, help="host threads of the CPU arm (capped at the core count)")
     ap.add_argument("--cpu-cg-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--solver", default="auto", choices=["auto", "classic"],
+                    help="auto: the one-pass iteration kernel (perc_set_solver 0); classic: the two-kernel form")
     ap.add_argument("--voltages", action="store_true",
                     help="form the interior voltages too (perc_conduct instead of perc_conduct_g; same G)")
     args = ap.parse_args()

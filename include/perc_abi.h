@@ -190,12 +190,23 @@ int32_t perc_batch_conduct(const int64_t *h, const int32_t *kind, const int32_t 
 int32_t perc_comm_init_rank(const int64_t *h, const int32_t *nranks, const int32_t *rank, const uint8_t *id128);
 int32_t perc_allreduce_stats(const int64_t *h, const int32_t *ni, int64_t *ivals, const int32_t *nd, double *dvals);
 
+/* ---- solver selection --------------------------------------------------------------------------- */
+/* Iteration kernels of the conductance solve (the body of linbcg's loop, Sq/bondc.f:780-833):
+ *   mode 0 (default): automatic -- perc_conduct_g on one GPU without periodic wrap runs the ONE-PASS kernel
+ *           (Chronopoulos-Gear form of the same Jacobi-PCG recurrences, one reduction per iteration, 33 B per
+ *           site and iteration); every other call runs the two-kernel form;
+ *   mode 1: always the two-kernel form (50 B per site and iteration; iter is linbcg's count exactly).
+ * The process-wide default can be set with the environment variable PERC_PCG_SOLVER=classic|fused.
+ * perc_solver_used reports which one the handle's last solve ran (1 = one-pass kernel). */
+int32_t perc_set_solver(const int64_t *h, const int32_t *mode);
+int32_t perc_solver_used(const int64_t *h, int32_t *fused);
+
 /* ---- instrumentation ---------------------------------------------------------------------------- */
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 int32_t perc_launch_count(const int64_t *h, int64_t *count);
 /* device time (ms, CUDA events on the handle's stream) of the last call's phases:
  * 0 mask build, 1 CCL local, 2 CCL merge, 3 CCL flatten+sizes, 4 spanning, 5 PCG total,
- * 6 PCG SpMV kernel avg, 7 PCG update kernel avg */
+ * 6 PCG SpMV kernel avg, 7 PCG update kernel avg (one-pass solver: 6 = the iteration kernel, 7 = 0) */
 int32_t perc_phase_ms(const int64_t *h, const int32_t *nphase, float *ms);
 /* raw stream handle (cudaStream_t) so a host can order its own work against the library's */
 int32_t perc_stream(const int64_t *h, uint64_t *stream);

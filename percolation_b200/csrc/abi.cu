@@ -106,7 +106,7 @@ void ctx_free(Ctx* c)
     if (c->d_stitch) cudaFree(c->d_stitch);
     if (c->h_iface) cudaFreeHost(c->h_iface);
     void* ptrs[] = {c->srank, c->brank, c->mask, c->label, c->size, c->rootlist, c->d_sum, c->d_pcg,
-                    c->d_hist, c->d_thr, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vp2, c->vq, c->partial, c->d_stage};
+                    c->d_hist, c->d_thr, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vp2, c->vq, c->xprow, c->partial, c->d_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_pcg) cudaFreeHost(c->h_pcg);
     if (c->h_sum_pin) cudaFreeHost(c->h_sum_pin);
@@ -738,6 +738,23 @@ int32_t perc_phase_ms(const int64_t* h, const int32_t* nphase, float* ms)
     GET_CTX(h);
     if (!nphase || !ms) return PERC_E_ARG;
     for (int k = 0; k < *nphase && k < 8; ++k) ms[k] = c->phase_ms[k];
+    return 0;
+}
+
+int32_t perc_set_solver(const int64_t* h, const int32_t* mode)
+{
+    GET_CTX(h);
+    if (!mode || *mode < 0 || *mode > 1) return PERC_E_ARG;
+    c->pcg_mode = *mode;
+    for (Ctx* k : c->batch_kids) k->pcg_mode = *mode;
+    return 0;
+}
+
+int32_t perc_solver_used(const int64_t* h, int32_t* fused)
+{
+    GET_CTX(h);
+    if (!fused) return PERC_E_ARG;
+    *fused = c->last_fused ? 1 : 0;
     return 0;
 }
 

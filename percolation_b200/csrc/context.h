@@ -77,6 +77,9 @@ struct Ctx {
     double* vp = nullptr;
     double* vp2 = nullptr;        // p is double-buffered (the fused SpMV reads neighbours' old p)
     double* vq = nullptr;
+    double* xprow = nullptr;      // [4 m] one-pass solver: x and p of rows 1 and n-2 (the rows the read-out consumes)
+    int pcg_mode = -1;            // -1 process default, 0 automatic (one-pass kernel when it applies), 1 two-kernel form
+    bool last_fused = false;      // the last solve ran the one-pass kernel
     double* partial = nullptr;    // per-block partial sums
     int partial_cap = 0;
     PcgState* d_pcg = nullptr;
@@ -147,6 +150,7 @@ int pcg_small_solve(Ctx* c, const uint8_t* cfbatch, int nreal, double Va, double
 int batch_conduct_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsigned long long stream0, int64_t ks, int64_t kb,
                       double Va, double g0, double gleak, double tol, int itmax, double read_thresh,
                       double* G, int32_t* iters, int64_t* stats);
+bool pcg_fused_applies(const Ctx* c, int keep_x, int warm);
 int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double tol, int itmax,
               double read_thresh, int keep_x, double* Gtop, double* Gbot, int* iter, double* err, int warm = 0);
 

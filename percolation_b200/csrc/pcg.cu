@@ -18,8 +18,11 @@
 // Reductions are two-stage and fixed-order (per-block partial, last block folds them), so a
 // solve is bit-reproducible for a given lattice size.
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <cuda.h>
 #include "context.h"
+#include "pcg_fused_tile.cuh"
 
 namespace perc {
 
@@ -655,6 +658,113 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K6+K7 in one pass (pcg_fused_tile.cuh): the whole iteration in ONE persistent TMA-fed kernel with ONE
+// grid-wide reduction.  Same pipeline as pcg_pipe_kernel (one CTA per SM, two shared-memory stages, one
+// thread issues the three tensor copies of the next tile while the CTA computes the current one); the
+// per-tile arithmetic lives in pcg_fused_tile.cuh, shared with the host emulation of the CPU tests.
+//   HBM traffic per site and iteration: r 8 + s 8 + conduct byte 1 read, r 8 + s 8 written = 33 B.
+// Single GPU, no periodic wrap, Gtop / Gbot only (x and p exist on rows 1 and n-2: xrow / prow, 2 m doubles
+// each); everything else takes the two-kernel path.  Consecutive iterations sweep the tiles in opposite
+// directions, so each starts on the part of r / s the previous one wrote last (still in L2).
+// ------------------------------------------------------------------------------------------
+constexpr size_t FT_SMEM = 2 * (size_t)FT_STAGE_BYTES + FT_R_BYTES + sizeof(FtDiag) * 64 * 32 + sizeof(double) * 96 + 16;
+static_assert(FT_SMEM <= 227 * 1024, "fused PCG tile does not fit the shared memory of one SM");
+
+// block sums of three values at once (fixed order); result valid in thread 0
+__device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double* sh)
+{
+    for (int o = 16; o; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        b += __shfl_down_sync(0xffffffffu, b, o);
+        c += __shfl_down_sync(0xffffffffu, c, o);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { sh[w] = a; sh[32 + w] = b; sh[64 + w] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x = 0.0, y = 0.0, z = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { x += sh[k]; y += sh[32 + k]; z += sh[64 + k]; }
+        a = x; b = y; c = z;
+    }
+}
+
+template <int LAT>
+__global__ void __launch_bounds__(FT_THREADS, 1)
+pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_s,
+                 const __grid_constant__ CUtensorMap tm_cf, Geom g, PcgParams prm, double* __restrict__ r_out,
+                 double* __restrict__ s_out, double* __restrict__ xrow, double* __restrict__ prow,
+                 double* __restrict__ partial, PcgState* __restrict__ st, int ntx, int ntiles, int rev, int prime)
+{
+    if (st->done) return;
+    extern __shared__ __align__(128) unsigned char ft_raw[];
+    double* su = reinterpret_cast<double*>(ft_raw + 2 * (size_t)FT_STAGE_BYTES);
+    FtDiag* dtab = reinterpret_cast<FtDiag*>(ft_raw + 2 * (size_t)FT_STAGE_BYTES + FT_R_BYTES);      // [64][32]
+    double* sh = reinterpret_cast<double*>(dtab + 64 * 32);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sh + 96);                      // one mbarrier per stage
+    const int tid = threadIdx.x;
+    for (int k = tid; k < 64 * 32; k += FT_THREADS) dtab[k] = ft_diag_entry(k >> 5, prm.g0, prm.gleak);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const FtScalars sc{prm.g0, prm.gleak, prime ? 0.0 : st->ak, prime ? 0.0 : st->bk};
+    auto tile_of = [&](int t) { return rev ? ntiles - 1 - t : t; };
+    auto stage_r = [&](int k) { return reinterpret_cast<double*>(ft_raw + (size_t)k * FT_STAGE_BYTES); };
+    auto stage_s = [&](int k) { return reinterpret_cast<double*>(ft_raw + (size_t)k * FT_STAGE_BYTES + FT_R_BYTES); };
+    auto stage_cf = [&](int k) { return reinterpret_cast<uint8_t*>(ft_raw + (size_t)k * FT_STAGE_BYTES + FT_R_BYTES + FT_S_BYTES); };
+    // one thread, three TMA tensor copies: r (tile + 2-site halo), s (tile + east / north / west ring), conduct bytes
+    auto issue = [&](int k, int tl) {
+        if (tid != 0) return;
+        const int x0 = (tl % ntx) * FT_TX, y0 = (tl / ntx) * FT_TY;
+        mbar_arrive_expect(&bars[k], (unsigned)(FT_RR * FT_LD * 8 + FT_SR * FT_LD * 8 + FT_RR * FT_CLD));
+        tma_box_g2s(stage_r(k), &tm_r, x0 - 2, y0 - 1, &bars[k]);
+        tma_box_g2s(stage_s(k), &tm_s, x0 - 2, y0, &bars[k]);
+        tma_box_g2s(stage_cf(k), &tm_cf, x0 - 16, y0 - 1, &bars[k]);
+    };
+
+    int t = blockIdx.x;
+    if (t < ntiles) issue(0, tile_of(t));
+    for (int k = 0; t < ntiles; t += gridDim.x, ++k) {
+        const int tl = tile_of(t), x0 = (tl % ntx) * FT_TX, y0 = (tl / ntx) * FT_TY;
+        const int tn = t + gridDim.x;
+        if (tn < ntiles) issue((k + 1) & 1, tile_of(tn));      // the other stage was released by the barriers of the last tile
+        mbar_wait(&bars[k & 1], (unsigned)((k >> 1) & 1));
+        const double* sr = stage_r(k & 1);
+        double* ss = stage_s(k & 1);
+        const uint8_t* scf = stage_cf(k & 1);
+        const bool interior = ft_interior(g, x0, y0);
+        ft_phase_u<LAT>(g, sr, scf, su, dtab, x0, y0, interior, tid);
+        __syncthreads();
+        double rz = 0.0, rr = 0.0, en = 0.0;
+        ft_phase_main<LAT>(g, sc, sr, ss, scf, su, dtab, x0, y0, interior, tid, r_out, s_out, xrow, prow, rz, rr);
+        ft_phase_ringcols<LAT>(g, sc, sr, ss, scf, su, dtab, x0, y0, tid);
+        __syncthreads();
+        ft_phase_energy<LAT>(g, sc, ss, scf, x0, y0, interior, tid, en);
+        // generic-proxy accesses to this stage are ordered before the bulk copies that will refill it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        block_sum3(rz, rr, en, sh);                             // synchronises: every thread is done with the stage
+        if (tid == 0) { partial[tl * 3 + 0] = rz; partial[tl * 3 + 1] = rr; partial[tl * 3 + 2] = en; }
+    }
+    if (last_block(&st->ticket_a)) {
+        const double fz = fold_partials(partial, ntiles, 3, 0, sh);
+        const double fr = fold_partials(partial, ntiles, 3, 1, sh);
+        const double fe = fold_partials(partial, ntiles, 3, 2, sh);
+        if (threadIdx.x == 0) {
+            FtState f;
+            f.gamma = st->bknum; f.alpha = st->ak; f.beta = st->bk; f.bnrm = st->bnrm; f.err = st->err; f.rr = st->rr;
+            f.tol = st->tol; f.iter = st->iter; f.itmax = st->itmax; f.done = st->done;
+            ft_scalar_step(f, fz, fr, fe, prime);
+            st->bkden = st->bknum; st->akden = fe;
+            st->bknum = f.gamma; st->ak = f.alpha; st->bk = f.beta; st->err = f.err; st->rr = f.rr;
+            st->iter = f.iter; st->done = f.done;
+        }
+    }
+}
+
 // slab mode: the scalar recurrences, run by one thread after the all-reduce of the rank-local sums
 //   phase 0: after pcg_init (red = |D^-1 b|^2, b.z, b.b)   phase 1: after MODE 0 (akden)
 //   phase 2: after MODE 1 (red = r.z, r.r)                  phase 3: after the read-out (Itop, Ibot are summed in place)
@@ -908,7 +1018,7 @@ static unsigned nblk(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) /
 
 // 2-D TMA descriptor of a row-major (cols x rows) array; box = box_cols x PT_ROWS elements.  The driver entry
 // point is resolved at run time, so the library still links against nothing but the CUDA runtime.
-static int make_tensor_map(CUtensorMap* map, void* base, int elem_bytes, int cols, int rows, int box_cols)
+static int make_tensor_map(CUtensorMap* map, void* base, int elem_bytes, int cols, int rows, int box_cols, int box_rows = PT_ROWS)
 {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -924,12 +1034,101 @@ static int make_tensor_map(CUtensorMap* map, void* base, int elem_bytes, int col
     }
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)cols * elem_bytes};
-    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)PT_ROWS};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(map, elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : 900 + (int)r;
+}
+
+// which iteration kernel(s) a solve uses: 0 = automatic (one-pass kernel whenever it applies), 1 = always the
+// two-kernel form.  perc_set_solver sets it per handle; PERC_PCG_SOLVER=classic|fused sets the default of the process.
+static int pcg_default_mode()
+{
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("PERC_PCG_SOLVER");
+        mode = (e && !strcmp(e, "classic")) ? 1 : 0;
+    }
+    return mode;
+}
+
+bool pcg_fused_applies(const Ctx* c, int keep_x, int warm)
+{
+    const Geom& g = c->g;
+    const int mode = c->pcg_mode >= 0 ? c->pcg_mode : pcg_default_mode();
+    return mode == 0 && !keep_x && !warm && c->nranks == 1 && !g.pbc && (g.m % 16) == 0 && g.n >= 4;
+}
+
+// the iteration loop of the one-pass kernel; on entry (after pcg_init_kernel) vr = b, vp = vx = 0, the scalars of
+// the solve are initialised.  Buffers: r ping-pongs between vr and vp, s between vp2 and vx; x / p of rows 1 and
+// n-2 live in xprow and are copied into vx for the read-out at the end.
+static int pcg_fused_loop(Ctx* c, const PcgParams& prm)
+{
+    const Geom& g = c->g;
+    cudaStream_t s = c->stream;
+    const int ntx = (g.m + FT_TX - 1) / FT_TX, ntiles = ntx * ((g.n + FT_TY - 1) / FT_TY);
+    const int grid = ntiles < c->num_sms ? ntiles : c->num_sms;
+    if (!c->xprow) PERC_CUDA(cudaMalloc(&c->xprow, sizeof(double) * 4 * g.m));
+    PERC_CUDA(cudaMemsetAsync(c->xprow, 0, sizeof(double) * 4 * g.m, s));
+    PERC_CUDA(cudaMemsetAsync(c->vp2, 0, sizeof(double) * g.t, s));
+    static bool attr_set = false;
+    if (!attr_set) {
+        PERC_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<LAT_SQUARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        PERC_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<LAT_TRIANGULAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        attr_set = true;
+    }
+    double* rbuf[2] = {c->vr, c->vp};
+    double* sbuf[2] = {c->vp2, c->vx};
+    CUtensorMap tm_r[2], tm_s[2], tm_cf;
+    int rc;
+    for (int k = 0; k < 2; ++k) {
+        rc = make_tensor_map(&tm_r[k], rbuf[k], 8, g.m, g.n, FT_LD, FT_RR); if (rc) return rc;
+        rc = make_tensor_map(&tm_s[k], sbuf[k], 8, g.m, g.n, FT_LD, FT_SR); if (rc) return rc;
+    }
+    rc = make_tensor_map(&tm_cf, c->cfull, 1, g.m, g.n, FT_CLD, FT_RR); if (rc) return rc;
+    double* xrow = c->xprow; double* prow = c->xprow + 2 * (size_t)g.m;
+    int cur = 0, pass = 0;
+    auto launch = [&](int prime) {
+        if (g.lattice == LAT_SQUARE)
+            pcg_fused_kernel<LAT_SQUARE><<<grid, FT_THREADS, FT_SMEM, s>>>(tm_r[cur], tm_s[cur], tm_cf, g, prm, rbuf[cur ^ 1], sbuf[cur ^ 1],
+                                                                           xrow, prow, c->partial, c->d_pcg, ntx, ntiles, pass & 1, prime);
+        else
+            pcg_fused_kernel<LAT_TRIANGULAR><<<grid, FT_THREADS, FT_SMEM, s>>>(tm_r[cur], tm_s[cur], tm_cf, g, prm, rbuf[cur ^ 1], sbuf[cur ^ 1],
+                                                                               xrow, prow, c->partial, c->d_pcg, ntx, ntiles, pass & 1, prime);
+        cur ^= 1; ++pass;
+        c->launches++;
+    };
+    launch(1);                     // s = A D^-1 b and delta0: alpha0, beta0 = 0
+    float it_ms = 0.f; int nsamp = 0;
+    int chunk = 32, iters_before = 0;
+    for (;;) {
+        for (int k = 0; k < chunk; ++k) {
+            // one mid-chunk iteration is bracketed with events (the stream is busy there, so the bracket is the
+            // kernel's own device time)
+            const bool sample = (k == chunk / 2);
+            if (sample) PERC_CUDA(cudaEventRecord(c->ev[8], s));
+            launch(0);
+            if (sample) PERC_CUDA(cudaEventRecord(c->ev[9], s));
+        }
+        PERC_CUDA(cudaMemcpyAsync(c->h_pcg, c->d_pcg, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
+        PERC_CUDA(cudaStreamSynchronize(s));
+        if (!c->h_pcg->done || c->h_pcg->iter > iters_before + chunk / 2) {
+            float a = 0.f;
+            cudaEventElapsedTime(&a, c->ev[8], c->ev[9]);
+            it_ms += a; nsamp++;
+        }
+        iters_before = c->h_pcg->iter;
+        if (c->h_pcg->done) break;
+        if (chunk < 512) chunk *= 2;
+    }
+    // the read-out consumes x on rows 1 and n-2 (vx was an s buffer: dead now)
+    PERC_CUDA(cudaMemcpyAsync(c->vx + g.m, xrow, sizeof(double) * g.m, cudaMemcpyDeviceToDevice, s));
+    PERC_CUDA(cudaMemcpyAsync(c->vx + (int64_t)(g.n - 2) * g.m, xrow + g.m, sizeof(double) * g.m, cudaMemcpyDeviceToDevice, s));
+    c->phase_ms[6] = nsamp ? it_ms / nsamp : 0.f;
+    c->phase_ms[7] = 0.f;
+    return 0;
 }
 
 int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double tol, int itmax,
@@ -954,6 +1153,7 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     int need = (int)(sgrid.x * sgrid.y);
     if (need < ugrid * 3) need = ugrid * 3;
     if (need < 2 * ntiles) need = 2 * ntiles;
+    { const int nf = 3 * ((g.m + FT_TX - 1) / FT_TX) * ((g.n + FT_TY - 1) / FT_TY); if (need < nf) need = nf; }
     const int want_x = keep_x;
     if (!vec) keep_x = 1;                // the scalar fallback always forms x
     if (need > c->partial_cap) {
@@ -987,6 +1187,8 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
         rc = slab_halo_exchange(c, c->vr, 8); if (rc) return rc;                        // r = b on the halo rows
         c->launches++;
     }
+    const bool fused = pcg_fused_applies(c, keep_x, warm);
+    c->last_fused = fused;
     // TMA descriptors of the arrays the pipeline stages (row-major m x n, boxes of 34 rows)
     CUtensorMap tm_r{}, tm_pa{}, tm_pb{}, tm_cf{};
     if (vec) {
@@ -1009,6 +1211,10 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     double* pold = c->vp; double* pnew = c->vp2;
     float sp_ms = 0.f, up_ms = 0.f; int nsamp = 0;
     int chunk = 16, iters_before = 0;
+    if (fused) {
+        rc = pcg_fused_loop(c, prm);
+        if (rc) return rc;
+    } else
     for (;;) {
         for (int k = 0; k < chunk; ++k) {
             // bracket the two kernels of one mid-chunk iteration with events (the pipeline is full
@@ -1063,8 +1269,10 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     PERC_CUDA(cudaStreamSynchronize(s));
     PERC_CUDA(cudaGetLastError());
     cudaEventElapsedTime(&c->phase_ms[5], c->ev[6], c->ev[7]);
-    c->phase_ms[6] = nsamp ? sp_ms / nsamp : 0.f;
-    c->phase_ms[7] = nsamp ? up_ms / nsamp : 0.f;
+    if (!fused) {
+        c->phase_ms[6] = nsamp ? sp_ms / nsamp : 0.f;
+        c->phase_ms[7] = nsamp ? up_ms / nsamp : 0.f;
+    }
     *Gtop = c->h_pcg->Itop / Va;
     *Gbot = fabs(c->h_pcg->Ibot) / Va;
     *iter = c->h_pcg->iter;

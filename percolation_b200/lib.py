@@ -27,7 +27,7 @@ SYMBOLS = [
     "perc_generate", "perc_get_occupancy",
     "perc_label", "perc_summary", "perc_get_site_labels", "perc_get_bond_labels", "perc_get_sizes",
     "perc_span", "perc_hist", "perc_hist_log2", "perc_site", "perc_bond", "perc_sitebond", "perc_first_span",
-    "perc_conduct", "perc_conduct_warm", "perc_conduct_g", "perc_get_voltage", "perc_launch_count", "perc_phase_ms", "perc_stream",
+    "perc_conduct", "perc_conduct_warm", "perc_conduct_g", "perc_get_voltage", "perc_launch_count", "perc_phase_ms", "perc_stream", "perc_set_solver", "perc_solver_used",
     "perc_create_slab", "perc_comm_unique_id", "perc_comm_init", "perc_slab_rows", "perc_generate_i8",
     "perc_summary_i8", "perc_span_i8", "perc_get_site_labels_i8", "perc_stitch_host",
     "perc_batch", "perc_batch_conduct", "perc_comm_init_rank", "perc_allreduce_stats",
@@ -289,6 +289,16 @@ class Lattice:
         return v
 
     # ---- instrumentation
+    def set_solver(self, mode):
+        """0 = automatic (one-pass iteration kernel whenever it applies), 1 = always the two-kernel form"""
+        self._call("perc_set_solver", _i32(mode))
+
+    def solver_used(self):
+        """1 if the handle's last conductance solve ran the one-pass kernel"""
+        f = C.c_int32(0)
+        self._call("perc_solver_used", C.byref(f))
+        return f.value
+
     def launch_count(self):
         n = C.c_int64(0)
         self._call("perc_launch_count", C.byref(n))

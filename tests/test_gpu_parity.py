@@ -202,9 +202,23 @@ def test_conductance_vs_oracle(P, O, lat, kind, pbc, m, n):
             chk = O.conduct_check(m, n, b1, b2, w, L.voltage())
             assert chk["err"] <= 2e-13
             assert abs(chk["Gtop"] - got["Gtop"]) <= 1e-12 * abs(got["Gtop"])
-            # (d) the sweep-driver entry point (no interior voltages): bit-identical G, iter, err
+            # (d) the sweep-driver entry point (no interior voltages), two-kernel form: bit-identical G, iter, err
+            L.set_solver(1)
             gonly = L.conduct(cid, tol=1e-13, itmax=200000, voltages=False)
-            assert gonly == got
+            assert gonly == got and L.solver_used() == 0
+            # (e) ... and with the one-pass iteration kernel where it applies (same recurrences in the
+            # Chronopoulos-Gear arrangement): 1e-9 against the oracle, linbcg's iteration count
+            L.set_solver(0)
+            gf = L.conduct(cid, tol=1e-13, itmax=200000, voltages=False)
+            assert L.solver_used() == (1 if (pbc == 0 and m % 16 == 0) else 0)
+            assert gf["err"] <= 1e-13
+            assert abs(gf["Gtop"] - ref["Gtop"]) <= 1e-9 * abs(ref["Gtop"])
+            assert abs(gf["Gbot"] - ref["Gbot"]) <= 1e-9 * abs(ref["Gbot"])
+            assert abs(gf["iter"] - got["iter"]) <= max(3, got["iter"] // 100)
+            gd = L.conduct(cid, voltages=False)             # reference defaults 1e-8 / 2500
+            refd = O.conduct_literal(m, n, b1, b2, w)
+            assert abs(gd["iter"] - refd["iter"]) <= 1
+            assert abs(gd["Gtop"] - refd["Gtop"]) <= 1e-7 * abs(refd["Gtop"])
             with pytest.raises(P.PercError) as e:
                 L.voltage()
             assert e.value.code == P.E_STATE
@@ -228,6 +242,49 @@ def test_full_lattice_closed_form(P, O):
             L.label(P.SITE)
             r = L.conduct(0, tol=1e-13, itmax=100000)
             assert abs(r["Gtop"] - want) < 2e-11 and abs(r["Gbot"] - want) < 2e-11
+
+
+@pytest.mark.parametrize("lat,kind,m,n,ps,pb", [(1, 3, 528, 101, 0.85, 0.70), (2, 1, 400, 70, 0.56, 0.0), (1, 2, 16, 130, 0.0, 0.75),
+                                                   (1, 3, 1024, 1024, 0.80, 0.70), (2, 2, 1024, 512, 0.0, 0.37)])
+def test_one_pass_solver_equals_two_kernel_solver(P, O, lat, kind, m, n, ps, pb):
+    """perc_conduct_g with the one-pass iteration kernel (pcg_fused_kernel: tiles with and without the
+    geometry-free fast path, partial tiles, both lattices) against the two-kernel form on the same handle;
+    the small shapes also against the oracle"""
+    with P.Lattice(lat, m, n, 0) as L:
+        t, nb = L.t, L.nb
+        found = 0
+        for stream in range(6):
+            L.generate(4711, stream, int(ps * t) if kind != 2 else -1, int(pb * nb) if kind != 1 else -1)
+            L.label(kind)
+            ids, _ = L.span()
+            if not len(ids):
+                continue
+            found += 1
+            for tol, itmax in ((1e-13, 2000000), (1e-8, 2500)):
+                L.set_solver(1)
+                a = L.conduct(0, tol=tol, itmax=itmax, voltages=False)
+                assert L.solver_used() == 0
+                L.set_solver(0)
+                b = L.conduct(0, tol=tol, itmax=itmax, voltages=False)
+                assert L.solver_used() == 1
+                rel = 1e-9 if tol < 1e-10 else 1e-6
+                assert abs(a["Gtop"] - b["Gtop"]) <= rel * abs(a["Gtop"]), (tol, a, b)
+                assert abs(a["Gbot"] - b["Gbot"]) <= rel * abs(a["Gbot"]), (tol, a, b)
+                assert abs(a["iter"] - b["iter"]) <= max(3, a["iter"] // 100), (tol, a, b)
+                if a["iter"] <= itmax:
+                    assert b["err"] <= tol
+            if t <= 60000:
+                b1, b2 = O.bondlist(lat, m, n, 0)
+                socc, bocc = L.get_occupancy(sites=kind != 2, bonds=kind != 1)
+                ws, wb, wsz, ncl, wmax = O.label_uf(kind, lat, m, n, 0, b1, b2, site_occ=socc, bond_occ=bocc)
+                w = O.weights(kind, b1, b2, ws, wb, int(ids[0]))
+                ref = O.conduct_cg(m, n, b1, b2, w, tol=1e-13, itmax=2000000)
+                b = L.conduct(0, tol=1e-13, itmax=2000000, voltages=False)
+                assert abs(b["Gtop"] - ref["Gtop"]) <= 1e-9 * abs(ref["Gtop"])
+                assert abs(b["Gbot"] - ref["Gbot"]) <= 1e-9 * abs(ref["Gbot"])
+            if found == 2:
+                break
+        assert found >= 1
 
 
 def test_first_span_matches_literal_fill(P, O):

@@ -1,0 +1,95 @@
+"""CPU check of the one-pass PCG kernel: tests/pcg_fused_emul.cpp compiles the kernel's shared source
+(percolation_b200/csrc/pcg_fused_tile.cuh) with g++ and runs every phase of every tile thread by thread.
+Gtop / Gbot must agree with the oracle's Jacobi-PCG (same matrix, same stopping rule, Sq/bondc.f:465-595)
+within the north star's 1e-9, and the iteration counts must be those of linbcg (the recurrences are the same
+iterates in exact arithmetic)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    out = os.path.join(HERE, "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libpcg_fused_emul.so")
+    src = os.path.join(HERE, "pcg_fused_emul.cpp")
+    deps = [src, os.path.join(ROOT, "percolation_b200", "csrc", "pcg_fused_tile.cuh"),
+            os.path.join(ROOT, "percolation_b200", "csrc", "geometry.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++", src, "-o", so])
+    return C.CDLL(so)
+
+
+def run_emul(lib, lat, m, n, w, tol, itmax, Va=1.0, g0=1.0, gleak=1e-12, read_thresh=1e-10):
+    Gt, Gb, err = C.c_double(), C.c_double(), C.c_double()
+    it, fast = C.c_int(), C.c_int()
+    w = np.ascontiguousarray(w, np.float64)
+    rc = lib.fused_emul_solve(C.c_int(lat), C.c_int(m), C.c_int(n), w.ctypes.data_as(C.POINTER(C.c_double)),
+                              C.c_double(Va), C.c_double(g0), C.c_double(gleak), C.c_double(tol), C.c_int(itmax),
+                              C.c_double(read_thresh), C.byref(Gt), C.byref(Gb), C.byref(it), C.byref(err), C.byref(fast))
+    assert rc == 0
+    return {"Gtop": Gt.value, "Gbot": Gb.value, "iter": it.value, "err": err.value, "tiles_fast": fast.value}
+
+
+def spanning_case(O, lat, kind, m, n, ps, pb, seed):
+    """one realization with a spanning cluster -> per-bond weights of the Kirchhoff problem (None if nothing spans)"""
+    t = m * n
+    b1, b2 = O.bondlist(lat, m, n, 0)
+    nb = len(b1)
+    rng = np.random.default_rng(seed)
+    socc = (rng.random(t) < ps).astype(np.uint8) if kind != O.BOND else None
+    bocc = (rng.random(nb) < pb).astype(np.uint8) if kind != O.SITE else None
+    ws, wb, wsz, ncl, wmax = O.label_uf(kind, lat, m, n, 0, b1, b2, site_occ=socc, bond_occ=bocc)
+    ids = O.spanning(kind, m, n, b1, b2, ws, wb)
+    if len(ids) == 0:
+        return None
+    return b1, b2, O.weights(kind, b1, b2, ws, wb, int(ids[0]))
+
+
+# shapes: one partial tile; several tiles in x with interior (fast-path) tiles; tile rows that straddle; m = 16
+CASES = [
+    (1, "MIXED", 48, 40, 0.85, 0.75), (1, "BOND", 400, 70, 0.0, 0.56), (1, "SITE", 144, 100, 0.65, 0.0),
+    (1, "MIXED", 528, 101, 0.85, 0.72), (1, "BOND", 16, 130, 0.0, 0.75), (1, "SITE", 256, 33, 0.66, 0.0),
+    (2, "BOND", 48, 40, 0.0, 0.42), (2, "SITE", 400, 70, 0.56, 0.0), (2, "MIXED", 144, 100, 0.8, 0.6),
+    (2, "BOND", 528, 101, 0.0, 0.40), (2, "SITE", 16, 130, 0.8, 0.0), (2, "MIXED", 256, 33, 0.85, 0.6),
+]
+
+
+@pytest.mark.parametrize("lat,kind,m,n,ps,pb", CASES)
+def test_emulated_fused_pcg_matches_oracle(emul, O, lat, kind, m, n, ps, pb):
+    kind = getattr(O, kind)
+    for seed in range(20):
+        case = spanning_case(O, lat, kind, m, n, ps, pb, 7000 + 13 * m + n + seed)
+        if case is not None:
+            break
+    else:
+        pytest.fail("no spanning realization among the seeds")
+    b1, b2, w = case
+    ref = O.conduct_cg(m, n, b1, b2, w, tol=1e-13, itmax=200000)
+    got = run_emul(emul, lat, m, n, w, 1e-13, 200000)
+    assert abs(got["Gtop"] - ref["Gtop"]) <= 1e-9 * abs(ref["Gtop"]), (got, ref["Gtop"])
+    assert abs(got["Gbot"] - ref["Gbot"]) <= 1e-9 * abs(ref["Gbot"]), (got, ref["Gbot"])
+    assert abs(got["iter"] - ref["iter"]) <= max(3, ref["iter"] // 100), (got["iter"], ref["iter"])
+    assert got["err"] <= 1e-13
+    if m >= 400 and n >= 70:
+        assert got["tiles_fast"] > 0          # the geometry-free fast path was exercised
+    # the reference's own defaults (tol 1e-8, itmax 2500, Sq/bondc.f:545): same iteration count, same G to 1e-6
+    ref8 = O.conduct_cg(m, n, b1, b2, w)
+    got8 = run_emul(emul, lat, m, n, w, 1e-8, 2500)
+    assert abs(got8["iter"] - ref8["iter"]) <= 1
+    assert abs(got8["Gtop"] - ref8["Gtop"]) <= 1e-6 * abs(ref8["Gtop"])
+
+
+def test_emulated_fused_full_lattice_closed_form(emul, O):
+    # every bond conducting: G = m / (n - 1) on the square lattice (series / parallel)
+    m, n = 272, 67
+    b1, b2 = O.bondlist(O.SQUARE, m, n, 0)
+    got = run_emul(emul, O.SQUARE, m, n, np.ones(len(b1)), 1e-13, 100000)
+    assert abs(got["Gtop"] - m / (n - 1)) < 1e-9 and abs(got["Gbot"] - m / (n - 1)) < 1e-9

@@ -1,0 +1,54 @@
+"""Per-iteration device time of the two PCG solver forms (perc_conduct_g) on one realization of BASELINE
+configs[2] (square mixed site/bond, ps 0.80, pb 0.70): the two-kernel form (pcg_pipe_kernel<0|1>, 50 B per
+site and iteration) against the one-pass kernel (pcg_fused_kernel, 33 B).  torch-free (ctypes binding only).
+Prints FUSED_OK when both forms agree (same iterates: G after a fixed number of iterations to 1e-9)."""
+import argparse, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import percolation_b200 as P
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--L", type=int, default=4096)
+ap.add_argument("--iters", type=int, default=600)
+ap.add_argument("--ps", type=float, default=0.80)
+ap.add_argument("--pb", type=float, default=0.70)
+ap.add_argument("--lattice", type=int, default=1)
+ap.add_argument("--converge", action="store_true", help="also run both forms to tol 1e-10")
+args = ap.parse_args()
+HBM = 6455.6
+with P.Lattice(args.lattice, args.L, args.L, 0) as L:
+    t = L.t
+    L.generate(20240611, 0, int(args.ps * t), int(args.pb * L.nb))
+    L.label(P.MIXED)
+    ids, _ = L.span()
+    print("L=%d lattice=%d nspan=%d" % (args.L, args.lattice, len(ids)), flush=True)
+    if not len(ids):
+        sys.exit("no spanning cluster")
+    interior = t - 2 * args.L
+    res = {}
+    for name, mode in (("two-kernel", 1), ("one-pass", 0), ("two-kernel", 1), ("one-pass", 0)):
+        L.set_solver(mode)
+        t0 = time.perf_counter()
+        r = L.conduct(0, tol=1e-300, itmax=args.iters - 1, voltages=False)
+        wall = time.perf_counter() - t0
+        ph = L.phase_ms()
+        used = L.solver_used()
+        per_it = float(ph[5]) / r["iter"]
+        bytes_it = (33.0 if used else 50.0) * interior
+        print("%-10s used_fused=%d iters=%d  %.4f ms/iter (solve %.1f ms, wall %.1f ms)  kernels %.4f + %.4f ms  "
+              "%.0f GB/s algorithmic = %.1f%% of %.1f | G=%.12e err=%.3e"
+              % (name, used, r["iter"], per_it, ph[5], wall * 1e3, ph[6], ph[7], bytes_it / (per_it * 1e-3) / 1e9,
+                 100 * bytes_it / (per_it * 1e-3) / 1e9 / HBM, HBM, r["Gtop"], r["err"]), flush=True)
+        res[name] = r
+    a, b = res["two-kernel"], res["one-pass"]
+    ok = a["iter"] == b["iter"] and abs(a["Gtop"] - b["Gtop"]) <= 1e-9 * abs(a["Gtop"]) and abs(a["Gbot"] - b["Gbot"]) <= 1e-9 * abs(a["Gbot"])
+    ok = ok and abs(a["err"] - b["err"]) <= 1e-6 * abs(a["err"])
+    if args.converge:
+        for name, mode in (("two-kernel", 1), ("one-pass", 0)):
+            L.set_solver(mode)
+            t0 = time.perf_counter()
+            r = L.conduct(0, tol=1e-10, itmax=4000000, voltages=False)
+            print("%-10s converged: iters=%d G=%.12e err=%.3e  %.2f s" % (name, r["iter"], r["Gtop"], r["err"], time.perf_counter() - t0), flush=True)
+            res[name + "-c"] = r
+        a, b = res["two-kernel-c"], res["one-pass-c"]
+        ok = ok and abs(a["Gtop"] - b["Gtop"]) <= 1e-8 * abs(a["Gtop"]) and abs(a["iter"] - b["iter"]) <= max(3, a["iter"] // 100)
+    print("FUSED_OK" if ok else "FUSED_MISMATCH", flush=True)
