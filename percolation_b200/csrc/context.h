@@ -79,6 +79,7 @@ struct Ctx {
     double* vq = nullptr;
     double* xprow = nullptr;      // [4 m] one-pass solver: x and p of rows 1 and n-2 (the rows the read-out consumes)
     int pcg_mode = -1;            // -1 process default, 0 automatic (one-pass kernel when it applies), 1 two-kernel form
+    int fused_cfg = -1;           // tile configuration of the one-pass kernel (-1: process default)
     bool last_fused = false;      // the last solve ran the one-pass kernel
     double* partial = nullptr;    // per-block partial sums
     int partial_cap = 0;

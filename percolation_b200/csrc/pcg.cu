@@ -668,10 +668,12 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
 // each); everything else takes the two-kernel path.  Consecutive iterations sweep the tiles in opposite
 // directions, so each starts on the part of r / s the previous one wrote last (still in L2).
 // ------------------------------------------------------------------------------------------
-constexpr size_t FT_SMEM = 2 * (size_t)FT_STAGE_BYTES + FT_R_BYTES + sizeof(FtDiag) * 64 * 32 + sizeof(double) * 96 + 16;
-static_assert(FT_SMEM <= 227 * 1024, "fused PCG tile does not fit the shared memory of one SM");
+static_assert(FtCfgA::SMEM <= 227 * 1024 && FtCfgB::SMEM <= 227 * 1024 && 2 * (FtCfgC::SMEM + 1024) <= 228 * 1024 &&
+              2 * (FtCfgD::SMEM + 1024) <= 228 * 1024 && 3 * (FtCfgE::SMEM + 1024) <= 228 * 1024,
+              "fused PCG tile does not fit the shared memory of one SM");
 
-// block sums of three values at once (fixed order); result valid in thread 0
+// block sums of three values at once (fixed order: lanes by shuffles, then warp 0 folds the per-warp partials by
+// shuffles); result valid in thread 0
 __device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double* sh)
 {
     for (int o = 16; o; o >>= 1) {
@@ -679,19 +681,22 @@ __device__ __forceinline__ void block_sum3(double& a, double& b, double& c, doub
         b += __shfl_down_sync(0xffffffffu, b, o);
         c += __shfl_down_sync(0xffffffffu, c, o);
     }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
     __syncthreads();
     if (lane == 0) { sh[w] = a; sh[32 + w] = b; sh[64 + w] = c; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double x = 0.0, y = 0.0, z = 0.0;
-        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { x += sh[k]; y += sh[32 + k]; z += sh[64 + k]; }
-        a = x; b = y; c = z;
+    if (w == 0) {
+        a = lane < nw ? sh[lane] : 0.0; b = lane < nw ? sh[32 + lane] : 0.0; c = lane < nw ? sh[64 + lane] : 0.0;
+        for (int o = 16; o; o >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, o);
+            b += __shfl_down_sync(0xffffffffu, b, o);
+            c += __shfl_down_sync(0xffffffffu, c, o);
+        }
     }
 }
 
-template <int LAT>
-__global__ void __launch_bounds__(FT_THREADS, 1)
+template <int LAT, class C>
+__global__ void __launch_bounds__(C::THREADS, C::CTAS)
 pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_s,
                  const __grid_constant__ CUtensorMap tm_cf, Geom g, PcgParams prm, double* __restrict__ r_out,
                  double* __restrict__ s_out, double* __restrict__ xrow, double* __restrict__ prow,
@@ -699,12 +704,12 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
 {
     if (st->done) return;
     extern __shared__ __align__(128) unsigned char ft_raw[];
-    double* su = reinterpret_cast<double*>(ft_raw + 2 * (size_t)FT_STAGE_BYTES);
-    FtDiag* dtab = reinterpret_cast<FtDiag*>(ft_raw + 2 * (size_t)FT_STAGE_BYTES + FT_R_BYTES);      // [64][32]
-    double* sh = reinterpret_cast<double*>(dtab + 64 * 32);
+    double* su = reinterpret_cast<double*>(ft_raw + 2 * (size_t)C::STAGE_BYTES);
+    FtDiag* dtab = reinterpret_cast<FtDiag*>(ft_raw + 2 * (size_t)C::STAGE_BYTES + C::R_BYTES);      // [64][DC]
+    double* sh = reinterpret_cast<double*>(dtab + 64 * C::DC);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sh + 96);                      // one mbarrier per stage
     const int tid = threadIdx.x;
-    for (int k = tid; k < 64 * 32; k += FT_THREADS) dtab[k] = ft_diag_entry(k >> 5, prm.g0, prm.gleak);
+    for (int k = tid; k < 64 * C::DC; k += C::THREADS) dtab[k] = ft_diag_entry(k / C::DC, prm.g0, prm.gleak);
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -713,14 +718,14 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
     __syncthreads();
     const FtScalars sc{prm.g0, prm.gleak, prime ? 0.0 : st->ak, prime ? 0.0 : st->bk};
     auto tile_of = [&](int t) { return rev ? ntiles - 1 - t : t; };
-    auto stage_r = [&](int k) { return reinterpret_cast<double*>(ft_raw + (size_t)k * FT_STAGE_BYTES); };
-    auto stage_s = [&](int k) { return reinterpret_cast<double*>(ft_raw + (size_t)k * FT_STAGE_BYTES + FT_R_BYTES); };
-    auto stage_cf = [&](int k) { return reinterpret_cast<uint8_t*>(ft_raw + (size_t)k * FT_STAGE_BYTES + FT_R_BYTES + FT_S_BYTES); };
+    auto stage_r = [&](int k) { return reinterpret_cast<double*>(ft_raw + (size_t)k * C::STAGE_BYTES); };
+    auto stage_s = [&](int k) { return reinterpret_cast<double*>(ft_raw + (size_t)k * C::STAGE_BYTES + C::R_BYTES); };
+    auto stage_cf = [&](int k) { return reinterpret_cast<uint8_t*>(ft_raw + (size_t)k * C::STAGE_BYTES + C::R_BYTES + C::S_BYTES); };
     // one thread, three TMA tensor copies: r (tile + 2-site halo), s (tile + east / north / west ring), conduct bytes
     auto issue = [&](int k, int tl) {
         if (tid != 0) return;
-        const int x0 = (tl % ntx) * FT_TX, y0 = (tl / ntx) * FT_TY;
-        mbar_arrive_expect(&bars[k], (unsigned)(FT_RR * FT_LD * 8 + FT_SR * FT_LD * 8 + FT_RR * FT_CLD));
+        const int x0 = (tl % ntx) * C::TX, y0 = (tl / ntx) * C::TY;
+        mbar_arrive_expect(&bars[k], (unsigned)(C::RR * C::LD * 8 + C::SR * C::LD * 8 + C::RR * C::CLD));
         tma_box_g2s(stage_r(k), &tm_r, x0 - 2, y0 - 1, &bars[k]);
         tma_box_g2s(stage_s(k), &tm_s, x0 - 2, y0, &bars[k]);
         tma_box_g2s(stage_cf(k), &tm_cf, x0 - 16, y0 - 1, &bars[k]);
@@ -729,21 +734,21 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
     int t = blockIdx.x;
     if (t < ntiles) issue(0, tile_of(t));
     for (int k = 0; t < ntiles; t += gridDim.x, ++k) {
-        const int tl = tile_of(t), x0 = (tl % ntx) * FT_TX, y0 = (tl / ntx) * FT_TY;
+        const int tl = tile_of(t), x0 = (tl % ntx) * C::TX, y0 = (tl / ntx) * C::TY;
         const int tn = t + gridDim.x;
         if (tn < ntiles) issue((k + 1) & 1, tile_of(tn));      // the other stage was released by the barriers of the last tile
         mbar_wait(&bars[k & 1], (unsigned)((k >> 1) & 1));
         const double* sr = stage_r(k & 1);
         double* ss = stage_s(k & 1);
         const uint8_t* scf = stage_cf(k & 1);
-        const bool interior = ft_interior(g, x0, y0);
-        ft_phase_u<LAT>(g, sr, scf, su, dtab, x0, y0, interior, tid);
+        const bool interior = ft_interior<C>(g, x0, y0);
+        ft_phase_u<LAT, C>(g, sr, scf, su, dtab, x0, y0, interior, tid);
         __syncthreads();
         double rz = 0.0, rr = 0.0, en = 0.0;
-        ft_phase_main<LAT>(g, sc, sr, ss, scf, su, dtab, x0, y0, interior, tid, r_out, s_out, xrow, prow, rz, rr);
-        ft_phase_ringcols<LAT>(g, sc, sr, ss, scf, su, dtab, x0, y0, tid);
+        ft_phase_main<LAT, C>(g, sc, sr, ss, scf, su, dtab, x0, y0, interior, tid, r_out, s_out, xrow, prow, rz, rr);
+        ft_phase_ringcols<LAT, C>(g, sc, sr, ss, scf, su, dtab, x0, y0, tid);
         __syncthreads();
-        ft_phase_energy<LAT>(g, sc, ss, scf, x0, y0, interior, tid, en);
+        ft_phase_energy<LAT, C>(g, sc, ss, scf, x0, y0, interior, tid, en);
         // generic-proxy accesses to this stage are ordered before the bulk copies that will refill it
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         block_sum3(rz, rr, en, sh);                             // synchronises: every thread is done with the stage
@@ -1064,19 +1069,20 @@ bool pcg_fused_applies(const Ctx* c, int keep_x, int warm)
 // the iteration loop of the one-pass kernel; on entry (after pcg_init_kernel) vr = b, vp = vx = 0, the scalars of
 // the solve are initialised.  Buffers: r ping-pongs between vr and vp, s between vp2 and vx; x / p of rows 1 and
 // n-2 live in xprow and are copied into vx for the read-out at the end.
-static int pcg_fused_loop(Ctx* c, const PcgParams& prm)
+template <class C>
+static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
 {
     const Geom& g = c->g;
     cudaStream_t s = c->stream;
-    const int ntx = (g.m + FT_TX - 1) / FT_TX, ntiles = ntx * ((g.n + FT_TY - 1) / FT_TY);
-    const int grid = ntiles < c->num_sms ? ntiles : c->num_sms;
+    const int ntx = (g.m + C::TX - 1) / C::TX, ntiles = ntx * ((g.n + C::TY - 1) / C::TY);
+    const int grid = ntiles < C::CTAS * c->num_sms ? ntiles : C::CTAS * c->num_sms;
     if (!c->xprow) PERC_CUDA(cudaMalloc(&c->xprow, sizeof(double) * 4 * g.m));
     PERC_CUDA(cudaMemsetAsync(c->xprow, 0, sizeof(double) * 4 * g.m, s));
     PERC_CUDA(cudaMemsetAsync(c->vp2, 0, sizeof(double) * g.t, s));
     static bool attr_set = false;
     if (!attr_set) {
-        PERC_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<LAT_SQUARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
-        PERC_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<LAT_TRIANGULAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        PERC_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<LAT_SQUARE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        PERC_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<LAT_TRIANGULAR, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         attr_set = true;
     }
     double* rbuf[2] = {c->vr, c->vp};
@@ -1084,18 +1090,18 @@ static int pcg_fused_loop(Ctx* c, const PcgParams& prm)
     CUtensorMap tm_r[2], tm_s[2], tm_cf;
     int rc;
     for (int k = 0; k < 2; ++k) {
-        rc = make_tensor_map(&tm_r[k], rbuf[k], 8, g.m, g.n, FT_LD, FT_RR); if (rc) return rc;
-        rc = make_tensor_map(&tm_s[k], sbuf[k], 8, g.m, g.n, FT_LD, FT_SR); if (rc) return rc;
+        rc = make_tensor_map(&tm_r[k], rbuf[k], 8, g.m, g.n, C::LD, C::RR); if (rc) return rc;
+        rc = make_tensor_map(&tm_s[k], sbuf[k], 8, g.m, g.n, C::LD, C::SR); if (rc) return rc;
     }
-    rc = make_tensor_map(&tm_cf, c->cfull, 1, g.m, g.n, FT_CLD, FT_RR); if (rc) return rc;
+    rc = make_tensor_map(&tm_cf, c->cfull, 1, g.m, g.n, C::CLD, C::RR); if (rc) return rc;
     double* xrow = c->xprow; double* prow = c->xprow + 2 * (size_t)g.m;
     int cur = 0, pass = 0;
     auto launch = [&](int prime) {
         if (g.lattice == LAT_SQUARE)
-            pcg_fused_kernel<LAT_SQUARE><<<grid, FT_THREADS, FT_SMEM, s>>>(tm_r[cur], tm_s[cur], tm_cf, g, prm, rbuf[cur ^ 1], sbuf[cur ^ 1],
+            pcg_fused_kernel<LAT_SQUARE, C><<<grid, C::THREADS, C::SMEM, s>>>(tm_r[cur], tm_s[cur], tm_cf, g, prm, rbuf[cur ^ 1], sbuf[cur ^ 1],
                                                                            xrow, prow, c->partial, c->d_pcg, ntx, ntiles, pass & 1, prime);
         else
-            pcg_fused_kernel<LAT_TRIANGULAR><<<grid, FT_THREADS, FT_SMEM, s>>>(tm_r[cur], tm_s[cur], tm_cf, g, prm, rbuf[cur ^ 1], sbuf[cur ^ 1],
+            pcg_fused_kernel<LAT_TRIANGULAR, C><<<grid, C::THREADS, C::SMEM, s>>>(tm_r[cur], tm_s[cur], tm_cf, g, prm, rbuf[cur ^ 1], sbuf[cur ^ 1],
                                                                                xrow, prow, c->partial, c->d_pcg, ntx, ntiles, pass & 1, prime);
         cur ^= 1; ++pass;
         c->launches++;
@@ -1131,6 +1137,24 @@ static int pcg_fused_loop(Ctx* c, const PcgParams& prm)
     return 0;
 }
 
+// tile configuration of the one-pass kernel: PERC_FUSED_CFG = A | B | C (default: see below)
+static int pcg_fused_loop(Ctx* c, const PcgParams& prm)
+{
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char* e = getenv("PERC_FUSED_CFG");
+        cfg = (e && *e >= 'A' && *e <= 'E') ? *e - 'A' : 0;
+    }
+    const int use = c->fused_cfg >= 0 ? c->fused_cfg : cfg;
+    switch (use) {
+    case 1: return pcg_fused_loop_t<FtCfgB>(c, prm);
+    case 2: return pcg_fused_loop_t<FtCfgC>(c, prm);
+    case 3: return pcg_fused_loop_t<FtCfgD>(c, prm);
+    case 4: return pcg_fused_loop_t<FtCfgE>(c, prm);
+    }
+    return pcg_fused_loop_t<FtCfgA>(c, prm);
+}
+
 int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double tol, int itmax,
               double read_thresh, int keep_x, double* Gtop, double* Gbot, int* iter, double* err, int warm)
 {
@@ -1153,7 +1177,7 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     int need = (int)(sgrid.x * sgrid.y);
     if (need < ugrid * 3) need = ugrid * 3;
     if (need < 2 * ntiles) need = 2 * ntiles;
-    { const int nf = 3 * ((g.m + FT_TX - 1) / FT_TX) * ((g.n + FT_TY - 1) / FT_TY); if (need < nf) need = nf; }
+    { const int nf = 3 * ((g.m + FtCfgE::TX - 1) / FtCfgE::TX) * ((g.n + FtCfgE::TY - 1) / FtCfgE::TY); if (need < nf) need = nf; }
     const int want_x = keep_x;
     if (!vec) keep_x = 1;                // the scalar fallback always forms x
     if (need > c->partial_cap) {

@@ -27,20 +27,33 @@
 
 namespace perc {
 
-constexpr int FT_TX = 128, FT_TY = 32;                   // tile, sites
-constexpr int FT_RPT = 3;                                // consecutive rows per thread (sliding 3-row window)
-constexpr int FT_NG = (FT_TY + 1) / FT_RPT;              // row groups
-static_assert(FT_NG * FT_RPT == FT_TY + 1, "compute rows (tile + north ring row) must split evenly");
-constexpr int FT_THREADS = 64 * FT_NG;                   // 2 columns per thread
-constexpr int FT_CR = FT_TY + 1;                         // compute rows: gy = y0 + lr, lr = 0 .. FT_TY (last = north ring)
-constexpr int FT_RR = FT_TY + 3;                         // staged rows of r, conduct bytes, u: gy = y0 - 1 + pr
-constexpr int FT_SR = FT_TY + 1;                         // staged rows of s:                   gy = y0 + ps
-constexpr int FT_LD = FT_TX + 4;                         // doubles per staged row: column c <-> gx = x0 - 2 + c
-constexpr int FT_CLD = FT_TX + 32;                       // bytes per staged conduct row: byte b <-> gx = x0 - 16 + b
-constexpr int FT_R_BYTES = (FT_RR * FT_LD * 8 + 127) / 128 * 128;
-constexpr int FT_S_BYTES = (FT_SR * FT_LD * 8 + 127) / 128 * 128;
-constexpr int FT_CF_BYTES = (FT_RR * FT_CLD + 127) / 128 * 128;
-constexpr int FT_STAGE_BYTES = FT_R_BYTES + FT_S_BYTES + FT_CF_BYTES;
+// tile configuration: TY tile rows, RPT consecutive rows per thread (sliding 3-row window), DC private copies of
+// the diagonal table (32 = one per lane, conflict-free; 8 = a quarter of the shared memory)
+template <int TY_, int RPT_, int DC_, int CTAS_>
+struct FtCfg {
+    static constexpr int TX = 128, TY = TY_, RPT = RPT_, DC = DC_, CTAS = CTAS_;   // CTAS: resident CTAs per SM
+    static constexpr int NG = (TY + 1) / RPT;               // row groups
+    static_assert(NG * RPT == TY + 1, "compute rows (tile + north ring row) must split evenly");
+    static constexpr int THREADS = 64 * NG;                 // 2 columns per thread
+    static constexpr int CR = TY + 1;                       // compute rows: gy = y0 + lr, lr = 0 .. TY (last = north ring)
+    static constexpr int RR = TY + 3;                       // staged rows of r, conduct bytes, u: gy = y0 - 1 + pr
+    static constexpr int SR = TY + 1;                       // staged rows of s:                   gy = y0 + ps
+    static constexpr int LD = TX + 4;                       // doubles per staged row: column c <-> gx = x0 - 2 + c
+    static constexpr int CLD = TX + 32;                     // bytes per staged conduct row: byte b <-> gx = x0 - 16 + b
+    static constexpr int R_BYTES = (RR * LD * 8 + 127) / 128 * 128;
+    static constexpr int S_BYTES = (SR * LD * 8 + 127) / 128 * 128;
+    static constexpr int CF_BYTES = (RR * CLD + 127) / 128 * 128;
+    static constexpr int STAGE_BYTES = R_BYTES + S_BYTES + CF_BYTES;
+    static constexpr int TAB_BYTES = 64 * DC * 16;
+    static constexpr int SMEM = 2 * STAGE_BYTES + R_BYTES + TAB_BYTES + 96 * 8 + 16;
+    static PERC_HD int tab(int nc, int nl, int lane) { return ((nc << 3) | nl) * DC + (lane & (DC - 1)); }
+};
+
+typedef FtCfg<32, 3, 32, 1> FtCfgA;      // 704 threads, one CTA per SM
+typedef FtCfg<31, 2, 32, 1> FtCfgB;      // 1024 threads, one CTA per SM
+typedef FtCfg<15, 2, 8, 2> FtCfgC;       // 512 threads, two CTAs per SM
+typedef FtCfg<15, 4, 8, 2> FtCfgD;       // 256 threads, two CTAs per SM
+typedef FtCfg<9, 2, 8, 3> FtCfgE;        // 320 threads, three CTAs per SM
 
 #ifdef __CUDACC__
 typedef double2 ft_d2;
@@ -75,8 +88,7 @@ template <int LAT> PERC_HD unsigned ft_interior_ex(int gx)
     if (LAT == LAT_SQUARE) return NB_E | NB_N | NB_W | NB_S;
     return (gx & 1) ? (NB_E | NB_N | NB_W | NB_S | NB_SW | NB_SE) : (NB_E | NB_N | NB_W | NB_S | NB_NW | NB_NE);
 }
-// table of diagonals indexed by (#conducting bonds << 3 | #leaking bonds), one private copy per lane
-PERC_HD int ft_tab(int nc, int nl, int lane) { return (((nc << 3) | nl) << 5) + lane; }
+// table of diagonals indexed by (#conducting bonds << 3 | #leaking bonds), DC private copies (FtCfg::tab)
 PERC_HD FtDiag ft_diag_entry(int idx, double g0, double gleak)
 {
     FtDiag e;
@@ -86,25 +98,31 @@ PERC_HD FtDiag ft_diag_entry(int idx, double g0, double gleak)
 }
 // every site the tile touches (2-site halo) is an unknown with its full neighbourhood, or lies on a Dirichlet
 // row where r = 0: the fast paths below need no per-site geometry
+template <class C>
 PERC_HD bool ft_interior(const Geom& g, int x0, int y0)
 {
-    return x0 - 2 >= 1 && x0 + FT_TX + 1 <= g.m - 2 && y0 >= 1 && y0 + FT_TY <= g.n - 2;
+    return x0 - 2 >= 1 && x0 + C::TX + 1 <= g.m - 2 && y0 >= 1 && y0 + C::TY <= g.n - 2;
 }
 
 // ---- phase U: u = r / d on the staged box (tile + 2-site halo; rows y0-1 .. y0+TY+1) -------------------------
-template <int LAT>
+template <int LAT, class C>
 PERC_HD void ft_phase_u(const Geom& g, const double* sr, const uint8_t* scf, double* su, const FtDiag* dtab,
                         int x0, int y0, bool interior, int tid)
 {
-    constexpr int NCP = FT_LD / 2;
+    constexpr int NCP = C::LD / 2, TRIPS = (C::RR * NCP + C::THREADS - 1) / C::THREADS;
     const int lane = tid & 31;
-    for (int k = tid; k < FT_RR * NCP; k += FT_THREADS) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int it = 0; it < TRIPS; ++it) {
+        const int k = tid + it * C::THREADS;
+        if (k >= C::RR * NCP) break;
         const int pr = k / NCP, cp = k - pr * NCP;
         const int gy = y0 - 1 + pr, gx = x0 - 2 + 2 * cp;
         double u0 = 0.0, u1 = 0.0;
         if (gy >= 1 && gy <= g.n - 2) {
-            const ft_d2 r2 = ft_ld2(&sr[pr * FT_LD + 2 * cp]);
-            const unsigned c01 = *reinterpret_cast<const unsigned short*>(&scf[pr * FT_CLD + 14 + 2 * cp]);
+            const ft_d2 r2 = ft_ld2(&sr[pr * C::LD + 2 * cp]);
+            const unsigned c01 = *reinterpret_cast<const unsigned short*>(&scf[pr * C::CLD + 14 + 2 * cp]);
             unsigned e0, e1;
             if (interior) { e0 = ft_interior_ex<LAT>(gx); e1 = ft_interior_ex<LAT>(gx + 1); }
             else {
@@ -112,37 +130,37 @@ PERC_HD void ft_phase_u(const Geom& g, const double* sr, const uint8_t* scf, dou
                 e1 = (gx + 1 >= 0 && gx + 1 < g.m) ? neighbour_bits(g, gx + 1, gy) : 0u;
             }
             const int n0 = ft_popc(c01 & 0xffu & e0), n1 = ft_popc((c01 >> 8) & e1);
-            u0 = r2.x * dtab[ft_tab(n0, ft_popc(e0) - n0, lane)].inv;
-            u1 = r2.y * dtab[ft_tab(n1, ft_popc(e1) - n1, lane)].inv;
+            u0 = r2.x * dtab[C::tab(n0, ft_popc(e0) - n0, lane)].inv;
+            u1 = r2.y * dtab[C::tab(n1, ft_popc(e1) - n1, lane)].inv;
         }
-        ft_st2(&su[pr * FT_LD + 2 * cp], u0, u1);
+        ft_st2(&su[pr * C::LD + 2 * cp], u0, u1);
     }
 }
 
 // ---- phase M: w = A u, s' = w + beta s, r' = r - alpha s', u' = r'/d on the compute rows; stores r', s' of
 // the tile rows; u' replaces s in shared memory (each thread overwrites only what it has read itself);
 // p / x of the two read-out rows; sums r'.u' and r'.r' over the tile's sites ---------------------------------
-template <int LAT>
+template <int LAT, class C>
 PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr, double* ss, const uint8_t* scf,
                            const double* su, const FtDiag* dtab, int x0, int y0, bool interior, int tid,
                            double* __restrict__ r_out, double* __restrict__ s_out, double* __restrict__ xrow,
                            double* __restrict__ prow, double& acc_rz, double& acc_rr)
 {
     const int tx = tid & 63, ty = tid >> 6, lane = tid & 31;
-    const int gx = x0 + 2 * tx, lr0 = ty * FT_RPT;
+    const int gx = x0 + 2 * tx, lr0 = ty * C::RPT;
     const double dg = sc.g0 - sc.gleak, alpha = sc.alpha, beta = sc.beta;
-    const double* c = &su[(lr0 + 1) * FT_LD + 2 + 2 * tx];
-    ft_d2 dn = ft_ld2(c - FT_LD), cc = ft_ld2(c);
-    double drt = c[-FT_LD + 2];                              // row below, x+2: SE neighbour of the odd column
+    const double* c = &su[(lr0 + 1) * C::LD + 2 + 2 * tx];
+    ft_d2 dn = ft_ld2(c - C::LD), cc = ft_ld2(c);
+    double drt = c[-C::LD + 2];                              // row below, x+2: SE neighbour of the odd column
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int j = 0; j < FT_RPT; ++j, c += FT_LD) {
+    for (int j = 0; j < C::RPT; ++j, c += C::LD) {
         const int lr = lr0 + j, gy = y0 + lr;
-        const ft_d2 up = ft_ld2(c + FT_LD);
+        const ft_d2 up = ft_ld2(c + C::LD);
         const double lf = c[-1], rt = c[2];
         const bool valid = interior || (gy >= 1 && gy <= g.n - 2 && gx < g.m);
-        const unsigned c01 = *reinterpret_cast<const unsigned short*>(&scf[(lr + 1) * FT_CLD + 16 + 2 * tx]);
+        const unsigned c01 = *reinterpret_cast<const unsigned short*>(&scf[(lr + 1) * C::CLD + 16 + 2 * tx]);
         unsigned cf0 = c01 & 0xffu, cf1 = c01 >> 8;
         unsigned e0, e1;
         double all0, all1;
@@ -150,7 +168,7 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
             e0 = ft_interior_ex<LAT>(gx); e1 = ft_interior_ex<LAT>(gx + 1);
             all0 = (cc.y + lf) + (up.x + dn.x);
             all1 = (rt + cc.x) + (up.y + dn.y);
-            if (LAT == LAT_TRIANGULAR) { all0 += c[FT_LD - 1] + up.y; all1 += dn.x + drt; }
+            if (LAT == LAT_TRIANGULAR) { all0 += c[C::LD - 1] + up.y; all1 += dn.x + drt; }
         } else {
             e0 = valid ? neighbour_bits(g, gx, gy) : 0u; e1 = valid ? neighbour_bits(g, gx + 1, gy) : 0u;
             cf0 &= e0; cf1 &= e1;
@@ -158,7 +176,7 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
             if (e0 & NB_E) all0 += cc.y;  if (e0 & NB_W) all0 += lf;   if (e0 & NB_N) all0 += up.x;  if (e0 & NB_S) all0 += dn.x;
             if (e1 & NB_E) all1 += rt;    if (e1 & NB_W) all1 += cc.x; if (e1 & NB_N) all1 += up.y;  if (e1 & NB_S) all1 += dn.y;
             if (LAT == LAT_TRIANGULAR) {
-                if (e0 & NB_NW) all0 += c[FT_LD - 1]; if (e0 & NB_NE) all0 += up.y;
+                if (e0 & NB_NW) all0 += c[C::LD - 1]; if (e0 & NB_NE) all0 += up.y;
                 if (e1 & NB_SW) all1 += dn.x;         if (e1 & NB_SE) all1 += drt;
             }
         }
@@ -166,19 +184,19 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
         ft_padd(con0, cc.y, cf0 & NB_E); ft_padd(con0, lf, cf0 & NB_W);   ft_padd(con0, up.x, cf0 & NB_N); ft_padd(con0, dn.x, cf0 & NB_S);
         ft_padd(con1, rt, cf1 & NB_E);   ft_padd(con1, cc.x, cf1 & NB_W); ft_padd(con1, up.y, cf1 & NB_N); ft_padd(con1, dn.y, cf1 & NB_S);
         if (LAT == LAT_TRIANGULAR) {
-            ft_padd(con0, c[FT_LD - 1], cf0 & NB_NW); ft_padd(con0, up.y, cf0 & NB_NE);
+            ft_padd(con0, c[C::LD - 1], cf0 & NB_NW); ft_padd(con0, up.y, cf0 & NB_NE);
             ft_padd(con1, dn.x, cf1 & NB_SW);         ft_padd(con1, drt, cf1 & NB_SE);
         }
         const int n0 = ft_popc(cf0), n1 = ft_popc(cf1);
-        const FtDiag t0 = dtab[ft_tab(n0, ft_popc(e0) - n0, lane)], t1 = dtab[ft_tab(n1, ft_popc(e1) - n1, lane)];
+        const FtDiag t0 = dtab[C::tab(n0, ft_popc(e0) - n0, lane)], t1 = dtab[C::tab(n1, ft_popc(e1) - n1, lane)];
         const double w0 = t0.d * cc.x - (sc.gleak * all0 + dg * con0);
         const double w1 = t1.d * cc.y - (sc.gleak * all1 + dg * con1);
-        double* sp = &ss[lr * FT_LD + 2 + 2 * tx];
-        const ft_d2 s2 = ft_ld2(sp), r2 = ft_ld2(&sr[(lr + 1) * FT_LD + 2 + 2 * tx]);
+        double* sp = &ss[lr * C::LD + 2 + 2 * tx];
+        const ft_d2 s2 = ft_ld2(sp), r2 = ft_ld2(&sr[(lr + 1) * C::LD + 2 + 2 * tx]);
         const double sn0 = w0 + beta * s2.x, sn1 = w1 + beta * s2.y;
         const double rn0 = r2.x - alpha * sn0, rn1 = r2.y - alpha * sn1;
         ft_st2(sp, valid ? rn0 * t0.inv : 0.0, valid ? rn1 * t1.inv : 0.0);
-        if (valid && lr < FT_TY) {
+        if (valid && lr < C::TY) {
             const int64_t i = (int64_t)gy * g.m + gx;
             ft_st2(s_out + i, sn0, sn1);
             ft_st2(r_out + i, rn0, rn1);
@@ -198,53 +216,53 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
 }
 
 // east / west ring columns (gx = x0 - 1 and x0 + TX) of the compute rows: u' only (one thread per site)
-template <int LAT>
+template <int LAT, class C>
 PERC_HD void ft_phase_ringcols(const Geom& g, const FtScalars& sc, const double* sr, double* ss, const uint8_t* scf,
                                const double* su, const FtDiag* dtab, int x0, int y0, int tid)
 {
-    if (tid >= 2 * FT_CR) return;
-    const int side = tid >= FT_CR, lr = tid - side * FT_CR, lane = tid & 31;
-    const int gy = y0 + lr, gx = side ? x0 + FT_TX : x0 - 1, col = side ? 2 + FT_TX : 1;
+    if (tid >= 2 * C::CR) return;
+    const int side = tid >= C::CR, lr = tid - side * C::CR, lane = tid & 31;
+    const int gy = y0 + lr, gx = side ? x0 + C::TX : x0 - 1, col = side ? 2 + C::TX : 1;
     double un = 0.0;
     if (gy >= 1 && gy <= g.n - 2 && gx >= 0 && gx < g.m) {
         const unsigned ex = neighbour_bits(g, gx, gy);
-        const unsigned cf = scf[(lr + 1) * FT_CLD + (side ? 16 + FT_TX : 15)] & ex;
-        const double* c = &su[(lr + 1) * FT_LD + col];
+        const unsigned cf = scf[(lr + 1) * C::CLD + (side ? 16 + C::TX : 15)] & ex;
+        const double* c = &su[(lr + 1) * C::LD + col];
         double all = 0.0, con = 0.0;
 #define FT_NB(bit, off) if (ex & bit) { const double v = c[off]; all += v; if (cf & bit) con += v; }
-        FT_NB(NB_E, 1) FT_NB(NB_W, -1) FT_NB(NB_N, FT_LD) FT_NB(NB_S, -FT_LD)
-        if (LAT == LAT_TRIANGULAR) { FT_NB(NB_NW, FT_LD - 1) FT_NB(NB_NE, FT_LD + 1) FT_NB(NB_SW, -FT_LD - 1) FT_NB(NB_SE, -FT_LD + 1) }
+        FT_NB(NB_E, 1) FT_NB(NB_W, -1) FT_NB(NB_N, C::LD) FT_NB(NB_S, -C::LD)
+        if (LAT == LAT_TRIANGULAR) { FT_NB(NB_NW, C::LD - 1) FT_NB(NB_NE, C::LD + 1) FT_NB(NB_SW, -C::LD - 1) FT_NB(NB_SE, -C::LD + 1) }
 #undef FT_NB
         const int nc = ft_popc(cf);
-        const FtDiag t = dtab[ft_tab(nc, ft_popc(ex) - nc, lane)];
+        const FtDiag t = dtab[C::tab(nc, ft_popc(ex) - nc, lane)];
         const double w = t.d * c[0] - (sc.gleak * all + (sc.g0 - sc.gleak) * con);
-        const double sn = w + sc.beta * ss[lr * FT_LD + col];
-        const double rn = sr[(lr + 1) * FT_LD + col] - sc.alpha * sn;
+        const double sn = w + sc.beta * ss[lr * C::LD + col];
+        const double rn = sr[(lr + 1) * C::LD + col] - sc.alpha * sn;
         un = rn * t.inv;
     }
-    ss[lr * FT_LD + col] = un;
+    ss[lr * C::LD + col] = un;
 }
 
 // ---- phase E: u'.A u' as the energy of the bonds OWNED by the tile's sites (E, N, NW, NE), u' from shared
 // memory (zeros on Dirichlet rows and outside the lattice) ---------------------------------------------------
-template <int LAT>
+template <int LAT, class C>
 PERC_HD void ft_phase_energy(const Geom& g, const FtScalars& sc, const double* ss, const uint8_t* scf, int x0, int y0,
                              bool interior, int tid, double& acc_e)
 {
     const int tx = tid & 63, ty = tid >> 6;
-    const int gx = x0 + 2 * tx, lr0 = ty * FT_RPT;
+    const int gx = x0 + 2 * tx, lr0 = ty * C::RPT;
     const double dg = sc.g0 - sc.gleak;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int j = 0; j < FT_RPT; ++j) {
+    for (int j = 0; j < C::RPT; ++j) {
         const int lr = lr0 + j, gy = y0 + lr;
-        if (lr >= FT_TY) continue;
+        if (lr >= C::TY) continue;
         if (!interior && !(gy >= 0 && gy < g.n && gx < g.m)) continue;
-        const double* c = &ss[lr * FT_LD + 2 + 2 * tx];
-        const ft_d2 cc = ft_ld2(c), up = ft_ld2(c + FT_LD);
+        const double* c = &ss[lr * C::LD + 2 + 2 * tx];
+        const ft_d2 cc = ft_ld2(c), up = ft_ld2(c + C::LD);
         const double rt = c[2];
-        const unsigned c01 = *reinterpret_cast<const unsigned short*>(&scf[(lr + 1) * FT_CLD + 16 + 2 * tx]);
+        const unsigned c01 = *reinterpret_cast<const unsigned short*>(&scf[(lr + 1) * C::CLD + 16 + 2 * tx]);
         const unsigned cf0 = c01 & 0xffu, cf1 = c01 >> 8;
         const double dE0 = cc.x - cc.y, dE1 = cc.y - rt, dN0 = cc.x - up.x, dN1 = cc.y - up.y;
         double all = 0.0, con = 0.0;
@@ -253,7 +271,7 @@ PERC_HD void ft_phase_energy(const Geom& g, const FtScalars& sc, const double* s
             ft_padd(con, dE0 * dE0, cf0 & NB_E); ft_padd(con, dE1 * dE1, cf1 & NB_E);
             ft_padd(con, dN0 * dN0, cf0 & NB_N); ft_padd(con, dN1 * dN1, cf1 & NB_N);
             if (LAT == LAT_TRIANGULAR) {
-                const double dNW = cc.x - c[FT_LD - 1], dNE = cc.x - up.y;
+                const double dNW = cc.x - c[C::LD - 1], dNE = cc.x - up.y;
                 all += dNW * dNW + dNE * dNE;
                 ft_padd(con, dNW * dNW, cf0 & NB_NW); ft_padd(con, dNE * dNE, cf0 & NB_NE);
             }
@@ -265,7 +283,7 @@ PERC_HD void ft_phase_energy(const Geom& g, const FtScalars& sc, const double* s
             if (e0 & NB_N) { all += dN0 * dN0; ft_padd(con, dN0 * dN0, cf0 & NB_N); }
             if (e1 & NB_N) { all += dN1 * dN1; ft_padd(con, dN1 * dN1, cf1 & NB_N); }
             if (LAT == LAT_TRIANGULAR) {
-                const double dNW = cc.x - c[FT_LD - 1], dNE = cc.x - up.y;
+                const double dNW = cc.x - c[C::LD - 1], dNE = cc.x - up.y;
                 if (e0 & NB_NW) { all += dNW * dNW; ft_padd(con, dNW * dNW, cf0 & NB_NW); }
                 if (e0 & NB_NE) { all += dNE * dNE; ft_padd(con, dNE * dNE, cf0 & NB_NE); }
             }

@@ -48,7 +48,7 @@ void box_copy(T* dst, const T* src, int m, int n, int cx, int cy, int cols, int 
         }
 }
 
-template <int LAT>
+template <int LAT, class C>
 int solve(const Geom& g, const std::vector<uint8_t>& cf, double Va, double g0, double gleak, double tol, int itmax,
           double read_thresh, double* Gtop, double* Gbot, int* iter, double* err, int* tiles_fast)
 {
@@ -72,11 +72,11 @@ int solve(const Geom& g, const std::vector<uint8_t>& cf, double Va, double g0, d
     FtState st{};
     st.bnrm = sqrt(bn); st.tol = tol; st.itmax = itmax;
 
-    std::vector<FtDiag> dtab(64 * 32);
-    for (int k = 0; k < 64 * 32; ++k) dtab[k] = ft_diag_entry(k >> 5, g0, gleak);
-    const int ntx = (m + FT_TX - 1) / FT_TX, nty = (n + FT_TY - 1) / FT_TY;
-    std::vector<double> sr((size_t)FT_RR * FT_LD), ss((size_t)FT_SR * FT_LD), su((size_t)FT_RR * FT_LD);
-    std::vector<uint8_t> scf((size_t)FT_RR * FT_CLD);
+    std::vector<FtDiag> dtab(64 * C::DC);
+    for (int k = 0; k < 64 * C::DC; ++k) dtab[k] = ft_diag_entry(k / C::DC, g0, gleak);
+    const int ntx = (m + C::TX - 1) / C::TX, nty = (n + C::TY - 1) / C::TY;
+    std::vector<double> sr((size_t)C::RR * C::LD), ss((size_t)C::SR * C::LD), su((size_t)C::RR * C::LD);
+    std::vector<uint8_t> scf((size_t)C::RR * C::CLD);
     *tiles_fast = 0;
     int cur = 0;
     for (int pass = 0; !st.done; ++pass) {
@@ -84,20 +84,20 @@ int solve(const Geom& g, const std::vector<uint8_t>& cf, double Va, double g0, d
         const FtScalars sc{g0, gleak, prime ? 0.0 : st.alpha, prime ? 0.0 : st.beta};
         double rz = 0.0, rr = 0.0, en = 0.0;
         for (int tl = 0; tl < ntx * nty; ++tl) {
-            const int x0 = (tl % ntx) * FT_TX, y0 = (tl / ntx) * FT_TY;
-            box_copy(sr.data(), r[cur].data(), m, n, x0 - 2, y0 - 1, FT_LD, FT_RR);
-            box_copy(ss.data(), s[cur].data(), m, n, x0 - 2, y0, FT_LD, FT_SR);
-            box_copy(scf.data(), cf.data(), m, n, x0 - 16, y0 - 1, FT_CLD, FT_RR);
+            const int x0 = (tl % ntx) * C::TX, y0 = (tl / ntx) * C::TY;
+            box_copy(sr.data(), r[cur].data(), m, n, x0 - 2, y0 - 1, C::LD, C::RR);
+            box_copy(ss.data(), s[cur].data(), m, n, x0 - 2, y0, C::LD, C::SR);
+            box_copy(scf.data(), cf.data(), m, n, x0 - 16, y0 - 1, C::CLD, C::RR);
             for (auto& v : su) v = NAN;                        // shared memory starts as garbage
-            const bool interior = ft_interior(g, x0, y0);
+            const bool interior = ft_interior<C>(g, x0, y0);
             if (prime && interior) ++*tiles_fast;
-            for (int tid = 0; tid < FT_THREADS; ++tid) ft_phase_u<LAT>(g, sr.data(), scf.data(), su.data(), dtab.data(), x0, y0, interior, tid);
-            for (int tid = FT_THREADS - 1; tid >= 0; --tid) {
-                ft_phase_main<LAT>(g, sc, sr.data(), ss.data(), scf.data(), su.data(), dtab.data(), x0, y0, interior, tid,
+            for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_u<LAT, C>(g, sr.data(), scf.data(), su.data(), dtab.data(), x0, y0, interior, tid);
+            for (int tid = C::THREADS - 1; tid >= 0; --tid) {
+                ft_phase_main<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), su.data(), dtab.data(), x0, y0, interior, tid,
                                    r[cur ^ 1].data(), s[cur ^ 1].data(), xrow.data(), prow.data(), rz, rr);
-                ft_phase_ringcols<LAT>(g, sc, sr.data(), ss.data(), scf.data(), su.data(), dtab.data(), x0, y0, tid);
+                ft_phase_ringcols<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), su.data(), dtab.data(), x0, y0, tid);
             }
-            for (int tid = 0; tid < FT_THREADS; ++tid) ft_phase_energy<LAT>(g, sc, ss.data(), scf.data(), x0, y0, interior, tid, en);
+            for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_energy<LAT, C>(g, sc, ss.data(), scf.data(), x0, y0, interior, tid, en);
         }
         ft_scalar_step(st, rz, rr, en, prime);
         cur ^= 1;
@@ -125,15 +125,25 @@ int solve(const Geom& g, const std::vector<uint8_t>& cf, double Va, double g0, d
 
 }  // namespace
 
-// w: per-bond weights in reference row order (g0 for conducting bonds, gleak otherwise)
+// w: per-bond weights in reference row order (g0 for conducting bonds, gleak otherwise); cfg: tile configuration
+// (the ones pcg.cu instantiates)
 extern "C" int fused_emul_solve(int lattice, int m, int n, const double* w, double Va, double g0, double gleak,
                                 double tol, int itmax, double read_thresh, double* Gtop, double* Gbot, int* iter,
-                                double* err, int* tiles_fast)
+                                double* err, int* tiles_fast, int cfg)
 {
     if (m % 16 || n < 4) return -2;
     const Geom g = make_geom(lattice, m, n, 0);
     std::vector<uint8_t> cf;
     build_cfull(g, w, gleak, cf);
-    return lattice == LAT_SQUARE ? solve<LAT_SQUARE>(g, cf, Va, g0, gleak, tol, itmax, read_thresh, Gtop, Gbot, iter, err, tiles_fast)
-                                 : solve<LAT_TRIANGULAR>(g, cf, Va, g0, gleak, tol, itmax, read_thresh, Gtop, Gbot, iter, err, tiles_fast);
+#define RUN(CFG) (lattice == LAT_SQUARE ? solve<LAT_SQUARE, CFG>(g, cf, Va, g0, gleak, tol, itmax, read_thresh, Gtop, Gbot, iter, err, tiles_fast) \
+                                        : solve<LAT_TRIANGULAR, CFG>(g, cf, Va, g0, gleak, tol, itmax, read_thresh, Gtop, Gbot, iter, err, tiles_fast))
+    switch (cfg) {
+    case 0: return RUN(FtCfgA);
+    case 1: return RUN(FtCfgB);
+    case 2: return RUN(FtCfgC);
+    case 3: return RUN(FtCfgD);
+    case 4: return RUN(FtCfgE);
+    }
+#undef RUN
+    return -3;
 }

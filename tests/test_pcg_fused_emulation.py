@@ -27,13 +27,13 @@ def emul():
     return C.CDLL(so)
 
 
-def run_emul(lib, lat, m, n, w, tol, itmax, Va=1.0, g0=1.0, gleak=1e-12, read_thresh=1e-10):
+def run_emul(lib, lat, m, n, w, tol, itmax, Va=1.0, g0=1.0, gleak=1e-12, read_thresh=1e-10, cfg=0):
     Gt, Gb, err = C.c_double(), C.c_double(), C.c_double()
     it, fast = C.c_int(), C.c_int()
     w = np.ascontiguousarray(w, np.float64)
     rc = lib.fused_emul_solve(C.c_int(lat), C.c_int(m), C.c_int(n), w.ctypes.data_as(C.POINTER(C.c_double)),
                               C.c_double(Va), C.c_double(g0), C.c_double(gleak), C.c_double(tol), C.c_int(itmax),
-                              C.c_double(read_thresh), C.byref(Gt), C.byref(Gb), C.byref(it), C.byref(err), C.byref(fast))
+                              C.c_double(read_thresh), C.byref(Gt), C.byref(Gb), C.byref(it), C.byref(err), C.byref(fast), C.c_int(cfg))
     assert rc == 0
     return {"Gtop": Gt.value, "Gbot": Gb.value, "iter": it.value, "err": err.value, "tiles_fast": fast.value}
 
@@ -62,8 +62,13 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("lat,kind,m,n,ps,pb", CASES)
-def test_emulated_fused_pcg_matches_oracle(emul, O, lat, kind, m, n, ps, pb):
+# every case with the first tile configuration (pcg_fused_tile.cuh: FtCfgA), a subset with the other two
+SUBSET = [CASES[3], CASES[2], CASES[9], CASES[10]]
+CFG_CASES = [(0,) + c for c in CASES] + [(cfg,) + c for cfg in (1, 2) for c in SUBSET] + [(cfg,) + c for cfg in (3, 4) for c in SUBSET[:2]]
+
+
+@pytest.mark.parametrize("cfg,lat,kind,m,n,ps,pb", CFG_CASES)
+def test_emulated_fused_pcg_matches_oracle(emul, O, cfg, lat, kind, m, n, ps, pb):
     kind = getattr(O, kind)
     for seed in range(20):
         case = spanning_case(O, lat, kind, m, n, ps, pb, 7000 + 13 * m + n + seed)
@@ -73,7 +78,7 @@ def test_emulated_fused_pcg_matches_oracle(emul, O, lat, kind, m, n, ps, pb):
         pytest.fail("no spanning realization among the seeds")
     b1, b2, w = case
     ref = O.conduct_cg(m, n, b1, b2, w, tol=1e-13, itmax=200000)
-    got = run_emul(emul, lat, m, n, w, 1e-13, 200000)
+    got = run_emul(emul, lat, m, n, w, 1e-13, 200000, cfg=cfg)
     assert abs(got["Gtop"] - ref["Gtop"]) <= 1e-9 * abs(ref["Gtop"]), (got, ref["Gtop"])
     assert abs(got["Gbot"] - ref["Gbot"]) <= 1e-9 * abs(ref["Gbot"]), (got, ref["Gbot"])
     assert abs(got["iter"] - ref["iter"]) <= max(3, ref["iter"] // 100), (got["iter"], ref["iter"])
@@ -82,7 +87,7 @@ def test_emulated_fused_pcg_matches_oracle(emul, O, lat, kind, m, n, ps, pb):
         assert got["tiles_fast"] > 0          # the geometry-free fast path was exercised
     # the reference's own defaults (tol 1e-8, itmax 2500, Sq/bondc.f:545): same iteration count, same G to 1e-6
     ref8 = O.conduct_cg(m, n, b1, b2, w)
-    got8 = run_emul(emul, lat, m, n, w, 1e-8, 2500)
+    got8 = run_emul(emul, lat, m, n, w, 1e-8, 2500, cfg=cfg)
     assert abs(got8["iter"] - ref8["iter"]) <= 1
     assert abs(got8["Gtop"] - ref8["Gtop"]) <= 1e-6 * abs(ref8["Gtop"])
 

@@ -13,6 +13,8 @@ ap.add_argument("--ps", type=float, default=0.80)
 ap.add_argument("--pb", type=float, default=0.70)
 ap.add_argument("--lattice", type=int, default=1)
 ap.add_argument("--converge", action="store_true", help="also run both forms to tol 1e-10")
+ap.add_argument("--configs", action="store_true", help="time every tile configuration of the one-pass kernel (perc_set_solver 10..14)")
+ap.add_argument("--fused-only", action="store_true", help="skip the two-kernel form (profiling runs)")
 args = ap.parse_args()
 HBM = 6455.6
 with P.Lattice(args.lattice, args.L, args.L, 0) as L:
@@ -25,7 +27,11 @@ with P.Lattice(args.lattice, args.L, args.L, 0) as L:
         sys.exit("no spanning cluster")
     interior = t - 2 * args.L
     res = {}
-    for name, mode in (("two-kernel", 1), ("one-pass", 0), ("two-kernel", 1), ("one-pass", 0)):
+    runs = (("two-kernel", 1), ("one-pass", 0), ("two-kernel", 1), ("one-pass", 0))
+    if args.configs:
+        runs = tuple(("one-pass-" + "ABCDE"[k], 10 + k) for k in range(5))
+        runs = (() if args.fused_only else (("two-kernel", 1),)) + runs + (() if args.fused_only else (("two-kernel", 1),) + runs)
+    for name, mode in runs:
         L.set_solver(mode)
         t0 = time.perf_counter()
         r = L.conduct(0, tol=1e-300, itmax=args.iters - 1, voltages=False)
@@ -34,11 +40,17 @@ with P.Lattice(args.lattice, args.L, args.L, 0) as L:
         used = L.solver_used()
         per_it = float(ph[5]) / r["iter"]
         bytes_it = (33.0 if used else 50.0) * interior
-        print("%-10s used_fused=%d iters=%d  %.4f ms/iter (solve %.1f ms, wall %.1f ms)  kernels %.4f + %.4f ms  "
+        print("%-11s used_fused=%d iters=%d  %.4f ms/iter (solve %.1f ms, wall %.1f ms)  kernels %.4f + %.4f ms  "
               "%.0f GB/s algorithmic = %.1f%% of %.1f | G=%.12e err=%.3e"
               % (name, used, r["iter"], per_it, ph[5], wall * 1e3, ph[6], ph[7], bytes_it / (per_it * 1e-3) / 1e9,
                  100 * bytes_it / (per_it * 1e-3) / 1e9 / HBM, HBM, r["Gtop"], r["err"]), flush=True)
         res[name] = r
+    if args.configs:
+        names = [n for n in res if n != "two-kernel"]
+        a = res.get("two-kernel", res[names[0]])
+        ok = all(a["iter"] == res[n]["iter"] and abs(a["Gtop"] - res[n]["Gtop"]) <= 1e-9 * abs(a["Gtop"]) for n in names)
+        print("FUSED_OK" if ok else "FUSED_MISMATCH", flush=True)
+        sys.exit(0)
     a, b = res["two-kernel"], res["one-pass"]
     ok = a["iter"] == b["iter"] and abs(a["Gtop"] - b["Gtop"]) <= 1e-9 * abs(a["Gtop"]) and abs(a["Gbot"] - b["Gbot"]) <= 1e-9 * abs(a["Gbot"])
     ok = ok and abs(a["err"] - b["err"]) <= 1e-6 * abs(a["err"])
