@@ -668,9 +668,8 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
 // each); everything else takes the two-kernel path.  Consecutive iterations sweep the tiles in opposite
 // directions, so each starts on the part of r / s the previous one wrote last (still in L2).
 // ------------------------------------------------------------------------------------------
-static_assert(FtCfgA::SMEM <= 227 * 1024 && FtCfgB::SMEM <= 227 * 1024 && 2 * (FtCfgC::SMEM + 1024) <= 228 * 1024 &&
-              2 * (FtCfgD::SMEM + 1024) <= 228 * 1024 && 3 * (FtCfgE::SMEM + 1024) <= 228 * 1024,
-              "fused PCG tile does not fit the shared memory of one SM");
+static_assert(FtCfgA::SMEM <= 227 * 1024 && FtCfgA2::SMEM <= 227 * 1024 && FtCfgA3::SMEM <= 227 * 1024 &&
+              FtCfgA3L::SMEM <= 227 * 1024 && FtCfgA3R::SMEM <= 227 * 1024, "fused PCG tile does not fit the shared memory of one SM");
 
 // block sums of three values at once (fixed order: lanes by shuffles, then warp 0 folds the per-warp partials by
 // shuffles); result valid in thread 0
@@ -704,8 +703,8 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
 {
     if (st->done) return;
     extern __shared__ __align__(128) unsigned char ft_raw[];
-    double* su = reinterpret_cast<double*>(ft_raw + 2 * (size_t)C::STAGE_BYTES);
-    FtDiag* dtab = reinterpret_cast<FtDiag*>(ft_raw + 2 * (size_t)C::STAGE_BYTES + C::R_BYTES);      // [64][DC]
+    double* su = reinterpret_cast<double*>(ft_raw + 2 * (size_t)C::STAGE_BYTES);                      // phase U (not with V = 3)
+    FtDiag* dtab = reinterpret_cast<FtDiag*>(ft_raw + 2 * (size_t)C::STAGE_BYTES + C::U_BYTES);      // [64][DC]
     double* sh = reinterpret_cast<double*>(dtab + 64 * C::DC);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sh + 96);                      // one mbarrier per stage
     const int tid = threadIdx.x;
@@ -722,42 +721,69 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
     auto stage_s = [&](int k) { return reinterpret_cast<double*>(ft_raw + (size_t)k * C::STAGE_BYTES + C::R_BYTES); };
     auto stage_cf = [&](int k) { return reinterpret_cast<uint8_t*>(ft_raw + (size_t)k * C::STAGE_BYTES + C::R_BYTES + C::S_BYTES); };
     // one thread, three TMA tensor copies: r (tile + 2-site halo), s (tile + east / north / west ring), conduct bytes
-    auto issue = [&](int k, int tl) {
+    auto issue = [&](int k, int x0, int y0) {
         if (tid != 0) return;
-        const int x0 = (tl % ntx) * C::TX, y0 = (tl / ntx) * C::TY;
         mbar_arrive_expect(&bars[k], (unsigned)(C::RR * C::LD * 8 + C::SR * C::LD * 8 + C::RR * C::CLD));
         tma_box_g2s(stage_r(k), &tm_r, x0 - 2, y0 - 1, &bars[k]);
         tma_box_g2s(stage_s(k), &tm_s, x0 - 2, y0, &bars[k]);
         tma_box_g2s(stage_cf(k), &tm_cf, x0 - 16, y0 - 1, &bars[k]);
     };
 
+    // tile coordinates advance incrementally (a CTA's tiles are gridDim.x apart: no division per tile)
+    const int G = (int)gridDim.x, dxs = G % ntx, dys = G / ntx;
+    auto advance = [&](int& ix, int& iy) {
+        if (rev) { ix -= dxs; iy -= dys; if (ix < 0) { ix += ntx; --iy; } }
+        else     { ix += dxs; iy += dys; if (ix >= ntx) { ix -= ntx; ++iy; } }
+    };
     int t = blockIdx.x;
-    if (t < ntiles) issue(0, tile_of(t));
-    for (int k = 0; t < ntiles; t += gridDim.x, ++k) {
-        const int tl = tile_of(t), x0 = (tl % ntx) * C::TX, y0 = (tl / ntx) * C::TY;
-        const int tn = t + gridDim.x;
-        if (tn < ntiles) issue((k + 1) & 1, tile_of(tn));      // the other stage was released by the barriers of the last tile
+    int ix = 0, iy = 0;                                          // tile t
+    if (t < ntiles) { const int tl = tile_of(t); ix = tl % ntx; iy = tl / ntx; issue(0, ix * C::TX, iy * C::TY); }
+    int nx = ix, ny = iy;                                        // tile t + gridDim.x
+    advance(nx, ny);
+    double rz = 0.0, rr = 0.0, en = 0.0;
+    for (int k = 0; t < ntiles; t += G, ++k) {
+        const int x0 = ix * C::TX, y0 = iy * C::TY;
+        if (t + G < ntiles) issue((k + 1) & 1, nx * C::TX, ny * C::TY);     // the other stage was released by the barriers of the last tile
         mbar_wait(&bars[k & 1], (unsigned)((k >> 1) & 1));
         const double* sr = stage_r(k & 1);
         double* ss = stage_s(k & 1);
         const uint8_t* scf = stage_cf(k & 1);
         const bool interior = ft_interior<C>(g, x0, y0);
-        ft_phase_u<LAT, C>(g, sr, scf, su, dtab, x0, y0, interior, tid);
-        __syncthreads();
-        double rz = 0.0, rr = 0.0, en = 0.0;
-        ft_phase_main<LAT, C>(g, sc, sr, ss, scf, su, dtab, x0, y0, interior, tid, r_out, s_out, xrow, prow, rz, rr);
-        ft_phase_ringcols<LAT, C>(g, sc, sr, ss, scf, su, dtab, x0, y0, tid);
+        if (!C::USTATE) {
+            ft_phase_u<LAT, C>(g, sr, scf, su, dtab, x0, y0, interior, tid);
+            __syncthreads();
+        }
+        const double* uu = C::USTATE ? sr : su;                 // V = 3: the staged vector IS u
+        if (C::V == 1) { rz = 0.0; rr = 0.0; en = 0.0; }
+        ft_phase_main<LAT, C>(g, sc, sr, ss, scf, uu, dtab, x0, y0, interior, tid, r_out, s_out, xrow, prow, rz, rr);
+        ft_phase_ringcols<LAT, C>(g, sc, sr, ss, scf, uu, dtab, x0, y0, tid);
         __syncthreads();
         ft_phase_energy<LAT, C>(g, sc, ss, scf, x0, y0, interior, tid, en);
         // generic-proxy accesses to this stage are ordered before the bulk copies that will refill it
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        block_sum3(rz, rr, en, sh);                             // synchronises: every thread is done with the stage
-        if (tid == 0) { partial[tl * 3 + 0] = rz; partial[tl * 3 + 1] = rr; partial[tl * 3 + 2] = en; }
+        if (C::V == 1) {
+            // per-tile partial sums, folded in tile order: the result does not depend on the number of CTAs
+            const int tl = iy * ntx + ix;
+            double a = rz, b = rr, c = en;
+            block_sum3(a, b, c, sh);                            // synchronises: every thread is done with the stage
+            if (tid == 0) { partial[tl * 3 + 0] = a; partial[tl * 3 + 1] = b; partial[tl * 3 + 2] = c; }
+        } else {
+            __syncthreads();                                    // every thread is done with the stage
+        }
+        ix = nx; iy = ny;
+        advance(nx, ny);
+    }
+    int nparts = ntiles;
+    if (C::V >= 2) {
+        // the sums stayed in registers over all tiles of this CTA: one reduction per CTA, folded in CTA order
+        block_sum3(rz, rr, en, sh);
+        if (tid == 0) { partial[blockIdx.x * 3 + 0] = rz; partial[blockIdx.x * 3 + 1] = rr; partial[blockIdx.x * 3 + 2] = en; }
+        nparts = G;
     }
     if (last_block(&st->ticket_a)) {
-        const double fz = fold_partials(partial, ntiles, 3, 0, sh);
-        const double fr = fold_partials(partial, ntiles, 3, 1, sh);
-        const double fe = fold_partials(partial, ntiles, 3, 2, sh);
+        const double fz = fold_partials(partial, nparts, 3, 0, sh);
+        const double fr = fold_partials(partial, nparts, 3, 1, sh);
+        const double fe = fold_partials(partial, nparts, 3, 2, sh);
         if (threadIdx.x == 0) {
             FtState f;
             f.gamma = st->bknum; f.alpha = st->ak; f.beta = st->bk; f.bnrm = st->bnrm; f.err = st->err; f.rr = st->rr;
@@ -1069,6 +1095,19 @@ bool pcg_fused_applies(const Ctx* c, int keep_x, int warm)
 // the iteration loop of the one-pass kernel; on entry (after pcg_init_kernel) vr = b, vp = vx = 0, the scalars of
 // the solve are initialised.  Buffers: r ping-pongs between vr and vp, s between vp2 and vx; x / p of rows 1 and
 // n-2 live in xprow and are copied into vx for the read-out at the end.
+// V = 3 of the one-pass kernel keeps u = D^-1 r in HBM: turn the initial residual into u (the unknown rows only;
+// everything else is and stays 0)
+__global__ void __launch_bounds__(256)
+pcg_scale_u_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double* __restrict__ vr)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + g.m;
+    if (i >= g.t - g.m) return;
+    const double r = vr[i];
+    if (r == 0.0) return;
+    const int x = (int)(i % g.m), y = (int)(i / g.m);
+    vr[i] = r / diag_of(cfull[i], neighbour_bits(g, x, y), prm.g0, prm.gleak);
+}
+
 template <class C>
 static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
 {
@@ -1106,6 +1145,10 @@ static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
         cur ^= 1; ++pass;
         c->launches++;
     };
+    if (C::USTATE) {
+        pcg_scale_u_kernel<<<nblk64(g.t - 2 * (int64_t)g.m), 256, 0, s>>>(g, prm, c->cfull, c->vr);
+        c->launches++;
+    }
     launch(1);                     // s = A D^-1 b and delta0: alpha0, beta0 = 0
     float it_ms = 0.f; int nsamp = 0;
     int chunk = 32, iters_before = 0;
@@ -1137,21 +1180,19 @@ static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
     return 0;
 }
 
-// tile configuration of the one-pass kernel: PERC_FUSED_CFG = A | B | C (default: see below)
+// variant of the one-pass kernel (FtCfg::V): PERC_FUSED_CFG = 1 | 2 | 3, default 3
 static int pcg_fused_loop(Ctx* c, const PcgParams& prm)
 {
     static int cfg = -1;
     if (cfg < 0) {
         const char* e = getenv("PERC_FUSED_CFG");
-        cfg = (e && *e >= 'A' && *e <= 'E') ? *e - 'A' : 0;
+        cfg = (e && *e >= '1' && *e <= '5') ? *e - '1' : 2;
     }
     const int use = c->fused_cfg >= 0 ? c->fused_cfg : cfg;
-    switch (use) {
-    case 1: return pcg_fused_loop_t<FtCfgB>(c, prm);
-    case 2: return pcg_fused_loop_t<FtCfgC>(c, prm);
-    case 3: return pcg_fused_loop_t<FtCfgD>(c, prm);
-    case 4: return pcg_fused_loop_t<FtCfgE>(c, prm);
-    }
+    if (use == 1) return pcg_fused_loop_t<FtCfgA2>(c, prm);
+    if (use == 2) return pcg_fused_loop_t<FtCfgA3>(c, prm);
+    if (use == 3) return pcg_fused_loop_t<FtCfgA3L>(c, prm);
+    if (use == 4) return pcg_fused_loop_t<FtCfgA3R>(c, prm);
     return pcg_fused_loop_t<FtCfgA>(c, prm);
 }
 
@@ -1177,7 +1218,7 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     int need = (int)(sgrid.x * sgrid.y);
     if (need < ugrid * 3) need = ugrid * 3;
     if (need < 2 * ntiles) need = 2 * ntiles;
-    { const int nf = 3 * ((g.m + FtCfgE::TX - 1) / FtCfgE::TX) * ((g.n + FtCfgE::TY - 1) / FtCfgE::TY); if (need < nf) need = nf; }
+    { const int nf = 3 * ((g.m + FtCfgA::TX - 1) / FtCfgA::TX) * ((g.n + FtCfgA::TY - 1) / FtCfgA::TY); if (need < nf) need = nf; }
     const int want_x = keep_x;
     if (!vec) keep_x = 1;                // the scalar fallback always forms x
     if (need > c->partial_cap) {

@@ -28,14 +28,21 @@
 namespace perc {
 
 // tile configuration: TY tile rows, RPT consecutive rows per thread (sliding 3-row window), DC private copies of
-// the diagonal table (32 = one per lane, conflict-free; 8 = a quarter of the shared memory)
-template <int TY_, int RPT_, int DC_, int CTAS_>
+// the diagonal table (32 = one per lane, conflict-free), V = 1: the ring columns are done by the first threads
+// after their own rows and every tile ends with a block reduction; V = 2: two extra warps own the ring columns
+// (the others do not wait for them) and the sums stay in registers until the CTA has done all its tiles; V = 3: as
+// V = 2, and the state vector in HBM is u = D^-1 r instead of r (u' = u - alpha D^-1 s'): phase U and its shared
+// array disappear, the residual is formed only inside the sums (r = d u)
+template <int TY_, int RPT_, int DC_, int CTAS_, int V_>
 struct FtCfg {
-    static constexpr int TX = 128, TY = TY_, RPT = RPT_, DC = DC_, CTAS = CTAS_;   // CTAS: resident CTAs per SM
+    static constexpr int TX = 128, TY = TY_, RPT = RPT_, DC = DC_, CTAS = CTAS_, V = V_;   // CTAS: resident CTAs per SM
     static constexpr int NG = (TY + 1) / RPT;               // row groups
     static_assert(NG * RPT == TY + 1, "compute rows (tile + north ring row) must split evenly");
-    static constexpr int THREADS = 64 * NG;                 // 2 columns per thread
+    static constexpr int MAIN_THREADS = 64 * NG;            // 2 columns per thread
     static constexpr int CR = TY + 1;                       // compute rows: gy = y0 + lr, lr = 0 .. TY (last = north ring)
+    static constexpr int RING_T0 = V == 1 ? 0 : MAIN_THREADS;    // first thread that works on the ring columns
+    static constexpr int RING_NT = V == 1 ? 2 * CR : 64;         // ... and how many of them share the 2 CR ring sites
+    static constexpr int THREADS = V == 1 ? MAIN_THREADS : MAIN_THREADS + RING_NT;
     static constexpr int RR = TY + 3;                       // staged rows of r, conduct bytes, u: gy = y0 - 1 + pr
     static constexpr int SR = TY + 1;                       // staged rows of s:                   gy = y0 + ps
     static constexpr int LD = TX + 4;                       // doubles per staged row: column c <-> gx = x0 - 2 + c
@@ -45,15 +52,20 @@ struct FtCfg {
     static constexpr int CF_BYTES = (RR * CLD + 127) / 128 * 128;
     static constexpr int STAGE_BYTES = R_BYTES + S_BYTES + CF_BYTES;
     static constexpr int TAB_BYTES = 64 * DC * 16;
-    static constexpr int SMEM = 2 * STAGE_BYTES + R_BYTES + TAB_BYTES + 96 * 8 + 16;
+    static constexpr bool USTATE = V == 3;
+    static constexpr int U_BYTES = USTATE ? 0 : R_BYTES;    // shared u array of phase U
+    static constexpr int SMEM = 2 * STAGE_BYTES + U_BYTES + TAB_BYTES + 96 * 8 + 16;
+    // table of diagonals: entry (#conducting bonds << 3 | #leaking bonds), DC private copies
     static PERC_HD int tab(int nc, int nl, int lane) { return ((nc << 3) | nl) * DC + (lane & (DC - 1)); }
+    // ... of a site with all its DEG neighbours (fast path): nl = DEG - nc, (nc << 3 | DEG - nc) = 7 nc + DEG
+    static PERC_HD int tab_full(int nc, int deg, int lane) { return nc * (7 * DC) + (deg * DC + (lane & (DC - 1))); }
 };
 
-typedef FtCfg<32, 3, 32, 1> FtCfgA;      // 704 threads, one CTA per SM
-typedef FtCfg<31, 2, 32, 1> FtCfgB;      // 1024 threads, one CTA per SM
-typedef FtCfg<15, 2, 8, 2> FtCfgC;       // 512 threads, two CTAs per SM
-typedef FtCfg<15, 4, 8, 2> FtCfgD;       // 256 threads, two CTAs per SM
-typedef FtCfg<9, 2, 8, 3> FtCfgE;        // 320 threads, three CTAs per SM
+typedef FtCfg<32, 3, 32, 1, 1> FtCfgA;      // 704 threads
+typedef FtCfg<32, 3, 32, 1, 2> FtCfgA2;     // 768 threads (two ring warps), one reduction per CTA
+typedef FtCfg<32, 3, 32, 1, 3> FtCfgA3;     // ... and u = D^-1 r as the state vector (no phase U)
+typedef FtCfg<35, 3, 32, 1, 3> FtCfgA3L;    // the same with 35-row tiles (768 + 64 threads)
+typedef FtCfg<39, 4, 32, 1, 3> FtCfgA3R;    // the same with 39-row tiles, 4 rows per thread (640 + 64 threads)
 
 #ifdef __CUDACC__
 typedef double2 ft_d2;
@@ -130,8 +142,9 @@ PERC_HD void ft_phase_u(const Geom& g, const double* sr, const uint8_t* scf, dou
                 e1 = (gx + 1 >= 0 && gx + 1 < g.m) ? neighbour_bits(g, gx + 1, gy) : 0u;
             }
             const int n0 = ft_popc(c01 & 0xffu & e0), n1 = ft_popc((c01 >> 8) & e1);
-            u0 = r2.x * dtab[C::tab(n0, ft_popc(e0) - n0, lane)].inv;
-            u1 = r2.y * dtab[C::tab(n1, ft_popc(e1) - n1, lane)].inv;
+            constexpr int DEG = LAT == LAT_SQUARE ? 4 : 6;
+            u0 = r2.x * dtab[interior ? C::tab_full(n0, DEG, lane) : C::tab(n0, ft_popc(e0) - n0, lane)].inv;
+            u1 = r2.y * dtab[interior ? C::tab_full(n1, DEG, lane) : C::tab(n1, ft_popc(e1) - n1, lane)].inv;
         }
         ft_st2(&su[pr * C::LD + 2 * cp], u0, u1);
     }
@@ -146,6 +159,7 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
                            double* __restrict__ r_out, double* __restrict__ s_out, double* __restrict__ xrow,
                            double* __restrict__ prow, double& acc_rz, double& acc_rr)
 {
+    if (tid >= C::MAIN_THREADS) return;
     const int tx = tid & 63, ty = tid >> 6, lane = tid & 31;
     const int gx = x0 + 2 * tx, lr0 = ty * C::RPT;
     const double dg = sc.g0 - sc.gleak, alpha = sc.alpha, beta = sc.beta;
@@ -188,19 +202,28 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
             ft_padd(con1, dn.x, cf1 & NB_SW);         ft_padd(con1, drt, cf1 & NB_SE);
         }
         const int n0 = ft_popc(cf0), n1 = ft_popc(cf1);
-        const FtDiag t0 = dtab[C::tab(n0, ft_popc(e0) - n0, lane)], t1 = dtab[C::tab(n1, ft_popc(e1) - n1, lane)];
+        constexpr int DEG = LAT == LAT_SQUARE ? 4 : 6;
+        const FtDiag t0 = dtab[interior ? C::tab_full(n0, DEG, lane) : C::tab(n0, ft_popc(e0) - n0, lane)];
+        const FtDiag t1 = dtab[interior ? C::tab_full(n1, DEG, lane) : C::tab(n1, ft_popc(e1) - n1, lane)];
         const double w0 = t0.d * cc.x - (sc.gleak * all0 + dg * con0);
         const double w1 = t1.d * cc.y - (sc.gleak * all1 + dg * con1);
         double* sp = &ss[lr * C::LD + 2 + 2 * tx];
         const ft_d2 s2 = ft_ld2(sp), r2 = ft_ld2(&sr[(lr + 1) * C::LD + 2 + 2 * tx]);
         const double sn0 = w0 + beta * s2.x, sn1 = w1 + beta * s2.y;
-        const double rn0 = r2.x - alpha * sn0, rn1 = r2.y - alpha * sn1;
-        ft_st2(sp, valid ? rn0 * t0.inv : 0.0, valid ? rn1 * t1.inv : 0.0);
+        double rn0, rn1, un0, un1;
+        if (C::USTATE) {                                     // sr / su hold u: u' = u - alpha D^-1 s', r' = d u'
+            un0 = cc.x - alpha * (sn0 * t0.inv); un1 = cc.y - alpha * (sn1 * t1.inv);
+            rn0 = t0.d * un0; rn1 = t1.d * un1;
+        } else {
+            rn0 = r2.x - alpha * sn0; rn1 = r2.y - alpha * sn1;
+            un0 = rn0 * t0.inv; un1 = rn1 * t1.inv;
+        }
+        ft_st2(sp, valid ? un0 : 0.0, valid ? un1 : 0.0);
         if (valid && lr < C::TY) {
             const int64_t i = (int64_t)gy * g.m + gx;
             ft_st2(s_out + i, sn0, sn1);
-            ft_st2(r_out + i, rn0, rn1);
-            acc_rz += rn0 * rn0 * t0.inv + rn1 * rn1 * t1.inv;
+            if (C::USTATE) ft_st2(r_out + i, un0, un1); else ft_st2(r_out + i, rn0, rn1);
+            acc_rz += rn0 * un0 + rn1 * un1;
             acc_rr += rn0 * rn0 + rn1 * rn1;
             if (gy == 1 || gy == g.n - 2) {                  // the rows the read-out consumes: p = u + beta p, x += alpha p
                 const int64_t o = (gy == 1 ? 0 : g.m) + gx;
@@ -220,8 +243,9 @@ template <int LAT, class C>
 PERC_HD void ft_phase_ringcols(const Geom& g, const FtScalars& sc, const double* sr, double* ss, const uint8_t* scf,
                                const double* su, const FtDiag* dtab, int x0, int y0, int tid)
 {
-    if (tid >= 2 * C::CR) return;
-    const int side = tid >= C::CR, lr = tid - side * C::CR, lane = tid & 31;
+    const int lane = tid & 31;
+    for (int q = tid - C::RING_T0; q >= 0 && q < 2 * C::CR; q += C::RING_NT) {
+    const int side = q >= C::CR, lr = q - side * C::CR;
     const int gy = y0 + lr, gx = side ? x0 + C::TX : x0 - 1, col = side ? 2 + C::TX : 1;
     double un = 0.0;
     if (gy >= 1 && gy <= g.n - 2 && gx >= 0 && gx < g.m) {
@@ -237,10 +261,11 @@ PERC_HD void ft_phase_ringcols(const Geom& g, const FtScalars& sc, const double*
         const FtDiag t = dtab[C::tab(nc, ft_popc(ex) - nc, lane)];
         const double w = t.d * c[0] - (sc.gleak * all + (sc.g0 - sc.gleak) * con);
         const double sn = w + sc.beta * ss[lr * C::LD + col];
-        const double rn = sr[(lr + 1) * C::LD + col] - sc.alpha * sn;
-        un = rn * t.inv;
+        if (C::USTATE) un = c[0] - sc.alpha * (sn * t.inv);
+        else un = (sr[(lr + 1) * C::LD + col] - sc.alpha * sn) * t.inv;
     }
     ss[lr * C::LD + col] = un;
+    }
 }
 
 // ---- phase E: u'.A u' as the energy of the bonds OWNED by the tile's sites (E, N, NW, NE), u' from shared
@@ -249,6 +274,7 @@ template <int LAT, class C>
 PERC_HD void ft_phase_energy(const Geom& g, const FtScalars& sc, const double* ss, const uint8_t* scf, int x0, int y0,
                              bool interior, int tid, double& acc_e)
 {
+    if (tid >= C::MAIN_THREADS) return;
     const int tx = tid & 63, ty = tid >> 6;
     const int gx = x0 + 2 * tx, lr0 = ty * C::RPT;
     const double dg = sc.g0 - sc.gleak;

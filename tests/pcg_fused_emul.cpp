@@ -65,8 +65,8 @@ int solve(const Geom& g, const std::vector<uint8_t>& cf, double Va, double g0, d
         if (ex & NB_N)  b += ((c & NB_N)  ? g0 : gleak) * Va;
         if (ex & NB_NW) b += ((c & NB_NW) ? g0 : gleak) * Va;
         if (ex & NB_NE) b += ((c & NB_NE) ? g0 : gleak) * Va;
-        r[0][(size_t)y * m + x] = b;
         const double z = b / diag_of(g, cf, x, y, g0, gleak);
+        r[0][(size_t)y * m + x] = C::USTATE ? z : b;          // V = 3: the state vector is u = D^-1 r
         bn += z * z;
     }
     FtState st{};
@@ -91,11 +91,13 @@ int solve(const Geom& g, const std::vector<uint8_t>& cf, double Va, double g0, d
             for (auto& v : su) v = NAN;                        // shared memory starts as garbage
             const bool interior = ft_interior<C>(g, x0, y0);
             if (prime && interior) ++*tiles_fast;
-            for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_u<LAT, C>(g, sr.data(), scf.data(), su.data(), dtab.data(), x0, y0, interior, tid);
+            if (!C::USTATE)
+                for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_u<LAT, C>(g, sr.data(), scf.data(), su.data(), dtab.data(), x0, y0, interior, tid);
+            const double* up = C::USTATE ? sr.data() : su.data();
             for (int tid = C::THREADS - 1; tid >= 0; --tid) {
-                ft_phase_main<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), su.data(), dtab.data(), x0, y0, interior, tid,
+                ft_phase_main<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), x0, y0, interior, tid,
                                    r[cur ^ 1].data(), s[cur ^ 1].data(), xrow.data(), prow.data(), rz, rr);
-                ft_phase_ringcols<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), su.data(), dtab.data(), x0, y0, tid);
+                ft_phase_ringcols<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), x0, y0, tid);
             }
             for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_energy<LAT, C>(g, sc, ss.data(), scf.data(), x0, y0, interior, tid, en);
         }
@@ -139,10 +141,10 @@ extern "C" int fused_emul_solve(int lattice, int m, int n, const double* w, doub
                                         : solve<LAT_TRIANGULAR, CFG>(g, cf, Va, g0, gleak, tol, itmax, read_thresh, Gtop, Gbot, iter, err, tiles_fast))
     switch (cfg) {
     case 0: return RUN(FtCfgA);
-    case 1: return RUN(FtCfgB);
-    case 2: return RUN(FtCfgC);
-    case 3: return RUN(FtCfgD);
-    case 4: return RUN(FtCfgE);
+    case 1: return RUN(FtCfgA2);
+    case 2: return RUN(FtCfgA3);
+    case 3: return RUN(FtCfgA3L);
+    case 4: return RUN(FtCfgA3R);
     }
 #undef RUN
     return -3;

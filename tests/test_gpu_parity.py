@@ -264,15 +264,22 @@ def test_one_pass_solver_equals_two_kernel_solver(P, O, lat, kind, m, n, ps, pb)
                 L.set_solver(1)
                 a = L.conduct(0, tol=tol, itmax=itmax, voltages=False)
                 assert L.solver_used() == 0
-                L.set_solver(0)
-                b = L.conduct(0, tol=tol, itmax=itmax, voltages=False)
-                assert L.solver_used() == 1
-                rel = 1e-9 if tol < 1e-10 else 1e-6
-                assert abs(a["Gtop"] - b["Gtop"]) <= rel * abs(a["Gtop"]), (tol, a, b)
-                assert abs(a["Gbot"] - b["Gbot"]) <= rel * abs(a["Gbot"]), (tol, a, b)
-                assert abs(a["iter"] - b["iter"]) <= max(3, a["iter"] // 100), (tol, a, b)
-                if a["iter"] <= itmax:
-                    assert b["err"] <= tol
+                # 0 = the default variant of the one-pass kernel; 10 / 11 = its other two variants (diagnostic modes)
+                for mode in (0, 10, 11):
+                    L.set_solver(mode)
+                    b = L.conduct(0, tol=tol, itmax=itmax, voltages=False)
+                    assert L.solver_used() == 1
+                    rel = 1e-9 if tol < 1e-10 else 1e-6
+                    if a["iter"] > itmax:
+                        # stopped by itmax, not converged: the two arrangements of the recurrences drift apart
+                        # like any two finite-precision CG runs; they agree to about the residual they stopped at
+                        rel = max(rel, a["err"])
+                    assert abs(a["Gtop"] - b["Gtop"]) <= rel * abs(a["Gtop"]), (mode, tol, a, b)
+                    assert abs(a["Gbot"] - b["Gbot"]) <= rel * abs(a["Gbot"]), (mode, tol, a, b)
+                    assert abs(a["iter"] - b["iter"]) <= max(3, a["iter"] // 100), (mode, tol, a, b)
+                    if a["iter"] <= itmax:
+                        assert b["err"] <= tol
+            L.set_solver(0)
             if t <= 60000:
                 b1, b2 = O.bondlist(lat, m, n, 0)
                 socc, bocc = L.get_occupancy(sites=kind != 2, bonds=kind != 1)

@@ -62,9 +62,9 @@ CASES = [
 ]
 
 
-# every case with the first tile configuration (pcg_fused_tile.cuh: FtCfgA), a subset with the other two
+# every case with the default tile configuration (pcg_fused_tile.cuh: FtCfgA3 = 2), a subset with the other two
 SUBSET = [CASES[3], CASES[2], CASES[9], CASES[10]]
-CFG_CASES = [(0,) + c for c in CASES] + [(cfg,) + c for cfg in (1, 2) for c in SUBSET] + [(cfg,) + c for cfg in (3, 4) for c in SUBSET[:2]]
+CFG_CASES = [(2,) + c for c in CASES] + [(cfg,) + c for cfg in (0, 1, 3, 4) for c in SUBSET]
 
 
 @pytest.mark.parametrize("cfg,lat,kind,m,n,ps,pb", CFG_CASES)
