@@ -195,7 +195,7 @@ def workload_config(args):
                         % (args.L, args.ps, args.pb),
             "lattice": "square", "L": args.L, "ps": args.ps, "pb": args.pb, "tol": args.tol,
             "occupancy": "Philox-4x32-10 exact-count generator, one stream per realization",
-            "l2": "per-iteration working set %.2f GB > 126 MB L2 (no flush needed)" % (3 * 8 * args.L * args.L / 1e9),
+            "l2": "per-iteration working set %.2f GB > 126 MB L2 (no flush needed)" % (4 * 8 * args.L * args.L / 1e9),
             "conduct": "perc_conduct (voltages kept)" if getattr(args, "voltages", False) else
                        "perc_conduct_g (Gtop/Gbot of the p-sweep drivers; interior voltages not formed)",
             "parallelism": "realizations sharded over %d GPU(s), one final NCCL all-reduce of statistics" % args.gpus}
@@ -337,8 +337,8 @@ def run_ours(args):
             # one-pass iteration kernel: r 8 + s 8 + conduct byte 1 read; r 8 + s 8 written
             spmv_bytes = 33.0 * interior
             roof_key = "pcg_fused_kernel"
-            roof_name = ("pcg_fused_kernel (one Jacobi-PCG iteration in one persistent TMA-fed pass: s = A D^-1 r + beta s, "
-                         "r -= alpha s, sums r.r/d, r.r and the bond energy of D^-1 r; p and x only on the read-out rows)")
+            roof_name = ("pcg_fused_kernel (one Jacobi-PCG iteration in one persistent TMA-fed pass over u = D^-1 r and s = A p: "
+                         "s = A u + beta s, u -= alpha D^-1 s, sums r.u, r.r and the bond energy u.A u; p and x only on the read-out rows)")
         else:
             spmv_bytes = 25.0 * interior          # r 8 + p_old 8 + conduct byte 1 read; p 8 written (q = A p is never stored)
             roof_key = "pcg_pipe_kernel<0>"

@@ -289,7 +289,7 @@ def test_one_pass_solver_equals_two_kernel_solver(P, O, lat, kind, m, n, ps, pb)
                 b = L.conduct(0, tol=1e-13, itmax=2000000, voltages=False)
                 assert abs(b["Gtop"] - ref["Gtop"]) <= 1e-9 * abs(ref["Gtop"])
                 assert abs(b["Gbot"] - ref["Gbot"]) <= 1e-9 * abs(ref["Gbot"])
-            if found == 2:
+            if found == 2 or t > 60000:
                 break
         assert found >= 1
 

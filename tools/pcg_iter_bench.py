@@ -15,6 +15,7 @@ ap.add_argument("--lattice", type=int, default=1)
 ap.add_argument("--converge", action="store_true", help="also run both forms to tol 1e-10")
 ap.add_argument("--configs", action="store_true", help="time every tile configuration of the one-pass kernel (perc_set_solver 10 .. 14)")
 ap.add_argument("--fused-only", action="store_true", help="skip the two-kernel form (profiling runs)")
+ap.add_argument("--default-only", action="store_true", help="one solve with the default solver (profiling runs)")
 args = ap.parse_args()
 HBM = 6455.6
 with P.Lattice(args.lattice, args.L, args.L, 0) as L:
@@ -31,6 +32,8 @@ with P.Lattice(args.lattice, args.L, args.L, 0) as L:
     if args.configs:
         runs = tuple(("one-pass-v%d" % (k + 1), 10 + k) for k in range(5))
         runs = (() if args.fused_only else (("two-kernel", 1),)) + runs + (() if args.fused_only else (("two-kernel", 1),) + runs)
+    if args.default_only:
+        runs = (("one-pass", 0),)
     for name, mode in runs:
         try:
             L.set_solver(mode)
@@ -49,6 +52,8 @@ with P.Lattice(args.lattice, args.L, args.L, 0) as L:
               % (name, used, r["iter"], per_it, ph[5], wall * 1e3, ph[6], ph[7], bytes_it / (per_it * 1e-3) / 1e9,
                  100 * bytes_it / (per_it * 1e-3) / 1e9 / HBM, HBM, r["Gtop"], r["err"]), flush=True)
         res[name] = r
+    if args.default_only:
+        sys.exit(0)
     if args.configs:
         names = [n for n in res if n != "two-kernel"]
         a = res.get("two-kernel", res[names[0]])
