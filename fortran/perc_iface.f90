@@ -308,6 +308,20 @@ module perc_iface
       real(c_double), intent(out) :: Vint(*)
     end function
 
+    ! iteration kernels of the conductance solve: mode 0 (default) = the one-pass kernel wherever it applies
+    ! (perc_conduct_g, one GPU, pbc = 0), mode 1 = always the two-kernel form (iter is linbcg's count exactly)
+    integer(c_int32_t) function perc_set_solver(h, mode) bind(C, name="perc_set_solver")
+      import :: c_int32_t, c_int64_t
+      integer(c_int64_t), intent(in) :: h
+      integer(c_int32_t), intent(in) :: mode
+    end function
+
+    integer(c_int32_t) function perc_solver_used(h, fused) bind(C, name="perc_solver_used")
+      import :: c_int32_t, c_int64_t
+      integer(c_int64_t), intent(in) :: h
+      integer(c_int32_t), intent(out) :: fused
+    end function
+
     integer(c_int32_t) function perc_launch_count(h, count) bind(C, name="perc_launch_count")
       import :: c_int32_t, c_int64_t
       integer(c_int64_t), intent(in) :: h
