@@ -334,7 +334,7 @@ def run_ours(args):
         ccl_ms = float(np.mean(stats["ccl_ms"]))
         fused = bool(stats["fused"]) and all(stats["fused"])
         if fused:
-            # one-pass iteration kernel: r 8 + s 8 + conduct byte 1 read; r 8 + s 8 written
+            # one-pass iteration kernel: u 8 + s 8 + conduct byte 1 read; u 8 + s 8 written
             spmv_bytes = 33.0 * interior
             roof_key = "pcg_fused_kernel"
             roof_name = ("pcg_fused_kernel (one Jacobi-PCG iteration in one persistent TMA-fed pass over u = D^-1 r and s = A p: "
@@ -344,7 +344,7 @@ def run_ours(args):
             roof_key = "pcg_pipe_kernel<0>"
             roof_name = "pcg_pipe_kernel<0> (persistent TMA tile pipeline: p = r/d + bk p, p.Ap as bond energies; q = A p is never stored)"
         upd_bytes = (41.0 if args.voltages else 25.0) * interior   # p 8 + r 8 + byte read, r 8 written (+ x 8 + 8)
-        ach = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+        ach = spmv_bytes / (max(spmv_ms, 1e-9) * 1e-3) / 1e9
         value = world * args.steps / (ms_total * 1e-3)
         mean_iters = st[3] / max(st[2], 1)
         line = {
