@@ -23,7 +23,7 @@ def needs_build():
     if not os.path.exists(SO):
         return True
     mt = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS + ["ccl_tile.cuh", "slab.h", "slab_stitch.cuh"]] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS + ["ccl_tile.cuh", "pcg_fused_tile.cuh", "slab.h", "slab_stitch.cuh"]] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > mt for d in deps)
 
 
