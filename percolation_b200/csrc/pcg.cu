@@ -669,7 +669,7 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
 // directions, so each starts on the part of r / s the previous one wrote last (still in L2).
 // ------------------------------------------------------------------------------------------
 static_assert(FtCfgA::SMEM <= 227 * 1024 && FtCfgA2::SMEM <= 227 * 1024 && FtCfgA3::SMEM <= 227 * 1024 &&
-              FtCfgA3L::SMEM <= 227 * 1024 && FtCfgA3R::SMEM <= 227 * 1024, "fused PCG tile does not fit the shared memory of one SM");
+              FtCfgA3L::SMEM <= 227 * 1024 && FtCfgA3R::SMEM <= 227 * 1024 && FtCfgA4::SMEM <= 227 * 1024, "fused PCG tile does not fit the shared memory of one SM");
 
 // block sums of three values at once (fixed order: lanes by shuffles, then warp 0 folds the per-warp partials by
 // shuffles); result valid in thread 0
@@ -755,10 +755,13 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         }
         const double* uu = C::USTATE ? sr : su;                 // V = 3: the staged vector IS u
         if (C::V == 1) { rz = 0.0; rr = 0.0; en = 0.0; }
-        ft_phase_main<LAT, C>(g, sc, sr, ss, scf, uu, dtab, x0, y0, interior, tid, r_out, s_out, xrow, prow, rz, rr);
+        // (C::SPLIT: the geometry-free tiles run their own instantiation; `interior` is uniform over the CTA)
+        if (C::SPLIT && interior) ft_phase_main<LAT, C, true>(g, sc, sr, ss, scf, uu, dtab, x0, y0, true, tid, r_out, s_out, xrow, prow, rz, rr);
+        else ft_phase_main<LAT, C, false>(g, sc, sr, ss, scf, uu, dtab, x0, y0, interior, tid, r_out, s_out, xrow, prow, rz, rr);
         ft_phase_ringcols<LAT, C>(g, sc, sr, ss, scf, uu, dtab, x0, y0, tid);
         __syncthreads();
-        ft_phase_energy<LAT, C>(g, sc, ss, scf, x0, y0, interior, tid, en);
+        if (C::SPLIT && interior) ft_phase_energy<LAT, C, true>(g, sc, ss, scf, x0, y0, true, tid, en);
+        else ft_phase_energy<LAT, C, false>(g, sc, ss, scf, x0, y0, interior, tid, en);
         // generic-proxy accesses to this stage are ordered before the bulk copies that will refill it
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (C::V == 1) {
@@ -1180,19 +1183,21 @@ static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
     return 0;
 }
 
-// variant of the one-pass kernel (FtCfg::V): PERC_FUSED_CFG = 1 | 2 | 3, default 3
+// variant of the one-pass kernel: PERC_FUSED_CFG = 1 .. 6 (FtCfgA, A2, A3, A3L, A3R, A4), default 3 = FtCfgA3 (the one
+// measured and profiled on the GPU in round 1; FtCfgA4 is bit-identical on the host emulation and has not run on a GPU yet)
 static int pcg_fused_loop(Ctx* c, const PcgParams& prm)
 {
     static int cfg = -1;
     if (cfg < 0) {
         const char* e = getenv("PERC_FUSED_CFG");
-        cfg = (e && *e >= '1' && *e <= '5') ? *e - '1' : 2;
+        cfg = (e && *e >= '1' && *e <= '6') ? *e - '1' : 2;
     }
     const int use = c->fused_cfg >= 0 ? c->fused_cfg : cfg;
     if (use == 1) return pcg_fused_loop_t<FtCfgA2>(c, prm);
     if (use == 2) return pcg_fused_loop_t<FtCfgA3>(c, prm);
     if (use == 3) return pcg_fused_loop_t<FtCfgA3L>(c, prm);
     if (use == 4) return pcg_fused_loop_t<FtCfgA3R>(c, prm);
+    if (use == 5) return pcg_fused_loop_t<FtCfgA4>(c, prm);
     return pcg_fused_loop_t<FtCfgA>(c, prm);
 }
 

@@ -52,7 +52,8 @@ struct FtCfg {
     static constexpr int CF_BYTES = (RR * CLD + 127) / 128 * 128;
     static constexpr int STAGE_BYTES = R_BYTES + S_BYTES + CF_BYTES;
     static constexpr int TAB_BYTES = 64 * DC * 16;
-    static constexpr bool USTATE = V == 3;
+    static constexpr bool USTATE = V >= 3;
+    static constexpr bool SPLIT = V >= 4;                   // tiles with the full neighbourhood run their own instantiation
     static constexpr int U_BYTES = USTATE ? 0 : R_BYTES;    // shared u array of phase U
     static constexpr int SMEM = 2 * STAGE_BYTES + U_BYTES + TAB_BYTES + 96 * 8 + 16;
     // table of diagonals: entry (#conducting bonds << 3 | #leaking bonds), DC private copies
@@ -64,6 +65,7 @@ struct FtCfg {
 typedef FtCfg<32, 3, 32, 1, 1> FtCfgA;      // 704 threads
 typedef FtCfg<32, 3, 32, 1, 2> FtCfgA2;     // 768 threads (two ring warps), one reduction per CTA
 typedef FtCfg<32, 3, 32, 1, 3> FtCfgA3;     // ... and u = D^-1 r as the state vector (no phase U)
+typedef FtCfg<32, 3, 32, 1, 4> FtCfgA4;     // the same arithmetic with fewer instructions (see above)
 typedef FtCfg<35, 3, 32, 1, 3> FtCfgA3L;    // the same with 35-row tiles (768 + 64 threads)
 typedef FtCfg<39, 4, 32, 1, 3> FtCfgA3R;    // the same with 39-row tiles, 4 rows per thread (640 + 64 threads)
 
@@ -86,7 +88,7 @@ PERC_HD int ft_popc(unsigned v)
     return __builtin_popcount(v);
 #endif
 }
-// acc += v if bit != 0 (device: one predicated DADD)
+// acc += v if bit != 0 (device: one predicated DADD, which ptxas turns into DADD + two selects)
 PERC_HD void ft_padd(double& acc, double v, unsigned bit)
 {
 #ifdef __CUDA_ARCH__
@@ -94,6 +96,13 @@ PERC_HD void ft_padd(double& acc, double v, unsigned bit)
 #else
     if (bit) acc += v;
 #endif
+}
+// the same value as a fused multiply-add by 1.0 / 0.0: fma(1, v, acc) = acc + v and fma(0, v, acc) = acc exactly
+// (v is finite), one select of the multiplier's high word + one DFMA
+PERC_HD void ft_padd_fma(double& acc, double v, unsigned bit) { acc = fma(bit ? 1.0 : 0.0, v, acc); }
+template <class C> PERC_HD void ft_cadd(double& acc, double v, unsigned bit)
+{
+    if (C::SPLIT) ft_padd_fma(acc, v, bit); else ft_padd(acc, v, bit);
 }
 template <int LAT> PERC_HD unsigned ft_interior_ex(int gx)
 {
@@ -153,13 +162,16 @@ PERC_HD void ft_phase_u(const Geom& g, const double* sr, const uint8_t* scf, dou
 // ---- phase M: w = A u, s' = w + beta s, r' = r - alpha s', u' = r'/d on the compute rows; stores r', s' of
 // the tile rows; u' replaces s in shared memory (each thread overwrites only what it has read itself);
 // p / x of the two read-out rows; sums r'.u' and r'.r' over the tile's sites ---------------------------------
-template <int LAT, class C>
+// FAST (only with C::SPLIT): the tile is geometry-free (ft_interior) by construction of the call -- the runtime flag is
+// not consulted, every compute row is an unknown row with its full neighbourhood and none of them is a read-out row
+template <int LAT, class C, bool FAST = false>
 PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr, double* ss, const uint8_t* scf,
-                           const double* su, const FtDiag* dtab, int x0, int y0, bool interior, int tid,
+                           const double* su, const FtDiag* dtab, int x0, int y0, bool interior_flag, int tid,
                            double* __restrict__ r_out, double* __restrict__ s_out, double* __restrict__ xrow,
                            double* __restrict__ prow, double& acc_rz, double& acc_rr)
 {
     if (tid >= C::MAIN_THREADS) return;
+    const bool interior = C::SPLIT ? FAST : interior_flag;
     const int tx = tid & 63, ty = tid >> 6, lane = tid & 31;
     const int gx = x0 + 2 * tx, lr0 = ty * C::RPT;
     const double dg = sc.g0 - sc.gleak, alpha = sc.alpha, beta = sc.beta;
@@ -195,11 +207,11 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
             }
         }
         double con0 = 0.0, con1 = 0.0;                       // conducting neighbours
-        ft_padd(con0, cc.y, cf0 & NB_E); ft_padd(con0, lf, cf0 & NB_W);   ft_padd(con0, up.x, cf0 & NB_N); ft_padd(con0, dn.x, cf0 & NB_S);
-        ft_padd(con1, rt, cf1 & NB_E);   ft_padd(con1, cc.x, cf1 & NB_W); ft_padd(con1, up.y, cf1 & NB_N); ft_padd(con1, dn.y, cf1 & NB_S);
+        ft_cadd<C>(con0, cc.y, cf0 & NB_E); ft_cadd<C>(con0, lf, cf0 & NB_W);   ft_cadd<C>(con0, up.x, cf0 & NB_N); ft_cadd<C>(con0, dn.x, cf0 & NB_S);
+        ft_cadd<C>(con1, rt, cf1 & NB_E);   ft_cadd<C>(con1, cc.x, cf1 & NB_W); ft_cadd<C>(con1, up.y, cf1 & NB_N); ft_cadd<C>(con1, dn.y, cf1 & NB_S);
         if (LAT == LAT_TRIANGULAR) {
-            ft_padd(con0, c[C::LD - 1], cf0 & NB_NW); ft_padd(con0, up.y, cf0 & NB_NE);
-            ft_padd(con1, dn.x, cf1 & NB_SW);         ft_padd(con1, drt, cf1 & NB_SE);
+            ft_cadd<C>(con0, c[C::LD - 1], cf0 & NB_NW); ft_cadd<C>(con0, up.y, cf0 & NB_NE);
+            ft_cadd<C>(con1, dn.x, cf1 & NB_SW);         ft_cadd<C>(con1, drt, cf1 & NB_SE);
         }
         const int n0 = ft_popc(cf0), n1 = ft_popc(cf1);
         constexpr int DEG = LAT == LAT_SQUARE ? 4 : 6;
@@ -225,7 +237,9 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
             if (C::USTATE) ft_st2(r_out + i, un0, un1); else ft_st2(r_out + i, rn0, rn1);
             acc_rz += rn0 * un0 + rn1 * un1;
             acc_rr += rn0 * rn0 + rn1 * rn1;
-            if (gy == 1 || gy == g.n - 2) {                  // the rows the read-out consumes: p = u + beta p, x += alpha p
+            // the rows the read-out consumes: p = u + beta p, x += alpha p (never inside a geometry-free tile: its rows
+            // lie in [TY, n-3])
+            if (!(C::SPLIT && FAST) && (gy == 1 || gy == g.n - 2)) {
                 const int64_t o = (gy == 1 ? 0 : g.m) + gx;
                 const ft_d2 p2 = ft_ld2(prow + o), x2 = ft_ld2(xrow + o);
                 const double p0 = cc.x + beta * p2.x, p1 = cc.y + beta * p2.y;
@@ -270,11 +284,12 @@ PERC_HD void ft_phase_ringcols(const Geom& g, const FtScalars& sc, const double*
 
 // ---- phase E: u'.A u' as the energy of the bonds OWNED by the tile's sites (E, N, NW, NE), u' from shared
 // memory (zeros on Dirichlet rows and outside the lattice) ---------------------------------------------------
-template <int LAT, class C>
+template <int LAT, class C, bool FAST = false>
 PERC_HD void ft_phase_energy(const Geom& g, const FtScalars& sc, const double* ss, const uint8_t* scf, int x0, int y0,
-                             bool interior, int tid, double& acc_e)
+                             bool interior_flag, int tid, double& acc_e)
 {
     if (tid >= C::MAIN_THREADS) return;
+    const bool interior = C::SPLIT ? FAST : interior_flag;
     const int tx = tid & 63, ty = tid >> 6;
     const int gx = x0 + 2 * tx, lr0 = ty * C::RPT;
     const double dg = sc.g0 - sc.gleak;
@@ -294,24 +309,24 @@ PERC_HD void ft_phase_energy(const Geom& g, const FtScalars& sc, const double* s
         double all = 0.0, con = 0.0;
         if (interior) {
             all = (dE0 * dE0 + dE1 * dE1) + (dN0 * dN0 + dN1 * dN1);
-            ft_padd(con, dE0 * dE0, cf0 & NB_E); ft_padd(con, dE1 * dE1, cf1 & NB_E);
-            ft_padd(con, dN0 * dN0, cf0 & NB_N); ft_padd(con, dN1 * dN1, cf1 & NB_N);
+            ft_cadd<C>(con, dE0 * dE0, cf0 & NB_E); ft_cadd<C>(con, dE1 * dE1, cf1 & NB_E);
+            ft_cadd<C>(con, dN0 * dN0, cf0 & NB_N); ft_cadd<C>(con, dN1 * dN1, cf1 & NB_N);
             if (LAT == LAT_TRIANGULAR) {
                 const double dNW = cc.x - c[C::LD - 1], dNE = cc.x - up.y;
                 all += dNW * dNW + dNE * dNE;
-                ft_padd(con, dNW * dNW, cf0 & NB_NW); ft_padd(con, dNE * dNE, cf0 & NB_NE);
+                ft_cadd<C>(con, dNW * dNW, cf0 & NB_NW); ft_cadd<C>(con, dNE * dNE, cf0 & NB_NE);
             }
         } else {
             const unsigned e0 = neighbour_bits(g, gx, gy), e1 = neighbour_bits(g, gx + 1, gy);
             const bool rowE = gy >= 1 && gy <= g.n - 2;      // an E bond joins two sites of one row
-            if (rowE && (e0 & NB_E)) { all += dE0 * dE0; ft_padd(con, dE0 * dE0, cf0 & NB_E); }
-            if (rowE && (e1 & NB_E)) { all += dE1 * dE1; ft_padd(con, dE1 * dE1, cf1 & NB_E); }
-            if (e0 & NB_N) { all += dN0 * dN0; ft_padd(con, dN0 * dN0, cf0 & NB_N); }
-            if (e1 & NB_N) { all += dN1 * dN1; ft_padd(con, dN1 * dN1, cf1 & NB_N); }
+            if (rowE && (e0 & NB_E)) { all += dE0 * dE0; ft_cadd<C>(con, dE0 * dE0, cf0 & NB_E); }
+            if (rowE && (e1 & NB_E)) { all += dE1 * dE1; ft_cadd<C>(con, dE1 * dE1, cf1 & NB_E); }
+            if (e0 & NB_N) { all += dN0 * dN0; ft_cadd<C>(con, dN0 * dN0, cf0 & NB_N); }
+            if (e1 & NB_N) { all += dN1 * dN1; ft_cadd<C>(con, dN1 * dN1, cf1 & NB_N); }
             if (LAT == LAT_TRIANGULAR) {
                 const double dNW = cc.x - c[C::LD - 1], dNE = cc.x - up.y;
-                if (e0 & NB_NW) { all += dNW * dNW; ft_padd(con, dNW * dNW, cf0 & NB_NW); }
-                if (e0 & NB_NE) { all += dNE * dNE; ft_padd(con, dNE * dNE, cf0 & NB_NE); }
+                if (e0 & NB_NW) { all += dNW * dNW; ft_cadd<C>(con, dNW * dNW, cf0 & NB_NW); }
+                if (e0 & NB_NE) { all += dNE * dNE; ft_cadd<C>(con, dNE * dNE, cf0 & NB_NE); }
             }
         }
         acc_e += sc.gleak * all + dg * con;

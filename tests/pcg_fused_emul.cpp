@@ -95,11 +95,18 @@ int solve(const Geom& g, const std::vector<uint8_t>& cf, double Va, double g0, d
                 for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_u<LAT, C>(g, sr.data(), scf.data(), su.data(), dtab.data(), x0, y0, interior, tid);
             const double* up = C::USTATE ? sr.data() : su.data();
             for (int tid = C::THREADS - 1; tid >= 0; --tid) {
-                ft_phase_main<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), x0, y0, interior, tid,
-                                   r[cur ^ 1].data(), s[cur ^ 1].data(), xrow.data(), prow.data(), rz, rr);
+                if (C::SPLIT && interior)
+                    ft_phase_main<LAT, C, true>(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), x0, y0, true, tid,
+                                                r[cur ^ 1].data(), s[cur ^ 1].data(), xrow.data(), prow.data(), rz, rr);
+                else
+                    ft_phase_main<LAT, C, false>(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), x0, y0, interior, tid,
+                                                 r[cur ^ 1].data(), s[cur ^ 1].data(), xrow.data(), prow.data(), rz, rr);
                 ft_phase_ringcols<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), x0, y0, tid);
             }
-            for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_energy<LAT, C>(g, sc, ss.data(), scf.data(), x0, y0, interior, tid, en);
+            for (int tid = 0; tid < C::THREADS; ++tid) {
+                if (C::SPLIT && interior) ft_phase_energy<LAT, C, true>(g, sc, ss.data(), scf.data(), x0, y0, true, tid, en);
+                else ft_phase_energy<LAT, C, false>(g, sc, ss.data(), scf.data(), x0, y0, interior, tid, en);
+            }
         }
         ft_scalar_step(st, rz, rr, en, prime);
         cur ^= 1;
@@ -145,6 +152,7 @@ extern "C" int fused_emul_solve(int lattice, int m, int n, const double* w, doub
     case 2: return RUN(FtCfgA3);
     case 3: return RUN(FtCfgA3L);
     case 4: return RUN(FtCfgA3R);
+    case 5: return RUN(FtCfgA4);
     }
 #undef RUN
     return -3;

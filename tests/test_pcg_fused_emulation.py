@@ -62,10 +62,11 @@ CASES = [
 ]
 
 
-# every case with the default variant (pcg_fused_tile.cuh: FtCfgA3 = 2); one case with interior tiles for each of the
-# other variants the library instantiates (0 FtCfgA, 1 FtCfgA2, 3 FtCfgA3L, 4 FtCfgA3R)
-CFG_CASES = [(2,) + c for c in CASES] + [(0, 1, "MIXED", 400, 84, 0.85, 0.72), (1, 2, "BOND", 400, 84, 0.0, 0.40),
-                                         (3, 1, "SITE", 400, 84, 0.65, 0.0), (4, 2, "MIXED", 400, 84, 0.8, 0.6)]
+# every case with the default variant (pcg_fused_tile.cuh: FtCfgA3 = 2) and, bit for bit, with FtCfgA4 = 5; one case with
+# interior tiles for each of the other variants the library instantiates (0 FtCfgA, 1 FtCfgA2, 3 FtCfgA3L, 4 FtCfgA3R)
+DEFAULT_CFG = 2
+CFG_CASES = [(DEFAULT_CFG,) + c for c in CASES] + [(0, 1, "MIXED", 400, 84, 0.85, 0.72), (1, 2, "BOND", 400, 84, 0.0, 0.40),
+                                                   (3, 1, "SITE", 400, 84, 0.65, 0.0), (4, 2, "MIXED", 400, 84, 0.8, 0.6)]
 
 
 @pytest.mark.parametrize("cfg,lat,kind,m,n,ps,pb", CFG_CASES)
@@ -86,8 +87,12 @@ def test_emulated_fused_pcg_matches_oracle(emul, O, cfg, lat, kind, m, n, ps, pb
     assert got["err"] <= 1e-13
     if m >= 400 and n >= 70:
         assert got["tiles_fast"] > 0          # the geometry-free fast path was exercised
-    if cfg != 2:
+    if cfg != DEFAULT_CFG:
         return
+    # FtCfgA4 is FtCfgA3 with fewer instructions (own instantiation for the geometry-free tiles, the conducting sums
+    # as multiply-adds by 0 / 1): the arithmetic must be the same to the last bit
+    a4 = run_emul(emul, lat, m, n, w, 1e-13, 200000, cfg=5)
+    assert (a4["Gtop"], a4["Gbot"], a4["iter"], a4["err"]) == (got["Gtop"], got["Gbot"], got["iter"], got["err"])
     # the reference's own defaults (tol 1e-8, itmax 2500, Sq/bondc.f:545): same iteration count, same G to 1e-6
     ref8 = O.conduct_cg(m, n, b1, b2, w)
     got8 = run_emul(emul, lat, m, n, w, 1e-8, 2500, cfg=cfg)
