@@ -196,8 +196,9 @@ int32_t perc_allreduce_stats(const int64_t *h, const int32_t *ni, int64_t *ivals
  *           (Chronopoulos-Gear form of the same Jacobi-PCG recurrences, one reduction per iteration, 33 B per
  *           site and iteration); every other call runs the two-kernel form;
  *   mode 1: always the two-kernel form (50 B per site and iteration; iter is linbcg's count exactly);
- *   modes 10 .. 15 (diagnostic): the one-pass kernel in one of its variants (pcg_fused_tile.cuh: FtCfgA, A2,
- *           A3 = the default, A3L, A3R, A4).
+ *   modes 10 / 12 / 15 (diagnostic): the one-pass kernel in one of its variants (pcg_fused_tile.cuh): FtCfgA
+ *           (per-tile partial sums folded in tile order: the result does not depend on the number of SMs),
+ *           FtCfgA3 (the default), FtCfgA4 (the default's arithmetic with fewer instructions).
  * The process-wide default can be set with the environment variable PERC_PCG_SOLVER=classic|fused.
  * perc_solver_used reports which one the handle's last solve ran (1 = one-pass kernel). */
 int32_t perc_set_solver(const int64_t *h, const int32_t *mode);

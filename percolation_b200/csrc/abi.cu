@@ -744,8 +744,8 @@ int32_t perc_phase_ms(const int64_t* h, const int32_t* nphase, float* ms)
 int32_t perc_set_solver(const int64_t* h, const int32_t* mode)
 {
     GET_CTX(h);
-    if (!mode || *mode < 0 || (*mode > 1 && (*mode < 10 || *mode > 15))) return PERC_E_ARG;
-    // 10 .. 15 (diagnostic): the one-pass kernel, variant FtCfgA / A2 / A3 / A3L / A3R / A4 (pcg_fused_tile.cuh)
+    if (!mode || *mode < 0 || (*mode > 1 && (*mode != 10 && *mode != 12 && *mode != 15))) return PERC_E_ARG;
+    // 10 / 12 / 15 (diagnostic): the one-pass kernel, variant FtCfgA / FtCfgA3 (the default) / FtCfgA4 (pcg_fused_tile.cuh)
     const int pm = *mode >= 10 ? 0 : *mode, fc = *mode >= 10 ? *mode - 10 : -1;
     c->pcg_mode = pm; c->fused_cfg = fc;
     for (Ctx* k : c->batch_kids) { k->pcg_mode = pm; k->fused_cfg = fc; }

@@ -668,8 +668,7 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
 // each); everything else takes the two-kernel path.  Consecutive iterations sweep the tiles in opposite
 // directions, so each starts on the part of r / s the previous one wrote last (still in L2).
 // ------------------------------------------------------------------------------------------
-static_assert(FtCfgA::SMEM <= 227 * 1024 && FtCfgA2::SMEM <= 227 * 1024 && FtCfgA3::SMEM <= 227 * 1024 &&
-              FtCfgA3L::SMEM <= 227 * 1024 && FtCfgA3R::SMEM <= 227 * 1024 && FtCfgA4::SMEM <= 227 * 1024, "fused PCG tile does not fit the shared memory of one SM");
+static_assert(FtCfgA::SMEM <= 227 * 1024 && FtCfgA3::SMEM <= 227 * 1024 && FtCfgA4::SMEM <= 227 * 1024, "fused PCG tile does not fit the shared memory of one SM");
 
 // block sums of three values at once (fixed order: lanes by shuffles, then warp 0 folds the per-warp partials by
 // shuffles); result valid in thread 0
@@ -1183,20 +1182,17 @@ static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
     return 0;
 }
 
-// variant of the one-pass kernel: PERC_FUSED_CFG = 1 .. 6 (FtCfgA, A2, A3, A3L, A3R, A4), default 3 = FtCfgA3 (the one
+// variant of the one-pass kernel: PERC_FUSED_CFG = 1 | 3 | 6 (FtCfgA, FtCfgA3, FtCfgA4), default 3 = FtCfgA3 (the one
 // measured and profiled on the GPU in round 1; FtCfgA4 is bit-identical on the host emulation and has not run on a GPU yet)
 static int pcg_fused_loop(Ctx* c, const PcgParams& prm)
 {
     static int cfg = -1;
     if (cfg < 0) {
         const char* e = getenv("PERC_FUSED_CFG");
-        cfg = (e && *e >= '1' && *e <= '6') ? *e - '1' : 2;
+        cfg = (e && (*e == '1' || *e == '3' || *e == '6')) ? *e - '1' : 2;
     }
     const int use = c->fused_cfg >= 0 ? c->fused_cfg : cfg;
-    if (use == 1) return pcg_fused_loop_t<FtCfgA2>(c, prm);
     if (use == 2) return pcg_fused_loop_t<FtCfgA3>(c, prm);
-    if (use == 3) return pcg_fused_loop_t<FtCfgA3L>(c, prm);
-    if (use == 4) return pcg_fused_loop_t<FtCfgA3R>(c, prm);
     if (use == 5) return pcg_fused_loop_t<FtCfgA4>(c, prm);
     return pcg_fused_loop_t<FtCfgA>(c, prm);
 }

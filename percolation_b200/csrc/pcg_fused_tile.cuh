@@ -63,11 +63,8 @@ struct FtCfg {
 };
 
 typedef FtCfg<32, 3, 32, 1, 1> FtCfgA;      // 704 threads
-typedef FtCfg<32, 3, 32, 1, 2> FtCfgA2;     // 768 threads (two ring warps), one reduction per CTA
-typedef FtCfg<32, 3, 32, 1, 3> FtCfgA3;     // ... and u = D^-1 r as the state vector (no phase U)
+typedef FtCfg<32, 3, 32, 1, 3> FtCfgA3;     // 768 threads (two ring warps), one reduction per CTA, u = D^-1 r as the state vector
 typedef FtCfg<32, 3, 32, 1, 4> FtCfgA4;     // the same arithmetic with fewer instructions (see above)
-typedef FtCfg<35, 3, 32, 1, 3> FtCfgA3L;    // the same with 35-row tiles (768 + 64 threads)
-typedef FtCfg<39, 4, 32, 1, 3> FtCfgA3R;    // the same with 39-row tiles, 4 rows per thread (640 + 64 threads)
 
 #ifdef __CUDACC__
 typedef double2 ft_d2;

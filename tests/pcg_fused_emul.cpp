@@ -148,10 +148,7 @@ extern "C" int fused_emul_solve(int lattice, int m, int n, const double* w, doub
                                         : solve<LAT_TRIANGULAR, CFG>(g, cf, Va, g0, gleak, tol, itmax, read_thresh, Gtop, Gbot, iter, err, tiles_fast))
     switch (cfg) {
     case 0: return RUN(FtCfgA);
-    case 1: return RUN(FtCfgA2);
     case 2: return RUN(FtCfgA3);
-    case 3: return RUN(FtCfgA3L);
-    case 4: return RUN(FtCfgA3R);
     case 5: return RUN(FtCfgA4);
     }
 #undef RUN

@@ -264,8 +264,8 @@ def test_one_pass_solver_equals_two_kernel_solver(P, O, lat, kind, m, n, ps, pb)
                 L.set_solver(1)
                 a = L.conduct(0, tol=tol, itmax=itmax, voltages=False)
                 assert L.solver_used() == 0
-                # 0 = the default variant of the one-pass kernel; 10 / 11 = its other two variants (diagnostic modes)
-                for mode in (0, 10, 11):
+                # 0 = the default variant of the one-pass kernel (12 names it explicitly); 10 = its first variant
+                for mode in (0, 10, 12):
                     L.set_solver(mode)
                     b = L.conduct(0, tol=tol, itmax=itmax, voltages=False)
                     assert L.solver_used() == 1

@@ -13,7 +13,7 @@ ap.add_argument("--ps", type=float, default=0.80)
 ap.add_argument("--pb", type=float, default=0.70)
 ap.add_argument("--lattice", type=int, default=1)
 ap.add_argument("--converge", action="store_true", help="also run both forms to tol 1e-10")
-ap.add_argument("--configs", action="store_true", help="time every tile configuration of the one-pass kernel (perc_set_solver 10 .. 15)")
+ap.add_argument("--configs", action="store_true", help="time every tile configuration of the one-pass kernel (perc_set_solver 10 / 12 / 15)")
 ap.add_argument("--fused-only", action="store_true", help="skip the two-kernel form (profiling runs)")
 ap.add_argument("--default-only", action="store_true", help="one solve with the default solver (profiling runs)")
 args = ap.parse_args()
@@ -30,7 +30,7 @@ with P.Lattice(args.lattice, args.L, args.L, 0) as L:
     res = {}
     runs = (("two-kernel", 1), ("one-pass", 0), ("two-kernel", 1), ("one-pass", 0))
     if args.configs:
-        runs = tuple(("one-pass-v%d" % (k + 1), 10 + k) for k in range(6))
+        runs = tuple(("one-pass-" + nm, md) for nm, md in (("A", 10), ("A3", 12), ("A4", 15)))
         runs = (() if args.fused_only else (("two-kernel", 1),)) + runs + (() if args.fused_only else (("two-kernel", 1),) + runs)
     if args.default_only:
         runs = (("one-pass", 0),)
