@@ -33,3 +33,25 @@ def test_our_arm_needs_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode != 0 and "no CUDA device" in (out.stdout + out.stderr)
+
+
+def test_e2e_host_inputs_are_the_drivers_orders():
+    """the host-side inputs of bench.py's e2e leg: a site permutation of 1..t and the bond list permuted as pairs"""
+    import importlib.util
+    import numpy as np
+    import torch
+    import percolation_b200 as P
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    m = n = 24
+    t = m * n
+    b1, b2 = P.geom_bondlist(P.SQUARE, m, n, 0)
+    nb = len(b1)
+    ins = bench.e2e_host_inputs(np.random.default_rng(5), t, nb, b1, b2, 2, lambda k: torch.empty(k, dtype=torch.int32))
+    assert len(ins) == 2
+    for hs, hb in ins:
+        so, bo = hs.numpy(), hb.numpy()
+        assert so.dtype == np.int32 and sorted(so.tolist()) == list(range(1, t + 1))
+        assert sorted(zip(bo[:nb].tolist(), bo[nb:].tolist())) == sorted(zip(b1.tolist(), b2.tolist()))
+    assert (ins[0][0].numpy() != ins[1][0].numpy()).any()
