@@ -17,6 +17,7 @@
 //   K5  ccl_span_kernel     labels present in row 0 and in row n-1
 #include <algorithm>
 #include <cstddef>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "context.h"
@@ -26,7 +27,7 @@ namespace perc {
 // ------------------------------------------------------------------------------------------
 // K2: tile-local labeling
 // ------------------------------------------------------------------------------------------
-template <int LAT, int KIND>
+template <int LAT, int KIND, int VAR>
 __global__ void __launch_bounds__(CT_THREADS)
 ccl_local_kernel(Geom g, const uint8_t* __restrict__ mask, int32_t* __restrict__ label, int32_t* __restrict__ size,
                  int32_t* __restrict__ rootlist, Summary* __restrict__ sum, int vec)
@@ -48,12 +49,12 @@ ccl_local_kernel(Geom g, const uint8_t* __restrict__ mask, int32_t* __restrict__
     tile_phase2_level<LAT, 5>(s, tid); __syncthreads();
     tile_phase2_level<LAT, 6>(s, tid); __syncthreads();
     tile_clear_ring(s, tid); __syncthreads();
-    tile_phase3<LAT, KIND>(s, g, x0, y0, tid, r);
+    tile_phase3<LAT, KIND, VAR>(s, g, x0, y0, tid, r);
     __syncthreads();
     tile_phase4_fill(s, g, x0, y0, tid, r, size);
     __syncthreads();
     if (tid == 0) tile_phase4_reserve(s, sum);
-    tile_phase4_labels(s, g, x0, y0, tid, label, vec != 0);
+    tile_phase4_labels<VAR>(s, g, x0, y0, tid, label, vec != 0);
     __syncthreads();
     tile_phase4_roots(s, g, x0, y0, tid, r, size, rootlist);
 }
@@ -225,19 +226,29 @@ export_bond_labels_kernel(Geom g, int kind, const uint8_t* __restrict__ mask, co
 // ------------------------------------------------------------------------------------------
 static unsigned nblk(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
-template <int LAT, int KIND>
-static cudaError_t launch_local(Ctx* c, dim3 grid, int vec)
+template <int LAT, int KIND, int VAR>
+static cudaError_t launch_local_v(Ctx* c, dim3 grid, int vec)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ccl_local_kernel<LAT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(ccl_local_kernel<LAT, KIND, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)tile_smem_bytes<LAT>());
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    ccl_local_kernel<LAT, KIND><<<grid, CT_THREADS, tile_smem_bytes<LAT>(), c->stream>>>(c->g, c->mask, c->label, c->size,
-                                                                                  c->rootlist, c->d_sum, vec);
+    ccl_local_kernel<LAT, KIND, VAR><<<grid, CT_THREADS, tile_smem_bytes<LAT>(), c->stream>>>(c->g, c->mask, c->label, c->size,
+                                                                                       c->rootlist, c->d_sum, vec);
     return cudaGetLastError();
+}
+
+// PERC_CCL_VAR=1 selects the opt-in variant of the tile kernel (ccl_tile.cuh: per-site roots derived in the label
+// phase); it is bit-identical on the host emulation and has not run on a GPU yet, so it is not the default
+template <int LAT, int KIND>
+static cudaError_t launch_local(Ctx* c, dim3 grid, int vec)
+{
+    static int var = -1;
+    if (var < 0) { const char* e = getenv("PERC_CCL_VAR"); var = (e && *e == '1') ? 1 : 0; }
+    return var == 1 ? launch_local_v<LAT, KIND, 1>(c, grid, vec) : launch_local_v<LAT, KIND, 0>(c, grid, vec);
 }
 
 int ccl_launch(Ctx* c, int kind)

@@ -343,7 +343,9 @@ PERC_HD void tile_clear_ring(TileSmem& s, int tid)
 // site); mixed (Sq/sitebond.f:231-305) = site + owned occupied bonds + incoming occupied bonds whose
 // owner site is unoccupied (dangling onto this site).  A bond with no occupied end is a lone
 // size-1 cluster (Sq/sitebond.f:231-242), counted into s.lone.
-template <int LAT, int KIND>
+// VAR = 1 (opt-in, PERC_CCL_VAR=1): the per-site root staging below is skipped; tile_phase4_labels<1> derives
+// each site's root from its run start instead
+template <int LAT, int KIND, int VAR = 0>
 PERC_HD void tile_phase3(TileSmem& s, const Geom& g, int x0, int y0, int tid, TileRegs& r)
 {
     const int w = tid % CT_NW, ly = tid / CT_NW, pr = ly + 1;
@@ -417,7 +419,8 @@ PERC_HD void tile_phase3(TileSmem& s, const Geom& g, int x0, int y0, int tid, Ti
         s.lab[base + a] = root;
         // spread the root over the other sites of the run: their entries of s.lab are no union-find nodes
         // (no find ever reads them), they stage the per-site root for the coalesced label output
-        for (uint32_t sg = seg & ~(1u << a); sg; sg &= sg - 1) s.lab[base + lobit(sg)] = root;
+        if (VAR == 0)
+            for (uint32_t sg = seg & ~(1u << a); sg; sg &= sg - 1) s.lab[base + lobit(sg)] = root;
         if (root == base + a) rootbits |= 1u << a;
         int wgt;
         if (!owned) wgt = 0;
@@ -492,6 +495,10 @@ PERC_HD void tile_phase4_reserve(TileSmem& s, Summary* sum)
 }
 
 // provisional labels: 32 threads per tile row, 4 consecutive sites each (128-bit stores)
+// VAR = 0: s.lab holds the root of every active site (staged by phase 3); VAR = 1: only of the run starts -- a site's run
+// start is the highest node bit at or below it (an active site that is no run start continues the run of its left
+// neighbour, which the same thread has just resolved)
+template <int VAR = 0>
 PERC_HD void tile_phase4_labels(const TileSmem& s, const Geom& g, int x0, int y0, int tid, int32_t* __restrict__ label, bool vec)
 {
     const int lane = tid & 31;
@@ -502,8 +509,25 @@ PERC_HD void tile_phase4_labels(const TileSmem& s, const Geom& g, int x0, int y0
         const uint32_t S4 = (s.pS[ly + 1][w] >> b0) & 0xFu;
         const int* st = &s.lab[ly * CT_TW + 4 * lane];
         int32_t out[4];
+        if (VAR == 0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) out[k] = (S4 >> k) & 1u ? tile_global_label(g, x0, y0, st[k]) : 0;
+            for (int k = 0; k < 4; ++k) out[k] = (S4 >> k) & 1u ? tile_global_label(g, x0, y0, st[k]) : 0;
+        } else {
+            const uint32_t Tw = s.pT[ly][w];
+            const int* wl = &s.lab[ly * CT_TW + (w << 5)];
+            int node = -1;
+            int32_t lab = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!((S4 >> k) & 1u)) { out[k] = 0; continue; }
+                const int b = b0 + k;
+                if (k == 0 || ((Tw >> b) & 1u) || !((S4 >> (k - 1)) & 1u)) {
+                    const int nd = hibit(Tw & le_mask(b));
+                    if (nd != node) { node = nd; lab = tile_global_label(g, x0, y0, wl[nd]); }
+                }
+                out[k] = lab;
+            }
+        }
         int32_t* dst = label + (int64_t)gy * g.m + gx;
         if (vec) {
 #if PERC_DEV

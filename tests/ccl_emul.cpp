@@ -36,8 +36,11 @@ static void build_mask(const Geom& g, int kind, const uint8_t* socc, const uint8
     }
 }
 
-template <int LAT, int KIND>
-static void run_local(const Geom& g, const uint8_t* mask, int32_t* label, int32_t* size, int32_t* rootlist, Summary* sum, bool vec)
+static int g_var = 0;          // variant of the tile kernel (ccl_tile.cuh, VAR)
+extern "C" void ccl_emul_set_variant(int v) { g_var = v; }
+
+template <int LAT, int KIND, int VAR>
+static void run_local_v(const Geom& g, const uint8_t* mask, int32_t* label, int32_t* size, int32_t* rootlist, Summary* sum, bool vec)
 {
     TileSmem* s = new TileSmem;
     std::vector<TileRegs> regs(CT_THREADS);
@@ -51,13 +54,20 @@ static void run_local(const Geom& g, const uint8_t* mask, int32_t* label, int32_
             LEVEL(1); LEVEL(2); LEVEL(3); LEVEL(4); LEVEL(5); LEVEL(6);
 #undef LEVEL
             for (int tid = 0; tid < CT_THREADS; ++tid) tile_clear_ring(*s, tid);
-            for (int tid = 0; tid < CT_THREADS; ++tid) tile_phase3<LAT, KIND>(*s, g, x0, y0, tid, regs[tid]);
+            for (int tid = 0; tid < CT_THREADS; ++tid) tile_phase3<LAT, KIND, VAR>(*s, g, x0, y0, tid, regs[tid]);
             for (int tid = 0; tid < CT_THREADS; ++tid) tile_phase4_fill(*s, g, x0, y0, tid, regs[tid], size);
             tile_phase4_reserve(*s, sum);
-            for (int tid = 0; tid < CT_THREADS; ++tid) tile_phase4_labels(*s, g, x0, y0, tid, label, vec);
+            for (int tid = 0; tid < CT_THREADS; ++tid) tile_phase4_labels<VAR>(*s, g, x0, y0, tid, label, vec);
             for (int tid = 0; tid < CT_THREADS; ++tid) tile_phase4_roots(*s, g, x0, y0, tid, regs[tid], size, rootlist);
         }
     delete s;
+}
+
+template <int LAT, int KIND>
+static void run_local(const Geom& g, const uint8_t* mask, int32_t* label, int32_t* size, int32_t* rootlist, Summary* sum, bool vec)
+{
+    if (g_var == 1) run_local_v<LAT, KIND, 1>(g, mask, label, size, rootlist, sum, vec);
+    else run_local_v<LAT, KIND, 0>(g, mask, label, size, rootlist, sum, vec);
 }
 
 extern "C" int ccl_emul(int lattice, int m, int n, int pbc, int kind, const uint8_t* socc, const uint8_t* bocc,

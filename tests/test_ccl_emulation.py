@@ -41,8 +41,12 @@ SHAPES = [(50, 50), (70, 45), (32, 32), (34, 66), (128, 96), (6, 3), (160, 130),
 CASES = [(lat, m, n, pbc) for lat in (1, 2) for (m, n) in SHAPES for pbc in (0, 1)]
 
 
+@pytest.mark.parametrize("var", [0, 1])
 @pytest.mark.parametrize("lat,m,n,pbc", CASES)
-def test_emulated_ccl_matches_oracle(emul, O, lat, m, n, pbc):
+def test_emulated_ccl_matches_oracle(emul, O, lat, m, n, pbc, var):
+    """var = 0: the tile kernel as the library runs it; var = 1: its opt-in variant (PERC_CCL_VAR=1: per-site roots
+    derived in the label phase instead of staged per run)"""
+    emul.ccl_emul_set_variant(var)
     t = m * n
     b1, b2 = O.bondlist(lat, m, n, pbc)
     nb = len(b1)
@@ -88,6 +92,7 @@ def test_emulated_slab_labeling_plus_stitch_matches_oracle(emul, O, lat, m, n, p
     import percolation_b200 as P
     from percolation_b200 import build
     build.build()
+    emul.ccl_emul_set_variant(0)
     t = m * n
     b1, b2 = O.bondlist(lat, m, n, pbc)
     nb = len(b1)
