@@ -49,7 +49,7 @@ ccl_local_kernel(Geom g, const uint8_t* __restrict__ mask, int32_t* __restrict__
     tile_phase2_level<LAT, 5>(s, tid); __syncthreads();
     tile_phase2_level<LAT, 6>(s, tid); __syncthreads();
     tile_clear_ring(s, tid); __syncthreads();
-    tile_phase3<LAT, KIND, VAR>(s, g, x0, y0, tid, r);
+    if (VAR == 2) tile_phase3_pair<LAT, KIND>(s, g, x0, y0, tid, r); else tile_phase3<LAT, KIND, VAR>(s, g, x0, y0, tid, r);
     __syncthreads();
     tile_phase4_fill(s, g, x0, y0, tid, r, size);
     __syncthreads();
@@ -241,14 +241,16 @@ static cudaError_t launch_local_v(Ctx* c, dim3 grid, int vec)
     return cudaGetLastError();
 }
 
-// PERC_CCL_VAR=1 selects the opt-in variant of the tile kernel (ccl_tile.cuh: per-site roots derived in the label
-// phase); it is bit-identical on the host emulation and has not run on a GPU yet, so it is not the default
+// PERC_CCL_VAR=1 | 2 selects an opt-in variant of the tile kernel (ccl_tile.cuh: per-site roots derived in the label
+// phase; 2: and two runs per trip of the per-run loop); bit-identical on the host emulation, not yet run on a GPU, so
+// not the default
 template <int LAT, int KIND>
 static cudaError_t launch_local(Ctx* c, dim3 grid, int vec)
 {
     static int var = -1;
-    if (var < 0) { const char* e = getenv("PERC_CCL_VAR"); var = (e && *e == '1') ? 1 : 0; }
-    return var == 1 ? launch_local_v<LAT, KIND, 1>(c, grid, vec) : launch_local_v<LAT, KIND, 0>(c, grid, vec);
+    if (var < 0) { const char* e = getenv("PERC_CCL_VAR"); var = (e && (*e == '1' || *e == '2')) ? *e - '0' : 0; }
+    return var == 2 ? launch_local_v<LAT, KIND, 2>(c, grid, vec)
+         : var == 1 ? launch_local_v<LAT, KIND, 1>(c, grid, vec) : launch_local_v<LAT, KIND, 0>(c, grid, vec);
 }
 
 int ccl_launch(Ctx* c, int kind)

@@ -210,6 +210,18 @@ PERC_HD int tile_find_ro(const int* lab_, int a)
     }
 }
 
+// two read-only finds walked in lockstep (the two shared-memory loads of a step are independent)
+PERC_HD void tile_find_ro2(const int* lab_, int a, int b, int& ra, int& rb)
+{
+    const volatile int* lab = lab_;
+    int pa = lab[a], pb = lab[b];
+    while (pa != a || pb != b) {
+        a = pa; b = pb;
+        pa = lab[a]; pb = lab[b];
+    }
+    ra = a; rb = b;
+}
+
 PERC_HD void tile_unite(int* lab, int a, int b)
 {
     for (;;) {
@@ -344,7 +356,7 @@ PERC_HD void tile_clear_ring(TileSmem& s, int tid)
 // owner site is unoccupied (dangling onto this site).  A bond with no occupied end is a lone
 // size-1 cluster (Sq/sitebond.f:231-242), counted into s.lone.
 // VAR = 1 (opt-in, PERC_CCL_VAR=1): the per-site root staging below is skipped; tile_phase4_labels<1> derives
-// each site's root from its run start instead
+// each site's root from its run start instead.  (VAR = 2: tile_phase3_pair below)
 template <int LAT, int KIND, int VAR = 0>
 PERC_HD void tile_phase3(TileSmem& s, const Geom& g, int x0, int y0, int tid, TileRegs& r)
 {
@@ -439,6 +451,115 @@ PERC_HD void tile_phase3(TileSmem& s, const Geom& g, int x0, int y0, int tid, Ti
     }
     flush();
     r.rootbits = rootbits;
+}
+
+// VAR = 2 (opt-in, PERC_CCL_VAR=2) of phase 3: a copy of tile_phase3<.., 1> whose per-run loop takes two runs per trip
+// (kept as a separate function so that the default kernel's code is not touched until this one has run on a GPU)
+template <int LAT, int KIND>
+PERC_HD void tile_phase3_pair(TileSmem& s, const Geom& g, int x0, int y0, int tid, TileRegs& r)
+{
+    const int w = tid % CT_NW, ly = tid / CT_NW, pr = ly + 1;
+    const int base = ly * CT_TW + (w << 5);
+    const uint32_t S = s.pS[pr][w], T = s.pT[ly][w];
+    const uint32_t E = s.pE[pr][w], N = s.pN[pr][w];
+    const uint32_t NW = LAT == LAT_TRIANGULAR ? s.pNW[pr][w] : 0u, NE = LAT == LAT_TRIANGULAR ? s.pNE[pr][w] : 0u;
+    uint32_t inW = 0, inS = 0, inSW = 0, inSE = 0;
+    // slab handles: only the rows this rank owns are counted (halo rows are the neighbour's)
+    const bool owned = y0 + ly >= g.own_lo && y0 + ly < g.own_hi;
+    if (KIND == KIND_MIXED && owned) {
+        const int xe = g.m - x0 < CT_TW ? g.m - x0 : CT_TW;
+        const int wl = (xe - 1) >> 5, bl = (xe - 1) & 31;          // word / bit of the last real column
+        auto dang = [](uint8_t v, unsigned bit) -> uint32_t { return ((v & bit) && !(v & MASK_SITE)) ? 1u : 0u; };
+        uint32_t c = w > 0 ? (s.pE[pr][w - 1] & ~s.pS[pr][w - 1]) >> 31 : dang(s.hL[pr], MASK_E);
+        inW = ((E & ~S) << 1) | c;
+        inS = s.pN[pr - 1][w] & ~s.pS[pr - 1][w];
+        const uint32_t Sup = s.pS[pr + 1][w];
+        uint32_t Sright = S >> 1;
+        if (w + 1 < CT_NW) Sright |= s.pS[pr][w + 1] << 31;
+        if (w == wl && (s.hR[pr] & MASK_SITE)) Sright |= 1u << bl;
+        unsigned lone = popc32(E & ~S & ~Sright) + popc32(N & ~S & ~Sup);
+        if (LAT == LAT_TRIANGULAR) {
+            uint32_t dne = s.pNE[pr - 1][w] & ~s.pS[pr - 1][w];
+            c = w > 0 ? (s.pNE[pr - 1][w - 1] & ~s.pS[pr - 1][w - 1]) >> 31 : dang(s.hL[pr - 1], MASK_NE);
+            inSW = (dne << 1) | c;
+            uint32_t dnw = s.pNW[pr - 1][w] & ~s.pS[pr - 1][w];
+            inSE = dnw >> 1;
+            if (w + 1 < CT_NW) inSE |= (s.pNW[pr - 1][w + 1] & ~s.pS[pr - 1][w + 1]) << 31;
+            if (w == wl && dang(s.hR[pr - 1], MASK_NW)) inSE |= 1u << bl;
+            uint32_t Supl = Sup << 1, Supr = Sup >> 1;
+            if (w > 0) Supl |= s.pS[pr + 1][w - 1] >> 31; else if (s.hL[pr + 1] & MASK_SITE) Supl |= 1u;
+            if (w + 1 < CT_NW) Supr |= s.pS[pr + 1][w + 1] << 31;
+            if (w == wl && (s.hR[pr + 1] & MASK_SITE)) Supr |= 1u << bl;
+            lone += popc32(NW & ~S & ~Supl) + popc32(NE & ~S & ~Supr);
+        }
+        if (lone) {
+#if PERC_DEV
+            atomicAdd(&s.lone, lone);
+#else
+            s.lone += lone;
+#endif
+        }
+    }
+    // border ring of the tile: only clusters with a site on it can continue into another tile
+    uint32_t ring = 0;
+    {
+        const int xe = g.m - x0 < CT_TW ? g.m - x0 : CT_TW;
+        if (ly == 0 || ly == CT_TH - 1) ring = 0xFFFFFFFFu;
+        if (w == 0) ring |= 1u;
+        if (w == CT_NW - 1) ring |= 0x80000000u;
+        if (g.pbc && w == ((xe - 1) >> 5)) ring |= 1u << ((xe - 1) & 31);      // wrap column of a partial tile
+    }
+    uint32_t rootbits = 0;
+    int prev = -1, acc = 0;
+    bool accring = false;
+    auto flush = [&]() {
+        if (prev < 0) return;
+        if (acc) cnt_add(s, prev, acc);
+        if (accring) ring_set(s, prev);
+    };
+    {
+        // two runs per trip (half the warp-uniform trips, two find chains in flight); per-site roots derived in the
+        // label phase as with VAR = 1.  Same roots, counters and ring bits as tile_phase3's loop.
+        auto account = [&](int a, uint32_t seg, int root) {
+            s.lab[base + a] = root;
+            if (root == base + a) rootbits |= 1u << a;
+            int wgt;
+            if (!owned) wgt = 0;
+            else if (KIND == KIND_SITE) wgt = popc32(seg);
+            else {
+                wgt = popc32(seg & E) + popc32(seg & N);
+                if (LAT == LAT_TRIANGULAR) wgt += popc32(seg & NW) + popc32(seg & NE);
+                if (KIND == KIND_MIXED) {
+                    wgt += popc32(seg) + popc32(seg & inW) + popc32(seg & inS);
+                    if (LAT == LAT_TRIANGULAR) wgt += popc32(seg & inSW) + popc32(seg & inSE);
+                }
+            }
+            if (root != prev) { flush(); prev = root; acc = 0; accring = false; }
+            acc += wgt;
+            accring |= (seg & ring) != 0;
+        };
+        uint32_t t2 = T;
+        for (int it = warp_max_count((popc32(T) + 1) >> 1); it > 0; --it) {
+            warp_converge();
+            if (!t2) continue;
+            const int a1 = lobit(t2);
+            t2 &= t2 - 1;
+            const uint32_t seg1 = S & (t2 ? ((1u << lobit(t2)) - 1u) : 0xFFFFFFFFu) & ~((1u << a1) - 1u);
+            int a2 = -1;
+            uint32_t seg2 = 0;
+            if (t2) {
+                a2 = lobit(t2);
+                t2 &= t2 - 1;
+                seg2 = S & (t2 ? ((1u << lobit(t2)) - 1u) : 0xFFFFFFFFu) & ~((1u << a2) - 1u);
+            }
+            int r1, r2;
+            tile_find_ro2(s.lab, base + a1, base + (a2 >= 0 ? a2 : a1), r1, r2);
+            account(a1, seg1, r1);
+            if (a2 >= 0) account(a2, seg2, r2);
+        }
+        flush();
+        r.rootbits = rootbits;
+    }
 }
 
 // ---- phase 4 --------------------------------------------------------------------------------

@@ -54,7 +54,7 @@ static void run_local_v(const Geom& g, const uint8_t* mask, int32_t* label, int3
             LEVEL(1); LEVEL(2); LEVEL(3); LEVEL(4); LEVEL(5); LEVEL(6);
 #undef LEVEL
             for (int tid = 0; tid < CT_THREADS; ++tid) tile_clear_ring(*s, tid);
-            for (int tid = 0; tid < CT_THREADS; ++tid) tile_phase3<LAT, KIND, VAR>(*s, g, x0, y0, tid, regs[tid]);
+            for (int tid = 0; tid < CT_THREADS; ++tid) { if (VAR == 2) tile_phase3_pair<LAT, KIND>(*s, g, x0, y0, tid, regs[tid]); else tile_phase3<LAT, KIND, VAR>(*s, g, x0, y0, tid, regs[tid]); }
             for (int tid = 0; tid < CT_THREADS; ++tid) tile_phase4_fill(*s, g, x0, y0, tid, regs[tid], size);
             tile_phase4_reserve(*s, sum);
             for (int tid = 0; tid < CT_THREADS; ++tid) tile_phase4_labels<VAR>(*s, g, x0, y0, tid, label, vec);
@@ -66,7 +66,8 @@ static void run_local_v(const Geom& g, const uint8_t* mask, int32_t* label, int3
 template <int LAT, int KIND>
 static void run_local(const Geom& g, const uint8_t* mask, int32_t* label, int32_t* size, int32_t* rootlist, Summary* sum, bool vec)
 {
-    if (g_var == 1) run_local_v<LAT, KIND, 1>(g, mask, label, size, rootlist, sum, vec);
+    if (g_var == 2) run_local_v<LAT, KIND, 2>(g, mask, label, size, rootlist, sum, vec);
+    else if (g_var == 1) run_local_v<LAT, KIND, 1>(g, mask, label, size, rootlist, sum, vec);
     else run_local_v<LAT, KIND, 0>(g, mask, label, size, rootlist, sum, vec);
 }
 
