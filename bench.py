@@ -377,6 +377,7 @@ def run_ours(args):
                 "ccl": {"gsites_per_s": t / (ccl_ms * 1e-3) / 1e9, "ms": ccl_ms,
                         "achieved_gbs": 5.0 * t / (ccl_ms * 1e-3) / 1e9, "frac": 5.0 * t / (ccl_ms * 1e-3) / 1e9 / peak},
                 "mean_pcg_iterations": mean_iters, "mean_G": st[0] / max(st[2], 1),
+                "all_solves_converged": bool(all(it <= args.itmax for it in stats["iters"])),
                 "pcg_ms_per_iteration": float(np.mean(stats["pcg_ms"])) / max(np.mean(stats["iters"]), 1),
                 "realizations": int(st[2]),
             },
@@ -418,7 +419,8 @@ def main():
     ap.add_argument("--ps", type=float, default=0.80)
     ap.add_argument("--pb", type=float, default=0.70)
     ap.add_argument("--tol", type=float, default=1e-10)
-    ap.add_argument("--itmax", type=int, default=2000000)
+    ap.add_argument("--itmax", type=int, default=400000,
+                    help="iteration cap of a solve (about 66 000 are needed at the default workload; the cap bounds the run time)")
     ap.add_argument("--e2e-steps", type=int, default=-1)
     ap.add_argument("--cpu-threads", type=int, default=16, help="host threads of the CPU arm (capped at the core count)")
     ap.add_argument("--cpu-cg-iters", type=int, default=10)
