@@ -3,7 +3,8 @@ the Kirchhoff problem of one square mixed site/bond realization near the thresho
 Saad, Yeung, Erhel, Guyomarc'h (SIAM J. Sci. Comput. 21, 2000): x0 = Z E^-1 Z^T b, p = z - Z E^-1 (A Z)^T z + beta p with
 E = Z^T A Z, Z = indicator vectors of bs x bs blocks of unknowns.  usage: deflation_experiment.py L pb tol bs1,bs2,...
 Results of round 1 (ps 0.80, pb 0.70, tol 1e-10): L = 256: x1.9 / x2.6 / x4.1 fewer iterations with 32 / 16 / 8-site blocks;
-L = 1024: x3.3 / x4.3 / x5.7 with 64 / 32 / 16-site blocks (coarse dimension 256 / 1024 / 4096); G unchanged to ~1e-9."""
+L = 1024: x3.3 / x4.3 / x5.7 with 64 / 32 / 16-site blocks (coarse dimension 256 / 1024 / 4096); L = 2048: 7662 / 5792
+iterations with 128 / 64-site blocks (plain: about 35 000); G unchanged to ~1e-9."""
 import numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spla, scipy.sparse.csgraph as csg, sys, time
 def build(L, ps, pb, seed):
     rng = np.random.default_rng(seed)
