@@ -45,6 +45,8 @@ extern "C" {
 #define PERC_E_NOSPAN    (-6)  /* requested cluster does not span               */
 #define PERC_E_NCCL      (-7)  /* libnccl.so.2 could not be loaded (slab mode)    */
 #define PERC_E_IFACE     (-8)  /* ranks disagree on an interface row (slab mode) */
+#define PERC_E_SELECT    (-9)  /* batch: the device-side exact-count selection missed for stats(7) realizations;
+                                   they are excluded from every statistic (re-run them singly with perc_generate) */
 
 /* ---- geometry (host-only index arithmetic; no device needed) ------------------------------ */
 /* nb formulas Sq/site.f:89-93, Tri/site.f:91-95 */
@@ -191,16 +193,22 @@ int32_t perc_comm_init_rank(const int64_t *h, const int32_t *nranks, const int32
 int32_t perc_allreduce_stats(const int64_t *h, const int32_t *ni, int64_t *ivals, const int32_t *nd, double *dvals);
 
 /* ---- solver selection --------------------------------------------------------------------------- */
-/* Iteration kernels of the conductance solve (the body of linbcg's loop, Sq/bondc.f:780-833):
- *   mode 0 (default): automatic -- perc_conduct_g on one GPU without periodic wrap runs the ONE-PASS kernel
- *           (Chronopoulos-Gear form of the same Jacobi-PCG recurrences, one reduction per iteration, 33 B per
- *           site and iteration); every other call runs the two-kernel form;
- *   mode 1: always the two-kernel form (50 B per site and iteration; iter is linbcg's count exactly);
- *   modes 10 / 12 / 15 (diagnostic): the one-pass kernel in one of its variants (pcg_fused_tile.cuh): FtCfgA
+/* Iteration kernels of the conductance solve (the body of linbcg's loop, Sq/bondc.f:780-833; Jacobi asolve :855-864):
+ *   mode 0 (default): automatic -- perc_conduct_g on one GPU without periodic wrap runs the DEFLATED ONE-PASS kernel:
+ *           the Chronopoulos-Gear arrangement of the Jacobi-PCG recurrences (one reduction per iteration, 33 B per
+ *           site and iteration) on top of a block-constant deflation space (Saad et al. 2000: x0 = Z E^-1 Z^T b,
+ *           search directions A-orthogonal to the blocks).  x, err = |r| / |D^-1 b| and the stopping rule are
+ *           linbcg's (r is the true residual of x); the iteration COUNT is several times smaller than linbcg's.
+ *           Every other call runs the two-kernel form;
+ *   mode 1: always the two-kernel form (50 B per site and iteration): plain Jacobi-PCG, linbcg's own sequence of
+ *           operations -- iter is linbcg's count exactly;
+ *   mode 2: the one-pass kernel without deflation (linbcg's iterates in exact arithmetic, iter within +-1);
+ *   modes 10 / 12 / 14 (diagnostic): the one-pass kernel in one of its variants (pcg_fused_tile.cuh): FtCfgA
  *           (per-tile partial sums folded in tile order: the result does not depend on the number of SMs),
- *           FtCfgA3 (the default), FtCfgA4 (the default's arithmetic with fewer instructions).
- * The process-wide default can be set with the environment variable PERC_PCG_SOLVER=classic|fused.
- * perc_solver_used reports which one the handle's last solve ran (1 = one-pass kernel). */
+ *           FtCfgA3 (= mode 2), FtCfgD (= mode 0).
+ * The process-wide default can be set with the environment variable PERC_PCG_SOLVER=classic|fused|deflated.
+ * perc_solver_used reports which one the handle's last solve ran (0 = two-kernel form, 1 = one-pass kernel,
+ * 2 = deflated one-pass kernel). */
 int32_t perc_set_solver(const int64_t *h, const int32_t *mode);
 int32_t perc_solver_used(const int64_t *h, int32_t *fused);
 

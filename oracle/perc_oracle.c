@@ -12,6 +12,8 @@
 #include <math.h>
 #include <time.h>
 
+#define ORC_OMP_MIN 2000000      /* systems above this size use OpenMP in the plain CG (golden-fixture runs) */
+
 /* ======================================================================== */
 /* geometry                                                                  */
 /* ======================================================================== */
@@ -727,6 +729,8 @@ static void csr_free(csr *A) { free(A->ptr); free(A->col); free(A->val); free(A-
 static void interior_ax(const csr *A, int m, int N, const double *x, double *y, double thresh)
 {
     int i, j; int64_t k;
+    /* (rows are independent: large systems are spread over the host threads, OMP_NUM_THREADS; each row's sum keeps its order) */
+#pragma omp parallel for private(j, k) schedule(static) if (N > ORC_OMP_MIN)
     for (i = 1; i <= N; ++i) {
         int site = i + m;
         double acc = A->diag[site] * x[i - 1];
@@ -851,18 +855,29 @@ int orc_conduct_cg(int m, int n, int nb, const int *b1, const int *b2, const dou
     s = 0.0;
     for (j = 0; j < N; ++j) { double zb = b[j] / A.diag[j + 1 + m]; s += zb * zb; }
     bnrm = sqrt(s);
+    /* (large systems, N > ORC_OMP_MIN: the vector loops run on the host threads -- sums are then folded per thread, which
+     * changes their rounding, not the algorithm; small systems run serially and are bit-reproducible) */
     while (it <= itmax) {
         it++;
         bknum = 0.0;
+#pragma omp parallel for reduction(+:bknum) schedule(static) if (N > ORC_OMP_MIN)
         for (j = 0; j < N; ++j) bknum += r[j] * r[j] / A.diag[j + 1 + m];
-        if (it == 1) for (j = 0; j < N; ++j) p[j] = r[j] / A.diag[j + 1 + m];
-        else { bk = bknum / bkden; for (j = 0; j < N; ++j) p[j] = bk * p[j] + r[j] / A.diag[j + 1 + m]; }
+        if (it == 1) {
+#pragma omp parallel for schedule(static) if (N > ORC_OMP_MIN)
+            for (j = 0; j < N; ++j) p[j] = r[j] / A.diag[j + 1 + m];
+        } else {
+            bk = bknum / bkden;
+#pragma omp parallel for schedule(static) if (N > ORC_OMP_MIN)
+            for (j = 0; j < N; ++j) p[j] = bk * p[j] + r[j] / A.diag[j + 1 + m];
+        }
         bkden = bknum;
         interior_ax(&A, m, N, p, q, 0.0);
         akden = 0.0;
+#pragma omp parallel for reduction(+:akden) schedule(static) if (N > ORC_OMP_MIN)
         for (j = 0; j < N; ++j) akden += q[j] * p[j];
         ak = bknum / akden;
         s = 0.0;
+#pragma omp parallel for reduction(+:s) schedule(static) if (N > ORC_OMP_MIN)
         for (j = 0; j < N; ++j) { Vint[j] += ak * p[j]; r[j] -= ak * q[j]; s += r[j] * r[j]; }
         e = sqrt(s) / bnrm;
         if (!(e > tol)) break;

@@ -106,11 +106,12 @@ void ctx_free(Ctx* c)
     if (c->d_stitch) cudaFree(c->d_stitch);
     if (c->h_iface) cudaFreeHost(c->h_iface);
     void* ptrs[] = {c->srank, c->brank, c->mask, c->label, c->size, c->rootlist, c->d_sum, c->d_pcg,
-                    c->d_hist, c->d_thr, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vp2, c->vq, c->xprow, c->partial, c->d_stage};
+                    c->d_hist, c->d_thr, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vp2, c->vq, c->xprow, c->partial, c->d_stage, c->d_defl, c->d_defl_terms};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_pcg) cudaFreeHost(c->h_pcg);
     if (c->h_sum_pin) cudaFreeHost(c->h_sum_pin);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_defl) cudaFreeHost(c->h_defl);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
 }
@@ -357,7 +358,8 @@ int32_t perc_span(const int64_t* h, const int32_t* max_ids, int32_t* nspan, int3
 int32_t perc_hist(const int64_t* h, const int32_t* nbins, int64_t* hist)
 {
     GET_CTX(h);
-    if (!c->labeled || !nbins || !hist) return PERC_E_STATE;
+    if (!nbins || !hist) return PERC_E_ARG;
+    if (!c->labeled || c->nranks > 1) return PERC_E_STATE;      // slab handles: rank-local labels, clusters not stitched here
     return ccl_hist(c, *nbins, hist);
 }
 
@@ -516,8 +518,8 @@ int32_t perc_conduct_warm(const int64_t* h, const int32_t* cluster_id, const dou
 {
     GET_CTX(h);
     // the labeling between two sweep points invalidates `solved`; the voltages themselves are still there
+    // (pcg_solve checks have_x itself; `solved` is only set by a solve that succeeded)
     const bool have = c->have_x && c->vx != nullptr;
-    if (have) c->solved = true;
     return conduct_common(c, cluster_id, Va, g0, gleak, tol, itmax, read_thresh, 1, Gtop, Gbot, iter, err, have ? 1 : 0);
 }
 
@@ -664,7 +666,8 @@ int32_t perc_batch(const int64_t* h, const int32_t* kind, const int32_t* nreal, 
     if (!kind || !nreal || !seed || !stream0 || !ks || !kb || !nbins || !stats) return PERC_E_ARG;
     if (*kind < KIND_SITE || *kind > KIND_MIXED || *nreal < 0 || *nbins < 0) return PERC_E_ARG;
     if ((*kind != KIND_BOND && (*ks < 0 || *ks > c->g.t)) || (*kind != KIND_SITE && (*kb < 0 || *kb > c->g.nb))) return PERC_E_ARG;
-    return batch_run(c, *kind, *nreal, (unsigned long long)*seed, (unsigned long long)*stream0, *ks, *kb, *nbins, hist, stats);
+    int rc = batch_run(c, *kind, *nreal, (unsigned long long)*seed, (unsigned long long)*stream0, *ks, *kb, *nbins, hist, stats);
+    return rc == 0 && stats[6] != 0 ? PERC_E_SELECT : rc;
 }
 
 int32_t perc_batch_conduct(const int64_t* h, const int32_t* kind, const int32_t* nreal, const int64_t* seed, const int64_t* stream0,
@@ -678,8 +681,9 @@ int32_t perc_batch_conduct(const int64_t* h, const int32_t* kind, const int32_t*
     if (*kind < KIND_SITE || *kind > KIND_MIXED || *nreal < 0 || c->g.n < 3 || *Va == 0.0 || *itmax < 0) return PERC_E_ARG;
     if ((*kind != KIND_BOND && (*ks < 0 || *ks > c->g.t)) || (*kind != KIND_SITE && (*kb < 0 || *kb > c->g.nb))) return PERC_E_ARG;
     if (!pcg_small_fits(c->g)) { int rc = ensure_pcg(c); if (rc) return rc; }
-    return batch_conduct_run(c, *kind, *nreal, (unsigned long long)*seed, (unsigned long long)*stream0, *ks, *kb,
-                             *Va, *g0, *gleak, *tol, *itmax, *read_thresh, G, iters, stats);
+    int rc = batch_conduct_run(c, *kind, *nreal, (unsigned long long)*seed, (unsigned long long)*stream0, *ks, *kb,
+                               *Va, *g0, *gleak, *tol, *itmax, *read_thresh, G, iters, stats);
+    return rc == 0 && stats[6] != 0 ? PERC_E_SELECT : rc;
 }
 
 // communicator for handles that shard independent realizations (mode 1): same bootstrap as the slab mode
@@ -744,8 +748,8 @@ int32_t perc_phase_ms(const int64_t* h, const int32_t* nphase, float* ms)
 int32_t perc_set_solver(const int64_t* h, const int32_t* mode)
 {
     GET_CTX(h);
-    if (!mode || *mode < 0 || (*mode > 1 && (*mode != 10 && *mode != 12 && *mode != 15))) return PERC_E_ARG;
-    // 10 / 12 / 15 (diagnostic): the one-pass kernel, variant FtCfgA / FtCfgA3 (the default) / FtCfgA4 (pcg_fused_tile.cuh)
+    if (!mode || *mode < 0 || (*mode > 2 && (*mode != 10 && *mode != 12 && *mode != 14))) return PERC_E_ARG;
+    // 10 / 12 / 14 (diagnostic): the one-pass kernel, variant FtCfgA / FtCfgA3 / FtCfgD (pcg_fused_tile.cuh)
     const int pm = *mode >= 10 ? 0 : *mode, fc = *mode >= 10 ? *mode - 10 : -1;
     c->pcg_mode = pm; c->fused_cfg = fc;
     for (Ctx* k : c->batch_kids) { k->pcg_mode = pm; k->fused_cfg = fc; }
@@ -756,7 +760,7 @@ int32_t perc_solver_used(const int64_t* h, int32_t* fused)
 {
     GET_CTX(h);
     if (!fused) return PERC_E_ARG;
-    *fused = c->last_fused ? 1 : 0;
+    *fused = c->last_fused ? (c->last_fused_cfg == 4 ? 2 : 1) : 0;
     return 0;
 }
 

@@ -16,9 +16,12 @@ namespace perc {
 // stats: [0] realizations  [1] sum ncl  [2] sum maxcs  [3] realizations with a spanning cluster
 //        [4] sum nspan  [5] sum size of the default spanning cluster  [6] failed selections
 //        [7] sum maxcs^2  [8] sum occupied sites  [9] sum occupied bonds
+// A realization whose device-side exact-count selection failed (occupancy.cu: select_pick_kernel, counted in stats[6]) was
+// labeled as an empty lattice: it is NOT folded into the statistics; the batch then returns PERC_E_SELECT.
 __global__ void batch_accum_kernel(const Summary* __restrict__ sum, unsigned long long* __restrict__ hist, int nbins,
-                                   long long* __restrict__ stats)
+                                   long long* __restrict__ stats, const PhiloxThreshold* __restrict__ thr, int use_s, int use_b)
 {
+    if ((use_s && thr[0].failed) || (use_b && thr[1].failed)) return;
     const unsigned long long mp = sum->maxpack;
     long long ms = (long long)(mp >> 32);
     if (ms == 0 && sum->nlone > 0) ms = 1;
@@ -31,10 +34,8 @@ __global__ void batch_accum_kernel(const Summary* __restrict__ sum, unsigned lon
     int ns = sum->nspan < MAX_SPAN ? sum->nspan : MAX_SPAN;
     if (ns > 0) {
         stats[3] += 1;
-        stats[4] += ns;
-        int best = 0;                                   // default choice: smallest canonical id
-        for (int k = 1; k < ns; ++k) if (sum->span_ids[k] < sum->span_ids[best]) best = k;
-        stats[5] += sum->span_sizes[best];
+        stats[4] += sum->nspan;
+        stats[5] += (long long)(sum->span_best & 0xffffffffull);       // default choice: smallest canonical id
     }
     if (nbins > 0 && sum->nlone) hist[0] += sum->nlone;  // lone bonds are size-1 clusters
 }
@@ -98,8 +99,11 @@ int batch_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsigned lon
     unsigned long long* d_acc = nullptr;
     const size_t way_words = (size_t)nb1 + BATCH_NSTATS;
     PERC_CUDA(cudaMalloc(&d_acc, sizeof(unsigned long long) * way_words * K));
-    PERC_CUDA(cudaMemset(d_acc, 0, sizeof(unsigned long long) * way_words * K));
-    PERC_CUDA(cudaDeviceSynchronize());              // the ways' streams do not synchronise with the legacy stream
+    {
+        cudaError_t e = cudaMemset(d_acc, 0, sizeof(unsigned long long) * way_words * K);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();   // the ways' streams do not synchronise with the legacy stream
+        if (e != cudaSuccess) { cudaFree(d_acc); return (int)e; }
+    }
     const int nsh = nbins < 4096 ? nbins : 4096;
     for (Ctx* w : ways) w->batch_thr = true;
     for (int i = 0; i < nreal && rc == 0; ++i) {
@@ -115,7 +119,7 @@ int batch_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsigned lon
             batch_hist_kernel<<<148 * 4, 256, sizeof(unsigned) * nsh, w->stream>>>(w->g.t, w->label, w->size, nbins, d_hist);
             w->launches++;
         }
-        batch_accum_kernel<<<1, 1, 0, w->stream>>>(w->d_sum, d_hist, nbins, d_stats);
+        batch_accum_kernel<<<1, 1, 0, w->stream>>>(w->d_sum, d_hist, nbins, d_stats, w->d_thr, kind != KIND_BOND, kind != KIND_SITE);
         w->launches++;
     }
     for (Ctx* w : ways) {
@@ -128,7 +132,10 @@ int batch_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsigned lon
     }
     if (rc == 0) {
         std::vector<unsigned long long> h(way_words * K);
-        PERC_CUDA(cudaMemcpy(h.data(), d_acc, sizeof(unsigned long long) * way_words * K, cudaMemcpyDeviceToHost));
+        {
+            cudaError_t e = cudaMemcpy(h.data(), d_acc, sizeof(unsigned long long) * way_words * K, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { cudaFree(d_acc); return (int)e; }
+        }
         for (int k = 0; k < BATCH_NSTATS; ++k) stats[k] = 0;
         if (nbins > 0 && hist) for (int b = 0; b < nbins; ++b) hist[b] = 0;
         for (int j = 0; j < K; ++j) {
@@ -176,6 +183,11 @@ int batch_conduct_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsi
         return 0;
     }
     uint8_t* d_cf = nullptr; double* d_G = nullptr; double* d_err = nullptr; int* d_it = nullptr; long long* d_stats = nullptr;
+    long long* d_wstats = nullptr;
+    struct Scratch {                                   // freed on every path out of this function
+        void** p[6];
+        ~Scratch() { for (void** q : p) if (*q) cudaFree(*q); }
+    } scratch{{(void**)&d_cf, (void**)&d_G, (void**)&d_err, (void**)&d_it, (void**)&d_stats, (void**)&d_wstats}};
     PERC_CUDA(cudaMalloc(&d_cf, (size_t)nreal * g.t));
     PERC_CUDA(cudaMalloc(&d_G, sizeof(double) * 2 * nreal));
     PERC_CUDA(cudaMalloc(&d_err, sizeof(double) * nreal));
@@ -186,7 +198,6 @@ int batch_conduct_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsi
     std::vector<Ctx*> ways;
     rc = batch_contexts(c, nreal, ways);
     const int K = (int)ways.size();
-    long long* d_wstats = nullptr;
     if (!rc) { PERC_CUDA(cudaMalloc(&d_wstats, sizeof(long long) * BATCH_NSTATS * K)); PERC_CUDA(cudaMemset(d_wstats, 0, sizeof(long long) * BATCH_NSTATS * K)); PERC_CUDA(cudaDeviceSynchronize()); }
     for (Ctx* w : ways) w->batch_thr = true;
     for (int i = 0; i < nreal && rc == 0; ++i) {
@@ -196,7 +207,7 @@ int batch_conduct_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsi
                               (unsigned long long*)(ws + 6));
         if (!rc) rc = ccl_launch(w, kind);
         if (!rc) rc = pcg_small_stage(w, d_cf, i);
-        if (!rc) { batch_accum_kernel<<<1, 1, 0, w->stream>>>(w->d_sum, nullptr, 0, ws); w->launches++; }
+        if (!rc) { batch_accum_kernel<<<1, 1, 0, w->stream>>>(w->d_sum, nullptr, 0, ws, w->d_thr, kind != KIND_BOND, kind != KIND_SITE); w->launches++; }
     }
     for (Ctx* w : ways) {
         w->batch_thr = false;
@@ -213,7 +224,6 @@ int batch_conduct_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsi
         PERC_CUDA(cudaMemcpy(d_stats, hs.data(), sizeof(long long) * BATCH_NSTATS, cudaMemcpyHostToDevice));
         PERC_CUDA(cudaDeviceSynchronize());
     }
-    if (d_wstats) cudaFree(d_wstats);
     if (!rc) rc = pcg_small_solve(c, d_cf, nreal, Va, g0, gleak, tol, itmax, read_thresh, d_G, d_it, d_err);
     if (!rc) {
         long long h[BATCH_NSTATS];
@@ -224,7 +234,6 @@ int batch_conduct_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsi
         for (int k = 0; k < BATCH_NSTATS; ++k) stats[k] = h[k];
         rc = (int)cudaGetLastError();
     } else cudaStreamSynchronize(st);
-    cudaFree(d_cf); cudaFree(d_G); cudaFree(d_err); cudaFree(d_it); cudaFree(d_stats);
     return rc;
 }
 

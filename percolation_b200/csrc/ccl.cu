@@ -146,17 +146,28 @@ __global__ void __launch_bounds__(1024)
 ccl_span_kernel(int m, int64_t top0, const int32_t* __restrict__ label, const int32_t* __restrict__ size,
                 Summary* __restrict__ sum)
 {
-    extern __shared__ unsigned seen[];
-    for (int k = threadIdx.x; k < (m + 31) / 32; k += blockDim.x) seen[k] = 0;
-    __syncthreads();
-    for (int x = threadIdx.x; x < m; x += blockDim.x) {
-        int32_t l = label[top0 + x];
-        if (l < 1 || l > m) continue;
-        unsigned bit = 1u << ((l - 1) & 31);
-        if (atomicOr(&seen[(l - 1) >> 5], bit) & bit) continue;
-        int pos = atomicAdd(&sum->nspan, 1);
-        if (pos < MAX_SPAN) { sum->span_ids[pos] = l; sum->span_sizes[pos] = size[l - 1]; }
-        else sum->span_overflow = 1;
+    // the bitmap covers SPAN_CHUNK labels at a time (any m fits the 48 KB static limit); a label is examined in the pass
+    // its chunk belongs to
+    constexpr int SPAN_CHUNK = 1 << 18;
+    __shared__ unsigned seen[SPAN_CHUNK / 32];
+    for (int base = 0; base < m; base += SPAN_CHUNK) {
+        const int nw = ((m - base < SPAN_CHUNK ? m - base : SPAN_CHUNK) + 31) / 32;
+        __syncthreads();
+        for (int k = threadIdx.x; k < nw; k += blockDim.x) seen[k] = 0;
+        __syncthreads();
+        for (int x = threadIdx.x; x < m; x += blockDim.x) {
+            const int32_t l = label[top0 + x];
+            if (l < 1 || l > m) continue;
+            const int r = l - 1 - base;
+            if (r < 0 || r >= SPAN_CHUNK) continue;
+            const unsigned bit = 1u << (r & 31);
+            if (atomicOr(&seen[r >> 5], bit) & bit) continue;
+            const int32_t sz = size[l - 1];
+            atomicMax(&sum->span_best, ((unsigned long long)(0xffffffffu - (unsigned)l) << 32) | (unsigned)sz);
+            const int pos = atomicAdd(&sum->nspan, 1);
+            if (pos < MAX_SPAN) { sum->span_ids[pos] = l; sum->span_sizes[pos] = sz; }
+            else sum->span_overflow = 1;
+        }
     }
 }
 
@@ -226,31 +237,22 @@ export_bond_labels_kernel(Geom g, int kind, const uint8_t* __restrict__ mask, co
 // ------------------------------------------------------------------------------------------
 static unsigned nblk(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
-template <int LAT, int KIND, int VAR>
-static cudaError_t launch_local_v(Ctx* c, dim3 grid, int vec)
+// the tile kernel needs more than 48 KB of dynamic shared memory: the opt-in is a per-DEVICE function attribute, so it is
+// tracked per handle (a process may hold handles on several GPUs), not per process
+template <int LAT, int KIND>
+static cudaError_t launch_local(Ctx* c, dim3 grid, int vec)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    constexpr int VAR = 2;          // per-site roots derived in the label phase, two runs per trip of the per-run loop
+    const unsigned bit = 1u << ((LAT - 1) * 3 + (KIND - 1));
+    if (!(c->ccl_attr & bit)) {
         cudaError_t e = cudaFuncSetAttribute(ccl_local_kernel<LAT, KIND, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)tile_smem_bytes<LAT>());
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        c->ccl_attr |= bit;
     }
     ccl_local_kernel<LAT, KIND, VAR><<<grid, CT_THREADS, tile_smem_bytes<LAT>(), c->stream>>>(c->g, c->mask, c->label, c->size,
                                                                                        c->rootlist, c->d_sum, vec);
     return cudaGetLastError();
-}
-
-// PERC_CCL_VAR=1 | 2 selects an opt-in variant of the tile kernel (ccl_tile.cuh: per-site roots derived in the label
-// phase; 2: and two runs per trip of the per-run loop); bit-identical on the host emulation, not yet run on a GPU, so
-// not the default
-template <int LAT, int KIND>
-static cudaError_t launch_local(Ctx* c, dim3 grid, int vec)
-{
-    static int var = -1;
-    if (var < 0) { const char* e = getenv("PERC_CCL_VAR"); var = (e && (*e == '1' || *e == '2')) ? *e - '0' : 0; }
-    return var == 2 ? launch_local_v<LAT, KIND, 2>(c, grid, vec)
-         : var == 1 ? launch_local_v<LAT, KIND, 1>(c, grid, vec) : launch_local_v<LAT, KIND, 0>(c, grid, vec);
 }
 
 int ccl_launch(Ctx* c, int kind)
@@ -307,7 +309,7 @@ int ccl_launch(Ctx* c, int kind)
         rc = slab_stitch(c);
         if (rc) return rc;
     } else {
-        ccl_span_kernel<<<1, 1024, sizeof(unsigned) * ((g.m + 31) / 32), st>>>(g.m, (int64_t)(g.n - 1) * g.m, c->label, c->size, c->d_sum);
+        ccl_span_kernel<<<1, 1024, 0, st>>>(g.m, (int64_t)(g.n - 1) * g.m, c->label, c->size, c->d_sum);
         c->launches++;
     }
     PERC_CUDA(cudaEventRecord(c->ev[5], st));
@@ -349,6 +351,15 @@ int ccl_fetch_summary(Ctx* c)
     c->h_span_ids.assign((size_t)ns, 0);
     c->h_span_sizes.assign((size_t)ns, 0);
     for (int k = 0; k < ns; ++k) { c->h_span_ids[k] = v[k].first; c->h_span_sizes[k] = v[k].second; }
+    // more spanning clusters than the list holds (strip lattices): which ones made it into the list depends on the order
+    // of the atomics, the smallest id -- perccln, the default cluster of perc_conduct -- does not (span_best)
+    if (c->h_sum.span_overflow && ns > 0) {
+        const int32_t bid = (int32_t)(0xffffffffu - (unsigned)(c->h_sum.span_best >> 32)), bsz = (int32_t)(c->h_sum.span_best & 0xffffffffu);
+        if (c->h_span_ids[0] != bid) {
+            c->h_span_ids.insert(c->h_span_ids.begin(), bid); c->h_span_sizes.insert(c->h_span_sizes.begin(), bsz);
+            c->h_span_ids.pop_back(); c->h_span_sizes.pop_back();
+        }
+    }
     return 0;
 }
 

@@ -45,9 +45,11 @@ struct Summary {
     unsigned long long maxpack;    // (size << 32) | (0xffffffff - label)  -> max size, then min label
     unsigned long long nocc_sites; // occupied sites in the mask
     unsigned long long nocc_bonds; // occupied bonds in the mask
+    unsigned long long span_best;  // ((0xffffffff - id) << 32) | size of the spanning cluster with the SMALLEST id (0: none);
+                                   // does not depend on the order or the capacity of the list below
     unsigned int nroots;           // tile-local roots appended to the root list
     int nspan;                     // spanning clusters found
-    int span_overflow;
+    int span_overflow;             // more than MAX_SPAN spanning clusters: the list holds MAX_SPAN of them (always incl. the smallest id)
     int pad;
     int32_t span_ids[MAX_SPAN];
     int32_t span_sizes[MAX_SPAN];

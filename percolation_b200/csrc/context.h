@@ -25,6 +25,8 @@ struct PhiloxThreshold {
     unsigned long long id;
     int enabled;              // 0: nothing occupied
     int all;                  // 1: everything occupied
+    int failed;               // device-resident selection (batches) missed: the realization is skipped, not counted
+    int pad;
 };
 
 enum OccSource { SRC_NONE = 0, SRC_RANK = 1, SRC_PHILOX = 2 };
@@ -81,6 +83,14 @@ struct Ctx {
     int pcg_mode = -1;            // -1 process default, 0 automatic (one-pass kernel when it applies), 1 two-kernel form
     int fused_cfg = -1;           // tile configuration of the one-pass kernel (-1: process default)
     bool last_fused = false;      // the last solve ran the one-pass kernel
+    int last_fused_cfg = -1;      // ... in this tile configuration (4 = deflated)
+    double* d_defl = nullptr;     // deflation: E^-1 [k*k], mu [KMAX], nu [KMAX], F [ntiles*8], W [ntiles*8]
+    double* h_defl = nullptr;     // pinned: E^-1, W
+    size_t defl_bytes = 0;
+    int defl_k = 0;               // coarse dimension of the last deflated solve
+    int* d_defl_terms = nullptr;  // term lists of Z^T A u' per block: tptr [KMAX + 1], tent [...] (built once per block shape)
+    int defl_terms_key[4] = {0, 0, 0, 0};   // (bw, bh, ntx, nty) the lists were built for
+    int defl_tw = 0;              // padded width of the lists (0: CSR walk)
     double* partial = nullptr;    // per-block partial sums
     int partial_cap = 0;
     PcgState* d_pcg = nullptr;
@@ -101,6 +111,9 @@ struct Ctx {
 
     // ---- batches: child contexts (own arrays + stream) so that small lattices overlap on the GPU
     std::vector<Ctx*> batch_kids;
+
+    // ---- per-device function attributes already set through this handle (bit sets)
+    unsigned ccl_attr = 0, pcg_attr = 0;
 
     // ---- instrumentation
     int64_t launches = 0;

@@ -527,9 +527,9 @@ __global__ void __launch_bounds__(1024) select_pick_kernel(long long k, const Se
                                                            const unsigned long long* __restrict__ cand, int cap,
                                                            PhiloxThreshold* __restrict__ thr, unsigned long long* __restrict__ nfail)
 {
-    if (threadIdx.x == 0) { thr->enabled = 1; thr->all = 0; }
+    if (threadIdx.x == 0) { thr->enabled = 1; thr->all = 0; thr->failed = 0; }
     if (!st->ok || st->count > (unsigned long long)cap || st->count != st->inbin) {
-        if (threadIdx.x == 0) { thr->key = 0; thr->id = 0; thr->enabled = 0; atomicAdd(nfail, 1ull); }
+        if (threadIdx.x == 0) { thr->key = 0; thr->id = 0; thr->enabled = 0; thr->failed = 1; atomicAdd(nfail, 1ull); }
         return;
     }
     const int n = (int)st->count;

@@ -18,11 +18,14 @@
 // Reductions are two-stage and fixed-order (per-block partial, last block folds them), so a
 // solve is bit-reproducible for a given lattice size.
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <cuda.h>
+#include <cooperative_groups.h>
 #include "context.h"
 #include "pcg_fused_tile.cuh"
+#include "pcg_defl_host.h"
 
 namespace perc {
 
@@ -55,8 +58,7 @@ build_cfull_kernel(Geom g, int kind, int32_t cid, const uint8_t* __restrict__ ma
     if (dsum) {
         // batch mode: the default spanning cluster (smallest canonical id) is chosen on the device; 0 = none spans
         cid = 0;
-        const int ns = dsum->nspan < MAX_SPAN ? dsum->nspan : MAX_SPAN;
-        for (int k = 0; k < ns; ++k) if (cid == 0 || dsum->span_ids[k] < cid) cid = dsum->span_ids[k];
+        if (dsum->nspan > 0) cid = (int32_t)(0xffffffffu - (unsigned)(dsum->span_best >> 32));
     }
     int x = (int)(i % g.m), y = (int)(i / g.m);
     if (y < g.own_lo || y >= g.own_hi) return;          // halo rows: copied from the neighbour rank
@@ -668,7 +670,7 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
 // each); everything else takes the two-kernel path.  Consecutive iterations sweep the tiles in opposite
 // directions, so each starts on the part of r / s the previous one wrote last (still in L2).
 // ------------------------------------------------------------------------------------------
-static_assert(FtCfgA::SMEM <= 227 * 1024 && FtCfgA3::SMEM <= 227 * 1024 && FtCfgA4::SMEM <= 227 * 1024, "fused PCG tile does not fit the shared memory of one SM");
+static_assert(FtCfgA::SMEM <= 227 * 1024 && FtCfgA3::SMEM <= 227 * 1024 && FtCfgD::SMEM <= 227 * 1024, "fused PCG tile does not fit the shared memory of one SM");
 
 // block sums of three values at once (fixed order: lanes by shuffles, then warp 0 folds the per-warp partials by
 // shuffles); result valid in thread 0
@@ -693,12 +695,18 @@ __device__ __forceinline__ void block_sum3(double& a, double& b, double& c, doub
     }
 }
 
+// device arrays of the deflated iteration (FtCfgD; unused otherwise): mu[k] of the blocks (read by the sweep, rewritten by
+// its coarse stage), F[ntiles][FS_STRIDE] crossing currents per tile, Einv[k][k] dense inverse of E = Z^T A Z
+// tptr / tent: the terms of Z^T A u' per block (ft_defl_terms); tw > 0: the lists padded to tw (16 or 32) entries per
+// block (-1 = no term), so that every thread gathers independent entries and a block's sum is a shuffle tree
+struct FtDeflDev { FtDefl D; double* mu; double* F; double* fglob; const double* Einv; const int* tptr; const int* tent; int tw; };
+
 template <int LAT, class C>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS)
 pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_s,
                  const __grid_constant__ CUtensorMap tm_cf, Geom g, PcgParams prm, double* __restrict__ r_out,
                  double* __restrict__ s_out, double* __restrict__ xrow, double* __restrict__ prow,
-                 double* __restrict__ partial, PcgState* __restrict__ st, int ntx, int ntiles, int rev, int prime)
+                 double* __restrict__ partial, PcgState* __restrict__ st, int ntx, int ntiles, int rev, int prime, FtDeflDev dd)
 {
     if (st->done) return;
     extern __shared__ __align__(128) unsigned char ft_raw[];
@@ -706,6 +714,10 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
     FtDiag* dtab = reinterpret_cast<FtDiag*>(ft_raw + 2 * (size_t)C::STAGE_BYTES + C::U_BYTES);      // [64][DC]
     double* sh = reinterpret_cast<double*>(dtab + 64 * C::DC);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sh + 96);                      // one mbarrier per stage
+    double* sft = reinterpret_cast<double*>(bars + 2);                                              // [2][RR * 4] shift tables (deflation)
+    double* sfl = sft + 2 * C::RR * 4;                                                              // [32][8] crossing currents per warp and slot
+    double* sf = sfl + 256;                                                                          // [FT_KMAX] mu of every block during the sweep, Z^T A u' in the coarse stage
+    int* sterm = reinterpret_cast<int*>(sf + FT_KMAX);                                              // [256] term lists of this CTA's blocks (padded form)
     const int tid = threadIdx.x;
     for (int k = tid; k < 64 * C::DC; k += C::THREADS) dtab[k] = ft_diag_entry(k / C::DC, prm.g0, prm.gleak);
     if (tid == 0) {
@@ -713,7 +725,6 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
     const FtScalars sc{prm.g0, prm.gleak, prime ? 0.0 : st->ak, prime ? 0.0 : st->bk};
     auto tile_of = [&](int t) { return rev ? ntiles - 1 - t : t; };
     auto stage_r = [&](int k) { return reinterpret_cast<double*>(ft_raw + (size_t)k * C::STAGE_BYTES); };
@@ -727,6 +738,11 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         tma_box_g2s(stage_s(k), &tm_s, x0 - 2, y0, &bars[k]);
         tma_box_g2s(stage_cf(k), &tm_cf, x0 - 16, y0 - 1, &bars[k]);
     };
+    // shift table of tile (ix, iy) into buffer b, by the threads t0, t0 + nt, ...
+    auto fill_shift = [&](int b, int ix, int iy, int t0, int nt) {
+        for (int j = t0; j < C::RR * 4; j += nt)
+            if ((j & 3) != 3) sft[b * C::RR * 4 + j] = ft_defl_shift_entry<C>(g, dd.D, sf, ix, iy, j >> 2, j & 3);
+    };
 
     // tile coordinates advance incrementally (a CTA's tiles are gridDim.x apart: no division per tile)
     const int G = (int)gridDim.x, dxs = G % ntx, dys = G / ntx;
@@ -736,7 +752,20 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
     };
     int t = blockIdx.x;
     int ix = 0, iy = 0;                                          // tile t
-    if (t < ntiles) { const int tl = tile_of(t); ix = tl % ntx; iy = tl / ntx; issue(0, ix * C::TX, iy * C::TY); }
+    if (t < ntiles) { const int tl = tile_of(t); ix = tl % ntx; iy = tl / ntx; }
+    if (C::DEFL) {
+        // mu of every block (8 KB) stays in shared memory for the sweep; the static term lists of the blocks whose
+        // Z^T A u' this CTA assembles in the coarse stage (block blockIdx.x + j gridDim.x) are fetched now, off the critical path
+        for (int B = tid; B < dd.D.k; B += C::THREADS) sf[B] = dd.mu[B];
+        if (dd.tw > 0 && tid < 256) {
+            const int B = (int)blockIdx.x + (int)gridDim.x * (tid / dd.tw);
+            sterm[tid] = B < dd.D.k ? dd.tent[B * dd.tw + (tid & (dd.tw - 1))] : -1;
+        }
+        __syncthreads();
+        if (t < ntiles) fill_shift(0, ix, iy, tid, C::THREADS);
+    }
+    __syncthreads();
+    if (t < ntiles) issue(0, ix * C::TX, iy * C::TY);
     int nx = ix, ny = iy;                                        // tile t + gridDim.x
     advance(nx, ny);
     double rz = 0.0, rr = 0.0, en = 0.0;
@@ -747,6 +776,7 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         const double* sr = stage_r(k & 1);
         double* ss = stage_s(k & 1);
         const uint8_t* scf = stage_cf(k & 1);
+        const double* sftk = C::DEFL ? sft + (k & 1) * C::RR * 4 : nullptr;
         const bool interior = ft_interior<C>(g, x0, y0);
         if (!C::USTATE) {
             ft_phase_u<LAT, C>(g, sr, scf, su, dtab, x0, y0, interior, tid);
@@ -754,13 +784,28 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         }
         const double* uu = C::USTATE ? sr : su;                 // V = 3: the staged vector IS u
         if (C::V == 1) { rz = 0.0; rr = 0.0; en = 0.0; }
-        // (C::SPLIT: the geometry-free tiles run their own instantiation; `interior` is uniform over the CTA)
-        if (C::SPLIT && interior) ft_phase_main<LAT, C, true>(g, sc, sr, ss, scf, uu, dtab, x0, y0, true, tid, r_out, s_out, xrow, prow, rz, rr);
-        else ft_phase_main<LAT, C, false>(g, sc, sr, ss, scf, uu, dtab, x0, y0, interior, tid, r_out, s_out, xrow, prow, rz, rr);
-        ft_phase_ringcols<LAT, C>(g, sc, sr, ss, scf, uu, dtab, x0, y0, tid);
+        ft_phase_main<LAT, C>(g, sc, sr, ss, scf, uu, dtab, x0, y0, interior, tid, r_out, s_out, xrow, prow, rz, rr, sftk);
+        ft_phase_ringcols<LAT, C>(g, sc, sr, ss, scf, uu, dtab, x0, y0, tid, sftk);
         __syncthreads();
-        if (C::SPLIT && interior) ft_phase_energy<LAT, C, true>(g, sc, ss, scf, x0, y0, true, tid, en);
-        else ft_phase_energy<LAT, C, false>(g, sc, ss, scf, x0, y0, interior, tid, en);
+        ft_phase_energy<LAT, C>(g, sc, ss, scf, x0, y0, interior, tid, en);
+        constexpr int FLUX_WARPS = (FtFluxItems<C>::N + 31) / 32, FLUX_LOW = (C::TY + C::TX + 31) / 32;
+        // work items beyond the east column / top row exist only on the triangular lattice (west column) and in tiles that
+        // hold row 1 or row n-2 (bonds into the Dirichlet rows): uniform over the CTA
+        const int fw = (LAT == LAT_TRIANGULAR || y0 <= 1 || y0 + C::TY >= g.n - 2) ? FLUX_WARPS : FLUX_LOW;
+        if (C::DEFL && tid < fw * 32) {
+            // currents through the bonds that cross the tile's borders: one work item per thread, summed per slot and warp
+            double f[FS_SLOTS] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            ft_phase_flux<LAT, C>(g, sc, ss, scf, x0, y0, tid, f);
+#pragma unroll
+            for (int q = 0; q < FS_SLOTS; ++q) {
+                if (LAT == LAT_SQUARE && (q == FS_W || q == FS_NW)) continue;
+                for (int o = 16; o; o >>= 1) f[q] += __shfl_down_sync(0xffffffffu, f[q], o);
+                if ((tid & 31) == 0) sfl[(tid >> 5) * 8 + q] = f[q];
+            }
+        }
+        // meanwhile the first ring warp prepares the next tile's shift table (the other buffer: its readers finished with the
+        // last tile's barriers, its next readers come after this tile's)
+        if (C::DEFL && tid >= C::RING_T0 && tid < C::RING_T0 + 32 && t + G < ntiles) fill_shift((k + 1) & 1, nx, ny, tid - C::RING_T0, 32);
         // generic-proxy accesses to this stage are ordered before the bulk copies that will refill it
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (C::V == 1) {
@@ -772,21 +817,93 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         } else {
             __syncthreads();                                    // every thread is done with the stage
         }
+        if (C::DEFL && tid >= C::RING_T0 + 32) {
+            // the second ring warp folds the per-warp currents (lane <-> warp, fixed shuffle tree) and stores the tile's slots
+            const int l = tid - C::RING_T0 - 32;
+            double* Ft = dd.F + (size_t)(iy * ntx + ix) * FS_STRIDE;
+#pragma unroll
+            for (int q = 0; q < FS_SLOTS; ++q) {
+                double v = 0.0;
+                if (!(LAT == LAT_SQUARE && (q == FS_W || q == FS_NW))) {
+                    v = l < fw ? sfl[l * 8 + q] : 0.0;
+                    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                }
+                if (l == 0) Ft[q] = v;
+            }
+        }
         ix = nx; iy = ny;
         advance(nx, ny);
     }
     int nparts = ntiles;
+    constexpr int NQ = C::DEFL ? 4 : 3;
     if (C::V >= 2) {
         // the sums stayed in registers over all tiles of this CTA: one reduction per CTA, folded in CTA order
         block_sum3(rz, rr, en, sh);
-        if (tid == 0) { partial[blockIdx.x * 3 + 0] = rz; partial[blockIdx.x * 3 + 1] = rr; partial[blockIdx.x * 3 + 2] = en; }
+        if (tid == 0) { partial[blockIdx.x * NQ + 0] = rz; partial[blockIdx.x * NQ + 1] = rr; partial[blockIdx.x * NQ + 2] = en; }
         nparts = G;
     }
+    if (C::DEFL) {
+        // coarse stage (cooperative launch: every CTA is resident): when all tiles of the lattice are done, every CTA
+        // assembles Z^T A u' of all blocks, forms its share of the rows of mu' = E^-1 (Z^T A u') -- one warp per row, E^-1
+        // streams from L2 -- and its share of mu'.(Z^T A u'), which the scalar recurrences subtract from u'.A u'
+        __threadfence();
+        cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+        grid.sync();
+        const int kk = dd.D.k;
+        const int lane = tid & 31, w = tid >> 5, nw = C::THREADS / 32;
+        // (1) Z^T A u' of this CTA's blocks (block blockIdx.x + j gridDim.x): one gather per thread, a shuffle tree per block
+        if (dd.tw > 0) {
+            const int tw = dd.tw;
+            if (tid < 256) {
+                const int en = sterm[tid];
+                double v = 0.0;
+                if (en >= 0) { v = __ldcg(&dd.F[en >> 1]); if (en & 1) v = -v; }
+                for (int o = tw >> 1; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o, tw);
+                const int B = (int)blockIdx.x + G * (tid / tw);
+                if ((tid & (tw - 1)) == 0 && B < kk) dd.fglob[B] = v;
+            }
+        } else {
+            for (int B = blockIdx.x + G * w; B < kk; B += G * nw) {
+                double a = 0.0;
+                for (int e = dd.tptr[B] + lane; e < dd.tptr[B + 1]; e += 32) {
+                    const int en = dd.tent[e];
+                    const double v = __ldcg(&dd.F[en >> 1]);
+                    a += (en & 1) ? -v : v;
+                }
+                for (int o = 16; o; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+                if (lane == 0) dd.fglob[B] = a;
+            }
+        }
+        __threadfence();
+        grid.sync();
+        // (2) every CTA reads the whole vector (8 KB) and forms its rows of mu' = E^-1 (Z^T A u')
+        for (int B = tid; B < kk; B += C::THREADS) sf[B] = __ldcg(&dd.fglob[B]);
+        __syncthreads();
+        double mf = 0.0;
+        for (int j = blockIdx.x + G * w; j < kk; j += G * nw) {
+            const double* row = dd.Einv + (size_t)j * kk;
+            double a = 0.0;
+#pragma unroll 8
+            for (int i = lane; i < kk; i += 32) a += row[i] * sf[i];
+            for (int o = 16; o; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+            if (lane == 0) { dd.mu[j] = a; mf += a * sf[j]; }
+        }
+        __syncthreads();
+        if (lane == 0) sh[w] = mf;
+        __syncthreads();
+        if (tid == 0) {
+            double a = 0.0;
+            for (int q = 0; q < nw; ++q) a += sh[q];
+            partial[blockIdx.x * NQ + 3] = a;
+        }
+    }
     if (last_block(&st->ticket_a)) {
-        const double fz = fold_partials(partial, nparts, 3, 0, sh);
-        const double fr = fold_partials(partial, nparts, 3, 1, sh);
-        const double fe = fold_partials(partial, nparts, 3, 2, sh);
+        const double fz = fold_partials(partial, nparts, NQ, 0, sh);
+        const double fr = fold_partials(partial, nparts, NQ, 1, sh);
+        double fe = fold_partials(partial, nparts, NQ, 2, sh);
+        const double fm = C::DEFL ? fold_partials(partial, nparts, NQ, 3, sh) : 0.0;
         if (threadIdx.x == 0) {
+            if (C::DEFL) fe -= fm;                              // p.A p = u.A u - mu.Z^T A u - beta gamma / alpha
             FtState f;
             f.gamma = st->bknum; f.alpha = st->ak; f.beta = st->bk; f.bnrm = st->bnrm; f.err = st->err; f.rr = st->rr;
             f.tol = st->tol; f.iter = st->iter; f.itmax = st->itmax; f.done = st->done;
@@ -796,6 +913,74 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
             st->iter = f.iter; st->done = f.done;
         }
     }
+}
+
+// ---- deflation set-up kernels -----------------------------------------------------------------------------------
+// sums of the weights of the bonds that cross each tile's borders (the entries of E = Z^T A Z), one CTA per tile
+template <int LAT, class C>
+__global__ void __launch_bounds__(64)
+defl_weights_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, int ntx, double* __restrict__ W)
+{
+    __shared__ double sw[2][8];
+    const int tl = blockIdx.x, x0 = (tl % ntx) * C::TX, y0 = (tl / ntx) * C::TY;
+    const FtGlobalAcc a{cfull, g.m};
+    double f[FS_SLOTS] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int q = threadIdx.x; q < FtFluxItems<C>::N; q += 64) ft_flux_item<LAT, C, true>(g, prm.g0, prm.gleak, a, x0, y0, q, f);
+#pragma unroll
+    for (int q = 0; q < FS_SLOTS; ++q) {
+        for (int o = 16; o; o >>= 1) f[q] += __shfl_down_sync(0xffffffffu, f[q], o);
+        if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5][q] = f[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < FS_STRIDE) W[(size_t)tl * FS_STRIDE + threadIdx.x] = threadIdx.x < FS_SLOTS ? sw[0][threadIdx.x] + sw[1][threadIdx.x] : 0.0;
+}
+
+// nu = E^-1 Z^T b: b lives on row n-2 only, so Z^T b has entries only in one block row (one CTA, thread B <-> block B)
+template <class C>
+__global__ void __launch_bounds__(1024)
+defl_nu_kernel(Geom g, PcgParams prm, FtDefl D, const uint8_t* __restrict__ cfull, const double* __restrict__ Einv,
+               double* __restrict__ nu, double* __restrict__ mu)
+{
+    __shared__ double fb[FT_KMAX];
+    const int by = ((g.n - 2) / C::TY) / D.bh;
+    for (int B = threadIdx.x; B < D.k; B += blockDim.x) {
+        double acc = 0.0;
+        if (B / D.nbx == by) {
+            const int bx = B % D.nbx;
+            const int xa = bx * D.bw * C::TX, xb = (bx + 1) * D.bw * C::TX < g.m ? (bx + 1) * D.bw * C::TX : g.m;
+            for (int x = xa; x < xb; ++x) {
+                const unsigned ex = neighbour_bits(g, x, g.n - 2), cf = cfull[(int64_t)(g.n - 2) * g.m + x];
+                double b = 0.0;
+                if (ex & NB_N)  b += ((cf & NB_N)  ? prm.g0 : prm.gleak) * prm.Va;
+                if (ex & NB_NW) b += ((cf & NB_NW) ? prm.g0 : prm.gleak) * prm.Va;
+                if (ex & NB_NE) b += ((cf & NB_NE) ? prm.g0 : prm.gleak) * prm.Va;
+                acc += b;
+            }
+        }
+        fb[B] = acc;
+    }
+    __syncthreads();
+    for (int B = threadIdx.x; B < D.k; B += blockDim.x) {
+        double a = 0.0;
+        for (int j = by * D.nbx; j < (by + 1) * D.nbx; ++j) a += Einv[(size_t)B * D.k + j] * fb[j];
+        nu[B] = a;
+        mu[B] = 0.0;                                             // the priming sweep runs unshifted
+    }
+}
+
+// x0 = Z nu on the read-out rows, u0 = D^-1 (b - A Z nu) on every unknown row (vr held b on row n-2, 0 elsewhere)
+template <class C>
+__global__ void __launch_bounds__(256)
+defl_init_kernel(Geom g, PcgParams prm, FtDefl D, const uint8_t* __restrict__ cfull, const double* __restrict__ nu,
+                 double* __restrict__ vr, double* __restrict__ xrow)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + g.m;
+    if (i >= g.t - g.m) return;
+    const int x = (int)(i % g.m), y = (int)(i / g.m);
+    double b, ni;
+    vr[i] = ft_defl_u0<C>(g, D, cfull[i], nu, x, y, prm.Va, prm.g0, prm.gleak, &b, &ni);
+    if (y == 1) xrow[x] = ni;
+    if (y == g.n - 2) xrow[g.m + x] = ni;
 }
 
 // slab mode: the scalar recurrences, run by one thread after the all-reduce of the rank-local sums
@@ -1075,28 +1260,24 @@ static int make_tensor_map(CUtensorMap* map, void* base, int elem_bytes, int col
     return r == CUDA_SUCCESS ? 0 : 900 + (int)r;
 }
 
-// which iteration kernel(s) a solve uses: 0 = automatic (one-pass kernel whenever it applies), 1 = always the
-// two-kernel form.  perc_set_solver sets it per handle; PERC_PCG_SOLVER=classic|fused sets the default of the process.
+// which iteration kernel(s) a solve uses (perc_set_solver): 0 = automatic: the one-pass kernel whenever it applies, deflated;
+// 1 = always the two-kernel form (linbcg's own sequence of operations); 2 = the one-pass kernel without deflation (linbcg's
+// iterates in exact arithmetic).  PERC_PCG_SOLVER=classic|fused|deflated sets the default of the process.
 static int pcg_default_mode()
 {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("PERC_PCG_SOLVER");
-        mode = (e && !strcmp(e, "classic")) ? 1 : 0;
-    }
-    return mode;
+    const char* e = getenv("PERC_PCG_SOLVER");
+    if (e && !strcmp(e, "classic")) return 1;
+    if (e && !strcmp(e, "fused")) return 2;
+    return 0;
 }
 
 bool pcg_fused_applies(const Ctx* c, int keep_x, int warm)
 {
     const Geom& g = c->g;
     const int mode = c->pcg_mode >= 0 ? c->pcg_mode : pcg_default_mode();
-    return mode == 0 && !keep_x && !warm && c->nranks == 1 && !g.pbc && (g.m % 16) == 0 && g.n >= 4;
+    return mode != 1 && !keep_x && !warm && c->nranks == 1 && !g.pbc && (g.m % 16) == 0 && g.n >= 4;
 }
 
-// the iteration loop of the one-pass kernel; on entry (after pcg_init_kernel) vr = b, vp = vx = 0, the scalars of
-// the solve are initialised.  Buffers: r ping-pongs between vr and vp, s between vp2 and vx; x / p of rows 1 and
-// n-2 live in xprow and are copied into vx for the read-out at the end.
 // V = 3 of the one-pass kernel keeps u = D^-1 r in HBM: turn the initial residual into u (the unknown rows only;
 // everything else is and stays 0)
 __global__ void __launch_bounds__(256)
@@ -1110,6 +1291,68 @@ pcg_scale_u_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, dou
     vr[i] = r / diag_of(cfull[i], neighbour_bits(g, x, y), prm.g0, prm.gleak);
 }
 
+// deflation set-up of a solve: E = Z^T A Z from the conduct bytes (weights kernel -> host: banded Cholesky, dense
+// inverse -> device), nu = E^-1 Z^T b, x0 = Z nu, u0 = D^-1 (b - A Z nu)
+template <class C>
+static int pcg_defl_setup(Ctx* c, const PcgParams& prm, const FtDefl& D, int ntiles, double* xrow)
+{
+    const Geom& g = c->g;
+    cudaStream_t s = c->stream;
+    const size_t need = sizeof(double) * ((size_t)D.k * D.k + 2 * (size_t)FT_KMAX + 2 * (size_t)ntiles * FS_STRIDE);
+    if (need > c->defl_bytes) {
+        if (c->d_defl) cudaFree(c->d_defl);
+        if (c->h_defl) cudaFreeHost(c->h_defl);
+        c->d_defl = nullptr; c->h_defl = nullptr; c->defl_bytes = 0;
+        PERC_CUDA(cudaMalloc(&c->d_defl, need));
+        PERC_CUDA(cudaMallocHost(&c->h_defl, sizeof(double) * ((size_t)D.k * D.k + (size_t)ntiles * FS_STRIDE)));
+        c->defl_bytes = need;
+    }
+    if (!c->d_defl_terms || c->defl_terms_key[0] != D.bw || c->defl_terms_key[1] != D.bh || c->defl_terms_key[2] != D.ntx || c->defl_terms_key[3] != D.nty) {
+        // the terms of Z^T A u' per block depend on the lattice and block shape only
+        std::vector<int> ptr, ent;
+        ft_defl_terms(D, ptr, ent);
+        int mx = 0;
+        for (int B = 0; B < D.k; ++B) mx = ptr[B + 1] - ptr[B] > mx ? ptr[B + 1] - ptr[B] : mx;
+        const int tw = mx <= 16 ? 16 : (mx <= 32 ? 32 : 0);
+        std::vector<int> up((size_t)FT_KMAX + 1, 0);
+        for (int B = 0; B <= D.k; ++B) up[B] = ptr[B];
+        if (tw) {
+            std::vector<int> pad((size_t)D.k * tw, -1);
+            for (int B = 0; B < D.k; ++B) for (int e = ptr[B]; e < ptr[B + 1]; ++e) pad[(size_t)B * tw + (e - ptr[B])] = ent[e];
+            up.insert(up.end(), pad.begin(), pad.end());
+        } else up.insert(up.end(), ent.begin(), ent.end());
+        if (c->d_defl_terms) cudaFree(c->d_defl_terms);
+        c->d_defl_terms = nullptr;
+        PERC_CUDA(cudaMalloc(&c->d_defl_terms, sizeof(int) * up.size()));
+        PERC_CUDA(cudaMemcpyAsync(c->d_defl_terms, up.data(), sizeof(int) * up.size(), cudaMemcpyHostToDevice, s));
+        PERC_CUDA(cudaStreamSynchronize(s));            // `up` is pageable and goes out of scope
+        c->defl_terms_key[0] = D.bw; c->defl_terms_key[1] = D.bh; c->defl_terms_key[2] = D.ntx; c->defl_terms_key[3] = D.nty;
+        c->defl_tw = tw;
+    }
+    double* d_einv = c->d_defl;
+    double* d_mu = d_einv + (size_t)D.k * D.k;
+    double* d_nu = d_mu + FT_KMAX;
+    double* d_F = d_nu + FT_KMAX;
+    double* d_W = d_F + (size_t)ntiles * FS_STRIDE;
+    double* h_einv = c->h_defl;
+    double* h_W = h_einv + (size_t)D.k * D.k;
+    if (g.lattice == LAT_SQUARE) defl_weights_kernel<LAT_SQUARE, C><<<ntiles, 64, 0, s>>>(g, prm, c->cfull, D.ntx, d_W);
+    else defl_weights_kernel<LAT_TRIANGULAR, C><<<ntiles, 64, 0, s>>>(g, prm, c->cfull, D.ntx, d_W);
+    PERC_CUDA(cudaGetLastError());
+    PERC_CUDA(cudaMemcpyAsync(h_W, d_W, sizeof(double) * (size_t)ntiles * FS_STRIDE, cudaMemcpyDeviceToHost, s));
+    PERC_CUDA(cudaStreamSynchronize(s));
+    unsigned hw = std::thread::hardware_concurrency();
+    if (ft_defl_build_einv(D, h_W, h_einv, hw > 16 ? 16 : (hw ? (int)hw : 1))) return (int)cudaErrorUnknown;
+    PERC_CUDA(cudaMemcpyAsync(d_einv, h_einv, sizeof(double) * (size_t)D.k * D.k, cudaMemcpyHostToDevice, s));
+    defl_nu_kernel<C><<<1, 1024, 0, s>>>(g, prm, D, c->cfull, d_einv, d_nu, d_mu);
+    defl_init_kernel<C><<<nblk64(g.t - 2 * (int64_t)g.m), 256, 0, s>>>(g, prm, D, c->cfull, d_nu, c->vr, xrow);
+    c->launches += 3;
+    return (int)cudaGetLastError();
+}
+
+// the iteration loop of the one-pass kernel; on entry (after pcg_init_kernel) vr = b, vp = vx = 0, the scalars of
+// the solve are initialised.  Buffers: r ping-pongs between vr and vp, s between vp2 and vx; x / p of rows 1 and
+// n-2 live in xprow and are copied into vx for the read-out at the end.
 template <class C>
 static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
 {
@@ -1120,12 +1363,9 @@ static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
     if (!c->xprow) PERC_CUDA(cudaMalloc(&c->xprow, sizeof(double) * 4 * g.m));
     PERC_CUDA(cudaMemsetAsync(c->xprow, 0, sizeof(double) * 4 * g.m, s));
     PERC_CUDA(cudaMemsetAsync(c->vp2, 0, sizeof(double) * g.t, s));
-    static bool attr_set = false;
-    if (!attr_set) {
-        PERC_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<LAT_SQUARE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        PERC_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<LAT_TRIANGULAR, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        attr_set = true;
-    }
+    // (function attributes are per device: set on every solve, the call is cheap)
+    PERC_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<LAT_SQUARE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    PERC_CUDA(cudaFuncSetAttribute(pcg_fused_kernel<LAT_TRIANGULAR, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     double* rbuf[2] = {c->vr, c->vp};
     double* sbuf[2] = {c->vp2, c->vx};
     CUtensorMap tm_r[2], tm_s[2], tm_cf;
@@ -1136,22 +1376,38 @@ static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
     }
     rc = make_tensor_map(&tm_cf, c->cfull, 1, g.m, g.n, C::CLD, C::RR); if (rc) return rc;
     double* xrow = c->xprow; double* prow = c->xprow + 2 * (size_t)g.m;
+    FtDeflDev dd{};
+    if (C::DEFL) {
+        int bw = 0, bh = 0;
+        if (const char* e = getenv("PERC_DEFL_BLOCK")) sscanf(e, "%d,%d", &bw, &bh);      // tiles per block (experiments)
+        dd.D = ft_defl_make(g, C::TX, C::TY, FT_KMAX, bw, bh);
+        rc = pcg_defl_setup<C>(c, prm, dd.D, ntiles, xrow); if (rc) return rc;
+        dd.Einv = c->d_defl; dd.mu = c->d_defl + (size_t)dd.D.k * dd.D.k; dd.F = dd.mu + 2 * FT_KMAX;
+        dd.tptr = c->d_defl_terms; dd.tent = c->d_defl_terms + FT_KMAX + 1; dd.tw = c->defl_tw;
+        dd.fglob = dd.mu + FT_KMAX;                      // (nu is dead once defl_init_kernel has run)
+        if (dd.tw > 0 && ((dd.D.k + grid - 1) / grid) * dd.tw > 256) dd.tw = 0;     // more blocks per CTA than the staged lists hold
+        c->defl_k = dd.D.k;
+    }
     int cur = 0, pass = 0;
-    auto launch = [&](int prime) {
-        if (g.lattice == LAT_SQUARE)
-            pcg_fused_kernel<LAT_SQUARE, C><<<grid, C::THREADS, C::SMEM, s>>>(tm_r[cur], tm_s[cur], tm_cf, g, prm, rbuf[cur ^ 1], sbuf[cur ^ 1],
-                                                                           xrow, prow, c->partial, c->d_pcg, ntx, ntiles, pass & 1, prime);
-        else
-            pcg_fused_kernel<LAT_TRIANGULAR, C><<<grid, C::THREADS, C::SMEM, s>>>(tm_r[cur], tm_s[cur], tm_cf, g, prm, rbuf[cur ^ 1], sbuf[cur ^ 1],
-                                                                               xrow, prow, c->partial, c->d_pcg, ntx, ntiles, pass & 1, prime);
+    Geom garg = g; PcgParams parg = prm;
+    auto launch = [&](int prime) -> cudaError_t {
+        int rev = pass & 1, ntx_ = ntx, ntiles_ = ntiles;
+        double* ro = rbuf[cur ^ 1]; double* so = sbuf[cur ^ 1];
+        void* args[] = {&tm_r[cur], &tm_s[cur], &tm_cf, &garg, &parg, &ro, &so, &xrow, &prow, &c->partial, &c->d_pcg,
+                        &ntx_, &ntiles_, &rev, &prime, &dd};
+        const void* fn = g.lattice == LAT_SQUARE ? (const void*)pcg_fused_kernel<LAT_SQUARE, C> : (const void*)pcg_fused_kernel<LAT_TRIANGULAR, C>;
+        // the deflated sweep ends with a grid-wide stage: cooperative launch (all CTAs resident: one per SM)
+        cudaError_t e = C::DEFL ? cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(C::THREADS), args, C::SMEM, s)
+                                : cudaLaunchKernel(fn, dim3(grid), dim3(C::THREADS), args, C::SMEM, s);
         cur ^= 1; ++pass;
         c->launches++;
+        return e;
     };
-    if (C::USTATE) {
+    if (C::USTATE && !C::DEFL) {
         pcg_scale_u_kernel<<<nblk64(g.t - 2 * (int64_t)g.m), 256, 0, s>>>(g, prm, c->cfull, c->vr);
         c->launches++;
     }
-    launch(1);                     // s = A D^-1 b and delta0: alpha0, beta0 = 0
+    PERC_CUDA(launch(1));          // s = A u0 and delta0: alpha0, beta0 = 0
     float it_ms = 0.f; int nsamp = 0;
     int chunk = 32, iters_before = 0;
     for (;;) {
@@ -1160,7 +1416,7 @@ static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
             // kernel's own device time)
             const bool sample = (k == chunk / 2);
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[8], s));
-            launch(0);
+            PERC_CUDA(launch(0));
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[9], s));
         }
         PERC_CUDA(cudaMemcpyAsync(c->h_pcg, c->d_pcg, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
@@ -1170,6 +1426,8 @@ static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
             cudaEventElapsedTime(&a, c->ev[8], c->ev[9]);
             it_ms += a; nsamp++;
         }
+        // a chunk that did not advance the iteration count means the launches did not run: never spin on that
+        if (!c->h_pcg->done && c->h_pcg->iter == iters_before) return (int)cudaErrorLaunchFailure;
         iters_before = c->h_pcg->iter;
         if (c->h_pcg->done) break;
         if (chunk < 512) chunk *= 2;
@@ -1182,18 +1440,16 @@ static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
     return 0;
 }
 
-// variant of the one-pass kernel: PERC_FUSED_CFG = 1 | 3 | 6 (FtCfgA, FtCfgA3, FtCfgA4), default 3 = FtCfgA3 (the one
-// measured and profiled on the GPU in round 1; FtCfgA4 is bit-identical on the host emulation and has not run on a GPU yet)
+// variant of the one-pass kernel: the deflated iteration FtCfgD by default; perc_set_solver(h, 2) / 12: FtCfgA3 (the same
+// sweep without deflation), 10: FtCfgA (the first version: per-tile partial sums folded in tile order)
 static int pcg_fused_loop(Ctx* c, const PcgParams& prm)
 {
-    static int cfg = -1;
-    if (cfg < 0) {
-        const char* e = getenv("PERC_FUSED_CFG");
-        cfg = (e && (*e == '1' || *e == '3' || *e == '6')) ? *e - '1' : 2;
-    }
-    const int use = c->fused_cfg >= 0 ? c->fused_cfg : cfg;
+    const int mode = c->pcg_mode >= 0 ? c->pcg_mode : pcg_default_mode();
+    int use = c->fused_cfg >= 0 ? c->fused_cfg : (mode == 2 ? 2 : 4);
+    if (const char* e = getenv("PERC_FUSED_CFG")) if (c->fused_cfg < 0 && (*e == '1' || *e == '3' || *e == '5')) use = *e - '1';
+    c->last_fused_cfg = use;
+    if (use == 4) return pcg_fused_loop_t<FtCfgD>(c, prm);
     if (use == 2) return pcg_fused_loop_t<FtCfgA3>(c, prm);
-    if (use == 5) return pcg_fused_loop_t<FtCfgA4>(c, prm);
     return pcg_fused_loop_t<FtCfgA>(c, prm);
 }
 
@@ -1202,8 +1458,9 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
 {
     const Geom& g = c->g;
     // warm start: the voltages of the handle's previous solve are the initial guess (they must exist)
-    if (warm && !(c->solved && c->have_x && c->nranks == 1)) warm = 0;
+    if (warm && !(c->have_x && c->vx && c->nranks == 1)) warm = 0;
     if (warm) keep_x = 1;
+    c->solved = false;                   // set again only when this solve succeeds (an error must not expose old voltages)
     cudaStream_t s = c->stream;
     PcgParams prm{g0, gleak, Va, read_thresh};
     dim3 sgrid((g.m + SP_TX - 1) / SP_TX, (g.n + SP_TY - 1) / SP_TY);
@@ -1228,8 +1485,7 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
         c->partial_cap = need;
     }
     int rc = 0;
-    static bool attr_set = false;
-    if (vec && !attr_set) {
+    if (vec && !(c->pcg_attr & 1u)) {      // per-device attribute, tracked per handle
         PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_SQUARE, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
         PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_SQUARE, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
         PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_SQUARE, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
@@ -1238,7 +1494,7 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
         PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_TRIANGULAR, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
         PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_TRIANGULAR, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
         PERC_CUDA(cudaFuncSetAttribute(pcg_pipe_kernel<LAT_TRIANGULAR, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
-        attr_set = true;
+        c->pcg_attr |= 1u;
     }
     PERC_CUDA(cudaMemsetAsync(c->d_pcg, 0, sizeof(PcgState), s));
     PERC_CUDA(cudaEventRecord(c->ev[6], s));
@@ -1312,9 +1568,11 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
             { double* tmp = pold; pold = pnew; pnew = tmp; }
             if (sample) PERC_CUDA(cudaEventRecord(c->ev[10], s));
             c->launches += 2;
+            PERC_CUDA(cudaGetLastError());               // a failed launch must not leave the host polling for `done`
         }
         PERC_CUDA(cudaMemcpyAsync(c->h_pcg, c->d_pcg, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
         PERC_CUDA(cudaStreamSynchronize(s));
+        if (!c->h_pcg->done && c->h_pcg->iter == iters_before) return (int)cudaErrorLaunchFailure;
         // a sample is valid if the solve was still live when it ran (always true for a chunk that
         // ended not-done; for the final chunk only if it finished after the sampled iteration)
         if (!c->h_pcg->done || c->h_pcg->iter > iters_before + chunk / 2) {

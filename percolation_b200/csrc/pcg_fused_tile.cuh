@@ -33,6 +33,8 @@ namespace perc {
 // (the others do not wait for them) and the sums stay in registers until the CTA has done all its tiles; V = 3: as
 // V = 2, and the state vector in HBM is u = D^-1 r instead of r (u' = u - alpha D^-1 s'): phase U and its shared
 // array disappear, the residual is formed only inside the sums (r = d u)
+constexpr int FT_KMAX = 1024;                              // largest coarse (deflation) dimension: E^-1 is dense, FT_KMAX^2 doubles
+
 template <int TY_, int RPT_, int DC_, int CTAS_, int V_>
 struct FtCfg {
     static constexpr int TX = 128, TY = TY_, RPT = RPT_, DC = DC_, CTAS = CTAS_, V = V_;   // CTAS: resident CTAs per SM
@@ -53,9 +55,11 @@ struct FtCfg {
     static constexpr int STAGE_BYTES = R_BYTES + S_BYTES + CF_BYTES;
     static constexpr int TAB_BYTES = 64 * DC * 16;
     static constexpr bool USTATE = V >= 3;
-    static constexpr bool SPLIT = V >= 4;                   // tiles with the full neighbourhood run their own instantiation
+    static constexpr bool DEFL = V >= 5;                    // deflated iteration (block-constant coarse space, see FtDefl)
     static constexpr int U_BYTES = USTATE ? 0 : R_BYTES;    // shared u array of phase U
-    static constexpr int SMEM = 2 * STAGE_BYTES + U_BYTES + TAB_BYTES + 96 * 8 + 16;
+    static constexpr int SHIFT_BYTES = DEFL ? 2 * RR * 4 * 8 : 0;         // per staged row: mu of the west / own / east block (two tiles in flight)
+    static constexpr int COARSE_BYTES = DEFL ? FT_KMAX * 8 + 256 * 8 + 256 * 4 : 0; // mu / Z^T A u' of every block, crossing currents per warp and slot, term lists
+    static constexpr int SMEM = 2 * STAGE_BYTES + U_BYTES + TAB_BYTES + 96 * 8 + 16 + SHIFT_BYTES + COARSE_BYTES;
     // table of diagonals: entry (#conducting bonds << 3 | #leaking bonds), DC private copies
     static PERC_HD int tab(int nc, int nl, int lane) { return ((nc << 3) | nl) * DC + (lane & (DC - 1)); }
     // ... of a site with all its DEG neighbours (fast path): nl = DEG - nc, (nc << 3 | DEG - nc) = 7 nc + DEG
@@ -64,7 +68,7 @@ struct FtCfg {
 
 typedef FtCfg<32, 3, 32, 1, 1> FtCfgA;      // 704 threads
 typedef FtCfg<32, 3, 32, 1, 3> FtCfgA3;     // 768 threads (two ring warps), one reduction per CTA, u = D^-1 r as the state vector
-typedef FtCfg<32, 3, 32, 1, 4> FtCfgA4;     // the same arithmetic with fewer instructions (see above)
+typedef FtCfg<32, 3, 32, 1, 5> FtCfgD;      // FtCfgA3 + deflation
 
 #ifdef __CUDACC__
 typedef double2 ft_d2;
@@ -94,13 +98,6 @@ PERC_HD void ft_padd(double& acc, double v, unsigned bit)
     if (bit) acc += v;
 #endif
 }
-// the same value as a fused multiply-add by 1.0 / 0.0: fma(1, v, acc) = acc + v and fma(0, v, acc) = acc exactly
-// (v is finite), one select of the multiplier's high word + one DFMA
-PERC_HD void ft_padd_fma(double& acc, double v, unsigned bit) { acc = fma(bit ? 1.0 : 0.0, v, acc); }
-template <class C> PERC_HD void ft_cadd(double& acc, double v, unsigned bit)
-{
-    if (C::SPLIT) ft_padd_fma(acc, v, bit); else ft_padd(acc, v, bit);
-}
 template <int LAT> PERC_HD unsigned ft_interior_ex(int gx)
 {
     if (LAT == LAT_SQUARE) return NB_E | NB_N | NB_W | NB_S;
@@ -120,6 +117,215 @@ template <class C>
 PERC_HD bool ft_interior(const Geom& g, int x0, int y0)
 {
     return x0 - 2 >= 1 && x0 + C::TX + 1 <= g.m - 2 && y0 >= 1 && y0 + C::TY <= g.n - 2;
+}
+
+// ---- deflation ("better preconditioning") -------------------------------------------------------------
+// Deflated Jacobi-PCG after Saad, Yeung, Erhel, Guyomarc'h (SIAM J. Sci. Comput. 21, 2000), in the one-pass arrangement:
+// coarse space Z = indicator vectors of blocks of bw x bh tiles (restricted to the unknown rows 1 .. n-2), E = Z^T A Z
+// (a weighted 5-point / 7-point graph Laplacian of the blocks; its dense inverse, <= FT_KMAX^2 doubles, lives in L2),
+//     x0 = Z E^-1 Z^T b,   every search direction  p = u - Z mu + beta p  with  E mu = Z^T A u   (=> Z^T A p = 0),
+//     s = A p = A (u - Z mu) + beta s,   p.A p = u.A u - mu.Z^T A u - beta gamma / alpha.
+// The sweep is the same 33 B per site: u is shifted by the mu of its block on its way into the stencil (the shift table
+// of a tile: one value per staged row and west / own / east block column), and Z^T A u' -- the net current leaving each
+// block -- comes from the bonds that CROSS tile borders, which the two ring warps sum per tile while the others do the
+// bond energies (five slots per tile: into the tile to the east / north / west / north-west, and into the Dirichlet rows).
+struct FtDefl {
+    int bw, bh;        // tiles per block
+    int nbx, nby;      // blocks per lattice row / column
+    int ntx, nty;      // tiles per lattice row / column
+    int k;             // nbx * nby <= FT_KMAX
+};
+enum : int { FS_E = 0, FS_N = 1, FS_W = 2, FS_NW = 3, FS_D = 4, FS_SLOTS = 5, FS_STRIDE = 8 };
+
+// blocks start at about TX x TX sites and grow (the shorter side first) until the coarse dimension fits
+PERC_HD FtDefl ft_defl_make(const Geom& g, int TX, int TY, int kmax, int bw0 = 0, int bh0 = 0)
+{
+    FtDefl D;
+    D.ntx = (g.m + TX - 1) / TX; D.nty = (g.n + TY - 1) / TY;
+    D.bw = bw0 > 0 ? bw0 : 1; D.bh = bh0 > 0 ? bh0 : (TX / TY > 0 ? TX / TY : 1);
+    for (;;) {
+        D.nbx = (D.ntx + D.bw - 1) / D.bw; D.nby = (D.nty + D.bh - 1) / D.bh;
+        D.k = D.nbx * D.nby;
+        if (D.k <= kmax) break;
+        if (D.bw * TX <= D.bh * TY) D.bw *= 2; else D.bh *= 2;
+    }
+    return D;
+}
+PERC_HD int ft_defl_block(const FtDefl& D, int ix, int iy) { return (iy / D.bh) * D.nbx + ix / D.bw; }
+
+#if defined(__CUDA_ARCH__)
+#define FT_LDCG(p) __ldcg(p)           // written by other CTAs of the same launch: read through L2
+#else
+#define FT_LDCG(p) (*(p))
+#endif
+
+// entry (staged row pr, block column cls: 0 west / 1 own / 2 east) of a tile's shift table: mu of the block the sites
+// of that row and column class lie in; 0 on rows that are not unknowns (Dirichlet rows, outside the lattice)
+template <class C>
+PERC_HD double ft_defl_shift_entry(const Geom& g, const FtDefl& D, const double* mu, int ix, int iy, int pr, int cls)
+{
+    const int gy = iy * C::TY - 1 + pr;
+    if (gy < 1 || gy > g.n - 2) return 0.0;
+    const int ty = pr == 0 ? iy - 1 : (pr > C::TY ? iy + 1 : iy), tx = ix + cls - 1;
+    if (tx < 0 || tx >= D.ntx || ty < 0 || ty >= D.nty) return 0.0;
+    return mu[ft_defl_block(D, tx, ty)];
+}
+// class of a staged column (column c <-> gx = x0 - 2 + c)
+template <class C> PERC_HD int ft_defl_cls(int col) { return col < 2 ? 0 : (col >= 2 + C::TX ? 2 : 1); }
+
+// Z^T (A u') of block B from the per-tile crossing currents F[tile][slot] (fixed order: bit-reproducible)
+PERC_HD double ft_defl_assemble(const FtDefl& D, const double* F, int B)
+{
+    const int bx = B % D.nbx, by = B / D.nbx;
+    const int dx[4] = {1, 0, -1, -1}, dy[4] = {0, 1, 0, 1};     // FS_E, FS_N, FS_W, FS_NW
+    double acc = 0.0;
+    for (int iy = by * D.bh; iy < (by + 1) * D.bh && iy < D.nty; ++iy)
+        for (int ix = bx * D.bw; ix < (bx + 1) * D.bw && ix < D.ntx; ++ix) {
+            const int tl = iy * D.ntx + ix;
+            acc += FT_LDCG(&F[tl * FS_STRIDE + FS_D]);
+            for (int s = 0; s < 4; ++s) {
+                int jx = ix + dx[s], jy = iy + dy[s];                 // current leaving through slot s
+                if (jx >= 0 && jx < D.ntx && jy < D.nty && ft_defl_block(D, jx, jy) != B) acc += FT_LDCG(&F[tl * FS_STRIDE + s]);
+                jx = ix - dx[s]; jy = iy - dy[s];                     // current entering from the tile whose slot s points here
+                if (jx >= 0 && jx < D.ntx && jy >= 0 && ft_defl_block(D, jx, jy) != B) acc -= FT_LDCG(&F[(jy * D.ntx + jx) * FS_STRIDE + s]);
+            }
+        }
+    return acc;
+}
+
+// one work item q of a tile's crossing currents: the E bonds of its east column, the N / NE / NW bonds of its top row,
+// (triangular) the NW bonds of its west column, and the bonds of rows 1 / n-2 into the Dirichlet rows.  Only bonds between
+// two unknown rows cross blocks; a bond into a Dirichlet row leaves the block for good (slot FS_D).  UNIT: u_i = 1, u_j = 0
+// (the bond weights themselves: the entries of E).  A: accessor with cf(gx, gy) and u(gx, gy).
+template <class C> struct FtFluxItems { static constexpr int N = 2 * C::TY + 3 * C::TX; };
+template <int LAT, class C, bool UNIT, class A>
+PERC_HD void ft_flux_item(const Geom& g, double g0, double gleak, const A& a, int x0, int y0, int q, double* f)
+{
+#define FT_W(cf, bit) (((cf) & (bit)) ? g0 : gleak)
+#define FT_UNK(gy) ((gy) >= 1 && (gy) <= g.n - 2)
+    if (q < C::TY) {
+        const int gy = y0 + q, gx = x0 + C::TX - 1;
+        if (gx + 1 < g.m && FT_UNK(gy)) f[FS_E] += FT_W(a.cf(gx, gy), NB_E) * (UNIT ? 1.0 : a.u(gx, gy) - a.u(gx + 1, gy));
+        return;
+    }
+    q -= C::TY;
+    if (q < C::TX) {
+        const int gx = x0 + q, gy = y0 + C::TY - 1;
+        if (gx < g.m && FT_UNK(gy) && FT_UNK(gy + 1)) {
+            const unsigned cf = a.cf(gx, gy), ex = neighbour_bits(g, gx, gy);
+            const double ui = UNIT ? 1.0 : a.u(gx, gy);
+            if (ex & NB_N) f[FS_N] += FT_W(cf, NB_N) * (UNIT ? 1.0 : ui - a.u(gx, gy + 1));
+            if (LAT == LAT_TRIANGULAR) {
+                if (ex & NB_NE) f[FS_N] += FT_W(cf, NB_NE) * (UNIT ? 1.0 : ui - a.u(gx + 1, gy + 1));
+                if (ex & NB_NW) f[q == 0 ? FS_NW : FS_N] += FT_W(cf, NB_NW) * (UNIT ? 1.0 : ui - a.u(gx - 1, gy + 1));
+            }
+        }
+        return;
+    }
+    q -= C::TX;
+    if (q < C::TY) {
+        if (LAT == LAT_TRIANGULAR && q < C::TY - 1) {
+            const int gx = x0, gy = y0 + q;
+            if (FT_UNK(gy) && FT_UNK(gy + 1) && (neighbour_bits(g, gx, gy) & NB_NW))
+                f[FS_W] += FT_W(a.cf(gx, gy), NB_NW) * (UNIT ? 1.0 : a.u(gx, gy) - a.u(gx - 1, gy + 1));
+        }
+        return;
+    }
+    q -= C::TY;
+    const int top = q >= C::TX;
+    q -= top * C::TX;
+    const int gy = top ? g.n - 2 : 1, gx = x0 + q;
+    if (gy < y0 || gy >= y0 + C::TY || !FT_UNK(gy) || gx >= g.m) return;
+    const unsigned cf = a.cf(gx, gy), ex = neighbour_bits(g, gx, gy);
+    const double ui = UNIT ? 1.0 : a.u(gx, gy);
+    double acc = 0.0;
+    if (top) {
+        if (ex & NB_N) acc += FT_W(cf, NB_N);
+        if (ex & NB_NW) acc += FT_W(cf, NB_NW);
+        if (ex & NB_NE) acc += FT_W(cf, NB_NE);
+    } else {
+        if (ex & NB_S) acc += FT_W(cf, NB_S);
+        if (ex & NB_SW) acc += FT_W(cf, NB_SW);
+        if (ex & NB_SE) acc += FT_W(cf, NB_SE);
+    }
+    // n = 3: row 1 is also row n-2 and both items add their share
+    f[FS_D] += acc * ui;
+#undef FT_W
+#undef FT_UNK
+}
+
+// accessor over a tile's shared-memory stage: u' of the compute rows (ss) and the staged conduct bytes
+template <class C> struct FtStageAcc {
+    const double* ss; const uint8_t* scf; int x0, y0;
+    PERC_HD unsigned cf(int gx, int gy) const { return scf[(gy - y0 + 1) * C::CLD + (gx - x0 + 16)]; }
+    PERC_HD double u(int gx, int gy) const { return ss[(gy - y0) * C::LD + (gx - x0 + 2)]; }
+};
+// accessor over the conduct bytes in global memory (UNIT items only)
+struct FtGlobalAcc {
+    const uint8_t* cfull; int m;
+    PERC_HD unsigned cf(int gx, int gy) const { return cfull[(int64_t)gy * m + gx]; }
+    PERC_HD double u(int, int) const { return 0.0; }
+};
+
+// crossing currents of a tile: thread tid < FtFluxItems::N takes work item tid, partial sums into f[FS_SLOTS]
+template <int LAT, class C>
+PERC_HD void ft_phase_flux(const Geom& g, const FtScalars& sc, const double* ss, const uint8_t* scf, int x0, int y0, int tid, double* f)
+{
+    if (tid >= FtFluxItems<C>::N) return;
+    const FtStageAcc<C> a{ss, scf, x0, y0};
+    ft_flux_item<LAT, C, false>(g, sc.g0, sc.gleak, a, x0, y0, tid, f);
+}
+
+// The terms of Z^T (A u') of every block as a static list (CSR over the blocks: ptr[k + 1], ent[]): entry = (tile * FS_STRIDE
+// + slot) << 1 | (1 if the current ENTERS the block).  Same terms in the same order as ft_defl_assemble; built once per
+// lattice shape on the host, walked by one warp per block on the device.
+template <class Vec>
+inline void ft_defl_terms(const FtDefl& D, Vec& ptr, Vec& ent)
+{
+    const int dx[4] = {1, 0, -1, -1}, dy[4] = {0, 1, 0, 1};
+    ptr.clear(); ent.clear();
+    for (int B = 0; B < D.k; ++B) {
+        ptr.push_back((int)ent.size());
+        const int bx = B % D.nbx, by = B / D.nbx;
+        for (int iy = by * D.bh; iy < (by + 1) * D.bh && iy < D.nty; ++iy)
+            for (int ix = bx * D.bw; ix < (bx + 1) * D.bw && ix < D.ntx; ++ix) {
+                const int tl = iy * D.ntx + ix;
+                ent.push_back((tl * FS_STRIDE + FS_D) << 1);
+                for (int s = 0; s < 4; ++s) {
+                    int jx = ix + dx[s], jy = iy + dy[s];
+                    if (jx >= 0 && jx < D.ntx && jy < D.nty && ft_defl_block(D, jx, jy) != B) ent.push_back((tl * FS_STRIDE + s) << 1);
+                    jx = ix - dx[s]; jy = iy - dy[s];
+                    if (jx >= 0 && jx < D.ntx && jy >= 0 && ft_defl_block(D, jx, jy) != B) ent.push_back((((jy * D.ntx + jx) * FS_STRIDE + s) << 1) | 1);
+                }
+            }
+    }
+    ptr.push_back((int)ent.size());
+}
+
+// deflated start: x0 = Z nu with E nu = Z^T b; returns u0 = D^-1 (b - A Z nu) of the unknown site (x, y) (cf: its conduct
+// byte); *bi = its right-hand side (bonds into the top row at Va), *nui = nu of its block
+template <class C>
+PERC_HD double ft_defl_u0(const Geom& g, const FtDefl& D, unsigned cf, const double* nu, int x, int y, double Va, double g0,
+                          double gleak, double* bi, double* nui)
+{
+    const unsigned ex = neighbour_bits(g, x, y);
+    cf &= ex;
+    const int nc = ft_popc(cf), nl = ft_popc(ex) - nc;
+    const double d = fma((double)nl, gleak, (double)nc * g0);
+    const double ni = nu[ft_defl_block(D, x / C::TX, y / C::TY)];
+    const unsigned bits[8] = {NB_E, NB_N, NB_NW, NB_NE, NB_W, NB_S, NB_SW, NB_SE};
+    const int ddx[8] = {1, 0, -1, 1, -1, 0, -1, 1}, ddy[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+    double b = 0.0, acc = 0.0;
+    for (int k = 0; k < 8; ++k) {
+        if (!(ex & bits[k])) continue;
+        const double w = (cf & bits[k]) ? g0 : gleak;
+        const int xx = x + ddx[k], yy = y + ddy[k];
+        if (yy == g.n - 1) b += w * Va;
+        if (yy >= 1 && yy <= g.n - 2) acc += w * (ni - nu[ft_defl_block(D, xx / C::TX, yy / C::TY)]);
+        else acc += w * ni;
+    }
+    *bi = b; *nui = ni;
+    return d > 0.0 ? (b - acc) / d : 0.0;
 }
 
 // ---- phase U: u = r / d on the staged box (tile + 2-site halo; rows y0-1 .. y0+TY+1) -------------------------
@@ -159,29 +365,45 @@ PERC_HD void ft_phase_u(const Geom& g, const double* sr, const uint8_t* scf, dou
 // ---- phase M: w = A u, s' = w + beta s, r' = r - alpha s', u' = r'/d on the compute rows; stores r', s' of
 // the tile rows; u' replaces s in shared memory (each thread overwrites only what it has read itself);
 // p / x of the two read-out rows; sums r'.u' and r'.r' over the tile's sites ---------------------------------
-// FAST (only with C::SPLIT): the tile is geometry-free (ft_interior) by construction of the call -- the runtime flag is
-// not consulted, every compute row is an unknown row with its full neighbourhood and none of them is a read-out row
-template <int LAT, class C, bool FAST = false>
+template <int LAT, class C>
 PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr, double* ss, const uint8_t* scf,
                            const double* su, const FtDiag* dtab, int x0, int y0, bool interior_flag, int tid,
                            double* __restrict__ r_out, double* __restrict__ s_out, double* __restrict__ xrow,
-                           double* __restrict__ prow, double& acc_rz, double& acc_rr)
+                           double* __restrict__ prow, double& acc_rz, double& acc_rr, const double* sft = nullptr)
 {
     if (tid >= C::MAIN_THREADS) return;
-    const bool interior = C::SPLIT ? FAST : interior_flag;
+    const bool interior = interior_flag;
     const int tx = tid & 63, ty = tid >> 6, lane = tid & 31;
     const int gx = x0 + 2 * tx, lr0 = ty * C::RPT;
     const double dg = sc.g0 - sc.gleak, alpha = sc.alpha, beta = sc.beta;
     const double* c = &su[(lr0 + 1) * C::LD + 2 + 2 * tx];
+    // deflation: the stencil sees u - Z mu (dn, cc, up, lf, rt, ... below are the SHIFTED values, c0 / c1 keep the site's
+    // own u for the update); sft[pr * 4 + class]: mu of staged row pr, block column west / own / east.  The first and the
+    // last thread of a tile row look across the tile's west / east border.
+    const int selL = tx == 0 ? 0 : 1, selR = tx == 63 ? 2 : 1;
     ft_d2 dn = ft_ld2(c - C::LD), cc = ft_ld2(c);
     double drt = c[-C::LD + 2];                              // row below, x+2: SE neighbour of the odd column
+    double c0 = cc.x, c1 = cc.y;
+    if (C::DEFL) {
+        const double md = sft[lr0 * 4 + 1], mc = sft[(lr0 + 1) * 4 + 1];
+        dn.x -= md; dn.y -= md; cc.x -= mc; cc.y -= mc;
+        drt -= sft[lr0 * 4 + selR];
+    }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int j = 0; j < C::RPT; ++j, c += C::LD) {
         const int lr = lr0 + j, gy = y0 + lr;
-        const ft_d2 up = ft_ld2(c + C::LD);
-        const double lf = c[-1], rt = c[2];
+        ft_d2 up = ft_ld2(c + C::LD);
+        double lf = c[-1], rt = c[2];
+        const double u0 = up.x, u1 = up.y;
+        double nw = LAT == LAT_TRIANGULAR ? c[C::LD - 1] : 0.0;
+        if (C::DEFL) {
+            const double mu_up = sft[(lr + 2) * 4 + 1];
+            up.x -= mu_up; up.y -= mu_up;
+            lf -= sft[(lr + 1) * 4 + selL]; rt -= sft[(lr + 1) * 4 + selR];
+            if (LAT == LAT_TRIANGULAR) nw -= sft[(lr + 2) * 4 + selL];
+        }
         const bool valid = interior || (gy >= 1 && gy <= g.n - 2 && gx < g.m);
         const unsigned c01 = *reinterpret_cast<const unsigned short*>(&scf[(lr + 1) * C::CLD + 16 + 2 * tx]);
         unsigned cf0 = c01 & 0xffu, cf1 = c01 >> 8;
@@ -191,7 +413,7 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
             e0 = ft_interior_ex<LAT>(gx); e1 = ft_interior_ex<LAT>(gx + 1);
             all0 = (cc.y + lf) + (up.x + dn.x);
             all1 = (rt + cc.x) + (up.y + dn.y);
-            if (LAT == LAT_TRIANGULAR) { all0 += c[C::LD - 1] + up.y; all1 += dn.x + drt; }
+            if (LAT == LAT_TRIANGULAR) { all0 += nw + up.y; all1 += dn.x + drt; }
         } else {
             e0 = valid ? neighbour_bits(g, gx, gy) : 0u; e1 = valid ? neighbour_bits(g, gx + 1, gy) : 0u;
             cf0 &= e0; cf1 &= e1;
@@ -199,16 +421,16 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
             if (e0 & NB_E) all0 += cc.y;  if (e0 & NB_W) all0 += lf;   if (e0 & NB_N) all0 += up.x;  if (e0 & NB_S) all0 += dn.x;
             if (e1 & NB_E) all1 += rt;    if (e1 & NB_W) all1 += cc.x; if (e1 & NB_N) all1 += up.y;  if (e1 & NB_S) all1 += dn.y;
             if (LAT == LAT_TRIANGULAR) {
-                if (e0 & NB_NW) all0 += c[C::LD - 1]; if (e0 & NB_NE) all0 += up.y;
+                if (e0 & NB_NW) all0 += nw; if (e0 & NB_NE) all0 += up.y;
                 if (e1 & NB_SW) all1 += dn.x;         if (e1 & NB_SE) all1 += drt;
             }
         }
         double con0 = 0.0, con1 = 0.0;                       // conducting neighbours
-        ft_cadd<C>(con0, cc.y, cf0 & NB_E); ft_cadd<C>(con0, lf, cf0 & NB_W);   ft_cadd<C>(con0, up.x, cf0 & NB_N); ft_cadd<C>(con0, dn.x, cf0 & NB_S);
-        ft_cadd<C>(con1, rt, cf1 & NB_E);   ft_cadd<C>(con1, cc.x, cf1 & NB_W); ft_cadd<C>(con1, up.y, cf1 & NB_N); ft_cadd<C>(con1, dn.y, cf1 & NB_S);
+        ft_padd(con0, cc.y, cf0 & NB_E); ft_padd(con0, lf, cf0 & NB_W);   ft_padd(con0, up.x, cf0 & NB_N); ft_padd(con0, dn.x, cf0 & NB_S);
+        ft_padd(con1, rt, cf1 & NB_E);   ft_padd(con1, cc.x, cf1 & NB_W); ft_padd(con1, up.y, cf1 & NB_N); ft_padd(con1, dn.y, cf1 & NB_S);
         if (LAT == LAT_TRIANGULAR) {
-            ft_cadd<C>(con0, c[C::LD - 1], cf0 & NB_NW); ft_cadd<C>(con0, up.y, cf0 & NB_NE);
-            ft_cadd<C>(con1, dn.x, cf1 & NB_SW);         ft_cadd<C>(con1, drt, cf1 & NB_SE);
+            ft_padd(con0, nw, cf0 & NB_NW); ft_padd(con0, up.y, cf0 & NB_NE);
+            ft_padd(con1, dn.x, cf1 & NB_SW);         ft_padd(con1, drt, cf1 & NB_SE);
         }
         const int n0 = ft_popc(cf0), n1 = ft_popc(cf1);
         constexpr int DEG = LAT == LAT_SQUARE ? 4 : 6;
@@ -221,7 +443,7 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
         const double sn0 = w0 + beta * s2.x, sn1 = w1 + beta * s2.y;
         double rn0, rn1, un0, un1;
         if (C::USTATE) {                                     // sr / su hold u: u' = u - alpha D^-1 s', r' = d u'
-            un0 = cc.x - alpha * (sn0 * t0.inv); un1 = cc.y - alpha * (sn1 * t1.inv);
+            un0 = c0 - alpha * (sn0 * t0.inv); un1 = c1 - alpha * (sn1 * t1.inv);
             rn0 = t0.d * un0; rn1 = t1.d * un1;
         } else {
             rn0 = r2.x - alpha * sn0; rn1 = r2.y - alpha * sn1;
@@ -234,9 +456,8 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
             if (C::USTATE) ft_st2(r_out + i, un0, un1); else ft_st2(r_out + i, rn0, rn1);
             acc_rz += rn0 * un0 + rn1 * un1;
             acc_rr += rn0 * rn0 + rn1 * rn1;
-            // the rows the read-out consumes: p = u + beta p, x += alpha p (never inside a geometry-free tile: its rows
-            // lie in [TY, n-3])
-            if (!(C::SPLIT && FAST) && (gy == 1 || gy == g.n - 2)) {
+            // the rows the read-out consumes: p = u + beta p, x += alpha p
+            if (gy == 1 || gy == g.n - 2) {
                 const int64_t o = (gy == 1 ? 0 : g.m) + gx;
                 const ft_d2 p2 = ft_ld2(prow + o), x2 = ft_ld2(xrow + o);
                 const double p0 = cc.x + beta * p2.x, p1 = cc.y + beta * p2.y;
@@ -246,13 +467,14 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
         }
         drt = rt;
         dn = cc; cc = up;
+        c0 = u0; c1 = u1;
     }
 }
 
 // east / west ring columns (gx = x0 - 1 and x0 + TX) of the compute rows: u' only (one thread per site)
 template <int LAT, class C>
 PERC_HD void ft_phase_ringcols(const Geom& g, const FtScalars& sc, const double* sr, double* ss, const uint8_t* scf,
-                               const double* su, const FtDiag* dtab, int x0, int y0, int tid)
+                               const double* su, const FtDiag* dtab, int x0, int y0, int tid, const double* sft = nullptr)
 {
     const int lane = tid & 31;
     for (int q = tid - C::RING_T0; q >= 0 && q < 2 * C::CR; q += C::RING_NT) {
@@ -264,13 +486,16 @@ PERC_HD void ft_phase_ringcols(const Geom& g, const FtScalars& sc, const double*
         const unsigned cf = scf[(lr + 1) * C::CLD + (side ? 16 + C::TX : 15)] & ex;
         const double* c = &su[(lr + 1) * C::LD + col];
         double all = 0.0, con = 0.0;
-#define FT_NB(bit, off) if (ex & bit) { const double v = c[off]; all += v; if (cf & bit) con += v; }
-        FT_NB(NB_E, 1) FT_NB(NB_W, -1) FT_NB(NB_N, C::LD) FT_NB(NB_S, -C::LD)
-        if (LAT == LAT_TRIANGULAR) { FT_NB(NB_NW, C::LD - 1) FT_NB(NB_NE, C::LD + 1) FT_NB(NB_SW, -C::LD - 1) FT_NB(NB_SE, -C::LD + 1) }
+        // (deflation: every value enters the stencil shifted by the mu of its block, see ft_phase_main)
+#define FT_SH(dc, dr) (C::DEFL ? sft[(lr + 1 + (dr)) * 4 + ft_defl_cls<C>(col + (dc))] : 0.0)
+#define FT_NB(bit, dc, dr) if (ex & bit) { const double v = c[(dr) * C::LD + (dc)] - FT_SH(dc, dr); all += v; if (cf & bit) con += v; }
+        FT_NB(NB_E, 1, 0) FT_NB(NB_W, -1, 0) FT_NB(NB_N, 0, 1) FT_NB(NB_S, 0, -1)
+        if (LAT == LAT_TRIANGULAR) { FT_NB(NB_NW, -1, 1) FT_NB(NB_NE, 1, 1) FT_NB(NB_SW, -1, -1) FT_NB(NB_SE, 1, -1) }
 #undef FT_NB
         const int nc = ft_popc(cf);
         const FtDiag t = dtab[C::tab(nc, ft_popc(ex) - nc, lane)];
-        const double w = t.d * c[0] - (sc.gleak * all + (sc.g0 - sc.gleak) * con);
+        const double w = t.d * (c[0] - FT_SH(0, 0)) - (sc.gleak * all + (sc.g0 - sc.gleak) * con);
+#undef FT_SH
         const double sn = w + sc.beta * ss[lr * C::LD + col];
         if (C::USTATE) un = c[0] - sc.alpha * (sn * t.inv);
         else un = (sr[(lr + 1) * C::LD + col] - sc.alpha * sn) * t.inv;
@@ -281,12 +506,12 @@ PERC_HD void ft_phase_ringcols(const Geom& g, const FtScalars& sc, const double*
 
 // ---- phase E: u'.A u' as the energy of the bonds OWNED by the tile's sites (E, N, NW, NE), u' from shared
 // memory (zeros on Dirichlet rows and outside the lattice) ---------------------------------------------------
-template <int LAT, class C, bool FAST = false>
+template <int LAT, class C>
 PERC_HD void ft_phase_energy(const Geom& g, const FtScalars& sc, const double* ss, const uint8_t* scf, int x0, int y0,
                              bool interior_flag, int tid, double& acc_e)
 {
     if (tid >= C::MAIN_THREADS) return;
-    const bool interior = C::SPLIT ? FAST : interior_flag;
+    const bool interior = interior_flag;
     const int tx = tid & 63, ty = tid >> 6;
     const int gx = x0 + 2 * tx, lr0 = ty * C::RPT;
     const double dg = sc.g0 - sc.gleak;
@@ -306,24 +531,24 @@ PERC_HD void ft_phase_energy(const Geom& g, const FtScalars& sc, const double* s
         double all = 0.0, con = 0.0;
         if (interior) {
             all = (dE0 * dE0 + dE1 * dE1) + (dN0 * dN0 + dN1 * dN1);
-            ft_cadd<C>(con, dE0 * dE0, cf0 & NB_E); ft_cadd<C>(con, dE1 * dE1, cf1 & NB_E);
-            ft_cadd<C>(con, dN0 * dN0, cf0 & NB_N); ft_cadd<C>(con, dN1 * dN1, cf1 & NB_N);
+            ft_padd(con, dE0 * dE0, cf0 & NB_E); ft_padd(con, dE1 * dE1, cf1 & NB_E);
+            ft_padd(con, dN0 * dN0, cf0 & NB_N); ft_padd(con, dN1 * dN1, cf1 & NB_N);
             if (LAT == LAT_TRIANGULAR) {
                 const double dNW = cc.x - c[C::LD - 1], dNE = cc.x - up.y;
                 all += dNW * dNW + dNE * dNE;
-                ft_cadd<C>(con, dNW * dNW, cf0 & NB_NW); ft_cadd<C>(con, dNE * dNE, cf0 & NB_NE);
+                ft_padd(con, dNW * dNW, cf0 & NB_NW); ft_padd(con, dNE * dNE, cf0 & NB_NE);
             }
         } else {
             const unsigned e0 = neighbour_bits(g, gx, gy), e1 = neighbour_bits(g, gx + 1, gy);
             const bool rowE = gy >= 1 && gy <= g.n - 2;      // an E bond joins two sites of one row
-            if (rowE && (e0 & NB_E)) { all += dE0 * dE0; ft_cadd<C>(con, dE0 * dE0, cf0 & NB_E); }
-            if (rowE && (e1 & NB_E)) { all += dE1 * dE1; ft_cadd<C>(con, dE1 * dE1, cf1 & NB_E); }
-            if (e0 & NB_N) { all += dN0 * dN0; ft_cadd<C>(con, dN0 * dN0, cf0 & NB_N); }
-            if (e1 & NB_N) { all += dN1 * dN1; ft_cadd<C>(con, dN1 * dN1, cf1 & NB_N); }
+            if (rowE && (e0 & NB_E)) { all += dE0 * dE0; ft_padd(con, dE0 * dE0, cf0 & NB_E); }
+            if (rowE && (e1 & NB_E)) { all += dE1 * dE1; ft_padd(con, dE1 * dE1, cf1 & NB_E); }
+            if (e0 & NB_N) { all += dN0 * dN0; ft_padd(con, dN0 * dN0, cf0 & NB_N); }
+            if (e1 & NB_N) { all += dN1 * dN1; ft_padd(con, dN1 * dN1, cf1 & NB_N); }
             if (LAT == LAT_TRIANGULAR) {
                 const double dNW = cc.x - c[C::LD - 1], dNE = cc.x - up.y;
-                if (e0 & NB_NW) { all += dNW * dNW; ft_cadd<C>(con, dNW * dNW, cf0 & NB_NW); }
-                if (e0 & NB_NE) { all += dNE * dNE; ft_cadd<C>(con, dNE * dNE, cf0 & NB_NE); }
+                if (e0 & NB_NW) { all += dNW * dNW; ft_padd(con, dNW * dNW, cf0 & NB_NW); }
+                if (e0 & NB_NE) { all += dNE * dNE; ft_padd(con, dNE * dNE, cf0 & NB_NE); }
             }
         }
         acc_e += sc.gleak * all + dg * con;

@@ -15,9 +15,9 @@ SO_PATH = os.path.join(_HERE, "libperc_b200.so")
 SQUARE, TRIANGULAR = 1, 2
 SITE, BOND, MIXED = 1, 2, 3
 
-E_ARG, E_ODD_M, E_HANDLE, E_STATE, E_SIZE, E_NOSPAN, E_NCCL, E_IFACE = -1, -2, -3, -4, -5, -6, -7, -8
+E_ARG, E_ODD_M, E_HANDLE, E_STATE, E_SIZE, E_NOSPAN, E_NCCL, E_IFACE, E_SELECT = -1, -2, -3, -4, -5, -6, -7, -8, -9
 _ENAMES = {E_ARG: "PERC_E_ARG", E_ODD_M: "PERC_E_ODD_M", E_HANDLE: "PERC_E_HANDLE", E_STATE: "PERC_E_STATE",
-           E_SIZE: "PERC_E_SIZE", E_NOSPAN: "PERC_E_NOSPAN", E_NCCL: "PERC_E_NCCL", E_IFACE: "PERC_E_IFACE"}
+           E_SIZE: "PERC_E_SIZE", E_NOSPAN: "PERC_E_NOSPAN", E_NCCL: "PERC_E_NCCL", E_IFACE: "PERC_E_IFACE", E_SELECT: "PERC_E_SELECT"}
 
 # every symbol include/perc_abi.h declares
 SYMBOLS = [
@@ -290,11 +290,12 @@ class Lattice:
 
     # ---- instrumentation
     def set_solver(self, mode):
-        """0 = automatic (one-pass iteration kernel whenever it applies), 1 = always the two-kernel form"""
+        """0 = automatic (deflated one-pass iteration kernel whenever it applies), 1 = always the two-kernel form
+        (plain Jacobi-PCG, linbcg's iteration count), 2 = one-pass kernel without deflation"""
         self._call("perc_set_solver", _i32(mode))
 
     def solver_used(self):
-        """1 if the handle's last conductance solve ran the one-pass kernel"""
+        """which iteration kernel the handle's last conductance solve ran: 0 two-kernel form, 1 one-pass, 2 deflated one-pass"""
         f = C.c_int32(0)
         self._call("perc_solver_used", C.byref(f))
         return f.value

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <vector>
 #include "../percolation_b200/csrc/pcg_fused_tile.cuh"
+#include "../percolation_b200/csrc/pcg_defl_host.h"
 
 using namespace perc;
 
@@ -95,24 +96,123 @@ int solve(const Geom& g, const std::vector<uint8_t>& cf, double Va, double g0, d
                 for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_u<LAT, C>(g, sr.data(), scf.data(), su.data(), dtab.data(), x0, y0, interior, tid);
             const double* up = C::USTATE ? sr.data() : su.data();
             for (int tid = C::THREADS - 1; tid >= 0; --tid) {
-                if (C::SPLIT && interior)
-                    ft_phase_main<LAT, C, true>(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), x0, y0, true, tid,
-                                                r[cur ^ 1].data(), s[cur ^ 1].data(), xrow.data(), prow.data(), rz, rr);
-                else
-                    ft_phase_main<LAT, C, false>(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), x0, y0, interior, tid,
-                                                 r[cur ^ 1].data(), s[cur ^ 1].data(), xrow.data(), prow.data(), rz, rr);
+                ft_phase_main<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), x0, y0, interior, tid,
+                                      r[cur ^ 1].data(), s[cur ^ 1].data(), xrow.data(), prow.data(), rz, rr);
                 ft_phase_ringcols<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), x0, y0, tid);
             }
-            for (int tid = 0; tid < C::THREADS; ++tid) {
-                if (C::SPLIT && interior) ft_phase_energy<LAT, C, true>(g, sc, ss.data(), scf.data(), x0, y0, true, tid, en);
-                else ft_phase_energy<LAT, C, false>(g, sc, ss.data(), scf.data(), x0, y0, interior, tid, en);
-            }
+            for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_energy<LAT, C>(g, sc, ss.data(), scf.data(), x0, y0, interior, tid, en);
         }
         ft_scalar_step(st, rz, rr, en, prime);
         cur ^= 1;
         if (pass > 50 * 1000 * 1000) return -1;
     }
     // read-out (Sq/bondc.f:554-592): rows 0 and n-1 of G~ V, off-diagonals below read_thresh dropped
+    double top = 0.0, bot = 0.0;
+    for (int e = 0; e < 2; ++e)
+        for (int x = 0; x < m; ++x) {
+            const int y = e == 0 ? 0 : n - 1;
+            const unsigned ex = neighbour_bits(g, x, y), c = cf[(size_t)y * m + x];
+            const double vi = e == 0 ? 0.0 : Va;
+            double acc = diag_of(g, cf, x, y, g0, gleak) * vi;
+            const int xl = x > 0 ? x - 1 : m - 1, xr = x + 1 < m ? x + 1 : 0;
+            auto val = [&](int xx, int yy) { return yy == 0 ? 0.0 : yy == n - 1 ? Va : yy == 1 ? xrow[xx] : xrow[(size_t)m + xx]; };
+#define NBR(bit, xx, yy) if (ex & bit) { const double wt = (c & bit) ? g0 : gleak; if (fabs(wt) >= read_thresh) acc -= wt * val(xx, yy); }
+            NBR(NB_E, xr, y) NBR(NB_W, xl, y) NBR(NB_N, x, y + 1) NBR(NB_S, x, y - 1)
+            NBR(NB_NW, xl, y + 1) NBR(NB_NE, xr, y + 1) NBR(NB_SW, xl, y - 1) NBR(NB_SE, xr, y - 1)
+#undef NBR
+            if (e == 0) bot += acc; else top += acc;
+        }
+    *Gtop = top / Va; *Gbot = fabs(bot) / Va; *iter = st.iter; *err = st.err;
+    return 0;
+}
+
+
+// the deflated one-pass solve (FtCfgD), phase by phase as pcg_fused_kernel<.., FtCfgD> runs it: shift table per tile,
+// main / ring / energy phases, the crossing currents by the ring threads, then the coarse stage (assemble Z^T A u',
+// mu = E^-1 ., the scalar recurrences with delta - mu . Z^T A u')
+template <int LAT, class C>
+int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double g0, double gleak, double tol, int itmax,
+               double read_thresh, double* Gtop, double* Gbot, int* iter, double* err, int* coarse_dim, int bw0, int bh0)
+{
+    const int m = g.m, n = g.n;
+    const int64_t t = g.t;
+    const FtDefl D = ft_defl_make(g, C::TX, C::TY, FT_KMAX, bw0, bh0);
+    *coarse_dim = D.k;
+    const int ntiles = D.ntx * D.nty;
+    // E from the crossing bond weights, dense inverse
+    std::vector<double> W((size_t)ntiles * FS_STRIDE, 0.0), Einv((size_t)D.k * D.k), F((size_t)ntiles * FS_STRIDE, 0.0);
+    const FtGlobalAcc ga{cf.data(), m};
+    for (int tl = 0; tl < ntiles; ++tl)
+        for (int q = 0; q < FtFluxItems<C>::N; ++q)
+            ft_flux_item<LAT, C, true>(g, g0, gleak, ga, (tl % D.ntx) * C::TX, (tl / D.ntx) * C::TY, q, &W[(size_t)tl * FS_STRIDE]);
+    if (ft_defl_build_einv(D, W.data(), Einv.data(), 2)) return -4;
+    std::vector<int> tptr, tent;
+    ft_defl_terms(D, tptr, tent);
+    // x0 = Z nu, E nu = Z^T b; u0 = D^-1 (b - A Z nu)
+    std::vector<double> r[2], s[2], xrow((size_t)2 * m, 0.0), prow((size_t)2 * m, 0.0), fb((size_t)D.k, 0.0), nu((size_t)D.k, 0.0), mu((size_t)D.k, 0.0);
+    for (int k = 0; k < 2; ++k) { r[k].assign((size_t)t, 0.0); s[k].assign((size_t)t, 0.0); }
+    double bn = 0.0;
+    {
+        const std::vector<double> zero((size_t)D.k, 0.0);
+        for (int x = 0; x < m; ++x) {
+            double b, ni;
+            const double z = ft_defl_u0<C>(g, D, cf[(size_t)(n - 2) * m + x], zero.data(), x, n - 2, Va, g0, gleak, &b, &ni);
+            fb[ft_defl_block(D, x / C::TX, (n - 2) / C::TY)] += b;
+            bn += z * z;
+        }
+    }
+    for (int i = 0; i < D.k; ++i) { double a = 0.0; for (int j = 0; j < D.k; ++j) a += Einv[(size_t)i * D.k + j] * fb[j]; nu[i] = a; }
+    for (int y = 1; y <= n - 2; ++y)
+        for (int x = 0; x < m; ++x) {
+            double b, ni;
+            r[0][(size_t)y * m + x] = ft_defl_u0<C>(g, D, cf[(size_t)y * m + x], nu.data(), x, y, Va, g0, gleak, &b, &ni);
+            if (y == 1) xrow[x] = ni;
+            if (y == n - 2) xrow[(size_t)m + x] = ni;
+        }
+    FtState st{};
+    st.bnrm = sqrt(bn); st.tol = tol; st.itmax = itmax;
+    std::vector<FtDiag> dtab(64 * C::DC);
+    for (int k = 0; k < 64 * C::DC; ++k) dtab[k] = ft_diag_entry(k / C::DC, g0, gleak);
+    std::vector<double> sr((size_t)C::RR * C::LD), ss((size_t)C::SR * C::LD), sft((size_t)C::RR * 4);
+    std::vector<uint8_t> scf((size_t)C::RR * C::CLD);
+    int cur = 0;
+    for (int pass = 0; !st.done; ++pass) {
+        const int prime = pass == 0;
+        const FtScalars sc{g0, gleak, prime ? 0.0 : st.alpha, prime ? 0.0 : st.beta};
+        double rz = 0.0, rr = 0.0, en = 0.0;
+        for (int tl = 0; tl < ntiles; ++tl) {
+            const int ix = tl % D.ntx, iy = tl / D.ntx, x0 = ix * C::TX, y0 = iy * C::TY;
+            box_copy(sr.data(), r[cur].data(), m, n, x0 - 2, y0 - 1, C::LD, C::RR);
+            box_copy(ss.data(), s[cur].data(), m, n, x0 - 2, y0, C::LD, C::SR);
+            box_copy(scf.data(), cf.data(), m, n, x0 - 16, y0 - 1, C::CLD, C::RR);
+            for (int j = 0; j < C::RR * 4; ++j) sft[j] = (j & 3) == 3 ? NAN : ft_defl_shift_entry<C>(g, D, mu.data(), ix, iy, j >> 2, j & 3);
+            const bool interior = ft_interior<C>(g, x0, y0);
+            for (int tid = C::THREADS - 1; tid >= 0; --tid) {
+                ft_phase_main<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), sr.data(), dtab.data(), x0, y0, interior, tid,
+                                             r[cur ^ 1].data(), s[cur ^ 1].data(), xrow.data(), prow.data(), rz, rr, sft.data());
+                ft_phase_ringcols<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), sr.data(), dtab.data(), x0, y0, tid, sft.data());
+            }
+            for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_energy<LAT, C>(g, sc, ss.data(), scf.data(), x0, y0, interior, tid, en);
+            // crossing currents: per ring thread partial sums, folded thread by thread (the kernel: shuffles, then the two warps)
+            double fl[FS_SLOTS] = {0, 0, 0, 0, 0};
+            for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_flux<LAT, C>(g, sc, ss.data(), scf.data(), x0, y0, tid, fl);
+            for (int k = 0; k < FS_SLOTS; ++k) F[(size_t)tl * FS_STRIDE + k] = fl[k];
+        }
+        // coarse stage
+        // (the kernel walks the static term list, one warp per block; both forms of the sum are checked against each other)
+        std::vector<double> f((size_t)D.k);
+        for (int B = 0; B < D.k; ++B) {
+            f[B] = ft_defl_assemble(D, F.data(), B);
+            double a = 0.0;
+            for (int e = tptr[B]; e < tptr[B + 1]; ++e) a += (tent[e] & 1) ? -F[tent[e] >> 1] : F[tent[e] >> 1];
+            if (a != f[B]) return -5;
+        }
+        double mf = 0.0;
+        for (int i = 0; i < D.k; ++i) { double a = 0.0; for (int j = 0; j < D.k; ++j) a += Einv[(size_t)i * D.k + j] * f[j]; mu[i] = a; mf += a * f[i]; }
+        ft_scalar_step(st, rz, rr, en - mf, prime);
+        cur ^= 1;
+        if (pass > 50 * 1000 * 1000) return -1;
+    }
     double top = 0.0, bot = 0.0;
     for (int e = 0; e < 2; ++e)
         for (int x = 0; x < m; ++x) {
@@ -149,8 +249,20 @@ extern "C" int fused_emul_solve(int lattice, int m, int n, const double* w, doub
     switch (cfg) {
     case 0: return RUN(FtCfgA);
     case 2: return RUN(FtCfgA3);
-    case 5: return RUN(FtCfgA4);
     }
 #undef RUN
     return -3;
+}
+
+// the deflated solver (FtCfgD); bw, bh: tiles per block (0 = the library's choice); coarse_dim: number of blocks
+extern "C" int fused_emul_solve_defl(int lattice, int m, int n, const double* w, double Va, double g0, double gleak,
+                                     double tol, int itmax, double read_thresh, double* Gtop, double* Gbot, int* iter,
+                                     double* err, int* coarse_dim, int bw, int bh)
+{
+    if (m % 16 || n < 4) return -2;
+    const Geom g = make_geom(lattice, m, n, 0);
+    std::vector<uint8_t> cf;
+    build_cfull(g, w, gleak, cf);
+    return lattice == LAT_SQUARE ? solve_defl<LAT_SQUARE, FtCfgD>(g, cf, Va, g0, gleak, tol, itmax, read_thresh, Gtop, Gbot, iter, err, coarse_dim, bw, bh)
+                                 : solve_defl<LAT_TRIANGULAR, FtCfgD>(g, cf, Va, g0, gleak, tol, itmax, read_thresh, Gtop, Gbot, iter, err, coarse_dim, bw, bh);
 }

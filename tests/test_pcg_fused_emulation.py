@@ -21,9 +21,10 @@ def emul():
     so = os.path.join(out, "libpcg_fused_emul.so")
     src = os.path.join(HERE, "pcg_fused_emul.cpp")
     deps = [src, os.path.join(ROOT, "percolation_b200", "csrc", "pcg_fused_tile.cuh"),
-            os.path.join(ROOT, "percolation_b200", "csrc", "geometry.cuh")]
+            os.path.join(ROOT, "percolation_b200", "csrc", "geometry.cuh"),
+            os.path.join(ROOT, "percolation_b200", "csrc", "pcg_defl_host.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++", src, "-o", so])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-x", "c++", src, "-o", so])
     return C.CDLL(so)
 
 
@@ -62,8 +63,8 @@ CASES = [
 ]
 
 
-# every case with the default variant (pcg_fused_tile.cuh: FtCfgA3 = 2) and, bit for bit, with FtCfgA4 = 5; two cases with
-# interior tiles for the first variant (0 = FtCfgA: r as the state vector, phase U, per-tile reductions)
+# every case with the plain one-pass variant (pcg_fused_tile.cuh: FtCfgA3 = 2); two cases with interior tiles for the
+# first variant (0 = FtCfgA: r as the state vector, phase U, per-tile reductions)
 DEFAULT_CFG = 2
 CFG_CASES = [(DEFAULT_CFG,) + c for c in CASES] + [(0, 1, "MIXED", 400, 84, 0.85, 0.72), (0, 2, "BOND", 400, 84, 0.0, 0.40)]
 
@@ -88,10 +89,6 @@ def test_emulated_fused_pcg_matches_oracle(emul, O, cfg, lat, kind, m, n, ps, pb
         assert got["tiles_fast"] > 0          # the geometry-free fast path was exercised
     if cfg != DEFAULT_CFG:
         return
-    # FtCfgA4 is FtCfgA3 with fewer instructions (own instantiation for the geometry-free tiles, the conducting sums
-    # as multiply-adds by 0 / 1): the arithmetic must be the same to the last bit
-    a4 = run_emul(emul, lat, m, n, w, 1e-13, 200000, cfg=5)
-    assert (a4["Gtop"], a4["Gbot"], a4["iter"], a4["err"]) == (got["Gtop"], got["Gbot"], got["iter"], got["err"])
     # the reference's own defaults (tol 1e-8, itmax 2500, Sq/bondc.f:545): same iteration count, same G to 1e-6
     ref8 = O.conduct_cg(m, n, b1, b2, w)
     got8 = run_emul(emul, lat, m, n, w, 1e-8, 2500, cfg=cfg)
@@ -104,4 +101,54 @@ def test_emulated_fused_full_lattice_closed_form(emul, O):
     m, n = 272, 67
     b1, b2 = O.bondlist(O.SQUARE, m, n, 0)
     got = run_emul(emul, O.SQUARE, m, n, np.ones(len(b1)), 1e-13, 100000)
+    assert abs(got["Gtop"] - m / (n - 1)) < 1e-9 and abs(got["Gbot"] - m / (n - 1)) < 1e-9
+
+
+def run_emul_defl(lib, lat, m, n, w, tol, itmax, Va=1.0, g0=1.0, gleak=1e-12, read_thresh=1e-10, bw=0, bh=0):
+    Gt, Gb, err = C.c_double(), C.c_double(), C.c_double()
+    it, k = C.c_int(), C.c_int()
+    w = np.ascontiguousarray(w, np.float64)
+    rc = lib.fused_emul_solve_defl(C.c_int(lat), C.c_int(m), C.c_int(n), w.ctypes.data_as(C.POINTER(C.c_double)),
+                                   C.c_double(Va), C.c_double(g0), C.c_double(gleak), C.c_double(tol), C.c_int(itmax),
+                                   C.c_double(read_thresh), C.byref(Gt), C.byref(Gb), C.byref(it), C.byref(err), C.byref(k),
+                                   C.c_int(bw), C.c_int(bh))
+    assert rc == 0, rc
+    return {"Gtop": Gt.value, "Gbot": Gb.value, "iter": it.value, "err": err.value, "coarse": k.value}
+
+
+# deflated one-pass solver (FtCfgD; blocks of bw x bh tiles): same G as the oracle's Jacobi-PCG to 1e-9, err is the TRUE
+# relative residual |r| / |D^-1 b| of linbcg's stopping rule, and never more iterations than the plain solver
+DEFL_CASES = [
+    (1, "MIXED", 528, 101, 0.85, 0.72, 1, 1), (1, "BOND", 400, 70, 0.0, 0.56, 1, 1), (1, "SITE", 144, 100, 0.65, 0.0, 1, 2),
+    (1, "MIXED", 48, 40, 0.85, 0.75, 1, 1), (1, "BOND", 16, 130, 0.0, 0.75, 1, 1), (1, "SITE", 256, 33, 0.66, 0.0, 1, 1),
+    (1, "MIXED", 272, 194, 0.85, 0.70, 0, 0), (1, "MIXED", 528, 130, 0.85, 0.72, 2, 1),
+    (2, "BOND", 528, 101, 0.0, 0.40, 1, 1), (2, "SITE", 400, 70, 0.56, 0.0, 1, 1), (2, "MIXED", 144, 100, 0.8, 0.6, 1, 2),
+    (2, "BOND", 48, 40, 0.0, 0.42, 1, 1), (2, "SITE", 16, 130, 0.8, 0.0, 1, 1), (2, "MIXED", 256, 33, 0.85, 0.6, 1, 1),
+    (2, "MIXED", 272, 194, 0.85, 0.58, 0, 0), (2, "SITE", 528, 130, 0.56, 0.0, 2, 1),
+]
+
+
+@pytest.mark.parametrize("lat,kind,m,n,ps,pb,bw,bh", DEFL_CASES)
+def test_emulated_deflated_pcg_matches_oracle(emul, O, lat, kind, m, n, ps, pb, bw, bh):
+    kind = getattr(O, kind)
+    for seed in range(20):
+        case = spanning_case(O, lat, kind, m, n, ps, pb, 7000 + 13 * m + n + seed)
+        if case is not None:
+            break
+    else:
+        pytest.fail("no spanning realization among the seeds")
+    b1, b2, w = case
+    ref = O.conduct_cg(m, n, b1, b2, w, tol=1e-13, itmax=200000)
+    got = run_emul_defl(emul, lat, m, n, w, 1e-13, 200000, bw=bw, bh=bh)
+    assert abs(got["Gtop"] - ref["Gtop"]) <= 1e-9 * abs(ref["Gtop"]), (got, ref["Gtop"])
+    assert abs(got["Gbot"] - ref["Gbot"]) <= 1e-9 * abs(ref["Gbot"]), (got, ref["Gbot"])
+    assert got["err"] <= 1e-13
+    assert got["iter"] <= ref["iter"] + 3, (got["iter"], ref["iter"])
+    print("coarse %d: %d iterations (plain %d)" % (got["coarse"], got["iter"], ref["iter"]))
+
+
+def test_emulated_deflated_full_lattice_closed_form(emul, O):
+    m, n = 272, 67
+    b1, b2 = O.bondlist(O.SQUARE, m, n, 0)
+    got = run_emul_defl(emul, O.SQUARE, m, n, np.ones(len(b1)), 1e-13, 100000, bw=1, bh=1)
     assert abs(got["Gtop"] - m / (n - 1)) < 1e-9 and abs(got["Gbot"] - m / (n - 1)) < 1e-9

@@ -13,7 +13,7 @@ ap.add_argument("--ps", type=float, default=0.80)
 ap.add_argument("--pb", type=float, default=0.70)
 ap.add_argument("--lattice", type=int, default=1)
 ap.add_argument("--converge", action="store_true", help="also run both forms to tol 1e-10")
-ap.add_argument("--configs", action="store_true", help="time every tile configuration of the one-pass kernel (perc_set_solver 10 / 12 / 15)")
+ap.add_argument("--configs", action="store_true", help="time every tile configuration of the one-pass kernel (perc_set_solver 10 / 12 / 14)")
 ap.add_argument("--fused-only", action="store_true", help="skip the two-kernel form (profiling runs)")
 ap.add_argument("--default-only", action="store_true", help="one solve with the default solver (profiling runs)")
 args = ap.parse_args()
@@ -28,9 +28,9 @@ with P.Lattice(args.lattice, args.L, args.L, 0) as L:
         sys.exit("no spanning cluster")
     interior = t - 2 * args.L
     res = {}
-    runs = (("two-kernel", 1), ("one-pass", 0), ("two-kernel", 1), ("one-pass", 0))
+    runs = (("two-kernel", 1), ("one-pass", 2), ("deflated", 0), ("two-kernel", 1), ("one-pass", 2), ("deflated", 0))
     if args.configs:
-        runs = tuple(("one-pass-" + nm, md) for nm, md in (("A", 10), ("A3", 12), ("A4", 15)))
+        runs = tuple(("one-pass-" + nm, md) for nm, md in (("A", 10), ("A3", 12), ("D", 14)))
         runs = (() if args.fused_only else (("two-kernel", 1),)) + runs + (() if args.fused_only else (("two-kernel", 1),) + runs)
     if args.default_only:
         runs = (("one-pass", 0),)
@@ -55,7 +55,7 @@ with P.Lattice(args.lattice, args.L, args.L, 0) as L:
     if args.default_only:
         sys.exit(0)
     if args.configs:
-        names = [n for n in res if n != "two-kernel"]
+        names = [n for n in res if n not in ("two-kernel", "one-pass-D")]
         a = res.get("two-kernel", res[names[0]])
         ok = all(a["iter"] == res[n]["iter"] and abs(a["Gtop"] - res[n]["Gtop"]) <= 1e-9 * abs(a["Gtop"]) for n in names)
         print("FUSED_OK" if ok else "FUSED_MISMATCH", flush=True)
@@ -64,12 +64,17 @@ with P.Lattice(args.lattice, args.L, args.L, 0) as L:
     ok = a["iter"] == b["iter"] and abs(a["Gtop"] - b["Gtop"]) <= 1e-9 * abs(a["Gtop"]) and abs(a["Gbot"] - b["Gbot"]) <= 1e-9 * abs(a["Gbot"])
     ok = ok and abs(a["err"] - b["err"]) <= 1e-6 * abs(a["err"])
     if args.converge:
-        for name, mode in (("two-kernel", 1), ("one-pass", 0)):
-            L.set_solver(mode)
-            t0 = time.perf_counter()
-            r = L.conduct(0, tol=1e-10, itmax=4000000, voltages=False)
-            print("%-10s converged: iters=%d G=%.12e err=%.3e  %.2f s" % (name, r["iter"], r["Gtop"], r["err"], time.perf_counter() - t0), flush=True)
-            res[name + "-c"] = r
+        for name, mode in (("deflated", 0), ("one-pass", 2), ("two-kernel", 1)):
+            for tol in ((1e-10, 1e-13) if name != "two-kernel" else (1e-10,)):
+                L.set_solver(mode)
+                t0 = time.perf_counter()
+                r = L.conduct(0, tol=tol, itmax=4000000, voltages=False)
+                print("%-10s converged (tol %.0e): iters=%d Gtop=%.13e Gbot=%.13e err=%.3e  %.2f s  %.4f ms/iter" % (name, tol, r["iter"], r["Gtop"], r["Gbot"], r["err"], time.perf_counter() - t0, L.phase_ms()[6]), flush=True)
+                res[name + "-c%.0e" % tol] = r
+        res["two-kernel-c"] = res["two-kernel-c1e-10"]; res["one-pass-c"] = res["one-pass-c1e-10"]
+        d13, p13 = res["deflated-c1e-13"], res["one-pass-c1e-13"]
+        print("deflated vs one-pass at tol 1e-13: relG = %.2e ; iterations %d vs %d (x%.2f)" % (abs(d13["Gtop"] - p13["Gtop"]) / p13["Gtop"], d13["iter"], p13["iter"], p13["iter"] / d13["iter"]), flush=True)
+        ok = ok and abs(d13["Gtop"] - p13["Gtop"]) <= 1e-9 * p13["Gtop"]
         a, b = res["two-kernel-c"], res["one-pass-c"]
         ok = ok and abs(a["Gtop"] - b["Gtop"]) <= 1e-8 * abs(a["Gtop"]) and abs(a["iter"] - b["iter"]) <= max(3, a["iter"] // 100)
     print("FUSED_OK" if ok else "FUSED_MISMATCH", flush=True)
