@@ -234,4 +234,81 @@ PERC_HD unsigned neighbour_bits(const Geom& g, int x, int y)
     return b;
 }
 
+
+// ---- diagonal of the conductance matrix, bit for bit as the reference forms it -------------------------------------
+// G(i,i) = -rowsum with rowsum accumulated over j = 1 .. t in ASCENDING j (Sq/bondc.f:499-505): the order of the additions
+// is the order of the neighbours' site numbers.  On this matrix the last bit matters: a diagonal that differs from the
+// reference's by one rounding (e.g. the correctly rounded nc*g0 + nl*gleak) is an inconsistent perturbation of relative
+// size 1e-16, which the smallest eigenvalue of the cluster (1e-8 .. 1e-9 after Jacobi scaling at L = 1024 .. 4096)
+// amplifies to 1e-9 .. 1e-8 in the voltages -- above the 1e-9 the conductance has to agree to.
+// Directions in ascending neighbour number for a site away from the periodic seam:
+//   square S W E N;  triangular, x even (up-type) S W E NW N NE;  x odd (down-type) SW S SE W E N.
+// At the seam (pbc) the wrapped neighbours move: W of x = 0 lies at +m-1 (after E), E of x = m-1 at -(m-1) (before W),
+// NW of x = 0 at +2m-1 (after NE), SE of x = m-1 at -(2m-1) (before SW).
+PERC_HD double diag_seq(const Geom& g, unsigned cf, unsigned ex, int x, double g0, double gleak)
+{
+    // weight of the bond in direction `bit`, +0.0 if the neighbour does not exist (d + 0.0 == d: a missing neighbour
+    // leaves the running sum as the reference's loop over G(i,j) = 0 does)
+#define PERC_W(bit) ((ex & (bit)) ? ((cf & (bit)) ? g0 : gleak) : 0.0)
+    const bool tri = g.lattice == LAT_TRIANGULAR;
+    if (!(g.pbc && (x == 0 || x == g.m - 1))) {
+        if (!tri) return ((PERC_W(NB_S) + PERC_W(NB_W)) + PERC_W(NB_E)) + PERC_W(NB_N);
+        if (!(x & 1)) return ((((PERC_W(NB_S) + PERC_W(NB_W)) + PERC_W(NB_E)) + PERC_W(NB_NW)) + PERC_W(NB_N)) + PERC_W(NB_NE);
+        return ((((PERC_W(NB_SW) + PERC_W(NB_S)) + PERC_W(NB_SE)) + PERC_W(NB_W)) + PERC_W(NB_E)) + PERC_W(NB_N);
+    }
+    // periodic seam: the wrapped neighbours change their place in the order
+    const bool seam0 = x == 0;
+    double d = 0.0;
+    if (tri && (x & 1)) {                                  // x = m - 1 (m even): SE wraps to the front
+        d = ((d + PERC_W(NB_SE)) + PERC_W(NB_SW)) + PERC_W(NB_S);
+        d = ((d + PERC_W(NB_E)) + PERC_W(NB_W)) + PERC_W(NB_N);
+        return d;
+    }
+    d = d + PERC_W(NB_S);
+    if (seam0) d = (d + PERC_W(NB_E)) + PERC_W(NB_W);      // W of x = 0 lies at +m-1
+    else d = (d + PERC_W(NB_E)) + PERC_W(NB_W);            // E of x = m-1 lies at -(m-1), before W at -1
+    if (tri) d = ((d + PERC_W(NB_N)) + PERC_W(NB_NE)) + PERC_W(NB_NW);   // x = 0 (up-type): NW wraps behind NE
+    else d = d + PERC_W(NB_N);
+    return d;
+#undef PERC_W
+}
+// The same ordered sum together with its rounding residue rho = d - (exact sum of the weights), recovered exactly by
+// error-free additions (Knuth's TwoSum; no multiplications, so no contraction can disturb it).  The reference's matrix is
+// the exact-row-sum Laplacian plus diag(rho): the deflated solver needs rho wherever it multiplies the matrix with a
+// block-constant vector analytically (pcg_fused_tile.cuh).
+PERC_HD double diag_seq_rho(const Geom& g, unsigned cf, unsigned ex, int x, double g0, double gleak, double* rho)
+{
+    double d = 0.0, err = 0.0;
+    // d += w with the rounding error of the addition added to err (w = +0.0 for a missing neighbour: no error)
+#define PERC_ADD(bit) { const double w_ = (ex & (bit)) ? ((cf & (bit)) ? g0 : gleak) : 0.0; const double t_ = d + w_, bb_ = t_ - d; \
+                        err += (d - (t_ - bb_)) + (w_ - bb_); d = t_; }
+    const bool tri = g.lattice == LAT_TRIANGULAR;
+    if (!(g.pbc && (x == 0 || x == g.m - 1))) {
+        if (!tri) { PERC_ADD(NB_S) PERC_ADD(NB_W) PERC_ADD(NB_E) PERC_ADD(NB_N) }
+        else if (!(x & 1)) { PERC_ADD(NB_S) PERC_ADD(NB_W) PERC_ADD(NB_E) PERC_ADD(NB_NW) PERC_ADD(NB_N) PERC_ADD(NB_NE) }
+        else { PERC_ADD(NB_SW) PERC_ADD(NB_S) PERC_ADD(NB_SE) PERC_ADD(NB_W) PERC_ADD(NB_E) PERC_ADD(NB_N) }
+    } else if (tri && (x & 1)) {
+        PERC_ADD(NB_SE) PERC_ADD(NB_SW) PERC_ADD(NB_S) PERC_ADD(NB_E) PERC_ADD(NB_W) PERC_ADD(NB_N)
+    } else {
+        PERC_ADD(NB_S) PERC_ADD(NB_E) PERC_ADD(NB_W)
+        if (tri) { PERC_ADD(NB_N) PERC_ADD(NB_NE) PERC_ADD(NB_NW) } else { PERC_ADD(NB_N) }
+    }
+#undef PERC_ADD
+    *rho = -err;
+    return d;
+}
+
+// right-hand side of a site of row n-2: Itemp = sum over its bonds into the top row of w Va, in bond-list order =
+// ascending neighbour number NW, N, NE (Sq/bondc.f:490-497; the seam moves NW of x = 0 behind NE)
+PERC_HD double rhs_seq(const Geom& g, unsigned cf, unsigned ex, int x, double g0, double gleak, double Va)
+{
+    const bool seam0 = g.pbc && x == 0;
+    double b = 0.0;
+    if (!seam0 && (ex & NB_NW)) b = b + ((cf & NB_NW) ? g0 : gleak) * Va;
+    if (ex & NB_N) b = b + ((cf & NB_N) ? g0 : gleak) * Va;
+    if (ex & NB_NE) b = b + ((cf & NB_NE) ? g0 : gleak) * Va;
+    if (seam0 && (ex & NB_NW)) b = b + ((cf & NB_NW) ? g0 : gleak) * Va;
+    return b;
+}
+
 }  // namespace perc

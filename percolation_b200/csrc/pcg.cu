@@ -39,10 +39,10 @@ struct PcgParams {
     double g0, gleak, Va, read_thresh;
 };
 
-__device__ __forceinline__ double diag_of(unsigned cf, unsigned ex, double g0, double gleak)
+// diagonal of site (x, .): the reference's G(i,i) = -rowsum, summed in ascending neighbour number (geometry.cuh: diag_seq)
+__device__ __forceinline__ double diag_of(const Geom& g, unsigned cf, unsigned ex, int x, double g0, double gleak)
 {
-    int nc = __popc(cf & ex), ne = __popc(ex);
-    return (double)nc * g0 + (double)(ne - nc) * gleak;
+    return diag_seq(g, cf & ex, ex, x, g0, gleak);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -148,11 +148,9 @@ pcg_init_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
         double b = 0.0;
         if (g.y0 + y == g.ng - 2 && solve_row(g, y)) {
             unsigned ex = neighbour_bits(g, x, y), cf = cfull[i];
-            // bonds into the top row: N, NW, NE
-            if (ex & NB_N)  b += ((cf & NB_N)  ? prm.g0 : prm.gleak) * prm.Va;
-            if (ex & NB_NW) b += ((cf & NB_NW) ? prm.g0 : prm.gleak) * prm.Va;
-            if (ex & NB_NE) b += ((cf & NB_NE) ? prm.g0 : prm.gleak) * prm.Va;
-            double d = diag_of(cf, ex, prm.g0, prm.gleak);
+            // bonds into the top row, summed in the reference's order (geometry.cuh: rhs_seq)
+            b = rhs_seq(g, cf, ex, x, prm.g0, prm.gleak, prm.Va);
+            double d = diag_of(g, cf, ex, x, prm.g0, prm.gleak);
             double z = b / d;
             s_b += z * z;
             if (!warm) { s_rz += b * z; s_rr += b * b; }
@@ -165,7 +163,7 @@ pcg_init_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, double
                 const unsigned ex = neighbour_bits(g, x, y), cf = cfull[i];
                 const int xl = x > 0 ? x - 1 : g.m - 1, xr = x + 1 < g.m ? x + 1 : 0;
                 const int64_t row = i - x;
-                const double d = diag_of(cf, ex, prm.g0, prm.gleak);
+                const double d = diag_of(g, cf, ex, x, prm.g0, prm.gleak);
                 double acc = d * vx[i];
 #define NB(bit, j) if (ex & bit) acc -= ((cf & bit) ? prm.g0 : prm.gleak) * vx[j];
                 NB(NB_E, row + xr) NB(NB_W, row + xl) NB(NB_N, i + g.m) NB(NB_S, i - g.m)
@@ -218,7 +216,7 @@ pcg_spmv_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, const 
         if (gx >= 0 && gx < g.m && gy >= 1 && gy < g.n - 1) {
             int64_t j = (int64_t)gy * g.m + gx;
             unsigned ex = neighbour_bits(g, gx, gy), cf = cfull[j];
-            double d = diag_of(cf, ex, prm.g0, prm.gleak);
+            double d = diag_of(g, cf, ex, gx, prm.g0, prm.gleak);
             v = vr[j] / d + bk * vp_old[j];      // p is double-buffered: neighbours' tiles write vp
         }
         pn[k] = v;
@@ -238,7 +236,7 @@ pcg_spmv_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, const 
         NB(NB_E, 1) NB(NB_W, -1) NB(NB_N, SP_HX) NB(NB_S, -SP_HX)
         if (LAT == LAT_TRIANGULAR) { NB(NB_NW, SP_HX - 1) NB(NB_NE, SP_HX + 1) NB(NB_SW, -SP_HX - 1) NB(NB_SE, -SP_HX + 1) }
 #undef NB
-        double qv = diag_of(cf, ex, prm.g0, prm.gleak) * pc - acc;
+        double qv = diag_of(g, cf, ex, gx, prm.g0, prm.gleak) * pc - acc;
         vp[i] = pc;
         vq[i] = qv;
         dot += pc * qv;
@@ -273,7 +271,7 @@ pcg_update_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, doub
         double r = vr[i] - ak * q;
         vx[i] += ak * p;
         vr[i] = r;
-        double d = diag_of(cfull[i], neighbour_bits(g, x, y), prm.g0, prm.gleak);
+        double d = diag_of(g, cfull[i], neighbour_bits(g, x, y), x, prm.g0, prm.gleak);
         s_rz += r * (r / d);
         s_rr += r * r;
     }
@@ -332,15 +330,7 @@ constexpr int PT_VEC_BYTES = (PT_ROWS * PT_LD * 8 + 127) / 128 * 128;      // on
 constexpr int PT_CF_BYTES = (PT_ROWS * PT_CLD + 127) / 128 * 128;
 constexpr int PT_STAGE_BYTES = 2 * PT_VEC_BYTES + PT_CF_BYTES;
 // (d, 1/d) table, one private copy per lane (entry [idx][lane]): a lookup is conflict-free whatever the indices
-constexpr size_t PT_SMEM = 2 * (size_t)PT_STAGE_BYTES + sizeof(double2) * 64 * 32 + sizeof(double) * 32 + 16;
-
-// diagonal of a site with nc conducting and nl leaking bonds; int -> double by the 2^52 trick (no I2F)
-__device__ __forceinline__ double pt_diag(int nc, int nl, const PcgParams& prm)
-{
-    const double two52 = 4503599627370496.0;
-    const double dc = __hiloint2double(0x43300000, nc) - two52, dl = __hiloint2double(0x43300000, nl) - two52;
-    return __fma_rn(dl, prm.gleak, __dmul_rn(dc, prm.g0));
-}
+constexpr size_t PT_SMEM = 2 * (size_t)PT_STAGE_BYTES + sizeof(double2) * 64 * 32 + sizeof(double) * (32 + 4 + 64) + 16;
 
 struct PtStage { double* sp; double* sr; uint8_t* scf; };
 
@@ -450,10 +440,18 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
     double2* dtab = reinterpret_cast<double2*>(pt_raw + 2 * (size_t)PT_STAGE_BYTES);    // [64][32] (d, 1/d)
     double* sh = reinterpret_cast<double*>(dtab + 64 * 32);
     const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6, lane = tid & 31;
-    for (int k = tid; k < 64 * 32; k += PT_THREADS) {
-        const double d = pt_diag((k >> 5) >> 3, (k >> 5) & 7, prm);
-        dtab[k] = make_double2(d, d > 0.0 ? 1.0 / d : 0.0);
+    // (d, 1/d) of the sites with all their neighbours, by conduct pattern (pcg_fused_tile.cuh: ft_pat; 16 x 32 private
+    // copies on the square lattice, 128 x 16 on the triangular one); every other site sums its diagonal in place (pt_dsite)
+    for (int k = tid; k < ft_tab_slots<LAT, FtCfgA3>(); k += PT_THREADS) {
+        const FtDiag e = ft_tab_slot<LAT, FtCfgA3>(g, k, prm.g0, prm.gleak);
+        dtab[k] = make_double2(e.d, e.inv);
     }
+    double* cinv = sh + 36;                                                             // [64] 1/d by bond counts (any positive scaling serves as the Jacobi preconditioner)
+    if (tid >= PT_THREADS - 64) cinv[tid - (PT_THREADS - 64)] = ft_cinv_entry(tid - (PT_THREADS - 64), prm.g0, prm.gleak);
+    auto pt_dsite = [&](unsigned cf, unsigned ex, int gx_) {
+        const FtDiag e = ft_diag_site(g, cf, ex, gx_, prm.g0, prm.gleak, cinv);
+        return make_double2(e.d, e.inv);
+    };
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sh + 32);          // one mbarrier per stage
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -462,7 +460,6 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
     }
     __syncthreads();
     const double bk = st->bk, ak = st->ak;          // slab mode: set by pcg_post_kernel after the all-reduce
-    const double dg = prm.g0 - prm.gleak;
     // MODE 0 sweeps the tiles from the END of the lattice to its start, MODE 1 front to back: each
     // kernel starts on the data the previous one touched last (still resident in the 126 MB L2)
     auto tile_of = [&](int t) { return MODE == 0 ? ntiles - 1 - t : t; };
@@ -500,9 +497,9 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
                         const unsigned c01 = *reinterpret_cast<const unsigned short*>(&s.scf[pr * PT_CLD + 16 + cx]);
                         const unsigned e0 = interior ? e0i : neighbour_bits(g, gxc, gy);
                         const unsigned e1 = interior ? e1i : neighbour_bits(g, gxc + 1, gy);
-                        const int n0 = __popc(c01 & 0xffu), n1 = __popc(c01 >> 8);
-                        v.x = r2.x * dtab[(((n0 << 3) | (__popc(e0) - n0)) << 5) + lane].y + bk * p2.x;
-                        v.y = r2.y * dtab[(((n1 << 3) | (__popc(e1) - n1)) << 5) + lane].y + bk * p2.y;
+                        const unsigned f0 = c01 & 0xffu, f1 = c01 >> 8;
+                        v.x = r2.x * ((interior || e0 == e0i) ? dtab[FtCfgA3::tabp(LAT, ft_pat<LAT>(f0, 0), lane)] : pt_dsite(f0, e0, gxc)).y + bk * p2.x;
+                        v.y = r2.y * ((interior || e1 == e1i) ? dtab[FtCfgA3::tabp(LAT, ft_pat<LAT>(f1, 1), lane)] : pt_dsite(f1, e1, gxc + 1)).y + bk * p2.y;
                     }
                     st2(&s.sp[pr * PT_LD + 2 + cx], v);
                     // slab mode: the halo copies of p are advanced here (pointwise recurrence) and stored for MODE 1
@@ -519,8 +516,7 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
                 if (pt_p_row<DIST>(g, gy) && hx >= 0 && hx < g.m) {
                     const unsigned cf = s.scf[pr * PT_CLD + (side ? 16 + xe : 15)];
                     const unsigned ex = neighbour_bits(g, hx, gy);
-                    const int nc = __popc(cf);
-                    v = s.sr[pr * PT_LD + col] * dtab[(((nc << 3) | (__popc(ex) - nc)) << 5) + lane].y + bk * s.sp[pr * PT_LD + col];
+                    v = s.sr[pr * PT_LD + col] * pt_dsite(cf, ex, hx).y + bk * s.sp[pr * PT_LD + col];
                 }
                 s.sp[pr * PT_LD + col] = v;
             }
@@ -576,7 +572,7 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
                                 if (e0 & NB_NE) { all += dNE * dNE; padd(con, dNE * dNE, cf0 & NB_NE); }
                             }
                         }
-                        acc0 += prm.gleak * all + dg * con;
+                        acc0 += prm.g0 * con + prm.gleak * (all - con);
                     }
                     if (valid) st2(vp_out + (int64_t)gy * g.m + gx, cc);
                 } else {
@@ -604,11 +600,11 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
                     padd(con0, c[PT_LD - 1], cf0 & NB_NW); padd(con0, up.y, cf0 & NB_NE);
                     padd(con1, dn.x, cf1 & NB_SW);         padd(con1, drt, cf1 & NB_SE);
                 }
-                const int n0 = __popc(cf0), n1 = __popc(cf1), l0 = __popc(e0) - n0, l1 = __popc(e1) - n1;
-                const double2 t0 = dtab[(((n0 << 3) | l0) << 5) + lane], t1 = dtab[(((n1 << 3) | l1) << 5) + lane];
+                const double2 t0 = (interior || e0 == interior_ex<LAT>(gx)) ? dtab[FtCfgA3::tabp(LAT, ft_pat<LAT>(cf0, 0), lane)] : pt_dsite(cf0, e0, gx);
+                const double2 t1 = (interior || e1 == interior_ex<LAT>(gx + 1)) ? dtab[FtCfgA3::tabp(LAT, ft_pat<LAT>(cf1, 1), lane)] : pt_dsite(cf1, e1, gx + 1);
                 double2 q;
-                q.x = t0.x * cc.x - (prm.gleak * all0 + dg * con0);
-                q.y = t1.x * cc.y - (prm.gleak * all1 + dg * con1);
+                q.x = t0.x * cc.x - (prm.g0 * con0 + prm.gleak * (all0 - con0));
+                q.y = t1.x * cc.y - (prm.g0 * con1 + prm.gleak * (all1 - con1));
                 if (valid) {
                     const int64_t i = (int64_t)gy * g.m + gx;
                     double2 r = ld2(&s.sr[(ly + 1) * PT_LD + 2 + 2 * tx]);
@@ -714,12 +710,14 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
     FtDiag* dtab = reinterpret_cast<FtDiag*>(ft_raw + 2 * (size_t)C::STAGE_BYTES + C::U_BYTES);      // [64][DC]
     double* sh = reinterpret_cast<double*>(dtab + 64 * C::DC);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sh + 96);                      // one mbarrier per stage
-    double* sft = reinterpret_cast<double*>(bars + 2);                                              // [2][RR * 4] shift tables (deflation)
+    double* cinv = reinterpret_cast<double*>(bars + 2);                                             // [64] 1/d by bond counts (boundary tiles)
+    double* sft = cinv + 64;                                                                        // [2][RR * 4] shift tables (deflation)
     double* sfl = sft + 2 * C::RR * 4;                                                              // [32][8] crossing currents per warp and slot
-    double* sf = sfl + 256;                                                                          // [FT_KMAX] mu of every block during the sweep, Z^T A u' in the coarse stage
+    double* sru = sfl + 256;                                                                         // [2][32] sum rho u' per warp (two tiles in flight)
+    double* sf = sru + 64;                                                                           // [FT_KMAX] mu of every block during the sweep, Z^T A u' in the coarse stage
     int* sterm = reinterpret_cast<int*>(sf + FT_KMAX);                                              // [256] term lists of this CTA's blocks (padded form)
+    double* rtab = reinterpret_cast<double*>(sterm + 256);                                          // rounding residue of the diagonal per table slot
     const int tid = threadIdx.x;
-    for (int k = tid; k < 64 * C::DC; k += C::THREADS) dtab[k] = ft_diag_entry(k / C::DC, prm.g0, prm.gleak);
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -738,10 +736,20 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         tma_box_g2s(stage_s(k), &tm_s, x0 - 2, y0, &bars[k]);
         tma_box_g2s(stage_cf(k), &tm_cf, x0 - 16, y0 - 1, &bars[k]);
     };
-    // shift table of tile (ix, iy) into buffer b, by the threads t0, t0 + nt, ...
-    auto fill_shift = [&](int b, int ix, int iy, int t0, int nt) {
-        for (int j = t0; j < C::RR * 4; j += nt)
-            if ((j & 3) != 3) sft[b * C::RR * 4 + j] = ft_defl_shift_entry<C>(g, dd.D, sf, ix, iy, j >> 2, j & 3);
+    // shift table of tile (ix, iy) into buffer b, by ONE warp (lane l): the nine mu of the 3 x 3 blocks around the tile
+    // first, then the entry of every staged row and block column (0 on rows that are not unknowns)
+    auto fill_shift = [&](int b, int ix, int iy, int l) {
+        double* m9 = sfl + 240;                                  // scratch behind the per-warp currents ([30][8] used)
+        if (l < 9) {
+            const int tx = ix + l % 3 - 1, ty = iy + l / 3 - 1;
+            m9[l] = (tx >= 0 && tx < dd.D.ntx && ty >= 0 && ty < dd.D.nty) ? sf[ft_defl_block(dd.D, tx, ty)] : 0.0;
+        }
+        __syncwarp();
+        for (int j = l; j < C::RR * 4; j += 32) {
+            const int pr = j >> 2, cls = j & 3, gy = iy * C::TY - 1 + pr;
+            if (cls != 3) sft[b * C::RR * 4 + j] = (gy >= 1 && gy <= g.n - 2) ? m9[(pr == 0 ? 0 : (pr > C::TY ? 2 : 1)) * 3 + cls] : 0.0;
+        }
+        __syncwarp();
     };
 
     // tile coordinates advance incrementally (a CTA's tiles are gridDim.x apart: no division per tile)
@@ -752,8 +760,11 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
     };
     int t = blockIdx.x;
     int ix = 0, iy = 0;                                          // tile t
-    if (t < ntiles) { const int tl = tile_of(t); ix = tl % ntx; iy = tl / ntx; }
+    if (t < ntiles) { const int tl = tile_of(t); ix = tl % ntx; iy = tl / ntx; issue(0, ix * C::TX, iy * C::TY); }   // (thread 0: it made the mbarriers)
+    for (int k = tid; k < ft_tab_slots<LAT, C>(); k += C::THREADS) dtab[k] = ft_tab_slot<LAT, C>(g, k, prm.g0, prm.gleak);
+    if (tid >= C::THREADS - 64) cinv[tid - (C::THREADS - 64)] = ft_cinv_entry(tid - (C::THREADS - 64), prm.g0, prm.gleak);
     if (C::DEFL) {
+        for (int k = tid; k < ft_tab_slots<LAT, C>(); k += C::THREADS) rtab[k] = ft_rho_slot<LAT, C>(g, k, prm.g0, prm.gleak);
         // mu of every block (8 KB) stays in shared memory for the sweep; the static term lists of the blocks whose
         // Z^T A u' this CTA assembles in the coarse stage (block blockIdx.x + j gridDim.x) are fetched now, off the critical path
         for (int B = tid; B < dd.D.k; B += C::THREADS) sf[B] = dd.mu[B];
@@ -762,10 +773,9 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
             sterm[tid] = B < dd.D.k ? dd.tent[B * dd.tw + (tid & (dd.tw - 1))] : -1;
         }
         __syncthreads();
-        if (t < ntiles) fill_shift(0, ix, iy, tid, C::THREADS);
+        if (t < ntiles && tid < 32) fill_shift(0, ix, iy, tid);
     }
     __syncthreads();
-    if (t < ntiles) issue(0, ix * C::TX, iy * C::TY);
     int nx = ix, ny = iy;                                        // tile t + gridDim.x
     advance(nx, ny);
     double rz = 0.0, rr = 0.0, en = 0.0;
@@ -779,13 +789,18 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         const double* sftk = C::DEFL ? sft + (k & 1) * C::RR * 4 : nullptr;
         const bool interior = ft_interior<C>(g, x0, y0);
         if (!C::USTATE) {
-            ft_phase_u<LAT, C>(g, sr, scf, su, dtab, x0, y0, interior, tid);
+            ft_phase_u<LAT, C>(g, sr, scf, su, dtab, x0, y0, interior, tid, prm.g0, prm.gleak, cinv);
             __syncthreads();
         }
         const double* uu = C::USTATE ? sr : su;                 // V = 3: the staged vector IS u
         if (C::V == 1) { rz = 0.0; rr = 0.0; en = 0.0; }
-        ft_phase_main<LAT, C>(g, sc, sr, ss, scf, uu, dtab, x0, y0, interior, tid, r_out, s_out, xrow, prow, rz, rr, sftk);
-        ft_phase_ringcols<LAT, C>(g, sc, sr, ss, scf, uu, dtab, x0, y0, tid, sftk);
+        double ru = 0.0;                                        // sum rho u' over this tile's sites (deflation)
+        ft_phase_main<LAT, C>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, interior, tid, r_out, s_out, xrow, prow, rz, rr, sftk, rtab, &ru);
+        ft_phase_ringcols<LAT, C>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, tid, sftk, interior, rtab);
+        if (C::DEFL) {
+            for (int o = 16; o; o >>= 1) ru += __shfl_down_sync(0xffffffffu, ru, o);
+            if ((tid & 31) == 0) sru[(k & 1) * 32 + (tid >> 5)] = ru;
+        }
         __syncthreads();
         ft_phase_energy<LAT, C>(g, sc, ss, scf, x0, y0, interior, tid, en);
         constexpr int FLUX_WARPS = (FtFluxItems<C>::N + 31) / 32, FLUX_LOW = (C::TY + C::TX + 31) / 32;
@@ -794,10 +809,10 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         const int fw = (LAT == LAT_TRIANGULAR || y0 <= 1 || y0 + C::TY >= g.n - 2) ? FLUX_WARPS : FLUX_LOW;
         if (C::DEFL && tid < fw * 32) {
             // currents through the bonds that cross the tile's borders: one work item per thread, summed per slot and warp
-            double f[FS_SLOTS] = {0.0, 0.0, 0.0, 0.0, 0.0};
-            ft_phase_flux<LAT, C>(g, sc, ss, scf, x0, y0, tid, f);
+            double f[FS_SLOTS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            ft_phase_flux<LAT, C>(g, sc, ss, scf, x0, y0, tid, f, interior);
 #pragma unroll
-            for (int q = 0; q < FS_SLOTS; ++q) {
+            for (int q = 0; q < FS_R; ++q) {
                 if (LAT == LAT_SQUARE && (q == FS_W || q == FS_NW)) continue;
                 for (int o = 16; o; o >>= 1) f[q] += __shfl_down_sync(0xffffffffu, f[q], o);
                 if ((tid & 31) == 0) sfl[(tid >> 5) * 8 + q] = f[q];
@@ -805,7 +820,7 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         }
         // meanwhile the first ring warp prepares the next tile's shift table (the other buffer: its readers finished with the
         // last tile's barriers, its next readers come after this tile's)
-        if (C::DEFL && tid >= C::RING_T0 && tid < C::RING_T0 + 32 && t + G < ntiles) fill_shift((k + 1) & 1, nx, ny, tid - C::RING_T0, 32);
+        if (C::DEFL && tid >= C::RING_T0 && tid < C::RING_T0 + 32 && t + G < ntiles) fill_shift((k + 1) & 1, nx, ny, tid - C::RING_T0);
         // generic-proxy accesses to this stage are ordered before the bulk copies that will refill it
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (C::V == 1) {
@@ -817,15 +832,15 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         } else {
             __syncthreads();                                    // every thread is done with the stage
         }
-        if (C::DEFL && tid >= C::RING_T0 + 32) {
-            // the second ring warp folds the per-warp currents (lane <-> warp, fixed shuffle tree) and stores the tile's slots
-            const int l = tid - C::RING_T0 - 32;
+        if (C::DEFL && tid >= C::RING_T0 + (C::RING_NT > 32 ? 32 : 0)) {
+            // the last ring warp folds the per-warp currents (lane <-> warp, fixed shuffle tree) and stores the tile's slots
+            const int l = tid - C::RING_T0 - (C::RING_NT > 32 ? 32 : 0);
             double* Ft = dd.F + (size_t)(iy * ntx + ix) * FS_STRIDE;
 #pragma unroll
             for (int q = 0; q < FS_SLOTS; ++q) {
                 double v = 0.0;
                 if (!(LAT == LAT_SQUARE && (q == FS_W || q == FS_NW))) {
-                    v = l < fw ? sfl[l * 8 + q] : 0.0;
+                    v = q == FS_R ? (l < C::THREADS / 32 ? sru[(k & 1) * 32 + l] : 0.0) : (l < fw ? sfl[l * 8 + q] : 0.0);
                     for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
                 }
                 if (l == 0) Ft[q] = v;
@@ -879,22 +894,32 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         // (2) every CTA reads the whole vector (8 KB) and forms its rows of mu' = E^-1 (Z^T A u')
         for (int B = tid; B < kk; B += C::THREADS) sf[B] = __ldcg(&dd.fglob[B]);
         __syncthreads();
-        double mf = 0.0;
-        for (int j = blockIdx.x + G * w; j < kk; j += G * nw) {
+        // unit (row r of this CTA, quarter q of the row): 8 independent loads per lane, one L2 latency per unit; the four
+        // quarter sums of a row are folded in fixed order afterwards
+        const int nrows = (kk - (int)blockIdx.x + G - 1) / G;               // rows blockIdx.x + r G < kk
+        const int qlen = ((kk + 3) / 4 + 31) / 32 * 32;
+        double* part = sfl;                                                  // [nrows][4] (nrows * 4 <= 240: checked on the host)
+        for (int u = w; u < nrows * 4; u += nw) {
+            const int r = u >> 2, q = u & 3, j = (int)blockIdx.x + r * G;
             const double* row = dd.Einv + (size_t)j * kk;
             double a = 0.0;
 #pragma unroll 8
-            for (int i = lane; i < kk; i += 32) a += row[i] * sf[i];
+            for (int i = q * qlen + lane; i < (q + 1) * qlen && i < kk; i += 32) a += row[i] * sf[i];
             for (int o = 16; o; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
-            if (lane == 0) { dd.mu[j] = a; mf += a * sf[j]; }
+            if (lane == 0) part[u] = a;
         }
         __syncthreads();
-        if (lane == 0) sh[w] = mf;
-        __syncthreads();
-        if (tid == 0) {
-            double a = 0.0;
-            for (int q = 0; q < nw; ++q) a += sh[q];
-            partial[blockIdx.x * NQ + 3] = a;
+        double mf = 0.0;
+        if (tid < nrows) {
+            const int j = (int)blockIdx.x + tid * G;
+            const double a = (part[tid * 4] + part[tid * 4 + 1]) + (part[tid * 4 + 2] + part[tid * 4 + 3]);
+            dd.mu[j] = a;
+            mf = a * sf[j];
+        }
+        if (w == 0) {
+            for (int o = 16; o; o >>= 1) mf += __shfl_down_sync(0xffffffffu, mf, o);
+            if (nrows > 32) mf = nan("");                                    // (never: nrows * 4 <= 240 on the host)
+            if (lane == 0) partial[blockIdx.x * NQ + 3] = mf;
         }
     }
     if (last_block(&st->ticket_a)) {
@@ -924,8 +949,17 @@ defl_weights_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, in
     __shared__ double sw[2][8];
     const int tl = blockIdx.x, x0 = (tl % ntx) * C::TX, y0 = (tl / ntx) * C::TY;
     const FtGlobalAcc a{cfull, g.m};
-    double f[FS_SLOTS] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    double f[FS_SLOTS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (int q = threadIdx.x; q < FtFluxItems<C>::N; q += 64) ft_flux_item<LAT, C, true>(g, prm.g0, prm.gleak, a, x0, y0, q, f);
+    // ... and the sum of the diagonal's rounding residues over the tile's unknown sites (the matrix is the exact-row-sum
+    // Laplacian + diag(rho): E gets sum rho on its diagonal)
+    for (int q = threadIdx.x; q < C::TX * C::TY; q += 64) {
+        const int gx = x0 + q % C::TX, gy = y0 + q / C::TX;
+        if (gx >= g.m || gy < 1 || gy > g.n - 2) continue;
+        double rho;
+        diag_seq_rho(g, a.cf(gx, gy), neighbour_bits(g, gx, gy), gx, prm.g0, prm.gleak, &rho);
+        f[FS_R] += rho;
+    }
 #pragma unroll
     for (int q = 0; q < FS_SLOTS; ++q) {
         for (int o = 16; o; o >>= 1) f[q] += __shfl_down_sync(0xffffffffu, f[q], o);
@@ -950,11 +984,7 @@ defl_nu_kernel(Geom g, PcgParams prm, FtDefl D, const uint8_t* __restrict__ cful
             const int xa = bx * D.bw * C::TX, xb = (bx + 1) * D.bw * C::TX < g.m ? (bx + 1) * D.bw * C::TX : g.m;
             for (int x = xa; x < xb; ++x) {
                 const unsigned ex = neighbour_bits(g, x, g.n - 2), cf = cfull[(int64_t)(g.n - 2) * g.m + x];
-                double b = 0.0;
-                if (ex & NB_N)  b += ((cf & NB_N)  ? prm.g0 : prm.gleak) * prm.Va;
-                if (ex & NB_NW) b += ((cf & NB_NW) ? prm.g0 : prm.gleak) * prm.Va;
-                if (ex & NB_NE) b += ((cf & NB_NE) ? prm.g0 : prm.gleak) * prm.Va;
-                acc += b;
+                acc += rhs_seq(g, cf, ex, x, prm.g0, prm.gleak, prm.Va);
             }
         }
         fb[B] = acc;
@@ -1017,7 +1047,7 @@ pcg_readout_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, con
             int64_t i = (int64_t)y * g.m + x;
             unsigned ex = neighbour_bits(g, x, y), cf = cfull[i];
             double vi = e == 0 ? 0.0 : prm.Va;
-            double acc = diag_of(cf, ex, prm.g0, prm.gleak) * vi;
+            double acc = diag_of(g, cf, ex, x, prm.g0, prm.gleak) * vi;
             int xl = x > 0 ? x - 1 : g.m - 1, xr = x + 1 < g.m ? x + 1 : 0;
             int64_t row = i - x;
 #define VAL(j) (g.y0 + (j) / g.m == 0 ? 0.0 : (g.y0 + (j) / g.m == g.ng - 1 ? prm.Va : vx[j]))
@@ -1076,10 +1106,6 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
     uint8_t* scf = reinterpret_cast<uint8_t*>(tab + 64);
     const int tid = threadIdx.x;
     const uint8_t* cfg = cfbatch + (size_t)blockIdx.x * t;
-    if (tid < 64) {
-        const double d = (double)(tid >> 3) * prm.g0 + (double)(tid & 7) * prm.gleak;
-        tab[tid] = make_double2(d, d > 0.0 ? 1.0 / d : 0.0);
-    }
     bool any = false;
     for (int i = tid; i < t; i += SM_THREADS) { uint8_t c = cfg[i]; scf[i] = c; any |= c != 0; }
     const int K = (t + SM_THREADS - 1) / SM_THREADS;
@@ -1095,11 +1121,8 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
         double b = 0.0;
         if (y == g.n - 2 && y >= 1) {
             const unsigned ex = neighbour_bits(g, x, y), cf = scf[i];
-            if (ex & NB_N)  b += ((cf & NB_N)  ? prm.g0 : prm.gleak) * prm.Va;
-            if (ex & NB_NW) b += ((cf & NB_NW) ? prm.g0 : prm.gleak) * prm.Va;
-            if (ex & NB_NE) b += ((cf & NB_NE) ? prm.g0 : prm.gleak) * prm.Va;
-            const int nc = __popc(cf);
-            const double z = b * tab[(nc << 3) | (__popc(ex) - nc)].y;
+            b = rhs_seq(g, cf, ex, x, prm.g0, prm.gleak, prm.Va);
+            const double z = b / diag_seq(g, cf & ex, ex, x, prm.g0, prm.gleak);
             s0 += z * z; s1 += b * z; s2 += b * b;
         }
         sr[i] = b; sp[i] = 0.0;
@@ -1110,7 +1133,6 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
     (void)s2;
     for (int i = tid; i < 2 * m; i += SM_THREADS) sx[i] = 0.0;
     int iter = 0;
-    const double dg = prm.g0 - prm.gleak;
     for (;;) {
         // p = r / d + bk p  (interior rows)
         for (int i = tid; i < t; i += SM_THREADS) {
@@ -1118,8 +1140,7 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
             if (y < 1 || y >= g.n - 1) continue;
             const int x = i - y * m;
             const unsigned ex = neighbour_bits(g, x, y), cf = scf[i];
-            const int nc = __popc(cf);
-            sp[i] = sr[i] * tab[(nc << 3) | (__popc(ex) - nc)].y + bk * sp[i];
+            sp[i] = sr[i] / diag_seq(g, cf & ex, ex, x, prm.g0, prm.gleak) + bk * sp[i];
         }
         __syncthreads();
         // q = A p, p.q
@@ -1139,9 +1160,8 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
             NBR(NB_E, row + xr) NBR(NB_W, row + xl) NBR(NB_N, i + m) NBR(NB_S, i - m)
             if (LAT == LAT_TRIANGULAR) { NBR(NB_NW, row + m + xl) NBR(NB_NE, row + m + xr) NBR(NB_SW, row - m + xl) NBR(NB_SE, row - m + xr) }
 #undef NBR
-            const int nc = __popc(cf);
             const double pc = sp[i];
-            q[k] = tab[(nc << 3) | (__popc(ex) - nc)].x * pc - (prm.gleak * all + dg * con);
+            q[k] = diag_seq(g, cf & ex, ex, x, prm.g0, prm.gleak) * pc - (prm.g0 * con + prm.gleak * (all - con));
             dot += pc * q[k];
         }
         const double akden = sm_block_sum(dot, sh);
@@ -1156,12 +1176,11 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
             if (y < 1 || y >= g.n - 1) continue;
             const int x = i - y * m;
             const unsigned ex = neighbour_bits(g, x, y), cf = scf[i];
-            const int nc = __popc(cf);
             const double r = sr[i] - ak * q[k];
             sr[i] = r;
             if (y == 1) sx[x] += ak * sp[i];
             if (y == g.n - 2) sx[m + x] += ak * sp[i];         // (n = 3: row 1 is both; the read-out uses sx[x])
-            rz += r * r * tab[(nc << 3) | (__popc(ex) - nc)].y;
+            rz += r * r / diag_seq(g, cf & ex, ex, x, prm.g0, prm.gleak);
             rr += r * r;
         }
         const double2 fs = sm_block_sum2(rz, rr, sh);
@@ -1180,7 +1199,7 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
             const int i = y * m + x, row = i - x;
             const unsigned ex = neighbour_bits(g, x, y), cf = scf[i];
             const double vi = e == 0 ? 0.0 : prm.Va;
-            double acc = diag_of(cf, ex, prm.g0, prm.gleak) * vi;
+            double acc = diag_of(g, cf, ex, x, prm.g0, prm.gleak) * vi;
             const int xl = x > 0 ? x - 1 : m - 1, xr = x + 1 < m ? x + 1 : 0;
 #define VAL(j) ((j) / m == 0 ? 0.0 : ((j) / m == g.n - 1 ? prm.Va : ((j) / m == 1 ? sx[(j) - m] : sx[m + (j) - (g.n - 2) * m])))
 #define NB(bit, j) if (ex & bit) { double w = (cf & bit) ? prm.g0 : prm.gleak; if (fabs(w) >= prm.read_thresh) acc -= w * VAL(j); }
@@ -1288,7 +1307,7 @@ pcg_scale_u_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfull, dou
     const double r = vr[i];
     if (r == 0.0) return;
     const int x = (int)(i % g.m), y = (int)(i / g.m);
-    vr[i] = r / diag_of(cfull[i], neighbour_bits(g, x, y), prm.g0, prm.gleak);
+    vr[i] = r / diag_of(g, cfull[i], neighbour_bits(g, x, y), x, prm.g0, prm.gleak);
 }
 
 // deflation set-up of a solve: E = Z^T A Z from the conduct bytes (weights kernel -> host: banded Cholesky, dense
@@ -1386,6 +1405,7 @@ static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
         dd.tptr = c->d_defl_terms; dd.tent = c->d_defl_terms + FT_KMAX + 1; dd.tw = c->defl_tw;
         dd.fglob = dd.mu + FT_KMAX;                      // (nu is dead once defl_init_kernel has run)
         if (dd.tw > 0 && ((dd.D.k + grid - 1) / grid) * dd.tw > 256) dd.tw = 0;     // more blocks per CTA than the staged lists hold
+        if ((dd.D.k + grid - 1) / grid > 32) return (int)cudaErrorInvalidConfiguration;   // (k <= 1024 and grid >= 32 SMs)
         c->defl_k = dd.D.k;
     }
     int cur = 0, pass = 0;

@@ -27,7 +27,7 @@ inline int ft_defl_build_einv(const FtDefl& D, const double* W, double* Einv, in
     for (int iy = 0; iy < D.nty; ++iy)
         for (int ix = 0; ix < D.ntx; ++ix) {
             const int tl = iy * D.ntx + ix, B = ft_defl_block(D, ix, iy);
-            at(B, B) += W[(size_t)tl * FS_STRIDE + FS_D];
+            at(B, B) += W[(size_t)tl * FS_STRIDE + FS_D] + W[(size_t)tl * FS_STRIDE + FS_R];
             for (int s = 0; s < 4; ++s) {
                 const int jx = ix + dx[s], jy = iy + dy[s];
                 if (jx < 0 || jx >= D.ntx || jy >= D.nty) continue;

@@ -38,12 +38,14 @@ constexpr int FT_KMAX = 1024;                              // largest coarse (de
 template <int TY_, int RPT_, int DC_, int CTAS_, int V_>
 struct FtCfg {
     static constexpr int TX = 128, TY = TY_, RPT = RPT_, DC = DC_, CTAS = CTAS_, V = V_;   // CTAS: resident CTAs per SM
+    static constexpr int NPAT_SQ = 16, NPAT_TRI = 128;      // conduct patterns of a site with all its neighbours (ft_pat)
     static constexpr int NG = (TY + 1) / RPT;               // row groups
     static_assert(NG * RPT == TY + 1, "compute rows (tile + north ring row) must split evenly");
     static constexpr int MAIN_THREADS = 64 * NG;            // 2 columns per thread
     static constexpr int CR = TY + 1;                       // compute rows: gy = y0 + lr, lr = 0 .. TY (last = north ring)
     static constexpr int RING_T0 = V == 1 ? 0 : MAIN_THREADS;    // first thread that works on the ring columns
-    static constexpr int RING_NT = V == 1 ? 2 * CR : 64;         // ... and how many of them share the 2 CR ring sites
+    static constexpr int RING_NT = V == 1 ? 2 * CR : (V >= 5 ? 32 : 64);   // ... and how many of them share the 2 CR ring sites (deflated: ONE ring
+                                                                           // warp, 736 threads, so that a thread may hold 88 registers)
     static constexpr int THREADS = V == 1 ? MAIN_THREADS : MAIN_THREADS + RING_NT;
     static constexpr int RR = TY + 3;                       // staged rows of r, conduct bytes, u: gy = y0 - 1 + pr
     static constexpr int SR = TY + 1;                       // staged rows of s:                   gy = y0 + ps
@@ -58,12 +60,13 @@ struct FtCfg {
     static constexpr bool DEFL = V >= 5;                    // deflated iteration (block-constant coarse space, see FtDefl)
     static constexpr int U_BYTES = USTATE ? 0 : R_BYTES;    // shared u array of phase U
     static constexpr int SHIFT_BYTES = DEFL ? 2 * RR * 4 * 8 : 0;         // per staged row: mu of the west / own / east block (two tiles in flight)
-    static constexpr int COARSE_BYTES = DEFL ? FT_KMAX * 8 + 256 * 8 + 256 * 4 : 0; // mu / Z^T A u' of every block, crossing currents per warp and slot, term lists
-    static constexpr int SMEM = 2 * STAGE_BYTES + U_BYTES + TAB_BYTES + 96 * 8 + 16 + SHIFT_BYTES + COARSE_BYTES;
-    // table of diagonals: entry (#conducting bonds << 3 | #leaking bonds), DC private copies
-    static PERC_HD int tab(int nc, int nl, int lane) { return ((nc << 3) | nl) * DC + (lane & (DC - 1)); }
-    // ... of a site with all its DEG neighbours (fast path): nl = DEG - nc, (nc << 3 | DEG - nc) = 7 nc + DEG
-    static PERC_HD int tab_full(int nc, int deg, int lane) { return nc * (7 * DC) + (deg * DC + (lane & (DC - 1))); }
+    static constexpr int RHO_BYTES = DEFL ? NPAT_TRI * (DC / 2) * 8 : 0;                 // rho per table slot
+    static constexpr int COARSE_BYTES = DEFL ? FT_KMAX * 8 + 256 * 8 + 64 * 8 + 256 * 4 + RHO_BYTES : 0; // mu / Z^T A u' of every block, crossing currents per warp and slot, term lists
+    static constexpr int SMEM = 2 * STAGE_BYTES + U_BYTES + TAB_BYTES + 96 * 8 + 16 + 64 * 8 + SHIFT_BYTES + COARSE_BYTES;
+    // table of diagonals of the sites with ALL their neighbours, indexed by which of them conduct (ft_pat: 16 patterns on
+    // the square lattice, 2 x 64 on the triangular one) -- the diagonal depends on the pattern, not only on the counts: it is
+    // the reference's sum in ascending neighbour order (diag_seq).  Private copies per lane: 32 (square) / 16 (triangular).
+    static PERC_HD int tabp(int lat, int pat, int lane) { return lat == LAT_SQUARE ? pat * DC + (lane & (DC - 1)) : pat * (DC / 2) + (lane & (DC / 2 - 1)); }
 };
 
 typedef FtCfg<32, 3, 32, 1, 1> FtCfgA;      // 704 threads
@@ -103,12 +106,55 @@ template <int LAT> PERC_HD unsigned ft_interior_ex(int gx)
     if (LAT == LAT_SQUARE) return NB_E | NB_N | NB_W | NB_S;
     return (gx & 1) ? (NB_E | NB_N | NB_W | NB_S | NB_SW | NB_SE) : (NB_E | NB_N | NB_W | NB_S | NB_NW | NB_NE);
 }
-// table of diagonals indexed by (#conducting bonds << 3 | #leaking bonds), DC private copies (FtCfg::tab)
-PERC_HD FtDiag ft_diag_entry(int idx, double g0, double gleak)
+// pattern of a site's conducting bonds as a table index; parity = x & 1 (triangular: up- / down-type site)
+template <int LAT> PERC_HD int ft_pat(unsigned cf, int parity)
+{
+    if (LAT == LAT_SQUARE) return (int)((cf & 3u) | ((cf >> 2) & 12u));                 // E N W S
+    return parity ? 64 + (int)((cf & 3u) | ((cf >> 2) & 60u)) : (int)(cf & 63u);        // E N NW NE W S  /  E N W S SW SE
+}
+// ... and back: conduct bits of table entry `pat`
+template <int LAT> PERC_HD unsigned ft_pat_bits(int pat)
+{
+    if (LAT == LAT_SQUARE) return (unsigned)((pat & 3) | ((pat & 12) << 2));
+    return pat >= 64 ? (unsigned)(((pat - 64) & 3) | (((pat - 64) & 60) << 2)) : (unsigned)pat;
+}
+// table entry: diagonal of an interior site with conduct pattern `pat`, summed as the reference sums it, and its reciprocal
+template <int LAT> PERC_HD FtDiag ft_diag_entry(const Geom& g, int pat, double g0, double gleak)
+{
+    const int parity = LAT == LAT_TRIANGULAR && pat >= 64;
+    FtDiag e;
+    e.d = diag_seq(g, ft_pat_bits<LAT>(pat), ft_interior_ex<LAT>(parity), 2 + parity, g0, gleak);
+    e.inv = e.d > 0.0 ? 1.0 / e.d : 0.0;
+    return e;
+}
+// slot k of the shared-memory table (all private copies of an entry are adjacent)
+template <int LAT, class C> PERC_HD int ft_tab_slots() { return LAT == LAT_SQUARE ? C::NPAT_SQ * C::DC : C::NPAT_TRI * (C::DC / 2); }
+template <int LAT, class C> PERC_HD FtDiag ft_tab_slot(const Geom& g, int k, double g0, double gleak)
+{
+    return ft_diag_entry<LAT>(g, LAT == LAT_SQUARE ? k / C::DC : k / (C::DC / 2), g0, gleak);
+}
+// ... and the rounding residue rho of the same entry (deflation)
+template <int LAT, class C> PERC_HD double ft_rho_slot(const Geom& g, int k, double g0, double gleak)
+{
+    const int pat = LAT == LAT_SQUARE ? k / C::DC : k / (C::DC / 2), parity = LAT == LAT_TRIANGULAR && pat >= 64;
+    double rho;
+    diag_seq_rho(g, ft_pat_bits<LAT>(pat), ft_interior_ex<LAT>(parity), 2 + parity, g0, gleak, &rho);
+    return rho;
+}
+// diagonal of ANY site (boundary tiles): the same ordered sum over the neighbours that exist
+// The reciprocal (the Jacobi scaling: any positive number close to 1/d serves, it does not enter the matrix) comes from a
+// small table by bond counts, cinv[(#conducting << 3) | #leaking] (ft_cinv_entry), instead of a division per site.
+PERC_HD double ft_cinv_entry(int idx, double g0, double gleak)
+{
+    const double d = fma((double)(idx & 7), gleak, (double)(idx >> 3) * g0);
+    return d > 0.0 ? 1.0 / d : 0.0;
+}
+PERC_HD FtDiag ft_diag_site(const Geom& g, unsigned cf, unsigned ex, int gx, double g0, double gleak, const double* cinv)
 {
     FtDiag e;
-    e.d = fma((double)(idx & 7), gleak, (double)(idx >> 3) * g0);     // same rounding as the two-kernel path (pt_diag)
-    e.inv = e.d > 0.0 ? 1.0 / e.d : 0.0;
+    e.d = diag_seq(g, cf, ex, gx, g0, gleak);
+    const int nc = ft_popc(cf & ex);
+    e.inv = cinv[(nc << 3) | (ft_popc(ex) - nc)];
     return e;
 }
 // every site the tile touches (2-site halo) is an unknown with its full neighbourhood, or lies on a Dirichlet
@@ -125,17 +171,23 @@ PERC_HD bool ft_interior(const Geom& g, int x0, int y0)
 // (a weighted 5-point / 7-point graph Laplacian of the blocks; its dense inverse, <= FT_KMAX^2 doubles, lives in L2),
 //     x0 = Z E^-1 Z^T b,   every search direction  p = u - Z mu + beta p  with  E mu = Z^T A u   (=> Z^T A p = 0),
 //     s = A p = A (u - Z mu) + beta s,   p.A p = u.A u - mu.Z^T A u - beta gamma / alpha.
-// The sweep is the same 33 B per site: u is shifted by the mu of its block on its way into the stencil (the shift table
-// of a tile: one value per staged row and west / own / east block column), and Z^T A u' -- the net current leaving each
-// block -- comes from the bonds that CROSS tile borders, which the two ring warps sum per tile while the others do the
-// bond energies (five slots per tile: into the tile to the east / north / west / north-west, and into the Dirichlet rows).
+// The sweep is the same 33 B per site.  A Z mu is applied ANALYTICALLY: the matrix is the exact-row-sum Laplacian plus the
+// rounding residue rho of its diagonal (diag_seq_rho), so (A Z mu)_i = rho_i mu_i + sum_j w_ij (mu_i - mu_j), and the sum
+// has terms only where a bond crosses a block border or ends on a Dirichlet row (the shift table of a tile: mu per staged
+// row and west / own / east block column).  Shifting u by mu on its way into the stencil instead would evaluate large
+// cancelling sums: every site of one conduct pattern in a block would commit the SAME rounding error, a block-coherent
+// residual that the deflated iteration cannot remove and the cluster's small eigenvalues amplify (2e-10 in G at L = 512,
+// 2e-8 at L = 4096).  Z^T A u' -- the net current leaving each block -- comes from the bonds that CROSS tile borders
+// (slots per tile: into the tile to the east / north / west / north-west, into the Dirichlet rows) plus sum rho_i u'_i.
 struct FtDefl {
     int bw, bh;        // tiles per block
     int nbx, nby;      // blocks per lattice row / column
     int ntx, nty;      // tiles per lattice row / column
     int k;             // nbx * nby <= FT_KMAX
 };
-enum : int { FS_E = 0, FS_N = 1, FS_W = 2, FS_NW = 3, FS_D = 4, FS_SLOTS = 5, FS_STRIDE = 8 };
+// FS_R: sum over the tile's unknown sites of rho_i u'_i (rho: rounding residue of the matrix diagonal, diag_seq_rho) -- the part of
+// Z^T A u' that is not a current between blocks; in the weight pass (UNIT) the sum of rho_i itself: the entry it adds to E
+enum : int { FS_E = 0, FS_N = 1, FS_W = 2, FS_NW = 3, FS_D = 4, FS_R = 5, FS_SLOTS = 6, FS_STRIDE = 8 };
 
 // blocks start at about TX x TX sites and grow (the shorter side first) until the coarse dimension fits
 PERC_HD FtDefl ft_defl_make(const Geom& g, int TX, int TY, int kmax, int bw0 = 0, int bh0 = 0)
@@ -183,6 +235,7 @@ PERC_HD double ft_defl_assemble(const FtDefl& D, const double* F, int B)
         for (int ix = bx * D.bw; ix < (bx + 1) * D.bw && ix < D.ntx; ++ix) {
             const int tl = iy * D.ntx + ix;
             acc += FT_LDCG(&F[tl * FS_STRIDE + FS_D]);
+            acc += FT_LDCG(&F[tl * FS_STRIDE + FS_R]);
             for (int s = 0; s < 4; ++s) {
                 int jx = ix + dx[s], jy = iy + dy[s];                 // current leaving through slot s
                 if (jx >= 0 && jx < D.ntx && jy < D.nty && ft_defl_block(D, jx, jy) != B) acc += FT_LDCG(&F[tl * FS_STRIDE + s]);
@@ -199,10 +252,30 @@ PERC_HD double ft_defl_assemble(const FtDefl& D, const double* F, int B)
 // (the bond weights themselves: the entries of E).  A: accessor with cf(gx, gy) and u(gx, gy).
 template <class C> struct FtFluxItems { static constexpr int N = 2 * C::TY + 3 * C::TX; };
 template <int LAT, class C, bool UNIT, class A>
-PERC_HD void ft_flux_item(const Geom& g, double g0, double gleak, const A& a, int x0, int y0, int q, double* f)
+PERC_HD void ft_flux_item(const Geom& g, double g0, double gleak, const A& a, int x0, int y0, int q, double* f, bool interior = false)
 {
 #define FT_W(cf, bit) (((cf) & (bit)) ? g0 : gleak)
 #define FT_UNK(gy) ((gy) >= 1 && (gy) <= g.n - 2)
+    if (interior && !UNIT) {
+        // tile without lattice borders (ft_interior): every bond exists, every row is an unknown, no Dirichlet items
+        if (q < C::TY) {
+            const int gy = y0 + q, gx = x0 + C::TX - 1;
+            f[FS_E] += FT_W(a.cf(gx, gy), NB_E) * (a.u(gx, gy) - a.u(gx + 1, gy));
+        } else if (q < C::TY + C::TX) {
+            const int gx = x0 + q - C::TY, gy = y0 + C::TY - 1;
+            const unsigned cf = a.cf(gx, gy);
+            const double ui = a.u(gx, gy);
+            f[FS_N] += FT_W(cf, NB_N) * (ui - a.u(gx, gy + 1));
+            if (LAT == LAT_TRIANGULAR && !(gx & 1)) {
+                f[FS_N] += FT_W(cf, NB_NE) * (ui - a.u(gx + 1, gy + 1));
+                f[q == C::TY ? FS_NW : FS_N] += FT_W(cf, NB_NW) * (ui - a.u(gx - 1, gy + 1));
+            }
+        } else if (LAT == LAT_TRIANGULAR && q < 2 * C::TY + C::TX - 1) {
+            const int gx = x0, gy = y0 + q - C::TY - C::TX;
+            f[FS_W] += FT_W(a.cf(gx, gy), NB_NW) * (a.u(gx, gy) - a.u(gx - 1, gy + 1));
+        }
+        return;
+    }
     if (q < C::TY) {
         const int gy = y0 + q, gx = x0 + C::TX - 1;
         if (gx + 1 < g.m && FT_UNK(gy)) f[FS_E] += FT_W(a.cf(gx, gy), NB_E) * (UNIT ? 1.0 : a.u(gx, gy) - a.u(gx + 1, gy));
@@ -269,11 +342,12 @@ struct FtGlobalAcc {
 
 // crossing currents of a tile: thread tid < FtFluxItems::N takes work item tid, partial sums into f[FS_SLOTS]
 template <int LAT, class C>
-PERC_HD void ft_phase_flux(const Geom& g, const FtScalars& sc, const double* ss, const uint8_t* scf, int x0, int y0, int tid, double* f)
+PERC_HD void ft_phase_flux(const Geom& g, const FtScalars& sc, const double* ss, const uint8_t* scf, int x0, int y0, int tid, double* f,
+                           bool interior = false)
 {
     if (tid >= FtFluxItems<C>::N) return;
     const FtStageAcc<C> a{ss, scf, x0, y0};
-    ft_flux_item<LAT, C, false>(g, sc.g0, sc.gleak, a, x0, y0, tid, f);
+    ft_flux_item<LAT, C, false>(g, sc.g0, sc.gleak, a, x0, y0, tid, f, interior);
 }
 
 // The terms of Z^T (A u') of every block as a static list (CSR over the blocks: ptr[k + 1], ent[]): entry = (tile * FS_STRIDE
@@ -291,6 +365,7 @@ inline void ft_defl_terms(const FtDefl& D, Vec& ptr, Vec& ent)
             for (int ix = bx * D.bw; ix < (bx + 1) * D.bw && ix < D.ntx; ++ix) {
                 const int tl = iy * D.ntx + ix;
                 ent.push_back((tl * FS_STRIDE + FS_D) << 1);
+                ent.push_back((tl * FS_STRIDE + FS_R) << 1);
                 for (int s = 0; s < 4; ++s) {
                     int jx = ix + dx[s], jy = iy + dy[s];
                     if (jx >= 0 && jx < D.ntx && jy < D.nty && ft_defl_block(D, jx, jy) != B) ent.push_back((tl * FS_STRIDE + s) << 1);
@@ -310,17 +385,19 @@ PERC_HD double ft_defl_u0(const Geom& g, const FtDefl& D, unsigned cf, const dou
 {
     const unsigned ex = neighbour_bits(g, x, y);
     cf &= ex;
-    const int nc = ft_popc(cf), nl = ft_popc(ex) - nc;
-    const double d = fma((double)nl, gleak, (double)nc * g0);
+    double rho;
+    const double d = diag_seq_rho(g, cf, ex, x, g0, gleak, &rho);
     const double ni = nu[ft_defl_block(D, x / C::TX, y / C::TY)];
     const unsigned bits[8] = {NB_E, NB_N, NB_NW, NB_NE, NB_W, NB_S, NB_SW, NB_SE};
     const int ddx[8] = {1, 0, -1, 1, -1, 0, -1, 1}, ddy[8] = {0, 1, 1, 1, 0, -1, -1, -1};
-    double b = 0.0, acc = 0.0;
+    const double b = y == g.n - 2 ? rhs_seq(g, cf, ex, x, g0, gleak, Va) : 0.0;
+    // (A Z nu)_i = rho_i nu_i + sum_j w_ij (nu_i - nu_j): its block sums are E nu exactly as E is assembled (weights of the
+    // crossing bonds + sum of rho on the diagonal), so Z^T r0 = 0 holds in the arithmetic the coarse stage works in
+    double acc = rho * ni;
     for (int k = 0; k < 8; ++k) {
         if (!(ex & bits[k])) continue;
         const double w = (cf & bits[k]) ? g0 : gleak;
         const int xx = x + ddx[k], yy = y + ddy[k];
-        if (yy == g.n - 1) b += w * Va;
         if (yy >= 1 && yy <= g.n - 2) acc += w * (ni - nu[ft_defl_block(D, xx / C::TX, yy / C::TY)]);
         else acc += w * ni;
     }
@@ -331,7 +408,7 @@ PERC_HD double ft_defl_u0(const Geom& g, const FtDefl& D, unsigned cf, const dou
 // ---- phase U: u = r / d on the staged box (tile + 2-site halo; rows y0-1 .. y0+TY+1) -------------------------
 template <int LAT, class C>
 PERC_HD void ft_phase_u(const Geom& g, const double* sr, const uint8_t* scf, double* su, const FtDiag* dtab,
-                        int x0, int y0, bool interior, int tid)
+                        int x0, int y0, bool interior, int tid, double g0, double gleak, const double* cinv)
 {
     constexpr int NCP = C::LD / 2, TRIPS = (C::RR * NCP + C::THREADS - 1) / C::THREADS;
     const int lane = tid & 31;
@@ -353,10 +430,9 @@ PERC_HD void ft_phase_u(const Geom& g, const double* sr, const uint8_t* scf, dou
                 e0 = (gx >= 0 && gx < g.m) ? neighbour_bits(g, gx, gy) : 0u;
                 e1 = (gx + 1 >= 0 && gx + 1 < g.m) ? neighbour_bits(g, gx + 1, gy) : 0u;
             }
-            const int n0 = ft_popc(c01 & 0xffu & e0), n1 = ft_popc((c01 >> 8) & e1);
-            constexpr int DEG = LAT == LAT_SQUARE ? 4 : 6;
-            u0 = r2.x * dtab[interior ? C::tab_full(n0, DEG, lane) : C::tab(n0, ft_popc(e0) - n0, lane)].inv;
-            u1 = r2.y * dtab[interior ? C::tab_full(n1, DEG, lane) : C::tab(n1, ft_popc(e1) - n1, lane)].inv;
+            const unsigned f0 = c01 & 0xffu & e0, f1 = (c01 >> 8) & e1;
+            u0 = r2.x * ((interior || e0 == ft_interior_ex<LAT>(gx)) ? dtab[C::tabp(LAT, ft_pat<LAT>(f0, gx & 1), lane)] : ft_diag_site(g, f0, e0, gx, g0, gleak, cinv)).inv;
+            u1 = r2.y * ((interior || e1 == ft_interior_ex<LAT>(gx + 1)) ? dtab[C::tabp(LAT, ft_pat<LAT>(f1, (gx + 1) & 1), lane)] : ft_diag_site(g, f1, e1, gx + 1, g0, gleak, cinv)).inv;
         }
         ft_st2(&su[pr * C::LD + 2 * cp], u0, u1);
     }
@@ -367,43 +443,30 @@ PERC_HD void ft_phase_u(const Geom& g, const double* sr, const uint8_t* scf, dou
 // p / x of the two read-out rows; sums r'.u' and r'.r' over the tile's sites ---------------------------------
 template <int LAT, class C>
 PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr, double* ss, const uint8_t* scf,
-                           const double* su, const FtDiag* dtab, int x0, int y0, bool interior_flag, int tid,
+                           const double* su, const FtDiag* dtab, const double* cinv, int x0, int y0, bool interior_flag, int tid,
                            double* __restrict__ r_out, double* __restrict__ s_out, double* __restrict__ xrow,
-                           double* __restrict__ prow, double& acc_rz, double& acc_rr, const double* sft = nullptr)
+                           double* __restrict__ prow, double& acc_rz, double& acc_rr, const double* sft = nullptr,
+                           const double* rtab = nullptr, double* acc_ru = nullptr)
 {
     if (tid >= C::MAIN_THREADS) return;
     const bool interior = interior_flag;
     const int tx = tid & 63, ty = tid >> 6, lane = tid & 31;
     const int gx = x0 + 2 * tx, lr0 = ty * C::RPT;
-    const double dg = sc.g0 - sc.gleak, alpha = sc.alpha, beta = sc.beta;
+    const double alpha = sc.alpha, beta = sc.beta;
     const double* c = &su[(lr0 + 1) * C::LD + 2 + 2 * tx];
-    // deflation: the stencil sees u - Z mu (dn, cc, up, lf, rt, ... below are the SHIFTED values, c0 / c1 keep the site's
-    // own u for the update); sft[pr * 4 + class]: mu of staged row pr, block column west / own / east.  The first and the
-    // last thread of a tile row look across the tile's west / east border.
+    // deflation: sft[pr * 4 + class] = mu of staged row pr, block column west / own / east (0 on rows that are not
+    // unknowns).  The first and the last thread of a tile row look across the tile's west / east border.
     const int selL = tx == 0 ? 0 : 1, selR = tx == 63 ? 2 : 1;
     ft_d2 dn = ft_ld2(c - C::LD), cc = ft_ld2(c);
     double drt = c[-C::LD + 2];                              // row below, x+2: SE neighbour of the odd column
-    double c0 = cc.x, c1 = cc.y;
-    if (C::DEFL) {
-        const double md = sft[lr0 * 4 + 1], mc = sft[(lr0 + 1) * 4 + 1];
-        dn.x -= md; dn.y -= md; cc.x -= mc; cc.y -= mc;
-        drt -= sft[lr0 * 4 + selR];
-    }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int j = 0; j < C::RPT; ++j, c += C::LD) {
         const int lr = lr0 + j, gy = y0 + lr;
-        ft_d2 up = ft_ld2(c + C::LD);
-        double lf = c[-1], rt = c[2];
-        const double u0 = up.x, u1 = up.y;
-        double nw = LAT == LAT_TRIANGULAR ? c[C::LD - 1] : 0.0;
-        if (C::DEFL) {
-            const double mu_up = sft[(lr + 2) * 4 + 1];
-            up.x -= mu_up; up.y -= mu_up;
-            lf -= sft[(lr + 1) * 4 + selL]; rt -= sft[(lr + 1) * 4 + selR];
-            if (LAT == LAT_TRIANGULAR) nw -= sft[(lr + 2) * 4 + selL];
-        }
+        const ft_d2 up = ft_ld2(c + C::LD);
+        const double lf = c[-1], rt = c[2];
+        const double nw = LAT == LAT_TRIANGULAR ? c[C::LD - 1] : 0.0;
         const bool valid = interior || (gy >= 1 && gy <= g.n - 2 && gx < g.m);
         const unsigned c01 = *reinterpret_cast<const unsigned short*>(&scf[(lr + 1) * C::CLD + 16 + 2 * tx]);
         unsigned cf0 = c01 & 0xffu, cf1 = c01 >> 8;
@@ -432,18 +495,46 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
             ft_padd(con0, nw, cf0 & NB_NW); ft_padd(con0, up.y, cf0 & NB_NE);
             ft_padd(con1, dn.x, cf1 & NB_SW);         ft_padd(con1, drt, cf1 & NB_SE);
         }
-        const int n0 = ft_popc(cf0), n1 = ft_popc(cf1);
-        constexpr int DEG = LAT == LAT_SQUARE ? 4 : 6;
-        const FtDiag t0 = dtab[interior ? C::tab_full(n0, DEG, lane) : C::tab(n0, ft_popc(e0) - n0, lane)];
-        const FtDiag t1 = dtab[interior ? C::tab_full(n1, DEG, lane) : C::tab(n1, ft_popc(e1) - n1, lane)];
-        const double w0 = t0.d * cc.x - (sc.gleak * all0 + dg * con0);
-        const double w1 = t1.d * cc.y - (sc.gleak * all1 + dg * con1);
+        // (gx is even: the thread's first column is an up-type site on the triangular lattice, its second a down-type one)
+        const int i0 = C::tabp(LAT, ft_pat<LAT>(cf0, 0), lane), i1 = C::tabp(LAT, ft_pat<LAT>(cf1, 1), lane);
+        // (boundary tiles: only the sites ON the lattice border lack neighbours; every other site is in the table as well)
+        const bool full0 = interior || e0 == ft_interior_ex<LAT>(gx), full1 = interior || e1 == ft_interior_ex<LAT>(gx + 1);
+        const FtDiag t0 = full0 ? dtab[i0] : ft_diag_site(g, cf0, e0, gx, sc.g0, sc.gleak, cinv);
+        const FtDiag t1 = full1 ? dtab[i1] : ft_diag_site(g, cf1, e1, gx + 1, sc.g0, sc.gleak, cinv);
+        // off-diagonal part with the weights g0 and gleak THEMSELVES (g0 con + gleak (all - con)): a rounded g0 - gleak would be
+        // a bond weight the diagonal does not contain
+        double w0 = t0.d * cc.x - (sc.g0 * con0 + sc.gleak * (all0 - con0));
+        double w1 = t1.d * cc.y - (sc.g0 * con1 + sc.gleak * (all1 - con1));
+        double mc = 0.0, rho0 = 0.0, rho1 = 0.0;
+        if (C::DEFL) {
+            // minus (A Z mu)_i = rho_i mu_i + sum_j w_ij (mu_i - mu_j): the differences vanish unless the bond crosses a block
+            // border or ends on a Dirichlet row (mu = 0 there).  North / south differences are uniform over the warp.
+            mc = sft[(lr + 1) * 4 + 1];
+            const double dN = mc - sft[(lr + 2) * 4 + 1], dS = mc - sft[lr * 4 + 1];
+            const double dW = mc - sft[(lr + 1) * 4 + selL], dE = mc - sft[(lr + 1) * 4 + selR];
+            if (full0) rho0 = rtab[i0]; else diag_seq_rho(g, cf0, e0, gx, sc.g0, sc.gleak, &rho0);
+            if (full1) rho1 = rtab[i1]; else diag_seq_rho(g, cf1, e1, gx + 1, sc.g0, sc.gleak, &rho1);
+#define FT_WB(cf, e, bit) (((e) & (bit)) ? (((cf) & (bit)) ? sc.g0 : sc.gleak) : 0.0)
+            double k0 = rho0 * mc + FT_WB(cf0, e0, NB_W) * dW, k1 = rho1 * mc + FT_WB(cf1, e1, NB_E) * dE;
+            if (dN != 0.0 || dS != 0.0) {
+                k0 += FT_WB(cf0, e0, NB_N) * dN + FT_WB(cf0, e0, NB_S) * dS;
+                k1 += FT_WB(cf1, e1, NB_N) * dN + FT_WB(cf1, e1, NB_S) * dS;
+            }
+            if (LAT == LAT_TRIANGULAR) {
+                // up-type column: NW -> (x-1, y+1), NE -> (x+1, y+1) (the thread's own second column); down-type column:
+                // SW -> (x-1, y-1) (the thread's first column), SE -> (x+1, y-1)
+                k0 += FT_WB(cf0, e0, NB_NW) * (mc - sft[(lr + 2) * 4 + selL]) + FT_WB(cf0, e0, NB_NE) * dN;
+                k1 += FT_WB(cf1, e1, NB_SW) * dS + FT_WB(cf1, e1, NB_SE) * (mc - sft[lr * 4 + selR]);
+            }
+#undef FT_WB
+            w0 -= k0; w1 -= k1;
+        }
         double* sp = &ss[lr * C::LD + 2 + 2 * tx];
         const ft_d2 s2 = ft_ld2(sp), r2 = ft_ld2(&sr[(lr + 1) * C::LD + 2 + 2 * tx]);
         const double sn0 = w0 + beta * s2.x, sn1 = w1 + beta * s2.y;
         double rn0, rn1, un0, un1;
         if (C::USTATE) {                                     // sr / su hold u: u' = u - alpha D^-1 s', r' = d u'
-            un0 = c0 - alpha * (sn0 * t0.inv); un1 = c1 - alpha * (sn1 * t1.inv);
+            un0 = cc.x - alpha * (sn0 * t0.inv); un1 = cc.y - alpha * (sn1 * t1.inv);
             rn0 = t0.d * un0; rn1 = t1.d * un1;
         } else {
             rn0 = r2.x - alpha * sn0; rn1 = r2.y - alpha * sn1;
@@ -456,25 +547,26 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
             if (C::USTATE) ft_st2(r_out + i, un0, un1); else ft_st2(r_out + i, rn0, rn1);
             acc_rz += rn0 * un0 + rn1 * un1;
             acc_rr += rn0 * rn0 + rn1 * rn1;
-            // the rows the read-out consumes: p = u + beta p, x += alpha p
+            if (C::DEFL) *acc_ru += rho0 * un0 + rho1 * un1;
+            // the rows the read-out consumes: p = (u - Z mu) + beta p, x += alpha p
             if (gy == 1 || gy == g.n - 2) {
                 const int64_t o = (gy == 1 ? 0 : g.m) + gx;
                 const ft_d2 p2 = ft_ld2(prow + o), x2 = ft_ld2(xrow + o);
-                const double p0 = cc.x + beta * p2.x, p1 = cc.y + beta * p2.y;
+                const double p0 = (cc.x - mc) + beta * p2.x, p1 = (cc.y - mc) + beta * p2.y;
                 ft_st2(prow + o, p0, p1);
                 ft_st2(xrow + o, x2.x + alpha * p0, x2.y + alpha * p1);
             }
         }
         drt = rt;
         dn = cc; cc = up;
-        c0 = u0; c1 = u1;
     }
 }
 
 // east / west ring columns (gx = x0 - 1 and x0 + TX) of the compute rows: u' only (one thread per site)
 template <int LAT, class C>
 PERC_HD void ft_phase_ringcols(const Geom& g, const FtScalars& sc, const double* sr, double* ss, const uint8_t* scf,
-                               const double* su, const FtDiag* dtab, int x0, int y0, int tid, const double* sft = nullptr)
+                               const double* su, const FtDiag* dtab, const double* cinv, int x0, int y0, int tid, const double* sft = nullptr,
+                               bool interior = false, const double* rtab = nullptr)
 {
     const int lane = tid & 31;
     for (int q = tid - C::RING_T0; q >= 0 && q < 2 * C::CR; q += C::RING_NT) {
@@ -485,17 +577,24 @@ PERC_HD void ft_phase_ringcols(const Geom& g, const FtScalars& sc, const double*
         const unsigned ex = neighbour_bits(g, gx, gy);
         const unsigned cf = scf[(lr + 1) * C::CLD + (side ? 16 + C::TX : 15)] & ex;
         const double* c = &su[(lr + 1) * C::LD + col];
-        double all = 0.0, con = 0.0;
-        // (deflation: every value enters the stencil shifted by the mu of its block, see ft_phase_main)
-#define FT_SH(dc, dr) (C::DEFL ? sft[(lr + 1 + (dr)) * 4 + ft_defl_cls<C>(col + (dc))] : 0.0)
-#define FT_NB(bit, dc, dr) if (ex & bit) { const double v = c[(dr) * C::LD + (dc)] - FT_SH(dc, dr); all += v; if (cf & bit) con += v; }
+        double all = 0.0, con = 0.0, kz = 0.0;
+        // (deflation: minus (A Z mu)_i as in ft_phase_main; mu of a neighbour from the shift table by its row and block column)
+        const double mi = C::DEFL ? sft[(lr + 1) * 4 + ft_defl_cls<C>(col)] : 0.0;
+#define FT_NB(bit, dc, dr) if (ex & bit) { const double v = c[(dr) * C::LD + (dc)]; all += v; if (cf & bit) con += v; \
+                                           if (C::DEFL) kz += ((cf & bit) ? sc.g0 : sc.gleak) * (mi - sft[(lr + 1 + (dr)) * 4 + ft_defl_cls<C>(col + (dc))]); }
         FT_NB(NB_E, 1, 0) FT_NB(NB_W, -1, 0) FT_NB(NB_N, 0, 1) FT_NB(NB_S, 0, -1)
         if (LAT == LAT_TRIANGULAR) { FT_NB(NB_NW, -1, 1) FT_NB(NB_NE, 1, 1) FT_NB(NB_SW, -1, -1) FT_NB(NB_SE, 1, -1) }
 #undef FT_NB
-        const int nc = ft_popc(cf);
-        const FtDiag t = dtab[C::tab(nc, ft_popc(ex) - nc, lane)];
-        const double w = t.d * (c[0] - FT_SH(0, 0)) - (sc.gleak * all + (sc.g0 - sc.gleak) * con);
-#undef FT_SH
+        // (a tile without lattice borders: its ring columns have all their neighbours too -- x0 - 1 is odd, x0 + TX even)
+        const int it = C::tabp(LAT, ft_pat<LAT>(cf, gx & 1), lane);
+        const bool full = interior || ex == ft_interior_ex<LAT>(gx);
+        const FtDiag t = full ? dtab[it] : ft_diag_site(g, cf, ex, gx, sc.g0, sc.gleak, cinv);
+        double w = t.d * c[0] - (sc.g0 * con + sc.gleak * (all - con));
+        if (C::DEFL) {
+            double rho;
+            if (full) rho = rtab[it]; else diag_seq_rho(g, cf, ex, gx, sc.g0, sc.gleak, &rho);
+            w -= rho * mi + kz;
+        }
         const double sn = w + sc.beta * ss[lr * C::LD + col];
         if (C::USTATE) un = c[0] - sc.alpha * (sn * t.inv);
         else un = (sr[(lr + 1) * C::LD + col] - sc.alpha * sn) * t.inv;
@@ -514,7 +613,6 @@ PERC_HD void ft_phase_energy(const Geom& g, const FtScalars& sc, const double* s
     const bool interior = interior_flag;
     const int tx = tid & 63, ty = tid >> 6;
     const int gx = x0 + 2 * tx, lr0 = ty * C::RPT;
-    const double dg = sc.g0 - sc.gleak;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -551,7 +649,7 @@ PERC_HD void ft_phase_energy(const Geom& g, const FtScalars& sc, const double* s
                 if (e0 & NB_NE) { all += dNE * dNE; ft_padd(con, dNE * dNE, cf0 & NB_NE); }
             }
         }
-        acc_e += sc.gleak * all + dg * con;
+        acc_e += sc.g0 * con + sc.gleak * (all - con);
     }
 }
 

@@ -8,6 +8,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include "../percolation_b200/csrc/pcg_fused_tile.cuh"
 #include "../percolation_b200/csrc/pcg_defl_host.h"
@@ -34,8 +37,7 @@ void build_cfull(const Geom& g, const double* w, double gleak, std::vector<uint8
 double diag_of(const Geom& g, const std::vector<uint8_t>& cf, int x, int y, double g0, double gleak)
 {
     const unsigned ex = neighbour_bits(g, x, y), c = cf[(size_t)y * g.m + x] & ex;
-    const int nc = __builtin_popcount(c), ne = __builtin_popcount(ex);
-    return fma((double)(ne - nc), gleak, (double)nc * g0);
+    return diag_seq(g, c, ex, x, g0, gleak);
 }
 
 // "TMA": box of `rows` x `cols` elements at element coordinates (cx, cy) of a row-major m x n array
@@ -62,10 +64,7 @@ int solve(const Geom& g, const std::vector<uint8_t>& cf, double Va, double g0, d
     for (int x = 0; x < m; ++x) {
         const int y = n - 2;
         const unsigned ex = neighbour_bits(g, x, y), c = cf[(size_t)y * m + x];
-        double b = 0.0;
-        if (ex & NB_N)  b += ((c & NB_N)  ? g0 : gleak) * Va;
-        if (ex & NB_NW) b += ((c & NB_NW) ? g0 : gleak) * Va;
-        if (ex & NB_NE) b += ((c & NB_NE) ? g0 : gleak) * Va;
+        const double b = rhs_seq(g, c, ex, x, g0, gleak, Va);
         const double z = b / diag_of(g, cf, x, y, g0, gleak);
         r[0][(size_t)y * m + x] = C::USTATE ? z : b;          // V = 3: the state vector is u = D^-1 r
         bn += z * z;
@@ -74,7 +73,9 @@ int solve(const Geom& g, const std::vector<uint8_t>& cf, double Va, double g0, d
     st.bnrm = sqrt(bn); st.tol = tol; st.itmax = itmax;
 
     std::vector<FtDiag> dtab(64 * C::DC);
-    for (int k = 0; k < 64 * C::DC; ++k) dtab[k] = ft_diag_entry(k / C::DC, g0, gleak);
+    for (int k = 0; k < ft_tab_slots<LAT, C>(); ++k) dtab[k] = ft_tab_slot<LAT, C>(g, k, g0, gleak);
+    std::vector<double> cinv(64);
+    for (int k = 0; k < 64; ++k) cinv[k] = ft_cinv_entry(k, g0, gleak);
     const int ntx = (m + C::TX - 1) / C::TX, nty = (n + C::TY - 1) / C::TY;
     std::vector<double> sr((size_t)C::RR * C::LD), ss((size_t)C::SR * C::LD), su((size_t)C::RR * C::LD);
     std::vector<uint8_t> scf((size_t)C::RR * C::CLD);
@@ -93,12 +94,12 @@ int solve(const Geom& g, const std::vector<uint8_t>& cf, double Va, double g0, d
             const bool interior = ft_interior<C>(g, x0, y0);
             if (prime && interior) ++*tiles_fast;
             if (!C::USTATE)
-                for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_u<LAT, C>(g, sr.data(), scf.data(), su.data(), dtab.data(), x0, y0, interior, tid);
+                for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_u<LAT, C>(g, sr.data(), scf.data(), su.data(), dtab.data(), x0, y0, interior, tid, g0, gleak, cinv.data());
             const double* up = C::USTATE ? sr.data() : su.data();
             for (int tid = C::THREADS - 1; tid >= 0; --tid) {
-                ft_phase_main<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), x0, y0, interior, tid,
+                ft_phase_main<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), cinv.data(), x0, y0, interior, tid,
                                       r[cur ^ 1].data(), s[cur ^ 1].data(), xrow.data(), prow.data(), rz, rr);
-                ft_phase_ringcols<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), x0, y0, tid);
+                ft_phase_ringcols<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), cinv.data(), x0, y0, tid, nullptr, interior);
             }
             for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_energy<LAT, C>(g, sc, ss.data(), scf.data(), x0, y0, interior, tid, en);
         }
@@ -132,7 +133,7 @@ int solve(const Geom& g, const std::vector<uint8_t>& cf, double Va, double g0, d
 // mu = E^-1 ., the scalar recurrences with delta - mu . Z^T A u')
 template <int LAT, class C>
 int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double g0, double gleak, double tol, int itmax,
-               double read_thresh, double* Gtop, double* Gbot, int* iter, double* err, int* coarse_dim, int bw0, int bh0)
+               double read_thresh, double* Gtop, double* Gbot, int* iter, double* err, int* coarse_dim, int bw0, int bh0, double* xfull = nullptr)
 {
     const int m = g.m, n = g.n;
     const int64_t t = g.t;
@@ -145,6 +146,12 @@ int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double 
     for (int tl = 0; tl < ntiles; ++tl)
         for (int q = 0; q < FtFluxItems<C>::N; ++q)
             ft_flux_item<LAT, C, true>(g, g0, gleak, ga, (tl % D.ntx) * C::TX, (tl / D.ntx) * C::TY, q, &W[(size_t)tl * FS_STRIDE]);
+    for (int y = 1; y <= n - 2; ++y)
+        for (int x = 0; x < m; ++x) {
+            double rho;
+            diag_seq_rho(g, cf[(size_t)y * m + x], neighbour_bits(g, x, y), x, g0, gleak, &rho);
+            W[(size_t)((y / C::TY) * D.ntx + x / C::TX) * FS_STRIDE + FS_R] += rho;
+        }
     if (ft_defl_build_einv(D, W.data(), Einv.data(), 2)) return -4;
     std::vector<int> tptr, tent;
     ft_defl_terms(D, tptr, tent);
@@ -171,14 +178,31 @@ int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double 
         }
     FtState st{};
     st.bnrm = sqrt(bn); st.tol = tol; st.itmax = itmax;
+    // (accuracy study: the full iterate x = Z nu + sum alpha p -- the kernel keeps it on two rows only)
+    std::vector<double> pfull;
+    if (xfull) {
+        pfull.assign((size_t)t, 0.0);
+        for (size_t q = 0; q < (size_t)t; ++q) xfull[q] = 0.0;
+        for (int y = 1; y <= n - 2; ++y) for (int x = 0; x < m; ++x) xfull[(size_t)y * m + x] = nu[ft_defl_block(D, x / C::TX, y / C::TY)];
+    }
     std::vector<FtDiag> dtab(64 * C::DC);
-    for (int k = 0; k < 64 * C::DC; ++k) dtab[k] = ft_diag_entry(k / C::DC, g0, gleak);
-    std::vector<double> sr((size_t)C::RR * C::LD), ss((size_t)C::SR * C::LD), sft((size_t)C::RR * 4);
+    for (int k = 0; k < ft_tab_slots<LAT, C>(); ++k) dtab[k] = ft_tab_slot<LAT, C>(g, k, g0, gleak);
+    std::vector<double> cinv(64);
+    for (int k = 0; k < 64; ++k) cinv[k] = ft_cinv_entry(k, g0, gleak);
+    std::vector<double> sr((size_t)C::RR * C::LD), ss((size_t)C::SR * C::LD), sft((size_t)C::RR * 4), rtab((size_t)ft_tab_slots<LAT, C>());
+    for (int k = 0; k < ft_tab_slots<LAT, C>(); ++k) rtab[k] = ft_rho_slot<LAT, C>(g, k, g0, gleak);
     std::vector<uint8_t> scf((size_t)C::RR * C::CLD);
     int cur = 0;
+    double esum = 0.0;
     for (int pass = 0; !st.done; ++pass) {
         const int prime = pass == 0;
         const FtScalars sc{g0, gleak, prime ? 0.0 : st.alpha, prime ? 0.0 : st.beta};
+        if (xfull && !prime)
+            for (int y = 1; y <= n - 2; ++y) for (int x = 0; x < m; ++x) {
+                const size_t q = (size_t)y * m + x;
+                pfull[q] = (r[cur][q] - mu[ft_defl_block(D, x / C::TX, y / C::TY)]) + sc.beta * pfull[q];
+                xfull[q] += sc.alpha * pfull[q];
+            }
         double rz = 0.0, rr = 0.0, en = 0.0;
         for (int tl = 0; tl < ntiles; ++tl) {
             const int ix = tl % D.ntx, iy = tl / D.ntx, x0 = ix * C::TX, y0 = iy * C::TY;
@@ -187,15 +211,16 @@ int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double 
             box_copy(scf.data(), cf.data(), m, n, x0 - 16, y0 - 1, C::CLD, C::RR);
             for (int j = 0; j < C::RR * 4; ++j) sft[j] = (j & 3) == 3 ? NAN : ft_defl_shift_entry<C>(g, D, mu.data(), ix, iy, j >> 2, j & 3);
             const bool interior = ft_interior<C>(g, x0, y0);
+            double ru = 0.0;
             for (int tid = C::THREADS - 1; tid >= 0; --tid) {
-                ft_phase_main<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), sr.data(), dtab.data(), x0, y0, interior, tid,
-                                             r[cur ^ 1].data(), s[cur ^ 1].data(), xrow.data(), prow.data(), rz, rr, sft.data());
-                ft_phase_ringcols<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), sr.data(), dtab.data(), x0, y0, tid, sft.data());
+                ft_phase_main<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), sr.data(), dtab.data(), cinv.data(), x0, y0, interior, tid,
+                                             r[cur ^ 1].data(), s[cur ^ 1].data(), xrow.data(), prow.data(), rz, rr, sft.data(), rtab.data(), &ru);
+                ft_phase_ringcols<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), sr.data(), dtab.data(), cinv.data(), x0, y0, tid, sft.data(), interior, rtab.data());
             }
             for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_energy<LAT, C>(g, sc, ss.data(), scf.data(), x0, y0, interior, tid, en);
             // crossing currents: per ring thread partial sums, folded thread by thread (the kernel: shuffles, then the two warps)
-            double fl[FS_SLOTS] = {0, 0, 0, 0, 0};
-            for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_flux<LAT, C>(g, sc, ss.data(), scf.data(), x0, y0, tid, fl);
+            double fl[FS_SLOTS] = {0, 0, 0, 0, 0, ru};
+            for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_flux<LAT, C>(g, sc, ss.data(), scf.data(), x0, y0, tid, fl, interior);
             for (int k = 0; k < FS_SLOTS; ++k) F[(size_t)tl * FS_STRIDE + k] = fl[k];
         }
         // coarse stage
@@ -209,9 +234,26 @@ int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double 
         }
         double mf = 0.0;
         for (int i = 0; i < D.k; ++i) { double a = 0.0; for (int j = 0; j < D.k; ++j) a += Einv[(size_t)i * D.k + j] * f[j]; mu[i] = a; mf += a * f[i]; }
+        if (!prime) esum += st.alpha * st.gamma;            // the step just applied: |e_k|_A^2 - |e_k+1|_A^2 = alpha_k gamma_k
         ft_scalar_step(st, rz, rr, en - mf, prime);
         cur ^= 1;
         if (pass > 50 * 1000 * 1000) return -1;
+    }
+    if (getenv("EMUL_FINALC")) {
+        // final coarse correction: x += Z E^-1 Z^T r with the recursive residual r = d u
+        std::vector<double> fr((size_t)D.k, 0.0), mr((size_t)D.k, 0.0);
+        for (int y = 1; y <= n - 2; ++y) for (int x = 0; x < m; ++x)
+            fr[ft_defl_block(D, x / C::TX, y / C::TY)] += diag_of(g, cf, x, y, g0, gleak) * r[cur][(size_t)y * m + x];
+        double nf = 0.0;
+        for (int i = 0; i < D.k; ++i) { double a2 = 0.0; for (int j = 0; j < D.k; ++j) a2 += Einv[(size_t)i * D.k + j] * fr[j]; mr[i] = a2; nf += fr[i] * fr[i]; }
+        printf("FINALC |Z^T r| = %.3e  max |mu_r| = %.3e\n", sqrt(nf), *std::max_element(mr.begin(), mr.end()));
+        for (int x = 0; x < m; ++x) { xrow[x] += mr[ft_defl_block(D, x / C::TX, 1 / C::TY)]; xrow[(size_t)m + x] += mr[ft_defl_block(D, x / C::TX, (n - 2) / C::TY)]; }
+        if (xfull) for (int y = 1; y <= n - 2; ++y) for (int x = 0; x < m; ++x) xfull[(size_t)y * m + x] += mr[ft_defl_block(D, x / C::TX, y / C::TY)];
+    }
+    if (getenv("EMUL_ENERGY")) {
+        double nufb = 0.0;
+        for (int i = 0; i < D.k; ++i) nufb += nu[i] * fb[i];
+        printf("ENERGY nu.fb=%.17g esum=%.17g bx=%.17g\n", nufb, esum, nufb + esum);
     }
     double top = 0.0, bot = 0.0;
     for (int e = 0; e < 2; ++e)
@@ -257,12 +299,12 @@ extern "C" int fused_emul_solve(int lattice, int m, int n, const double* w, doub
 // the deflated solver (FtCfgD); bw, bh: tiles per block (0 = the library's choice); coarse_dim: number of blocks
 extern "C" int fused_emul_solve_defl(int lattice, int m, int n, const double* w, double Va, double g0, double gleak,
                                      double tol, int itmax, double read_thresh, double* Gtop, double* Gbot, int* iter,
-                                     double* err, int* coarse_dim, int bw, int bh)
+                                     double* err, int* coarse_dim, int bw, int bh, double* xfull)
 {
     if (m % 16 || n < 4) return -2;
     const Geom g = make_geom(lattice, m, n, 0);
     std::vector<uint8_t> cf;
     build_cfull(g, w, gleak, cf);
-    return lattice == LAT_SQUARE ? solve_defl<LAT_SQUARE, FtCfgD>(g, cf, Va, g0, gleak, tol, itmax, read_thresh, Gtop, Gbot, iter, err, coarse_dim, bw, bh)
-                                 : solve_defl<LAT_TRIANGULAR, FtCfgD>(g, cf, Va, g0, gleak, tol, itmax, read_thresh, Gtop, Gbot, iter, err, coarse_dim, bw, bh);
+    return lattice == LAT_SQUARE ? solve_defl<LAT_SQUARE, FtCfgD>(g, cf, Va, g0, gleak, tol, itmax, read_thresh, Gtop, Gbot, iter, err, coarse_dim, bw, bh, xfull)
+                                 : solve_defl<LAT_TRIANGULAR, FtCfgD>(g, cf, Va, g0, gleak, tol, itmax, read_thresh, Gtop, Gbot, iter, err, coarse_dim, bw, bh, xfull);
 }

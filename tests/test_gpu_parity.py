@@ -501,6 +501,7 @@ def test_batch_conduct_equals_realization_loop(P, lat, kind, m, n, pbc, ps, pb):
         for i in range(nreal):
             L.generate(seed, stream0 + i, ks if kind != 2 else -1, kb if kind != 1 else -1)
             L.label(kind)
+            L.set_solver(2)                         # plain Jacobi-PCG, as the one-CTA batch solver runs it (same iteration counts)
             if len(L.span()[0]):
                 r = L.conduct(0, tol=1e-13, itmax=200000, voltages=False)
                 want.append((r["Gtop"], r["Gbot"], r["iter"]))

@@ -111,7 +111,7 @@ def run_emul_defl(lib, lat, m, n, w, tol, itmax, Va=1.0, g0=1.0, gleak=1e-12, re
     rc = lib.fused_emul_solve_defl(C.c_int(lat), C.c_int(m), C.c_int(n), w.ctypes.data_as(C.POINTER(C.c_double)),
                                    C.c_double(Va), C.c_double(g0), C.c_double(gleak), C.c_double(tol), C.c_int(itmax),
                                    C.c_double(read_thresh), C.byref(Gt), C.byref(Gb), C.byref(it), C.byref(err), C.byref(k),
-                                   C.c_int(bw), C.c_int(bh))
+                                   C.c_int(bw), C.c_int(bh), None)
     assert rc == 0, rc
     return {"Gtop": Gt.value, "Gbot": Gb.value, "iter": it.value, "err": err.value, "coarse": k.value}
 
