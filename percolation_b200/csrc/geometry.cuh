@@ -20,8 +20,10 @@
 
 #ifdef __CUDACC__
 #define PERC_HD __host__ __device__ __forceinline__
+#define PERC_HD_COLD __host__ __device__ __forceinline__
 #else
 #define PERC_HD inline
+#define PERC_HD_COLD inline
 #endif
 
 namespace perc {
@@ -276,7 +278,7 @@ PERC_HD double diag_seq(const Geom& g, unsigned cf, unsigned ex, int x, double g
 // error-free additions (Knuth's TwoSum; no multiplications, so no contraction can disturb it).  The reference's matrix is
 // the exact-row-sum Laplacian plus diag(rho): the deflated solver needs rho wherever it multiplies the matrix with a
 // block-constant vector analytically (pcg_fused_tile.cuh).
-PERC_HD double diag_seq_rho(const Geom& g, unsigned cf, unsigned ex, int x, double g0, double gleak, double* rho)
+PERC_HD_COLD double diag_seq_rho(const Geom& g, unsigned cf, unsigned ex, int x, double g0, double gleak, double* rho)
 {
     double d = 0.0, err = 0.0;
     // d += w with the rounding error of the addition added to err (w = +0.0 for a missing neighbour: no error)

@@ -752,7 +752,8 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         __syncwarp();
     };
 
-    // tile coordinates advance incrementally (a CTA's tiles are gridDim.x apart: no division per tile)
+    // tile coordinates advance incrementally (a CTA's tiles are gridDim.x apart: no division per tile).  (Numbering the
+    // tiles column by column, which spreads the slower boundary tiles more evenly over the CTAs, was measured: slower.)
     const int G = (int)gridDim.x, dxs = G % ntx, dys = G / ntx;
     auto advance = [&](int& ix, int& iy) {
         if (rev) { ix -= dxs; iy -= dys; if (ix < 0) { ix += ntx; --iy; } }
@@ -795,14 +796,20 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         const double* uu = C::USTATE ? sr : su;                 // V = 3: the staged vector IS u
         if (C::V == 1) { rz = 0.0; rr = 0.0; en = 0.0; }
         double ru = 0.0;                                        // sum rho u' over this tile's sites (deflation)
-        ft_phase_main<LAT, C>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, interior, tid, r_out, s_out, xrow, prow, rz, rr, sftk, rtab, &ru);
-        ft_phase_ringcols<LAT, C>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, tid, sftk, interior, rtab);
+        if (interior) {                                         // (uniform over the CTA: two instantiations of the tile phases)
+            ft_phase_main<LAT, C, true>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, true, tid, r_out, s_out, xrow, prow, rz, rr, sftk, rtab, &ru);
+            ft_phase_ringcols<LAT, C, true>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, tid, sftk, rtab);
+        } else {
+            ft_phase_main<LAT, C, false>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, false, tid, r_out, s_out, xrow, prow, rz, rr, sftk, rtab, &ru);
+            ft_phase_ringcols<LAT, C, false>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, tid, sftk, rtab);
+        }
         if (C::DEFL) {
             for (int o = 16; o; o >>= 1) ru += __shfl_down_sync(0xffffffffu, ru, o);
             if ((tid & 31) == 0) sru[(k & 1) * 32 + (tid >> 5)] = ru;
         }
         __syncthreads();
-        ft_phase_energy<LAT, C>(g, sc, ss, scf, x0, y0, interior, tid, en);
+        if (interior) ft_phase_energy<LAT, C, true>(g, sc, ss, scf, x0, y0, tid, en);
+        else ft_phase_energy<LAT, C, false>(g, sc, ss, scf, x0, y0, tid, en);
         constexpr int FLUX_WARPS = (FtFluxItems<C>::N + 31) / 32, FLUX_LOW = (C::TY + C::TX + 31) / 32;
         // work items beyond the east column / top row exist only on the triangular lattice (west column) and in tiles that
         // hold row 1 or row n-2 (bonds into the Dirichlet rows): uniform over the CTA

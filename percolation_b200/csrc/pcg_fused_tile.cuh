@@ -44,8 +44,7 @@ struct FtCfg {
     static constexpr int MAIN_THREADS = 64 * NG;            // 2 columns per thread
     static constexpr int CR = TY + 1;                       // compute rows: gy = y0 + lr, lr = 0 .. TY (last = north ring)
     static constexpr int RING_T0 = V == 1 ? 0 : MAIN_THREADS;    // first thread that works on the ring columns
-    static constexpr int RING_NT = V == 1 ? 2 * CR : (V >= 5 ? 32 : 64);   // ... and how many of them share the 2 CR ring sites (deflated: ONE ring
-                                                                           // warp, 736 threads, so that a thread may hold 88 registers)
+    static constexpr int RING_NT = V == 1 ? 2 * CR : 64;         // ... and how many of them share the 2 CR ring sites
     static constexpr int THREADS = V == 1 ? MAIN_THREADS : MAIN_THREADS + RING_NT;
     static constexpr int RR = TY + 3;                       // staged rows of r, conduct bytes, u: gy = y0 - 1 + pr
     static constexpr int SR = TY + 1;                       // staged rows of s:                   gy = y0 + ps
@@ -149,7 +148,7 @@ PERC_HD double ft_cinv_entry(int idx, double g0, double gleak)
     const double d = fma((double)(idx & 7), gleak, (double)(idx >> 3) * g0);
     return d > 0.0 ? 1.0 / d : 0.0;
 }
-PERC_HD FtDiag ft_diag_site(const Geom& g, unsigned cf, unsigned ex, int gx, double g0, double gleak, const double* cinv)
+PERC_HD_COLD FtDiag ft_diag_site(const Geom& g, unsigned cf, unsigned ex, int gx, double g0, double gleak, const double* cinv)
 {
     FtDiag e;
     e.d = diag_seq(g, cf, ex, gx, g0, gleak);
@@ -441,7 +440,10 @@ PERC_HD void ft_phase_u(const Geom& g, const double* sr, const uint8_t* scf, dou
 // ---- phase M: w = A u, s' = w + beta s, r' = r - alpha s', u' = r'/d on the compute rows; stores r', s' of
 // the tile rows; u' replaces s in shared memory (each thread overwrites only what it has read itself);
 // p / x of the two read-out rows; sums r'.u' and r'.r' over the tile's sites ---------------------------------
-template <int LAT, class C>
+// INT: the tile has no lattice border within its 2-site halo (ft_interior) -- its own instantiation: no geometry, no
+// validity tests, no read-out rows (they lie in boundary tiles), every diagonal from the pattern table; the boundary tiles
+// (a few per cent) run the general code without weighing on the registers and the instruction count of this one
+template <int LAT, class C, bool INT>
 PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr, double* ss, const uint8_t* scf,
                            const double* su, const FtDiag* dtab, const double* cinv, int x0, int y0, bool interior_flag, int tid,
                            double* __restrict__ r_out, double* __restrict__ s_out, double* __restrict__ xrow,
@@ -449,7 +451,8 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
                            const double* rtab = nullptr, double* acc_ru = nullptr)
 {
     if (tid >= C::MAIN_THREADS) return;
-    const bool interior = interior_flag;
+    constexpr bool interior = INT;
+    (void)interior_flag;
     const int tx = tid & 63, ty = tid >> 6, lane = tid & 31;
     const int gx = x0 + 2 * tx, lr0 = ty * C::RPT;
     const double alpha = sc.alpha, beta = sc.beta;
@@ -549,7 +552,7 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
             acc_rr += rn0 * rn0 + rn1 * rn1;
             if (C::DEFL) *acc_ru += rho0 * un0 + rho1 * un1;
             // the rows the read-out consumes: p = (u - Z mu) + beta p, x += alpha p
-            if (gy == 1 || gy == g.n - 2) {
+            if (!INT && (gy == 1 || gy == g.n - 2)) {
                 const int64_t o = (gy == 1 ? 0 : g.m) + gx;
                 const ft_d2 p2 = ft_ld2(prow + o), x2 = ft_ld2(xrow + o);
                 const double p0 = (cc.x - mc) + beta * p2.x, p1 = (cc.y - mc) + beta * p2.y;
@@ -563,27 +566,31 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
 }
 
 // east / west ring columns (gx = x0 - 1 and x0 + TX) of the compute rows: u' only (one thread per site)
-template <int LAT, class C>
+template <int LAT, class C, bool INT>
 PERC_HD void ft_phase_ringcols(const Geom& g, const FtScalars& sc, const double* sr, double* ss, const uint8_t* scf,
                                const double* su, const FtDiag* dtab, const double* cinv, int x0, int y0, int tid, const double* sft = nullptr,
-                               bool interior = false, const double* rtab = nullptr)
+                               const double* rtab = nullptr)
 {
+    constexpr bool interior = INT;
     const int lane = tid & 31;
     for (int q = tid - C::RING_T0; q >= 0 && q < 2 * C::CR; q += C::RING_NT) {
     const int side = q >= C::CR, lr = q - side * C::CR;
     const int gy = y0 + lr, gx = side ? x0 + C::TX : x0 - 1, col = side ? 2 + C::TX : 1;
     double un = 0.0;
     if (gy >= 1 && gy <= g.n - 2 && gx >= 0 && gx < g.m) {
-        const unsigned ex = neighbour_bits(g, gx, gy);
+        const unsigned ex = interior ? ft_interior_ex<LAT>(gx) : neighbour_bits(g, gx, gy);
         const unsigned cf = scf[(lr + 1) * C::CLD + (side ? 16 + C::TX : 15)] & ex;
         const double* c = &su[(lr + 1) * C::LD + col];
         double all = 0.0, con = 0.0, kz = 0.0;
         // (deflation: minus (A Z mu)_i as in ft_phase_main; mu of a neighbour from the shift table by its row and block column)
         const double mi = C::DEFL ? sft[(lr + 1) * 4 + ft_defl_cls<C>(col)] : 0.0;
-#define FT_NB(bit, dc, dr) if (ex & bit) { const double v = c[(dr) * C::LD + (dc)]; all += v; if (cf & bit) con += v; \
-                                           if (C::DEFL) kz += ((cf & bit) ? sc.g0 : sc.gleak) * (mi - sft[(lr + 1 + (dr)) * 4 + ft_defl_cls<C>(col + (dc))]); }
+#define FT_NB(bit, dc, dr) if (interior || (ex & bit)) { const double v = c[(dr) * C::LD + (dc)]; all += v; if (cf & bit) con += v; \
+                                           if (C::DEFL) { const double dm = mi - sft[(lr + 1 + (dr)) * 4 + ft_defl_cls<C>(col + (dc))]; \
+                                                          if (dm != 0.0) kz += ((cf & bit) ? sc.g0 : sc.gleak) * dm; } }
         FT_NB(NB_E, 1, 0) FT_NB(NB_W, -1, 0) FT_NB(NB_N, 0, 1) FT_NB(NB_S, 0, -1)
-        if (LAT == LAT_TRIANGULAR) { FT_NB(NB_NW, -1, 1) FT_NB(NB_NE, 1, 1) FT_NB(NB_SW, -1, -1) FT_NB(NB_SE, 1, -1) }
+        if (LAT == LAT_TRIANGULAR) {
+            if (gx & 1) { FT_NB(NB_SW, -1, -1) FT_NB(NB_SE, 1, -1) } else { FT_NB(NB_NW, -1, 1) FT_NB(NB_NE, 1, 1) }
+        }
 #undef FT_NB
         // (a tile without lattice borders: its ring columns have all their neighbours too -- x0 - 1 is odd, x0 + TX even)
         const int it = C::tabp(LAT, ft_pat<LAT>(cf, gx & 1), lane);
@@ -605,12 +612,12 @@ PERC_HD void ft_phase_ringcols(const Geom& g, const FtScalars& sc, const double*
 
 // ---- phase E: u'.A u' as the energy of the bonds OWNED by the tile's sites (E, N, NW, NE), u' from shared
 // memory (zeros on Dirichlet rows and outside the lattice) ---------------------------------------------------
-template <int LAT, class C>
+template <int LAT, class C, bool INT>
 PERC_HD void ft_phase_energy(const Geom& g, const FtScalars& sc, const double* ss, const uint8_t* scf, int x0, int y0,
-                             bool interior_flag, int tid, double& acc_e)
+                             int tid, double& acc_e)
 {
     if (tid >= C::MAIN_THREADS) return;
-    const bool interior = interior_flag;
+    constexpr bool interior = INT;
     const int tx = tid & 63, ty = tid >> 6;
     const int gx = x0 + 2 * tx, lr0 = ty * C::RPT;
 #if defined(__CUDA_ARCH__)

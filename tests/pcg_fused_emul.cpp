@@ -17,6 +17,11 @@
 
 using namespace perc;
 
+// the kernel picks the instantiation of the tile phases per tile (interior / boundary): same dispatch here
+#define EMUL_MAIN(...) do { if (interior) ft_phase_main<LAT, C, true>(__VA_ARGS__); else ft_phase_main<LAT, C, false>(__VA_ARGS__); } while (0)
+#define EMUL_RING(...) do { if (interior) ft_phase_ringcols<LAT, C, true>(__VA_ARGS__); else ft_phase_ringcols<LAT, C, false>(__VA_ARGS__); } while (0)
+#define EMUL_ENERGY(...) do { if (interior) ft_phase_energy<LAT, C, true>(__VA_ARGS__); else ft_phase_energy<LAT, C, false>(__VA_ARGS__); } while (0)
+
 namespace {
 
 // conduct bytes (8 direction bits per site) from per-bond weights in reference row order
@@ -97,11 +102,11 @@ int solve(const Geom& g, const std::vector<uint8_t>& cf, double Va, double g0, d
                 for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_u<LAT, C>(g, sr.data(), scf.data(), su.data(), dtab.data(), x0, y0, interior, tid, g0, gleak, cinv.data());
             const double* up = C::USTATE ? sr.data() : su.data();
             for (int tid = C::THREADS - 1; tid >= 0; --tid) {
-                ft_phase_main<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), cinv.data(), x0, y0, interior, tid,
+                EMUL_MAIN(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), cinv.data(), x0, y0, interior, tid,
                                       r[cur ^ 1].data(), s[cur ^ 1].data(), xrow.data(), prow.data(), rz, rr);
-                ft_phase_ringcols<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), cinv.data(), x0, y0, tid, nullptr, interior);
+                EMUL_RING(g, sc, sr.data(), ss.data(), scf.data(), up, dtab.data(), cinv.data(), x0, y0, tid, nullptr);
             }
-            for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_energy<LAT, C>(g, sc, ss.data(), scf.data(), x0, y0, interior, tid, en);
+            for (int tid = 0; tid < C::THREADS; ++tid) EMUL_ENERGY(g, sc, ss.data(), scf.data(), x0, y0, tid, en);
         }
         ft_scalar_step(st, rz, rr, en, prime);
         cur ^= 1;
@@ -213,11 +218,11 @@ int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double 
             const bool interior = ft_interior<C>(g, x0, y0);
             double ru = 0.0;
             for (int tid = C::THREADS - 1; tid >= 0; --tid) {
-                ft_phase_main<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), sr.data(), dtab.data(), cinv.data(), x0, y0, interior, tid,
+                EMUL_MAIN(g, sc, sr.data(), ss.data(), scf.data(), sr.data(), dtab.data(), cinv.data(), x0, y0, interior, tid,
                                              r[cur ^ 1].data(), s[cur ^ 1].data(), xrow.data(), prow.data(), rz, rr, sft.data(), rtab.data(), &ru);
-                ft_phase_ringcols<LAT, C>(g, sc, sr.data(), ss.data(), scf.data(), sr.data(), dtab.data(), cinv.data(), x0, y0, tid, sft.data(), interior, rtab.data());
+                EMUL_RING(g, sc, sr.data(), ss.data(), scf.data(), sr.data(), dtab.data(), cinv.data(), x0, y0, tid, sft.data(), rtab.data());
             }
-            for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_energy<LAT, C>(g, sc, ss.data(), scf.data(), x0, y0, interior, tid, en);
+            for (int tid = 0; tid < C::THREADS; ++tid) EMUL_ENERGY(g, sc, ss.data(), scf.data(), x0, y0, tid, en);
             // crossing currents: per ring thread partial sums, folded thread by thread (the kernel: shuffles, then the two warps)
             double fl[FS_SLOTS] = {0, 0, 0, 0, 0, ru};
             for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_flux<LAT, C>(g, sc, ss.data(), scf.data(), x0, y0, tid, fl, interior);
