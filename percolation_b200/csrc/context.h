@@ -88,9 +88,6 @@ struct Ctx {
     double* h_defl = nullptr;     // pinned: E^-1, W
     size_t defl_bytes = 0;
     int defl_k = 0;               // coarse dimension of the last deflated solve
-    int* d_defl_terms = nullptr;  // term lists of Z^T A u' per block: tptr [KMAX + 1], tent [...] (built once per block shape)
-    int defl_terms_key[4] = {0, 0, 0, 0};   // (bw, bh, ntx, nty) the lists were built for
-    int defl_tw = 0;              // padded width of the lists (0: CSR walk)
     double* partial = nullptr;    // per-block partial sums
     int partial_cap = 0;
     PcgState* d_pcg = nullptr;

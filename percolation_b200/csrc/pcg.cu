@@ -666,6 +666,7 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
 // each); everything else takes the two-kernel path.  Consecutive iterations sweep the tiles in opposite
 // directions, so each starts on the part of r / s the previous one wrote last (still in L2).
 // ------------------------------------------------------------------------------------------
+static_assert(FT_KMAX <= 2 * FtCfgD::THREADS, "the coarse stage takes at most two blocks per thread");
 static_assert(FtCfgA::SMEM <= 227 * 1024 && FtCfgA3::SMEM <= 227 * 1024 && FtCfgD::SMEM <= 227 * 1024, "fused PCG tile does not fit the shared memory of one SM");
 
 // block sums of three values at once (fixed order: lanes by shuffles, then warp 0 folds the per-warp partials by
@@ -691,18 +692,18 @@ __device__ __forceinline__ void block_sum3(double& a, double& b, double& c, doub
     }
 }
 
-// device arrays of the deflated iteration (FtCfgD; unused otherwise): mu[k] of the blocks (read by the sweep, rewritten by
-// its coarse stage), F[ntiles][FS_STRIDE] crossing currents per tile, Einv[k][k] dense inverse of E = Z^T A Z
-// tptr / tent: the terms of Z^T A u' per block (ft_defl_terms); tw > 0: the lists padded to tw (16 or 32) entries per
-// block (-1 = no term), so that every thread gathers independent entries and a block's sum is a shuffle tree
-struct FtDeflDev { FtDefl D; double* mu; double* F; double* fglob; const double* Einv; const int* tptr; const int* tent; int tw; };
+// device arrays of the deflated iteration (FtCfgD; the others use D only: the order in which the tiles are visited):
+// mu[k] of the blocks (read by the sweep, rewritten by its coarse stage), Fb[FB_PLANES][FT_KMAX] crossing currents
+// summed per block, Einv[k][k] dense inverse of E = Z^T A Z
+struct FtDeflDev { FtDefl D; double* mu; double* Fb; const double* Einv; };
+constexpr int FW_VALID = 256;           // tcoord.z: FtWalk::info of the tile | FW_VALID
 
 template <int LAT, class C>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS)
 pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_s,
                  const __grid_constant__ CUtensorMap tm_cf, Geom g, PcgParams prm, double* __restrict__ r_out,
                  double* __restrict__ s_out, double* __restrict__ xrow, double* __restrict__ prow,
-                 double* __restrict__ partial, PcgState* __restrict__ st, int ntx, int ntiles, int rev, int prime, FtDeflDev dd)
+                 double* __restrict__ partial, PcgState* __restrict__ st, int rev, int prime, FtDeflDev dd)
 {
     if (st->done) return;
     extern __shared__ __align__(128) unsigned char ft_raw[];
@@ -711,83 +712,122 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
     double* sh = reinterpret_cast<double*>(dtab + 64 * C::DC);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sh + 96);                      // one mbarrier per stage
     double* cinv = reinterpret_cast<double*>(bars + 2);                                             // [64] 1/d by bond counts (boundary tiles)
-    double* sft = cinv + 64;                                                                        // [2][RR * 4] shift tables (deflation)
-    double* sfl = sft + 2 * C::RR * 4;                                                              // [32][8] crossing currents per warp and slot
-    double* sru = sfl + 256;                                                                         // [2][32] sum rho u' per warp (two tiles in flight)
-    double* sf = sru + 64;                                                                           // [FT_KMAX] mu of every block during the sweep, Z^T A u' in the coarse stage
-    int* sterm = reinterpret_cast<int*>(sf + FT_KMAX);                                              // [256] term lists of this CTA's blocks (padded form)
-    double* rtab = reinterpret_cast<double*>(sterm + 256);                                          // rounding residue of the diagonal per table slot
+    int4* tcoord = reinterpret_cast<int4*>(cinv + 64);                                              // [2] tile (ix, iy, info | FW_VALID, block) of the two stages
+    FtWalk* wk_sm = reinterpret_cast<FtWalk*>(tcoord + 2);                                          // the producer's position on the lattice (32 bytes; in registers only while it moves)
+    double* sft = reinterpret_cast<double*>(tcoord + 4);                                            // [2][SFT_N] shift tables (deflation)
+    double* srec = sft + 2 * C::SFT_N;                                                              // [2][REC_N] ... and their per-row records
+    double* sfl = srec + 2 * C::REC_N;                                                              // [256] row partials of the coarse product; scratch
+    double* sru = sfl + 256;                                                                        // [THREADS] sum rho u' per main thread
+    double* tsl = sru + C::THREADS;                                                                 // [8] slot totals of the tile just done
+    double* bacc = tsl + 8;                                                                         // [8] running sums of the block being walked
+    double* sf = bacc + 8;                                                                          // [FT_KMAX] mu of every block during the sweep, Z^T A u' in the coarse stage
+    double* rtab = sf + FT_KMAX;                                                                    // rounding residue of the diagonal per table slot
     const int tid = threadIdx.x;
-    if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    const int G = (int)gridDim.x;
     const FtScalars sc{prm.g0, prm.gleak, prime ? 0.0 : st->ak, prime ? 0.0 : st->bk};
-    auto tile_of = [&](int t) { return rev ? ntiles - 1 - t : t; };
     auto stage_r = [&](int k) { return reinterpret_cast<double*>(ft_raw + (size_t)k * C::STAGE_BYTES); };
     auto stage_s = [&](int k) { return reinterpret_cast<double*>(ft_raw + (size_t)k * C::STAGE_BYTES + C::R_BYTES); };
     auto stage_cf = [&](int k) { return reinterpret_cast<uint8_t*>(ft_raw + (size_t)k * C::STAGE_BYTES + C::R_BYTES + C::S_BYTES); };
-    // one thread, three TMA tensor copies: r (tile + 2-site halo), s (tile + east / north / west ring), conduct bytes
-    auto issue = [&](int k, int x0, int y0) {
-        if (tid != 0) return;
+    // the producer thread (first lane of the second ring warp, which has time to spare) walks the lattice (FtWalk: block by
+    // block) one tile ahead of the CTA: it publishes the coordinates of the next tile and issues its three TMA tensor copies:
+    // r (tile + 2-site halo), s (tile + east / north / west ring), conduct bytes
+    constexpr int PROD = C::V == 1 ? 0 : C::RING_T0 + 32;
+    auto publish_issue = [&](const FtWalk& wk, int k) {
+        int4 nt = make_int4(0, 0, 0, 0);
+        if (wk.valid(dd.D)) nt = make_int4(wk.ix(dd.D), wk.iy(dd.D), wk.info(dd.D, rev) | FW_VALID, wk.B);
+        tcoord[k] = nt;
+        if (!(nt.z & FW_VALID)) return;
+        const int x0 = nt.x * C::TX, y0 = nt.y * C::TY;
         mbar_arrive_expect(&bars[k], (unsigned)(C::RR * C::LD * 8 + C::SR * C::LD * 8 + C::RR * C::CLD));
         tma_box_g2s(stage_r(k), &tm_r, x0 - 2, y0 - 1, &bars[k]);
         tma_box_g2s(stage_s(k), &tm_s, x0 - 2, y0, &bars[k]);
         tma_box_g2s(stage_cf(k), &tm_cf, x0 - 16, y0 - 1, &bars[k]);
     };
-    // shift table of tile (ix, iy) into buffer b, by ONE warp (lane l): the nine mu of the 3 x 3 blocks around the tile
-    // first, then the entry of every staged row and block column (0 on rows that are not unknowns)
+    if (tid == PROD) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        FtWalk wk;
+        wk.start(dd.D, (int)blockIdx.x, G, rev);
+        publish_issue(wk, 0);
+        *wk_sm = wk;
+    }
+    // shift table of tile (ix, iy) into buffer b, by ONE warp (lane l): the nine mu of the 3 x 3 tiles around the tile
+    // first, then one lane per staged row: mu of the west / own / east block column (0 on rows that are not unknowns),
+    // then one lane per compute row: its record (ft_defl_rec_entry: the same differences, formed here without the switch)
     auto fill_shift = [&](int b, int ix, int iy, int l) {
-        double* m9 = sfl + 240;                                  // scratch behind the per-warp currents ([30][8] used)
+        double* m9 = sfl + 240;
+        double* T = sft + b * C::SFT_N;
+        double* R = srec + b * C::REC_N;
         if (l < 9) {
             const int tx = ix + l % 3 - 1, ty = iy + l / 3 - 1;
             m9[l] = (tx >= 0 && tx < dd.D.ntx && ty >= 0 && ty < dd.D.nty) ? sf[ft_defl_block(dd.D, tx, ty)] : 0.0;
         }
         __syncwarp();
-        for (int j = l; j < C::RR * 4; j += 32) {
-            const int pr = j >> 2, cls = j & 3, gy = iy * C::TY - 1 + pr;
-            if (cls != 3) sft[b * C::RR * 4 + j] = (gy >= 1 && gy <= g.n - 2) ? m9[(pr == 0 ? 0 : (pr > C::TY ? 2 : 1)) * 3 + cls] : 0.0;
+        for (int pr = l; pr < C::RR; pr += 32) {
+            const int gy = iy * C::TY - 1 + pr;
+            const bool unk = gy >= 1 && gy <= g.n - 2;
+            const double* mrow = m9 + (pr == 0 ? 0 : (pr > C::TY ? 6 : 3));      // tile row below / own / above
+            ft_st2(&T[pr * 4 + 0], unk ? mrow[0] : 0.0, unk ? mrow[1] : 0.0);
+            ft_st2(&T[pr * 4 + 2], unk ? mrow[2] : 0.0, 0.0);
+        }
+        __syncwarp();
+        for (int lr = l; lr < C::CR; lr += 32) {
+            const double* a = T + lr * 4;                       // rows pr = lr (below), lr + 1 (own), lr + 2 (above)
+            const double mc = a[5];
+            ft_st2(&R[lr * 8 + 0], mc, mc - a[9]);              // mu, north
+            ft_st2(&R[lr * 8 + 2], mc - a[1], 0.0);             // south, (zero)
+            ft_st2(&R[lr * 8 + 4], mc - a[4], mc - a[6]);       // west, east
+            ft_st2(&R[lr * 8 + 6], mc - a[8], mc - a[2]);       // north-west across the west border, south-east across the east border
         }
         __syncwarp();
     };
-
-    // tile coordinates advance incrementally (a CTA's tiles are gridDim.x apart: no division per tile).  (Numbering the
-    // tiles column by column, which spreads the slower boundary tiles more evenly over the CTAs, was measured: slower.)
-    const int G = (int)gridDim.x, dxs = G % ntx, dys = G / ntx;
-    auto advance = [&](int& ix, int& iy) {
-        if (rev) { ix -= dxs; iy -= dys; if (ix < 0) { ix += ntx; --iy; } }
-        else     { ix += dxs; iy += dys; if (ix >= ntx) { ix -= ntx; ++iy; } }
+    // slot totals of a finished tile into the running sums of its block; the block's sums go out with its last tile
+    auto block_step = [&](int info, int B) {
+        ft_defl_block_add(info, tsl, bacc);
+        if (info & FW_LAST) {
+#pragma unroll
+            for (int q = 0; q < FB_PLANES; ++q) { dd.Fb[q * FT_KMAX + B] = bacc[q]; bacc[q] = 0.0; }
+        }
     };
-    int t = blockIdx.x;
-    int ix = 0, iy = 0;                                          // tile t
-    if (t < ntiles) { const int tl = tile_of(t); ix = tl % ntx; iy = tl / ntx; issue(0, ix * C::TX, iy * C::TY); }   // (thread 0: it made the mbarriers)
+
     for (int k = tid; k < ft_tab_slots<LAT, C>(); k += C::THREADS) dtab[k] = ft_tab_slot<LAT, C>(g, k, prm.g0, prm.gleak);
     if (tid >= C::THREADS - 64) cinv[tid - (C::THREADS - 64)] = ft_cinv_entry(tid - (C::THREADS - 64), prm.g0, prm.gleak);
     if (C::DEFL) {
         for (int k = tid; k < ft_tab_slots<LAT, C>(); k += C::THREADS) rtab[k] = ft_rho_slot<LAT, C>(g, k, prm.g0, prm.gleak);
-        // mu of every block (8 KB) stays in shared memory for the sweep; the static term lists of the blocks whose
-        // Z^T A u' this CTA assembles in the coarse stage (block blockIdx.x + j gridDim.x) are fetched now, off the critical path
+        // mu of every block (8 KB) stays in shared memory for the sweep
         for (int B = tid; B < dd.D.k; B += C::THREADS) sf[B] = dd.mu[B];
-        if (dd.tw > 0 && tid < 256) {
-            const int B = (int)blockIdx.x + (int)gridDim.x * (tid / dd.tw);
-            sterm[tid] = B < dd.D.k ? dd.tent[B * dd.tw + (tid & (dd.tw - 1))] : -1;
-        }
-        __syncthreads();
-        if (t < ntiles && tid < 32) fill_shift(0, ix, iy, tid);
+        if (tid < 16) tsl[tid] = 0.0;                                    // (tsl and bacc)
     }
     __syncthreads();
-    int nx = ix, ny = iy;                                        // tile t + gridDim.x
-    advance(nx, ny);
+    if (C::DEFL && tid >= PROD && tid < PROD + 32) { const int4 t0 = tcoord[0]; if (t0.z & FW_VALID) fill_shift(0, t0.x, t0.y, tid - PROD); }
+    __syncthreads();
     double rz = 0.0, rr = 0.0, en = 0.0;
-    for (int k = 0; t < ntiles; t += G, ++k) {
-        const int x0 = ix * C::TX, y0 = iy * C::TY;
-        if (t + G < ntiles) issue((k + 1) & 1, nx * C::TX, ny * C::TY);     // the other stage was released by the barriers of the last tile
+    int pinfo = 0, pB = 0;                                       // the tile before this one
+    for (int k = 0;; ++k) {
+        const int4 tc = tcoord[k & 1];
+        if (!(tc.z & FW_VALID)) break;
+        const int ix = tc.x, iy = tc.y, x0 = ix * C::TX, y0 = iy * C::TY;
+        if (tid == PROD) {                                       // the other stage was released by the barriers of the last tile
+            FtWalk wk = *wk_sm;
+            wk.next(dd.D, G, rev);
+            publish_issue(wk, (k + 1) & 1);
+            *wk_sm = wk;
+        }
+        if (C::DEFL && tid >= PROD && tid < PROD + 32) {
+            // ... and its warp prepares the next tile's shift table while the others wait for this tile's data (the other
+            // buffer: its readers finished before the last tile's barriers)
+            __syncwarp();
+            const int4 nt = tcoord[(k + 1) & 1];
+            if (nt.z & FW_VALID) fill_shift((k + 1) & 1, nt.x, nt.y, tid - PROD);
+        }
+        if (C::DEFL && tid == C::RING_T0 && (pinfo & FW_VALID)) block_step(pinfo, pB);
         mbar_wait(&bars[k & 1], (unsigned)((k >> 1) & 1));
         const double* sr = stage_r(k & 1);
         double* ss = stage_s(k & 1);
         const uint8_t* scf = stage_cf(k & 1);
-        const double* sftk = C::DEFL ? sft + (k & 1) * C::RR * 4 : nullptr;
+        const double* sftk = C::DEFL ? sft + (k & 1) * C::SFT_N : nullptr;
+        const double* sreck = C::DEFL ? srec + (k & 1) * C::REC_N : nullptr;
         const bool interior = ft_interior<C>(g, x0, y0);
         if (!C::USTATE) {
             ft_phase_u<LAT, C>(g, sr, scf, su, dtab, x0, y0, interior, tid, prm.g0, prm.gleak, cinv);
@@ -795,68 +835,51 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         }
         const double* uu = C::USTATE ? sr : su;                 // V = 3: the staged vector IS u
         if (C::V == 1) { rz = 0.0; rr = 0.0; en = 0.0; }
-        double ru = 0.0;                                        // sum rho u' over this tile's sites (deflation)
+        double ru = 0.0;                                        // sum rho u' over this thread's sites of the tile (deflation)
         if (interior) {                                         // (uniform over the CTA: two instantiations of the tile phases)
-            ft_phase_main<LAT, C, true>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, true, tid, r_out, s_out, xrow, prow, rz, rr, sftk, rtab, &ru);
+            ft_phase_main<LAT, C, true>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, true, tid, r_out, s_out, xrow, prow, rz, rr, sreck, rtab, &ru);
             ft_phase_ringcols<LAT, C, true>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, tid, sftk, rtab);
         } else {
-            ft_phase_main<LAT, C, false>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, false, tid, r_out, s_out, xrow, prow, rz, rr, sftk, rtab, &ru);
+            ft_phase_main<LAT, C, false>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, false, tid, r_out, s_out, xrow, prow, rz, rr, sreck, rtab, &ru);
             ft_phase_ringcols<LAT, C, false>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, tid, sftk, rtab);
         }
-        if (C::DEFL) {
-            for (int o = 16; o; o >>= 1) ru += __shfl_down_sync(0xffffffffu, ru, o);
-            if ((tid & 31) == 0) sru[(k & 1) * 32 + (tid >> 5)] = ru;
-        }
+        if (C::DEFL && tid < C::MAIN_THREADS) sru[tid] = ru;
         __syncthreads();
         if (interior) ft_phase_energy<LAT, C, true>(g, sc, ss, scf, x0, y0, tid, en);
         else ft_phase_energy<LAT, C, false>(g, sc, ss, scf, x0, y0, tid, en);
-        constexpr int FLUX_WARPS = (FtFluxItems<C>::N + 31) / 32, FLUX_LOW = (C::TY + C::TX + 31) / 32;
-        // work items beyond the east column / top row exist only on the triangular lattice (west column) and in tiles that
-        // hold row 1 or row n-2 (bonds into the Dirichlet rows): uniform over the CTA
-        const int fw = (LAT == LAT_TRIANGULAR || y0 <= 1 || y0 + C::TY >= g.n - 2) ? FLUX_WARPS : FLUX_LOW;
-        if (C::DEFL && tid < fw * 32) {
-            // currents through the bonds that cross the tile's borders: one work item per thread, summed per slot and warp
+        if (C::DEFL && tid >= C::RING_T0) {
+            // meanwhile the two ring warps form the currents through the bonds that cross the tile's borders: every slot
+            // has one producer warp (ft_flux_thread), lanes folded by a fixed shuffle tree
+            const int rl = tid - C::RING_T0;
             double f[FS_SLOTS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            ft_phase_flux<LAT, C>(g, sc, ss, scf, x0, y0, tid, f, interior);
+            ft_flux_thread<LAT, C>(g, sc, ss, scf, sru, x0, y0, rl, interior, f);
+            const bool dirichlet = !interior && (y0 <= 1 || y0 + C::TY >= g.n - 2);
 #pragma unroll
-            for (int q = 0; q < FS_R; ++q) {
-                if (LAT == LAT_SQUARE && (q == FS_W || q == FS_NW)) continue;
-                for (int o = 16; o; o >>= 1) f[q] += __shfl_down_sync(0xffffffffu, f[q], o);
-                if ((tid & 31) == 0) sfl[(tid >> 5) * 8 + q] = f[q];
+            for (int q = 0; q < FS_SLOTS; ++q) {
+                const bool second = q == FS_N || q == FS_NW;                     // slots of the second ring warp
+                if (second != (rl >= 32)) continue;
+                if (LAT == LAT_SQUARE && (q == FS_W || q == FS_NW)) continue;    // (stay 0)
+                double v = f[q];
+                if (q != FS_D || dirichlet)
+                    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                if ((rl & 31) == 0) tsl[q] = v;
             }
         }
-        // meanwhile the first ring warp prepares the next tile's shift table (the other buffer: its readers finished with the
-        // last tile's barriers, its next readers come after this tile's)
-        if (C::DEFL && tid >= C::RING_T0 && tid < C::RING_T0 + 32 && t + G < ntiles) fill_shift((k + 1) & 1, nx, ny, tid - C::RING_T0);
         // generic-proxy accesses to this stage are ordered before the bulk copies that will refill it
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (C::V == 1) {
             // per-tile partial sums, folded in tile order: the result does not depend on the number of CTAs
-            const int tl = iy * ntx + ix;
+            const int tl = iy * dd.D.ntx + ix;
             double a = rz, b = rr, c = en;
             block_sum3(a, b, c, sh);                            // synchronises: every thread is done with the stage
             if (tid == 0) { partial[tl * 3 + 0] = a; partial[tl * 3 + 1] = b; partial[tl * 3 + 2] = c; }
         } else {
             __syncthreads();                                    // every thread is done with the stage
         }
-        if (C::DEFL && tid >= C::RING_T0 + (C::RING_NT > 32 ? 32 : 0)) {
-            // the last ring warp folds the per-warp currents (lane <-> warp, fixed shuffle tree) and stores the tile's slots
-            const int l = tid - C::RING_T0 - (C::RING_NT > 32 ? 32 : 0);
-            double* Ft = dd.F + (size_t)(iy * ntx + ix) * FS_STRIDE;
-#pragma unroll
-            for (int q = 0; q < FS_SLOTS; ++q) {
-                double v = 0.0;
-                if (!(LAT == LAT_SQUARE && (q == FS_W || q == FS_NW))) {
-                    v = q == FS_R ? (l < C::THREADS / 32 ? sru[(k & 1) * 32 + l] : 0.0) : (l < fw ? sfl[l * 8 + q] : 0.0);
-                    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-                }
-                if (l == 0) Ft[q] = v;
-            }
-        }
-        ix = nx; iy = ny;
-        advance(nx, ny);
+        pinfo = tc.z; pB = tc.w;
     }
-    int nparts = ntiles;
+    if (C::DEFL && tid == C::RING_T0 && (pinfo & FW_VALID)) block_step(pinfo, pB);
+    int nparts = dd.D.ntx * dd.D.nty;
     constexpr int NQ = C::DEFL ? 4 : 3;
     if (C::V >= 2) {
         // the sums stayed in registers over all tiles of this CTA: one reduction per CTA, folded in CTA order
@@ -865,47 +888,27 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         nparts = G;
     }
     if (C::DEFL) {
-        // coarse stage (cooperative launch: every CTA is resident): when all tiles of the lattice are done, every CTA
-        // assembles Z^T A u' of all blocks, forms its share of the rows of mu' = E^-1 (Z^T A u') -- one warp per row, E^-1
-        // streams from L2 -- and its share of mu'.(Z^T A u'), which the scalar recurrences subtract from u'.A u'
+        // coarse stage (cooperative launch: every CTA is resident): when all tiles of the lattice are done -- ONE grid-wide
+        // barrier -- every CTA forms Z^T A u' of all blocks from the block sums (five loads per block, 40 KB from L2), its
+        // share of the rows of mu' = E^-1 (Z^T A u') -- E^-1 streams from L2 -- and its share of mu'.(Z^T A u'), which the
+        // scalar recurrences subtract from u'.A u'
         __threadfence();
         cooperative_groups::grid_group grid = cooperative_groups::this_grid();
         grid.sync();
         const int kk = dd.D.k;
         const int lane = tid & 31, w = tid >> 5, nw = C::THREADS / 32;
-        // (1) Z^T A u' of this CTA's blocks (block blockIdx.x + j gridDim.x): one gather per thread, a shuffle tree per block
-        if (dd.tw > 0) {
-            const int tw = dd.tw;
-            if (tid < 256) {
-                const int en = sterm[tid];
-                double v = 0.0;
-                if (en >= 0) { v = __ldcg(&dd.F[en >> 1]); if (en & 1) v = -v; }
-                for (int o = tw >> 1; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o, tw);
-                const int B = (int)blockIdx.x + G * (tid / tw);
-                if ((tid & (tw - 1)) == 0 && B < kk) dd.fglob[B] = v;
-            }
-        } else {
-            for (int B = blockIdx.x + G * w; B < kk; B += G * nw) {
-                double a = 0.0;
-                for (int e = dd.tptr[B] + lane; e < dd.tptr[B + 1]; e += 32) {
-                    const int en = dd.tent[e];
-                    const double v = __ldcg(&dd.F[en >> 1]);
-                    a += (en & 1) ? -v : v;
-                }
-                for (int o = 16; o; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
-                if (lane == 0) dd.fglob[B] = a;
-            }
+        {   // (k <= FT_KMAX < 2 THREADS: at most two blocks per thread, their ten loads in flight together)
+            const int B0 = tid, B1 = tid + C::THREADS;
+            const double f0 = ft_defl_block_f(dd.D, dd.Fb, B0 < kk ? B0 : 0), f1 = ft_defl_block_f(dd.D, dd.Fb, B1 < kk ? B1 : 0);
+            if (B0 < kk) sf[B0] = f0;
+            if (B1 < kk) sf[B1] = f1;
         }
-        __threadfence();
-        grid.sync();
-        // (2) every CTA reads the whole vector (8 KB) and forms its rows of mu' = E^-1 (Z^T A u')
-        for (int B = tid; B < kk; B += C::THREADS) sf[B] = __ldcg(&dd.fglob[B]);
         __syncthreads();
-        // unit (row r of this CTA, quarter q of the row): 8 independent loads per lane, one L2 latency per unit; the four
-        // quarter sums of a row are folded in fixed order afterwards
         const int nrows = (kk - (int)blockIdx.x + G - 1) / G;               // rows blockIdx.x + r G < kk
         const int qlen = ((kk + 3) / 4 + 31) / 32 * 32;
         double* part = sfl;                                                  // [nrows][4] (nrows * 4 <= 240: checked on the host)
+        // unit (row r of this CTA, quarter q of the row): 8 independent loads per lane, one L2 latency per unit; the four
+        // quarter sums of a row are folded in fixed order afterwards
         for (int u = w; u < nrows * 4; u += nw) {
             const int r = u >> 2, q = u & 3, j = (int)blockIdx.x + r * G;
             const double* row = dd.Einv + (size_t)j * kk;
@@ -1324,7 +1327,8 @@ static int pcg_defl_setup(Ctx* c, const PcgParams& prm, const FtDefl& D, int nti
 {
     const Geom& g = c->g;
     cudaStream_t s = c->stream;
-    const size_t need = sizeof(double) * ((size_t)D.k * D.k + 2 * (size_t)FT_KMAX + 2 * (size_t)ntiles * FS_STRIDE);
+    // Einv[k][k], mu[FT_KMAX], nu[FT_KMAX], Fb[FB_PLANES][FT_KMAX], W[ntiles][FS_STRIDE]
+    const size_t need = sizeof(double) * ((size_t)D.k * D.k + (2 + FB_PLANES) * (size_t)FT_KMAX + (size_t)ntiles * FS_STRIDE);
     if (need > c->defl_bytes) {
         if (c->d_defl) cudaFree(c->d_defl);
         if (c->h_defl) cudaFreeHost(c->h_defl);
@@ -1333,33 +1337,10 @@ static int pcg_defl_setup(Ctx* c, const PcgParams& prm, const FtDefl& D, int nti
         PERC_CUDA(cudaMallocHost(&c->h_defl, sizeof(double) * ((size_t)D.k * D.k + (size_t)ntiles * FS_STRIDE)));
         c->defl_bytes = need;
     }
-    if (!c->d_defl_terms || c->defl_terms_key[0] != D.bw || c->defl_terms_key[1] != D.bh || c->defl_terms_key[2] != D.ntx || c->defl_terms_key[3] != D.nty) {
-        // the terms of Z^T A u' per block depend on the lattice and block shape only
-        std::vector<int> ptr, ent;
-        ft_defl_terms(D, ptr, ent);
-        int mx = 0;
-        for (int B = 0; B < D.k; ++B) mx = ptr[B + 1] - ptr[B] > mx ? ptr[B + 1] - ptr[B] : mx;
-        const int tw = mx <= 16 ? 16 : (mx <= 32 ? 32 : 0);
-        std::vector<int> up((size_t)FT_KMAX + 1, 0);
-        for (int B = 0; B <= D.k; ++B) up[B] = ptr[B];
-        if (tw) {
-            std::vector<int> pad((size_t)D.k * tw, -1);
-            for (int B = 0; B < D.k; ++B) for (int e = ptr[B]; e < ptr[B + 1]; ++e) pad[(size_t)B * tw + (e - ptr[B])] = ent[e];
-            up.insert(up.end(), pad.begin(), pad.end());
-        } else up.insert(up.end(), ent.begin(), ent.end());
-        if (c->d_defl_terms) cudaFree(c->d_defl_terms);
-        c->d_defl_terms = nullptr;
-        PERC_CUDA(cudaMalloc(&c->d_defl_terms, sizeof(int) * up.size()));
-        PERC_CUDA(cudaMemcpyAsync(c->d_defl_terms, up.data(), sizeof(int) * up.size(), cudaMemcpyHostToDevice, s));
-        PERC_CUDA(cudaStreamSynchronize(s));            // `up` is pageable and goes out of scope
-        c->defl_terms_key[0] = D.bw; c->defl_terms_key[1] = D.bh; c->defl_terms_key[2] = D.ntx; c->defl_terms_key[3] = D.nty;
-        c->defl_tw = tw;
-    }
     double* d_einv = c->d_defl;
     double* d_mu = d_einv + (size_t)D.k * D.k;
     double* d_nu = d_mu + FT_KMAX;
-    double* d_F = d_nu + FT_KMAX;
-    double* d_W = d_F + (size_t)ntiles * FS_STRIDE;
+    double* d_W = d_nu + (1 + FB_PLANES) * (size_t)FT_KMAX;
     double* h_einv = c->h_defl;
     double* h_W = h_einv + (size_t)D.k * D.k;
     if (g.lattice == LAT_SQUARE) defl_weights_kernel<LAT_SQUARE, C><<<ntiles, 64, 0, s>>>(g, prm, c->cfull, D.ntx, d_W);
@@ -1385,7 +1366,14 @@ static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
     const Geom& g = c->g;
     cudaStream_t s = c->stream;
     const int ntx = (g.m + C::TX - 1) / C::TX, ntiles = ntx * ((g.n + C::TY - 1) / C::TY);
-    const int grid = ntiles < C::CTAS * c->num_sms ? ntiles : C::CTAS * c->num_sms;
+    // the order in which the tiles are visited: block by block (FtWalk); without deflation every tile is a block
+    FtDeflDev dd{};
+    if (C::DEFL) {
+        int bw = 0, bh = 0;
+        if (const char* e = getenv("PERC_DEFL_BLOCK")) sscanf(e, "%d,%d", &bw, &bh);      // tiles per block (experiments)
+        dd.D = ft_defl_make(g, C::TX, C::TY, FT_KMAX, bw, bh);
+    } else dd.D = ft_defl_make(g, C::TX, C::TY, 0, 1, 1);
+    const int grid = dd.D.k < C::CTAS * c->num_sms ? dd.D.k : C::CTAS * c->num_sms;
     if (!c->xprow) PERC_CUDA(cudaMalloc(&c->xprow, sizeof(double) * 4 * g.m));
     PERC_CUDA(cudaMemsetAsync(c->xprow, 0, sizeof(double) * 4 * g.m, s));
     PERC_CUDA(cudaMemsetAsync(c->vp2, 0, sizeof(double) * g.t, s));
@@ -1402,26 +1390,19 @@ static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
     }
     rc = make_tensor_map(&tm_cf, c->cfull, 1, g.m, g.n, C::CLD, C::RR); if (rc) return rc;
     double* xrow = c->xprow; double* prow = c->xprow + 2 * (size_t)g.m;
-    FtDeflDev dd{};
     if (C::DEFL) {
-        int bw = 0, bh = 0;
-        if (const char* e = getenv("PERC_DEFL_BLOCK")) sscanf(e, "%d,%d", &bw, &bh);      // tiles per block (experiments)
-        dd.D = ft_defl_make(g, C::TX, C::TY, FT_KMAX, bw, bh);
         rc = pcg_defl_setup<C>(c, prm, dd.D, ntiles, xrow); if (rc) return rc;
-        dd.Einv = c->d_defl; dd.mu = c->d_defl + (size_t)dd.D.k * dd.D.k; dd.F = dd.mu + 2 * FT_KMAX;
-        dd.tptr = c->d_defl_terms; dd.tent = c->d_defl_terms + FT_KMAX + 1; dd.tw = c->defl_tw;
-        dd.fglob = dd.mu + FT_KMAX;                      // (nu is dead once defl_init_kernel has run)
-        if (dd.tw > 0 && ((dd.D.k + grid - 1) / grid) * dd.tw > 256) dd.tw = 0;     // more blocks per CTA than the staged lists hold
+        dd.Einv = c->d_defl; dd.mu = c->d_defl + (size_t)dd.D.k * dd.D.k; dd.Fb = dd.mu + 2 * FT_KMAX;
         if ((dd.D.k + grid - 1) / grid > 32) return (int)cudaErrorInvalidConfiguration;   // (k <= 1024 and grid >= 32 SMs)
         c->defl_k = dd.D.k;
     }
     int cur = 0, pass = 0;
     Geom garg = g; PcgParams parg = prm;
     auto launch = [&](int prime) -> cudaError_t {
-        int rev = pass & 1, ntx_ = ntx, ntiles_ = ntiles;
+        int rev = pass & 1;
         double* ro = rbuf[cur ^ 1]; double* so = sbuf[cur ^ 1];
         void* args[] = {&tm_r[cur], &tm_s[cur], &tm_cf, &garg, &parg, &ro, &so, &xrow, &prow, &c->partial, &c->d_pcg,
-                        &ntx_, &ntiles_, &rev, &prime, &dd};
+                        &rev, &prime, &dd};
         const void* fn = g.lattice == LAT_SQUARE ? (const void*)pcg_fused_kernel<LAT_SQUARE, C> : (const void*)pcg_fused_kernel<LAT_TRIANGULAR, C>;
         // the deflated sweep ends with a grid-wide stage: cooperative launch (all CTAs resident: one per SM)
         cudaError_t e = C::DEFL ? cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(C::THREADS), args, C::SMEM, s)

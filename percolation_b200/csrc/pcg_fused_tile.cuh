@@ -58,10 +58,13 @@ struct FtCfg {
     static constexpr bool USTATE = V >= 3;
     static constexpr bool DEFL = V >= 5;                    // deflated iteration (block-constant coarse space, see FtDefl)
     static constexpr int U_BYTES = USTATE ? 0 : R_BYTES;    // shared u array of phase U
-    static constexpr int SHIFT_BYTES = DEFL ? 2 * RR * 4 * 8 : 0;         // per staged row: mu of the west / own / east block (two tiles in flight)
+    static constexpr int SFT_N = RR * 4, REC_N = CR * 8;    // shift table (mu per staged row and block column) and its per-row records
+    static constexpr int SHIFT_BYTES = DEFL ? 2 * (SFT_N + REC_N) * 8 : 0;               // two tiles in flight
     static constexpr int RHO_BYTES = DEFL ? NPAT_TRI * (DC / 2) * 8 : 0;                 // rho per table slot
-    static constexpr int COARSE_BYTES = DEFL ? FT_KMAX * 8 + 256 * 8 + 64 * 8 + 256 * 4 + RHO_BYTES : 0; // mu / Z^T A u' of every block, crossing currents per warp and slot, term lists
-    static constexpr int SMEM = 2 * STAGE_BYTES + U_BYTES + TAB_BYTES + 96 * 8 + 16 + 64 * 8 + SHIFT_BYTES + COARSE_BYTES;
+    // mu / Z^T A u' of every block, row partials of the coarse product (+ scratch), rho u' per main thread, slot totals of a
+    // tile and the running sums of its block
+    static constexpr int COARSE_BYTES = DEFL ? FT_KMAX * 8 + 256 * 8 + THREADS * 8 + 16 * 8 + RHO_BYTES : 0;
+    static constexpr int SMEM = 2 * STAGE_BYTES + U_BYTES + TAB_BYTES + 96 * 8 + 16 + 64 * 8 + 4 * 16 + SHIFT_BYTES + COARSE_BYTES;
     // table of diagonals of the sites with ALL their neighbours, indexed by which of them conduct (ft_pat: 16 patterns on
     // the square lattice, 2 x 64 on the triangular one) -- the diagonal depends on the pattern, not only on the counts: it is
     // the reference's sum in ascending neighbour order (diag_seq).  Private copies per lane: 32 (square) / 16 (triangular).
@@ -188,17 +191,18 @@ struct FtDefl {
 // Z^T A u' that is not a current between blocks; in the weight pass (UNIT) the sum of rho_i itself: the entry it adds to E
 enum : int { FS_E = 0, FS_N = 1, FS_W = 2, FS_NW = 3, FS_D = 4, FS_R = 5, FS_SLOTS = 6, FS_STRIDE = 8 };
 
-// blocks start at about TX x TX sites and grow (the shorter side first) until the coarse dimension fits
+// blocks start as single tiles and grow (towards square blocks) until the coarse dimension fits; kmax <= 0: no limit
+// (the kernels without deflation walk the lattice with bw = bh = 1: block = tile)
 PERC_HD FtDefl ft_defl_make(const Geom& g, int TX, int TY, int kmax, int bw0 = 0, int bh0 = 0)
 {
     FtDefl D;
     D.ntx = (g.m + TX - 1) / TX; D.nty = (g.n + TY - 1) / TY;
-    D.bw = bw0 > 0 ? bw0 : 1; D.bh = bh0 > 0 ? bh0 : (TX / TY > 0 ? TX / TY : 1);
+    D.bw = bw0 > 0 ? bw0 : 1; D.bh = bh0 > 0 ? bh0 : 1;
     for (;;) {
         D.nbx = (D.ntx + D.bw - 1) / D.bw; D.nby = (D.nty + D.bh - 1) / D.bh;
         D.k = D.nbx * D.nby;
-        if (D.k <= kmax) break;
-        if (D.bw * TX <= D.bh * TY) D.bw *= 2; else D.bh *= 2;
+        if (kmax <= 0 || D.k <= kmax) break;
+        if (D.bw * TX < D.bh * TY) D.bw *= 2; else D.bh *= 2;
     }
     return D;
 }
@@ -223,26 +227,87 @@ PERC_HD double ft_defl_shift_entry(const Geom& g, const FtDefl& D, const double*
 }
 // class of a staged column (column c <-> gx = x0 - 2 + c)
 template <class C> PERC_HD int ft_defl_cls(int col) { return col < 2 ? 0 : (col >= 2 + C::TX ? 2 : 1); }
+// entry e of the record of compute row lr, from the tile's shift table: 0 mu of the row's own sites, then mu minus the mu of
+// the neighbour to the 1 north, 2 south, (3: always 0) 4 west, 5 east, 6 north-west across the west border, 7 south-east
+// across the east border -- what ft_phase_main adds to the neighbours' values
+template <class C>
+PERC_HD double ft_defl_rec_entry(const double* sft, int lr, int e)
+{
+    const double mc = sft[(lr + 1) * 4 + 1];
+    switch (e) {
+    case 0: return mc;
+    case 1: return mc - sft[(lr + 2) * 4 + 1];
+    case 2: return mc - sft[lr * 4 + 1];
+    case 4: return mc - sft[(lr + 1) * 4 + 0];
+    case 5: return mc - sft[(lr + 1) * 4 + 2];
+    case 6: return mc - sft[(lr + 2) * 4 + 0];
+    case 7: return mc - sft[lr * 4 + 2];
+    default: return 0.0;
+    }
+}
 
-// Z^T (A u') of block B from the per-tile crossing currents F[tile][slot] (fixed order: bit-reproducible)
-PERC_HD double ft_defl_assemble(const FtDefl& D, const double* F, int B)
+// The order in which a CTA visits the lattice: block by block (block bid, bid + G, ...), the tiles of a block one after the
+// other, so that the crossing currents of a block are summed by the CTA that owns it; rev: the same sequence backwards
+// (consecutive iterations sweep in opposite directions: each starts on what L2 still holds).
+struct FtWalk {
+    int B, bx, by, w, h, jx, jy;
+    PERC_HD bool valid(const FtDefl& D) const { return B >= 0 && B < D.k; }
+    PERC_HD void enter(const FtDefl& D, int rev)
+    {
+        bx = B % D.nbx; by = B / D.nbx;
+        w = D.ntx - bx * D.bw < D.bw ? D.ntx - bx * D.bw : D.bw;
+        h = D.nty - by * D.bh < D.bh ? D.nty - by * D.bh : D.bh;
+        jx = rev ? w - 1 : 0; jy = rev ? h - 1 : 0;
+    }
+    PERC_HD void start(const FtDefl& D, int bid, int G, int rev)
+    {
+        B = bid < D.k ? (rev ? bid + ((D.k - 1 - bid) / G) * G : bid) : -1;
+        if (valid(D)) enter(D, rev);
+    }
+    PERC_HD void next(const FtDefl& D, int G, int rev)
+    {
+        if (!rev) { if (++jx == w) { jx = 0; if (++jy == h) { B += G; if (valid(D)) enter(D, 0); } } }
+        else      { if (--jx < 0) { jx = w - 1; if (--jy < 0) { B -= G; if (valid(D)) enter(D, 1); } } }
+    }
+    PERC_HD int ix(const FtDefl& D) const { return bx * D.bw + jx; }
+    PERC_HD int iy(const FtDefl& D) const { return by * D.bh + jy; }
+    // which of the tile's slots leave the block, and whether the tile is the first / last of its block in walking order
+    PERC_HD int info(const FtDefl& D, int rev) const
+    {
+        const int x = bx * D.bw + jx, y = by * D.bh + jy;
+        const int cE = jx == w - 1 && x + 1 < D.ntx, cN = jy == h - 1 && y + 1 < D.nty, cW = jx == 0 && x >= 1;
+        const int nwx = jx == 0, nwy = jy == h - 1, cNW = x >= 1 && y + 1 < D.nty && (nwx | nwy);
+        const int first = rev ? (jx == w - 1 && jy == h - 1) : (jx == 0 && jy == 0), last = rev ? (jx == 0 && jy == 0) : (jx == w - 1 && jy == h - 1);
+        return cE | cN << 1 | cW << 2 | cNW << 3 | (nwx & cNW) << 4 | (nwy & cNW) << 5 | first << 6 | last << 7;
+    }
+};
+enum : int { FW_E = 1, FW_N = 2, FW_W = 4, FW_NW = 8, FW_NWX = 16, FW_NWY = 32, FW_FIRST = 64, FW_LAST = 128 };
+// running sums of a block: what leaves it altogether, and what enters the block to the east / north / west / north-west
+enum : int { FB_OUT = 0, FB_E = 1, FB_N = 2, FB_W = 3, FB_NW = 4, FB_PLANES = 5 };
+
+// slot totals ts[FS_*] of one tile into the running sums of its block (info: FtWalk::info of the tile)
+PERC_HD void ft_defl_block_add(int info, const double* ts, double* acc)
+{
+    double out = ts[FS_D] + ts[FS_R];
+    if (info & FW_E) { out += ts[FS_E]; acc[FB_E] += ts[FS_E]; }
+    if (info & FW_N) { out += ts[FS_N]; acc[FB_N] += ts[FS_N]; }
+    if (info & FW_W) { out += ts[FS_W]; acc[FB_W] += ts[FS_W]; }
+    if (info & FW_NW) { out += ts[FS_NW]; acc[(info & FW_NWX) ? ((info & FW_NWY) ? FB_NW : FB_W) : FB_N] += ts[FS_NW]; }
+    acc[FB_OUT] += out;
+}
+// Z^T (A u') of block B -- the net current leaving it -- from the block sums Fb[plane * FT_KMAX + block]
+PERC_HD double ft_defl_block_f(const FtDefl& D, const double* Fb, int B)
 {
     const int bx = B % D.nbx, by = B / D.nbx;
-    const int dx[4] = {1, 0, -1, -1}, dy[4] = {0, 1, 0, 1};     // FS_E, FS_N, FS_W, FS_NW
-    double acc = 0.0;
-    for (int iy = by * D.bh; iy < (by + 1) * D.bh && iy < D.nty; ++iy)
-        for (int ix = bx * D.bw; ix < (bx + 1) * D.bw && ix < D.ntx; ++ix) {
-            const int tl = iy * D.ntx + ix;
-            acc += FT_LDCG(&F[tl * FS_STRIDE + FS_D]);
-            acc += FT_LDCG(&F[tl * FS_STRIDE + FS_R]);
-            for (int s = 0; s < 4; ++s) {
-                int jx = ix + dx[s], jy = iy + dy[s];                 // current leaving through slot s
-                if (jx >= 0 && jx < D.ntx && jy < D.nty && ft_defl_block(D, jx, jy) != B) acc += FT_LDCG(&F[tl * FS_STRIDE + s]);
-                jx = ix - dx[s]; jy = iy - dy[s];                     // current entering from the tile whose slot s points here
-                if (jx >= 0 && jx < D.ntx && jy >= 0 && ft_defl_block(D, jx, jy) != B) acc -= FT_LDCG(&F[(jy * D.ntx + jx) * FS_STRIDE + s]);
-            }
-        }
-    return acc;
+    // (five independent loads: the addresses are clamped, the values selected afterwards)
+    const bool he = bx > 0, hn = by > 0, hw = bx + 1 < D.nbx, hnw = hw && hn;
+    const double o = FT_LDCG(&Fb[FB_OUT * FT_KMAX + B]);
+    double e = FT_LDCG(&Fb[FB_E * FT_KMAX + (he ? B - 1 : B)]);
+    double n = FT_LDCG(&Fb[FB_N * FT_KMAX + (hn ? B - D.nbx : B)]);
+    double w = FT_LDCG(&Fb[FB_W * FT_KMAX + (hw ? B + 1 : B)]);
+    double nw = FT_LDCG(&Fb[FB_NW * FT_KMAX + (hnw ? B - D.nbx + 1 : B)]);
+    e = he ? e : 0.0; n = hn ? n : 0.0; w = hw ? w : 0.0; nw = hnw ? nw : 0.0;
+    return (((o - e) - n) - w) - nw;
 }
 
 // one work item q of a tile's crossing currents: the E bonds of its east column, the N / NE / NW bonds of its top row,
@@ -339,41 +404,26 @@ struct FtGlobalAcc {
     PERC_HD double u(int, int) const { return 0.0; }
 };
 
-// crossing currents of a tile: thread tid < FtFluxItems::N takes work item tid, partial sums into f[FS_SLOTS]
+// crossing currents of a tile by the 64 ring threads (rl = 0 .. 63) while the others sum the bond energies.  Every slot has ONE
+// producer warp: the first takes the east column (FS_E), the west column (FS_W, triangular), the bonds into the Dirichlet
+// rows (FS_D) and sum rho u' (FS_R: the per-thread sums the main threads left in sru); the second the top row (FS_N, FS_NW).
+// Partial sums of this thread into f[FS_SLOTS]; the caller folds the lanes of each warp.
 template <int LAT, class C>
-PERC_HD void ft_phase_flux(const Geom& g, const FtScalars& sc, const double* ss, const uint8_t* scf, int x0, int y0, int tid, double* f,
-                           bool interior = false)
+PERC_HD void ft_flux_thread(const Geom& g, const FtScalars& sc, const double* ss, const uint8_t* scf, const double* sru, int x0, int y0,
+                            int rl, bool interior, double* f)
 {
-    if (tid >= FtFluxItems<C>::N) return;
     const FtStageAcc<C> a{ss, scf, x0, y0};
-    ft_flux_item<LAT, C, false>(g, sc.g0, sc.gleak, a, x0, y0, tid, f, interior);
-}
-
-// The terms of Z^T (A u') of every block as a static list (CSR over the blocks: ptr[k + 1], ent[]): entry = (tile * FS_STRIDE
-// + slot) << 1 | (1 if the current ENTERS the block).  Same terms in the same order as ft_defl_assemble; built once per
-// lattice shape on the host, walked by one warp per block on the device.
-template <class Vec>
-inline void ft_defl_terms(const FtDefl& D, Vec& ptr, Vec& ent)
-{
-    const int dx[4] = {1, 0, -1, -1}, dy[4] = {0, 1, 0, 1};
-    ptr.clear(); ent.clear();
-    for (int B = 0; B < D.k; ++B) {
-        ptr.push_back((int)ent.size());
-        const int bx = B % D.nbx, by = B / D.nbx;
-        for (int iy = by * D.bh; iy < (by + 1) * D.bh && iy < D.nty; ++iy)
-            for (int ix = bx * D.bw; ix < (bx + 1) * D.bw && ix < D.ntx; ++ix) {
-                const int tl = iy * D.ntx + ix;
-                ent.push_back((tl * FS_STRIDE + FS_D) << 1);
-                ent.push_back((tl * FS_STRIDE + FS_R) << 1);
-                for (int s = 0; s < 4; ++s) {
-                    int jx = ix + dx[s], jy = iy + dy[s];
-                    if (jx >= 0 && jx < D.ntx && jy < D.nty && ft_defl_block(D, jx, jy) != B) ent.push_back((tl * FS_STRIDE + s) << 1);
-                    jx = ix - dx[s]; jy = iy - dy[s];
-                    if (jx >= 0 && jx < D.ntx && jy >= 0 && ft_defl_block(D, jx, jy) != B) ent.push_back((((jy * D.ntx + jx) * FS_STRIDE + s) << 1) | 1);
-                }
-            }
+    const int l = rl & 31;
+    if (rl < 32) {
+        for (int q = l; q < C::TY; q += 32) ft_flux_item<LAT, C, false>(g, sc.g0, sc.gleak, a, x0, y0, q, f, interior);
+        if (LAT == LAT_TRIANGULAR)
+            for (int q = C::TY + C::TX + l; q < 2 * C::TY + C::TX; q += 32) ft_flux_item<LAT, C, false>(g, sc.g0, sc.gleak, a, x0, y0, q, f, interior);
+        if (!interior && (y0 <= 1 || y0 + C::TY >= g.n - 2))
+            for (int q = 2 * C::TY + C::TX + l; q < FtFluxItems<C>::N; q += 32) ft_flux_item<LAT, C, false>(g, sc.g0, sc.gleak, a, x0, y0, q, f, false);
+        for (int j = l; j < C::MAIN_THREADS; j += 32) f[FS_R] += sru[j];
+    } else {
+        for (int q = C::TY + l; q < C::TY + C::TX; q += 32) ft_flux_item<LAT, C, false>(g, sc.g0, sc.gleak, a, x0, y0, q, f, interior);
     }
-    ptr.push_back((int)ent.size());
 }
 
 // deflated start: x0 = Z nu with E nu = Z^T b; returns u0 = D^-1 (b - A Z nu) of the unknown site (x, y) (cf: its conduct
@@ -447,7 +497,7 @@ template <int LAT, class C, bool INT>
 PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr, double* ss, const uint8_t* scf,
                            const double* su, const FtDiag* dtab, const double* cinv, int x0, int y0, bool interior_flag, int tid,
                            double* __restrict__ r_out, double* __restrict__ s_out, double* __restrict__ xrow,
-                           double* __restrict__ prow, double& acc_rz, double& acc_rr, const double* sft = nullptr,
+                           double* __restrict__ prow, double& acc_rz, double& acc_rr, const double* srec = nullptr,
                            const double* rtab = nullptr, double* acc_ru = nullptr)
 {
     if (tid >= C::MAIN_THREADS) return;
@@ -457,9 +507,6 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
     const int gx = x0 + 2 * tx, lr0 = ty * C::RPT;
     const double alpha = sc.alpha, beta = sc.beta;
     const double* c = &su[(lr0 + 1) * C::LD + 2 + 2 * tx];
-    // deflation: sft[pr * 4 + class] = mu of staged row pr, block column west / own / east (0 on rows that are not
-    // unknowns).  The first and the last thread of a tile row look across the tile's west / east border.
-    const int selL = tx == 0 ? 0 : 1, selR = tx == 63 ? 2 : 1;
     ft_d2 dn = ft_ld2(c - C::LD), cc = ft_ld2(c);
     double drt = c[-C::LD + 2];                              // row below, x+2: SE neighbour of the odd column
 #if defined(__CUDA_ARCH__)
@@ -473,30 +520,52 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
         const bool valid = interior || (gy >= 1 && gy <= g.n - 2 && gx < g.m);
         const unsigned c01 = *reinterpret_cast<const unsigned short*>(&scf[(lr + 1) * C::CLD + 16 + 2 * tx]);
         unsigned cf0 = c01 & 0xffu, cf1 = c01 >> 8;
+        // the neighbours' values as the two sites see them
+        double vE0 = cc.y, vW0 = lf, vN0 = up.x, vS0 = dn.x, vE1 = rt, vW1 = cc.x, vN1 = up.y, vS1 = dn.y;
+        double vNW0 = nw, vNE0 = up.y, vSW1 = dn.x, vSE1 = drt;
+        double mc = 0.0;
+        if (C::DEFL) {
+            // minus (A Z mu)_i = rho_i mu_i + sum_j w_ij (mu_i - mu_j): every neighbour j enters the stencil as u_j + (mu_i - mu_j).
+            // The differences vanish unless the bond crosses a block border or ends on a Dirichlet row (mu = 0 there), so
+            // nothing is added -- and nothing rounded -- in the interior of a block.  Record of the row (ft_defl_rec_entry):
+            // mu, the north / south differences (uniform over the row), west / east (first / last thread of the row only).
+            const double* rec = srec + lr * 8;
+            const ft_d2 m01 = ft_ld2(rec);
+            mc = m01.x;
+            const double dN = m01.y, dS = rec[2];
+            vW0 += rec[tx == 0 ? 4 : 3]; vE1 += rec[tx == 63 ? 5 : 3];
+            vN0 += dN; vN1 += dN; vS0 += dS; vS1 += dS;
+            if (LAT == LAT_TRIANGULAR) {
+                // up-type column: NW -> (x-1, y+1), NE -> (x+1, y+1) (the thread's own second column); down-type column:
+                // SW -> (x-1, y-1) (the thread's first column), SE -> (x+1, y-1)
+                vNW0 += tx == 0 ? rec[6] : dN; vNE0 += dN;
+                vSW1 += dS; vSE1 += tx == 63 ? rec[7] : dS;
+            }
+        }
         unsigned e0, e1;
         double all0, all1;
         if (interior) {
             e0 = ft_interior_ex<LAT>(gx); e1 = ft_interior_ex<LAT>(gx + 1);
-            all0 = (cc.y + lf) + (up.x + dn.x);
-            all1 = (rt + cc.x) + (up.y + dn.y);
-            if (LAT == LAT_TRIANGULAR) { all0 += nw + up.y; all1 += dn.x + drt; }
+            all0 = (vE0 + vW0) + (vN0 + vS0);
+            all1 = (vE1 + vW1) + (vN1 + vS1);
+            if (LAT == LAT_TRIANGULAR) { all0 += vNW0 + vNE0; all1 += vSW1 + vSE1; }
         } else {
             e0 = valid ? neighbour_bits(g, gx, gy) : 0u; e1 = valid ? neighbour_bits(g, gx + 1, gy) : 0u;
             cf0 &= e0; cf1 &= e1;
             all0 = 0.0; all1 = 0.0;
-            if (e0 & NB_E) all0 += cc.y;  if (e0 & NB_W) all0 += lf;   if (e0 & NB_N) all0 += up.x;  if (e0 & NB_S) all0 += dn.x;
-            if (e1 & NB_E) all1 += rt;    if (e1 & NB_W) all1 += cc.x; if (e1 & NB_N) all1 += up.y;  if (e1 & NB_S) all1 += dn.y;
+            if (e0 & NB_E) all0 += vE0;  if (e0 & NB_W) all0 += vW0; if (e0 & NB_N) all0 += vN0;  if (e0 & NB_S) all0 += vS0;
+            if (e1 & NB_E) all1 += vE1;  if (e1 & NB_W) all1 += vW1; if (e1 & NB_N) all1 += vN1;  if (e1 & NB_S) all1 += vS1;
             if (LAT == LAT_TRIANGULAR) {
-                if (e0 & NB_NW) all0 += nw; if (e0 & NB_NE) all0 += up.y;
-                if (e1 & NB_SW) all1 += dn.x;         if (e1 & NB_SE) all1 += drt;
+                if (e0 & NB_NW) all0 += vNW0; if (e0 & NB_NE) all0 += vNE0;
+                if (e1 & NB_SW) all1 += vSW1; if (e1 & NB_SE) all1 += vSE1;
             }
         }
         double con0 = 0.0, con1 = 0.0;                       // conducting neighbours
-        ft_padd(con0, cc.y, cf0 & NB_E); ft_padd(con0, lf, cf0 & NB_W);   ft_padd(con0, up.x, cf0 & NB_N); ft_padd(con0, dn.x, cf0 & NB_S);
-        ft_padd(con1, rt, cf1 & NB_E);   ft_padd(con1, cc.x, cf1 & NB_W); ft_padd(con1, up.y, cf1 & NB_N); ft_padd(con1, dn.y, cf1 & NB_S);
+        ft_padd(con0, vE0, cf0 & NB_E); ft_padd(con0, vW0, cf0 & NB_W); ft_padd(con0, vN0, cf0 & NB_N); ft_padd(con0, vS0, cf0 & NB_S);
+        ft_padd(con1, vE1, cf1 & NB_E); ft_padd(con1, vW1, cf1 & NB_W); ft_padd(con1, vN1, cf1 & NB_N); ft_padd(con1, vS1, cf1 & NB_S);
         if (LAT == LAT_TRIANGULAR) {
-            ft_padd(con0, nw, cf0 & NB_NW); ft_padd(con0, up.y, cf0 & NB_NE);
-            ft_padd(con1, dn.x, cf1 & NB_SW);         ft_padd(con1, drt, cf1 & NB_SE);
+            ft_padd(con0, vNW0, cf0 & NB_NW); ft_padd(con0, vNE0, cf0 & NB_NE);
+            ft_padd(con1, vSW1, cf1 & NB_SW); ft_padd(con1, vSE1, cf1 & NB_SE);
         }
         // (gx is even: the thread's first column is an up-type site on the triangular lattice, its second a down-type one)
         const int i0 = C::tabp(LAT, ft_pat<LAT>(cf0, 0), lane), i1 = C::tabp(LAT, ft_pat<LAT>(cf1, 1), lane);
@@ -508,29 +577,11 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
         // a bond weight the diagonal does not contain
         double w0 = t0.d * cc.x - (sc.g0 * con0 + sc.gleak * (all0 - con0));
         double w1 = t1.d * cc.y - (sc.g0 * con1 + sc.gleak * (all1 - con1));
-        double mc = 0.0, rho0 = 0.0, rho1 = 0.0;
+        double rho0 = 0.0, rho1 = 0.0;
         if (C::DEFL) {
-            // minus (A Z mu)_i = rho_i mu_i + sum_j w_ij (mu_i - mu_j): the differences vanish unless the bond crosses a block
-            // border or ends on a Dirichlet row (mu = 0 there).  North / south differences are uniform over the warp.
-            mc = sft[(lr + 1) * 4 + 1];
-            const double dN = mc - sft[(lr + 2) * 4 + 1], dS = mc - sft[lr * 4 + 1];
-            const double dW = mc - sft[(lr + 1) * 4 + selL], dE = mc - sft[(lr + 1) * 4 + selR];
             if (full0) rho0 = rtab[i0]; else diag_seq_rho(g, cf0, e0, gx, sc.g0, sc.gleak, &rho0);
             if (full1) rho1 = rtab[i1]; else diag_seq_rho(g, cf1, e1, gx + 1, sc.g0, sc.gleak, &rho1);
-#define FT_WB(cf, e, bit) (((e) & (bit)) ? (((cf) & (bit)) ? sc.g0 : sc.gleak) : 0.0)
-            double k0 = rho0 * mc + FT_WB(cf0, e0, NB_W) * dW, k1 = rho1 * mc + FT_WB(cf1, e1, NB_E) * dE;
-            if (dN != 0.0 || dS != 0.0) {
-                k0 += FT_WB(cf0, e0, NB_N) * dN + FT_WB(cf0, e0, NB_S) * dS;
-                k1 += FT_WB(cf1, e1, NB_N) * dN + FT_WB(cf1, e1, NB_S) * dS;
-            }
-            if (LAT == LAT_TRIANGULAR) {
-                // up-type column: NW -> (x-1, y+1), NE -> (x+1, y+1) (the thread's own second column); down-type column:
-                // SW -> (x-1, y-1) (the thread's first column), SE -> (x+1, y-1)
-                k0 += FT_WB(cf0, e0, NB_NW) * (mc - sft[(lr + 2) * 4 + selL]) + FT_WB(cf0, e0, NB_NE) * dN;
-                k1 += FT_WB(cf1, e1, NB_SW) * dS + FT_WB(cf1, e1, NB_SE) * (mc - sft[lr * 4 + selR]);
-            }
-#undef FT_WB
-            w0 -= k0; w1 -= k1;
+            w0 -= rho0 * mc; w1 -= rho1 * mc;
         }
         double* sp = &ss[lr * C::LD + 2 + 2 * tx];
         const ft_d2 s2 = ft_ld2(sp), r2 = ft_ld2(&sr[(lr + 1) * C::LD + 2 + 2 * tx]);
@@ -581,12 +632,12 @@ PERC_HD void ft_phase_ringcols(const Geom& g, const FtScalars& sc, const double*
         const unsigned ex = interior ? ft_interior_ex<LAT>(gx) : neighbour_bits(g, gx, gy);
         const unsigned cf = scf[(lr + 1) * C::CLD + (side ? 16 + C::TX : 15)] & ex;
         const double* c = &su[(lr + 1) * C::LD + col];
-        double all = 0.0, con = 0.0, kz = 0.0;
-        // (deflation: minus (A Z mu)_i as in ft_phase_main; mu of a neighbour from the shift table by its row and block column)
+        double all = 0.0, con = 0.0;
+        // (deflation: as in ft_phase_main, neighbour j enters as u_j + (mu_i - mu_j); mu from the shift table by row and block column)
         const double mi = C::DEFL ? sft[(lr + 1) * 4 + ft_defl_cls<C>(col)] : 0.0;
-#define FT_NB(bit, dc, dr) if (interior || (ex & bit)) { const double v = c[(dr) * C::LD + (dc)]; all += v; if (cf & bit) con += v; \
-                                           if (C::DEFL) { const double dm = mi - sft[(lr + 1 + (dr)) * 4 + ft_defl_cls<C>(col + (dc))]; \
-                                                          if (dm != 0.0) kz += ((cf & bit) ? sc.g0 : sc.gleak) * dm; } }
+#define FT_NB(bit, dc, dr) if (interior || (ex & bit)) { double v = c[(dr) * C::LD + (dc)]; \
+                                           if (C::DEFL) v += mi - sft[(lr + 1 + (dr)) * 4 + ft_defl_cls<C>(col + (dc))]; \
+                                           all += v; if (cf & bit) con += v; }
         FT_NB(NB_E, 1, 0) FT_NB(NB_W, -1, 0) FT_NB(NB_N, 0, 1) FT_NB(NB_S, 0, -1)
         if (LAT == LAT_TRIANGULAR) {
             if (gx & 1) { FT_NB(NB_SW, -1, -1) FT_NB(NB_SE, 1, -1) } else { FT_NB(NB_NW, -1, 1) FT_NB(NB_NE, 1, 1) }
@@ -600,7 +651,7 @@ PERC_HD void ft_phase_ringcols(const Geom& g, const FtScalars& sc, const double*
         if (C::DEFL) {
             double rho;
             if (full) rho = rtab[it]; else diag_seq_rho(g, cf, ex, gx, sc.g0, sc.gleak, &rho);
-            w -= rho * mi + kz;
+            w -= rho * mi;
         }
         const double sn = w + sc.beta * ss[lr * C::LD + col];
         if (C::USTATE) un = c[0] - sc.alpha * (sn * t.inv);

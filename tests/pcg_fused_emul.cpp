@@ -146,7 +146,7 @@ int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double 
     *coarse_dim = D.k;
     const int ntiles = D.ntx * D.nty;
     // E from the crossing bond weights, dense inverse
-    std::vector<double> W((size_t)ntiles * FS_STRIDE, 0.0), Einv((size_t)D.k * D.k), F((size_t)ntiles * FS_STRIDE, 0.0);
+    std::vector<double> W((size_t)ntiles * FS_STRIDE, 0.0), Einv((size_t)D.k * D.k), Fb((size_t)FB_PLANES * FT_KMAX, 0.0);
     const FtGlobalAcc ga{cf.data(), m};
     for (int tl = 0; tl < ntiles; ++tl)
         for (int q = 0; q < FtFluxItems<C>::N; ++q)
@@ -158,8 +158,6 @@ int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double 
             W[(size_t)((y / C::TY) * D.ntx + x / C::TX) * FS_STRIDE + FS_R] += rho;
         }
     if (ft_defl_build_einv(D, W.data(), Einv.data(), 2)) return -4;
-    std::vector<int> tptr, tent;
-    ft_defl_terms(D, tptr, tent);
     // x0 = Z nu, E nu = Z^T b; u0 = D^-1 (b - A Z nu)
     std::vector<double> r[2], s[2], xrow((size_t)2 * m, 0.0), prow((size_t)2 * m, 0.0), fb((size_t)D.k, 0.0), nu((size_t)D.k, 0.0), mu((size_t)D.k, 0.0);
     for (int k = 0; k < 2; ++k) { r[k].assign((size_t)t, 0.0); s[k].assign((size_t)t, 0.0); }
@@ -194,7 +192,7 @@ int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double 
     for (int k = 0; k < ft_tab_slots<LAT, C>(); ++k) dtab[k] = ft_tab_slot<LAT, C>(g, k, g0, gleak);
     std::vector<double> cinv(64);
     for (int k = 0; k < 64; ++k) cinv[k] = ft_cinv_entry(k, g0, gleak);
-    std::vector<double> sr((size_t)C::RR * C::LD), ss((size_t)C::SR * C::LD), sft((size_t)C::RR * 4), rtab((size_t)ft_tab_slots<LAT, C>());
+    std::vector<double> sr((size_t)C::RR * C::LD), ss((size_t)C::SR * C::LD), sft((size_t)C::SFT_N), srec((size_t)C::REC_N), sru((size_t)C::THREADS), rtab((size_t)ft_tab_slots<LAT, C>());
     for (int k = 0; k < ft_tab_slots<LAT, C>(); ++k) rtab[k] = ft_rho_slot<LAT, C>(g, k, g0, gleak);
     std::vector<uint8_t> scf((size_t)C::RR * C::CLD);
     int cur = 0;
@@ -209,34 +207,43 @@ int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double 
                 xfull[q] += sc.alpha * pfull[q];
             }
         double rz = 0.0, rr = 0.0, en = 0.0;
-        for (int tl = 0; tl < ntiles; ++tl) {
-            const int ix = tl % D.ntx, iy = tl / D.ntx, x0 = ix * C::TX, y0 = iy * C::TY;
-            box_copy(sr.data(), r[cur].data(), m, n, x0 - 2, y0 - 1, C::LD, C::RR);
-            box_copy(ss.data(), s[cur].data(), m, n, x0 - 2, y0, C::LD, C::SR);
-            box_copy(scf.data(), cf.data(), m, n, x0 - 16, y0 - 1, C::CLD, C::RR);
-            for (int j = 0; j < C::RR * 4; ++j) sft[j] = (j & 3) == 3 ? NAN : ft_defl_shift_entry<C>(g, D, mu.data(), ix, iy, j >> 2, j & 3);
-            const bool interior = ft_interior<C>(g, x0, y0);
-            double ru = 0.0;
-            for (int tid = C::THREADS - 1; tid >= 0; --tid) {
-                EMUL_MAIN(g, sc, sr.data(), ss.data(), scf.data(), sr.data(), dtab.data(), cinv.data(), x0, y0, interior, tid,
-                                             r[cur ^ 1].data(), s[cur ^ 1].data(), xrow.data(), prow.data(), rz, rr, sft.data(), rtab.data(), &ru);
-                EMUL_RING(g, sc, sr.data(), ss.data(), scf.data(), sr.data(), dtab.data(), cinv.data(), x0, y0, tid, sft.data(), rtab.data());
+        // the kernel's walk (FtWalk) as a grid of GRID CTAs runs it, forwards and backwards in turn: block by block, the slot
+        // totals of a tile folded into the running sums of its block, which go out with the block's last tile
+        const int GRID = 5, rev = pass & 1;
+        for (int bid = 0; bid < GRID; ++bid) {
+            FtWalk wk;
+            double bacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (wk.start(D, bid, GRID, rev); wk.valid(D); wk.next(D, GRID, rev)) {
+                const int ix = wk.ix(D), iy = wk.iy(D), x0 = ix * C::TX, y0 = iy * C::TY, info = wk.info(D, rev);
+                if (ft_defl_block(D, ix, iy) != wk.B) return -6;
+                box_copy(sr.data(), r[cur].data(), m, n, x0 - 2, y0 - 1, C::LD, C::RR);
+                box_copy(ss.data(), s[cur].data(), m, n, x0 - 2, y0, C::LD, C::SR);
+                box_copy(scf.data(), cf.data(), m, n, x0 - 16, y0 - 1, C::CLD, C::RR);
+                for (int j = 0; j < C::SFT_N; ++j) sft[j] = (j & 3) == 3 ? 0.0 : ft_defl_shift_entry<C>(g, D, mu.data(), ix, iy, j >> 2, j & 3);
+                for (int j = 0; j < C::REC_N; ++j) srec[j] = ft_defl_rec_entry<C>(sft.data(), j >> 3, j & 7);
+                const bool interior = ft_interior<C>(g, x0, y0);
+                for (int tid = C::THREADS - 1; tid >= 0; --tid) {
+                    double ru = 0.0;
+                    EMUL_MAIN(g, sc, sr.data(), ss.data(), scf.data(), sr.data(), dtab.data(), cinv.data(), x0, y0, interior, tid,
+                                                 r[cur ^ 1].data(), s[cur ^ 1].data(), xrow.data(), prow.data(), rz, rr, srec.data(), rtab.data(), &ru);
+                    EMUL_RING(g, sc, sr.data(), ss.data(), scf.data(), sr.data(), dtab.data(), cinv.data(), x0, y0, tid, sft.data(), rtab.data());
+                    sru[tid] = ru;
+                }
+                for (int tid = 0; tid < C::THREADS; ++tid) EMUL_ENERGY(g, sc, ss.data(), scf.data(), x0, y0, tid, en);
+                // crossing currents by the 64 ring threads: per-thread partial sums, folded lane by lane (the kernel: a shuffle tree)
+                double tsl[FS_STRIDE] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int rl = 0; rl < 64; ++rl) {
+                    double fl[FS_SLOTS] = {0, 0, 0, 0, 0, 0};
+                    ft_flux_thread<LAT, C>(g, sc, ss.data(), scf.data(), sru.data(), x0, y0, rl, interior, fl);
+                    for (int k = 0; k < FS_SLOTS; ++k) tsl[k] += fl[k];
+                }
+                ft_defl_block_add(info, tsl, bacc);
+                if (info & FW_LAST) for (int q = 0; q < FB_PLANES; ++q) { Fb[(size_t)q * FT_KMAX + wk.B] = bacc[q]; bacc[q] = 0.0; }
             }
-            for (int tid = 0; tid < C::THREADS; ++tid) EMUL_ENERGY(g, sc, ss.data(), scf.data(), x0, y0, tid, en);
-            // crossing currents: per ring thread partial sums, folded thread by thread (the kernel: shuffles, then the two warps)
-            double fl[FS_SLOTS] = {0, 0, 0, 0, 0, ru};
-            for (int tid = 0; tid < C::THREADS; ++tid) ft_phase_flux<LAT, C>(g, sc, ss.data(), scf.data(), x0, y0, tid, fl, interior);
-            for (int k = 0; k < FS_SLOTS; ++k) F[(size_t)tl * FS_STRIDE + k] = fl[k];
         }
         // coarse stage
-        // (the kernel walks the static term list, one warp per block; both forms of the sum are checked against each other)
         std::vector<double> f((size_t)D.k);
-        for (int B = 0; B < D.k; ++B) {
-            f[B] = ft_defl_assemble(D, F.data(), B);
-            double a = 0.0;
-            for (int e = tptr[B]; e < tptr[B + 1]; ++e) a += (tent[e] & 1) ? -F[tent[e] >> 1] : F[tent[e] >> 1];
-            if (a != f[B]) return -5;
-        }
+        for (int B = 0; B < D.k; ++B) f[B] = ft_defl_block_f(D, Fb.data(), B);
         double mf = 0.0;
         for (int i = 0; i < D.k; ++i) { double a = 0.0; for (int j = 0; j < D.k; ++j) a += Einv[(size_t)i * D.k + j] * f[j]; mu[i] = a; mf += a * f[i]; }
         if (!prime) esum += st.alpha * st.gamma;            // the step just applied: |e_k|_A^2 - |e_k+1|_A^2 = alpha_k gamma_k
