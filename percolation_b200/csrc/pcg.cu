@@ -728,10 +728,11 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
     auto stage_r = [&](int k) { return reinterpret_cast<double*>(ft_raw + (size_t)k * C::STAGE_BYTES); };
     auto stage_s = [&](int k) { return reinterpret_cast<double*>(ft_raw + (size_t)k * C::STAGE_BYTES + C::R_BYTES); };
     auto stage_cf = [&](int k) { return reinterpret_cast<uint8_t*>(ft_raw + (size_t)k * C::STAGE_BYTES + C::R_BYTES + C::S_BYTES); };
-    // the producer thread (first lane of the second ring warp, which has time to spare) walks the lattice (FtWalk: block by
+    // the producer thread (first lane of the first ring warp, which has time to spare: on the square lattice it has no ring column) walks the lattice (FtWalk: block by
     // block) one tile ahead of the CTA: it publishes the coordinates of the next tile and issues its three TMA tensor copies:
     // r (tile + 2-site halo), s (tile + east / north / west ring), conduct bytes
-    constexpr int PROD = C::V == 1 ? 0 : C::RING_T0 + 32;
+    constexpr int PROD = C::V == 1 ? 0 : C::RING_T0;
+    constexpr int BSTEP = C::RING_NT == 32 ? C::RING_T0 + 1 : C::RING_T0 + 32;    // folds the slot totals of a finished tile into its block's sums                     // first lane of the second ring warp: folds the slot totals of a finished tile
     auto publish_issue = [&](const FtWalk& wk, int k) {
         int4 nt = make_int4(0, 0, 0, 0);
         if (wk.valid(dd.D)) nt = make_int4(wk.ix(dd.D), wk.iy(dd.D), wk.info(dd.D, rev) | FW_VALID, wk.B);
@@ -821,7 +822,7 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
             const int4 nt = tcoord[(k + 1) & 1];
             if (nt.z & FW_VALID) fill_shift((k + 1) & 1, nt.x, nt.y, tid - PROD);
         }
-        if (C::DEFL && tid == C::RING_T0 && (pinfo & FW_VALID)) block_step(pinfo, pB);
+        if (C::DEFL && tid == BSTEP && (pinfo & FW_VALID)) block_step(pinfo, pB);
         mbar_wait(&bars[k & 1], (unsigned)((k >> 1) & 1));
         const double* sr = stage_r(k & 1);
         double* ss = stage_s(k & 1);
@@ -836,6 +837,8 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         const double* uu = C::USTATE ? sr : su;                 // V = 3: the staged vector IS u
         if (C::V == 1) { rz = 0.0; rr = 0.0; en = 0.0; }
         double ru = 0.0;                                        // sum rho u' over this thread's sites of the tile (deflation)
+        // (the deflated main phase needs every register: the running bond-energy sum waits in shared memory meanwhile)
+        if (C::DEFL && tid < C::MAIN_THREADS) sru[tid] = en;
         if (interior) {                                         // (uniform over the CTA: two instantiations of the tile phases)
             ft_phase_main<LAT, C, true>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, true, tid, r_out, s_out, xrow, prow, rz, rr, sreck, rtab, &ru);
             ft_phase_ringcols<LAT, C, true>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, tid, sftk, rtab);
@@ -843,7 +846,7 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
             ft_phase_main<LAT, C, false>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, false, tid, r_out, s_out, xrow, prow, rz, rr, sreck, rtab, &ru);
             ft_phase_ringcols<LAT, C, false>(g, sc, sr, ss, scf, uu, dtab, cinv, x0, y0, tid, sftk, rtab);
         }
-        if (C::DEFL && tid < C::MAIN_THREADS) sru[tid] = ru;
+        if (C::DEFL && tid < C::MAIN_THREADS) { en = sru[tid]; sru[tid] = ru; }
         __syncthreads();
         if (interior) ft_phase_energy<LAT, C, true>(g, sc, ss, scf, x0, y0, tid, en);
         else ft_phase_energy<LAT, C, false>(g, sc, ss, scf, x0, y0, tid, en);
@@ -852,12 +855,12 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
             // has one producer warp (ft_flux_thread), lanes folded by a fixed shuffle tree
             const int rl = tid - C::RING_T0;
             double f[FS_SLOTS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            ft_flux_thread<LAT, C>(g, sc, ss, scf, sru, x0, y0, rl, interior, f);
+            ft_flux_thread<LAT, C>(g, sc, ss, scf, sru, x0, y0, rl, interior, true, f);
             const bool dirichlet = !interior && (y0 <= 1 || y0 + C::TY >= g.n - 2);
 #pragma unroll
             for (int q = 0; q < FS_SLOTS; ++q) {
                 const bool second = q == FS_N || q == FS_NW;                     // slots of the second ring warp
-                if (second != (rl >= 32)) continue;
+                if (C::RING_NT == 64 && second != (rl >= 32)) continue;
                 if (LAT == LAT_SQUARE && (q == FS_W || q == FS_NW)) continue;    // (stay 0)
                 double v = f[q];
                 if (q != FS_D || dirichlet)
@@ -878,7 +881,7 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         }
         pinfo = tc.z; pB = tc.w;
     }
-    if (C::DEFL && tid == C::RING_T0 && (pinfo & FW_VALID)) block_step(pinfo, pB);
+    if (C::DEFL && tid == BSTEP && (pinfo & FW_VALID)) block_step(pinfo, pB);
     int nparts = dd.D.ntx * dd.D.nty;
     constexpr int NQ = C::DEFL ? 4 : 3;
     if (C::V >= 2) {

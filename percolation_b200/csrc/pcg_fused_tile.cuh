@@ -44,7 +44,8 @@ struct FtCfg {
     static constexpr int MAIN_THREADS = 64 * NG;            // 2 columns per thread
     static constexpr int CR = TY + 1;                       // compute rows: gy = y0 + lr, lr = 0 .. TY (last = north ring)
     static constexpr int RING_T0 = V == 1 ? 0 : MAIN_THREADS;    // first thread that works on the ring columns
-    static constexpr int RING_NT = V == 1 ? 2 * CR : 64;         // ... and how many of them share the 2 CR ring sites
+    static constexpr int RING_NT = V == 1 ? 2 * CR : 64;         // ... and how many of them share the ring sites (32: ONE ring warp -- measured: no gain,
+                                                                 // warps are allocated four at a time, so 23 warps get no more registers than 24)
     static constexpr int THREADS = V == 1 ? MAIN_THREADS : MAIN_THREADS + RING_NT;
     static constexpr int RR = TY + 3;                       // staged rows of r, conduct bytes, u: gy = y0 - 1 + pr
     static constexpr int SR = TY + 1;                       // staged rows of s:                   gy = y0 + ps
@@ -186,6 +187,7 @@ struct FtDefl {
     int nbx, nby;      // blocks per lattice row / column
     int ntx, nty;      // tiles per lattice row / column
     int k;             // nbx * nby <= FT_KMAX
+    int sw, sh;        // log2 bw / log2 bh when they are powers of two (the library's own choice always is), else -1
 };
 // FS_R: sum over the tile's unknown sites of rho_i u'_i (rho: rounding residue of the matrix diagonal, diag_seq_rho) -- the part of
 // Z^T A u' that is not a current between blocks; in the weight pass (UNIT) the sum of rho_i itself: the entry it adds to E
@@ -204,9 +206,14 @@ PERC_HD FtDefl ft_defl_make(const Geom& g, int TX, int TY, int kmax, int bw0 = 0
         if (kmax <= 0 || D.k <= kmax) break;
         if (D.bw * TX < D.bh * TY) D.bw *= 2; else D.bh *= 2;
     }
+    D.sw = D.sh = -1;
+    for (int b = 0; b < 30; ++b) { if (D.bw == (1 << b)) D.sw = b; if (D.bh == (1 << b)) D.sh = b; }
     return D;
 }
-PERC_HD int ft_defl_block(const FtDefl& D, int ix, int iy) { return (iy / D.bh) * D.nbx + ix / D.bw; }
+PERC_HD int ft_defl_block(const FtDefl& D, int ix, int iy)
+{
+    return (D.sh >= 0 ? iy >> D.sh : iy / D.bh) * D.nbx + (D.sw >= 0 ? ix >> D.sw : ix / D.bw);
+}
 
 #if defined(__CUDA_ARCH__)
 #define FT_LDCG(p) __ldcg(p)           // written by other CTAs of the same launch: read through L2
@@ -404,26 +411,28 @@ struct FtGlobalAcc {
     PERC_HD double u(int, int) const { return 0.0; }
 };
 
-// crossing currents of a tile by the 64 ring threads (rl = 0 .. 63) while the others sum the bond energies.  Every slot has ONE
+// crossing currents of a tile by the ring threads (rl = 0 .. RING_NT-1) while the others sum the bond energies.  Every slot has ONE
 // producer warp: the first takes the east column (FS_E), the west column (FS_W, triangular), the bonds into the Dirichlet
-// rows (FS_D) and sum rho u' (FS_R: the per-thread sums the main threads left in sru); the second the top row (FS_N, FS_NW).
-// Partial sums of this thread into f[FS_SLOTS]; the caller folds the lanes of each warp.
+// rows (FS_D) and sum rho u' (FS_R: the per-thread sums the main threads left in sru -- they run over all tiles of a block
+// and are collected with its last tile: with_r); the second the top row (FS_N, FS_NW).  Configurations with ONE ring warp
+// (RING_NT = 32): that warp plays both.  Partial sums of this thread into f[FS_SLOTS]; the caller folds the lanes of each warp.
 template <int LAT, class C>
 PERC_HD void ft_flux_thread(const Geom& g, const FtScalars& sc, const double* ss, const uint8_t* scf, const double* sru, int x0, int y0,
-                            int rl, bool interior, double* f)
+                            int rl, bool interior, bool with_r, double* f)
 {
     const FtStageAcc<C> a{ss, scf, x0, y0};
     const int l = rl & 31;
-    if (rl < 32) {
+    const bool first = rl < 32, second = C::RING_NT == 32 || rl >= 32;      // (one ring warp plays both)
+    if (first) {
         for (int q = l; q < C::TY; q += 32) ft_flux_item<LAT, C, false>(g, sc.g0, sc.gleak, a, x0, y0, q, f, interior);
         if (LAT == LAT_TRIANGULAR)
             for (int q = C::TY + C::TX + l; q < 2 * C::TY + C::TX; q += 32) ft_flux_item<LAT, C, false>(g, sc.g0, sc.gleak, a, x0, y0, q, f, interior);
         if (!interior && (y0 <= 1 || y0 + C::TY >= g.n - 2))
             for (int q = 2 * C::TY + C::TX + l; q < FtFluxItems<C>::N; q += 32) ft_flux_item<LAT, C, false>(g, sc.g0, sc.gleak, a, x0, y0, q, f, false);
-        for (int j = l; j < C::MAIN_THREADS; j += 32) f[FS_R] += sru[j];
-    } else {
-        for (int q = C::TY + l; q < C::TY + C::TX; q += 32) ft_flux_item<LAT, C, false>(g, sc.g0, sc.gleak, a, x0, y0, q, f, interior);
+        if (with_r) for (int j = l; j < C::MAIN_THREADS; j += 32) f[FS_R] += sru[j];
     }
+    if (second)
+        for (int q = C::TY + l; q < C::TY + C::TX; q += 32) ft_flux_item<LAT, C, false>(g, sc.g0, sc.gleak, a, x0, y0, q, f, interior);
 }
 
 // deflated start: x0 = Z nu with E nu = Z^T b; returns u0 = D^-1 (b - A Z nu) of the unknown site (x, y) (cf: its conduct
@@ -510,7 +519,11 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
     ft_d2 dn = ft_ld2(c - C::LD), cc = ft_ld2(c);
     double drt = c[-C::LD + 2];                              // row below, x+2: SE neighbour of the odd column
 #if defined(__CUDA_ARCH__)
+#ifdef FT_NOUNROLL
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
 #endif
     for (int j = 0; j < C::RPT; ++j, c += C::LD) {
         const int lr = lr0 + j, gy = y0 + lr;
@@ -616,34 +629,38 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
     }
 }
 
-// east / west ring columns (gx = x0 - 1 and x0 + TX) of the compute rows: u' only (one thread per site)
-template <int LAT, class C, bool INT>
-PERC_HD void ft_phase_ringcols(const Geom& g, const FtScalars& sc, const double* sr, double* ss, const uint8_t* scf,
-                               const double* su, const FtDiag* dtab, const double* cinv, int x0, int y0, int tid, const double* sft = nullptr,
-                               const double* rtab = nullptr)
+// east / west ring columns (gx = x0 - 1 and x0 + TX) of the compute rows: u' only (one thread per site).  SIDE (0 west,
+// 1 east) is a template parameter: the block-column classes of the site and of its neighbours are then constants.
+// Who reads these values: the E bonds of the tile's east column and (triangular) the NW bonds of its west column -- rows
+// 0 .. TY-1 -- and the NW bond of the tile's top-left site, which ends on the west ring site of row TY; the east ring
+// site of row TY is never read (the last tile column is a down-type column: no NE bond).
+template <int LAT, class C, bool INT, int SIDE>
+PERC_HD void ft_ring_site(const Geom& g, const FtScalars& sc, const double* sr, double* ss, const uint8_t* scf,
+                          const double* su, const FtDiag* dtab, const double* cinv, int x0, int y0, int lr, int lane,
+                          const double* sft, const double* rtab)
 {
     constexpr bool interior = INT;
-    const int lane = tid & 31;
-    for (int q = tid - C::RING_T0; q >= 0 && q < 2 * C::CR; q += C::RING_NT) {
-    const int side = q >= C::CR, lr = q - side * C::CR;
-    const int gy = y0 + lr, gx = side ? x0 + C::TX : x0 - 1, col = side ? 2 + C::TX : 1;
+    constexpr int col = SIDE ? 2 + C::TX : 1;
+    const int gy = y0 + lr, gx = SIDE ? x0 + C::TX : x0 - 1;
     double un = 0.0;
-    if (gy >= 1 && gy <= g.n - 2 && gx >= 0 && gx < g.m) {
+    if (interior || (gy >= 1 && gy <= g.n - 2 && gx >= 0 && gx < g.m)) {
         const unsigned ex = interior ? ft_interior_ex<LAT>(gx) : neighbour_bits(g, gx, gy);
-        const unsigned cf = scf[(lr + 1) * C::CLD + (side ? 16 + C::TX : 15)] & ex;
+        const unsigned cf = scf[(lr + 1) * C::CLD + (SIDE ? 16 + C::TX : 15)] & ex;
         const double* c = &su[(lr + 1) * C::LD + col];
         double all = 0.0, con = 0.0;
-        // (deflation: as in ft_phase_main, neighbour j enters as u_j + (mu_i - mu_j); mu from the shift table by row and block column)
+        // (deflation: as in ft_phase_main, neighbour j enters as u_j + (mu_i - mu_j); mu from the shift table by row and
+        // block column -- a neighbour in the site's own row and block column needs no look-up)
         const double mi = C::DEFL ? sft[(lr + 1) * 4 + ft_defl_cls<C>(col)] : 0.0;
 #define FT_NB(bit, dc, dr) if (interior || (ex & bit)) { double v = c[(dr) * C::LD + (dc)]; \
-                                           if (C::DEFL) v += mi - sft[(lr + 1 + (dr)) * 4 + ft_defl_cls<C>(col + (dc))]; \
+                                           if (C::DEFL && ((dr) != 0 || ft_defl_cls<C>(col + (dc)) != ft_defl_cls<C>(col))) \
+                                               v += mi - sft[(lr + 1 + (dr)) * 4 + ft_defl_cls<C>(col + (dc))]; \
                                            all += v; if (cf & bit) con += v; }
         FT_NB(NB_E, 1, 0) FT_NB(NB_W, -1, 0) FT_NB(NB_N, 0, 1) FT_NB(NB_S, 0, -1)
         if (LAT == LAT_TRIANGULAR) {
+            // (x0 - 1 is odd, a down-type column; x0 + TX even, an up-type one -- but only when x0 is even, which TX = 128 makes it)
             if (gx & 1) { FT_NB(NB_SW, -1, -1) FT_NB(NB_SE, 1, -1) } else { FT_NB(NB_NW, -1, 1) FT_NB(NB_NE, 1, 1) }
         }
 #undef FT_NB
-        // (a tile without lattice borders: its ring columns have all their neighbours too -- x0 - 1 is odd, x0 + TX even)
         const int it = C::tabp(LAT, ft_pat<LAT>(cf, gx & 1), lane);
         const bool full = interior || ex == ft_interior_ex<LAT>(gx);
         const FtDiag t = full ? dtab[it] : ft_diag_site(g, cf, ex, gx, sc.g0, sc.gleak, cinv);
@@ -658,6 +675,44 @@ PERC_HD void ft_phase_ringcols(const Geom& g, const FtScalars& sc, const double*
         else un = (sr[(lr + 1) * C::LD + col] - sc.alpha * sn) * t.inv;
     }
     ss[lr * C::LD + col] = un;
+}
+template <int LAT, class C, bool INT>
+PERC_HD void ft_phase_ringcols(const Geom& g, const FtScalars& sc, const double* sr, double* ss, const uint8_t* scf,
+                               const double* su, const FtDiag* dtab, const double* cinv, int x0, int y0, int tid, const double* sft = nullptr,
+                               const double* rtab = nullptr)
+{
+    const int lane = tid & 31;
+    if (C::V >= 2 && C::TY == 32 && C::RING_NT == 64) {
+        // two ring warps: the first takes the west column, the second the east one, lane <-> tile row
+        const int rl = tid - C::RING_T0;
+        if (rl < 0 || rl >= 64) return;
+        if (rl < 32) {
+            // (square lattice: the tile owns E and N bonds only -- nothing reads the west ring column)
+            if (LAT == LAT_TRIANGULAR) {
+                ft_ring_site<LAT, C, INT, 0>(g, sc, sr, ss, scf, su, dtab, cinv, x0, y0, rl, lane, sft, rtab);
+                if (rl == 0) ft_ring_site<LAT, C, INT, 0>(g, sc, sr, ss, scf, su, dtab, cinv, x0, y0, C::TY, lane, sft, rtab);
+            }
+        } else {
+            ft_ring_site<LAT, C, INT, 1>(g, sc, sr, ss, scf, su, dtab, cinv, x0, y0, rl - 32, lane, sft, rtab);
+        }
+        return;
+    }
+    if (C::V >= 2 && C::TY == 32 && C::RING_NT == 32) {
+        // one ring warp: lane <-> tile row of the east column, then (triangular) of the west one
+        const int rl = tid - C::RING_T0;
+        if (rl < 0 || rl >= 32) return;
+        ft_ring_site<LAT, C, INT, 1>(g, sc, sr, ss, scf, su, dtab, cinv, x0, y0, rl, lane, sft, rtab);
+        if (LAT == LAT_TRIANGULAR) {
+            ft_ring_site<LAT, C, INT, 0>(g, sc, sr, ss, scf, su, dtab, cinv, x0, y0, rl, lane, sft, rtab);
+            if (rl == 0) ft_ring_site<LAT, C, INT, 0>(g, sc, sr, ss, scf, su, dtab, cinv, x0, y0, C::TY, lane, sft, rtab);
+        }
+        return;
+    }
+    for (int q = tid - C::RING_T0; q >= 0 && q < 2 * C::CR; q += C::RING_NT) {
+        const int side = q >= C::CR, lr = q - side * C::CR;
+        if ((lr == C::TY && side) || (LAT == LAT_SQUARE && !side)) continue;       // never read
+        if (side) ft_ring_site<LAT, C, INT, 1>(g, sc, sr, ss, scf, su, dtab, cinv, x0, y0, lr, lane, sft, rtab);
+        else ft_ring_site<LAT, C, INT, 0>(g, sc, sr, ss, scf, su, dtab, cinv, x0, y0, lr, lane, sft, rtab);
     }
 }
 
@@ -672,7 +727,11 @@ PERC_HD void ft_phase_energy(const Geom& g, const FtScalars& sc, const double* s
     const int tx = tid & 63, ty = tid >> 6;
     const int gx = x0 + 2 * tx, lr0 = ty * C::RPT;
 #if defined(__CUDA_ARCH__)
+#ifdef FT_NOUNROLL
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
 #endif
     for (int j = 0; j < C::RPT; ++j) {
         const int lr = lr0 + j, gy = y0 + lr;

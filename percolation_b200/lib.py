@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libperc_b200.so")
+SO_PATH = os.environ.get("PERC_B200_SO") or os.path.join(_HERE, "libperc_b200.so")     # (override: kernel experiments)
 
 SQUARE, TRIANGULAR = 1, 2
 SITE, BOND, MIXED = 1, 2, 3

@@ -232,9 +232,9 @@ int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double 
                 for (int tid = 0; tid < C::THREADS; ++tid) EMUL_ENERGY(g, sc, ss.data(), scf.data(), x0, y0, tid, en);
                 // crossing currents by the 64 ring threads: per-thread partial sums, folded lane by lane (the kernel: a shuffle tree)
                 double tsl[FS_STRIDE] = {0, 0, 0, 0, 0, 0, 0, 0};
-                for (int rl = 0; rl < 64; ++rl) {
+                for (int rl = 0; rl < C::RING_NT; ++rl) {
                     double fl[FS_SLOTS] = {0, 0, 0, 0, 0, 0};
-                    ft_flux_thread<LAT, C>(g, sc, ss.data(), scf.data(), sru.data(), x0, y0, rl, interior, fl);
+                    ft_flux_thread<LAT, C>(g, sc, ss.data(), scf.data(), sru.data(), x0, y0, rl, interior, true, fl);
                     for (int k = 0; k < FS_SLOTS; ++k) tsl[k] += fl[k];
                 }
                 ft_defl_block_add(info, tsl, bacc);
