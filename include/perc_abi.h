@@ -192,6 +192,18 @@ int32_t perc_batch_conduct(const int64_t *h, const int32_t *kind, const int32_t 
 int32_t perc_comm_init_rank(const int64_t *h, const int32_t *nranks, const int32_t *rank, const uint8_t *id128);
 int32_t perc_allreduce_stats(const int64_t *h, const int32_t *ni, int64_t *ivals, const int32_t *nd, double *dvals);
 
+/* ---- per-bond conductances ----------------------------------------------------------
+ * The reference's MATLAB post-processor can give every bond of the spanning cluster its own conductance
+ * (MATLAB/ConductCalc.m:38-47 `condtype = 2`; :94-96, :117-119, :139-141: G(i,j) = -g0*rand for a conducting bond, -1e-12
+ * for every other lattice bond).  w(nb): conductance of bond row i of the reference's bond list (perc_geom_bondlist)
+ * WHEN that bond conducts -- which bonds conduct is decided by the labels as before (bond / site / mixed rule), the
+ * others keep gleak; g0 of the perc_conduct* calls is then ignored.  The array is copied; it stays in force for
+ * every following perc_conduct / perc_conduct_g on the handle (voltages are always formed) until w = NULL
+ * (Fortran: c_null_ptr) drops it.  Not available on slab handles and for warm starts.  The solve runs plain two-kernel
+ * Jacobi-PCG on four weight planes + the diagonal (112 B per site and iteration on the square lattice, 144 B
+ * triangular, against 50 B for the uniform-g0 kernels: csrc/pcg_weighted.cu). */
+int32_t perc_set_bond_conductance(const int64_t *h, const double *w);
+
 /* ---- solver selection --------------------------------------------------------------------------- */
 /* Iteration kernels of the conductance solve (the body of linbcg's loop, Sq/bondc.f:780-833; Jacobi asolve :855-864):
  *   mode 0 (default): automatic -- perc_conduct_g on one GPU without periodic wrap runs the DEFLATED ONE-PASS kernel:

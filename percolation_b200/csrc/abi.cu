@@ -106,7 +106,7 @@ void ctx_free(Ctx* c)
     if (c->d_stitch) cudaFree(c->d_stitch);
     if (c->h_iface) cudaFreeHost(c->h_iface);
     void* ptrs[] = {c->srank, c->brank, c->mask, c->label, c->size, c->rootlist, c->d_sum, c->d_pcg,
-                    c->d_hist, c->d_thr, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vp2, c->vq, c->xprow, c->partial, c->d_stage, c->d_defl};
+                    c->d_hist, c->d_thr, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vp2, c->vq, c->xprow, c->partial, c->d_stage, c->d_defl, c->bond_w, c->wplane, c->wdiag};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_pcg) cudaFreeHost(c->h_pcg);
     if (c->h_sum_pin) cudaFreeHost(c->h_sum_pin);
@@ -754,6 +754,16 @@ int32_t perc_set_solver(const int64_t* h, const int32_t* mode)
     c->pcg_mode = pm; c->fused_cfg = fc;
     for (Ctx* k : c->batch_kids) { k->pcg_mode = pm; k->fused_cfg = fc; }
     return 0;
+}
+
+// per-bond conductances: w(nb), reference bond-row order; NULL = back to the uniform g0 (MATLAB/ConductCalc.m:38-47,94-96)
+int32_t perc_set_bond_conductance(const int64_t* h, const double* w)
+{
+    GET_CTX(h);
+    if (c->nranks > 1) return PERC_E_STATE;
+    const int rc = pcg_set_bond_weights(c, w);
+    c->solved = false;
+    return rc < 0 ? PERC_E_ARG : rc;
 }
 
 int32_t perc_solver_used(const int64_t* h, int32_t* fused)

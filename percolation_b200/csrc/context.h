@@ -80,6 +80,10 @@ struct Ctx {
     double* vp2 = nullptr;        // p is double-buffered (the fused SpMV reads neighbours' old p)
     double* vq = nullptr;
     double* xprow = nullptr;      // [4 m] one-pass solver: x and p of rows 1 and n-2 (the rows the read-out consumes)
+    double* bond_w = nullptr;     // [nb] caller's per-bond conductances (perc_set_bond_conductance; pcg_weighted.cu)
+    double* wplane = nullptr;     // [4][t] weight of the bond each site owns in direction E, N, NW, NE
+    double* wdiag = nullptr;      // [t] diagonal of the weighted matrix
+    bool have_bond_w = false;
     int pcg_mode = -1;            // -1 process default, 0 automatic (one-pass kernel when it applies), 1 two-kernel form
     int fused_cfg = -1;           // tile configuration of the one-pass kernel (-1: process default)
     bool last_fused = false;      // the last solve ran the one-pass kernel
@@ -162,6 +166,8 @@ int batch_conduct_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsi
                       double Va, double g0, double gleak, double tol, int itmax, double read_thresh,
                       double* G, int32_t* iters, int64_t* stats);
 bool pcg_fused_applies(const Ctx* c, int keep_x, int warm);
+int pcg_set_bond_weights(Ctx* c, const double* w);
+int pcg_solve_weighted(Ctx* c, double Va, double gleak, double tol, int itmax, double read_thresh);
 int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double tol, int itmax,
               double read_thresh, int keep_x, double* Gtop, double* Gbot, int* iter, double* err, int warm = 0);
 

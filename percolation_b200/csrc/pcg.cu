@@ -1419,26 +1419,25 @@ static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
         c->launches++;
     }
     PERC_CUDA(launch(1));          // s = A u0 and delta0: alpha0, beta0 = 0
-    float it_ms = 0.f; int nsamp = 0;
+    // average duration of a launch: CUDA events around whole chunks of launches (back to back on the stream, so the
+    // bracket is the kernels' own device time incl. the gaps between them) / launches in them.  Chunks in which the
+    // solve ended are left out (their trailing launches return at once) unless there is no other.
+    float it_ms = 0.f; long nlaunch = 0;
     int chunk = 32, iters_before = 0;
     for (;;) {
-        for (int k = 0; k < chunk; ++k) {
-            // one mid-chunk iteration is bracketed with events (the stream is busy there, so the bracket is the
-            // kernel's own device time)
-            const bool sample = (k == chunk / 2);
-            if (sample) PERC_CUDA(cudaEventRecord(c->ev[8], s));
-            PERC_CUDA(launch(0));
-            if (sample) PERC_CUDA(cudaEventRecord(c->ev[9], s));
-        }
+        PERC_CUDA(cudaEventRecord(c->ev[8], s));
+        for (int k = 0; k < chunk; ++k) PERC_CUDA(launch(0));
+        PERC_CUDA(cudaEventRecord(c->ev[9], s));
         PERC_CUDA(cudaMemcpyAsync(c->h_pcg, c->d_pcg, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
         PERC_CUDA(cudaStreamSynchronize(s));
-        if (!c->h_pcg->done || c->h_pcg->iter > iters_before + chunk / 2) {
+        const int live = c->h_pcg->iter - iters_before;
+        if (!c->h_pcg->done || nlaunch == 0) {
             float a = 0.f;
             cudaEventElapsedTime(&a, c->ev[8], c->ev[9]);
-            it_ms += a; nsamp++;
+            it_ms += a; nlaunch += c->h_pcg->done ? (live > 0 ? live : 1) : chunk;
         }
         // a chunk that did not advance the iteration count means the launches did not run: never spin on that
-        if (!c->h_pcg->done && c->h_pcg->iter == iters_before) return (int)cudaErrorLaunchFailure;
+        if (!c->h_pcg->done && live == 0) return (int)cudaErrorLaunchFailure;
         iters_before = c->h_pcg->iter;
         if (c->h_pcg->done) break;
         if (chunk < 512) chunk *= 2;
@@ -1446,7 +1445,7 @@ static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
     // the read-out consumes x on rows 1 and n-2 (vx was an s buffer: dead now)
     PERC_CUDA(cudaMemcpyAsync(c->vx + g.m, xrow, sizeof(double) * g.m, cudaMemcpyDeviceToDevice, s));
     PERC_CUDA(cudaMemcpyAsync(c->vx + (int64_t)(g.n - 2) * g.m, xrow + g.m, sizeof(double) * g.m, cudaMemcpyDeviceToDevice, s));
-    c->phase_ms[6] = nsamp ? it_ms / nsamp : 0.f;
+    c->phase_ms[6] = nlaunch ? it_ms / (float)nlaunch : 0.f;
     c->phase_ms[7] = 0.f;
     return 0;
 }
@@ -1520,7 +1519,10 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
         rc = slab_halo_exchange(c, c->vr, 8); if (rc) return rc;                        // r = b on the halo rows
         c->launches++;
     }
-    const bool fused = pcg_fused_applies(c, keep_x, warm);
+    // per-bond conductances (perc_set_bond_conductance): their own kernels (pcg_weighted.cu), voltages always formed
+    const bool weighted = c->have_bond_w;
+    if (weighted && (dist || warm)) return -1;
+    const bool fused = !weighted && pcg_fused_applies(c, keep_x, warm);
     c->last_fused = fused;
     // TMA descriptors of the arrays the pipeline stages (row-major m x n, boxes of 34 rows)
     CUtensorMap tm_r{}, tm_pa{}, tm_pb{}, tm_cf{};
@@ -1544,7 +1546,10 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     double* pold = c->vp; double* pnew = c->vp2;
     float sp_ms = 0.f, up_ms = 0.f; int nsamp = 0;
     int chunk = 16, iters_before = 0;
-    if (fused) {
+    if (weighted) {
+        rc = pcg_solve_weighted(c, Va, gleak, tol, itmax, read_thresh);
+        if (rc) return rc;
+    } else if (fused) {
         rc = pcg_fused_loop(c, prm);
         if (rc) return rc;
     } else
@@ -1596,15 +1601,17 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
         if (c->h_pcg->done) break;
         if (chunk < 256) chunk *= 2;
     }
-    pcg_readout_kernel<<<1, 256, 0, s>>>(g, prm, c->cfull, c->vx, c->d_pcg);
-    c->launches++;
+    if (!weighted) {
+        pcg_readout_kernel<<<1, 256, 0, s>>>(g, prm, c->cfull, c->vx, c->d_pcg);
+        c->launches++;
+    }
     if (dist) { rc = slab_allreduce_f64(c, &c->d_pcg->Itop, 2); if (rc) return rc; }     // Itop from the last rank, Ibot from the first
     PERC_CUDA(cudaEventRecord(c->ev[7], s));
     PERC_CUDA(cudaMemcpyAsync(c->h_pcg, c->d_pcg, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
     PERC_CUDA(cudaStreamSynchronize(s));
     PERC_CUDA(cudaGetLastError());
     cudaEventElapsedTime(&c->phase_ms[5], c->ev[6], c->ev[7]);
-    if (!fused) {
+    if (!fused && !weighted) {
         c->phase_ms[6] = nsamp ? sp_ms / nsamp : 0.f;
         c->phase_ms[7] = nsamp ? up_ms / nsamp : 0.f;
     }
@@ -1613,7 +1620,7 @@ int pcg_solve(Ctx* c, int cluster_id, double Va, double g0, double gleak, double
     *iter = c->h_pcg->iter;
     *err = c->h_pcg->err;
     c->solved = true;
-    c->have_x = want_x != 0;
+    c->have_x = want_x != 0 || weighted;
     return 0;
 #undef PIPE_LAUNCH
 #undef PIPE_ARGS

@@ -30,7 +30,7 @@ SYMBOLS = [
     "perc_conduct", "perc_conduct_warm", "perc_conduct_g", "perc_get_voltage", "perc_launch_count", "perc_phase_ms", "perc_stream", "perc_set_solver", "perc_solver_used",
     "perc_create_slab", "perc_comm_unique_id", "perc_comm_init", "perc_slab_rows", "perc_generate_i8",
     "perc_summary_i8", "perc_span_i8", "perc_get_site_labels_i8", "perc_stitch_host",
-    "perc_batch", "perc_batch_conduct", "perc_comm_init_rank", "perc_allreduce_stats",
+    "perc_batch", "perc_batch_conduct", "perc_comm_init_rank", "perc_allreduce_stats", "perc_set_bond_conductance",
 ]
 
 
@@ -283,6 +283,16 @@ class Lattice:
                    _f64(read_thresh), C.byref(Gtop), C.byref(Gbot), C.byref(it), C.byref(err))
         return dict(Gtop=Gtop.value, Gbot=Gbot.value, iter=it.value, err=err.value)
 
+    def set_bond_conductance(self, w):
+        """per-bond conductances (MATLAB/ConductCalc.m condtype = 2): w[nb] in the reference's bond-row order, used for the
+        bonds that conduct; None restores the uniform g0"""
+        if w is None:
+            self._call("perc_set_bond_conductance", None)
+            return
+        w = np.ascontiguousarray(w, np.float64)
+        assert w.size == self.nb
+        self._call("perc_set_bond_conductance", _ptr(w, C.c_double))
+
     def voltage(self):
         v = np.zeros(self.t - 2 * self.m, np.float64)
         self._call("perc_get_voltage", _ptr(v, C.c_double))
@@ -316,6 +326,17 @@ class Lattice:
 
 # ---- one lattice decomposed into row slabs over several GPUs ---------------------------------------
 IFACE_WORDS = lambda m: 5 * m + 8          # block a rank contributes to the interface all-gather (csrc/slab.h)
+
+
+def matlab_variable_conductances(conducting, g0=1.0, seed=1838534):
+    """The draw of MATLAB/ConductCalc.m with condtype = 2: `rand('twister', 1838534)` (:44-46: MT19937 seeded by
+    init_genrand, 53-bit doubles -- numpy's legacy RandomState(seed).random_sample() is the same generator), one draw
+    per CONDUCTING bond in bond-list order (:94-96, :117-119, :139-141: G(i,j) = -g0*rand inside the loop over the bonds).
+    conducting: bool[nb].  Returns w[nb] for perc_set_bond_conductance (entries of non-conducting bonds are not used)."""
+    conducting = np.asarray(conducting, bool)
+    w = np.zeros(conducting.size, np.float64)
+    w[conducting] = g0 * np.random.RandomState(seed).random_sample(int(conducting.sum()))
+    return w
 
 
 def comm_unique_id():

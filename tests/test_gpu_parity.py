@@ -239,6 +239,62 @@ def test_conductance_vs_oracle(P, O, lat, kind, pbc, m, n):
     assert done >= 1
 
 
+# ---- per-bond conductances (MATLAB/ConductCalc.m condtype = 2) -----------------------------------
+@pytest.mark.parametrize("m,n", [(40, 36), (64, 50)])
+@pytest.mark.parametrize("lat,kind", [(1, 2), (2, 2), (1, 1), (2, 1), (1, 3), (2, 3)])
+@pytest.mark.parametrize("pbc", [0, 1])
+def test_variable_bond_conductance_vs_oracle(P, O, lat, kind, pbc, m, n):
+    """conducting bonds get g0 * rand drawn as ConductCalc.m draws it (twister seed 1838534, one draw per conducting bond
+    in bond order, :44-46, :94-96); Gtop / Gbot / voltages against the oracle's CG on the same weights: 1e-9"""
+    t = m * n
+    b1, b2 = O.bondlist(lat, m, n, pbc)
+    nb = len(b1)
+    done = 0
+    with P.Lattice(lat, m, n, pbc) as L:
+        for seed in range(5):
+            sorder = O.shuffle_sites(626504 + seed, t)
+            bo1, bo2 = O.shuffle_bonds(184489 + seed, b1, b2)
+            if kind == O.BOND:
+                b3, c, res = L.bond(bo1, bo2, O.fill_count(0.54 if lat == 1 else 0.38, nb)); s = None
+            elif kind == O.SITE:
+                s, c, res = L.site(sorder, O.fill_count(0.63 if lat == 1 else 0.54, t)); b3 = None
+            else:
+                s, b3, c, res = L.sitebond(sorder, O.fill_count(0.85, t), bo1, bo2, O.fill_count(0.68 if lat == 1 else 0.5, nb))
+            if not res["perccln"]:
+                continue
+            cid = res["perccln"]
+            w0 = O.weights(kind, b1, b2, s, b3, cid, g0=1.0, gleak=1e-12)     # 1.0 on the bonds that conduct
+            wv = P.matlab_variable_conductances(w0 == 1.0, g0=1.0)
+            w = np.where(w0 == 1.0, wv, 1e-12)
+            uniform = L.conduct(cid, tol=1e-13, itmax=400000)
+            L.set_bond_conductance(wv)
+            got = L.conduct(cid, tol=1e-13, itmax=400000)
+            ref = O.conduct_cg(m, n, b1, b2, w, tol=1e-13, itmax=400000)
+            assert got["err"] <= 1e-13 and abs(got["iter"] - ref["iter"]) <= max(3, ref["iter"] // 100)
+            assert abs(got["Gtop"] - ref["Gtop"]) <= 1e-9 * abs(ref["Gtop"])
+            assert abs(got["Gbot"] - ref["Gbot"]) <= 1e-9 * abs(ref["Gbot"])
+            assert got["Gtop"] < uniform["Gtop"]                                 # every conducting bond got weaker
+            chk = O.conduct_check(m, n, b1, b2, w, L.voltage())
+            assert chk["err"] <= 2e-13 and abs(chk["Gtop"] - got["Gtop"]) <= 1e-12 * abs(got["Gtop"])
+            gonly = L.conduct(cid, tol=1e-13, itmax=400000, voltages=False)     # the sweep drivers' entry point: same solve
+            assert gonly["Gtop"] == got["Gtop"] and gonly["Gbot"] == got["Gbot"]
+            # the reference's own tolerance / iteration cap against the literal linbcg
+            lit = O.conduct_literal(m, n, b1, b2, w)
+            gd = L.conduct(cid)
+            assert abs(gd["iter"] - lit["iter"]) <= 1 and abs(gd["Gtop"] - lit["Gtop"]) <= 1e-6 * abs(lit["Gtop"])
+            # all weights equal to g0: the uniform solve, and dropping the weights restores it exactly
+            L.set_bond_conductance(np.ones(nb))
+            same = L.conduct(cid, tol=1e-13, itmax=400000)
+            assert abs(same["Gtop"] - uniform["Gtop"]) <= 1e-9 * abs(uniform["Gtop"])
+            L.set_bond_conductance(None)
+            again = L.conduct(cid, tol=1e-13, itmax=400000)
+            assert again == uniform
+            done += 1
+            if done == 2:
+                break
+    assert done >= 1
+
+
 def test_full_lattice_closed_form(P, O):
     """every bond occupied: square G = m/(n-1) exactly"""
     for (m, n, pbc) in ((10, 10, 0), (16, 8, 1), (50, 50, 0)):
