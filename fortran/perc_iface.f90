@@ -316,6 +316,15 @@ module perc_iface
       integer(c_int32_t), intent(in) :: mode
     end function
 
+    ! the reference programs' text files from the current labeling, in their own formats (which = 1 site.txt, 2 bond.txt,
+    ! 3 sbsite.txt, 4 sbbond.txt, 5 bondlist.txt):  ierr = perc_write_txt(h, 1, 'site.txt', len('site.txt'))
+    integer(c_int32_t) function perc_write_txt(h, which, path, pathlen) bind(C, name="perc_write_txt")
+      import :: c_int32_t, c_int64_t, c_char
+      integer(c_int64_t), intent(in) :: h
+      integer(c_int32_t), intent(in) :: which, pathlen
+      character(kind=c_char), intent(in) :: path(*)
+    end function
+
     ! per-bond conductances (MATLAB/ConductCalc.m condtype = 2: g0*rand on the conducting bonds): w(nb) in bond-list
     ! order, used for the bonds that conduct; pass c_null_ptr through perc_clear_bond_conductance to drop them
     integer(c_int32_t) function perc_set_bond_conductance(h, w) bind(C, name="perc_set_bond_conductance")

@@ -192,6 +192,20 @@ int32_t perc_batch_conduct(const int64_t *h, const int32_t *kind, const int32_t 
 int32_t perc_comm_init_rank(const int64_t *h, const int32_t *nranks, const int32_t *rank, const uint8_t *id128);
 int32_t perc_allreduce_stats(const int64_t *h, const int32_t *ni, int64_t *ivals, const int32_t *nd, double *dvals);
 
+/* ---- the reference programs' output files --------------------------------------
+ * Writes one of the text files the reference's programs leave behind, in their own record formats, from the handle's
+ * current labeling, so that MATLAB/SitePlot.m, BondPlot.m, SiteBondPlot.m and ConductCalc.m read GPU results unchanged:
+ *   which = 1 site.txt     j, s(j), c(j)                     (i10,",",i10,",",i10)                    Sq/site.f:354-359
+ *           2 bond.txt     b(j,1), b(j,2), b(j,3), j, c(j)   (i10,",",i10,",",i10,",",i10,",",i10)    Sq/bond.f:443-448
+ *           3 sbsite.txt   i, s(i), c(i)                                                               Sq/sitebond.f:469-471
+ *           4 sbbond.txt   b(i,1), b(i,2), b(i,3)                                                      Sq/sitebond.f:473-475
+ *           5 bondlist.txt blist(i,1), blist(i,2)            (i10,",",i10)                             Sq/site.f:106-120
+ * 1 needs a site labeling, 2 a bond labeling, 3 / 4 a mixed one (PERC_E_STATE otherwise).  Labels are canonical
+ * (smallest member site id), not the reference's creation counters: the partition, the sizes and the label of the
+ * spanning cluster (`perccln` of perc_site / perc_bond / perc_sitebond) are consistent within the files, which is all the
+ * MATLAB scripts use.  path(pathlen) is a Fortran character variable (no terminating NUL needed). */
+int32_t perc_write_txt(const int64_t *h, const int32_t *which, const char *path, const int32_t *pathlen);
+
 /* ---- per-bond conductances ----------------------------------------------------------
  * The reference's MATLAB post-processor can give every bond of the spanning cluster its own conductance
  * (MATLAB/ConductCalc.m:38-47 `condtype = 2`; :94-96, :117-119, :139-141: G(i,j) = -g0*rand for a conducting bond, -1e-12

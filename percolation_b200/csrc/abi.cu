@@ -2,6 +2,7 @@
 // Thin argument checking + dispatch; all compute is in the CUDA kernels of the sibling files.
 #include <cstdio>
 #include <cstring>
+#include <string>
 #include <mutex>
 #include <unordered_map>
 #include "../../include/perc_abi.h"
@@ -342,6 +343,51 @@ int32_t perc_get_sizes(const int64_t* h, int32_t* cs)
     GET_CTX(h);
     if (!c->labeled || !cs) return PERC_E_STATE;
     return ccl_export_sizes(c, cs);
+}
+
+// ---- the reference programs' output files, in their own formats -----------------------------
+// which = 1 `site.txt`   : j, s(j), c(j)                      format(i10,",",i10,",",i10)            Sq/site.f:354-359
+//         2 `bond.txt`   : b(j,1), b(j,2), b(j,3), j, c(j)    format(i10,",",i10,",",i10,",",i10,",",i10)  Sq/bond.f:443-448
+//         3 `sbsite.txt` : i, s(i), c(i)                                                               Sq/sitebond.f:469-471
+//         4 `sbbond.txt` : b(i,1), b(i,2), b(i,3)                                                      Sq/sitebond.f:473-475
+//         5 `bondlist.txt`: blist(i,1), blist(i,2)            format(i10,",",i10)                      Sq/site.f:106-120
+// Labels are the library's canonical ones (smallest member site id), c(.) is indexed by them (a label beyond the table
+// -- a lone bond of the mixed problem -- has size 1 by construction); MATLAB/ConductCalc.m and the *Plot.m scripts only
+// compare labels with `perccln`, so they read these files unchanged.  path(pathlen): not NUL-terminated (Fortran character).
+int32_t perc_write_txt(const int64_t* h, const int32_t* which, const char* path, const int32_t* pathlen)
+{
+    GET_CTX(h);
+    if (!which || !path || !pathlen || *pathlen < 1 || *pathlen > 4096 || *which < 1 || *which > 5) return PERC_E_ARG;
+    if (c->nranks > 1) return PERC_E_STATE;
+    const Geom& g = c->g;
+    const int w = *which;
+    if (w != 5 && !c->labeled) return PERC_E_STATE;
+    if ((w == 1 && c->kind != KIND_SITE) || (w == 2 && c->kind != KIND_BOND) || ((w == 3 || w == 4) && c->kind != KIND_MIXED)) return PERC_E_STATE;
+    std::vector<int32_t> s, b3, cs, bl;
+    int rc = 0;
+    if (w == 1 || w == 3) { s.resize((size_t)g.t); rc = download(c, s.data(), c->label, sizeof(int32_t) * g.t); if (rc) return rc; }
+    if (w == 2 || w == 4) { b3.resize((size_t)g.nb); rc = ccl_export_bond_labels(c, b3.data()); if (rc) return rc; }
+    if (w <= 3) { cs.resize((size_t)g.t); rc = ccl_export_sizes(c, cs.data()); if (rc) return rc; }
+    if (w == 2 || w == 4 || w == 5) {
+        bl.resize(2 * (size_t)g.nb);
+        const int32_t lat = g.lattice, m = g.m, n = g.n, pbc = g.pbc;
+        rc = perc_geom_bondlist(&lat, &m, &n, &pbc, bl.data()); if (rc) return rc;
+    }
+    const std::string fn(path, (size_t)*pathlen);
+    FILE* f = std::fopen(fn.c_str(), "w");
+    if (!f) return PERC_E_ARG;
+    if (w == 1 || w == 3)
+        for (int64_t j = 0; j < g.t; ++j) std::fprintf(f, "%10d,%10d,%10d\n", (int)(j + 1), s[j], cs[j]);
+    else if (w == 2)
+        for (int64_t j = 0; j < g.nb; ++j)
+            std::fprintf(f, "%10d,%10d,%10d,%10d,%10d\n", bl[j], bl[g.nb + j], b3[j], (int)(j + 1), j < g.t ? cs[j] : 0);
+    else if (w == 4)
+        for (int64_t j = 0; j < g.nb; ++j) std::fprintf(f, "%10d,%10d,%10d\n", bl[j], bl[g.nb + j], b3[j]);
+    else
+        for (int64_t j = 0; j < g.nb; ++j) std::fprintf(f, "%10d,%10d\n", bl[j], bl[g.nb + j]);
+    const bool bad = std::ferror(f) != 0;
+    if (std::fclose(f) != 0 || bad) return PERC_E_ARG;
+    return 0;
 }
 
 int32_t perc_span(const int64_t* h, const int32_t* max_ids, int32_t* nspan, int32_t* ids, int32_t* sizes)

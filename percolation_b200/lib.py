@@ -30,7 +30,7 @@ SYMBOLS = [
     "perc_conduct", "perc_conduct_warm", "perc_conduct_g", "perc_get_voltage", "perc_launch_count", "perc_phase_ms", "perc_stream", "perc_set_solver", "perc_solver_used",
     "perc_create_slab", "perc_comm_unique_id", "perc_comm_init", "perc_slab_rows", "perc_generate_i8",
     "perc_summary_i8", "perc_span_i8", "perc_get_site_labels_i8", "perc_stitch_host",
-    "perc_batch", "perc_batch_conduct", "perc_comm_init_rank", "perc_allreduce_stats", "perc_set_bond_conductance",
+    "perc_batch", "perc_batch_conduct", "perc_comm_init_rank", "perc_allreduce_stats", "perc_set_bond_conductance", "perc_write_txt",
 ]
 
 
@@ -282,6 +282,15 @@ class Lattice:
         self._call("perc_conduct_warm" if warm else "perc_conduct" if voltages else "perc_conduct_g", _i32(cluster_id), _f64(Va), _f64(g0), _f64(gleak), _f64(tol), _i32(itmax),
                    _f64(read_thresh), C.byref(Gtop), C.byref(Gbot), C.byref(it), C.byref(err))
         return dict(Gtop=Gtop.value, Gbot=Gbot.value, iter=it.value, err=err.value)
+
+    TXT_FILES = {"site.txt": 1, "bond.txt": 2, "sbsite.txt": 3, "sbbond.txt": 4, "bondlist.txt": 5}
+
+    def write_txt(self, which, path):
+        """one of the reference programs' output files (site.txt, bond.txt, sbsite.txt, sbbond.txt, bondlist.txt) in the
+        reference's record format, from the current labeling (Sq/site.f:354-359, Sq/bond.f:443-448, Sq/sitebond.f:469-477)"""
+        w = self.TXT_FILES[which] if isinstance(which, str) else int(which)
+        p = os.fsencode(path)
+        self._call("perc_write_txt", _i32(w), C.c_char_p(p), _i32(len(p)))
 
     def set_bond_conductance(self, w):
         """per-bond conductances (MATLAB/ConductCalc.m condtype = 2): w[nb] in the reference's bond-row order, used for the

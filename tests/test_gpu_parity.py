@@ -600,6 +600,78 @@ def test_warm_start_sweep(P, lat, kind, m, n):
         assert sum(w["iter"] for w in warm[1:]) < sum(c["iter"] for c in cold[1:])
 
 
+# ---- the reference programs' output files -------------------------------------------------------
+def _read_txt(path, ncol):
+    lines = open(path).read().split("\n")
+    assert lines[-1] == ""
+    rows = lines[:-1]
+    assert all(len(r) == 11 * ncol - 1 and r.count(",") == ncol - 1 for r in rows)      # i10 fields joined by commas
+    return np.array([[int(f) for f in r.split(",")] for r in rows], np.int64)
+
+
+def test_reference_output_files(P, O, tmp_path):
+    """perc_write_txt: site.txt / bond.txt / sbsite.txt / sbbond.txt / bondlist.txt in the reference's record formats
+    (Sq/site.f:354-359, Sq/bond.f:443-448, Sq/sitebond.f:469-477), contents = the getters' arrays = the oracle's"""
+    for lat in (1, 2):
+        m, n = 24, 20
+        t = m * n
+        b1, b2 = O.bondlist(lat, m, n, 0)
+        nb = len(b1)
+        sorder = O.shuffle_sites(1080115, t)
+        bo1, bo2 = O.shuffle_bonds(184489, b1, b2)
+        with P.Lattice(lat, m, n, 0) as L:
+            s, c, res = L.site(sorder, O.fill_count(0.6, t))
+            L.write_txt("site.txt", str(tmp_path / "site.txt"))
+            a = _read_txt(tmp_path / "site.txt", 3)
+            assert (a[:, 0] == np.arange(1, t + 1)).all() and (a[:, 1] == s).all() and (a[:, 2] == c).all()
+            socc = np.zeros(t, np.uint8); socc[sorder[:O.fill_count(0.6, t)] - 1] = 1
+            ws, wb, wsz, ncl, wmax = O.label_uf(O.SITE, lat, m, n, 0, b1, b2, site_occ=socc)
+            assert (a[:, 1] == ws).all() and (a[:, 2] == wsz[1:]).all()
+            with pytest.raises(P.PercError):
+                L.write_txt("bond.txt", str(tmp_path / "x.txt"))                 # no bond labeling on the handle
+            L.write_txt("bondlist.txt", str(tmp_path / "bondlist.txt"))
+            a = _read_txt(tmp_path / "bondlist.txt", 2)
+            assert (a[:, 0] == b1).all() and (a[:, 1] == b2).all()
+            b3, c, res = L.bond(bo1, bo2, O.fill_count(0.5, nb))
+            L.write_txt("bond.txt", str(tmp_path / "bond.txt"))
+            a = _read_txt(tmp_path / "bond.txt", 5)
+            assert (a[:, 0] == b1).all() and (a[:, 1] == b2).all() and (a[:, 2] == b3).all() and (a[:, 3] == np.arange(1, nb + 1)).all()
+            assert (a[:t, 4] == c).all() and (a[t:, 4] == 0).all()
+            s, b3, c, res = L.sitebond(sorder, O.fill_count(0.8, t), bo1, bo2, O.fill_count(0.6, nb))
+            L.write_txt("sbsite.txt", str(tmp_path / "sbsite.txt"))
+            L.write_txt("sbbond.txt", str(tmp_path / "sbbond.txt"))
+            a, b = _read_txt(tmp_path / "sbsite.txt", 3), _read_txt(tmp_path / "sbbond.txt", 3)
+            assert (a[:, 1] == s).all() and (a[:, 2] == c).all()
+            assert (b[:, 0] == b1).all() and (b[:, 1] == b2).all() and (b[:, 2] == b3).all()
+
+
+# ---- the bench configuration (square mixed L = 4096, ps 0.80, pb 0.70): every solver form on one realization ---------------
+def test_bench_configuration_solver_forms_agree(P):
+    """bench.py's first timed realization at its single-point fill: deflated one-pass, plain one-pass and two-kernel form at
+    tol 1e-13 agree to 1e-9 (the north star's tolerance) in Gtop and Gbot; the plain forms take linbcg's iteration count,
+    the deflated one several times fewer; a tol 1e-10 solve (the bench's tolerance) is within 1e-9 of the 1e-13 one"""
+    from percolation_b200.shard import stream_id
+    Lsz = 4096
+    with P.Lattice(1, Lsz, Lsz, 0) as L:
+        L.generate(20240611, stream_id(0, 3), int(0.80 * L.t), int(0.70 * L.nb))
+        L.label(P.MIXED)
+        assert L.summary()["nspan"] >= 1
+        res = {}
+        for mode in (0, 2, 1):
+            L.set_solver(mode)
+            res[mode] = L.conduct(0, tol=1e-13, itmax=4000000, voltages=False)
+            assert L.solver_used() == {0: 2, 2: 1, 1: 0}[mode] and res[mode]["err"] <= 1e-13
+        L.set_solver(0)
+        r10 = L.conduct(0, tol=1e-10, itmax=4000000, voltages=False)
+    a = res[1]
+    for mode in (0, 2):
+        b = res[mode]
+        assert abs(a["Gtop"] - b["Gtop"]) <= 1e-9 * abs(a["Gtop"]) and abs(a["Gbot"] - b["Gbot"]) <= 1e-9 * abs(a["Gbot"]), (mode, a, b)
+    assert abs(res[2]["iter"] - a["iter"]) <= max(3, a["iter"] // 100)
+    assert res[0]["iter"] * 3 < a["iter"]
+    assert abs(r10["Gtop"] - res[0]["Gtop"]) <= 1e-9 * abs(res[0]["Gtop"])
+
+
 # ---- conductance against the oracle's golden values (tests/golden/conduct_fixtures.json) -------------------------
 def _golden():
     import json
