@@ -326,7 +326,8 @@ int32_t perc_summary(const int64_t* h, int64_t* ncl, int32_t* maxcs, int32_t* ma
 int32_t perc_get_site_labels(const int64_t* h, int32_t* s)
 {
     GET_CTX(h);
-    if (!c->labeled || !s) return PERC_E_STATE;
+    if (!s) return PERC_E_ARG;
+    if (!c->labeled) return PERC_E_STATE;
     if (c->kind == KIND_BOND) { std::memset(s, 0, sizeof(int32_t) * c->g.t); return 0; }   // bond problem has no s()
     return download(c, s, c->label, sizeof(int32_t) * c->g.t);
 }
@@ -334,14 +335,16 @@ int32_t perc_get_site_labels(const int64_t* h, int32_t* s)
 int32_t perc_get_bond_labels(const int64_t* h, int32_t* b3)
 {
     GET_CTX(h);
-    if (!c->labeled || !b3) return PERC_E_STATE;
+    if (!b3) return PERC_E_ARG;
+    if (!c->labeled) return PERC_E_STATE;
     return ccl_export_bond_labels(c, b3);
 }
 
 int32_t perc_get_sizes(const int64_t* h, int32_t* cs)
 {
     GET_CTX(h);
-    if (!c->labeled || !cs) return PERC_E_STATE;
+    if (!cs) return PERC_E_ARG;
+    if (!c->labeled) return PERC_E_STATE;
     return ccl_export_sizes(c, cs);
 }
 
@@ -675,7 +678,8 @@ int32_t perc_span_i8(const int64_t* h, const int32_t* max_ids, int32_t* nspan, i
 int32_t perc_get_site_labels_i8(const int64_t* h, int64_t* s)
 {
     GET_CTX(h);
-    if (!c->labeled || !s) return PERC_E_STATE;
+    if (!s) return PERC_E_ARG;
+    if (!c->labeled) return PERC_E_STATE;
     return slab_export_labels(c, s);
 }
 

@@ -357,8 +357,10 @@ PERC_HD void tile_clear_ring(TileSmem& s, int tid)
 // site); mixed (Sq/sitebond.f:231-305) = site + owned occupied bonds + incoming occupied bonds whose
 // owner site is unoccupied (dangling onto this site).  A bond with no occupied end is a lone
 // size-1 cluster (Sq/sitebond.f:231-242), counted into s.lone.
-// VAR = 1 (opt-in, PERC_CCL_VAR=1): the per-site root staging below is skipped; tile_phase4_labels<1> derives
-// each site's root from its run start instead.  (VAR = 2: tile_phase3_pair below)
+// VAR = 0: the first form (per-site roots staged per run); VAR = 1: the staging is skipped, tile_phase4_labels<1> derives
+// each site's root from its run start instead.  The library runs VAR = 2 (tile_phase3_pair below: VAR = 1 with two runs
+// per trip of the per-run loop; on the GPU 0.166 ms against 0.197 for VAR = 0 at L = 4096 mixed); 0 and 1 are kept for the
+// host emulation's cross-check (tests/test_ccl_emulation.py).
 template <int LAT, int KIND, int VAR = 0>
 PERC_HD void tile_phase3(TileSmem& s, const Geom& g, int x0, int y0, int tid, TileRegs& r)
 {
@@ -455,8 +457,8 @@ PERC_HD void tile_phase3(TileSmem& s, const Geom& g, int x0, int y0, int tid, Ti
     r.rootbits = rootbits;
 }
 
-// VAR = 2 (opt-in, PERC_CCL_VAR=2) of phase 3: a copy of tile_phase3<.., 1> whose per-run loop takes two runs per trip
-// (kept as a separate function so that the default kernel's code is not touched until this one has run on a GPU)
+// VAR = 2 of phase 3 (the form the library runs): tile_phase3<.., 1> with a per-run loop that takes two runs per trip
+// (two find chains in flight)
 template <int LAT, int KIND>
 PERC_HD void tile_phase3_pair(TileSmem& s, const Geom& g, int x0, int y0, int tid, TileRegs& r)
 {

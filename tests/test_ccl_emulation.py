@@ -44,8 +44,8 @@ CASES = [(lat, m, n, pbc) for lat in (1, 2) for (m, n) in SHAPES for pbc in (0, 
 @pytest.mark.parametrize("var", [0, 1, 2])
 @pytest.mark.parametrize("lat,m,n,pbc", CASES)
 def test_emulated_ccl_matches_oracle(emul, O, lat, m, n, pbc, var):
-    """var = 0: the tile kernel as the library runs it; var = 1 / 2: its opt-in variants (PERC_CCL_VAR: per-site roots
-    derived in the label phase instead of staged per run; 2: and two runs per trip of the per-run loop)"""
+    """var = 2: the tile kernel as the library runs it (per-site roots derived in the label phase, two runs per trip of the
+    per-run loop); var = 0 / 1: its earlier forms (roots staged per run / one run per trip), kept as a cross-check"""
     emul.ccl_emul_set_variant(var)
     t = m * n
     b1, b2 = O.bondlist(lat, m, n, pbc)
