@@ -107,7 +107,7 @@ void ctx_free(Ctx* c)
     if (c->d_stitch) cudaFree(c->d_stitch);
     if (c->h_iface) cudaFreeHost(c->h_iface);
     void* ptrs[] = {c->srank, c->brank, c->mask, c->label, c->size, c->rootlist, c->d_sum, c->d_pcg,
-                    c->d_hist, c->d_thr, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vp2, c->vq, c->xprow, c->partial, c->d_stage, c->d_defl, c->bond_w, c->wplane, c->wdiag};
+                    c->d_hist, c->d_thr, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vp2, c->vq, c->xprow, c->partial, c->d_stage, c->d_defl, c->bond_w, c->wplane, c->wdiag, c->d_sched};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_pcg) cudaFreeHost(c->h_pcg);
     if (c->h_sum_pin) cudaFreeHost(c->h_sum_pin);

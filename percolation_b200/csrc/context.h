@@ -92,6 +92,8 @@ struct Ctx {
     double* h_defl = nullptr;     // pinned: E^-1, W
     size_t defl_bytes = 0;
     int defl_k = 0;               // coarse dimension of the last deflated solve
+    int* d_sched = nullptr;       // deflated sweep: which CTA walks which blocks (ft_defl_schedule)
+    int sched_key[6] = {0, 0, 0, 0, 0, 0};
     double* partial = nullptr;    // per-block partial sums
     int partial_cap = 0;
     PcgState* d_pcg = nullptr;

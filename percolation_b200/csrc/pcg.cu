@@ -695,7 +695,7 @@ __device__ __forceinline__ void block_sum3(double& a, double& b, double& c, doub
 // device arrays of the deflated iteration (FtCfgD; the others use D only: the order in which the tiles are visited):
 // mu[k] of the blocks (read by the sweep, rewritten by its coarse stage), Fb[FB_PLANES][FT_KMAX] crossing currents
 // summed per block, Einv[k][k] dense inverse of E = Z^T A Z
-struct FtDeflDev { FtDefl D; double* mu; double* Fb; const double* Einv; };
+struct FtDeflDev { FtDefl D; double* mu; double* Fb; const double* Einv; const int* sched; };
 constexpr int FW_VALID = 256;           // tcoord.z: FtWalk::info of the tile | FW_VALID
 
 template <int LAT, class C>
@@ -713,8 +713,8 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sh + 96);                      // one mbarrier per stage
     double* cinv = reinterpret_cast<double*>(bars + 2);                                             // [64] 1/d by bond counts (boundary tiles)
     int4* tcoord = reinterpret_cast<int4*>(cinv + 64);                                              // [2] tile (ix, iy, info | FW_VALID, block) of the two stages
-    FtWalk* wk_sm = reinterpret_cast<FtWalk*>(tcoord + 2);                                          // the producer's position on the lattice (32 bytes; in registers only while it moves)
-    double* sft = reinterpret_cast<double*>(tcoord + 4);                                            // [2][SFT_N] shift tables (deflation)
+    FtWalk* wk_sm = reinterpret_cast<FtWalk*>(tcoord + 2);                                          // the producer's position on the lattice (48 bytes; in registers only while it moves)
+    double* sft = reinterpret_cast<double*>(tcoord + 5);                                            // [2][SFT_N] shift tables (deflation)
     double* srec = sft + 2 * C::SFT_N;                                                              // [2][REC_N] ... and their per-row records
     double* sfl = srec + 2 * C::REC_N;                                                              // [256] row partials of the coarse product; scratch
     double* sru = sfl + 256;                                                                        // [THREADS] sum rho u' per main thread
@@ -749,7 +749,7 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         FtWalk wk;
-        wk.start(dd.D, (int)blockIdx.x, G, rev);
+        wk.start(dd.D, (int)blockIdx.x, G, rev, dd.sched);
         publish_issue(wk, 0);
         *wk_sm = wk;
     }
@@ -811,7 +811,7 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         const int ix = tc.x, iy = tc.y, x0 = ix * C::TX, y0 = iy * C::TY;
         if (tid == PROD) {                                       // the other stage was released by the barriers of the last tile
             FtWalk wk = *wk_sm;
-            wk.next(dd.D, G, rev);
+            wk.next(dd.D, G, rev, dd.sched);
             publish_issue(wk, (k + 1) & 1);
             *wk_sm = wk;
         }
@@ -1398,6 +1398,23 @@ static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
         dd.Einv = c->d_defl; dd.mu = c->d_defl + (size_t)dd.D.k * dd.D.k; dd.Fb = dd.mu + 2 * FT_KMAX;
         if ((dd.D.k + grid - 1) / grid > 32) return (int)cudaErrorInvalidConfiguration;   // (k <= 1024 and grid >= 32 SMs)
         c->defl_k = dd.D.k;
+        // which CTA walks which blocks (boundary tiles cost about twice an interior one); built once per lattice / block shape
+        double bcost = 2.0;
+        if (const char* e = getenv("PERC_DEFL_BCOST")) bcost = atof(e);                   // (experiments; 0: blocks bid, bid + G, ...)
+        const int key[6] = {g.m, g.n, dd.D.bw, dd.D.bh, grid, (int)(bcost * 1000)};
+        if (bcost > 0.0) {
+            if (!c->d_sched || memcmp(key, c->sched_key, sizeof(key)) != 0) {
+                std::vector<int> sch;
+                ft_defl_schedule<C>(g, dd.D, grid, bcost, sch);
+                if (c->d_sched) cudaFree(c->d_sched);
+                c->d_sched = nullptr;
+                PERC_CUDA(cudaMalloc(&c->d_sched, sizeof(int) * sch.size()));
+                PERC_CUDA(cudaMemcpyAsync(c->d_sched, sch.data(), sizeof(int) * sch.size(), cudaMemcpyHostToDevice, s));
+                PERC_CUDA(cudaStreamSynchronize(s));            // `sch` is pageable and goes out of scope
+                memcpy(c->sched_key, key, sizeof(key));
+            }
+            dd.sched = c->d_sched;
+        }
     }
     int cur = 0, pass = 0;
     Geom garg = g; PcgParams parg = prm;

@@ -6,6 +6,7 @@
 // bandwidth nbx + 1 in the ordering B = by * nbx + bx.  Plain C++ (no CUDA): pcg.cu calls it between the weight kernel
 // and the first sweep; tests/pcg_fused_emul.cpp calls the same code on the CPU.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <thread>
 #include <vector>
@@ -83,6 +84,37 @@ inline int ft_defl_build_einv(const FtDefl& D, const double* W, double* Einv, in
         for (auto& t : th) t.join();
     }
     return 0;
+}
+
+// Which CTA walks which blocks: tiles that touch the lattice border run the general code of the tile phases (about twice the
+// time of an interior tile), and a block on the left / right edge consists of such tiles only.  Longest-processing-time-first
+// over the blocks' costs, then every CTA's list in ascending block order.  out = offsets [G + 1] followed by the lists [k].
+template <class C>
+inline void ft_defl_schedule(const Geom& g, const FtDefl& D, int G, double boundary_cost, std::vector<int>& out)
+{
+    std::vector<double> cost((size_t)D.k, 0.0);
+    for (int iy = 0; iy < D.nty; ++iy)
+        for (int ix = 0; ix < D.ntx; ++ix)
+            cost[ft_defl_block(D, ix, iy)] += ft_interior<C>(g, ix * C::TX, iy * C::TY) ? 1.0 : boundary_cost;
+    std::vector<int> order((size_t)D.k);
+    for (int B = 0; B < D.k; ++B) order[B] = B;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    std::vector<double> load((size_t)G, 0.0);
+    std::vector<std::vector<int>> lists((size_t)G);
+    for (int B : order) {
+        int best = 0;
+        for (int c = 1; c < G; ++c) if (load[c] < load[best]) best = c;
+        load[best] += cost[B];
+        lists[best].push_back(B);
+    }
+    out.assign((size_t)G + 1 + D.k, 0);
+    int off = 0;
+    for (int c = 0; c < G; ++c) {
+        std::sort(lists[c].begin(), lists[c].end());
+        out[c] = off;
+        for (int B : lists[c]) out[(size_t)G + 1 + off++] = B;
+    }
+    out[G] = off;
 }
 
 }  // namespace perc

@@ -65,7 +65,7 @@ struct FtCfg {
     // mu / Z^T A u' of every block, row partials of the coarse product (+ scratch), rho u' per main thread, slot totals of a
     // tile and the running sums of its block
     static constexpr int COARSE_BYTES = DEFL ? FT_KMAX * 8 + 256 * 8 + THREADS * 8 + 16 * 8 + RHO_BYTES : 0;
-    static constexpr int SMEM = 2 * STAGE_BYTES + U_BYTES + TAB_BYTES + 96 * 8 + 16 + 64 * 8 + 4 * 16 + SHIFT_BYTES + COARSE_BYTES;
+    static constexpr int SMEM = 2 * STAGE_BYTES + U_BYTES + TAB_BYTES + 96 * 8 + 16 + 64 * 8 + 5 * 16 + SHIFT_BYTES + COARSE_BYTES;
     // table of diagonals of the sites with ALL their neighbours, indexed by which of them conduct (ft_pat: 16 patterns on
     // the square lattice, 2 x 64 on the triangular one) -- the diagonal depends on the pattern, not only on the counts: it is
     // the reference's sum in ascending neighbour order (diag_seq).  Private copies per lane: 32 (square) / 16 (triangular).
@@ -258,6 +258,7 @@ PERC_HD double ft_defl_rec_entry(const double* sft, int lr, int e)
 // (consecutive iterations sweep in opposite directions: each starts on what L2 still holds).
 struct FtWalk {
     int B, bx, by, w, h, jx, jy;
+    int pos, lo, hi;                   // with a schedule: position in this CTA's list of blocks [lo, hi)
     PERC_HD bool valid(const FtDefl& D) const { return B >= 0 && B < D.k; }
     PERC_HD void enter(const FtDefl& D, int rev)
     {
@@ -266,15 +267,28 @@ struct FtWalk {
         h = D.nty - by * D.bh < D.bh ? D.nty - by * D.bh : D.bh;
         jx = rev ? w - 1 : 0; jy = rev ? h - 1 : 0;
     }
-    PERC_HD void start(const FtDefl& D, int bid, int G, int rev)
+    // sched = nullptr: block bid, bid + G, ...; else sched[0 .. G] = offsets of the CTAs' lists, which follow (ascending block
+    // numbers; built on the host so that the slower boundary tiles are spread evenly: ft_defl_schedule)
+    PERC_HD void start(const FtDefl& D, int bid, int G, int rev, const int* sched = nullptr)
     {
-        B = bid < D.k ? (rev ? bid + ((D.k - 1 - bid) / G) * G : bid) : -1;
+        pos = lo = hi = 0;
+        if (sched) {
+            lo = sched[bid]; hi = sched[bid + 1];
+            pos = rev ? hi - 1 : lo;
+            B = lo < hi ? sched[G + 1 + pos] : -1;
+        } else B = bid < D.k ? (rev ? bid + ((D.k - 1 - bid) / G) * G : bid) : -1;
         if (valid(D)) enter(D, rev);
     }
-    PERC_HD void next(const FtDefl& D, int G, int rev)
+    PERC_HD void next_block(const FtDefl& D, int G, int rev, const int* sched)
     {
-        if (!rev) { if (++jx == w) { jx = 0; if (++jy == h) { B += G; if (valid(D)) enter(D, 0); } } }
-        else      { if (--jx < 0) { jx = w - 1; if (--jy < 0) { B -= G; if (valid(D)) enter(D, 1); } } }
+        if (sched) { pos += rev ? -1 : 1; B = (pos >= lo && pos < hi) ? sched[G + 1 + pos] : -1; }
+        else B += rev ? -G : G;
+        if (valid(D)) enter(D, rev);
+    }
+    PERC_HD void next(const FtDefl& D, int G, int rev, const int* sched = nullptr)
+    {
+        if (!rev) { if (++jx == w) { jx = 0; if (++jy == h) next_block(D, G, 0, sched); } }
+        else      { if (--jx < 0) { jx = w - 1; if (--jy < 0) next_block(D, G, 1, sched); } }
     }
     PERC_HD int ix(const FtDefl& D) const { return bx * D.bw + jx; }
     PERC_HD int iy(const FtDefl& D) const { return by * D.bh + jy; }
