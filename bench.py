@@ -580,6 +580,19 @@ def run_ours(args):
                   "realizations_per_s": args.single_steps / dt, "mean_pcg_iterations": float(np.mean([r["iter"] for r in res[1:]])),
                   "G": [0.5 * (r["Gtop"] + r["Gbot"]) for r in res[1:]]}
 
+    # ---- the same sweep WITHOUT deflation on the same lattice (plain one-pass kernel, capped): its launch time / roofline
+    plain = None
+    if rank == 0 and args.plain_iters > 0:
+        kb1 = int(args.pb * nb)
+        L.generate(SEED, stream_id(0, 1), ks, kb1)
+        L.label(P.MIXED)
+        L.set_solver(2)
+        rp = L.conduct(0, tol=1e-30, itmax=args.plain_iters, voltages=False)
+        php = L.phase_ms()
+        L.set_solver(solver_mode)
+        plain = {"kernel": "pcg_fused_kernel<FtCfgA3> (perc_set_solver 2: the same one-pass sweep without deflation, linbcg's iterates)",
+                 "iterations_timed": rp["iter"], "avg_launch_ms": float(php[6])}
+
     # ---- accuracy of the bench's tolerance: the first timed realization's sweep point at a 1e-13 solve
     acc = None
     if rank == 0 and args.check_tol:
@@ -671,6 +684,11 @@ def run_ours(args):
             line["extra"]["single_point"] = single
         if acc:
             line["extra"]["tolerance_check"] = acc
+        if plain:
+            pa = 33.0 * interior / (max(plain["avg_launch_ms"], 1e-9) * 1e-3) / 1e9
+            plain.update({"achieved_gbs": pa, "frac": pa / peak, "algorithmic_bytes_per_launch": 33.0 * interior,
+                          "traffic": ncu_traffic_bytes("pcg_fused_kernel") if Lsz == 4096 else None})
+            line["extra"]["plain_one_pass_kernel"] = plain
         if fused == 0 and upd_ms > 0:
             line["extra"]["pcg_pipe_kernel<1> (residual update, A p recomputed)"] = {
                 "achieved_gbs": upd_bytes / (upd_ms * 1e-3) / 1e9, "frac": upd_bytes / (upd_ms * 1e-3) / 1e9 / peak,
@@ -728,6 +746,7 @@ def main():
     ap.add_argument("--itmax", type=int, default=2000000,
                     help="iteration cap of a solve (the cap bounds the run time; all_solves_converged reports whether it was hit)")
     ap.add_argument("--e2e-steps", type=int, default=-1)
+    ap.add_argument("--plain-iters", type=int, default=3000, help="iterations of the plain one-pass kernel timed for extra.plain_one_pass_kernel (0: skip)")
     ap.add_argument("--single-steps", type=int, default=2, help="realizations of the single-point leg (extra.single_point)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU arm (0 = every core this process may use)")
     ap.add_argument("--cpu-cg-iters", type=int, default=10)

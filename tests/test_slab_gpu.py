@@ -35,7 +35,7 @@ def test_two_handles_on_two_devices_in_one_process():
         out = {}
         for stream in (0, 1):
             for name, L in (("a", A), ("b", B)):
-                L.generate(4711, stream, int(0.8 * L.t), int(0.7 * L.nb))
+                L.generate(4711, stream, int(0.8 * L.t), int(0.75 * L.nb))
             for name, L in (("b", B), ("a", A)):                          # interleaved: label on 1, then on 0
                 L.label(P.MIXED)
             for mode in (0, 2, 1):                                         # deflated one-pass, plain one-pass, two-kernel form
