@@ -197,6 +197,8 @@ int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double 
     std::vector<uint8_t> scf((size_t)C::RR * C::CLD);
     int cur = 0;
     double esum = 0.0;
+    std::vector<int> sched;
+    ft_defl_schedule<C>(g, D, 5, 2.0, sched);
     for (int pass = 0; !st.done; ++pass) {
         const int prime = pass == 0;
         const FtScalars sc{g0, gleak, prime ? 0.0 : st.alpha, prime ? 0.0 : st.beta};
@@ -209,11 +211,15 @@ int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double 
         double rz = 0.0, rr = 0.0, en = 0.0;
         // the kernel's walk (FtWalk) as a grid of GRID CTAs runs it, forwards and backwards in turn: block by block, the slot
         // totals of a tile folded into the running sums of its block, which go out with the block's last tile
+        // (every third pass with the host-built schedule of the library -- ft_defl_schedule: boundary tiles spread over the CTAs)
         const int GRID = 5, rev = pass & 1;
+        const int* schp = (pass % 3 == 2) ? sched.data() : nullptr;
+        int visited = 0;
         for (int bid = 0; bid < GRID; ++bid) {
             FtWalk wk;
             double bacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            for (wk.start(D, bid, GRID, rev); wk.valid(D); wk.next(D, GRID, rev)) {
+            for (wk.start(D, bid, GRID, rev, schp); wk.valid(D); wk.next(D, GRID, rev, schp)) {
+                ++visited;
                 const int ix = wk.ix(D), iy = wk.iy(D), x0 = ix * C::TX, y0 = iy * C::TY, info = wk.info(D, rev);
                 if (ft_defl_block(D, ix, iy) != wk.B) return -6;
                 box_copy(sr.data(), r[cur].data(), m, n, x0 - 2, y0 - 1, C::LD, C::RR);
@@ -241,6 +247,7 @@ int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double 
                 if (info & FW_LAST) for (int q = 0; q < FB_PLANES; ++q) { Fb[(size_t)q * FT_KMAX + wk.B] = bacc[q]; bacc[q] = 0.0; }
             }
         }
+        if (visited != ntiles) return -7;                     // every tile exactly once (the sums below would not notice a repeat)
         // coarse stage
         std::vector<double> f((size_t)D.k);
         for (int B = 0; B < D.k; ++B) f[B] = ft_defl_block_f(D, Fb.data(), B);
