@@ -1117,6 +1117,8 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
     double* sh = sx + 2 * m;                                 // 2 x 32 partials + 2 results
     double2* tab = reinterpret_cast<double2*>(sh + 66);      // 64 x (d, 1/d)
     uint8_t* scf = reinterpret_cast<uint8_t*>(tab + 64);
+    uint8_t* sidx = scf + t;                                 // per site: index into dtab (sites with all their neighbours), 255 = compute
+    double* dtab = reinterpret_cast<double*>(sm_raw + (((size_t)(sidx + t - sm_raw)) + 15) / 16 * 16);     // [128] diagonal by conduct pattern
     const int tid = threadIdx.x;
     const uint8_t* cfg = cfbatch + (size_t)blockIdx.x * t;
     bool any = false;
@@ -1127,15 +1129,32 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
         if (tid == 0) { Gout[2 * blockIdx.x] = 0.0; Gout[2 * blockIdx.x + 1] = 0.0; iters[blockIdx.x] = -1; errs[blockIdx.x] = 0.0; }
         return;
     }
+    // The diagonal is the reference's ordered row sum (diag_seq): for a site with all its neighbours away from the periodic
+    // seam it depends only on which of them conduct -- a table of 16 (square) / 2 x 64 (triangular: m is even, so the parity
+    // of x is the parity of the site index) entries, looked up through a byte per site; the few border sites are computed.
+    if (tid < 128) dtab[tid] = ft_diag_entry<LAT>(g, tid < (LAT == LAT_SQUARE ? 16 : 128) ? tid : 0, prm.g0, prm.gleak).d;
+    for (int i = tid; i < t; i += SM_THREADS) {
+        const int x = i % m, y = i / m, par = LAT == LAT_TRIANGULAR ? (x & 1) : 0;
+        const unsigned ex = neighbour_bits(g, x, y);
+        const bool table = ex == ft_interior_ex<LAT>(par) && !(g.pbc && (x == 0 || x == m - 1));
+        sidx[i] = table ? (uint8_t)ft_pat<LAT>(scf[i] & ex, par) : (uint8_t)255;
+    }
+    __syncthreads();
+    // (ex, conducting bits, diagonal) of site i
+    auto site = [&](int i, unsigned& ex, unsigned& cf, double& d) {
+        const unsigned idx = sidx[i];
+        if (idx != 255u) { ex = ft_interior_ex<LAT>(LAT == LAT_TRIANGULAR ? (i & 1) : 0); cf = scf[i] & ex; d = dtab[idx]; }
+        else { const int x = i % m; ex = neighbour_bits(g, x, i / m); cf = scf[i] & ex; d = diag_seq(g, cf, ex, x, prm.g0, prm.gleak); }
+    };
     // r = b (bonds from row n-2 into the top row at Va), p = 0; bnrm = |D^-1 b|, bknum = b.z
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     for (int i = tid; i < t; i += SM_THREADS) {
-        const int x = i % m, y = i / m;
         double b = 0.0;
-        if (y == g.n - 2 && y >= 1) {
-            const unsigned ex = neighbour_bits(g, x, y), cf = scf[i];
-            b = rhs_seq(g, cf, ex, x, prm.g0, prm.gleak, prm.Va);
-            const double z = b / diag_seq(g, cf & ex, ex, x, prm.g0, prm.gleak);
+        if (i >= t - 2 * m && i < t - m && i >= m) {
+            unsigned ex, cf; double d;
+            site(i, ex, cf, d);
+            b = rhs_seq(g, cf, ex, i % m, prm.g0, prm.gleak, prm.Va);
+            const double z = b / d;
             s0 += z * z; s1 += b * z; s2 += b * b;
         }
         sr[i] = b; sp[i] = 0.0;
@@ -1148,12 +1167,10 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
     int iter = 0;
     for (;;) {
         // p = r / d + bk p  (interior rows)
-        for (int i = tid; i < t; i += SM_THREADS) {
-            const int y = i / m;
-            if (y < 1 || y >= g.n - 1) continue;
-            const int x = i - y * m;
-            const unsigned ex = neighbour_bits(g, x, y), cf = scf[i];
-            sp[i] = sr[i] / diag_seq(g, cf & ex, ex, x, prm.g0, prm.gleak) + bk * sp[i];
+        for (int i = tid + m; i < t - m; i += SM_THREADS) {
+            unsigned ex, cf; double d;
+            site(i, ex, cf, d);
+            sp[i] = sr[i] / d + bk * sp[i];
         }
         __syncthreads();
         // q = A p, p.q
@@ -1162,19 +1179,18 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
         for (int k = 0; k < SM_KMAX; ++k) {
             q[k] = 0.0;
             const int i = tid + k * SM_THREADS;
-            if (k >= K || i >= t) continue;
-            const int y = i / m;
-            if (y < 1 || y >= g.n - 1) continue;
-            const int x = i - y * m, row = i - x;
-            const unsigned ex = neighbour_bits(g, x, y), cf = scf[i];
-            const int xl = x > 0 ? x - 1 : m - 1, xr = x + 1 < m ? x + 1 : 0;
+            if (k >= K || i < m || i >= t - m) continue;
+            unsigned ex, cf; double d;
+            site(i, ex, cf, d);
+            int xl = i - 1, xr = i + 1;                        // west / east neighbour (wrapped at the seam)
+            if (sidx[i] == 255u) { const int x = i % m; if (x == 0) xl = i + m - 1; if (x == m - 1) xr = i - (m - 1); }
             double all = 0.0, con = 0.0;
 #define NBR(bit, j) if (ex & bit) { const double v = sp[j]; all += v; if (cf & bit) con += v; }
-            NBR(NB_E, row + xr) NBR(NB_W, row + xl) NBR(NB_N, i + m) NBR(NB_S, i - m)
-            if (LAT == LAT_TRIANGULAR) { NBR(NB_NW, row + m + xl) NBR(NB_NE, row + m + xr) NBR(NB_SW, row - m + xl) NBR(NB_SE, row - m + xr) }
+            NBR(NB_E, xr) NBR(NB_W, xl) NBR(NB_N, i + m) NBR(NB_S, i - m)
+            if (LAT == LAT_TRIANGULAR) { NBR(NB_NW, xl + m) NBR(NB_NE, xr + m) NBR(NB_SW, xl - m) NBR(NB_SE, xr - m) }
 #undef NBR
             const double pc = sp[i];
-            q[k] = diag_seq(g, cf & ex, ex, x, prm.g0, prm.gleak) * pc - (prm.g0 * con + prm.gleak * (all - con));
+            q[k] = d * pc - (prm.g0 * con + prm.gleak * (all - con));
             dot += pc * q[k];
         }
         const double akden = sm_block_sum(dot, sh);
@@ -1184,16 +1200,14 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
 #pragma unroll
         for (int k = 0; k < SM_KMAX; ++k) {
             const int i = tid + k * SM_THREADS;
-            if (k >= K || i >= t) continue;
-            const int y = i / m;
-            if (y < 1 || y >= g.n - 1) continue;
-            const int x = i - y * m;
-            const unsigned ex = neighbour_bits(g, x, y), cf = scf[i];
+            if (k >= K || i < m || i >= t - m) continue;
+            unsigned ex, cf; double d;
+            site(i, ex, cf, d);
             const double r = sr[i] - ak * q[k];
             sr[i] = r;
-            if (y == 1) sx[x] += ak * sp[i];
-            if (y == g.n - 2) sx[m + x] += ak * sp[i];         // (n = 3: row 1 is both; the read-out uses sx[x])
-            rz += r * r / diag_seq(g, cf & ex, ex, x, prm.g0, prm.gleak);
+            if (i < 2 * m) sx[i - m] += ak * sp[i];
+            if (i >= t - 2 * m) sx[m + i - (t - 2 * m)] += ak * sp[i];     // (n = 3: row 1 is both; the read-out uses sx[x])
+            rz += r * r / d;
             rr += r * r;
         }
         const double2 fs = sm_block_sum2(rz, rr, sh);
@@ -1231,7 +1245,7 @@ pcg_small_kernel(Geom g, PcgParams prm, const uint8_t* __restrict__ cfbatch, dou
     }
 }
 
-static size_t small_smem_bytes(const Geom& g) { return sizeof(double) * (2 * (size_t)g.t + 2 * (size_t)g.m + 66) + sizeof(double2) * 64 + (size_t)g.t + 16; }
+static size_t small_smem_bytes(const Geom& g) { return sizeof(double) * (2 * (size_t)g.t + 2 * (size_t)g.m + 66 + 128) + sizeof(double2) * 64 + 2 * (size_t)g.t + 32; }
 
 bool pcg_small_fits(const Geom& g) { return g.t <= (int64_t)SM_KMAX * SM_THREADS && small_smem_bytes(g) <= 227 * 1024 && g.n >= 3; }
 
