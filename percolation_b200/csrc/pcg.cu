@@ -703,7 +703,8 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS)
 pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_s,
                  const __grid_constant__ CUtensorMap tm_cf, Geom g, PcgParams prm, double* __restrict__ r_out,
                  double* __restrict__ s_out, double* __restrict__ xrow, double* __restrict__ prow,
-                 double* __restrict__ partial, PcgState* __restrict__ st, int rev, int prime, FtDeflDev dd)
+                 double* __restrict__ partial, PcgState* __restrict__ st, int rev, int prime, FtDeflDev dd,
+                 const double* __restrict__ u_in, const double* __restrict__ s_in, const uint8_t* __restrict__ cfull)
 {
     if (st->done) return;
     extern __shared__ __align__(128) unsigned char ft_raw[];
@@ -830,6 +831,11 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         const double* sftk = C::DEFL ? sft + (k & 1) * C::SFT_N : nullptr;
         const double* sreck = C::DEFL ? srec + (k & 1) * C::REC_N : nullptr;
         const bool interior = ft_interior<C>(g, x0, y0);
+        if (C::USTATE && g.pbc && (x0 == 0 || x0 + C::TX == g.m)) {
+            // periodic wrap: the halo columns beyond the seam come straight from the input vectors (uniform over the CTA)
+            if (tid >= C::RING_T0) ft_wrap_patch<C>(g, x0, y0, u_in, s_in, cfull, const_cast<double*>(sr), ss, const_cast<uint8_t*>(scf), tid - C::RING_T0, C::RING_NT);
+            __syncthreads();
+        }
         if (!C::USTATE) {
             ft_phase_u<LAT, C>(g, sr, scf, su, dtab, x0, y0, interior, tid, prm.g0, prm.gleak, cinv);
             __syncthreads();
@@ -1321,7 +1327,8 @@ bool pcg_fused_applies(const Ctx* c, int keep_x, int warm)
 {
     const Geom& g = c->g;
     const int mode = c->pcg_mode >= 0 ? c->pcg_mode : pcg_default_mode();
-    return mode != 1 && !keep_x && !warm && c->nranks == 1 && !g.pbc && (g.m % 16) == 0 && g.n >= 4;
+    // (periodic wrap: the plain one-pass kernel only, and only when the seam falls on a tile border)
+    return mode != 1 && !keep_x && !warm && c->nranks == 1 && (!g.pbc || g.m % FtCfgA3::TX == 0) && (g.m % 16) == 0 && g.n >= 4;
 }
 
 // V = 3 of the one-pass kernel keeps u = D^-1 r in HBM: turn the initial residual into u (the unknown rows only;
@@ -1435,8 +1442,9 @@ static int pcg_fused_loop_t(Ctx* c, const PcgParams& prm)
     auto launch = [&](int prime) -> cudaError_t {
         int rev = pass & 1;
         double* ro = rbuf[cur ^ 1]; double* so = sbuf[cur ^ 1];
+        const double* ui = rbuf[cur]; const double* si = sbuf[cur]; const uint8_t* cfp = c->cfull;
         void* args[] = {&tm_r[cur], &tm_s[cur], &tm_cf, &garg, &parg, &ro, &so, &xrow, &prow, &c->partial, &c->d_pcg,
-                        &rev, &prime, &dd};
+                        &rev, &prime, &dd, &ui, &si, &cfp};
         const void* fn = g.lattice == LAT_SQUARE ? (const void*)pcg_fused_kernel<LAT_SQUARE, C> : (const void*)pcg_fused_kernel<LAT_TRIANGULAR, C>;
         // the deflated sweep ends with a grid-wide stage: cooperative launch (all CTAs resident: one per SM)
         cudaError_t e = C::DEFL ? cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(C::THREADS), args, C::SMEM, s)
@@ -1488,6 +1496,7 @@ static int pcg_fused_loop(Ctx* c, const PcgParams& prm)
     const int mode = c->pcg_mode >= 0 ? c->pcg_mode : pcg_default_mode();
     int use = c->fused_cfg >= 0 ? c->fused_cfg : (mode == 2 ? 2 : 4);
     if (const char* e = getenv("PERC_FUSED_CFG")) if (c->fused_cfg < 0 && (*e == '1' || *e == '3' || *e == '5')) use = *e - '1';
+    if (c->g.pbc) use = 2;                // the deflated sweep and the first variant have no periodic wrap
     c->last_fused_cfg = use;
     if (use == 4) return pcg_fused_loop_t<FtCfgD>(c, prm);
     if (use == 2) return pcg_fused_loop_t<FtCfgA3>(c, prm);

@@ -477,6 +477,30 @@ PERC_HD double ft_defl_u0(const Geom& g, const FtDefl& D, unsigned cf, const dou
     return d > 0.0 ? (b - acc) / d : 0.0;
 }
 
+// ---- periodic wrap in x (pbc = 1; one-pass kernel with u as the state vector, m a multiple of TX) ----------------------
+// a site of the first / last lattice column with pbc: its wrapped neighbours change their place in the reference's ordered
+// diagonal sum (diag_seq), so its diagonal is computed, not taken from the pattern table
+PERC_HD bool ft_seam(const Geom& g, int gx) { return g.pbc && (gx == 0 || gx == g.m - 1); }
+// The TMA boxes of the first / last tile of a lattice row hold zeros in the halo columns beyond the seam; before the tile
+// phases run, the ring threads (rl of nthr) overwrite them with the wrapped columns read straight from the input vectors.
+// Work item q = (side, staged row): side 0 = west halo of a tile with x0 = 0 (lattice columns m-2, m-1), side 1 = east halo
+// of a tile with x0 + TX = m (lattice columns 0, 1).
+template <class C>
+PERC_HD void ft_wrap_patch(const Geom& g, int x0, int y0, const double* u_in, const double* s_in, const uint8_t* cfull,
+                           double* sr, double* ss, uint8_t* scf, int rl, int nthr)
+{
+    for (int q = rl; q < 2 * C::RR; q += nthr) {
+        const int side = q >= C::RR, pr = q - side * C::RR, gy = y0 - 1 + pr;
+        if (side == 0 ? x0 != 0 : x0 + C::TX != g.m) continue;
+        if (gy < 0 || gy >= g.n) continue;
+        const int gx = side ? 0 : g.m - 2, col = side ? 2 + C::TX : 0;     // lattice columns gx, gx + 1 -> box columns col, col + 1
+        const int64_t o = (int64_t)gy * g.m + gx;
+        sr[pr * C::LD + col] = u_in[o]; sr[pr * C::LD + col + 1] = u_in[o + 1];
+        scf[pr * C::CLD + (side ? 16 + C::TX : 14)] = cfull[o]; scf[pr * C::CLD + (side ? 17 + C::TX : 15)] = cfull[o + 1];
+        if (pr >= 1 && pr <= C::SR) { ss[(pr - 1) * C::LD + col] = s_in[o]; ss[(pr - 1) * C::LD + col + 1] = s_in[o + 1]; }
+    }
+}
+
 // ---- phase U: u = r / d on the staged box (tile + 2-site halo; rows y0-1 .. y0+TY+1) -------------------------
 template <int LAT, class C>
 PERC_HD void ft_phase_u(const Geom& g, const double* sr, const uint8_t* scf, double* su, const FtDiag* dtab,
@@ -597,7 +621,7 @@ PERC_HD void ft_phase_main(const Geom& g, const FtScalars& sc, const double* sr,
         // (gx is even: the thread's first column is an up-type site on the triangular lattice, its second a down-type one)
         const int i0 = C::tabp(LAT, ft_pat<LAT>(cf0, 0), lane), i1 = C::tabp(LAT, ft_pat<LAT>(cf1, 1), lane);
         // (boundary tiles: only the sites ON the lattice border lack neighbours; every other site is in the table as well)
-        const bool full0 = interior || e0 == ft_interior_ex<LAT>(gx), full1 = interior || e1 == ft_interior_ex<LAT>(gx + 1);
+        const bool full0 = interior || (e0 == ft_interior_ex<LAT>(gx) && !ft_seam(g, gx)), full1 = interior || (e1 == ft_interior_ex<LAT>(gx + 1) && !ft_seam(g, gx + 1));
         const FtDiag t0 = full0 ? dtab[i0] : ft_diag_site(g, cf0, e0, gx, sc.g0, sc.gleak, cinv);
         const FtDiag t1 = full1 ? dtab[i1] : ft_diag_site(g, cf1, e1, gx + 1, sc.g0, sc.gleak, cinv);
         // off-diagonal part with the weights g0 and gleak THEMSELVES (g0 con + gleak (all - con)): a rounded g0 - gleak would be
@@ -655,7 +679,9 @@ PERC_HD void ft_ring_site(const Geom& g, const FtScalars& sc, const double* sr, 
 {
     constexpr bool interior = INT;
     constexpr int col = SIDE ? 2 + C::TX : 1;
-    const int gy = y0 + lr, gx = SIDE ? x0 + C::TX : x0 - 1;
+    const int gy = y0 + lr;
+    int gx = SIDE ? x0 + C::TX : x0 - 1;
+    if (!interior && g.pbc) gx = gx < 0 ? g.m - 1 : (gx >= g.m ? 0 : gx);      // (the wrapped column: its values were patched into the box)
     double un = 0.0;
     if (interior || (gy >= 1 && gy <= g.n - 2 && gx >= 0 && gx < g.m)) {
         const unsigned ex = interior ? ft_interior_ex<LAT>(gx) : neighbour_bits(g, gx, gy);
@@ -676,7 +702,7 @@ PERC_HD void ft_ring_site(const Geom& g, const FtScalars& sc, const double* sr, 
         }
 #undef FT_NB
         const int it = C::tabp(LAT, ft_pat<LAT>(cf, gx & 1), lane);
-        const bool full = interior || ex == ft_interior_ex<LAT>(gx);
+        const bool full = interior || (ex == ft_interior_ex<LAT>(gx) && !ft_seam(g, gx));
         const FtDiag t = full ? dtab[it] : ft_diag_site(g, cf, ex, gx, sc.g0, sc.gleak, cinv);
         double w = t.d * c[0] - (sc.g0 * con + sc.gleak * (all - con));
         if (C::DEFL) {

@@ -96,6 +96,9 @@ int solve(const Geom& g, const std::vector<uint8_t>& cf, double Va, double g0, d
             box_copy(ss.data(), s[cur].data(), m, n, x0 - 2, y0, C::LD, C::SR);
             box_copy(scf.data(), cf.data(), m, n, x0 - 16, y0 - 1, C::CLD, C::RR);
             for (auto& v : su) v = NAN;                        // shared memory starts as garbage
+            if (C::USTATE && g.pbc && (x0 == 0 || x0 + C::TX == m))   // periodic wrap: the ring threads patch the halo columns
+                for (int rl = 0; rl < C::RING_NT; ++rl)
+                    ft_wrap_patch<C>(g, x0, y0, r[cur].data(), s[cur].data(), cf.data(), sr.data(), ss.data(), scf.data(), rl, C::RING_NT);
             const bool interior = ft_interior<C>(g, x0, y0);
             if (prime && interior) ++*tiles_fast;
             if (!C::USTATE)
@@ -299,10 +302,11 @@ int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double 
 // (the ones pcg.cu instantiates)
 extern "C" int fused_emul_solve(int lattice, int m, int n, const double* w, double Va, double g0, double gleak,
                                 double tol, int itmax, double read_thresh, double* Gtop, double* Gbot, int* iter,
-                                double* err, int* tiles_fast, int cfg)
+                                double* err, int* tiles_fast, int cfg, int pbc)
 {
     if (m % 16 || n < 4) return -2;
-    const Geom g = make_geom(lattice, m, n, 0);
+    if (pbc && (cfg != 2 || m % FtCfgA3::TX)) return -2;     // (what pcg_fused_applies admits)
+    const Geom g = make_geom(lattice, m, n, pbc);
     std::vector<uint8_t> cf;
     build_cfull(g, w, gleak, cf);
 #define RUN(CFG) (lattice == LAT_SQUARE ? solve<LAT_SQUARE, CFG>(g, cf, Va, g0, gleak, tol, itmax, read_thresh, Gtop, Gbot, iter, err, tiles_fast) \

@@ -369,6 +369,51 @@ def test_one_pass_solver_equals_two_kernel_solver(P, O, lat, kind, m, n, ps, pb)
         assert found >= 1
 
 
+@pytest.mark.parametrize("lat,kind,m,n,ps,pb", [(1, 3, 128, 60, 0.85, 0.70), (1, 2, 256, 101, 0.0, 0.55), (2, 1, 256, 70, 0.56, 0.0),
+                                                   (2, 3, 384, 66, 0.8, 0.6), (1, 3, 1024, 256, 0.80, 0.70)])
+def test_one_pass_solver_with_periodic_wrap(P, O, lat, kind, m, n, ps, pb):
+    """pbc = 1 with the seam on a tile border (m a multiple of 128): perc_conduct_g runs the plain one-pass kernel (the halo
+    columns beyond the seam are patched into the TMA boxes); against the two-kernel form on the same handle and, for the small
+    shapes, the oracle.  The deflated sweep has no periodic wrap: the automatic mode falls back to the plain one-pass kernel."""
+    with P.Lattice(lat, m, n, 1) as L:
+        t, nb = L.t, L.nb
+        found = 0
+        for stream in range(6):
+            L.generate(4712, stream, int(ps * t) if kind != 2 else -1, int(pb * nb) if kind != 1 else -1)
+            L.label(kind)
+            ids, _ = L.span()
+            if not len(ids):
+                continue
+            found += 1
+            for tol, itmax in ((1e-13, 2000000), (1e-8, 2500)):
+                L.set_solver(1)
+                a = L.conduct(0, tol=tol, itmax=itmax, voltages=False)
+                assert L.solver_used() == 0
+                for mode in (2, 0):
+                    L.set_solver(mode)
+                    b = L.conduct(0, tol=tol, itmax=itmax, voltages=False)
+                    assert L.solver_used() == 1
+                    rel = 1e-9 if tol < 1e-10 else 1e-6
+                    if a["iter"] > itmax:
+                        rel = max(rel, a["err"])
+                    assert abs(a["Gtop"] - b["Gtop"]) <= rel * abs(a["Gtop"]), (mode, tol, a, b)
+                    assert abs(a["Gbot"] - b["Gbot"]) <= rel * abs(a["Gbot"]), (mode, tol, a, b)
+                    assert abs(a["iter"] - b["iter"]) <= max(3, a["iter"] // 100), (mode, tol, a, b)
+            if t <= 60000:
+                b1, b2 = O.bondlist(lat, m, n, 1)
+                socc, bocc = L.get_occupancy(sites=kind != 2, bonds=kind != 1)
+                ws, wb, wsz, ncl, wmax = O.label_uf(kind, lat, m, n, 1, b1, b2, site_occ=socc, bond_occ=bocc)
+                w = O.weights(kind, b1, b2, ws, wb, int(ids[0]))
+                ref = O.conduct_cg(m, n, b1, b2, w, tol=1e-13, itmax=2000000)
+                L.set_solver(0)
+                b = L.conduct(0, tol=1e-13, itmax=2000000, voltages=False)
+                assert abs(b["Gtop"] - ref["Gtop"]) <= 1e-9 * abs(ref["Gtop"])
+                assert abs(b["Gbot"] - ref["Gbot"]) <= 1e-9 * abs(ref["Gbot"])
+            if found == 2 or t > 60000:
+                break
+        assert found >= 1
+
+
 def test_first_span_matches_literal_fill(P, O):
     for lat in (1, 2):
         m = n = 24

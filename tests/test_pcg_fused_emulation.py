@@ -28,26 +28,26 @@ def emul():
     return C.CDLL(so)
 
 
-def run_emul(lib, lat, m, n, w, tol, itmax, Va=1.0, g0=1.0, gleak=1e-12, read_thresh=1e-10, cfg=0):
+def run_emul(lib, lat, m, n, w, tol, itmax, Va=1.0, g0=1.0, gleak=1e-12, read_thresh=1e-10, cfg=0, pbc=0):
     Gt, Gb, err = C.c_double(), C.c_double(), C.c_double()
     it, fast = C.c_int(), C.c_int()
     w = np.ascontiguousarray(w, np.float64)
     rc = lib.fused_emul_solve(C.c_int(lat), C.c_int(m), C.c_int(n), w.ctypes.data_as(C.POINTER(C.c_double)),
                               C.c_double(Va), C.c_double(g0), C.c_double(gleak), C.c_double(tol), C.c_int(itmax),
-                              C.c_double(read_thresh), C.byref(Gt), C.byref(Gb), C.byref(it), C.byref(err), C.byref(fast), C.c_int(cfg))
+                              C.c_double(read_thresh), C.byref(Gt), C.byref(Gb), C.byref(it), C.byref(err), C.byref(fast), C.c_int(cfg), C.c_int(pbc))
     assert rc == 0
     return {"Gtop": Gt.value, "Gbot": Gb.value, "iter": it.value, "err": err.value, "tiles_fast": fast.value}
 
 
-def spanning_case(O, lat, kind, m, n, ps, pb, seed):
+def spanning_case(O, lat, kind, m, n, ps, pb, seed, pbc=0):
     """one realization with a spanning cluster -> per-bond weights of the Kirchhoff problem (None if nothing spans)"""
     t = m * n
-    b1, b2 = O.bondlist(lat, m, n, 0)
+    b1, b2 = O.bondlist(lat, m, n, pbc)
     nb = len(b1)
     rng = np.random.default_rng(seed)
     socc = (rng.random(t) < ps).astype(np.uint8) if kind != O.BOND else None
     bocc = (rng.random(nb) < pb).astype(np.uint8) if kind != O.SITE else None
-    ws, wb, wsz, ncl, wmax = O.label_uf(kind, lat, m, n, 0, b1, b2, site_occ=socc, bond_occ=bocc)
+    ws, wb, wsz, ncl, wmax = O.label_uf(kind, lat, m, n, pbc, b1, b2, site_occ=socc, bond_occ=bocc)
     ids = O.spanning(kind, m, n, b1, b2, ws, wb)
     if len(ids) == 0:
         return None
@@ -94,6 +94,34 @@ def test_emulated_fused_pcg_matches_oracle(emul, O, cfg, lat, kind, m, n, ps, pb
     got8 = run_emul(emul, lat, m, n, w, 1e-8, 2500, cfg=cfg)
     assert abs(got8["iter"] - ref8["iter"]) <= 1
     assert abs(got8["Gtop"] - ref8["Gtop"]) <= 1e-6 * abs(ref8["Gtop"])
+
+
+# periodic wrap in x (pbc = 1): the plain one-pass kernel when the seam falls on a tile border (m a multiple of 128) -- one tile
+# per lattice row (both halos wrap), two and three tiles, both lattices, tile rows that straddle
+PBC_CASES = [(1, "MIXED", 128, 40, 0.85, 0.72), (1, "BOND", 256, 70, 0.0, 0.55), (1, "SITE", 128, 33, 0.66, 0.0),
+             (2, "SITE", 128, 50, 0.56, 0.0), (2, "MIXED", 384, 66, 0.8, 0.6), (2, "BOND", 256, 36, 0.0, 0.40)]
+
+
+@pytest.mark.parametrize("lat,kind,m,n,ps,pb", PBC_CASES)
+def test_emulated_fused_pcg_periodic_wrap(emul, O, lat, kind, m, n, ps, pb):
+    kind = getattr(O, kind)
+    for seed in range(20):
+        case = spanning_case(O, lat, kind, m, n, ps, pb, 9000 + 13 * m + n + seed, pbc=1)
+        if case is not None:
+            break
+    else:
+        pytest.fail("no spanning realization among the seeds")
+    b1, b2, w = case
+    ref = O.conduct_cg(m, n, b1, b2, w, tol=1e-13, itmax=200000)
+    got = run_emul(emul, lat, m, n, w, 1e-13, 200000, cfg=2, pbc=1)
+    assert abs(got["Gtop"] - ref["Gtop"]) <= 1e-9 * abs(ref["Gtop"]), (got, ref["Gtop"])
+    assert abs(got["Gbot"] - ref["Gbot"]) <= 1e-9 * abs(ref["Gbot"]), (got, ref["Gbot"])
+    assert abs(got["iter"] - ref["iter"]) <= max(3, ref["iter"] // 100), (got["iter"], ref["iter"])
+    assert got["err"] <= 1e-13
+    # without the wrap the same bonds give a different conductance: the wrap bonds matter in these realizations
+    lit = O.conduct_literal(m, n, b1, b2, w)
+    got8 = run_emul(emul, lat, m, n, w, 1e-8, 2500, cfg=2, pbc=1)
+    assert abs(got8["iter"] - lit["iter"]) <= 1 and abs(got8["Gtop"] - lit["Gtop"]) <= 1e-6 * abs(lit["Gtop"])
 
 
 def test_emulated_fused_full_lattice_closed_form(emul, O):
