@@ -666,8 +666,8 @@ pcg_pipe_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant_
 // each); everything else takes the two-kernel path.  Consecutive iterations sweep the tiles in opposite
 // directions, so each starts on the part of r / s the previous one wrote last (still in L2).
 // ------------------------------------------------------------------------------------------
-static_assert(FT_KMAX <= 2 * FtCfgD::THREADS, "the coarse stage takes at most two blocks per thread");
-static_assert(FtCfgA::SMEM <= 227 * 1024 && FtCfgA3::SMEM <= 227 * 1024 && FtCfgD::SMEM <= 227 * 1024, "fused PCG tile does not fit the shared memory of one SM");
+static_assert(FT_KMAX <= 2 * FtCfgD::THREADS && FT_KMAX <= 2 * FtCfgD32::THREADS, "the coarse stage takes at most two blocks per thread");
+static_assert(FtCfgA::SMEM <= 227 * 1024 && FtCfgA3::SMEM <= 227 * 1024 && FtCfgD::SMEM <= 227 * 1024 && FtCfgD32::SMEM <= 227 * 1024, "fused PCG tile does not fit the shared memory of one SM");
 
 // block sums of three values at once (fixed order: lanes by shuffles, then warp 0 folds the per-warp partials by
 // shuffles); result valid in thread 0
@@ -1498,7 +1498,10 @@ static int pcg_fused_loop(Ctx* c, const PcgParams& prm)
     if (const char* e = getenv("PERC_FUSED_CFG")) if (c->fused_cfg < 0 && (*e == '1' || *e == '3' || *e == '5')) use = *e - '1';
     if (c->g.pbc) use = 2;                // the deflated sweep and the first variant have no periodic wrap
     c->last_fused_cfg = use;
-    if (use == 4) return pcg_fused_loop_t<FtCfgD>(c, prm);
+    if (use == 4) {
+        if (const char* e = getenv("PERC_FUSED_TILE32")) if (*e == '1') return pcg_fused_loop_t<FtCfgD32>(c, prm);    // (the 32-row tile shape: timing comparisons)
+        return pcg_fused_loop_t<FtCfgD>(c, prm);
+    }
     if (use == 2) return pcg_fused_loop_t<FtCfgA3>(c, prm);
     return pcg_fused_loop_t<FtCfgA>(c, prm);
 }

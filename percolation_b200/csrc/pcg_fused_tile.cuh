@@ -33,7 +33,8 @@ namespace perc {
 // (the others do not wait for them) and the sums stay in registers until the CTA has done all its tiles; V = 3: as
 // V = 2, and the state vector in HBM is u = D^-1 r instead of r (u' = u - alpha D^-1 s'): phase U and its shared
 // array disappear, the residual is formed only inside the sums (r = d u)
-constexpr int FT_KMAX = 1024;                              // largest coarse (deflation) dimension: E^-1 is dense, FT_KMAX^2 doubles
+constexpr int FT_KMAX = 1152;                              // largest coarse (deflation) dimension: E^-1 is dense, FT_KMAX^2 doubles
+                                                           // (L = 4096 with 31-row tiles: 32 x 34 blocks of 1 x 4 tiles = 1088)
 
 template <int TY_, int RPT_, int DC_, int CTAS_, int V_>
 struct FtCfg {
@@ -74,7 +75,11 @@ struct FtCfg {
 
 typedef FtCfg<32, 3, 32, 1, 1> FtCfgA;      // 704 threads
 typedef FtCfg<32, 3, 32, 1, 3> FtCfgA3;     // 768 threads (two ring warps), one reduction per CTA, u = D^-1 r as the state vector
-typedef FtCfg<32, 3, 32, 1, 5> FtCfgD;      // FtCfgA3 + deflation
+// deflated sweep: 31-row tiles, four rows per thread -- 16 main warps (four per scheduler) + two ring warps = 576 threads with
+// 96 registers each instead of 768 with 80: 0.143 ms per iteration at L = 4096 against 0.151 for the 32-row shape (FtCfgD32,
+// PERC_FUSED_TILE32=1), which sits at its register cap; without deflation the two shapes time the same (0.1015 / 0.1007)
+typedef FtCfg<31, 4, 32, 1, 5> FtCfgD;
+typedef FtCfg<32, 3, 32, 1, 5> FtCfgD32;
 
 #ifdef __CUDACC__
 typedef double2 ft_d2;
