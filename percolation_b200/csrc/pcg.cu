@@ -907,10 +907,14 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         const int kk = dd.D.k;
         const int lane = tid & 31, w = tid >> 5, nw = C::THREADS / 32;
         {   // (k <= FT_KMAX < 2 THREADS: at most two blocks per thread, their ten loads in flight together)
-            const int B0 = tid, B1 = tid + C::THREADS;
-            const double f0 = ft_defl_block_f(dd.D, dd.Fb, B0 < kk ? B0 : 0), f1 = ft_defl_block_f(dd.D, dd.Fb, B1 < kk ? B1 : 0);
-            if (B0 < kk) sf[B0] = f0;
-            if (B1 < kk) sf[B1] = f1;
+            // (every CTA reads the same 30 KB: each starts at another block so that they do not queue on the same L2 sectors)
+            const int rot = (int)(((unsigned)blockIdx.x * 37u) % (unsigned)kk);
+            int B0 = tid + rot, B1 = tid + C::THREADS + rot;
+            const bool v0 = tid < kk, v1 = tid + C::THREADS < kk;
+            B0 = B0 >= kk ? B0 - kk : B0; B1 = B1 >= kk ? B1 - kk : B1; B1 = B1 >= kk ? B1 - kk : B1;
+            const double f0 = ft_defl_block_f<LAT>(dd.D, dd.Fb, v0 ? B0 : 0), f1 = ft_defl_block_f<LAT>(dd.D, dd.Fb, v1 ? B1 : 0);
+            if (v0) sf[B0] = f0;
+            if (v1) sf[B1] = f1;
         }
         __syncthreads();
         const int nrows = (kk - (int)blockIdx.x + G - 1) / G;               // rows blockIdx.x + r G < kk

@@ -322,17 +322,21 @@ PERC_HD void ft_defl_block_add(int info, const double* ts, double* acc)
     acc[FB_OUT] += out;
 }
 // Z^T (A u') of block B -- the net current leaving it -- from the block sums Fb[plane * FT_KMAX + block]
+// (square lattice: nothing ever enters from the east / south-east, those planes are not read)
+template <int LAT>
 PERC_HD double ft_defl_block_f(const FtDefl& D, const double* Fb, int B)
 {
     const int bx = B % D.nbx, by = B / D.nbx;
-    // (five independent loads: the addresses are clamped, the values selected afterwards)
+    // (independent loads: the addresses are clamped, the values selected afterwards)
     const bool he = bx > 0, hn = by > 0, hw = bx + 1 < D.nbx, hnw = hw && hn;
     const double o = FT_LDCG(&Fb[FB_OUT * FT_KMAX + B]);
     double e = FT_LDCG(&Fb[FB_E * FT_KMAX + (he ? B - 1 : B)]);
     double n = FT_LDCG(&Fb[FB_N * FT_KMAX + (hn ? B - D.nbx : B)]);
+    e = he ? e : 0.0; n = hn ? n : 0.0;
+    if (LAT == LAT_SQUARE) return (o - e) - n;
     double w = FT_LDCG(&Fb[FB_W * FT_KMAX + (hw ? B + 1 : B)]);
     double nw = FT_LDCG(&Fb[FB_NW * FT_KMAX + (hnw ? B - D.nbx + 1 : B)]);
-    e = he ? e : 0.0; n = hn ? n : 0.0; w = hw ? w : 0.0; nw = hnw ? nw : 0.0;
+    w = hw ? w : 0.0; nw = hnw ? nw : 0.0;
     return (((o - e) - n) - w) - nw;
 }
 

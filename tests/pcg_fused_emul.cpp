@@ -253,7 +253,7 @@ int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double 
         if (visited != ntiles) return -7;                     // every tile exactly once (the sums below would not notice a repeat)
         // coarse stage
         std::vector<double> f((size_t)D.k);
-        for (int B = 0; B < D.k; ++B) f[B] = ft_defl_block_f(D, Fb.data(), B);
+        for (int B = 0; B < D.k; ++B) f[B] = ft_defl_block_f<LAT>(D, Fb.data(), B);
         double mf = 0.0;
         for (int i = 0; i < D.k; ++i) { double a = 0.0; for (int j = 0; j < D.k; ++j) a += Einv[(size_t)i * D.k + j] * f[j]; mu[i] = a; mf += a * f[i]; }
         if (!prime) esum += st.alpha * st.gamma;            // the step just applied: |e_k|_A^2 - |e_k+1|_A^2 = alpha_k gamma_k
