@@ -316,6 +316,15 @@ module perc_iface
       integer(c_int32_t), intent(in) :: mode
     end function
 
+    ! re-labeling along a sweep: after perc_set_fill raised the fill of a labeled handle only the added elements are united;
+    ! incremental = 1 if that pass ran, 0 if the full perc_label pass was needed
+    integer(c_int32_t) function perc_label_incremental(h, kind, incremental) bind(C, name="perc_label_incremental")
+      import :: c_int32_t, c_int64_t
+      integer(c_int64_t), intent(in) :: h
+      integer(c_int32_t), intent(in) :: kind
+      integer(c_int32_t), intent(out) :: incremental
+    end function
+
     ! the reference programs' text files from the current labeling, in their own formats (which = 1 site.txt, 2 bond.txt,
     ! 3 sbsite.txt, 4 sbbond.txt, 5 bondlist.txt):  ierr = perc_write_txt(h, 1, 'site.txt', len('site.txt'))
     integer(c_int32_t) function perc_write_txt(h, which, path, pathlen) bind(C, name="perc_write_txt")

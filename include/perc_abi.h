@@ -192,6 +192,15 @@ int32_t perc_batch_conduct(const int64_t *h, const int32_t *kind, const int32_t 
 int32_t perc_comm_init_rank(const int64_t *h, const int32_t *nranks, const int32_t *rank, const uint8_t *id128);
 int32_t perc_allreduce_stats(const int64_t *h, const int32_t *ni, int64_t *ivals, const int32_t *nd, double *dvals);
 
+/* ---- re-labeling along a sweep -----------------------------------------------------------
+ * The reference's sweep drivers add elements one by one to a labeled lattice (Sq/site_perc.f:133-254, Sq/bond_cond.f:208-485,
+ * Sq/sb_perc.f, Sq/bs_perc.f).  After perc_set_fill raised the fill counts of a handle that holds the labels of a SMALLER
+ * fill of the same order / generator stream (same kind, one GPU), perc_label_incremental unites only the added elements on the
+ * label table, folds the sizes of the clusters that merged and adds the new elements' weights -- labels, sizes, counts and
+ * spanning clusters are identical to perc_label's.  In every other case it runs perc_label's full pass.
+ * incremental (may be NULL): 1 = the incremental pass ran, 0 = the full one. */
+int32_t perc_label_incremental(const int64_t *h, const int32_t *kind, int32_t *incremental);
+
 /* ---- the reference programs' output files --------------------------------------
  * Writes one of the text files the reference's programs leave behind, in their own record formats, from the handle's
  * current labeling, so that MATLAB/SitePlot.m, BondPlot.m, SiteBondPlot.m and ConductCalc.m read GPU results unchanged:

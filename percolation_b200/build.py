@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libperc_b200.so")
-SOURCES = ["abi.cu", "occupancy.cu", "ccl.cu", "pcg.cu", "pcg_weighted.cu", "slab.cu", "batch.cu"]
+SOURCES = ["abi.cu", "occupancy.cu", "ccl.cu", "ccl_incremental.cu", "pcg.cu", "pcg_weighted.cu", "slab.cu", "batch.cu"]
 HEADERS = ["context.h", "geometry.cuh", "philox.cuh", os.path.join("..", "..", "include", "perc_abi.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]

@@ -107,7 +107,7 @@ void ctx_free(Ctx* c)
     if (c->d_stitch) cudaFree(c->d_stitch);
     if (c->h_iface) cudaFreeHost(c->h_iface);
     void* ptrs[] = {c->srank, c->brank, c->mask, c->label, c->size, c->rootlist, c->d_sum, c->d_pcg,
-                    c->d_hist, c->d_thr, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vp2, c->vq, c->xprow, c->partial, c->d_stage, c->d_defl, c->bond_w, c->wplane, c->wdiag, c->d_sched};
+                    c->d_hist, c->d_thr, c->d_cand, c->cfull, c->vx, c->vr, c->vp, c->vp2, c->vq, c->xprow, c->partial, c->d_stage, c->d_defl, c->bond_w, c->wplane, c->wdiag, c->d_sched, c->mask_prev};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_pcg) cudaFreeHost(c->h_pcg);
     if (c->h_sum_pin) cudaFreeHost(c->h_sum_pin);
@@ -305,6 +305,19 @@ int32_t perc_label(const int64_t* h, const int32_t* kind)
     if ((*kind == KIND_SITE || *kind == KIND_MIXED) && c->site_src == SRC_NONE) return PERC_E_STATE;
     if ((*kind == KIND_BOND || *kind == KIND_MIXED) && c->bond_src == SRC_NONE) return PERC_E_STATE;
     return ccl_run(c, *kind);
+}
+
+// re-labeling along a sweep: when the handle holds the labels of a smaller fill of the same order / generator stream, only the
+// added elements are united (csrc/ccl_incremental.cu); otherwise the full pass of perc_label runs.  *incremental tells which.
+int32_t perc_label_incremental(const int64_t* h, const int32_t* kind, int32_t* incremental)
+{
+    GET_CTX(h);
+    if (!kind || *kind < KIND_SITE || *kind > KIND_MIXED) return PERC_E_ARG;
+    if ((*kind == KIND_SITE || *kind == KIND_MIXED) && c->site_src == SRC_NONE) return PERC_E_STATE;
+    if ((*kind == KIND_BOND || *kind == KIND_MIXED) && c->bond_src == SRC_NONE) return PERC_E_STATE;
+    const bool inc = ccl_incremental_applies(c, *kind);
+    if (incremental) *incremental = inc ? 1 : 0;
+    return inc ? ccl_incremental_run(c, *kind) : ccl_run(c, *kind);
 }
 
 int32_t perc_summary(const int64_t* h, int64_t* ncl, int32_t* maxcs, int32_t* maxcn, int32_t* nspan)

@@ -318,8 +318,21 @@ int ccl_launch(Ctx* c, int kind)
     return 0;
 }
 
+void ccl_span_launch(Ctx* c)
+{
+    ccl_span_kernel<<<1, 1024, 0, c->stream>>>(c->g.m, (int64_t)(c->g.n - 1) * c->g.m, c->label, c->size, c->d_sum);
+}
+
+void ccl_note_labeled(Ctx* c, int kind)
+{
+    c->lab_valid = c->nranks == 1;
+    c->lab_kind = kind; c->lab_site_src = c->site_src; c->lab_bond_src = c->bond_src;
+    c->lab_ks = c->ks; c->lab_kb = c->kb; c->lab_seed = c->seed; c->lab_stream = c->stream_id; c->lab_epoch = c->occ_epoch;
+}
+
 int ccl_run(Ctx* c, int kind)
 {
+    c->lab_valid = false;
     int rc = ccl_launch(c, kind);
     if (rc) return rc;
     const bool slab = c->nranks > 1;
@@ -334,6 +347,7 @@ int ccl_run(Ctx* c, int kind)
         c->h_span_gid.assign(c->h_span_ids.begin(), c->h_span_ids.end());
         c->h_span_total.assign(c->h_span_sizes.begin(), c->h_span_sizes.end());
     }
+    ccl_note_labeled(c, kind);
     return 0;
 }
 

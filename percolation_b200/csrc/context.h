@@ -62,6 +62,13 @@ struct Ctx {
 
     // ---- realization state
     uint8_t* mask = nullptr;      // [t]
+    uint8_t* mask_prev = nullptr; // [t] incremental re-labeling: the mask of the fill the labels on the device belong to
+    // what the labels on the device were made from (ccl_note_labeled): perc_label_incremental advances them when only elements were added
+    bool lab_valid = false;
+    int lab_kind = 0, lab_site_src = SRC_NONE, lab_bond_src = SRC_NONE;
+    int64_t lab_ks = 0, lab_kb = 0;
+    unsigned long long lab_seed = 0, lab_stream = 0, lab_epoch = 0;
+    unsigned long long occ_epoch = 1;     // bumped whenever an order / occupancy array is uploaded or a batch consumed the inputs
     int32_t* label = nullptr;     // [t]  parent+1 during CCL, canonical label after flatten
     int32_t* size = nullptr;      // [t]  cluster size at the ROOT's index (label-1); other entries undefined
     int32_t* rootlist = nullptr;  // [t]  site indices of the tile-local roots of the last labeling
@@ -145,6 +152,10 @@ int ccl_launch(Ctx* c, int kind);        // the labeling pipeline without the fi
 int batch_run(Ctx* c, int kind, int nreal, unsigned long long seed, unsigned long long stream0, int64_t ks, int64_t kb,
               int nbins, int64_t* hist, int64_t* stats);
 int ccl_fetch_summary(Ctx* c);
+void ccl_span_launch(Ctx* c);            // K5 on the handle's stream
+void ccl_note_labeled(Ctx* c, int kind);  // remember what the labels on the device were made from
+bool ccl_incremental_applies(const Ctx* c, int kind);
+int ccl_incremental_run(Ctx* c, int kind);
 int ccl_hist(Ctx* c, int nbins, int64_t* hist, int logbin = 0);
 int ccl_export_bond_labels(Ctx* c, int32_t* b3);
 int ccl_export_sizes(Ctx* c, int32_t* cs);

@@ -226,7 +226,7 @@ int occ_upload_site_order(Ctx* c, const int32_t* order)
     scatter_site_rank_kernel<<<nblk(t), 256, 0, c->stream>>>(d, t, c->srank);
     c->launches++;
     c->site_src = SRC_RANK;
-    c->labeled = false;
+    c->labeled = false; c->occ_epoch++;
     return (int)cudaGetLastError();
 }
 
@@ -247,7 +247,7 @@ int occ_upload_bond_order(Ctx* c, const int32_t* border)
     PERC_CUDA(cudaStreamSynchronize(c->stream));
     if (hbad) return -1;      // PERC_E_ARG: a pair that is not a lattice bond
     c->bond_src = SRC_RANK;
-    c->labeled = false;
+    c->labeled = false; c->occ_epoch++;
     return 0;
 }
 
@@ -274,7 +274,7 @@ int occ_upload_flags(Ctx* c, const uint8_t* socc, const uint8_t* bocc)
         PERC_CUDA(cudaStreamSynchronize(c->stream));
         c->bond_src = SRC_RANK; c->kb = 1;
     }
-    c->labeled = false;
+    c->labeled = false; c->occ_epoch++;
     return (int)cudaGetLastError();
 }
 
@@ -595,7 +595,7 @@ int occ_generate_dev(Ctx* c, unsigned long long seed, unsigned long long stream,
         if (rc) return rc;
         c->bond_src = SRC_PHILOX; c->kb = kb;
     }
-    c->labeled = false;
+    c->labeled = false; c->occ_epoch++;
     return 0;
 }
 

@@ -30,7 +30,7 @@ SYMBOLS = [
     "perc_conduct", "perc_conduct_warm", "perc_conduct_g", "perc_get_voltage", "perc_launch_count", "perc_phase_ms", "perc_stream", "perc_set_solver", "perc_solver_used",
     "perc_create_slab", "perc_comm_unique_id", "perc_comm_init", "perc_slab_rows", "perc_generate_i8",
     "perc_summary_i8", "perc_span_i8", "perc_get_site_labels_i8", "perc_stitch_host",
-    "perc_batch", "perc_batch_conduct", "perc_comm_init_rank", "perc_allreduce_stats", "perc_set_bond_conductance", "perc_write_txt",
+    "perc_batch", "perc_batch_conduct", "perc_comm_init_rank", "perc_allreduce_stats", "perc_set_bond_conductance", "perc_write_txt", "perc_label_incremental",
 ]
 
 
@@ -163,6 +163,14 @@ class Lattice:
     # ---- labeling
     def label(self, kind):
         self._call("perc_label", _i32(kind))
+
+    def label_incremental(self, kind):
+        """re-labeling after perc_set_fill RAISED the fill of a labeled handle (same order / generator stream): only the added
+        elements are united (Newman-Ziff along a sweep, Sq/bond_cond.f:208-485); otherwise the full pass.  Returns True when
+        the incremental pass ran."""
+        inc = C.c_int32(0)
+        self._call("perc_label_incremental", _i32(kind), C.byref(inc))
+        return bool(inc.value)
 
     def summary(self):
         ncl, maxcs, maxcn, nspan = C.c_int64(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)

@@ -645,6 +645,63 @@ def test_warm_start_sweep(P, lat, kind, m, n):
         assert sum(w["iter"] for w in warm[1:]) < sum(c["iter"] for c in cold[1:])
 
 
+# ---- re-labeling along a sweep ------------------------------------------------------------------
+@pytest.mark.parametrize("lat,kind,which,m,n,pbc", [(1, 1, 1, 70, 45, 0), (2, 1, 1, 64, 40, 1), (1, 2, 2, 130, 70, 0), (2, 2, 2, 48, 36, 1),
+                                                       (1, 3, 2, 144, 70, 0), (2, 3, 2, 160, 96, 1), (1, 3, 1, 50, 41, 1), (2, 3, 1, 64, 50, 0),
+                                                       (1, 3, 2, 1024, 512, 0)])
+@pytest.mark.parametrize("source", ["order", "generator"])
+def test_incremental_labeling_equals_full_labeling(P, O, lat, kind, which, m, n, pbc, source):
+    """perc_label_incremental along a sweep (elements of one kind added at rising fill, the other kind fixed) against perc_label
+    at every sweep point on a second handle: labels, bond labels, sizes, counts, spanning clusters bit-identical; the small
+    lattices also against the oracle"""
+    t = m * n
+    b1, b2 = O.bondlist(lat, m, n, pbc)
+    nb = len(b1)
+    with P.Lattice(lat, m, n, pbc) as A, P.Lattice(lat, m, n, pbc) as B:
+        for L in (A, B):
+            if source == "order" and t <= 100000:
+                L.set_site_order(O.shuffle_sites(626504, t))
+                L.set_bond_order(*O.shuffle_bonds(184489, b1, b2))
+            elif source == "order":                          # (the reference's float32 shuffle is for its own sizes, t <= 10^6)
+                rng = np.random.default_rng(5)
+                L.set_site_order(rng.permutation(t).astype(np.int32) + 1)
+                bp = rng.permutation(nb)
+                L.set_bond_order(b1[bp], b2[bp])
+            else:
+                L.generate(99, 7, t, nb)
+        # sweep of the `which` elements from empty to full in uneven steps; the other kind fixed at 0.8 (mixed)
+        N = t if which == 1 else nb
+        fills = sorted(set([0, 1, 2, int(0.1 * N), int(0.3 * N), int(0.45 * N), int(0.5 * N), int(0.5 * N) + 1, int(0.55 * N),
+                            int(0.6 * N), int(0.75 * N), int(0.9 * N), N - 1, N]))
+        ks0, kb0 = (-1, int(0.8 * nb)) if which == 1 else (int(0.8 * t), -1)
+        nin = 0
+        for k in fills:
+            ks, kb = (k, kb0) if which == 1 else (ks0, k)
+            for L in (A, B):
+                L.set_fill(ks if kind != 2 else -1, kb if kind != 1 else -1)
+            B.label(kind)
+            nin += A.label_incremental(kind)
+            assert A.summary() == B.summary(), (k, A.summary(), B.summary())
+            sa, sb = A.span(), B.span()
+            assert list(sa[0]) == list(sb[0]) and list(sa[1]) == list(sb[1])
+            if kind != 2:
+                assert (A.site_labels() == B.site_labels()).all()
+            if kind != 1:
+                assert (A.bond_labels() == B.bond_labels()).all()
+            assert (A.sizes() == B.sizes()).all()
+            assert (A.hist(16) == B.hist(16)).all()
+        assert nin == len(fills) - 1                        # everything after the first point was incremental
+        if t <= 20000:
+            socc, bocc = A.get_occupancy(sites=kind != 2, bonds=kind != 1)
+            ws, wb, wsz, ncl, wmax = O.label_uf(kind, lat, m, n, pbc, b1, b2, site_occ=socc, bond_occ=bocc)
+            if kind != 2:
+                assert (A.site_labels() == ws).all()
+            assert (A.sizes() == wsz[1:]).all()
+        # a smaller fill, or another order, takes the full pass again
+        A.set_fill(0 if kind != 2 else -1, 0 if kind != 1 else -1)
+        assert A.label_incremental(kind) is False
+
+
 # ---- the reference programs' output files (SURVEY 8(f).2) -------------------------------------------------------
 def _read_txt(path, ncol):
     lines = open(path).read().split("\n")
