@@ -1,12 +1,3 @@
-// Largest cluster without a recount: sizes only grow and a merged cluster is larger than its parts, so the previous maximum
-// (carried in sum->maxpack) competes only with roots whose size entry received something in this pass; the LAST atomicAdd to
-// an entry returns its final value minus the addend, so taking (returned + addend) of every add as a candidate includes the
-// final size of every such root.  Candidates of a block are maximised in shared memory first.
-__device__ __forceinline__ unsigned long long inc_pack(int size, int r)
-{
-    return ((unsigned long long)(unsigned)size << 32) | (unsigned long long)(0xffffffffu - (unsigned)(r + 1));
-}
-
 // ccl_incremental.cu -- re-labeling after elements were ADDED to a labeled lattice.
 //
 // The reference's sweep drivers add elements one by one and relabel as they go (Sq/site_perc.f:133-254,
@@ -198,41 +189,6 @@ inc_init4_kernel(int64_t nquad, const uint32_t* __restrict__ mnew4, uint32_t* __
 __device__ __forceinline__ unsigned long long inc_pack(int size, int r)
 {
     return ((unsigned long long)(unsigned)size << 32) | (unsigned long long)(0xffffffffu - (unsigned)(r + 1));
-}
-
-// ---- fast path: only BONDS were added (site bits of the mask unchanged, or the bond problem, where a site is a node iff
-// one of its bonds is occupied): four sites per thread, 32-bit mask words; the weight of a new bond goes to whatever root
-// its cluster has at that moment -- every root there can be is flagged (an old root or a new node), so inc_fold4 carries
-// the sum on if that root loses its independence later in the same pass.
-__global__ void __launch_bounds__(256)
-inc_init4_kernel(int64_t nquad, const uint32_t* __restrict__ mnew4, uint32_t* __restrict__ mold4, int4* __restrict__ label4,
-                 int32_t* __restrict__ size, Summary* __restrict__ sum)
-{
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nquad) return;
-    const uint32_t mo = mold4[q], mn = mnew4[q];
-    if (!((mo | mn) & 0x01010101u)) return;                      // no node among the four
-    const int nnew = __popc(mn & ~mo & 0x01010101u);            // new nodes: clusters of their own until something unites them
-    if (nnew) atomicAdd(&sum->ncl, (unsigned long long)nnew);
-    int4 lab = label4[q];
-    int l[4] = {lab.x, lab.y, lab.z, lab.w};
-    uint32_t flags = 0;
-    bool changed = false;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        const int64_t i = 4 * q + b;
-        if ((mo >> (8 * b)) & 1u) { if (l[b] == (int32_t)(i + 1)) flags |= WASROOT << (8 * b); }
-        else if ((mn >> (8 * b)) & 1u) { l[b] = (int32_t)(i + 1); size[i] = 0; flags |= WASROOT << (8 * b); changed = true; }
-    }
-    if (flags) mold4[q] = mo | flags;
-    if (changed) label4[q] = make_int4(l[0], l[1], l[2], l[3]);
-}
-
-// candidate for the largest cluster: a root whose size entry received something (checked by inc_maxlist_kernel once all sums are final)
-// (list = nullptr: the pass recounts everything at its end instead -- steps that add more bonds than the list could hold)
-__device__ __forceinline__ void inc_touch(Summary* sum, int32_t* list, int r)
-{
-    if (list) list[atomicAdd(&sum->nroots, 1u)] = r;
 }
 
 __global__ void __launch_bounds__(256)
