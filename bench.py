@@ -129,7 +129,7 @@ def host_occupancy(rng, t, nb, ks, kb):
     return socc, bocc
 
 
-def plain_iters_table(npts, fallback_mean=None):
+def plain_iters_table(npts, Lsz=4096, fallback_mean=None):
     """iterations the reference's solver (plain Jacobi-PCG = linbcg on a symmetric matrix) needs at each sweep point of
     the bench's realizations: measured once on the GPU with the plain one-pass kernel (`bench.py --measure-plain`,
     committed as profiles/bench_iters.json) -- the CPU arm cannot run 10^5 iterations of a 2^24-site system per
@@ -138,12 +138,12 @@ def plain_iters_table(npts, fallback_mean=None):
         with open(ITERS_FILE) as f:
             d = json.load(f)
         it = [float(v) for v in d["plain_iters_per_point"]][:npts]
-        if len(it) == npts:
+        if len(it) == npts and int(d.get("L", 0)) == int(Lsz):
             return it, "profiles/bench_iters.json (plain Jacobi-PCG counts of the bench realizations, GPU-measured)"
     except Exception:
         pass
-    v = float(fallback_mean) if fallback_mean else 66000.0
-    return [v] * npts, "documented constant (about 66 000 at pb = 0.70, DESIGN.md)"
+    v = float(fallback_mean) if fallback_mean else 66000.0 * Lsz / 4096.0          # (Jacobi-PCG iterations grow about linearly with L)
+    return [v] * npts, "documented constant (about 66 000 x L / 4096 at pb = 0.70, DESIGN.md)"
 
 
 def cpu_sample(Lsz, socc, bocc, nthreads, cg_iters):
@@ -242,7 +242,7 @@ def run_reference(args):
     t, nb = Lsz * Lsz, 2 * Lsz * Lsz - 2 * Lsz
     ks, kb = int(args.ps * t), int(args.pb * nb)
     nthreads = host_threads(args)
-    iters, src = plain_iters_table(args.npts)
+    iters, src = plain_iters_table(args.npts, Lsz)
     rng = np.random.default_rng(SEED)
     vals, t0 = [], None
     for step in range(args.warmup + args.steps):
@@ -713,7 +713,7 @@ def run_ours(args):
             L.generate(SEED, stream_id(0, args.warmup), ks, kb1)
             socc, bocc = L.get_occupancy()
             nthreads = host_threads(args)
-            iters_tab, src = plain_iters_table(args.npts)
+            iters_tab, src = plain_iters_table(args.npts, Lsz)
             r = cpu_sample(Lsz, socc, bocc, nthreads, args.cpu_cg_iters)
             v, per_real = cpu_extrapolate(r, nthreads, iters_tab)
             line["cpu_baseline"] = {
