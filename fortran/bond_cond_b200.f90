@@ -6,7 +6,7 @@
 ! (:140-180), output rows "pb,Gbot,Gtop,avg" with format f12.9 (:481-482,505).
 ! Replaced: the add-one-bond-and-rescan loop (:208-370) and the dense conductance block
 ! (:392-476).  Because the bond order is uploaded once as a rank table, each sweep point is
-! perc_set_fill(kb = nbarr(jj)) + perc_label + perc_conduct -- the nesting property of the
+! perc_set_fill(kb = nbarr(jj)) + perc_label_incremental + perc_conduct -- the nesting property of the
 ! reference's single fill order is preserved (App. B: the stall on duplicate nbarr entries is
 ! not reproduced; jj advances past duplicates).
 ! Not compile-tested in this image (no Fortran compiler).
@@ -17,7 +17,7 @@ program bond_cond_b200
   implicit none
   integer(c_int32_t) :: m, n, t, pbc, lattice, device, rc, nb
   integer(c_int32_t) :: numtrials, seed, i, ii, j, jj, keep, itmax, iter, cid
-  integer(c_int32_t) :: maxcs, perccln, perccls, kstar, nspan
+  integer(c_int32_t) :: maxcs, perccln, perccls, kstar, nspan, inc
   integer(c_int32_t) :: btemp(2), nbarr(250), ids(16), sizes(16)
   integer(c_int32_t), allocatable :: b(:,:), border(:,:), b3(:), c(:), tseed(:)
   integer(c_int64_t) :: h, ncl
@@ -74,7 +74,7 @@ program bond_cond_b200
            end if
         end if
         rc = perc_set_fill(h, keep, nbarr(jj))
-        rc = perc_label(h, PERC_BOND)
+        rc = perc_label_incremental(h, PERC_BOND, inc)   ! only the bonds added since the last point are united
         rc = perc_span(h, 16, nspan, ids, sizes)
         pb = real(nbarr(jj))/real(nb)
         if (nspan > 0) then
