@@ -55,3 +55,21 @@ def test_e2e_host_inputs_are_the_drivers_orders():
         assert so.dtype == np.int32 and sorted(so.tolist()) == list(range(1, t + 1))
         assert sorted(zip(bo[:nb].tolist(), bo[nb:].tolist())) == sorted(zip(b1.tolist(), b2.tolist()))
     assert (ins[0][0].numpy() != ins[1][0].numpy()).any()
+
+
+def test_sweep_points_follow_the_reference_table_rule():
+    """bench.py's sweep points: pb accumulated in fp64 by repeated + 5e-3 from pb* = k*/nb and truncated -- the rule of the
+    reference's table (Sq/bond_cond.f:89-94, restated by the oracle's sweep_table); point 0 is the first-spanning fill itself"""
+    import importlib.util
+    from oracle import pyoracle as O
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    nb = 2 * 4096 * 4096 - 2 * 4096
+    for kstar in (22388211, 22390015, 1, nb - 5):
+        pbarr, nbarr = O.sweep_table(float(kstar) / float(nb), 5.0e-3, 9, nb)
+        got = [bench.sweep_fill(kstar, nb, j) for j in range(9)]
+        assert got[0] == kstar
+        for j in range(1, 9):
+            assert got[j] == min(nb, max(kstar, int(nbarr[j]))), (kstar, j, got[j], nbarr[j])
+        assert all(a <= b for a, b in zip(got, got[1:]))
