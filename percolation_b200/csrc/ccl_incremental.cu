@@ -359,8 +359,6 @@ bool ccl_incremental_applies(const Ctx* c, int kind)
     return true;
 }
 
-int ccl_incremental_launch(Ctx* c, int kind);
-
 int ccl_incremental_run(Ctx* c, int kind)
 {
     const Geom& g = c->g;

@@ -266,7 +266,6 @@ int pcg_solve_weighted(Ctx* c, double Va, double gleak, double tol, int itmax, d
 {
     const Geom& g = c->g;
     cudaStream_t s = c->stream;
-    const int ndir = g.lattice == LAT_TRIANGULAR ? 4 : 2;
     if (!c->wplane) PERC_CUDA(cudaMalloc(&c->wplane, sizeof(double) * 4 * (size_t)g.t));
     if (!c->wdiag) PERC_CUDA(cudaMalloc(&c->wdiag, sizeof(double) * (size_t)g.t));
     if (!c->vq) PERC_CUDA(cudaMalloc(&c->vq, sizeof(double) * (size_t)g.t));
@@ -315,7 +314,6 @@ int pcg_solve_weighted(Ctx* c, double Va, double gleak, double tol, int itmax, d
     c->launches++;
     c->phase_ms[6] = nsamp ? sp_ms / nsamp : 0.f;
     c->phase_ms[7] = nsamp ? up_ms / nsamp : 0.f;
-    (void)ndir;
     return (int)cudaGetLastError();
 }
 
