@@ -406,7 +406,9 @@ def slab_leg(P, torch, dist, rank, world, local, args):
                     "pcg_gbs_per_gpu": 50.0 * own / (float(ms_it.item()) * 1e-3) / 1e9,
                     "pcg_bytes_per_site_iter": 50, "pcg_form": "two-kernel form, 2 all-reduces + 1 halo exchange per iteration"})
     S.close()
-    if rank == 0 and t <= 2 ** 30:
+    if rank == 0 and t >= 2 ** 30:
+        out["equals_single_gpu"] = "not checked: 2^%d sites do not fit a single-GPU handle (int32 labels)" % (t.bit_length() - 1)
+    if rank == 0 and t < 2 ** 30:
         # the same lattice undecomposed on one GPU: counts must be bit-identical
         try:
             with P.Lattice(P.SQUARE, Lsz, Lsz, 0, device=local) as L1:
