@@ -229,8 +229,8 @@ int32_t perc_set_bond_conductance(const int64_t *h, const double *w);
 
 /* ---- solver selection --------------------------------------------------------------------------- */
 /* Iteration kernels of the conductance solve (the body of linbcg's loop, Sq/bondc.f:780-833; Jacobi asolve :855-864):
- *   mode 0 (default): automatic -- perc_conduct_g on one GPU runs a one-pass kernel: with periodic wrap (pbc = 1, m a multiple
- *           of 128) the plain one of mode 2, without periodic wrap the DEFLATED ONE-PASS kernel:
+ *   mode 0 (default): automatic -- perc_conduct_g on one GPU (pbc = 0, or pbc = 1 with m a multiple of 128) runs the
+ *           DEFLATED ONE-PASS kernel:
  *           the Chronopoulos-Gear arrangement of the Jacobi-PCG recurrences (one reduction per iteration, 33 B per
  *           site and iteration) on top of a block-constant deflation space (Saad et al. 2000: x0 = Z E^-1 Z^T b,
  *           search directions A-orthogonal to the blocks).  x, err = |r| / |D^-1 b| and the stopping rule are

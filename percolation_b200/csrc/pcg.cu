@@ -762,7 +762,9 @@ pcg_fused_kernel(const __grid_constant__ CUtensorMap tm_r, const __grid_constant
         double* T = sft + b * C::SFT_N;
         double* R = srec + b * C::REC_N;
         if (l < 9) {
-            const int tx = ix + l % 3 - 1, ty = iy + l / 3 - 1;
+            int tx = ix + l % 3 - 1;
+            const int ty = iy + l / 3 - 1;
+            if (dd.D.pbc) tx = tx < 0 ? dd.D.ntx - 1 : (tx >= dd.D.ntx ? 0 : tx);        // periodic wrap: the tile column beyond the seam
             m9[l] = (tx >= 0 && tx < dd.D.ntx && ty >= 0 && ty < dd.D.nty) ? sf[ft_defl_block(dd.D, tx, ty)] : 0.0;
         }
         __syncwarp();
@@ -1500,7 +1502,7 @@ static int pcg_fused_loop(Ctx* c, const PcgParams& prm)
     const int mode = c->pcg_mode >= 0 ? c->pcg_mode : pcg_default_mode();
     int use = c->fused_cfg >= 0 ? c->fused_cfg : (mode == 2 ? 2 : 4);
     if (const char* e = getenv("PERC_FUSED_CFG")) if (c->fused_cfg < 0 && (*e == '1' || *e == '3' || *e == '5')) use = *e - '1';
-    if (c->g.pbc) use = 2;                // the deflated sweep and the first variant have no periodic wrap
+    if (c->g.pbc && use != 4) use = 2;    // the first variant (r as the state vector) has no periodic wrap
     c->last_fused_cfg = use;
     if (use == 4) {
         if (const char* e = getenv("PERC_FUSED_TILE32")) if (*e == '1') return pcg_fused_loop_t<FtCfgD32>(c, prm);    // (the 32-row tile shape: timing comparisons)

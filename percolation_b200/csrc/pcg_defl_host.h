@@ -19,7 +19,8 @@ namespace perc {
 // Returns 0, or -1 if E is not positive definite (cannot happen for a lattice with n >= 3).
 inline int ft_defl_build_einv(const FtDefl& D, const double* W, double* Einv, int nthreads = 8)
 {
-    const int k = D.k, hb = D.nbx + 1;                   // half bandwidth
+    // half bandwidth: (bx - 1, by + 1) is nbx - 1 away; with the periodic wrap (bx = 0) <-> (nbx - 1, by + 1) is 2 nbx - 1 away
+    const int k = D.k, hb = D.pbc ? 2 * D.nbx : D.nbx + 1;
     // lower band: L[i * (hb + 1) + (hb - (i - j))] = E[i][j], j = i - hb .. i
     const int ld = hb + 1;
     std::vector<double> L((size_t)k * ld, 0.0);
@@ -30,7 +31,9 @@ inline int ft_defl_build_einv(const FtDefl& D, const double* W, double* Einv, in
             const int tl = iy * D.ntx + ix, B = ft_defl_block(D, ix, iy);
             at(B, B) += W[(size_t)tl * FS_STRIDE + FS_D] + W[(size_t)tl * FS_STRIDE + FS_R];
             for (int s = 0; s < 4; ++s) {
-                const int jx = ix + dx[s], jy = iy + dy[s];
+                int jx = ix + dx[s];
+                const int jy = iy + dy[s];
+                if (D.pbc) jx = jx < 0 ? D.ntx - 1 : (jx >= D.ntx ? 0 : jx);
                 if (jx < 0 || jx >= D.ntx || jy >= D.nty) continue;
                 const int B2 = ft_defl_block(D, jx, jy);
                 if (B2 == B) continue;

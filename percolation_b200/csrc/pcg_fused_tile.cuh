@@ -193,6 +193,7 @@ struct FtDefl {
     int ntx, nty;      // tiles per lattice row / column
     int k;             // nbx * nby <= FT_KMAX
     int sw, sh;        // log2 bw / log2 bh when they are powers of two (the library's own choice always is), else -1
+    int pbc;           // periodic wrap in x (m a multiple of TX): the last tile / block column is the west neighbour of the first
 };
 // FS_R: sum over the tile's unknown sites of rho_i u'_i (rho: rounding residue of the matrix diagonal, diag_seq_rho) -- the part of
 // Z^T A u' that is not a current between blocks; in the weight pass (UNIT) the sum of rho_i itself: the entry it adds to E
@@ -211,7 +212,7 @@ PERC_HD FtDefl ft_defl_make(const Geom& g, int TX, int TY, int kmax, int bw0 = 0
         if (kmax <= 0 || D.k <= kmax) break;
         if (D.bw * TX < D.bh * TY) D.bw *= 2; else D.bh *= 2;
     }
-    D.sw = D.sh = -1;
+    D.sw = D.sh = -1; D.pbc = g.pbc;
     for (int b = 0; b < 30; ++b) { if (D.bw == (1 << b)) D.sw = b; if (D.bh == (1 << b)) D.sh = b; }
     return D;
 }
@@ -233,8 +234,10 @@ PERC_HD double ft_defl_shift_entry(const Geom& g, const FtDefl& D, const double*
 {
     const int gy = iy * C::TY - 1 + pr;
     if (gy < 1 || gy > g.n - 2) return 0.0;
-    const int ty = pr == 0 ? iy - 1 : (pr > C::TY ? iy + 1 : iy), tx = ix + cls - 1;
-    if (tx < 0 || tx >= D.ntx || ty < 0 || ty >= D.nty) return 0.0;
+    const int ty = pr == 0 ? iy - 1 : (pr > C::TY ? iy + 1 : iy);
+    int tx = ix + cls - 1;
+    if (ty < 0 || ty >= D.nty) return 0.0;
+    if (tx < 0 || tx >= D.ntx) { if (!D.pbc) return 0.0; tx = tx < 0 ? D.ntx - 1 : 0; }
     return mu[ft_defl_block(D, tx, ty)];
 }
 // class of a staged column (column c <-> gx = x0 - 2 + c)
@@ -301,8 +304,10 @@ struct FtWalk {
     PERC_HD int info(const FtDefl& D, int rev) const
     {
         const int x = bx * D.bw + jx, y = by * D.bh + jy;
-        const int cE = jx == w - 1 && x + 1 < D.ntx, cN = jy == h - 1 && y + 1 < D.nty, cW = jx == 0 && x >= 1;
-        const int nwx = jx == 0, nwy = jy == h - 1, cNW = x >= 1 && y + 1 < D.nty && (nwx | nwy);
+        // (periodic wrap: the tile east of the last column is the first one -- another block unless there is only one block column)
+        const int wrapx = D.pbc && D.nbx > 1;
+        const int cE = jx == w - 1 && (x + 1 < D.ntx || wrapx), cN = jy == h - 1 && y + 1 < D.nty, cW = jx == 0 && (x >= 1 || wrapx);
+        const int nwx = jx == 0 && (x >= 1 || wrapx), nwy = jy == h - 1, cNW = (x >= 1 || D.pbc) && y + 1 < D.nty && (nwx | nwy);
         const int first = rev ? (jx == w - 1 && jy == h - 1) : (jx == 0 && jy == 0), last = rev ? (jx == 0 && jy == 0) : (jx == w - 1 && jy == h - 1);
         return cE | cN << 1 | cW << 2 | cNW << 3 | (nwx & cNW) << 4 | (nwy & cNW) << 5 | first << 6 | last << 7;
     }
@@ -328,14 +333,16 @@ PERC_HD double ft_defl_block_f(const FtDefl& D, const double* Fb, int B)
 {
     const int bx = B % D.nbx, by = B / D.nbx;
     // (independent loads: the addresses are clamped, the values selected afterwards)
-    const bool he = bx > 0, hn = by > 0, hw = bx + 1 < D.nbx, hnw = hw && hn;
+    const int wrapx = D.pbc && D.nbx > 1;
+    const bool he = bx > 0 || wrapx, hn = by > 0, hw = bx + 1 < D.nbx || wrapx, hnw = hw && hn;
+    const int Bw = bx > 0 ? B - 1 : B + D.nbx - 1, Be = bx + 1 < D.nbx ? B + 1 : B - (D.nbx - 1);     // west / east neighbour block (wrapped)
     const double o = FT_LDCG(&Fb[FB_OUT * FT_KMAX + B]);
-    double e = FT_LDCG(&Fb[FB_E * FT_KMAX + (he ? B - 1 : B)]);
+    double e = FT_LDCG(&Fb[FB_E * FT_KMAX + (he ? Bw : B)]);
     double n = FT_LDCG(&Fb[FB_N * FT_KMAX + (hn ? B - D.nbx : B)]);
     e = he ? e : 0.0; n = hn ? n : 0.0;
     if (LAT == LAT_SQUARE) return (o - e) - n;
-    double w = FT_LDCG(&Fb[FB_W * FT_KMAX + (hw ? B + 1 : B)]);
-    double nw = FT_LDCG(&Fb[FB_NW * FT_KMAX + (hnw ? B - D.nbx + 1 : B)]);
+    double w = FT_LDCG(&Fb[FB_W * FT_KMAX + (hw ? Be : B)]);
+    double nw = FT_LDCG(&Fb[FB_NW * FT_KMAX + (hnw ? Be - D.nbx : B)]);
     w = hw ? w : 0.0; nw = hnw ? nw : 0.0;
     return (((o - e) - n) - w) - nw;
 }
@@ -372,7 +379,7 @@ PERC_HD void ft_flux_item(const Geom& g, double g0, double gleak, const A& a, in
     }
     if (q < C::TY) {
         const int gy = y0 + q, gx = x0 + C::TX - 1;
-        if (gx + 1 < g.m && FT_UNK(gy)) f[FS_E] += FT_W(a.cf(gx, gy), NB_E) * (UNIT ? 1.0 : a.u(gx, gy) - a.u(gx + 1, gy));
+        if ((gx + 1 < g.m || g.pbc) && FT_UNK(gy)) f[FS_E] += FT_W(a.cf(gx, gy), NB_E) * (UNIT ? 1.0 : a.u(gx, gy) - a.u(gx + 1, gy));
         return;
     }
     q -= C::TY;
@@ -479,7 +486,7 @@ PERC_HD double ft_defl_u0(const Geom& g, const FtDefl& D, unsigned cf, const dou
         if (!(ex & bits[k])) continue;
         const double w = (cf & bits[k]) ? g0 : gleak;
         const int xx = x + ddx[k], yy = y + ddy[k];
-        if (yy >= 1 && yy <= g.n - 2) acc += w * (ni - nu[ft_defl_block(D, xx / C::TX, yy / C::TY)]);
+        if (yy >= 1 && yy <= g.n - 2) acc += w * (ni - nu[ft_defl_block(D, (xx < 0 ? xx + g.m : (xx >= g.m ? xx - g.m : xx)) / C::TX, yy / C::TY)]);
         else acc += w * ni;
     }
     *bi = b; *nui = ni;

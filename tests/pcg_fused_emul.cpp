@@ -228,6 +228,9 @@ int solve_defl(const Geom& g, const std::vector<uint8_t>& cf, double Va, double 
                 box_copy(sr.data(), r[cur].data(), m, n, x0 - 2, y0 - 1, C::LD, C::RR);
                 box_copy(ss.data(), s[cur].data(), m, n, x0 - 2, y0, C::LD, C::SR);
                 box_copy(scf.data(), cf.data(), m, n, x0 - 16, y0 - 1, C::CLD, C::RR);
+                if (g.pbc && (x0 == 0 || x0 + C::TX == m))           // periodic wrap: the ring threads patch the halo columns
+                    for (int rl = 0; rl < C::RING_NT; ++rl)
+                        ft_wrap_patch<C>(g, x0, y0, r[cur].data(), s[cur].data(), cf.data(), sr.data(), ss.data(), scf.data(), rl, C::RING_NT);
                 for (int j = 0; j < C::SFT_N; ++j) sft[j] = (j & 3) == 3 ? 0.0 : ft_defl_shift_entry<C>(g, D, mu.data(), ix, iy, j >> 2, j & 3);
                 for (int j = 0; j < C::REC_N; ++j) srec[j] = ft_defl_rec_entry<C>(sft.data(), j >> 3, j & 7);
                 const bool interior = ft_interior<C>(g, x0, y0);
@@ -322,10 +325,11 @@ extern "C" int fused_emul_solve(int lattice, int m, int n, const double* w, doub
 // the deflated solver (FtCfgD); bw, bh: tiles per block (0 = the library's choice); coarse_dim: number of blocks
 extern "C" int fused_emul_solve_defl(int lattice, int m, int n, const double* w, double Va, double g0, double gleak,
                                      double tol, int itmax, double read_thresh, double* Gtop, double* Gbot, int* iter,
-                                     double* err, int* coarse_dim, int bw, int bh, double* xfull)
+                                     double* err, int* coarse_dim, int bw, int bh, double* xfull, int pbc)
 {
     if (m % 16 || n < 4) return -2;
-    const Geom g = make_geom(lattice, m, n, 0);
+    if (pbc && m % FtCfgD::TX) return -2;                   // (what pcg_fused_applies admits)
+    const Geom g = make_geom(lattice, m, n, pbc);
     std::vector<uint8_t> cf;
     build_cfull(g, w, gleak, cf);
     return lattice == LAT_SQUARE ? solve_defl<LAT_SQUARE, FtCfgD>(g, cf, Va, g0, gleak, tol, itmax, read_thresh, Gtop, Gbot, iter, err, coarse_dim, bw, bh, xfull)

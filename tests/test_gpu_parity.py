@@ -372,9 +372,10 @@ def test_one_pass_solver_equals_two_kernel_solver(P, O, lat, kind, m, n, ps, pb)
 @pytest.mark.parametrize("lat,kind,m,n,ps,pb", [(1, 3, 128, 60, 0.85, 0.70), (1, 2, 256, 101, 0.0, 0.55), (2, 1, 256, 70, 0.56, 0.0),
                                                    (2, 3, 384, 66, 0.8, 0.6), (1, 3, 1024, 256, 0.80, 0.70)])
 def test_one_pass_solver_with_periodic_wrap(P, O, lat, kind, m, n, ps, pb):
-    """pbc = 1 with the seam on a tile border (m a multiple of 128): perc_conduct_g runs the plain one-pass kernel (the halo
-    columns beyond the seam are patched into the TMA boxes); against the two-kernel form on the same handle and, for the small
-    shapes, the oracle.  The deflated sweep has no periodic wrap: the automatic mode falls back to the plain one-pass kernel."""
+    """pbc = 1 with the seam on a tile border (m a multiple of 128): perc_conduct_g runs the one-pass kernels (the halo columns
+    beyond the seam are patched into the TMA boxes; in the deflated sweep the coarse operator, the crossing currents and the
+    mu records wrap as well: the last block column is the west neighbour of the first).  Against the two-kernel form on the
+    same handle and, for the small shapes, the oracle."""
     with P.Lattice(lat, m, n, 1) as L:
         t, nb = L.t, L.nb
         found = 0
@@ -392,13 +393,19 @@ def test_one_pass_solver_with_periodic_wrap(P, O, lat, kind, m, n, ps, pb):
                 for mode in (2, 0):
                     L.set_solver(mode)
                     b = L.conduct(0, tol=tol, itmax=itmax, voltages=False)
-                    assert L.solver_used() == 1
+                    assert L.solver_used() == (1 if mode == 2 else 2)
+                    if mode == 0:
+                        # the deflated sweep: never more iterations than plain Jacobi-PCG; G compared when both converged
+                        assert b["iter"] <= a["iter"] + 3, (tol, a, b)
+                        if a["iter"] > itmax:
+                            continue
                     rel = 1e-9 if tol < 1e-10 else 1e-6
                     if a["iter"] > itmax:
                         rel = max(rel, a["err"])
                     assert abs(a["Gtop"] - b["Gtop"]) <= rel * abs(a["Gtop"]), (mode, tol, a, b)
                     assert abs(a["Gbot"] - b["Gbot"]) <= rel * abs(a["Gbot"]), (mode, tol, a, b)
-                    assert abs(a["iter"] - b["iter"]) <= max(3, a["iter"] // 100), (mode, tol, a, b)
+                    if mode == 2:
+                        assert abs(a["iter"] - b["iter"]) <= max(3, a["iter"] // 100), (mode, tol, a, b)
             if t <= 60000:
                 b1, b2 = O.bondlist(lat, m, n, 1)
                 socc, bocc = L.get_occupancy(sites=kind != 2, bonds=kind != 1)

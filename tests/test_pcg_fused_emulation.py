@@ -124,6 +124,43 @@ def test_emulated_fused_pcg_periodic_wrap(emul, O, lat, kind, m, n, ps, pb):
     assert abs(got8["iter"] - lit["iter"]) <= 1 and abs(got8["Gtop"] - lit["Gtop"]) <= 1e-6 * abs(lit["Gtop"])
 
 
+@pytest.mark.parametrize("lat,kind,m,n,ps,pb", PBC_CASES)
+def test_emulated_deflated_pcg_periodic_wrap(emul, O, lat, kind, m, n, ps, pb, bw=0, bh=0):
+    """the deflated sweep with pbc = 1: the coarse operator couples the first and the last block column, the crossing currents
+    and the mu records wrap; same G as the oracle's Jacobi-PCG, fewer iterations (the library's own block choice: one tile per
+    block at these sizes, 1 / 2 / 3 block columns)"""
+    kind = getattr(O, kind)
+    for seed in range(20):
+        case = spanning_case(O, lat, kind, m, n, ps, pb, 9000 + 13 * m + n + seed, pbc=1)
+        if case is not None:
+            break
+    else:
+        pytest.fail("no spanning realization among the seeds")
+    b1, b2, w = case
+    ref = O.conduct_cg(m, n, b1, b2, w, tol=1e-13, itmax=200000)
+    got = run_emul_defl(emul, lat, m, n, w, 1e-13, 200000, bw=bw, bh=bh, pbc=1)
+    assert abs(got["Gtop"] - ref["Gtop"]) <= 1e-9 * abs(ref["Gtop"]), (got, ref["Gtop"])
+    assert abs(got["Gbot"] - ref["Gbot"]) <= 1e-9 * abs(ref["Gbot"]), (got, ref["Gbot"])
+    assert got["err"] <= 1e-13 and got["iter"] <= ref["iter"] + 3
+
+
+@pytest.mark.parametrize("lat,m,n,bw,bh", [(1, 768, 70, 2, 1), (2, 512, 130, 2, 2)])
+def test_emulated_deflated_pcg_periodic_wrap_wide_blocks(emul, O, lat, m, n, bw, bh):
+    """periodic wrap with blocks of several tiles: the seam lies between the last and the first block column (3 resp. 2 of them)"""
+    for seed in range(20):
+        case = spanning_case(O, lat, O.MIXED, m, n, 0.85, 0.7, 7100 + m + seed, pbc=1)
+        if case is not None:
+            break
+    else:
+        pytest.fail("no spanning realization among the seeds")
+    b1, b2, w = case
+    ref = O.conduct_cg(m, n, b1, b2, w, tol=1e-13, itmax=200000)
+    got = run_emul_defl(emul, lat, m, n, w, 1e-13, 200000, bw=bw, bh=bh, pbc=1)
+    assert abs(got["Gtop"] - ref["Gtop"]) <= 1e-9 * abs(ref["Gtop"]), (got, ref["Gtop"])
+    assert abs(got["Gbot"] - ref["Gbot"]) <= 1e-9 * abs(ref["Gbot"]), (got, ref["Gbot"])
+    assert got["err"] <= 1e-13 and got["iter"] <= ref["iter"] + 3
+
+
 def test_emulated_fused_full_lattice_closed_form(emul, O):
     # every bond conducting: G = m / (n - 1) on the square lattice (series / parallel)
     m, n = 272, 67
@@ -132,14 +169,14 @@ def test_emulated_fused_full_lattice_closed_form(emul, O):
     assert abs(got["Gtop"] - m / (n - 1)) < 1e-9 and abs(got["Gbot"] - m / (n - 1)) < 1e-9
 
 
-def run_emul_defl(lib, lat, m, n, w, tol, itmax, Va=1.0, g0=1.0, gleak=1e-12, read_thresh=1e-10, bw=0, bh=0):
+def run_emul_defl(lib, lat, m, n, w, tol, itmax, Va=1.0, g0=1.0, gleak=1e-12, read_thresh=1e-10, bw=0, bh=0, pbc=0):
     Gt, Gb, err = C.c_double(), C.c_double(), C.c_double()
     it, k = C.c_int(), C.c_int()
     w = np.ascontiguousarray(w, np.float64)
     rc = lib.fused_emul_solve_defl(C.c_int(lat), C.c_int(m), C.c_int(n), w.ctypes.data_as(C.POINTER(C.c_double)),
                                    C.c_double(Va), C.c_double(g0), C.c_double(gleak), C.c_double(tol), C.c_int(itmax),
                                    C.c_double(read_thresh), C.byref(Gt), C.byref(Gb), C.byref(it), C.byref(err), C.byref(k),
-                                   C.c_int(bw), C.c_int(bh), None)
+                                   C.c_int(bw), C.c_int(bh), None, C.c_int(pbc))
     assert rc == 0, rc
     return {"Gtop": Gt.value, "Gbot": Gb.value, "iter": it.value, "err": err.value, "coarse": k.value}
 
