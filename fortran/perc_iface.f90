@@ -335,16 +335,15 @@ module perc_iface
     end function
 
     ! per-bond conductances (MATLAB/ConductCalc.m condtype = 2: g0*rand on the conducting bonds): w(nb) in bond-list
-    ! order, used for the bonds that conduct; pass c_null_ptr through perc_clear_bond_conductance to drop them
+    ! order, used for the bonds that conduct; perc_clear_bond_conductance drops them
     integer(c_int32_t) function perc_set_bond_conductance(h, w) bind(C, name="perc_set_bond_conductance")
       import :: c_int32_t, c_int64_t, c_double
       integer(c_int64_t), intent(in) :: h
       real(c_double), intent(in) :: w(*)
     end function
-    integer(c_int32_t) function perc_clear_bond_conductance(h, w) bind(C, name="perc_set_bond_conductance")
-      import :: c_int32_t, c_int64_t, c_ptr
+    integer(c_int32_t) function perc_clear_bond_conductance(h) bind(C, name="perc_clear_bond_conductance")
+      import :: c_int32_t, c_int64_t
       integer(c_int64_t), intent(in) :: h
-      type(c_ptr), value :: w                      ! c_null_ptr
     end function
 
     integer(c_int32_t) function perc_solver_used(h, fused) bind(C, name="perc_solver_used")

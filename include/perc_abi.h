@@ -226,6 +226,7 @@ int32_t perc_write_txt(const int64_t *h, const int32_t *which, const char *path,
  * Jacobi-PCG on four weight planes + the diagonal (112 B per site and iteration on the square lattice, 144 B
  * triangular, against 50 B for the uniform-g0 kernels: csrc/pcg_weighted.cu). */
 int32_t perc_set_bond_conductance(const int64_t *h, const double *w);
+int32_t perc_clear_bond_conductance(const int64_t *h);                     /* = perc_set_bond_conductance(h, NULL) */
 
 /* ---- solver selection --------------------------------------------------------------------------- */
 /* Iteration kernels of the conductance solve (the body of linbcg's loop, Sq/bondc.f:780-833; Jacobi asolve :855-864):

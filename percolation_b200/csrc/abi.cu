@@ -829,6 +829,9 @@ int32_t perc_set_bond_conductance(const int64_t* h, const double* w)
     return rc < 0 ? PERC_E_ARG : rc;
 }
 
+// back to the uniform g0 on every conducting bond (a Fortran caller cannot pass a null array)
+int32_t perc_clear_bond_conductance(const int64_t* h) { return perc_set_bond_conductance(h, nullptr); }
+
 int32_t perc_solver_used(const int64_t* h, int32_t* fused)
 {
     GET_CTX(h);

@@ -30,7 +30,7 @@ SYMBOLS = [
     "perc_conduct", "perc_conduct_warm", "perc_conduct_g", "perc_get_voltage", "perc_launch_count", "perc_phase_ms", "perc_stream", "perc_set_solver", "perc_solver_used",
     "perc_create_slab", "perc_comm_unique_id", "perc_comm_init", "perc_slab_rows", "perc_generate_i8",
     "perc_summary_i8", "perc_span_i8", "perc_get_site_labels_i8", "perc_stitch_host",
-    "perc_batch", "perc_batch_conduct", "perc_comm_init_rank", "perc_allreduce_stats", "perc_set_bond_conductance", "perc_write_txt", "perc_label_incremental",
+    "perc_batch", "perc_batch_conduct", "perc_comm_init_rank", "perc_allreduce_stats", "perc_set_bond_conductance", "perc_clear_bond_conductance", "perc_write_txt", "perc_label_incremental",
 ]
 
 
@@ -304,7 +304,7 @@ class Lattice:
         """per-bond conductances (MATLAB/ConductCalc.m condtype = 2): w[nb] in the reference's bond-row order, used for the
         bonds that conduct; None restores the uniform g0"""
         if w is None:
-            self._call("perc_set_bond_conductance", None)
+            self._call("perc_clear_bond_conductance")
             return
         w = np.ascontiguousarray(w, np.float64)
         assert w.size == self.nb

@@ -28,6 +28,23 @@ def test_exports_every_declared_symbol(P):
         assert hasattr(lib, s), s
 
 
+def test_fortran_interface_binds_every_entry_point():
+    """fortran/perc_iface.f90 (the module a reference driver would `use`) declares one bind(C) interface per entry point of
+    include/perc_abi.h -- except perc_stitch_host, the host-executed stitch that exists for the CPU tests only -- with the
+    header's argument count"""
+    hdr = open(os.path.join(ROOT, "include", "perc_abi.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    f90 = open(os.path.join(ROOT, "fortran", "perc_iface.f90")).read()
+    decl = {nm: args for nm, args in re.findall(r"^int32_t\s+(perc_\w+)\s*\(([^;]*?)\)\s*;", hdr, re.M | re.S)}
+    bound = {nm: args for args, nm in re.findall(r"function\s+perc_\w+\s*\(([^)]*)\)\s*(?:&\s*)?bind\(C,\s*name=\"(perc_\w+)\"\)", f90, re.S)}
+    assert set(decl) - set(bound) == {"perc_stitch_host"}
+    assert not set(bound) - set(decl)
+    for nm, args in bound.items():
+        nc = 0 if decl[nm].strip() in ("", "void") else decl[nm].count(",") + 1
+        nf = len([a for a in re.sub(r"[&\s]", "", args).split(",") if a])
+        assert nc == nf, (nm, nc, nf)
+
+
 GEOMS = [(lat, m, n, pbc) for lat in (1, 2) for (m, n) in ((4, 3), (6, 5), (8, 2), (10, 10), (34, 7), (66, 35))
          for pbc in (0, 1)]
 
