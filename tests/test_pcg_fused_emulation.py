@@ -144,9 +144,10 @@ def test_emulated_deflated_pcg_periodic_wrap(emul, O, lat, kind, m, n, ps, pb, b
     assert got["err"] <= 1e-13 and got["iter"] <= ref["iter"] + 3
 
 
-@pytest.mark.parametrize("lat,m,n,bw,bh", [(1, 768, 70, 2, 1), (2, 512, 130, 2, 2)])
+@pytest.mark.parametrize("lat,m,n,bw,bh", [(1, 768, 70, 2, 1), (2, 512, 130, 2, 2), (2, 256, 70, 2, 1)])
 def test_emulated_deflated_pcg_periodic_wrap_wide_blocks(emul, O, lat, m, n, bw, bh):
-    """periodic wrap with blocks of several tiles: the seam lies between the last and the first block column (3 resp. 2 of them)"""
+    """periodic wrap with blocks of several tiles: the seam lies between the last and the first block column (3 resp. 2 of them);
+    the third shape has ONE block column of two tiles: the tiles wrap, no block border lies on the seam"""
     for seed in range(20):
         case = spanning_case(O, lat, O.MIXED, m, n, 0.85, 0.7, 7100 + m + seed, pbc=1)
         if case is not None:
